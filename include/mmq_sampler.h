@@ -1,0 +1,431 @@
+/* mmq_sampler.h — counter-based RNG and exact samplers shared by the sm_100a
+ * kernels (mmseq_b200/csrc) and by the CPU replay in oracle/.
+ *
+ * Everything in this header is built only from IEEE-754 binary64 add, sub,
+ * mul, div, sqrt, floor and integer/bit operations, so that the SAME source
+ * compiled by nvcc (-fmad=false) and by gcc (-ffp-contract=off) produces
+ * bit-identical results for the same (seed, sweep, id) Philox counter.  No
+ * libm transcendental is used: mmq_log / mmq_exp are fdlibm-style polynomial
+ * kernels written out here.  That is what makes north_star's correctness
+ * part (a) — allocations and counts bit-exact against a CPU replay — possible.
+ *
+ * What is sampled, and which reference call each sampler stands in for
+ * (paths relative to /root/reference):
+ *   mmq_alloc_row    Multinomial(k_i; mu_j/sum mu) for one hit class
+ *                    src/mmseq.cpp:871-889 (gsl_ran_multinomial at :880:
+ *                    a chain of conditional binomials with running
+ *                    norm - sum_p, zero-probability categories skipped)
+ *   mmq_gamma        Gamma(shape, scale 1/rate), Marsaglia-Tsang
+ *                    src/mmseq.cpp:907 and :974 (gsl_ran_gamma)
+ *   mmq_ndtri        inverse standard normal CDF, Wichura AS241 PPND16
+ *                    src/mmseq.cpp:1250, :1286 (gsl_cdf_ugaussian_Pinv)
+ * The DISTRIBUTIONS are those of the reference; the bit streams are not
+ * GSL's MT19937 streams (those depend on the OpenMP thread count in the
+ * reference, src/mmseq.cpp:834-838, so no fixed stream exists to match).
+ */
+#ifndef MMQ_SAMPLER_H
+#define MMQ_SAMPLER_H
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define MMQ_HD __host__ __device__ __forceinline__
+#else
+#define MMQ_HD static inline
+#endif
+
+/* Philox key word 1: which of the path's independent streams a counter is on. */
+#define MMQ_STREAM_ALLOC 0x414c4c4fu /* per hit class, per sweep   */
+#define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
+#define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
+
+/* ------------------------------------------------------------------ bits */
+
+MMQ_HD uint64_t mmq_d2u(double x) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)__double_as_longlong(x);
+#else
+  uint64_t u;
+  memcpy(&u, &x, 8);
+  return u;
+#endif
+}
+
+MMQ_HD double mmq_u2d(uint64_t u) {
+#if defined(__CUDA_ARCH__)
+  return __longlong_as_double((long long)u);
+#else
+  double x;
+  memcpy(&x, &u, 8);
+  return x;
+#endif
+}
+
+MMQ_HD uint32_t mmq_mulhi32(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+/* ---------------------------------------------------------------- Philox */
+
+/* Philox4x32-10 (Salmon et al., SC'11).  ctr and key are updated in place:
+ * on return ctr[0..3] holds the 128 output bits. */
+MMQ_HD void mmq_philox4x32_10(uint32_t ctr[4], uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+  const uint32_t W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = mmq_mulhi32(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = mmq_mulhi32(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  ctr[0] = c0; ctr[1] = c1; ctr[2] = c2; ctr[3] = c3;
+}
+
+/* A stream = (seed, stream tag) key and (id_lo, id_hi, sweep, block) counter.
+ * Each block yields two 52-bit uniforms; `block` counts upwards from 0, so a
+ * draw is a pure function of (seed, stream, id, sweep, how many uniforms the
+ * same (id, sweep) consumed before it). */
+typedef struct {
+  uint32_t seed, stream;
+  uint32_t id_lo, id_hi, sweep, block;
+  uint32_t w[4];
+  int left; /* uniforms left in w: 0, 1 or 2 */
+} mmq_rng;
+
+MMQ_HD void mmq_rng_init(mmq_rng* g, uint32_t seed, uint32_t stream, uint64_t id, uint32_t sweep) {
+  g->seed = seed; g->stream = stream;
+  g->id_lo = (uint32_t)id; g->id_hi = (uint32_t)(id >> 32);
+  g->sweep = sweep; g->block = 0; g->left = 0;
+  g->w[0] = g->w[1] = g->w[2] = g->w[3] = 0;
+}
+
+/* Uniform on the open interval (0,1): (j + 1/2) * 2^-52, j a 52-bit integer.
+ * Never 0 and never 1, exactly representable, identical on host and device. */
+MMQ_HD double mmq_uniform(mmq_rng* g) {
+  if (g->left == 0) {
+    g->w[0] = g->id_lo; g->w[1] = g->id_hi; g->w[2] = g->sweep; g->w[3] = g->block;
+    mmq_philox4x32_10(g->w, g->seed, g->stream);
+    g->block += 1;
+    g->left = 2;
+  }
+  uint32_t hi, lo;
+  if (g->left == 2) { hi = g->w[0]; lo = g->w[1]; } else { hi = g->w[2]; lo = g->w[3]; }
+  g->left -= 1;
+  uint64_t j = (((uint64_t)hi << 32) | (uint64_t)lo) >> 12;
+  return ((double)j + 0.5) * 2.220446049250313080847263336181640625e-16; /* 2^-52 */
+}
+
+/* ------------------------------------------------------- log / exp kernels */
+
+/* Natural logarithm, fdlibm e_log.c scheme: x = 2^k (1+f), sqrt(1/2) < 1+f <
+ * sqrt(2); s = f/(2+f); log(1+f) = f - hfsq + s (hfsq + R(s^2)).  < 1 ulp.
+ * Domain here: x > 0 finite (callers never pass 0, negatives or NaN, but the
+ * edge values are still mapped the IEEE way). */
+MMQ_HD double mmq_log(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+  const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01,
+               Lg3 = 2.857142874366239149e-01, Lg4 = 2.222219843214978396e-01,
+               Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
+               Lg7 = 1.479819860511658591e-01;
+  uint64_t u = mmq_d2u(x);
+  int k = 0;
+  if (x != x) return x;
+  if ((u >> 63) != 0 && x != 0.0) return mmq_u2d(0x7ff8000000000000ull); /* log(<0) = nan */
+  if (x == 0.0) return mmq_u2d(0xfff0000000000000ull);                    /* -inf */
+  if ((u >> 52) == 0x7ffull) return x;                                    /* +inf */
+  if ((u >> 52) == 0) { /* subnormal: scale up by 2^54 */
+    x = x * 18014398509481984.0;
+    u = mmq_d2u(x);
+    k = -54;
+  }
+  uint32_t hx = (uint32_t)(u >> 32);
+  /* normalise so that the mantissa lies in [sqrt(2)/2, sqrt(2)) */
+  hx += 0x3ff00000u - 0x3fe6a09eu;
+  k += (int)(hx >> 20) - 0x3ff;
+  hx = (hx & 0x000fffffu) + 0x3fe6a09eu;
+  u = ((uint64_t)hx << 32) | (u & 0xffffffffull);
+  double f = mmq_u2d(u) - 1.0;
+  double hfsq = 0.5 * f * f;
+  double s = f / (2.0 + f);
+  double z = s * s;
+  double w = z * z;
+  double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
+  double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  double R = t2 + t1;
+  double dk = (double)k;
+  return s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+}
+
+/* log(1+x) for |x| < 1 through log(): log(u) * x / (u - 1), u = 1 + x
+ * (the rounding error of u cancels between log(u) and u - 1). */
+MMQ_HD double mmq_log1p(double x) {
+  double u = 1.0 + x;
+  if (u == 1.0) return x;
+  return mmq_log(u) * x / (u - 1.0);
+}
+
+/* 2^k as a double for -1022 <= k <= 1023 */
+MMQ_HD double mmq_pow2i(int k) { return mmq_u2d((uint64_t)(k + 1023) << 52); }
+
+/* exp(x), fdlibm e_exp.c scheme: x = k ln2 + r, |r| <= ln2/2;
+ * exp(r) = 1 + r + r c/(2 - c), c = r - r^2 P(r^2).  < 1 ulp. */
+MMQ_HD double mmq_exp(double x) {
+  const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10;
+  const double invln2 = 1.44269504088896338700e+00;
+  const double P1 = 1.66666666666666019037e-01, P2 = -2.77777777770155933842e-03,
+               P3 = 6.61375632143793436117e-05, P4 = -1.65339022054652515390e-06,
+               P5 = 4.13813679705723846039e-08;
+  if (x != x) return x;
+  if (x > 709.782712893383973096) return mmq_u2d(0x7ff0000000000000ull);
+  if (x < -745.13321910194110842) return 0.0;
+  double fk = floor(invln2 * x + 0.5);
+  int k = (int)fk;
+  double hi = x - fk * ln2_hi;
+  double lo = fk * ln2_lo;
+  double r = hi - lo;
+  double t = r * r;
+  double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
+  if (k >= -1021 && k <= 1023) return y * mmq_pow2i(k);
+  if (k > 1023) return y * mmq_pow2i(1023) * mmq_pow2i(k - 1023);
+  return y * mmq_pow2i(k + 1000) * mmq_pow2i(-1000); /* gradual underflow */
+}
+
+/* ------------------------------------------------------------- normal */
+
+/* Inverse of the standard normal CDF, Wichura's AS241 PPND16 (relative
+ * accuracy about 1e-16).  GSL's gsl_cdf_ugaussian_Pinv (cdf/gaussinv.c) is an
+ * implementation of the same algorithm; the reference calls it at
+ * src/mmseq.cpp:1250 and :1286. */
+MMQ_HD double mmq_ndtri(double p) {
+  double q = p - 0.5, r, val;
+  if (q >= -0.425 && q <= 0.425) {
+    r = 0.180625 - q * q;
+    val = q * (((((((2.5090809287301226727e+3 * r + 3.3430575583588128105e+4) * r +
+                    6.7265770927008700853e+4) * r + 4.5921953931549871457e+4) * r +
+                  1.3731693765509461125e+4) * r + 1.9715909503065514427e+3) * r +
+                1.3314166789178437745e+2) * r + 3.3871328727963666080e0) /
+          (((((((5.2264952788528545610e+3 * r + 2.8729085735721942674e+4) * r +
+                3.9307895800092710610e+4) * r + 2.1213794301586595867e+4) * r +
+              5.3941960214247511077e+3) * r + 6.8718700749205790830e+2) * r +
+            4.2313330701600911252e+1) * r + 1.0);
+    return val;
+  }
+  r = (q < 0.0) ? p : 1.0 - p;
+  if (r <= 0.0) return (q < 0.0) ? mmq_u2d(0xfff0000000000000ull) : mmq_u2d(0x7ff0000000000000ull);
+  r = sqrt(-mmq_log(r));
+  if (r <= 5.0) {
+    r -= 1.6;
+    val = (((((((7.74545014278341407640e-4 * r + 2.27238449892691845833e-2) * r +
+                2.41780725177450611770e-1) * r + 1.27045825245236838258e0) * r +
+              3.64784832476320460504e0) * r + 5.76949722146069140550e0) * r +
+            4.63033784615654529590e0) * r + 1.42343711074968357734e0) /
+          (((((((1.05075007164441684324e-9 * r + 5.47593808499534494600e-4) * r +
+                1.51986665636164571966e-2) * r + 1.48103976427480074590e-1) * r +
+              6.89767334985100004550e-1) * r + 1.67638483018380384940e0) * r +
+            2.05319162663775882187e0) * r + 1.0);
+  } else {
+    r -= 5.0;
+    val = (((((((2.01033439929228813265e-7 * r + 2.71155556874348757815e-5) * r +
+                1.24266094738807843860e-3) * r + 2.65321895265761230930e-2) * r +
+              2.96560571828504891230e-1) * r + 1.78482653991729133580e0) * r +
+            5.46378491116411436990e0) * r + 6.65790464350110377720e0) /
+          (((((((2.04426310338993978564e-15 * r + 1.42151175831644588870e-7) * r +
+                1.84631831751005468180e-5) * r + 7.86869131145613259100e-4) * r +
+              1.48753612908506148525e-2) * r + 1.36929880922735805310e-1) * r +
+            5.99832206555887937690e-1) * r + 1.0);
+  }
+  return (q < 0.0) ? -val : val;
+}
+
+/* Standard normal variate by inversion of one 52-bit uniform. */
+MMQ_HD double mmq_normal(mmq_rng* g) { return mmq_ndtri(mmq_uniform(g)); }
+
+/* -------------------------------------------------------------- gamma */
+
+/* Gamma(shape a > 0, rate b > 0): Marsaglia & Tsang (2000), with the
+ * Gamma(a+1) * U^(1/a) boost for a < 1 — the algorithm of gsl_ran_gamma, which
+ * the reference calls as gsl_ran_gamma(rg, alpha + Xcolsum[t], 1/(beta+l[t]))
+ * at src/mmseq.cpp:907. */
+MMQ_HD double mmq_gamma(mmq_rng* g, double a, double rate) {
+  double boost = 1.0;
+  if (a < 1.0) {
+    double u = mmq_uniform(g);
+    boost = mmq_exp(mmq_log(u) / a);
+    a += 1.0;
+  }
+  const double d = a - 1.0 / 3.0;
+  const double c = (1.0 / 3.0) / sqrt(d);
+  double v;
+  for (;;) {
+    double x;
+    do {
+      x = mmq_normal(g);
+      v = 1.0 + c * x;
+    } while (v <= 0.0);
+    v = v * v * v;
+    double u = mmq_uniform(g);
+    double x2 = x * x;
+    if (u < 1.0 - 0.0331 * x2 * x2) break;
+    if (mmq_log(u) < 0.5 * x2 + d * (1.0 - v + mmq_log(v))) break;
+  }
+  return boost * d * v / rate;
+}
+
+/* ------------------------------------------------------------ binomial */
+
+/* log(k!) - [ (k+1/2) log(k+1) - (k+1) + log(2 pi)/2 ] */
+MMQ_HD double mmq_stirling_tail(double k) {
+  if (k <= 9.0) {
+    switch ((int)k) {
+      case 0: return 0.08106146679532726;
+      case 1: return 0.04134069595540929;
+      case 2: return 0.02767792568499834;
+      case 3: return 0.02079067210376509;
+      case 4: return 0.01664469118982119;
+      case 5: return 0.01387612882307075;
+      case 6: return 0.01189670994589177;
+      case 7: return 0.01041126526197209;
+      case 8: return 0.009255462182712733;
+      default: return 0.008330563433362871;
+    }
+  }
+  double kp1 = k + 1.0;
+  double kp1sq = kp1 * kp1;
+  return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / kp1;
+}
+
+/* Binomial(n, p) for 0 <= p <= 1/2.
+ *   n*p <  10 : sequential inversion (BINV, Kachitvichyanukul & Schmeiser 1988)
+ *   n*p >= 10 : transformed rejection BTRS (Hoermann 1993)
+ * Both are exact samplers; GSL's gsl_ran_binomial (BTPE + inversion) samples
+ * the same distribution. */
+MMQ_HD int64_t mmq_binomial_half(mmq_rng* g, int64_t n, double p) {
+  const double dn = (double)n;
+  if (dn * p < 10.0) {
+    const double q = 1.0 - p;
+    const double s = p / q;
+    const double a = (dn + 1.0) * s;
+    const double r0 = mmq_exp(dn * mmq_log1p(-p));
+    for (;;) {
+      double r = r0;
+      double u = mmq_uniform(g);
+      int64_t x = 0;
+      while (u > r) {
+        u -= r;
+        x += 1;
+        if (x > n) break;
+        r *= (a / (double)x - s);
+      }
+      if (x <= n) return x;
+    }
+  }
+  const double q = 1.0 - p;
+  const double spq = sqrt(dn * p * q);
+  const double b = 1.15 + 2.53 * spq;
+  const double a = -0.0873 + 0.0248 * b + 0.01 * p;
+  const double c = dn * p + 0.5;
+  const double vr = 0.92 - 4.2 / b;
+  const double r = p / q;
+  const double alpha = (2.83 + 5.1 / b) * spq;
+  const double m = floor((dn + 1.0) * p);
+  for (;;) {
+    double u = mmq_uniform(g) - 0.5;
+    double v = mmq_uniform(g);
+    double us = 0.5 - fabs(u);
+    double kk = floor((2.0 * a / us + b) * u + c);
+    if (kk < 0.0 || kk > dn) continue;
+    if (us >= 0.07 && v <= vr) return (int64_t)kk;
+    double lv = mmq_log(v * alpha / (a / (us * us) + b));
+    double ub = (m + 0.5) * mmq_log((m + 1.0) / (r * (dn - m + 1.0))) +
+                (dn + 1.0) * mmq_log((dn - m + 1.0) / (dn - kk + 1.0)) +
+                (kk + 0.5) * mmq_log(r * (dn - kk + 1.0) / (kk + 1.0)) +
+                mmq_stirling_tail(m) + mmq_stirling_tail(dn - m) -
+                mmq_stirling_tail(kk) - mmq_stirling_tail(dn - kk);
+    if (lv <= ub) return (int64_t)kk;
+  }
+}
+
+/* Binomial(n, p), any p in [0,1]. */
+MMQ_HD int64_t mmq_binomial(mmq_rng* g, int64_t n, double p) {
+  if (n <= 0 || !(p > 0.0)) return 0;
+  if (p >= 1.0) return n;
+  if (n == 1) return (mmq_uniform(g) < p) ? 1 : 0;
+  if (p > 0.5) return n - mmq_binomial_half(g, n, 1.0 - p);
+  return mmq_binomial_half(g, n, p);
+}
+
+/* ---------------------------------------------------- one hit class */
+
+/* Allocate the k fragments of one hit class among its d member transcripts.
+ *   p[j]  unnormalised probability of member j (mu[col_j], times the per-hit
+ *         weight when weights are present); read twice, never written
+ *   x[j]  out: number of fragments given to member j; sum_j x[j] == k
+ * d == 1 consumes no random numbers (x = k).  k == 1 is one categorical draw
+ * (one uniform).  k > 1 is gsl_ran_multinomial's chain of conditional
+ * binomials x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)).
+ * The arithmetic order (left-to-right sums) is part of the contract: the CPU
+ * replay and every kernel variant walk the row in the same order. */
+template <typename PIt, typename XIt>
+MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_t class_id,
+                          uint32_t sweep) {
+  if (d <= 0) return;
+  if (d == 1) { x[0] = (int32_t)k; return; }
+  double norm = 0.0;
+  int last_pos = d - 1; /* last member with p > 0 (d-1 if none) */
+  {
+    int lp = -1;
+    for (int j = 0; j < d; ++j) {
+      const double pj = p[j];
+      norm += pj;
+      if (pj > 0.0) lp = j;
+    }
+    if (lp >= 0) last_pos = lp;
+  }
+  mmq_rng g;
+  mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, class_id, sweep);
+  if (k == 1) {
+    const double target = mmq_uniform(&g) * norm;
+    double acc = 0.0;
+    int chosen = -1;
+    for (int j = 0; j < d; ++j) {
+      acc += p[j];
+      x[j] = 0;
+      if (chosen < 0 && target < acc) chosen = j;
+    }
+    if (chosen < 0) chosen = last_pos; /* rounding at the top end, or norm == 0 */
+    x[chosen] = 1;
+    return;
+  }
+  int64_t rem = k;
+  double sum_p = 0.0;
+  for (int j = 0; j < d; ++j) {
+    int64_t xj = 0;
+    const double pj = p[j];
+    if (j == last_pos) {
+      xj = rem; /* zero-probability members never receive fragments */
+    } else if (rem > 0 && pj > 0.0) {
+      const double denom = norm - sum_p;
+      double pr = (denom > 0.0) ? pj / denom : 1.0;
+      if (pr > 1.0) pr = 1.0;
+      xj = mmq_binomial(&g, rem, pr);
+    }
+    x[j] = (int32_t)xj;
+    rem -= xj;
+    sum_p += pj;
+  }
+}
+
+#endif /* MMQ_SAMPLER_H */

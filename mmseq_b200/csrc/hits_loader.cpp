@@ -1,0 +1,592 @@
+/* hits_loader.cpp — see hits_loader.h.  Format facts follow the reference's
+ * writer/reader pair: src/hitsio.cpp:162-240 (writer), :250-447 (reader),
+ * README.md:388-403. */
+#include "hits_loader.h"
+
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <sstream>
+#include <unordered_map>
+
+namespace mmq {
+
+namespace {
+
+/* Buffered byte stream over a file, transparently zlib-inflated when the file
+ * starts with 0x78 (src/hitsio.cpp:258: "lazy but sufficient" detection). */
+class ByteSource {
+ public:
+  ~ByteSource() { close(); }
+  bool open(const std::string& path) {
+    f_ = fopen(path.c_str(), "rb");
+    if (!f_) return false;
+    int c = fgetc(f_);
+    if (c == EOF) { compressed_ = false; }
+    else { ungetc(c, f_); compressed_ = (c == 0x78); }
+    if (compressed_) {
+      memset(&zs_, 0, sizeof zs_);
+      if (inflateInit(&zs_) != Z_OK) return false;
+      zinit_ = true;
+      in_.resize(1 << 20);
+    }
+    buf_.resize(1 << 20);
+    pos_ = len_ = 0;
+    hit_eof_ = false;
+    return true;
+  }
+  void close() {
+    if (zinit_) { inflateEnd(&zs_); zinit_ = false; }
+    if (f_) { fclose(f_); f_ = nullptr; }
+  }
+  bool corrupt() const { return corrupt_; }
+  int peek() {
+    if (pos_ == len_ && !fill()) return EOF;
+    return (unsigned char)buf_[pos_];
+  }
+  int get() {
+    if (pos_ == len_ && !fill()) return EOF;
+    return (unsigned char)buf_[pos_++];
+  }
+  /* like std::getline: false only when nothing at all could be read */
+  bool getline(std::string& out) {
+    out.clear();
+    bool any = false;
+    for (;;) {
+      if (pos_ == len_ && !fill()) return any;
+      any = true;
+      const char* b = buf_.data() + pos_;
+      const char* nl = (const char*)memchr(b, '\n', len_ - pos_);
+      if (nl) {
+        out.append(b, (size_t)(nl - b));
+        pos_ += (size_t)(nl - b) + 1;
+        return true;
+      }
+      out.append(b, len_ - pos_);
+      pos_ = len_;
+    }
+  }
+  bool read_bytes(void* dst, size_t n) {
+    char* d = (char*)dst;
+    while (n) {
+      if (pos_ == len_ && !fill()) return false;
+      size_t c = std::min(n, len_ - pos_);
+      memcpy(d, buf_.data() + pos_, c);
+      pos_ += c; d += c; n -= c;
+    }
+    return true;
+  }
+  bool read_u32(uint32_t& v) { return read_bytes(&v, 4); } /* raw little-endian, src/hitsio.cpp:22-34 */
+  /* one byte, or 0xFF followed by a uint32 (src/hitsio.cpp:36-55) */
+  bool read_small(uint32_t& v) {
+    int c = get();
+    if (c == EOF) return false;
+    if (c == 255) return read_u32(v);
+    v = (uint32_t)c;
+    return true;
+  }
+
+ private:
+  bool fill() {
+    if (hit_eof_) return false;
+    pos_ = len_ = 0;
+    if (!compressed_) {
+      len_ = fread(buf_.data(), 1, buf_.size(), f_);
+      if (len_ == 0) { hit_eof_ = true; return false; }
+      return true;
+    }
+    while (len_ == 0) {
+      if (zs_.avail_in == 0) {
+        size_t got = fread(in_.data(), 1, in_.size(), f_);
+        if (got == 0) { hit_eof_ = true; return false; }
+        zs_.next_in = (Bytef*)in_.data();
+        zs_.avail_in = (uInt)got;
+      }
+      zs_.next_out = (Bytef*)buf_.data();
+      zs_.avail_out = (uInt)buf_.size();
+      int rc = inflate(&zs_, Z_NO_FLUSH);
+      len_ = buf_.size() - zs_.avail_out;
+      if (rc == Z_STREAM_END) { if (len_ == 0) { hit_eof_ = true; return false; } hit_eof_ = (zs_.avail_in == 0); zend_ = true; return true; }
+      if (rc != Z_OK && rc != Z_BUF_ERROR) { corrupt_ = true; hit_eof_ = true; return len_ > 0; }
+    }
+    return true;
+  }
+  FILE* f_ = nullptr;
+  bool compressed_ = false, zinit_ = false, hit_eof_ = false, corrupt_ = false, zend_ = false;
+  z_stream zs_;
+  std::vector<char> buf_, in_;
+  size_t pos_ = 0, len_ = 0;
+};
+
+inline uint64_t mix64(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+  return x;
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------ class builder */
+
+struct ClassBuilder::Impl {
+  int layout;
+  bool weighted;
+  int64_t N = 0;
+  std::vector<int32_t> hdr2col, col2hdr, doublehits;
+  /* distinct classes in first-appearance order */
+  std::vector<int64_t> cls_ptr{0};
+  std::vector<int32_t> cls_col;
+  std::vector<int32_t> cls_k;
+  /* open-addressing table of class ids keyed by the sorted column set */
+  std::vector<int32_t> table;
+  std::vector<uint64_t> cls_hash;
+  /* per-fragment layouts: class of each record and (weighted) the weights in class column order */
+  std::vector<int32_t> rec_class;
+  std::vector<float> rec_w;
+  std::vector<int64_t> rec_wptr{0};
+  std::vector<std::pair<int32_t, float>> comb;
+
+  void grow_table() {
+    size_t nsz = table.empty() ? (size_t)1 << 16 : table.size() * 2;
+    std::vector<int32_t> nt(nsz, -1);
+    for (size_t c = 0; c < cls_hash.size(); ++c) {
+      size_t s = (size_t)cls_hash[c] & (nsz - 1);
+      while (nt[s] >= 0) s = (s + 1) & (nsz - 1);
+      nt[s] = (int32_t)c;
+    }
+    table.swap(nt);
+  }
+};
+
+ClassBuilder::ClassBuilder(int64_t T, int layout, bool weighted) : p_(new Impl()) {
+  p_->layout = layout & 15;
+  p_->weighted = weighted;
+  p_->hdr2col.assign((size_t)T, -1);
+  if (layout & LAYOUT_IDENTITY_COLUMNS) {
+    p_->col2hdr.resize((size_t)T);
+    p_->doublehits.assign((size_t)T, 0);
+    for (int64_t t = 0; t < T; ++t) { p_->hdr2col[(size_t)t] = (int32_t)t; p_->col2hdr[(size_t)t] = (int32_t)t; }
+  }
+  p_->grow_table();
+}
+ClassBuilder::~ClassBuilder() { delete p_; }
+
+void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
+  Impl& P = *p_;
+  P.N++;
+  auto& comb = P.comb;
+  comb.clear();
+  for (int j = 0; j < cnt; ++j) {
+    const int32_t h = tids[j];
+    int32_t c = P.hdr2col[(size_t)h];
+    if (c < 0) { /* first appearance: new column (src/mmseq.cpp:403) */
+      c = (int32_t)P.col2hdr.size();
+      P.hdr2col[(size_t)h] = c;
+      P.col2hdr.push_back(h);
+      P.doublehits.push_back(0);
+    }
+    bool dup = false;
+    for (auto& e : comb)
+      if (e.first == c) { dup = true; if (w) e.second += w[j]; break; }
+    if (dup) P.doublehits[(size_t)c]++; /* :404-409 */
+    else comb.emplace_back(c, w ? w[j] : 1.0f);
+  }
+  if (comb.empty()) return; /* a record without hits adds to N only */
+  std::sort(comb.begin(), comb.end(), [](const std::pair<int32_t, float>& a, const std::pair<int32_t, float>& b) { return a.first < b.first; });
+  uint64_t hsh = 0x9e3779b97f4a7c15ull ^ (uint64_t)comb.size();
+  for (auto& e : comb) hsh = mix64(hsh ^ (uint64_t)(uint32_t)e.first) + 0x632be59bd9b4e019ull;
+  size_t mask = P.table.size() - 1;
+  size_t s = (size_t)hsh & mask;
+  int32_t cid = -1;
+  for (;;) {
+    const int32_t c = P.table[s];
+    if (c < 0) break;
+    if (P.cls_hash[(size_t)c] == hsh) {
+      const int64_t b = P.cls_ptr[(size_t)c], e = P.cls_ptr[(size_t)c + 1];
+      if (e - b == (int64_t)comb.size()) {
+        bool same = true;
+        for (size_t j = 0; j < comb.size(); ++j)
+          if (P.cls_col[(size_t)b + j] != comb[j].first) { same = false; break; }
+        if (same) { cid = c; break; }
+      }
+    }
+    s = (s + 1) & mask;
+  }
+  if (cid < 0) { /* new class, index = order of first appearance (:417-418) */
+    cid = (int32_t)P.cls_hash.size();
+    for (auto& e : comb) P.cls_col.push_back(e.first);
+    P.cls_ptr.push_back((int64_t)P.cls_col.size());
+    P.cls_k.push_back(0);
+    P.cls_hash.push_back(hsh);
+    P.table[s] = cid;
+    if (P.cls_hash.size() * 2 > P.table.size()) P.grow_table();
+  }
+  P.cls_k[(size_t)cid]++; /* :440 */
+  if (P.layout != LAYOUT_COLLAPSED) {
+    P.rec_class.push_back(cid);
+    if (P.weighted) {
+      for (auto& e : comb) P.rec_w.push_back(e.second);
+      P.rec_wptr.push_back((int64_t)P.rec_w.size());
+    }
+  }
+}
+
+void ClassBuilder::finish(HitClasses& out) {
+  Impl& P = *p_;
+  out.layout = P.layout;
+  out.N = P.N;
+  out.n = (int64_t)P.col2hdr.size();
+  out.n_classes = (int64_t)P.cls_hash.size();
+  out.col2hdr = P.col2hdr;
+  out.hdr2col = P.hdr2col;
+  out.doublehits = P.doublehits;
+  out.w.clear();
+  if (P.layout == LAYOUT_COLLAPSED) {
+    out.m = out.n_classes;
+    out.row_ptr.swap(P.cls_ptr);
+    out.col.swap(P.cls_col);
+    out.k.swap(P.cls_k);
+    return;
+  }
+  const int64_t R = (int64_t)P.rec_class.size();
+  std::vector<int64_t> order((size_t)R);
+  if (P.layout == LAYOUT_PER_FRAGMENT_SORTED) { /* stable counting sort of records by class */
+    std::vector<int64_t> start((size_t)out.n_classes + 1, 0);
+    for (int64_t r = 0; r < R; ++r) start[(size_t)P.rec_class[(size_t)r] + 1]++;
+    for (int64_t c = 0; c < out.n_classes; ++c) start[(size_t)c + 1] += start[(size_t)c];
+    for (int64_t r = 0; r < R; ++r) order[(size_t)start[(size_t)P.rec_class[(size_t)r]]++] = r;
+  } else {
+    for (int64_t r = 0; r < R; ++r) order[(size_t)r] = r;
+  }
+  out.m = R;
+  out.k.clear();
+  out.row_ptr.assign((size_t)R + 1, 0);
+  int64_t total = 0;
+  for (int64_t i = 0; i < R; ++i) {
+    const int32_t c = P.rec_class[(size_t)order[(size_t)i]];
+    total += P.cls_ptr[(size_t)c + 1] - P.cls_ptr[(size_t)c];
+    out.row_ptr[(size_t)i + 1] = total;
+  }
+  out.col.resize((size_t)total);
+  if (P.weighted) out.w.resize((size_t)total);
+  for (int64_t i = 0; i < R; ++i) {
+    const int64_t r = order[(size_t)i];
+    const int32_t c = P.rec_class[(size_t)r];
+    const int64_t b = P.cls_ptr[(size_t)c], d = P.cls_ptr[(size_t)c + 1] - b;
+    std::memcpy(out.col.data() + out.row_ptr[(size_t)i], P.cls_col.data() + b, sizeof(int32_t) * (size_t)d);
+    if (P.weighted) std::memcpy(out.w.data() + out.row_ptr[(size_t)i], P.rec_w.data() + P.rec_wptr[(size_t)r], sizeof(float) * (size_t)d);
+  }
+}
+
+/* ------------------------------------------------------------------ header */
+
+int validate_header(const HitsHeader& hdr, std::string& err) {
+  /* src/mmseq.cpp:342-379 */
+  const size_t T = hdr.names.size();
+  {
+    std::vector<std::string> s = hdr.names;
+    std::sort(s.begin(), s.end());
+    if (std::unique(s.begin(), s.end()) != s.end()) { err = "Error: duplicate transcripts in @TranscriptMetaData entries."; return 1; }
+  }
+  std::vector<int> seen(T, 0);
+  for (size_t g = 0; g < hdr.gene_members.size(); ++g)
+    for (int32_t h : hdr.gene_members[g]) {
+      if (seen[(size_t)h]) { err = "Error: transcripts must be nested within genes in GeneIsoforms metadata."; return 1; }
+      seen[(size_t)h] = 1;
+    }
+  for (size_t t = 0; t < T; ++t)
+    if (!seen[t]) { err = "Error: " + hdr.names[t] + " does not belong to a gene in the @GeneIsoforms header entries."; return 1; }
+  return 0;
+}
+
+namespace {
+
+struct NameIndex {
+  std::unordered_map<std::string, int32_t> map;
+  int32_t find(const std::string& s) const {
+    auto it = map.find(s);
+    return it == map.end() ? -1 : it->second;
+  }
+};
+
+int finish_header(HitsHeader& hdr, const std::vector<std::pair<std::string, std::vector<std::string>>>& genes_raw,
+                  const std::vector<std::vector<std::string>>& ident_raw, NameIndex& idx, std::string& err) {
+  for (size_t t = 0; t < hdr.names.size(); ++t) idx.map.emplace(hdr.names[t], (int32_t)t); /* first wins, as map::insert */
+  std::map<std::string, std::vector<std::string>> gmap; /* std::map: byte-wise order, insert keeps the first */
+  for (auto& g : genes_raw) gmap.insert(g);
+  hdr.gene_of.assign(hdr.names.size(), -1);
+  for (auto& g : gmap) {
+    std::vector<int32_t> mem;
+    for (auto& nm : g.second) {
+      int32_t h = idx.find(nm);
+      if (h < 0) { err = "Error: transcript '" + nm + "' of gene '" + g.first + "' has no @TranscriptMetaData entry."; return 1; }
+      mem.push_back(h);
+      if (hdr.gene_of[(size_t)h] < 0) hdr.gene_of[(size_t)h] = (int32_t)hdr.gene_names.size();
+    }
+    hdr.gene_names.push_back(g.first);
+    hdr.gene_members.push_back(mem);
+  }
+  for (auto& s : ident_raw) {
+    std::vector<int32_t> mem;
+    for (auto& nm : s) {
+      int32_t h = idx.find(nm);
+      if (h < 0) { err = "Error: transcript '" + nm + "' in @IdenticalTranscripts has no @TranscriptMetaData entry."; return 1; }
+      mem.push_back(h);
+    }
+    hdr.identical.push_back(mem);
+  }
+  return validate_header(hdr, err);
+}
+
+double parse_double_like_istream(const std::string& s) { /* string_to_double, src/hitsio.cpp:14-20 */
+  std::istringstream i(s);
+  double x;
+  if (!(i >> x)) return 0;
+  return x;
+}
+
+}  // namespace
+
+int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClasses& cls, std::string& err) {
+  ByteSource src;
+  if (!src.open(path)) { err = "Error reading hits file \"" + path + "\"."; return 1; }
+  hdr = HitsHeader();
+  std::vector<std::pair<std::string, std::vector<std::string>>> genes_raw;
+  std::vector<std::vector<std::string>> ident_raw;
+  NameIndex idx;
+  std::string line;
+  /* schema detection on the first line, src/hitsio.cpp:261-275 */
+  if (!src.getline(line)) { err = "Input file \"" + path + "\" does not seem to be a hits file."; return 1; }
+  {
+    std::istringstream tok(line);
+    std::string t1;
+    tok >> t1;
+    if (t1 == "@TranscriptMetaData") hdr.schema = 0;
+    else if (line == "MMSEQ_HITSFILE") {
+      uint32_t s = 99;
+      if (!src.read_u32(s) || s != 1) { err = "Input file \"" + path + "\" does not seem to be a hits file."; return 1; }
+      hdr.schema = 1;
+    } else { err = "Input file \"" + path + "\" does not seem to be a hits file."; return 1; }
+  }
+  if (hdr.schema == 0) {
+    /* text header, src/hitsio.cpp:286-329; `line` already holds the first header line */
+    bool have_line = true;
+    for (;;) {
+      if (!have_line) {
+        int c = src.peek();
+        if (c == EOF || c == '>') break;
+        if (!src.getline(line)) break;
+      }
+      have_line = false;
+      std::istringstream tok(line);
+      std::string t1;
+      tok >> t1;
+      if (t1 == "@TranscriptMetaData") {
+        std::string nm; double el = 0; int tl = 0;
+        tok >> nm >> el >> tl;
+        hdr.names.push_back(nm);
+        hdr.efflen.push_back(el);
+        hdr.truelen.push_back(tl);
+      } else if (t1 == "@GeneIsoforms") {
+        std::string gid, tid;
+        std::vector<std::string> mem;
+        tok >> gid;
+        while (tok >> tid) mem.push_back(tid);
+        genes_raw.emplace_back(gid, mem);
+      } else if (t1 == "@IdenticalTranscripts") {
+        std::string tid;
+        std::vector<std::string> mem;
+        while (tok >> tid) mem.push_back(tid);
+        ident_raw.push_back(mem);
+      } else { err = "Hits file looks malformed."; return 1; }
+    }
+  } else {
+    /* binary header, src/hitsio.cpp:349-398 */
+    uint32_t T = 0;
+    if (!src.read_u32(T)) { err = "Hits file looks malformed."; return 1; }
+    for (uint32_t i = 0; i < T; ++i) {
+      std::string nm, el; uint32_t tl = 0;
+      if (!src.getline(nm) || !src.getline(el) || !src.read_u32(tl)) { err = "Hits file looks malformed."; return 1; }
+      hdr.names.push_back(nm);
+      hdr.efflen.push_back(parse_double_like_istream(el));
+      hdr.truelen.push_back((int32_t)tl);
+    }
+    uint32_t G = 0;
+    if (!src.read_u32(G)) { err = "Hits file looks malformed."; return 1; }
+    for (uint32_t g = 0; g < G; ++g) {
+      std::string gid; uint32_t c = 0;
+      if (!src.getline(gid) || !src.read_u32(c)) { err = "Hits file looks malformed."; return 1; }
+      std::vector<std::string> mem;
+      for (uint32_t j = 0; j < c; ++j) { std::string nm; if (!src.getline(nm)) { err = "Hits file looks malformed."; return 1; } mem.push_back(nm); }
+      genes_raw.emplace_back(gid, mem);
+    }
+    uint32_t I = 0;
+    if (!src.read_u32(I)) { err = "Hits file looks malformed."; return 1; }
+    for (uint32_t s = 0; s < I; ++s) {
+      uint32_t c = 0;
+      if (!src.read_u32(c)) { err = "Hits file looks malformed."; return 1; }
+      std::vector<std::string> mem;
+      for (uint32_t j = 0; j < c; ++j) { std::string nm; if (!src.getline(nm)) { err = "Hits file looks malformed."; return 1; } mem.push_back(nm); }
+      ident_raw.push_back(mem);
+    }
+  }
+  /* the binary header may repeat a name: the reference's maps keep the first entry but
+   * headerTranscriptName keeps every slot, so record indices address the full list */
+  std::vector<std::string> all_names = hdr.names;
+  if (finish_header(hdr, genes_raw, ident_raw, idx, err)) return 1;
+  const int64_t T = (int64_t)hdr.names.size();
+  ClassBuilder cb(T, layout, false);
+  std::vector<int32_t> tids;
+  if (hdr.schema == 0) {
+    /* records, src/hitsio.cpp:331-347 */
+    for (;;) {
+      if (src.peek() == EOF) break;
+      if (!src.getline(line)) break;
+      if (line.empty() || line[0] != '>') { err = "Hits file looks malformed."; return 1; }
+      if (src.peek() == EOF) {
+        fprintf(stderr, "Warning: read record without any mapping transcripts found at the end of the hits file. The hits file may be corrupted.\n");
+        break;
+      }
+      tids.clear();
+      while (src.peek() != EOF && src.peek() != '>') {
+        if (!src.getline(line)) break;
+        int32_t h = idx.find(line);
+        if (h < 0) { err = "Error: transcript '" + line + "' has no length."; return 1; } /* src/mmseq.cpp:599-601 */
+        tids.push_back(h);
+      }
+      cb.add_record(tids.data(), nullptr, (int)tids.size());
+    }
+  } else {
+    /* records, src/hitsio.cpp:413-439; read names are delta-coded (:101-115) and unused here */
+    std::string mid;
+    for (;;) {
+      if (!src.getline(line)) break;
+      if (line.empty()) {
+        uint32_t nb = 0, ne = 0;
+        if (!src.read_small(nb)) break;
+        if (!src.getline(mid)) break;
+        if (!src.read_small(ne)) break;
+      }
+      uint32_t cnt = 0;
+      if (!src.read_u32(cnt)) break;
+      tids.resize(cnt);
+      bool ok = true;
+      for (uint32_t j = 0; j < cnt; ++j) {
+        uint32_t v = 0;
+        if (!src.read_u32(v)) { ok = false; break; }
+        if (v >= (uint32_t)all_names.size()) { err = "Hits file looks malformed."; return 1; }
+        tids[j] = (int32_t)v;
+      }
+      if (!ok) break;
+      cb.add_record(tids.data(), nullptr, (int)cnt);
+    }
+  }
+  if (src.corrupt()) { err = "Error: zlib stream of \"" + path + "\" is corrupt."; return 1; }
+  cb.finish(cls);
+  return 0;
+}
+
+int scaled_lengths(const HitsHeader& hdr, const HitClasses& cls, std::vector<double>& l, std::string& err) {
+  l.resize((size_t)cls.n);
+  for (int64_t t = 0; t < cls.n; ++t) {
+    const int32_t h = cls.col2hdr[(size_t)t];
+    l[(size_t)t] = hdr.efflen[(size_t)h] * (double)cls.N / 1000000000.0;
+    if (l[(size_t)t] <= 0) { err = "Error: transcript '" + hdr.names[(size_t)h] + "' has a length of zero."; return 1; }
+  }
+  return 0;
+}
+
+}  // namespace mmq
+
+/* ---------------------------------------------------------------- C ABI
+ * (for the Python harness; the host program links the C++ API directly) */
+extern "C" {
+
+struct mmqh_hits {
+  mmq::HitsHeader hdr;
+  mmq::HitClasses cls;
+  std::vector<int64_t> gene_ptr, ident_ptr;
+  std::vector<int32_t> gene_mem, ident_mem;
+};
+
+static void set_err(char* err, int errlen, const std::string& s) {
+  if (err && errlen > 0) { snprintf(err, (size_t)errlen, "%s", s.c_str()); }
+}
+
+static void flatten(mmqh_hits* H) {
+  H->gene_ptr.assign(1, 0);
+  for (auto& g : H->hdr.gene_members) { for (int32_t h : g) H->gene_mem.push_back(h); H->gene_ptr.push_back((int64_t)H->gene_mem.size()); }
+  H->ident_ptr.assign(1, 0);
+  for (auto& g : H->hdr.identical) { for (int32_t h : g) H->ident_mem.push_back(h); H->ident_ptr.push_back((int64_t)H->ident_mem.size()); }
+}
+
+mmqh_hits* mmqh_load(const char* path, int layout, char* err, int errlen) {
+  mmqh_hits* H = new mmqh_hits();
+  std::string e;
+  if (mmq::load_hits_file(path, layout, H->hdr, H->cls, e)) { set_err(err, errlen, e); delete H; return nullptr; }
+  flatten(H);
+  return H;
+}
+
+/* In-memory records (header transcript indices), no names or genes. */
+mmqh_hits* mmqh_from_records(int64_t T, const double* efflen, int64_t N, const int64_t* frag_ptr, const int32_t* frag_tid,
+                             const float* frag_w, int layout, char* err, int errlen) {
+  if (frag_w && (layout & 15) == mmq::LAYOUT_COLLAPSED) { set_err(err, errlen, "per-hit weights need a per-fragment layout"); return nullptr; }
+  mmqh_hits* H = new mmqh_hits();
+  H->hdr.efflen.assign(efflen, efflen + T);
+  H->hdr.names.resize((size_t)T);
+  mmq::ClassBuilder cb(T, layout, frag_w != nullptr);
+  for (int64_t f = 0; f < N; ++f) {
+    const int64_t b = frag_ptr[f], e = frag_ptr[f + 1];
+    for (int64_t q = b; q < e; ++q)
+      if (frag_tid[q] < 0 || frag_tid[q] >= T) { set_err(err, errlen, "transcript index out of range"); delete H; return nullptr; }
+    cb.add_record(frag_tid + b, frag_w ? frag_w + b : nullptr, (int)(e - b));
+  }
+  cb.finish(H->cls);
+  flatten(H);
+  return H;
+}
+
+void mmqh_free(mmqh_hits* H) { delete H; }
+
+int64_t mmqh_dim(const mmqh_hits* H, int which) {
+  switch (which) {
+    case 0: return (int64_t)H->hdr.names.size();
+    case 1: return (int64_t)H->hdr.gene_names.size();
+    case 2: return (int64_t)H->hdr.identical.size();
+    case 3: return H->cls.N;
+    case 4: return H->cls.n;
+    case 5: return H->cls.m;
+    case 6: return (int64_t)H->cls.col.size();
+    case 7: return H->cls.n_classes;
+    case 8: return H->hdr.schema;
+    default: return -1;
+  }
+}
+const int64_t* mmqh_row_ptr(const mmqh_hits* H) { return H->cls.row_ptr.data(); }
+const int32_t* mmqh_col(const mmqh_hits* H) { return H->cls.col.data(); }
+const int32_t* mmqh_k(const mmqh_hits* H) { return H->cls.k.empty() ? nullptr : H->cls.k.data(); }
+const float* mmqh_w(const mmqh_hits* H) { return H->cls.w.empty() ? nullptr : H->cls.w.data(); }
+const int32_t* mmqh_col2hdr(const mmqh_hits* H) { return H->cls.col2hdr.data(); }
+const int32_t* mmqh_hdr2col(const mmqh_hits* H) { return H->cls.hdr2col.data(); }
+const int32_t* mmqh_doublehits(const mmqh_hits* H) { return H->cls.doublehits.data(); }
+const double* mmqh_efflen(const mmqh_hits* H) { return H->hdr.efflen.data(); }
+const int32_t* mmqh_truelen(const mmqh_hits* H) { return H->hdr.truelen.data(); }
+const int32_t* mmqh_gene_of(const mmqh_hits* H) { return H->hdr.gene_of.data(); }
+const char* mmqh_name(const mmqh_hits* H, int64_t t) { return H->hdr.names[(size_t)t].c_str(); }
+const char* mmqh_gene_name(const mmqh_hits* H, int64_t g) { return H->hdr.gene_names[(size_t)g].c_str(); }
+const int64_t* mmqh_gene_ptr(const mmqh_hits* H) { return H->gene_ptr.data(); }
+const int32_t* mmqh_gene_members(const mmqh_hits* H) { return H->gene_mem.data(); }
+const int64_t* mmqh_ident_ptr(const mmqh_hits* H) { return H->ident_ptr.data(); }
+const int32_t* mmqh_ident_members(const mmqh_hits* H) { return H->ident_mem.data(); }
+int mmqh_scaled_len(const mmqh_hits* H, double* l_out) {
+  std::vector<double> l;
+  std::string e;
+  if (mmq::scaled_lengths(H->hdr, H->cls, l, e)) return 1;
+  std::memcpy(l_out, l.data(), sizeof(double) * l.size());
+  return 0;
+}
+
+} /* extern "C" */

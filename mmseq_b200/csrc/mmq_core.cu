@@ -1,0 +1,832 @@
+/* mmq_core.cu — device-resident hit-class CSR, EM and Gibbs kernels (sm_100a)
+ * and the C ABI over them (include/mmq.h).
+ *
+ * Reference loops replaced (eturro/mmseq 1.0.11, /root/reference):
+ *   k_init_acc / k_divide    src/mmseq.cpp:617-638  initial mu, unique hits
+ *   k_rowterm                src/mmseq.cpp:745-754, :796-802 (log-lik), :787-791 (D_i)
+ *   k_em_acc / k_em_apply    src/mmseq.cpp:781-794  EM update
+ *   k_alloc                  src/mmseq.cpp:862-891  multinomial per hit class
+ *   k_count_reduce           src/mmseq.cpp:887, :895-899  per-transcript counts
+ *   k_gamma                  src/mmseq.cpp:904-917  Gamma update + trace capture
+ * Compile with -fmad=false: the samplers of include/mmq_sampler.h must round
+ * exactly like the gcc build of the CPU replay.
+ */
+#include <cub/cub.cuh>
+#include <dlfcn.h>
+#include <nccl.h> /* types only; the library is dlopen'ed */
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/mmq_sampler.h"
+#include "mmq_internal.h"
+
+std::atomic<long long> g_mmq_launches{0};
+thread_local std::string g_mmq_create_err;
+
+/* ------------------------------------------------------------------ errors */
+
+int mmq_fail(mmq_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg; else g_mmq_create_err = msg;
+  return code;
+}
+
+int mmq_cuda_fail(mmq_handle* h, cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+  return mmq_fail(h, MMQ_ERR_CUDA, buf);
+}
+
+int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes) {
+  *p = nullptr;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaMalloc", __FILE__, __LINE__);
+  h->bytes += (int64_t)bytes;
+  h->allocs.push_back(*p);
+  return MMQ_OK;
+}
+
+void mmq_dev_free(mmq_handle* h, void* p) {
+  if (!p) return;
+  auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
+  if (it != h->allocs.end()) h->allocs.erase(it);
+  cudaFree(p);
+}
+
+/* ------------------------------------------------------- device utilities */
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+/* Deterministic block sum (blockDim.x a multiple of 32, <= 1024); result valid in thread 0. */
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double s_part[32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_part[wid] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) r += s_part[i];
+  }
+  return r;
+}
+
+/* out[slot] = sum of partial[0..count) in index order (single block of 256). */
+__global__ void k_sum_partials(const double* __restrict__ partial, int count, double* __restrict__ out, int slot) {
+  double v = 0.0;
+  for (int i = threadIdx.x; i < count; i += blockDim.x) v += partial[i];
+  v = block_sum(v);
+  if (threadIdx.x == 0) out[slot] = v;
+}
+
+/* flags[0] |= 1 for an empty / negative-length row, |= 2 for a column out of range,
+ * |= 4 for columns not strictly ascending within a row */
+__global__ void k_validate(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, int64_t m,
+                           int64_t n, int* __restrict__ flags) {
+  int bad = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = row_ptr[i], e = row_ptr[i + 1];
+    if (e <= b) { bad |= 1; continue; }
+    int32_t prev = -1;
+    for (int64_t q = b; q < e; ++q) {
+      const int32_t c = col[q];
+      if (c < 0 || c >= n) bad |= 2;
+      if (c <= prev) bad |= 4;
+      prev = c;
+    }
+  }
+  if (bad) atomicOr(flags, bad);
+}
+
+/* ---------------------------------------------------- transpose building */
+
+__global__ void k_iota(uint32_t* __restrict__ v, int64_t nnz) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x)
+    v[q] = (uint32_t)q;
+}
+
+/* keys sorted ascending: tptr[t] = first q with keys[q] >= t, tptr[n] = nnz */
+__global__ void k_tptr(const int32_t* __restrict__ keys, int64_t nnz, int64_t n, int64_t* __restrict__ tptr) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q <= nnz; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t prev = (q == 0) ? -1 : (int64_t)keys[q - 1];
+    const int64_t cur = (q == nnz) ? n : (int64_t)keys[q];
+    for (int64_t t = prev + 1; t <= cur; ++t) tptr[t] = q;
+  }
+}
+
+/* trow[q'] = class whose CSR range contains position perm[q'] */
+__global__ void k_trow(const uint32_t* __restrict__ perm, const int64_t* __restrict__ row_ptr, int64_t m, int64_t nnz,
+                       int32_t* __restrict__ trow) {
+  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t pos = (int64_t)perm[q];
+    int64_t lo = 0, hi = m; /* row_ptr[lo] <= pos < row_ptr[hi] */
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (row_ptr[mid] <= pos) lo = mid; else hi = mid;
+    }
+    trow[q] = (int32_t)lo;
+  }
+}
+
+/* --------------------------------------------------------- init / EM */
+
+/* acc[t] = sum_{i containing t} k[i]/|i| (ascending i), uh[t] = sum of k[i] over
+ * singleton classes {t}.  One warp per transcript.  src/mmseq.cpp:625-635. */
+template <bool HAS_K>
+__global__ void k_init_acc(const int64_t* __restrict__ tptr, const int32_t* __restrict__ trow,
+                           const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ kk,
+                           double* __restrict__ acc, int32_t* __restrict__ uh, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp0; t < n; t += nwarps) {
+    double s = 0.0;
+    int u = 0;
+    for (int64_t q = tptr[t] + lane; q < tptr[t + 1]; q += 32) {
+      const int32_t i = trow[q];
+      const int64_t d = row_ptr[i + 1] - row_ptr[i];
+      const int32_t kv = HAS_K ? kk[i] : 1;
+      s += (double)kv / (double)d;
+      if (d == 1) u += kv;
+    }
+    s = warp_sum(s);
+    u = warp_sum_i(u);
+    if (lane == 0) { acc[t] = s; uh[t] = u; }
+  }
+}
+
+__global__ void k_divide(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int64_t n) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    out[t] = a[t] / b[t];
+}
+
+/* rterm[i] = k_i / D_i with D_i = sum_{s in i} w_is mu_s; partial[block] = sum_i k_i log D_i.
+ * src/mmseq.cpp:748-751 and :797-800 (log-lik), :789-790 (k[row]/inner_prod). */
+template <bool HAS_K, bool HAS_W>
+__global__ void k_rowterm(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                          const int32_t* __restrict__ kk, const float* __restrict__ w,
+                          const double* __restrict__ mu, double* __restrict__ rterm,
+                          double* __restrict__ partial, int64_t m) {
+  double ll = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = row_ptr[i], e = row_ptr[i + 1];
+    double D = 0.0;
+    for (int64_t q = b; q < e; ++q) D += HAS_W ? (double)w[q] * mu[col[q]] : mu[col[q]];
+    const double kv = (double)(HAS_K ? kk[i] : 1);
+    rterm[i] = kv / D;
+    ll += kv * log(D);
+  }
+  ll = block_sum(ll);
+  if (threadIdx.x == 0) partial[blockIdx.x] = ll;
+}
+
+/* acc[t] = sum_{i containing t} w_it k_i / D_i, one warp per transcript. src/mmseq.cpp:786-791. */
+template <bool HAS_W>
+__global__ void k_em_acc(const int64_t* __restrict__ tptr, const uint32_t* __restrict__ perm,
+                         const int32_t* __restrict__ trow, const float* __restrict__ w,
+                         const double* __restrict__ rterm, double* __restrict__ acc, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp0; t < n; t += nwarps) {
+    double s = 0.0;
+    for (int64_t q = tptr[t] + lane; q < tptr[t + 1]; q += 32)
+      s += HAS_W ? (double)w[perm[q]] * rterm[trow[q]] : rterm[trow[q]];
+    s = warp_sum(s);
+    if (lane == 0) acc[t] = s;
+  }
+}
+
+/* mu_out[t] = mu[t]*acc[t]/l[t] (src/mmseq.cpp:792); partial[block] = sum_t mu_out[t] l[t] (:802). */
+__global__ void k_em_apply(const double* __restrict__ mu, const double* __restrict__ acc,
+                           const double* __restrict__ len, double* __restrict__ mu_out,
+                           double* __restrict__ partial, int64_t n) {
+  double s = 0.0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const double v = mu[t] * acc[t] / len[t];
+    mu_out[t] = v;
+    s += v * len[t];
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void k_mul_sum(const double* __restrict__ a, const double* __restrict__ b,
+                          double* __restrict__ partial, int64_t n) {
+  double s = 0.0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    s += a[t] * b[t];
+  s = block_sum(s);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+/* ------------------------------------------------------------- Gibbs */
+
+/* x[j] = v on this proxy adds v to counts[col_j] (no X matrix is kept: the
+ * reference's X is write-only, src/mmseq.cpp:884). */
+struct XRed {
+  const int32_t* c;
+  int32_t* counts;
+  struct Ref {
+    int32_t* addr;
+    __device__ __forceinline__ void operator=(int32_t v) const { if (v != 0) atomicAdd(addr, v); }
+  };
+  __device__ __forceinline__ Ref operator[](int j) const { return Ref{counts + c[j]}; }
+};
+
+/* p[j] straight from global memory, for tiles too large to stage. */
+template <bool HAS_W>
+struct PGlobal {
+  const int32_t* c;
+  const float* w;
+  const double* mu;
+  __device__ __forceinline__ double operator[](int j) const {
+    return HAS_W ? mu[c[j]] * (double)w[j] : mu[c[j]];
+  }
+};
+
+/* K2: allocate the k_i fragments of every hit class among its transcripts.
+ * A CTA takes a tile of `rows_per_tile` consecutive classes, stages the tile's
+ * contiguous CSR segment (columns, and p = mu[col] * weight gathered once) in
+ * shared memory with coalesced loads, then one thread per class runs
+ * mmq_alloc_row on its slice.  MATERIALIZE writes x into the X array (CSR
+ * order) for k_count_reduce; otherwise each non-zero x goes straight to
+ * counts[] as a reduction (the fused path).  Persistent over tiles. */
+template <bool MATERIALIZE, bool HAS_K, bool HAS_W>
+__global__ void __launch_bounds__(MMQ_ALLOC_THREADS)
+k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+        const int32_t* __restrict__ kk, const float* __restrict__ w, const double* __restrict__ mu,
+        int32_t* __restrict__ counts, int32_t* __restrict__ xout, int64_t m, int rows_per_tile,
+        int64_t n_tiles, uint32_t seed, uint32_t sweep, int64_t class_id_base) {
+  __shared__ double s_p[MMQ_ALLOC_CAP];
+  __shared__ int32_t s_c[MMQ_ALLOC_CAP];
+  __shared__ int32_t s_x[MATERIALIZE ? MMQ_ALLOC_CAP : 1];
+  __shared__ int64_t s_rp[MMQ_ALLOC_THREADS + 1];
+  const int tid = threadIdx.x;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t r0 = tile * rows_per_tile;
+    const int nrows = (int)((m - r0 < rows_per_tile) ? (m - r0) : rows_per_tile);
+    for (int i = tid; i <= nrows; i += MMQ_ALLOC_THREADS) s_rp[i] = row_ptr[r0 + i];
+    __syncthreads();
+    const int64_t base = s_rp[0];
+    const int64_t cnt = s_rp[nrows] - base;
+    const bool staged = cnt <= MMQ_ALLOC_CAP;
+    if (staged) {
+      for (int q = tid; q < (int)cnt; q += MMQ_ALLOC_THREADS) {
+        const int32_t c = col[base + q];
+        double p = mu[c];
+        if (HAS_W) p *= (double)w[base + q];
+        s_c[q] = c;
+        s_p[q] = p;
+      }
+    }
+    __syncthreads();
+    if (tid < nrows) {
+      const int64_t rb = s_rp[tid];
+      const int d = (int)(s_rp[tid + 1] - rb);
+      const int64_t kv = HAS_K ? (int64_t)kk[r0 + tid] : 1;
+      const uint64_t cid = (uint64_t)(class_id_base + r0 + tid);
+      if (staged) {
+        const int off = (int)(rb - base);
+        if (MATERIALIZE) mmq_alloc_row(s_p + off, s_x + off, d, kv, seed, cid, sweep);
+        else mmq_alloc_row(s_p + off, XRed{s_c + off, counts}, d, kv, seed, cid, sweep);
+      } else {
+        PGlobal<HAS_W> pg{col + rb, HAS_W ? w + rb : nullptr, mu};
+        if (MATERIALIZE) mmq_alloc_row(pg, xout + rb, d, kv, seed, cid, sweep);
+        else mmq_alloc_row(pg, XRed{col + rb, counts}, d, kv, seed, cid, sweep);
+      }
+    }
+    __syncthreads();
+    if (MATERIALIZE && staged)
+      for (int q = tid; q < (int)cnt; q += MMQ_ALLOC_THREADS) xout[base + q] = s_x[q];
+  }
+}
+
+/* K3: counts[t] = sum over the transposed CSR of X — an atomic-free segmented
+ * reduction, one warp per transcript.  src/mmseq.cpp:887, :895-899. */
+__global__ void k_count_reduce(const int64_t* __restrict__ tptr, const uint32_t* __restrict__ perm,
+                               const int32_t* __restrict__ x, int32_t* __restrict__ counts, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t t = warp0; t < n; t += nwarps) {
+    int s = 0;
+    for (int64_t q = tptr[t] + lane; q < tptr[t + 1]; q += 32) s += x[perm[q]];
+    s = warp_sum_i(s);
+    if (lane == 0) counts[t] = s;
+  }
+}
+
+/* K4 (+K5 capture): mu[t] ~ Gamma(alpha + counts[t], rate beta + l[t]); counts
+ * are cleared for the next sweep; trace_col (= trace + slot, or null) receives
+ * mu at stride trace_len.  src/mmseq.cpp:904-917. */
+__global__ void k_gamma(int32_t* __restrict__ counts, const double* __restrict__ len,
+                        double* __restrict__ mu, double* __restrict__ trace_col, int trace_len, int64_t n,
+                        double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t c = counts[t];
+    counts[t] = 0;
+    if (counts_copy) counts_copy[t] = c;
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
+    const double v = mmq_gamma(&g, alpha + (double)c, beta + len[t]);
+    mu[t] = v;
+    if (trace_col) trace_col[t * (int64_t)trace_len] = v;
+  }
+}
+
+/* -------------------------------------------------------------- NCCL */
+
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi g_nccl;
+
+const char* nccl_load() {
+  if (g_nccl.lib) return nullptr;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* nm : names) { lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+  if (!lib) return "cannot dlopen libnccl.so.2";
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy) return "libnccl lacks a required symbol";
+  g_nccl.lib = lib;
+  return nullptr;
+}
+}  // namespace
+
+int mmq_allreduce(mmq_handle* h, void* buf, size_t count, int is_double) {
+  if (h->nranks <= 1 || !h->comm) return MMQ_OK;
+  ncclResult_t r = g_nccl.AllReduce(buf, buf, count, is_double ? ncclFloat64 : ncclInt32, ncclSum, (ncclComm_t)h->comm, h->stream);
+  if (r != ncclSuccess)
+    return mmq_fail(h, MMQ_ERR_NCCL, std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  return MMQ_OK;
+}
+
+/* ---------------------------------------------------------------- C ABI */
+
+extern "C" {
+
+const char* mmq_version(void) { return "mmseq-b200 0.1 (hot path of eturro/mmseq 1.0.11)"; }
+int64_t mmq_launch_count(void) { return (int64_t)g_mmq_launches.load(); }
+
+const char* mmq_last_error(const mmq_handle* h) { return h ? h->err.c_str() : g_mmq_create_err.c_str(); }
+
+static int upload(mmq_handle* h, void** dst, const void* src, size_t bytes) {
+  int rc = mmq_dev_alloc(h, dst, bytes);
+  if (rc) return rc;
+  if (bytes) MMQ_CUDA(h, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+  return MMQ_OK;
+}
+
+static int build_transpose(mmq_handle* h) {
+  if (h->tptr) return MMQ_OK; /* built on first use: the fused Gibbs path never needs it */
+  const int64_t nnz = h->nnz, n = h->n, m = h->m;
+  int rc;
+  if ((rc = mmq_dev_alloc(h, (void**)&h->tptr, sizeof(int64_t) * (size_t)(n + 1)))) return rc;
+  if ((rc = mmq_dev_alloc(h, (void**)&h->perm, sizeof(uint32_t) * (size_t)nnz))) return rc;
+  if ((rc = mmq_dev_alloc(h, (void**)&h->trow, sizeof(int32_t) * (size_t)nnz))) return rc;
+  if (nnz == 0) {
+    MMQ_CUDA(h, cudaMemsetAsync(h->tptr, 0, sizeof(int64_t) * (size_t)(n + 1), h->stream));
+    return MMQ_OK;
+  }
+  int32_t* keys_out = nullptr;
+  uint32_t* iota = nullptr;
+  void* temp = nullptr;
+  size_t temp_bytes = 0;
+  MMQ_CUDA(h, cudaMalloc(&keys_out, sizeof(int32_t) * (size_t)nnz));
+  MMQ_CUDA(h, cudaMalloc(&iota, sizeof(uint32_t) * (size_t)nnz));
+  const int grid = mmq_grid_for(nnz, 256, h->num_sms * 8);
+  k_iota<<<grid, 256, 0, h->stream>>>(iota, nnz);
+  MMQ_LAUNCHED(h);
+  int end_bit = 1;
+  while (end_bit < 31 && ((int64_t)1 << end_bit) < n) ++end_bit;
+  /* stable LSD radix sort of (column, position): positions stay ascending within a column */
+  MMQ_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, h->col, keys_out, iota, h->perm, nnz, 0, end_bit, h->stream));
+  MMQ_CUDA(h, cudaMalloc(&temp, temp_bytes));
+  MMQ_CUDA(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, h->col, keys_out, iota, h->perm, nnz, 0, end_bit, h->stream));
+  k_tptr<<<grid, 256, 0, h->stream>>>(keys_out, nnz, n, h->tptr);
+  MMQ_LAUNCHED(h);
+  k_trow<<<grid, 256, 0, h->stream>>>(h->perm, h->row_ptr, m, nnz, h->trow);
+  MMQ_LAUNCHED(h);
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  cudaFree(keys_out);
+  cudaFree(iota);
+  cudaFree(temp);
+  return MMQ_OK;
+}
+
+int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
+  if (!out) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: out is NULL");
+  *out = nullptr;
+  if (!p || p->n <= 0 || p->m < 0 || p->nnz < 0 || !p->row_ptr || (!p->col && p->nnz > 0) || !p->len)
+    return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: bad problem (n <= 0, m < 0 or NULL arrays)");
+  if (p->nnz >= (int64_t)0xffffffffll) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: nnz per shard must be < 2^32");
+  if (p->n >= (int64_t)0x7fffffffll || p->m >= (int64_t)0x7fffffffll) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: n and m per shard must be < 2^31");
+  if (p->row_ptr[0] != 0 || p->row_ptr[p->m] != p->nnz) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: row_ptr[0] != 0 or row_ptr[m] != nnz");
+  if (!(p->alpha > 0.0) || !(p->beta >= 0.0)) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: alpha must be > 0 and beta >= 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "mmq_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    return mmq_fail(nullptr, MMQ_ERR_CUDA, buf);
+  }
+  if (device < 0 || device >= ndev) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: device index out of range");
+  mmq_handle* h = new mmq_handle();
+  h->device = device;
+#define CREATE_TRY(expr)                      \
+  do {                                        \
+    int rc__ = (expr);                        \
+    if (rc__) {                               \
+      g_mmq_create_err = h->err;              \
+      mmq_destroy(h);                         \
+      return rc__;                            \
+    }                                         \
+  } while (0)
+  auto cuda_try = [&](cudaError_t ce, const char* what) -> int {
+    return ce == cudaSuccess ? MMQ_OK : mmq_cuda_fail(h, ce, what, __FILE__, __LINE__);
+  };
+  CREATE_TRY(cuda_try(cudaSetDevice(device), "cudaSetDevice"));
+  CREATE_TRY(cuda_try(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+  h->own_stream = true;
+  cudaDeviceProp prop;
+  CREATE_TRY(cuda_try(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"));
+  h->num_sms = prop.multiProcessorCount;
+  h->n = p->n; h->m = p->m; h->nnz = p->nnz; h->class_id_base = p->class_id_base;
+  h->alpha = p->alpha; h->beta = p->beta;
+  h->has_k = p->k != nullptr; h->has_w = p->weight != nullptr;
+  for (int64_t t = 0; t < p->n; ++t)
+    if (!(p->len[t] > 0.0)) { h->err = "mmq_create: transcript length must be > 0 (src/mmseq.cpp:604-607)"; CREATE_TRY(MMQ_ERR_ARG); }
+  CREATE_TRY(upload(h, (void**)&h->row_ptr, p->row_ptr, sizeof(int64_t) * (size_t)(p->m + 1)));
+  CREATE_TRY(upload(h, (void**)&h->col, p->col, sizeof(int32_t) * (size_t)p->nnz));
+  if (h->has_k) CREATE_TRY(upload(h, (void**)&h->k, p->k, sizeof(int32_t) * (size_t)p->m));
+  if (h->has_w) CREATE_TRY(upload(h, (void**)&h->w, p->weight, sizeof(float) * (size_t)p->nnz));
+  CREATE_TRY(upload(h, (void**)&h->len, p->len, sizeof(double) * (size_t)p->n));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->mu, sizeof(double) * (size_t)p->n));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->mu_tmp, sizeof(double) * (size_t)p->n));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->acc, sizeof(double) * (size_t)p->n));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->counts, sizeof(int32_t) * (size_t)p->n));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->uh, sizeof(int32_t) * (size_t)p->n));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->rterm, sizeof(double) * (size_t)std::max<int64_t>(p->m, 1)));
+  h->partial_cap = h->num_sms * 8;
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->partial, sizeof(double) * (size_t)h->partial_cap));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->scalars, sizeof(double) * 4));
+  CREATE_TRY(cuda_try(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * (size_t)p->n, h->stream), "memset counts"));
+  CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu, 0, sizeof(double) * (size_t)p->n, h->stream), "memset mu"));
+  if (p->m > 0) { /* structural checks on the device: no O(nnz) host loop in front of the upload */
+    int* d_flags = (int*)h->scalars;
+    CREATE_TRY(cuda_try(cudaMemsetAsync(d_flags, 0, sizeof(int), h->stream), "memset flags"));
+    k_validate<<<mmq_grid_for(p->m, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->row_ptr, h->col, p->m, p->n, d_flags);
+    g_mmq_launches.fetch_add(1);
+    int flags = 0;
+    CREATE_TRY(cuda_try(cudaMemcpyAsync(&flags, d_flags, sizeof(int), cudaMemcpyDeviceToHost, h->stream), "copy flags"));
+    CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "validate"));
+    if (flags & 1) { h->err = "mmq_create: empty or negative-length class row"; CREATE_TRY(MMQ_ERR_ARG); }
+    if (flags & 2) { h->err = "mmq_create: column index out of range"; CREATE_TRY(MMQ_ERR_ARG); }
+    if (flags & 4) { h->err = "mmq_create: columns must be strictly ascending within a class (src/mmseq.cpp:412)"; CREATE_TRY(MMQ_ERR_ARG); }
+  }
+  /* tile shape: as many classes per CTA as keeps the mean tile inside the staging buffer */
+  {
+    const double mean_d = p->m > 0 ? (double)p->nnz / (double)p->m : 1.0;
+    int r = MMQ_ALLOC_THREADS;
+    while (r > 32 && (double)r * mean_d * 1.25 > (double)MMQ_ALLOC_CAP) r >>= 1;
+    h->rows_per_tile = r;
+    h->n_tiles = (p->m + r - 1) / r;
+  }
+  CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
+#undef CREATE_TRY
+  *out = h;
+  return MMQ_OK;
+}
+
+void mmq_destroy(mmq_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (cudaEvent_t e : h->ev_alloc) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->ev_gamma) cudaEventDestroy(e);
+  if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+int mmq_set_stream(mmq_handle* h, void* s) {
+  if (!h) return MMQ_ERR_ARG;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  h->stream = (cudaStream_t)s;
+  h->own_stream = false;
+  return MMQ_OK;
+}
+void* mmq_get_stream(mmq_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int mmq_synchronize(mmq_handle* h) {
+  if (!h) return MMQ_ERR_ARG;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMQ_OK;
+}
+
+int64_t mmq_device_bytes(const mmq_handle* h) { return h ? h->bytes : 0; }
+
+int mmq_comm_id(char id[128]) {
+  const char* e = nccl_load();
+  if (e) return mmq_fail(nullptr, MMQ_ERR_NCCL, e);
+  ncclUniqueId uid;
+  static_assert(sizeof(uid) == 128, "ncclUniqueId is 128 bytes");
+  ncclResult_t r = g_nccl.GetUniqueId(&uid);
+  if (r != ncclSuccess) return mmq_fail(nullptr, MMQ_ERR_NCCL, "ncclGetUniqueId failed");
+  memcpy(id, &uid, 128);
+  return MMQ_OK;
+}
+
+int mmq_comm_init(mmq_handle* h, const char id[128], int rank, int nranks) {
+  if (!h || !id || nranks < 1 || rank < 0 || rank >= nranks) return mmq_fail(h, MMQ_ERR_ARG, "mmq_comm_init: bad arguments");
+  if (nranks == 1) { h->rank = 0; h->nranks = 1; return MMQ_OK; }
+  const char* e = nccl_load();
+  if (e) return mmq_fail(h, MMQ_ERR_NCCL, e);
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclComm_t comm;
+  ncclResult_t r = g_nccl.CommInitRank(&comm, nranks, uid, rank);
+  if (r != ncclSuccess)
+    return mmq_fail(h, MMQ_ERR_NCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"));
+  h->comm = comm; h->rank = rank; h->nranks = nranks;
+  return MMQ_OK;
+}
+
+/* ---- initial mu ---- */
+int mmq_init_mu(mmq_handle* h, int32_t* unique_hits_out) {
+  if (!h) return MMQ_ERR_ARG;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  { int rc0 = build_transpose(h); if (rc0) return rc0; }
+  const int grid = mmq_grid_for(h->n * 32, 256, h->num_sms * 8);
+  if (h->has_k) k_init_acc<true><<<grid, 256, 0, h->stream>>>(h->tptr, h->trow, h->row_ptr, h->k, h->acc, h->uh, h->n);
+  else k_init_acc<false><<<grid, 256, 0, h->stream>>>(h->tptr, h->trow, h->row_ptr, h->k, h->acc, h->uh, h->n);
+  MMQ_LAUNCHED(h);
+  int rc;
+  if ((rc = mmq_allreduce(h, h->acc, (size_t)h->n, 1))) return rc;
+  if ((rc = mmq_allreduce(h, h->uh, (size_t)h->n, 0))) return rc;
+  k_divide<<<mmq_grid_for(h->n, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->acc, h->len, h->mu, h->n);
+  MMQ_LAUNCHED(h);
+  if (unique_hits_out) MMQ_CUDA(h, cudaMemcpyAsync(unique_hits_out, h->uh, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMQ_OK;
+}
+
+int mmq_set_mu(mmq_handle* h, const double* mu) {
+  if (!h || !mu) return mmq_fail(h, MMQ_ERR_ARG, "mmq_set_mu: NULL argument");
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaMemcpyAsync(h->mu, mu, sizeof(double) * (size_t)h->n, cudaMemcpyHostToDevice, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMQ_OK;
+}
+
+int mmq_get_mu(mmq_handle* h, double* mu_out) {
+  if (!h || !mu_out) return mmq_fail(h, MMQ_ERR_ARG, "mmq_get_mu: NULL argument");
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaMemcpyAsync(mu_out, h->mu, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMQ_OK;
+}
+
+/* ---- log-likelihood and EM ---- */
+
+/* scalars[0] = sum over this shard's classes of k log D (and rterm refreshed) from `mu_dev`. */
+static int launch_rowterm(mmq_handle* h, const double* mu_dev) {
+  const int grid = mmq_grid_for(h->m, 256, h->partial_cap);
+  if (h->has_k) {
+    if (h->has_w) k_rowterm<true, true><<<grid, 256, 0, h->stream>>>(h->row_ptr, h->col, h->k, h->w, mu_dev, h->rterm, h->partial, h->m);
+    else k_rowterm<true, false><<<grid, 256, 0, h->stream>>>(h->row_ptr, h->col, h->k, h->w, mu_dev, h->rterm, h->partial, h->m);
+  } else {
+    if (h->has_w) k_rowterm<false, true><<<grid, 256, 0, h->stream>>>(h->row_ptr, h->col, h->k, h->w, mu_dev, h->rterm, h->partial, h->m);
+    else k_rowterm<false, false><<<grid, 256, 0, h->stream>>>(h->row_ptr, h->col, h->k, h->w, mu_dev, h->rterm, h->partial, h->m);
+  }
+  MMQ_LAUNCHED(h);
+  k_sum_partials<<<1, 256, 0, h->stream>>>(h->partial, grid, h->scalars, 0);
+  MMQ_LAUNCHED(h);
+  return mmq_allreduce(h, h->scalars, 1, 1);
+}
+
+int mmq_loglik(mmq_handle* h, double* out) {
+  if (!h || !out) return mmq_fail(h, MMQ_ERR_ARG, "mmq_loglik: NULL argument");
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  int rc = launch_rowterm(h, h->mu);
+  if (rc) return rc;
+  const int grid = mmq_grid_for(h->n, 256, h->partial_cap);
+  k_mul_sum<<<grid, 256, 0, h->stream>>>(h->mu, h->len, h->partial, h->n);
+  MMQ_LAUNCHED(h);
+  k_sum_partials<<<1, 256, 0, h->stream>>>(h->partial, grid, h->scalars, 1);
+  MMQ_LAUNCHED(h);
+  double s[2];
+  MMQ_CUDA(h, cudaMemcpyAsync(s, h->scalars, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  *out = s[0] - s[1];
+  return MMQ_OK;
+}
+
+int mmq_em(mmq_handle* h, int max_iter, double eps, int* iters_out, double* loglik_out, double* llr_out) {
+  if (!h) return MMQ_ERR_ARG;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  double loglik = 0.0;
+  int rc = build_transpose(h);
+  if (rc) return rc;
+  rc = mmq_loglik(h, &loglik); /* also leaves rterm = k/D(mu) */
+  if (rc) return rc;
+  double llr = eps + 1.0;
+  int iter = 0;
+  const int grid_w = mmq_grid_for(h->n * 32, 256, h->num_sms * 8);
+  const int grid_t = mmq_grid_for(h->n, 256, h->partial_cap);
+  while (iter < max_iter && llr > eps) {
+    if (h->has_w) k_em_acc<true><<<grid_w, 256, 0, h->stream>>>(h->tptr, h->perm, h->trow, h->w, h->rterm, h->acc, h->n);
+    else k_em_acc<false><<<grid_w, 256, 0, h->stream>>>(h->tptr, h->perm, h->trow, h->w, h->rterm, h->acc, h->n);
+    MMQ_LAUNCHED(h);
+    if ((rc = mmq_allreduce(h, h->acc, (size_t)h->n, 1))) return rc;
+    k_em_apply<<<grid_t, 256, 0, h->stream>>>(h->mu, h->acc, h->len, h->mu_tmp, h->partial, h->n);
+    MMQ_LAUNCHED(h);
+    k_sum_partials<<<1, 256, 0, h->stream>>>(h->partial, grid_t, h->scalars, 1);
+    MMQ_LAUNCHED(h);
+    if ((rc = launch_rowterm(h, h->mu_tmp))) return rc;
+    double s[2];
+    MMQ_CUDA(h, cudaMemcpyAsync(s, h->scalars, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+    MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::swap(h->mu, h->mu_tmp);
+    const double ll2 = s[0] - s[1];
+    llr = ll2 - loglik;
+    loglik = ll2;
+    ++iter;
+  }
+  if (iters_out) *iters_out = iter;
+  if (loglik_out) *loglik_out = loglik;
+  if (llr_out) *llr_out = llr;
+  return MMQ_OK;
+}
+
+/* ---- Gibbs ---- */
+
+static int ensure_x(mmq_handle* h) {
+  if (h->x) return MMQ_OK;
+  return mmq_dev_alloc(h, (void**)&h->x, sizeof(int32_t) * (size_t)std::max<int64_t>(h->nnz, 1));
+}
+
+} /* extern "C" */
+template <bool MAT>
+static void launch_alloc_t(mmq_handle* h, int grid, uint32_t seed, uint32_t sweep) {
+#define MMQ_ALLOC_ARGS h->row_ptr, h->col, h->k, h->w, h->mu, h->counts, h->x, h->m, h->rows_per_tile, h->n_tiles, seed, sweep, h->class_id_base
+  if (h->has_k) {
+    if (h->has_w) k_alloc<MAT, true, true><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+    else k_alloc<MAT, true, false><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+  } else {
+    if (h->has_w) k_alloc<MAT, false, true><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+    else k_alloc<MAT, false, false><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+  }
+#undef MMQ_ALLOC_ARGS
+}
+extern "C" {
+
+/* One sweep on the stream.  trace_col = device address of trace[0*L + slot] or null. */
+static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags, double* trace_col, int32_t* counts_copy) {
+  const bool transposed = (flags & MMQ_GIBBS_TRANSPOSED) != 0;
+  const bool timed = (flags & MMQ_GIBBS_TIME_KERNELS) != 0;
+  int rc;
+  auto mark = [&](std::vector<cudaEvent_t>& v) {
+    if (!timed) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, h->stream);
+    v.push_back(e);
+  };
+  if (h->m > 0) {
+    const int grid = (int)std::min<int64_t>(h->n_tiles, (int64_t)h->num_sms * 6);
+    if (transposed) {
+      if ((rc = ensure_x(h))) return rc;
+      if ((rc = build_transpose(h))) return rc;
+      mark(h->ev_alloc);
+      launch_alloc_t<true>(h, grid, seed, sweep);
+      MMQ_LAUNCHED(h);
+      mark(h->ev_alloc);
+      k_count_reduce<<<mmq_grid_for(h->n * 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->tptr, h->perm, h->x, h->counts, h->n);
+      MMQ_LAUNCHED(h);
+    } else {
+      mark(h->ev_alloc);
+      launch_alloc_t<false>(h, grid, seed, sweep);
+      MMQ_LAUNCHED(h);
+      mark(h->ev_alloc);
+    }
+  }
+  if ((rc = mmq_allreduce(h, h->counts, (size_t)h->n, 0))) return rc;
+  mark(h->ev_gamma);
+  k_gamma<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->counts, h->len, h->mu, trace_col, h->trace_len, h->n,
+                                                                          h->alpha, h->beta, seed, sweep, counts_copy);
+  MMQ_LAUNCHED(h);
+  mark(h->ev_gamma);
+  return MMQ_OK;
+}
+
+static int ensure_trace(mmq_handle* h, int trace_len) {
+  if (trace_len <= 0) return MMQ_OK;
+  if (h->trace && h->trace_len == trace_len) return MMQ_OK;
+  if (h->trace) { mmq_dev_free(h, h->trace); h->bytes -= (int64_t)sizeof(double) * h->n * h->trace_len; h->trace = nullptr; }
+  int rc = mmq_dev_alloc(h, (void**)&h->trace, sizeof(double) * (size_t)h->n * (size_t)trace_len);
+  if (rc) return rc;
+  h->trace_len = trace_len;
+  MMQ_CUDA(h, cudaMemsetAsync(h->trace, 0, sizeof(double) * (size_t)h->n * (size_t)trace_len, h->stream));
+  for (auto& g : h->groups) g.trace_valid = false;
+  return MMQ_OK;
+}
+
+int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweeps, int stride, int trace_len, int flags) {
+  if (!h) return MMQ_ERR_ARG;
+  if (first_sweep < 0 || n_sweeps < 0 || first_sweep + n_sweeps > (int64_t)0xffffffffll) return mmq_fail(h, MMQ_ERR_ARG, "mmq_gibbs: sweep range out of bounds");
+  if (trace_len > 0 && stride <= 0) return mmq_fail(h, MMQ_ERR_ARG, "mmq_gibbs: stride must be > 0");
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  int rc = ensure_trace(h, trace_len);
+  if (rc) return rc;
+  for (auto& g : h->groups) g.trace_valid = false;
+  for (int64_t s = first_sweep; s < first_sweep + n_sweeps; ++s) {
+    double* tc = nullptr;
+    if (trace_len > 0 && s % stride == 0 && s / stride < trace_len) tc = h->trace + s / stride;
+    if ((rc = enqueue_sweep(h, seed, (uint32_t)s, flags, tc, nullptr))) return rc;
+  }
+  return MMQ_OK;
+}
+
+int mmq_sweep_debug(mmq_handle* h, uint32_t seed, int64_t sweep, int flags, int32_t* x_out, int32_t* counts_out, double* mu_out) {
+  if (!h) return MMQ_ERR_ARG;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  if (x_out && !(flags & MMQ_GIBBS_TRANSPOSED)) return mmq_fail(h, MMQ_ERR_ARG, "mmq_sweep_debug: x_out needs MMQ_GIBBS_TRANSPOSED (the fused path keeps no X)");
+  int32_t* counts_copy = nullptr;
+  MMQ_CUDA(h, cudaMalloc(&counts_copy, sizeof(int32_t) * (size_t)h->n));
+  int rc = enqueue_sweep(h, seed, (uint32_t)sweep, flags, nullptr, counts_copy);
+  if (rc) { cudaFree(counts_copy); return rc; }
+  cudaError_t e = cudaSuccess;
+  if (x_out) e = cudaMemcpyAsync(x_out, h->x, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && counts_out) e = cudaMemcpyAsync(counts_out, counts_copy, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess && mu_out) e = cudaMemcpyAsync(mu_out, h->mu, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(counts_copy);
+  if (e != cudaSuccess) return mmq_cuda_fail(h, e, "mmq_sweep_debug copies", __FILE__, __LINE__);
+  return MMQ_OK;
+}
+
+static void drain_events(std::vector<cudaEvent_t>& v, double* ms_total, int64_t* launches) {
+  double tot = 0.0;
+  int64_t cnt = 0;
+  for (size_t i = 0; i + 1 < v.size(); i += 2) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) { tot += ms; ++cnt; }
+  }
+  for (cudaEvent_t e : v) cudaEventDestroy(e);
+  v.clear();
+  if (ms_total) *ms_total = tot;
+  if (launches) *launches = cnt;
+}
+
+int mmq_kernel_times(mmq_handle* h, double* alloc_ms, int64_t* alloc_launches, double* gamma_ms, int64_t* gamma_launches) {
+  if (!h) return MMQ_ERR_ARG;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  drain_events(h->ev_alloc, alloc_ms, alloc_launches);
+  drain_events(h->ev_gamma, gamma_ms, gamma_launches);
+  return MMQ_OK;
+}
+
+int mmq_trace_len(const mmq_handle* h) { return h ? h->trace_len : 0; }
+
+int mmq_get_trace(mmq_handle* h, double* out) {
+  if (!h || !out) return mmq_fail(h, MMQ_ERR_ARG, "mmq_get_trace: NULL argument");
+  if (!h->trace) return mmq_fail(h, MMQ_ERR_STATE, "mmq_get_trace: no trace recorded (run mmq_gibbs with trace_len > 0)");
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaMemcpyAsync(out, h->trace, sizeof(double) * (size_t)h->n * (size_t)h->trace_len, cudaMemcpyDeviceToHost, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMQ_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,111 @@
+/* mmq_internal.h — state behind the opaque mmq_handle and small launch helpers.
+ * Internal to libmmseq_b200.so; the public surface is include/mmq.h. */
+#ifndef MMQ_INTERNAL_H
+#define MMQ_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/mmq.h"
+
+/* Tiling of the allocation kernel: a CTA of MMQ_ALLOC_THREADS threads stages up
+ * to MMQ_ALLOC_CAP CSR entries of up to MMQ_ALLOC_THREADS consecutive classes. */
+#define MMQ_ALLOC_THREADS 256
+#define MMQ_ALLOC_CAP 2048
+
+struct mmq_group_set {
+  int64_t ngroups = 0;
+  int64_t* ptr_dev = nullptr;     /* [ngroups+1] */
+  int32_t* members_dev = nullptr; /* [ptr[ngroups]] */
+  double* extra_dev = nullptr;    /* [ngroups*trace_len] or null */
+  double* trace_dev = nullptr;    /* [trace_len * ngroups] slot-major, built lazily */
+  bool trace_valid = false;
+};
+
+struct mmq_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int num_sms = 148;
+
+  int64_t n = 0, m = 0, nnz = 0, class_id_base = 0;
+  double alpha = 0.1, beta = 0.1;
+  bool has_k = false, has_w = false;
+  int rows_per_tile = MMQ_ALLOC_THREADS;
+  int64_t n_tiles = 0;
+
+  /* class-major CSR */
+  int64_t* row_ptr = nullptr; /* [m+1] */
+  int32_t* col = nullptr;     /* [nnz] */
+  int32_t* k = nullptr;       /* [m] or null */
+  float* w = nullptr;         /* [nnz] or null */
+  double* len = nullptr;      /* [n] */
+  /* transcript-major transpose */
+  int64_t* tptr = nullptr;  /* [n+1] */
+  uint32_t* perm = nullptr; /* [nnz] position in the class-major arrays */
+  int32_t* trow = nullptr;  /* [nnz] class (row) of that position */
+
+  /* state */
+  double* mu = nullptr;      /* [n] */
+  double* mu_tmp = nullptr;  /* [n] */
+  double* acc = nullptr;     /* [n] fp64 per-transcript partial sums (EM, init) */
+  int32_t* counts = nullptr; /* [n] zero between sweeps */
+  int32_t* uh = nullptr;     /* [n] */
+  int32_t* x = nullptr;      /* [nnz], only for the transposed / debug path */
+  double* rterm = nullptr;   /* [m] k_i / D_i */
+  double* partial = nullptr; /* block partial sums */
+  int partial_cap = 0;
+  double* scalars = nullptr; /* [4] device scalars */
+
+  double* trace = nullptr; /* [trace_len * n] slot-major: trace[s*n + t] */
+  int trace_len = 0;
+
+  mmq_group_set groups[2];
+
+  /* multi-GPU */
+  void* comm = nullptr; /* ncclComm_t */
+  int rank = 0, nranks = 1;
+
+  /* MMQ_GIBBS_TIME_KERNELS: (start, stop) event pairs around each launch */
+  std::vector<cudaEvent_t> ev_alloc, ev_gamma;
+
+  int64_t bytes = 0;
+  std::string err;
+  std::vector<void*> allocs;
+};
+
+extern std::atomic<long long> g_mmq_launches;
+extern thread_local std::string g_mmq_create_err;
+
+int mmq_fail(mmq_handle* h, int code, const std::string& msg);
+int mmq_cuda_fail(mmq_handle* h, cudaError_t e, const char* what, const char* file, int line);
+int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes);
+void mmq_dev_free(mmq_handle* h, void* p);
+int mmq_allreduce(mmq_handle* h, void* buf, size_t count, int is_double);
+int mmq_ensure_trace_groups(mmq_handle* h);
+
+#define MMQ_CUDA(h, call)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (call);                                                          \
+    if (e__ != cudaSuccess) return mmq_cuda_fail((h), e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define MMQ_LAUNCHED(h)                                                                       \
+  do {                                                                                        \
+    g_mmq_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+    cudaError_t e__ = cudaGetLastError();                                                     \
+    if (e__ != cudaSuccess) return mmq_cuda_fail((h), e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+static inline int mmq_grid_for(int64_t work_items, int per_block, int max_blocks) {
+  int64_t b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+#endif

@@ -1,0 +1,105 @@
+"""ctypes view of libmmq_host.so: the product's .hits loader and hit-class
+builder (mmseq_b200/csrc/hits_loader.cpp), replacing src/hitsio.cpp:250-447 and
+src/mmseq.cpp:395-441 of the reference."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmq_host.so")
+
+LAYOUT_COLLAPSED = 0
+LAYOUT_PER_FRAGMENT = 1
+LAYOUT_PER_FRAGMENT_SORTED = 2
+LAYOUT_IDENTITY_COLUMNS = 16
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run `make hostlib`")
+        L = C.CDLL(LIB_PATH)
+        vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+        L.mmqh_load.restype = vp
+        L.mmqh_load.argtypes = [C.c_char_p, i32, C.c_char_p, i32]
+        L.mmqh_from_records.restype = vp
+        L.mmqh_from_records.argtypes = [i64, vp, i64, vp, vp, vp, i32, C.c_char_p, i32]
+        L.mmqh_free.restype = None
+        L.mmqh_free.argtypes = [vp]
+        L.mmqh_dim.restype = i64
+        L.mmqh_dim.argtypes = [vp, i32]
+        for nm in ["row_ptr", "col", "k", "w", "col2hdr", "hdr2col", "doublehits", "efflen", "truelen", "gene_of",
+                   "gene_ptr", "gene_members", "ident_ptr", "ident_members"]:
+            f = getattr(L, "mmqh_" + nm)
+            f.restype = vp
+            f.argtypes = [vp]
+        L.mmqh_name.restype = C.c_char_p
+        L.mmqh_name.argtypes = [vp, i64]
+        L.mmqh_gene_name.restype = C.c_char_p
+        L.mmqh_gene_name.argtypes = [vp, i64]
+        L.mmqh_scaled_len.restype = i32
+        L.mmqh_scaled_len.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+def _arr(ptr, n, dtype):
+    if not ptr or n == 0:
+        return None if not ptr else np.zeros(0, dtype)
+    ct = {np.int64: C.c_int64, np.int32: C.c_int32, np.float32: C.c_float, np.float64: C.c_double}[dtype]
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+
+
+class Hits:
+    """Header tables + hit-class CSR of one hits file (or of in-memory records)."""
+
+    def __init__(self, handle, with_names=True):
+        L = lib()
+        d = lambda w: int(L.mmqh_dim(handle, w))
+        self.T, self.G, self.I, self.N, self.n, self.m, self.nnz, self.n_classes, self.schema = [d(i) for i in range(9)]
+        self.row_ptr = _arr(L.mmqh_row_ptr(handle), self.m + 1, np.int64)
+        self.col = _arr(L.mmqh_col(handle), self.nnz, np.int32)
+        self.k = _arr(L.mmqh_k(handle), self.m, np.int32)
+        self.w = _arr(L.mmqh_w(handle), self.nnz, np.float32)
+        self.col2hdr = _arr(L.mmqh_col2hdr(handle), self.n, np.int32)
+        self.hdr2col = _arr(L.mmqh_hdr2col(handle), self.T, np.int32)
+        self.doublehits = _arr(L.mmqh_doublehits(handle), self.n, np.int32)
+        self.efflen = _arr(L.mmqh_efflen(handle), self.T, np.float64)
+        self.truelen = _arr(L.mmqh_truelen(handle), self.T, np.int32) if with_names else None
+        self.len = np.zeros(self.n)
+        if L.mmqh_scaled_len(handle, self.len.ctypes.data_as(C.c_void_p)):
+            raise RuntimeError("Error: transcript has a length of zero.")
+        if with_names:
+            self.names = [L.mmqh_name(handle, t).decode() for t in range(self.T)]
+            self.gene_names = [L.mmqh_gene_name(handle, g).decode() for g in range(self.G)]
+            self.gene_of = _arr(L.mmqh_gene_of(handle), self.T, np.int32)
+            self.gene_ptr = _arr(L.mmqh_gene_ptr(handle), self.G + 1, np.int64)
+            self.gene_members = _arr(L.mmqh_gene_members(handle), int(self.gene_ptr[-1]), np.int32)
+            self.ident_ptr = _arr(L.mmqh_ident_ptr(handle), self.I + 1, np.int64)
+            self.ident_members = _arr(L.mmqh_ident_members(handle), int(self.ident_ptr[-1]), np.int32)
+        L.mmqh_free(handle)
+
+
+def load_hits(path, layout=LAYOUT_COLLAPSED):
+    err = C.create_string_buffer(512)
+    h = lib().mmqh_load(os.fsencode(path), layout, err, 512)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    return Hits(h)
+
+
+def from_records(T, efflen, frag_ptr, frag_tid, frag_w=None, layout=LAYOUT_COLLAPSED):
+    efflen = np.ascontiguousarray(efflen, np.float64)
+    frag_ptr = np.ascontiguousarray(frag_ptr, np.int64)
+    frag_tid = np.ascontiguousarray(frag_tid, np.int32)
+    fw = None if frag_w is None else np.ascontiguousarray(frag_w, np.float32)
+    err = C.create_string_buffer(512)
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    h = lib().mmqh_from_records(T, p(efflen), len(frag_ptr) - 1, p(frag_ptr), p(frag_tid), p(fw), layout, err, 512)
+    if not h:
+        raise RuntimeError(err.value.decode())
+    return Hits(h, with_names=False)

@@ -1,0 +1,567 @@
+/* mmseq_oracle.cpp — CPU ORACLE for the mmseq EM + Gibbs hot path.
+ *
+ * TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library.
+ * The product (mmseq_b200/csrc, the `mmseq` host program) never links, imports
+ * or executes anything under oracle/.
+ *
+ * PARITY STATUS: "parity unpinned" for everything except sokal().  The
+ * reference (eturro/mmseq 1.0.11, /root/reference) ships no tests, golden
+ * vectors or fixtures for this path (test.sh:1-8 only runs make), and
+ * src/mmseq.cpp cannot be compiled here (needs Boost uBLAS/iostreams and GSL,
+ * both absent).  src/sokal.cc is self-contained and IS compiled from where it
+ * lies into oracle/_ref/ (see oracle/Makefile); orc_sokal below is pinned
+ * against it in tests/test_oracle_sokal.py.  Everything else is a restatement
+ * anchored on the reference's own call sites, cited per function, plus the
+ * analytic known answers listed in SURVEY.md section 4.
+ *
+ * Third-party arithmetic the reference takes from GSL (unpinned version,
+ * src/Makefile:16 -lgsl; .travis.yml:12 libgsl-dev on bionic => 2.4) is
+ * restated here from the published algorithms:
+ *   gsl_rng_mt19937       Matsumoto & Nishimura 1998 (std::mt19937 is the same
+ *                         generator and the same 2002 seeding recurrence)
+ *   gsl_ran_multinomial   conditional binomials (Davis 1993), zero categories skipped
+ *   gsl_ran_binomial      BTPE (Kachitvichyanukul & Schmeiser 1988), inversion below mean 14
+ *   gsl_ran_gamma         Marsaglia & Tsang 2000; a<1 boost U^(1/a)
+ *   gsl_ran_gaussian*     GSL uses a ziggurat inside gsl_ran_gamma; the polar
+ *                         method is used here (same distribution, other stream)
+ * Two Gibbs chains are provided:
+ *   orc_gibbs_replay   the shared Philox stream of include/mmq_sampler.h, same
+ *                      arithmetic as the kernels => integer outputs bit-exact
+ *   orc_gibbs_gsl      the reference's own data flow (src/mmseq.cpp:851-918):
+ *                      one MT19937 per OpenMP thread seeded seed+thread, dense
+ *                      per-thread count partials summed after a barrier; used
+ *                      for statistical comparison and as the CPU baseline.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/mmq_sampler.h"
+
+extern "C" {
+
+/* ------------------------------------------------------------------------
+ * Philox known-answer hook (Random123 kat_vectors: philox4x32 10 rounds). */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c[4] = {ctr[0], ctr[1], ctr[2], ctr[3]};
+  mmq_philox4x32_10(c, key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = c[i];
+}
+
+/* Sampler hooks for distribution tests (shared-header samplers). */
+void orc_draw_uniform(uint32_t seed, int64_t cnt, double* out) {
+  for (int64_t i = 0; i < cnt; ++i) {
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)i, 0);
+    out[i] = mmq_uniform(&g);
+  }
+}
+void orc_draw_gamma(uint32_t seed, int64_t cnt, double a, double rate, double* out) {
+  for (int64_t i = 0; i < cnt; ++i) {
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)i, 0);
+    out[i] = mmq_gamma(&g, a, rate);
+  }
+}
+void orc_draw_binomial(uint32_t seed, int64_t cnt, int64_t n, double p, int64_t* out) {
+  for (int64_t i = 0; i < cnt; ++i) {
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, (uint64_t)i, 0);
+    out[i] = mmq_binomial(&g, n, p);
+  }
+}
+void orc_draw_alloc(uint32_t seed, int64_t cnt, int d, const double* p, int64_t k, int32_t* out) {
+  for (int64_t i = 0; i < cnt; ++i) mmq_alloc_row(p, out + i * d, d, k, seed, (uint64_t)i, 0);
+}
+void orc_math(int which, int64_t cnt, const double* in, double* out) {
+  for (int64_t i = 0; i < cnt; ++i)
+    out[i] = which == 0 ? mmq_log(in[i]) : which == 1 ? mmq_exp(in[i]) : which == 2 ? mmq_ndtri(in[i]) : mmq_log1p(in[i]);
+}
+
+/* ------------------------------------------------------------------------
+ * Initial mu and the shared-count histogram.  src/mmseq.cpp:610-638:
+ *   mu[t] = (sum over classes i containing t of k[i]/|i|) / l[t]
+ *   counts_shared[t][min(|i|,100)-1] += k[i]      (bin 0 = unique_hits)
+ * The reference walks column t of M top to bottom, i.e. classes in ascending
+ * row index; the same summation order is used here. */
+void orc_init_mu(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+                 const double* l, double* mu, int32_t* unique_hits, int32_t* counts_shared) {
+  for (int64_t t = 0; t < n; ++t) mu[t] = 0.0;
+  if (unique_hits) for (int64_t t = 0; t < n; ++t) unique_hits[t] = 0;
+  if (counts_shared) std::memset(counts_shared, 0, sizeof(int32_t) * (size_t)n * 100);
+  for (int64_t i = 0; i < m; ++i) {
+    const int64_t d = rp[i + 1] - rp[i];
+    const int32_t ki = k ? k[i] : 1;
+    for (int64_t q = rp[i]; q < rp[i + 1]; ++q) {
+      const int32_t t = col[q];
+      mu[t] += (double)ki / (double)d;
+      if (counts_shared) counts_shared[(size_t)t * 100 + (size_t)std::min<int64_t>(d, 100) - 1] += ki;
+      if (unique_hits && d == 1) unique_hits[t] += ki;
+    }
+  }
+  for (int64_t t = 0; t < n; ++t) mu[t] /= l[t];
+}
+
+/* inner_prod(row i of M, mu): ascending column order (uBLAS sparse row iteration). */
+static inline double row_dot(const int64_t* rp, const int32_t* col, const float* w, const double* mu, int64_t i) {
+  double s = 0.0;
+  if (w) for (int64_t q = rp[i]; q < rp[i + 1]; ++q) s += (double)w[q] * mu[col[q]];
+  else for (int64_t q = rp[i]; q < rp[i + 1]; ++q) s += mu[col[q]];
+  return s;
+}
+
+/* Log-likelihood.  src/mmseq.cpp:745-754 (and :796-802):
+ *   sum_i k[i] log(inner_prod(M_i, mu)) - sum_t mu[t] l[t] */
+double orc_loglik(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+                  const float* w, const double* l, const double* mu) {
+  double ll = 0.0;
+  for (int64_t i = 0; i < m; ++i) ll += (double)(k ? k[i] : 1) * std::log(row_dot(rp, col, w, mu, i));
+  for (int64_t t = 0; t < n; ++t) ll -= mu[t] * l[t];
+  return ll;
+}
+
+/* EM.  src/mmseq.cpp:756-811.  llr starts at epsilon+1; loop while
+ * iter < max_em_iter && llr > epsilon; update
+ *   mu'[t] = mu[t] * (sum_{i containing t} k[i] / inner_prod(M_i, mu)) / l[t]     (:781-794)
+ * with classes visited in ascending row index (row t of Mt).  The reference
+ * recomputes inner_prod for every (t,i) pair; the value is the same number
+ * every time, so it is computed once per class here.  Returns the number of
+ * iterations; *loglik_out = final log-likelihood. */
+int orc_em(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+           const float* w, const double* l, double* mu, int max_iter, double eps,
+           double* loglik_out, double* llr_out) {
+  const int64_t nnz = rp[m];
+  /* transposed structure: for each t the classes containing it, ascending */
+  std::vector<int64_t> tp((size_t)n + 1, 0);
+  for (int64_t q = 0; q < nnz; ++q) tp[(size_t)col[q] + 1]++;
+  for (int64_t t = 0; t < n; ++t) tp[(size_t)t + 1] += tp[(size_t)t];
+  std::vector<int64_t> trow((size_t)nnz), tpos((size_t)nnz), fill(tp.begin(), tp.end() - 1);
+  for (int64_t i = 0; i < m; ++i)
+    for (int64_t q = rp[i]; q < rp[i + 1]; ++q) {
+      int64_t dst = fill[(size_t)col[q]]++;
+      trow[(size_t)dst] = i;
+      tpos[(size_t)dst] = q;
+    }
+  std::vector<double> D((size_t)m), mu_temp((size_t)n);
+  double loglik = orc_loglik(m, n, rp, col, k, w, l, mu);
+  double llr = eps + 1.0;
+  int iter = 0;
+  while (iter < max_iter && llr > eps) {
+    for (int64_t i = 0; i < m; ++i) D[(size_t)i] = row_dot(rp, col, w, mu, i);
+    for (int64_t t = 0; t < n; ++t) {
+      double sum = 0.0;
+      for (int64_t q = tp[(size_t)t]; q < tp[(size_t)t + 1]; ++q) {
+        const int64_t i = trow[(size_t)q];
+        const double ki = (double)(k ? k[i] : 1);
+        sum += (w ? ki * (double)w[tpos[(size_t)q]] : ki) / D[(size_t)i];
+      }
+      mu_temp[(size_t)t] = mu[t] * sum / l[t];
+    }
+    const double ll2 = orc_loglik(m, n, rp, col, k, w, l, mu_temp.data());
+    for (int64_t t = 0; t < n; ++t) mu[t] = mu_temp[(size_t)t];
+    llr = ll2 - loglik;
+    loglik = ll2;
+    ++iter;
+  }
+  if (loglik_out) *loglik_out = loglik;
+  if (llr_out) *llr_out = llr;
+  return iter;
+}
+
+/* ------------------------------------------------------------------------
+ * Gibbs, shared Philox stream (CPU replay of the kernels).
+ * One sweep = src/mmseq.cpp:857-908:
+ *   x_i ~ Multinomial(k[i]; mu[cols(i)])              (:865-880)
+ *   counts[t] = sum_i x_it                             (:887, :895-899)
+ *   mu[t] ~ Gamma(alpha + counts[t], 1/(beta + l[t]))  (:904-908)
+ * x (nnz ints, CSR order) and counts are optional outputs of this sweep. */
+void orc_sweep_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+                      const float* w, const double* l, double alpha, double beta, uint32_t seed,
+                      uint32_t sweep, int64_t class_id_base, double* mu, int32_t* x_out,
+                      int32_t* counts_out, int do_gamma) {
+  std::vector<int32_t> counts((size_t)n, 0);
+  std::vector<double> p;
+  std::vector<int32_t> x;
+  for (int64_t i = 0; i < m; ++i) {
+    const int d = (int)(rp[i + 1] - rp[i]);
+    p.resize((size_t)d);
+    x.resize((size_t)d);
+    for (int j = 0; j < d; ++j) {
+      const int64_t q = rp[i] + j;
+      p[(size_t)j] = w ? mu[col[q]] * (double)w[q] : mu[col[q]];
+    }
+    mmq_alloc_row(p.data(), x.data(), d, (int64_t)(k ? k[i] : 1), seed, (uint64_t)(class_id_base + i), sweep);
+    for (int j = 0; j < d; ++j) {
+      const int64_t q = rp[i] + j;
+      counts[(size_t)col[q]] += x[(size_t)j];
+      if (x_out) x_out[q] = x[(size_t)j];
+    }
+  }
+  if (counts_out) for (int64_t t = 0; t < n; ++t) counts_out[t] = counts[(size_t)t];
+  if (do_gamma)
+    for (int64_t t = 0; t < n; ++t) {
+      mmq_rng g;
+      mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
+      mu[t] = mmq_gamma(&g, alpha + (double)counts[(size_t)t], beta + l[t]);
+    }
+}
+
+/* Gamma step alone from given counts (used for the multi-shard replay). */
+void orc_gamma_replay(int64_t n, const int32_t* counts, const double* l, double alpha, double beta,
+                      uint32_t seed, uint32_t sweep, double* mu) {
+  for (int64_t t = 0; t < n; ++t) {
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
+    mu[t] = mmq_gamma(&g, alpha + (double)counts[t], beta + l[t]);
+  }
+}
+
+/* n_sweeps sweeps starting at first_sweep; every sweep with sweep % stride == 0
+ * stores mu into trace[t*trace_len + sweep/stride]   (src/mmseq.cpp:911-917). */
+void orc_gibbs_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+                      const float* w, const double* l, double alpha, double beta, uint32_t seed,
+                      int64_t first_sweep, int64_t n_sweeps, int stride, int trace_len, double* mu,
+                      double* trace) {
+  for (int64_t s = first_sweep; s < first_sweep + n_sweeps; ++s) {
+    orc_sweep_replay(m, n, rp, col, k, w, l, alpha, beta, seed, (uint32_t)s, 0, mu, nullptr, nullptr, 1);
+    if (trace && s % stride == 0 && s / stride < trace_len)
+      for (int64_t t = 0; t < n; ++t) trace[t * trace_len + s / stride] = mu[t];
+  }
+}
+
+/* Prior draws for transcripts without hits: Gamma(alpha, 1/(beta + len*N/1e9)),
+ * src/mmseq.cpp:971-978.  Stream: (seed, PRIOR, header index, slot). */
+void orc_prior_replay(int64_t cnt, const int64_t* ids, const double* lscaled, double alpha, double beta,
+                      uint32_t seed, int trace_len, double* out) {
+  for (int64_t u = 0; u < cnt; ++u)
+    for (int s = 0; s < trace_len; ++s) {
+      mmq_rng g;
+      mmq_rng_init(&g, seed, MMQ_STREAM_PRIOR, (uint64_t)ids[u], (uint32_t)s);
+      out[u * trace_len + s] = mmq_gamma(&g, alpha, beta + lscaled[u]);
+    }
+}
+
+} /* extern "C" */
+
+/* ------------------------------------------------------------------------
+ * GSL-style samplers on MT19937 (independent of mmq_sampler.h). */
+namespace gsl_like {
+
+struct Rng {
+  std::mt19937 mt;
+  explicit Rng(uint32_t seed) : mt(seed == 0 ? 4357u : seed) {}
+  double uniform() { return mt() / 4294967296.0; }                    /* gsl_rng_uniform */
+  double uniform_pos() { double x; do { x = uniform(); } while (x == 0.0); return x; }
+};
+
+static double gaussian(Rng& r) { /* polar (Box-Muller, Marsaglia) as gsl_ran_gaussian */
+  double x, y, r2;
+  do {
+    x = -1.0 + 2.0 * r.uniform_pos();
+    y = -1.0 + 2.0 * r.uniform_pos();
+    r2 = x * x + y * y;
+  } while (r2 > 1.0 || r2 == 0.0);
+  return y * std::sqrt(-2.0 * std::log(r2) / r2);
+}
+
+static double gamma(Rng& r, double a, double b) { /* gsl_ran_gamma(r, a, b): shape a, scale b */
+  if (a < 1.0) {
+    double u = r.uniform_pos();
+    return gamma(r, 1.0 + a, b) * std::pow(u, 1.0 / a);
+  }
+  double x, v, u;
+  const double d = a - 1.0 / 3.0;
+  const double c = (1.0 / 3.0) / std::sqrt(d);
+  for (;;) {
+    do {
+      x = gaussian(r);
+      v = 1.0 + c * x;
+    } while (v <= 0.0);
+    v = v * v * v;
+    u = r.uniform_pos();
+    if (u < 1.0 - 0.0331 * x * x * x * x) break;
+    if (std::log(u) < 0.5 * x * x + d * (1.0 - v + std::log(v))) break;
+  }
+  return b * d * v;
+}
+
+static inline double stirling_corr(double y1) { /* BTPE's series for the log-gamma correction */
+  const double y2 = y1 * y1;
+  return (13860.0 - (462.0 - (132.0 - (99.0 - 140.0 / y2) / y2) / y2) / y2) / y1 / 166320.0;
+}
+
+/* Binomial(n, p): BTPE (Kachitvichyanukul & Schmeiser 1988) for n*min(p,1-p) >= 14,
+ * sequential inversion below that (the split GSL's binomial_tpe.c uses). */
+static unsigned int binomial(Rng& rng, double p, unsigned int n) {
+  if (n == 0) return 0;
+  bool flipped = false;
+  if (p > 0.5) { p = 1.0 - p; flipped = true; }
+  if (p <= 0.0) return flipped ? n : 0;
+  const double q = 1.0 - p;
+  const double s = p / q;
+  const double np = n * p;
+  int ix;
+  if (np < 14.0) {
+    const double f0 = std::pow(q, (double)n);
+    for (;;) {
+      double f = f0;
+      double u = rng.uniform();
+      for (ix = 0; ix <= 110; ++ix) {
+        if (u < f) goto finish;
+        u -= f;
+        f *= s * (double)(n - ix) / (double)(ix + 1);
+      }
+    }
+  } else {
+    const double ffm = np + p;
+    const int m = (int)ffm;
+    const double xm = m + 0.5;
+    const double npq = np * q;
+    const double p1 = std::floor(2.195 * std::sqrt(npq) - 4.6 * q) + 0.5;
+    const double xl = xm - p1;
+    const double xr = xm + p1;
+    const double c = 0.134 + 20.5 / (15.3 + (double)m);
+    const double p2 = p1 * (1.0 + c + c);
+    const double al = (ffm - xl) / (ffm - xl * p);
+    const double lambda_l = al * (1.0 + 0.5 * al);
+    const double ar = (xr - ffm) / (xr * q);
+    const double lambda_r = ar * (1.0 + 0.5 * ar);
+    const double p3 = p2 + c / lambda_l;
+    const double p4 = p3 + c / lambda_r;
+    double var, accept, u, v;
+    for (;;) {
+      u = rng.uniform() * p4;
+      v = rng.uniform();
+      if (u <= p1) { /* triangular region */
+        ix = (int)(xm - p1 * v + u);
+        goto finish;
+      } else if (u <= p2) { /* parallelogram */
+        const double x = xl + (u - p1) / c;
+        v = v * c + 1.0 - std::fabs(x - xm) / p1;
+        if (v > 1.0 || v <= 0.0) continue;
+        ix = (int)x;
+      } else if (u <= p3) { /* left tail */
+        ix = (int)(xl + std::log(v) / lambda_l);
+        if (ix < 0) continue;
+        v *= ((u - p2) * lambda_l);
+      } else { /* right tail */
+        ix = (int)(xr - std::log(v) / lambda_r);
+        if (ix > (double)n) continue;
+        v *= ((u - p3) * lambda_r);
+      }
+      const int k = std::abs(ix - m);
+      if (k <= 20) { /* explicit evaluation of f(ix)/f(m) */
+        const double g = (n + 1) * s;
+        double f = 1.0;
+        var = v;
+        if (m < ix) { for (int i = m + 1; i <= ix; ++i) f *= (g / i - s); }
+        else if (m > ix) { for (int i = ix + 1; i <= m; ++i) f /= (g / i - s); }
+        accept = f;
+      } else { /* squeeze using upper and lower bounds on log(f(x)) */
+        var = std::log(v);
+        if (k < npq / 2 - 1) {
+          const double amaxp = k / npq * ((k * (k / 3.0 + 0.625) + (1.0 / 6.0)) / npq + 0.5);
+          const double ynorm = -(double)k * k / (2.0 * npq);
+          if (var < ynorm - amaxp) goto finish;
+          if (var > ynorm + amaxp) continue;
+        }
+        const double x1 = ix + 1.0;
+        const double w = n - ix + 1.0;
+        const double f1 = m + 1.0;
+        const double z = n + 1.0 - m;
+        accept = xm * std::log(f1 / x1) + (n - m + 0.5) * std::log(z / w) +
+                 (ix - m) * std::log(w * p / (x1 * q)) + stirling_corr(f1) + stirling_corr(z) +
+                 stirling_corr(x1) + stirling_corr(w);
+      }
+      if (var <= accept) goto finish;
+    }
+  }
+finish:
+  return flipped ? (n - (unsigned int)ix) : (unsigned int)ix;
+}
+
+/* gsl_ran_multinomial(r, K, N, p, n) */
+static void multinomial(Rng& r, size_t K, unsigned int N, const double* p, unsigned int* n) {
+  double norm = 0.0, sum_p = 0.0;
+  unsigned int sum_n = 0;
+  for (size_t k = 0; k < K; ++k) norm += p[k];
+  for (size_t k = 0; k < K; ++k) {
+    if (p[k] > 0.0) n[k] = binomial(r, p[k] / (norm - sum_p), N - sum_n);
+    else n[k] = 0;
+    sum_p += p[k];
+    sum_n += n[k];
+  }
+}
+
+} /* namespace gsl_like */
+
+extern "C" {
+
+void orc_gsl_binomial(uint32_t seed, int64_t cnt, int64_t n, double p, int64_t* out) {
+  gsl_like::Rng r(seed);
+  for (int64_t i = 0; i < cnt; ++i) out[i] = gsl_like::binomial(r, p, (unsigned int)n);
+}
+void orc_gsl_gamma(uint32_t seed, int64_t cnt, double a, double scale, double* out) {
+  gsl_like::Rng r(seed);
+  for (int64_t i = 0; i < cnt; ++i) out[i] = gsl_like::gamma(r, a, scale);
+}
+void orc_gsl_multinomial(uint32_t seed, int64_t cnt, int d, const double* p, int64_t k, int32_t* out) {
+  gsl_like::Rng r(seed);
+  std::vector<unsigned int> x((size_t)d);
+  for (int64_t i = 0; i < cnt; ++i) {
+    gsl_like::multinomial(r, (size_t)d, (unsigned int)k, p, x.data());
+    for (int j = 0; j < d; ++j) out[i * d + j] = (int32_t)x[(size_t)j];
+  }
+}
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* The reference's Gibbs loop with its own data flow, src/mmseq.cpp:834-918:
+ *   rg[i] = mt19937 seeded seed+i, one per thread                         (:834-838)
+ *   per sweep: memset Xcolsum and the n*threads partials                   (:854-855)
+ *   omp for schedule(static) over classes: p = mu[cols], gsl_ran_multinomial,
+ *     store x, Xcolsums[t + n*thread] += x                                 (:864-891)
+ *   barrier; Xcolsum[t] = sum over threads                                 (:893-899)
+ *   mu[t] = gsl_ran_gamma(rg[thread], alpha + Xcolsum[t], 1/(beta+l[t]))   (:904-908)
+ *   every stride-th sweep from 0: trace[t*L + sweep/stride] = mu[t]        (:911-917)
+ * x_store (nnz ints) stands for the write-only X matrix.  Returns seconds
+ * spent in the sweep loop.  threads <= 0 means omp_get_max_threads(). */
+double orc_gibbs_gsl(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+                     const double* l, double alpha, double beta, int seed, int threads,
+                     int64_t n_sweeps, int stride, int trace_len, double* mu, double* trace) {
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+  const int64_t nnz = rp[m];
+  std::vector<gsl_like::Rng> rg;
+  for (int i = 0; i < threads; ++i) rg.emplace_back((uint32_t)(seed + i));
+  std::vector<int> Xcolsum((size_t)n), Xcolsums((size_t)n * (size_t)threads);
+  std::vector<int32_t> x_store((size_t)nnz);
+  int64_t maxd = 1;
+  for (int64_t i = 0; i < m; ++i) maxd = std::max<int64_t>(maxd, rp[i + 1] - rp[i]);
+  auto t0 = std::chrono::steady_clock::now();
+  for (int64_t iter = 0; iter < n_sweeps; ++iter) {
+    std::memset(Xcolsum.data(), 0, sizeof(int) * (size_t)n);
+    std::memset(Xcolsums.data(), 0, sizeof(int) * (size_t)n * (size_t)threads);
+#pragma omp parallel num_threads(threads)
+    {
+#ifdef _OPENMP
+      const int tid = omp_get_thread_num();
+#else
+      const int tid = 0;
+#endif
+      std::vector<double> p((size_t)maxd);
+      std::vector<unsigned int> x((size_t)maxd);
+#pragma omp for schedule(static)
+      for (int64_t i = 0; i < m; ++i) {
+        const int64_t d = rp[i + 1] - rp[i];
+        for (int64_t j = 0; j < d; ++j) p[(size_t)j] = mu[col[rp[i] + j]];
+        gsl_like::multinomial(rg[(size_t)tid], (size_t)d, (unsigned int)(k ? k[i] : 1), p.data(), x.data());
+        for (int64_t j = 0; j < d; ++j) {
+          x_store[(size_t)(rp[i] + j)] = (int32_t)x[(size_t)j];
+          Xcolsums[(size_t)col[rp[i] + j] + (size_t)n * (size_t)tid] += (int)x[(size_t)j];
+        }
+      }
+      /* implicit barrier of the omp for */
+#pragma omp for schedule(static)
+      for (int64_t t = 0; t < n; ++t)
+        for (int i = 0; i < threads; ++i) Xcolsum[(size_t)t] += Xcolsums[(size_t)t + (size_t)i * (size_t)n];
+#pragma omp for schedule(static)
+      for (int64_t t = 0; t < n; ++t)
+        mu[t] = gsl_like::gamma(rg[(size_t)tid], alpha + Xcolsum[(size_t)t], 1.0 / (beta + l[t]));
+    }
+    if (trace && iter % stride == 0 && iter / stride < trace_len)
+      for (int64_t t = 0; t < n; ++t) trace[t * trace_len + iter / stride] = mu[t];
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+/* ------------------------------------------------------------------------
+ * Sokal.  src/sokal.cc:33-87 restated with a plain iterative radix-2 FFT in
+ * place of the reference's radix-4 routine (:96-293): FFT(x) -> power spectrum
+ * -> DC bin zeroed -> FFT again (n * circular autocovariance) ->
+ * var = acov0/(n(n-1)); normalise; sum = -1/3; for i: sum += rho_i - 1/6, stop
+ * at the first sum < 0 with m = i+1; tau = 2(sum + (m-1)/6).  x is destroyed.
+ * Return codes as the reference: 100 n > 2^21, 200 n < 4, 201 not a power of 2. */
+static void fft_radix2(std::vector<double>& re, std::vector<double>& im) {
+  const size_t n = re.size();
+  for (size_t i = 1, j = 0; i < n; ++i) {
+    size_t bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) { std::swap(re[i], re[j]); std::swap(im[i], im[j]); }
+  }
+  for (size_t len = 2; len <= n; len <<= 1) {
+    const double ang = -2.0 * M_PI / (double)len;
+    for (size_t i = 0; i < n; i += len)
+      for (size_t j = 0; j < len / 2; ++j) {
+        const double wr = std::cos(ang * (double)j), wi = std::sin(ang * (double)j);
+        const size_t a = i + j, b = i + j + len / 2;
+        const double xr = re[b] * wr - im[b] * wi, xi = re[b] * wi + im[b] * wr;
+        re[b] = re[a] - xr; im[b] = im[a] - xi;
+        re[a] += xr; im[a] += xi;
+      }
+  }
+}
+
+int orc_sokal(int n, double* x, double* var, double* tau, int* m) {
+  if (n > (2 << 20)) return 100;
+  if (n < 4) return 200;
+  for (int t = n; t > 1; t >>= 1) if (t & 1) return 201;
+  std::vector<double> re(x, x + n), im((size_t)n, 0.0);
+  fft_radix2(re, im);
+  for (int i = 0; i < n; ++i) { re[(size_t)i] = re[(size_t)i] * re[(size_t)i] + im[(size_t)i] * im[(size_t)i]; im[(size_t)i] = 0.0; }
+  re[0] = 0.0;
+  fft_radix2(re, im);
+  *var = re[0] / ((double)n * (n - 1));
+  const double c = 1.0 / re[0];
+  for (int i = 0; i < n; ++i) x[i] = re[(size_t)i] * c;
+  double sum = -0.333333333333333333333;
+  *m = n + 1;
+  for (int i = 0; i < n; ++i) {
+    sum += x[i] - 0.166666666666666666666;
+    if (sum < 0) { *m = i + 1; break; }
+  }
+  *tau = 2 * (sum + (*m - 1.0) / 6.0);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------
+ * uh().  src/uh.cpp:3-26: for every set s, sum k[i] over the classes whose
+ * members ALL lie in s.  Literal restatement (every set scans every class) —
+ * small inputs only.  Membership is given as set_ptr/set_members (a transcript
+ * may be in several sets in principle; genes and identical sets are disjoint). */
+void orc_uh_literal(int64_t m, const int64_t* rp, const int32_t* col, const int32_t* k, int64_t nsets,
+                    const int64_t* set_ptr, const int32_t* set_members, int32_t* out) {
+  for (int64_t s = 0; s < nsets; ++s) {
+    out[s] = 0;
+    for (int64_t i = 0; i < m; ++i) {
+      bool uniq = true;
+      for (int64_t q = rp[i]; q < rp[i + 1] && uniq; ++q) {
+        bool in = false;
+        for (int64_t e = set_ptr[s]; e < set_ptr[s + 1]; ++e) if (set_members[e] == col[q]) { in = true; break; }
+        if (!in) uniq = false;
+      }
+      if (uniq) out[s] += k ? k[i] : 1;
+    }
+  }
+}
+
+} /* extern "C" */

@@ -1,0 +1,182 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.
+  (a) allocations X, counts and the Gamma draws: BIT-EXACT with the shared Philox stream
+  (b) EM: relative 1e-6 (north_star), same iteration count
+  (c) posterior mean / sd of log mu vs the GSL-style reference-like chain: within Monte-Carlo error
+"""
+import numpy as np
+import pytest
+
+from mmseq_b200 import capi, hostlib
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+SEED = 1234
+
+
+def _handle(h, **kw):
+    return capi.Handle(h.row_ptr, h.col, h.k, h.len, weight=h.w, **kw)
+
+
+def _oracle(h, **kw):
+    return orc.Problem(h.row_ptr, h.col, h.k, h.len, weight=h.w, **kw)
+
+
+def test_init_mu_and_unique_hits(small_problem):
+    h = small_problem
+    mu_o, uh_o, _ = _oracle(h).init_mu()
+    with _handle(h) as H:
+        uh = H.init_mu()
+        mu = H.get_mu()
+    assert np.array_equal(uh, uh_o)
+    assert np.allclose(mu, mu_o, rtol=1e-12)
+
+
+def test_loglik_and_em_match_oracle(small_problem):
+    h = small_problem
+    P = _oracle(h)
+    mu0, _, _ = P.init_mu()
+    mu_o, it_o, ll_o, llr_o = P.em(mu0, 1000, 0.1)
+    with _handle(h) as H:
+        H.init_mu()
+        assert np.isclose(H.loglik(), P.loglik(mu0), rtol=1e-12)
+        it, ll, llr = H.em(1000, 0.1)
+        mu = H.get_mu()
+    assert it == it_o
+    assert np.max(np.abs(mu / mu_o - 1)) <= 1e-6          # north_star (b)
+    assert np.isclose(ll, ll_o, rtol=1e-10) and abs(llr - llr_o) < 1e-6 * abs(ll_o)
+    assert np.isclose((mu * h.len).sum(), h.N, rtol=1e-10)  # EM mass conservation
+
+
+@pytest.mark.parametrize("layout", ["collapsed", "per_fragment"])
+def test_sweep_bit_exact_vs_cpu_replay(small_problem, small_problem_pf, layout):
+    h = small_problem if layout == "collapsed" else small_problem_pf
+    P = _oracle(h)
+    mu, _, _ = P.init_mu()
+    with _handle(h) as H:
+        H.set_mu(mu)
+        for sweep in range(4):
+            x_o, c_o, mu_o = P.sweep_replay(mu, SEED, sweep)
+            x, c, mu_g = H.sweep_debug(SEED, sweep, capi.MMQ_GIBBS_TRANSPOSED)
+            assert np.array_equal(x, x_o), f"X differs at sweep {sweep}"
+            assert np.array_equal(c, c_o)
+            assert c.sum() == h.N                                   # per-sweep conservation
+            kk = h.k if h.k is not None else np.ones(h.m, np.int32)
+            assert np.array_equal(np.add.reduceat(x, h.row_ptr[:-1]), kk)   # per-class conservation
+            assert np.array_equal(mu_g, mu_o), "Gamma draws not bit-exact"
+            mu = mu_o
+        # the fused (reduction) path produces the same integers and the same chain
+        H.set_mu(mu)
+        _, c_f, mu_f = H.sweep_debug(SEED, 4, capi.MMQ_GIBBS_DEFAULT)
+        _, c_o, mu_o = P.sweep_replay(mu, SEED, 4)
+        assert np.array_equal(c_f, c_o) and np.array_equal(mu_f, mu_o)
+
+
+def test_weighted_rows_bit_exact(small_synth):
+    s = small_synth
+    rng = np.random.default_rng(3)
+    w = np.exp(0.5 * rng.standard_normal(len(s.frag_tid))).astype(np.float32)
+    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=w, layout=hostlib.LAYOUT_PER_FRAGMENT)
+    assert h.w is not None
+    P = _oracle(h)
+    mu, _, _ = P.init_mu()
+    with _handle(h) as H:
+        H.set_mu(mu)
+        for sweep in range(2):
+            x_o, c_o, mu_o = P.sweep_replay(mu, SEED, sweep)
+            x, c, mu_g = H.sweep_debug(SEED, sweep, capi.MMQ_GIBBS_TRANSPOSED)
+            assert np.array_equal(x, x_o) and np.array_equal(c, c_o) and np.array_equal(mu_g, mu_o)
+            mu = mu_o
+        mu_o2, it_o, ll_o, _ = P.em(P.init_mu()[0], 50, 0.1)
+        H.init_mu()
+        it, ll, _ = H.em(50, 0.1)
+        assert it == it_o and np.max(np.abs(H.get_mu() / mu_o2 - 1)) <= 1e-6
+
+
+def test_trace_bit_exact_over_many_sweeps(small_problem):
+    h = small_problem
+    P = _oracle(h)
+    mu0, _, _ = P.init_mu()
+    mu_o, tr_o = P.gibbs_replay(mu0, SEED, 0, 64, 4, 16)
+    for flags in (capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_TRANSPOSED):
+        with _handle(h) as H:
+            H.set_mu(mu0)
+            H.gibbs(SEED, 0, 40, stride=4, trace_len=16, flags=flags)
+            H.gibbs(SEED, 40, 24, stride=4, trace_len=16, flags=flags)   # restartable from (seed, sweep)
+            tr = H.get_trace()
+            assert np.array_equal(tr, tr_o)
+            assert np.array_equal(H.get_mu(), mu_o)
+
+
+def test_ragged_and_extreme_rows():
+    """Singletons, a row longer than the staging tile, huge k, tiny mu."""
+    rng = np.random.default_rng(11)
+    n = 5000
+    rows = [[0], [1], [0, 1], list(range(2, 2 + 3000)), [7, 9], [4999]]
+    rows += [sorted(rng.choice(n, size=int(d), replace=False).tolist()) for d in rng.integers(1, 40, 300)]
+    k = [2_000_000_000 // 4, 1, 123456, 777, 1, 5] + rng.integers(1, 5000, 300).tolist()
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])])
+    col = np.concatenate(rows).astype(np.int32)
+    l = rng.uniform(1e-6, 1e-2, n)
+    mu = rng.gamma(0.3, 100.0, n)
+    mu[:50] = 1e-300
+    mu[2] = 0.0                                # an exact zero inside a long row
+    P = orc.Problem(row_ptr, col, k, l)
+    with capi.Handle(row_ptr, col, k, l) as H:
+        for sweep in (0, 1, 2):
+            H.set_mu(mu)
+            x_o, c_o, mu_o = P.sweep_replay(mu, 99, sweep)
+            x, c, mu_g = H.sweep_debug(99, sweep, capi.MMQ_GIBBS_TRANSPOSED)
+            assert np.array_equal(x, x_o) and np.array_equal(c, c_o) and np.array_equal(mu_g, mu_o)
+            H.set_mu(mu)
+            _, c_f, _ = H.sweep_debug(99, sweep, capi.MMQ_GIBBS_DEFAULT)
+            assert np.array_equal(c_f, c_o)
+
+
+def test_class_id_base_shards_reproduce_the_whole(small_problem):
+    """Two shards on one GPU (handles are independent): summed counts == unsharded counts."""
+    h = small_problem
+    P = _oracle(h)
+    mu, _, _ = P.init_mu()
+    _, c_o, _ = P.sweep_replay(mu, SEED, 3)
+    cut = h.m // 3
+    parts = []
+    for a, b in ((0, cut), (cut, h.m)):
+        lo, hi = h.row_ptr[a], h.row_ptr[b]
+        with capi.Handle(h.row_ptr[a:b + 1] - lo, h.col[lo:hi], h.k[a:b], h.len, class_id_base=a) as H:
+            H.set_mu(mu)
+            parts.append(H.sweep_debug(SEED, 3, capi.MMQ_GIBBS_DEFAULT)[1])
+    assert np.array_equal(parts[0] + parts[1], c_o)
+
+
+def test_posterior_matches_reference_like_chain(small_problem):
+    """north_star (c): log_mu and sd within Monte-Carlo error of the GSL-style MT19937 chain."""
+    h = small_problem
+    P = _oracle(h)
+    mu0, _, _ = P.init_mu()
+    mu_em, _, _, _ = P.em(mu0, 1000, 0.1)
+    L, stride = 1024, 4
+    _, tr_ref, _ = P.gibbs_gsl(mu_em, SEED, L * stride, stride, L, threads=1)
+    with _handle(h) as H:
+        H.set_mu(mu_em)
+        H.gibbs(SEED, 0, L * stride, stride=stride, trace_len=L)
+        tr = H.get_trace()
+    a = orc.summaries_transcripts(tr)
+    b = orc.summaries_transcripts(tr_ref)
+    z = np.abs(a["log_mu"] - b["log_mu"]) / np.sqrt(a["mcse"] ** 2 + b["mcse"] ** 2)
+    assert np.mean(z <= 4.0) >= 0.99, np.sort(z)[-10:]
+    ratio = a["sd"] / b["sd"]
+    assert abs(np.median(ratio) - 1) < 0.05 and np.mean(np.abs(np.log(ratio)) < 0.5) > 0.97
+
+
+def test_errors_are_reported_not_fatal(small_problem):
+    h = small_problem
+    with _handle(h) as H:
+        with pytest.raises(capi.MmqError):
+            H.get_trace()                                          # no trace yet
+        with pytest.raises(capi.MmqError):
+            H.gibbs(SEED, 0, 4, stride=0, trace_len=8)
+    with pytest.raises(capi.MmqError):
+        capi.Handle(h.row_ptr, np.where(np.arange(h.nnz) == 5, h.n + 3, h.col), h.k, h.len)   # column out of range
+    with pytest.raises(capi.MmqError):
+        capi.Handle(h.row_ptr, h.col, h.k, np.where(np.arange(h.n) == 0, 0.0, h.len))          # zero length

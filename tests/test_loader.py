@@ -1,0 +1,105 @@
+"""The product's .hits loader / class builder (libmmq_host.so) against the
+Python restatement of the reference reader and of src/mmseq.cpp:395-441.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from mmseq_b200 import hostlib, synth
+from oracle import oracle as orc
+
+
+def _same(h, o):
+    assert (h.n, h.m, h.N) == (o["n"], o["m"], o["N"])
+    assert np.array_equal(h.row_ptr, o["row_ptr"]) and np.array_equal(h.col, o["col"]) and np.array_equal(h.k, o["k"])
+    assert [h.names[i] for i in h.col2hdr] == o["names_by_col"]
+    assert np.array_equal(h.doublehits, o["doublehits"])
+    assert np.allclose(h.len, o["len"], rtol=1e-15)
+
+
+@pytest.mark.parametrize("fmt", ["text", "binary"])
+def test_loader_matches_oracle_reader(tmp_path, small_synth, fmt):
+    s = small_synth
+    path = str(tmp_path / f"x.{fmt}.hits")
+    ident = [[0, 1], [5, 6, 7]]
+    (synth.write_hits_text if fmt == "text" else synth.write_hits_binary)(s, path, identical=ident)
+    h = hostlib.load_hits(path)
+    hf = orc.HitsFile(path)
+    assert h.schema == hf.schema == (0 if fmt == "text" else 1)
+    assert h.names == hf.names and h.T == s.T
+    assert np.allclose(h.efflen, [hf.efflen[n] for n in hf.names]) and list(h.truelen) == [hf.truelen[n] for n in hf.names]
+    assert h.gene_names == sorted(hf.genes)                      # std::map order
+    for g, name in enumerate(h.gene_names):
+        mem = [h.names[i] for i in h.gene_members[h.gene_ptr[g]:h.gene_ptr[g + 1]]]
+        assert mem == hf.genes[name]
+    assert [[h.names[i] for i in h.ident_members[h.ident_ptr[j]:h.ident_ptr[j + 1]]] for j in range(h.I)] == hf.identical
+    _same(h, orc.build_classes(hf))
+    assert h.k.sum() == s.N
+
+
+def test_text_and_binary_and_in_memory_agree(tmp_path, small_synth):
+    s = small_synth
+    a = str(tmp_path / "a.hits"); b = str(tmp_path / "b.hits")
+    synth.write_hits_text(s, a); synth.write_hits_binary(s, b)
+    ha, hb = hostlib.load_hits(a), hostlib.load_hits(b)
+    hc = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid)
+    for x in (hb, hc):
+        assert np.array_equal(ha.row_ptr, x.row_ptr) and np.array_equal(ha.col, x.col) and np.array_equal(ha.k, x.k)
+        assert np.allclose(ha.len, x.len)
+    assert os.path.getsize(b) < os.path.getsize(a) / 3            # "~7x" smaller per src/README.md:26
+
+
+def test_per_fragment_layouts_expand_the_same_classes(small_synth):
+    s = small_synth
+    c = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_COLLAPSED)
+    for layout in (hostlib.LAYOUT_PER_FRAGMENT, hostlib.LAYOUT_PER_FRAGMENT_SORTED):
+        p = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=layout)
+        assert p.m == s.N and p.k is None and p.n == c.n and p.n_classes == c.m
+        # every per-fragment row is one of the classes; multiplicities equal k
+        key = lambda rp, col, i: tuple(col[rp[i]:rp[i + 1]])
+        cls = {key(c.row_ptr, c.col, i): i for i in range(c.m)}
+        cnt = np.zeros(c.m, np.int64)
+        ids = [cls[key(p.row_ptr, p.col, i)] for i in range(p.m)]
+        np.add.at(cnt, ids, 1)
+        assert np.array_equal(cnt, c.k)
+        if layout == hostlib.LAYOUT_PER_FRAGMENT_SORTED:
+            assert ids == sorted(ids)
+
+
+def test_duplicates_and_first_appearance_order(tmp_path):
+    txt = ("@TranscriptMetaData\tA\t1000\t1180\n@TranscriptMetaData\tB\t500.5\t680\n@TranscriptMetaData\tC\t2000\t2180\n"
+           "@TranscriptMetaData\tD\t100\t280\n@GeneIsoforms\tg2\tC\tD\n@GeneIsoforms\tg1\tA\tB\n@IdenticalTranscripts\tA\tB\n"
+           ">r1\nC\nA\n>r2\nA\nC\nA\n>r3\nB\n>r4\nA\nC\n>r5\n")
+    p = tmp_path / "t.hits"
+    p.write_text(txt)
+    h = hostlib.load_hits(str(p))
+    assert h.N == 4                                    # the trailing empty record is dropped with a warning
+    assert [h.names[i] for i in h.col2hdr] == ["C", "A", "B"]   # first appearance; D never hit => not a column
+    assert list(h.hdr2col) == [1, 2, 0, -1]
+    assert list(h.row_ptr) == [0, 2, 3] and list(h.col) == [0, 1, 2] and list(h.k) == [3, 1]
+    assert list(h.doublehits) == [0, 1, 0]
+    assert h.gene_names == ["g1", "g2"]
+    assert np.allclose(h.len, np.array([2000, 1000, 500.5]) * 4 / 1e9)
+    _same(h, orc.build_classes(orc.HitsFile(str(p))))
+
+
+@pytest.mark.parametrize("txt,msg", [
+    ("@TranscriptMetaData\tA\t10\t20\n@TranscriptMetaData\tA\t10\t20\n@GeneIsoforms\tg\tA\n>r\nA\n", "duplicate transcripts in @TranscriptMetaData"),
+    ("@TranscriptMetaData\tA\t10\t20\n@TranscriptMetaData\tB\t10\t20\n@GeneIsoforms\tg\tA\n>r\nA\n", "does not belong to a gene"),
+    ("@TranscriptMetaData\tA\t10\t20\n@GeneIsoforms\tg\tA\n@GeneIsoforms\th\tA\n>r\nA\n", "nested within genes"),
+    ("@TranscriptMetaData\tA\t10\t20\n@GeneIsoforms\tg\tA\n>r\nZ\n", "has no length"),
+    ("@TranscriptMetaData\tA\t0\t20\n@GeneIsoforms\tg\tA\n>r\nA\n", "length of zero"),
+    ("hello\n", "does not seem to be a hits file"),
+])
+def test_loader_errors_follow_the_reference(tmp_path, txt, msg):
+    p = tmp_path / "bad.hits"
+    p.write_text(txt)
+    with pytest.raises(RuntimeError) as e:
+        hostlib.load_hits(str(p))
+    assert msg in str(e.value)
+
+
+def test_missing_file(tmp_path):
+    with pytest.raises(RuntimeError) as e:
+        hostlib.load_hits(str(tmp_path / "nope.hits"))
+    assert "Error reading hits file" in str(e.value)
