@@ -109,6 +109,9 @@ int mmq_em(mmq_handle* h, int max_iter, double eps, int* iters_out, double* logl
 #define MMQ_GIBBS_TIME_KERNELS 4 /* bracket every k_alloc / k_gamma launch with
                                   CUDA events on the handle's stream; read the
                                   totals with mmq_kernel_times               */
+#define MMQ_GIBBS_GENERIC_KERNEL 8 /* k == 1 shards: use the general multinomial
+                                  kernel instead of the categorical fast path
+                                  (same results; for tests and comparison)   */
 int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweeps, int stride,
               int trace_len, int flags);
 

@@ -40,6 +40,7 @@
 #define MMQ_STREAM_ALLOC 0x414c4c4fu /* per hit class, per sweep   */
 #define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
 #define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
+#define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per PAIR of classes */
 
 /* ------------------------------------------------------------------ bits */
 
@@ -374,7 +375,7 @@ MMQ_HD int64_t mmq_binomial(mmq_rng* g, int64_t n, double p) {
  *         weight when weights are present); read twice, never written
  *   x[j]  out: number of fragments given to member j; sum_j x[j] == k
  * d == 1 consumes no random numbers (x = k).  k == 1 is one categorical draw
- * (one uniform).  k > 1 is gsl_ran_multinomial's chain of conditional
+ * (one uniform: chosen = first j with u * sum_p < p_0 + ... + p_j).  k > 1 is gsl_ran_multinomial's chain of conditional
  * binomials x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)).
  * The arithmetic order (left-to-right sums) is part of the contract: the CPU
  * replay and every kernel variant walk the row in the same order. */
@@ -395,9 +396,14 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
     if (lp >= 0) last_pos = lp;
   }
   mmq_rng g;
-  mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, class_id, sweep);
   if (k == 1) {
-    const double target = mmq_uniform(&g) * norm;
+    /* one categorical draw needs one uniform; a Philox block holds two, so classes
+     * 2c and 2c+1 share block c of the CAT stream (first / second uniform).  A
+     * kernel thread that owns two consecutive classes runs Philox once. */
+    mmq_rng_init(&g, seed, MMQ_STREAM_CAT, class_id >> 1, sweep);
+    double u = mmq_uniform(&g);
+    if (class_id & 1) u = mmq_uniform(&g);
+    const double target = u * norm;
     double acc = 0.0;
     int chosen = -1;
     for (int j = 0; j < d; ++j) {
@@ -409,6 +415,7 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
     x[chosen] = 1;
     return;
   }
+  mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, class_id, sweep);
   int64_t rem = k;
   double sum_p = 0.0;
   for (int j = 0; j < d; ++j) {

@@ -315,6 +315,247 @@ k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
   }
 }
 
+
+/* ------------------------------------------------ K2 fast path: k == 1 rows */
+
+#define MMQ_CAT_WARPS 8   /* warps per CTA; warps are autonomous (no block barrier) */
+#define MMQ_CAT_ROWS 64   /* classes per warp chunk: two consecutive classes per lane */
+#define MMQ_CAT_SLAB 640  /* staged CSR entries per warp and buffer (unweighted) */
+#define MMQ_CAT_SLAB_W 384 /* ... with per-hit weights (two arrays are staged) */
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+/* TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP) */
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(b))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(smem_u32(b)), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+/* (j + 1/2) 2^-52 for the 52-bit integer j = (hi:lo) >> 12 — the value of mmq_uniform —
+ * built without an int->double conversion: [1,2) mantissa trick, both steps exact. */
+__device__ __forceinline__ double cat_u52(uint32_t hi, uint32_t lo) {
+  const uint64_t j = (((uint64_t)hi << 32) | (uint64_t)lo) >> 12;
+  return (__longlong_as_double((long long)(0x3ff0000000000000ull | j)) - 1.0) + 1.1102230246251565404e-16; /* + 2^-53 */
+}
+
+/* The two k == 1 classes of one lane: categorical draws with the arithmetic, and its order,
+ * of the k == 1 branch of mmq_alloc_row (include/mmq_sampler.h): running sums S_j = p_0 + ... + p_j
+ * left to right, target = u * S_{d-1}, chosen = first j with target < S_j.
+ * Control flow is warp-uniform (trip counts are warp maxima, lanes past their row gather the
+ * sentinel mu[n] == 0, adding 0.0 is exact), and gathers are issued in independent batches.
+ * Returns the chosen COLUMNS (or -1 for an absent class). */
+template <bool HAS_W>
+__device__ __forceinline__ void cat_draw2(const int32_t* ca, const float* wa, int da, double ua, const int32_t* cb,
+                                          const float* wb, int db, double ub, const double* __restrict__ mu,
+                                          int32_t sentinel, int32_t& out_a, int32_t& out_b) {
+  /* singletons (d == 1) need no mu: they gather the sentinel and fall to chosen = 0 below */
+  const int ga = da > 1 ? da : 0, gb = db > 1 ? db : 0;
+#define MMQ_PJ(c, wv, g, j) (HAS_W ? mu[(j) < (g) ? (c)[j] : sentinel] * (double)((j) < (g) ? (wv)[j] : 0.f) \
+                                   : mu[(j) < (g) ? (c)[j] : sentinel])
+  double Sa[4], Sb[4];
+  {
+    double pa[4], pb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { pa[j] = MMQ_PJ(ca, wa, ga, j); pb[j] = MMQ_PJ(cb, wb, gb, j); }
+    Sa[0] = pa[0]; Sb[0] = pb[0];
+#pragma unroll
+    for (int j = 1; j < 4; ++j) { Sa[j] = Sa[j - 1] + pa[j]; Sb[j] = Sb[j - 1] + pb[j]; }
+  }
+  double na = Sa[3], nb = Sb[3];
+  const int gmax = __reduce_max_sync(0xffffffffu, ga > gb ? ga : gb); /* warp-uniform */
+  for (int j0 = 4; j0 < gmax; j0 += 4) {
+    double pa[4], pb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { pa[q] = MMQ_PJ(ca, wa, ga, j0 + q); pb[q] = MMQ_PJ(cb, wb, gb, j0 + q); }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { na += pa[q]; nb += pb[q]; }
+  }
+  const double ta = ua * na, tb = ub * nb;
+  int cha = -1, chb = -1;
+#pragma unroll
+  for (int j = 3; j >= 0; --j) { /* descending: the smallest hit index wins */
+    if (j < ga && ta < Sa[j]) cha = j;
+    if (j < gb && tb < Sb[j]) chb = j;
+  }
+  /* rows longer than 4 that were not decided in their first four members: rescan the tail */
+  const bool more_a = cha < 0 && ga > 4, more_b = chb < 0 && gb > 4;
+  if (__any_sync(0xffffffffu, more_a || more_b)) {
+    double xa = Sa[3], xb = Sb[3];
+    for (int j0 = 4; j0 < gmax; j0 += 4) {
+      double pa[4], pb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { pa[q] = MMQ_PJ(ca, wa, ga, j0 + q); pb[q] = MMQ_PJ(cb, wb, gb, j0 + q); }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        xa += pa[q]; xb += pb[q];
+        if (cha < 0 && j0 + q < ga && ta < xa) cha = j0 + q;
+        if (chb < 0 && j0 + q < gb && tb < xb) chb = j0 + q;
+      }
+    }
+  }
+  /* d == 1; or rounding at the top end / all-zero row: last member with p > 0, else the last member */
+  if (cha < 0 && da > 0) {
+    cha = da - 1;
+    if (da > 1)
+      for (int j = da - 1; j >= 0; --j)
+        if (MMQ_PJ(ca, wa, da, j) > 0.0) { cha = j; break; }
+  }
+  if (chb < 0 && db > 0) {
+    chb = db - 1;
+    if (db > 1)
+      for (int j = db - 1; j >= 0; --j)
+        if (MMQ_PJ(cb, wb, db, j) > 0.0) { chb = j; break; }
+  }
+#undef MMQ_PJ
+  out_a = da > 0 ? ca[cha] : -1;
+  out_b = db > 0 ? cb[chb] : -1;
+}
+
+/* counts[c] += 1 for every lane with c >= 0, one reduction per distinct column in the warp */
+__device__ __forceinline__ void cat_red(int32_t* __restrict__ counts, int32_t c, int lane) {
+  const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+  if (c >= 0) {
+    const unsigned grp = __match_any_sync(act, c);
+    if (lane == __ffs(grp) - 1) atomicAdd(counts + c, __popc(grp));
+  }
+}
+
+/* K2 for the per-fragment layout (k == 1, no X kept).  A warp owns chunks of 64 consecutive
+ * classes, two per lane.  Pipeline per warp, no block barrier anywhere:
+ *   - row pointers of chunk i+2 are loaded into registers (one 128-bit load per lane),
+ *   - the contiguous column (and weight) segment of chunk i+1 is fetched by ONE TMA bulk
+ *     copy (cp.async.bulk, 16-byte aligned, completion on a per-warp mbarrier) into the
+ *     other half of the warp's shared-memory double buffer,
+ *   - chunk i is processed from shared memory: every lane gathers mu for its two classes,
+ *     draws both with ONE Philox block (classes 2c, 2c+1 share block c of the CAT stream)
+ *     and the chosen columns are added to counts[], aggregated across the warp first.
+ * Chunks whose segment exceeds the buffer are read straight from global memory. */
+template <bool HAS_W, int SLAB>
+__global__ void __launch_bounds__(MMQ_CAT_WARPS * 32, 3)
+k_alloc_cat(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const float* __restrict__ w,
+            const double* __restrict__ mu, int32_t* __restrict__ counts, int64_t m, int64_t n_chunks,
+            uint32_t seed, uint32_t sweep, int64_t class_id_base, int32_t sentinel) {
+  extern __shared__ __align__(16) unsigned char cat_smem[];
+  constexpr int PER_WARP = 16 + 2 * SLAB * 4 * (HAS_W ? 2 : 1);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* wbase = cat_smem + wib * PER_WARP;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);            /* [2] */
+  int32_t* sc = reinterpret_cast<int32_t*>(wbase + 16);           /* [2][SLAB] */
+  float* sw = reinterpret_cast<float*>(wbase + 16 + 2 * SLAB * 4); /* [2][SLAB] when HAS_W */
+  const int64_t chunk0 = (int64_t)blockIdx.x * MMQ_CAT_WARPS + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * MMQ_CAT_WARPS;
+  if (chunk0 >= n_chunks) return;
+  if (lane == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  /* raw row pointers of this lane's two classes in a chunk: q0, q1 (and q2 = next lane's q0) */
+  auto load_rp = [&](int64_t chunk, int64_t& q0, int64_t& q1, int64_t& q2) {
+    const int64_t r0 = chunk * MMQ_CAT_ROWS;
+    const int64_t ia = r0 + 2 * lane;
+    if (r0 + MMQ_CAT_ROWS <= m) {
+      const longlong2 v = *reinterpret_cast<const longlong2*>(row_ptr + ia); /* 16-byte aligned: ia is even */
+      q0 = v.x; q1 = v.y;
+      q2 = (lane == 31) ? row_ptr[r0 + MMQ_CAT_ROWS] : 0;
+    } else {
+      q0 = row_ptr[ia < m ? ia : m];
+      q1 = row_ptr[ia + 1 < m ? ia + 1 : m];
+      q2 = row_ptr[ia + 2 < m ? ia + 2 : m];
+    }
+  };
+  /* turn raw pointers into (start, offsets) and launch the bulk copy into buffer `buf` */
+  struct ChunkState { int64_t start; int oa, ob, oe; bool staged; };
+  uint32_t uses0 = 0, uses1 = 0; /* completed-phase counters of the two mbarriers */
+  auto prepare = [&](int64_t chunk, int64_t q0, int64_t q1, int64_t q2, int buf) -> ChunkState {
+    const int64_t r0 = chunk * MMQ_CAT_ROWS;
+    if (r0 + MMQ_CAT_ROWS <= m) {
+      const int64_t nx = __shfl_down_sync(0xffffffffu, q0, 1);
+      if (lane != 31) q2 = nx;
+    }
+    const int64_t base = __shfl_sync(0xffffffffu, q0, 0);
+    const int64_t end = __shfl_sync(0xffffffffu, q2, 31);
+    ChunkState st;
+    st.start = base & ~(int64_t)3; /* col / weight arrays are 256-byte aligned and padded by 4 entries */
+    st.oa = (int)(q0 - st.start);
+    st.ob = (int)(q1 - st.start);
+    st.oe = (int)(q2 - st.start);
+    const int span = (int)(end - st.start);
+    st.staged = span <= SLAB && span > 0;
+    if (st.staged && lane == 0) {
+      const uint32_t bytes = (uint32_t)((span + 3) & ~3) * 4u;
+      mbar_expect_tx(&mbar[buf], HAS_W ? 2 * bytes : bytes);
+      bulk_g2s(sc + buf * SLAB, col + st.start, bytes, &mbar[buf]);
+      if (HAS_W) bulk_g2s(sw + buf * SLAB, w + st.start, bytes, &mbar[buf]);
+    }
+    return st;
+  };
+
+  int64_t q0, q1, q2;
+  load_rp(chunk0, q0, q1, q2);
+  ChunkState cur = prepare(chunk0, q0, q1, q2, 0);
+  if (chunk0 + nwarps < n_chunks) load_rp(chunk0 + nwarps, q0, q1, q2);
+  int it = 0;
+  for (int64_t chunk = chunk0; chunk < n_chunks; chunk += nwarps, ++it) {
+    const int buf = it & 1;
+    const int64_t nxt = chunk + nwarps;
+    ChunkState next;
+    next.staged = false; next.start = 0; next.oa = next.ob = next.oe = 0;
+    if (nxt < n_chunks) next = prepare(nxt, q0, q1, q2, buf ^ 1);       /* bulk copy for chunk i+1 */
+    if (nxt + nwarps < n_chunks) load_rp(nxt + nwarps, q0, q1, q2);     /* row pointers for chunk i+2 */
+
+    /* uniforms of this lane's two classes (independent of the data in flight) */
+    const uint64_t ca = (uint64_t)(class_id_base + chunk * MMQ_CAT_ROWS + 2 * lane);
+    uint32_t wd[4] = {(uint32_t)(ca >> 1), (uint32_t)(ca >> 33), sweep, 0u};
+    mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
+    double ua, ub;
+    if ((ca & 1) == 0) { /* warp-uniform: parity of class_id_base */
+      ua = cat_u52(wd[0], wd[1]);
+      ub = cat_u52(wd[2], wd[3]);
+    } else {
+      ua = cat_u52(wd[2], wd[3]);
+      const uint64_t cb = ca + 1;
+      uint32_t w2[4] = {(uint32_t)(cb >> 1), (uint32_t)(cb >> 33), sweep, 0u};
+      mmq_philox4x32_10(w2, seed, MMQ_STREAM_CAT);
+      ub = cat_u52(w2[0], w2[1]);
+    }
+    const int da = cur.ob - cur.oa, db = cur.oe - cur.ob;
+    int32_t ca_col, cb_col;
+    if (cur.staged) {
+      mbar_wait(&mbar[buf], (buf ? uses1 : uses0) & 1u);
+      if (buf) ++uses1; else ++uses0;
+      const int32_t* c0 = sc + buf * SLAB;
+      const float* w0 = sw + buf * SLAB;
+      cat_draw2<HAS_W>(c0 + cur.oa, w0 + cur.oa, da, ua, c0 + cur.ob, w0 + cur.ob, db, ub, mu, sentinel, ca_col, cb_col);
+    } else {
+      const int32_t* c0 = col + cur.start;
+      const float* w0 = w + cur.start;
+      cat_draw2<HAS_W>(c0 + cur.oa, w0 + cur.oa, da, ua, c0 + cur.ob, w0 + cur.ob, db, ub, mu, sentinel, ca_col, cb_col);
+    }
+    cat_red(counts, ca_col, lane);
+    cat_red(counts, cb_col, lane);
+    __syncwarp(); /* every lane is done with buffer `buf` before the next iteration refills it */
+    cur = next;
+  }
+}
+
 /* K3: counts[t] = sum over the transposed CSR of X — an atomic-free segmented
  * reduction, one warp per transcript.  src/mmseq.cpp:887, :895-899. */
 __global__ void k_count_reduce(const int64_t* __restrict__ tptr, const uint32_t* __restrict__ perm,
@@ -395,8 +636,8 @@ int64_t mmq_launch_count(void) { return (int64_t)g_mmq_launches.load(); }
 
 const char* mmq_last_error(const mmq_handle* h) { return h ? h->err.c_str() : g_mmq_create_err.c_str(); }
 
-static int upload(mmq_handle* h, void** dst, const void* src, size_t bytes) {
-  int rc = mmq_dev_alloc(h, dst, bytes);
+static int upload(mmq_handle* h, void** dst, const void* src, size_t bytes, size_t pad = 0) {
+  int rc = mmq_dev_alloc(h, dst, bytes + pad);
   if (rc) return rc;
   if (bytes) MMQ_CUDA(h, cudaMemcpyAsync(*dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
   return MMQ_OK;
@@ -482,12 +723,12 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   for (int64_t t = 0; t < p->n; ++t)
     if (!(p->len[t] > 0.0)) { h->err = "mmq_create: transcript length must be > 0 (src/mmseq.cpp:604-607)"; CREATE_TRY(MMQ_ERR_ARG); }
   CREATE_TRY(upload(h, (void**)&h->row_ptr, p->row_ptr, sizeof(int64_t) * (size_t)(p->m + 1)));
-  CREATE_TRY(upload(h, (void**)&h->col, p->col, sizeof(int32_t) * (size_t)p->nnz));
+  CREATE_TRY(upload(h, (void**)&h->col, p->col, sizeof(int32_t) * (size_t)p->nnz, 16)); /* +4 entries: aligned 128-bit staging may over-read */
   if (h->has_k) CREATE_TRY(upload(h, (void**)&h->k, p->k, sizeof(int32_t) * (size_t)p->m));
-  if (h->has_w) CREATE_TRY(upload(h, (void**)&h->w, p->weight, sizeof(float) * (size_t)p->nnz));
+  if (h->has_w) CREATE_TRY(upload(h, (void**)&h->w, p->weight, sizeof(float) * (size_t)p->nnz, 16));
   CREATE_TRY(upload(h, (void**)&h->len, p->len, sizeof(double) * (size_t)p->n));
-  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->mu, sizeof(double) * (size_t)p->n));
-  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->mu_tmp, sizeof(double) * (size_t)p->n));
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->mu, sizeof(double) * (size_t)(p->n + 1))); /* mu[n] == 0: gather sentinel */
+  CREATE_TRY(mmq_dev_alloc(h, (void**)&h->mu_tmp, sizeof(double) * (size_t)(p->n + 1)));
   CREATE_TRY(mmq_dev_alloc(h, (void**)&h->acc, sizeof(double) * (size_t)p->n));
   CREATE_TRY(mmq_dev_alloc(h, (void**)&h->counts, sizeof(int32_t) * (size_t)p->n));
   CREATE_TRY(mmq_dev_alloc(h, (void**)&h->uh, sizeof(int32_t) * (size_t)p->n));
@@ -496,7 +737,8 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   CREATE_TRY(mmq_dev_alloc(h, (void**)&h->partial, sizeof(double) * (size_t)h->partial_cap));
   CREATE_TRY(mmq_dev_alloc(h, (void**)&h->scalars, sizeof(double) * 4));
   CREATE_TRY(cuda_try(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * (size_t)p->n, h->stream), "memset counts"));
-  CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu, 0, sizeof(double) * (size_t)p->n, h->stream), "memset mu"));
+  CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu, 0, sizeof(double) * (size_t)(p->n + 1), h->stream), "memset mu"));
+  CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu_tmp, 0, sizeof(double) * (size_t)(p->n + 1), h->stream), "memset mu_tmp"));
   if (p->m > 0) { /* structural checks on the device: no O(nnz) host loop in front of the upload */
     int* d_flags = (int*)h->scalars;
     CREATE_TRY(cuda_try(cudaMemsetAsync(d_flags, 0, sizeof(int), h->stream), "memset flags"));
@@ -736,7 +978,23 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       MMQ_LAUNCHED(h);
     } else {
       mark(h->ev_alloc);
-      launch_alloc_t<false>(h, grid, seed, sweep);
+      if (!h->has_k && !(flags & MMQ_GIBBS_GENERIC_KERNEL)) {
+        const int64_t n_chunks = (h->m + MMQ_CAT_ROWS - 1) / MMQ_CAT_ROWS;
+        const int64_t want = (n_chunks + MMQ_CAT_WARPS - 1) / MMQ_CAT_WARPS;
+        if (h->has_w) {
+          constexpr int SM = MMQ_CAT_WARPS * (16 + 2 * MMQ_CAT_SLAB_W * 4 * 2);
+          MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_cat<true, MMQ_CAT_SLAB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+          const int cgrid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * 3);
+          k_alloc_cat<true, MMQ_CAT_SLAB_W><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n);
+        } else {
+          constexpr int SM = MMQ_CAT_WARPS * (16 + 2 * MMQ_CAT_SLAB * 4);
+          MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_cat<false, MMQ_CAT_SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+          const int cgrid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * 3);
+          k_alloc_cat<false, MMQ_CAT_SLAB><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n);
+        }
+      } else {
+        launch_alloc_t<false>(h, grid, seed, sweep);
+      }
       MMQ_LAUNCHED(h);
       mark(h->ev_alloc);
     }
