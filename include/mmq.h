@@ -169,6 +169,12 @@ int mmq_prop_summaries(mmq_handle* h, const int32_t* gene_of, const uint8_t* mul
  * each transcript or -1.  out int32[nsets] (all-reduced over shards). */
 int mmq_unique_hits_sets(mmq_handle* h, const int32_t* set_of, int64_t nsets, int32_t* out);
 
+/* Prior draws for transcripts without hits, src/mmseq.cpp:971-978:
+ * out[u*trace_len + s] ~ Gamma(alpha, rate[u]) with rate[u] = beta + len*N/1e9, from the
+ * PRIOR Philox stream keyed by (seed, ids[u], s) — the reference draws them from rg[0]. */
+int mmq_prior_draws(int device, int64_t count, const int64_t* ids, const double* rate, double alpha,
+                    uint32_t seed, int trace_len, double* out);
+
 /* Stand-alone batched Sokal on host data: rows x len fp64 (len a power of two,
  * 4..2048); src/sokal.cc:33-87. */
 int mmq_sokal_batch(int device, int64_t rows, int len, const double* x, double* var, double* tau,

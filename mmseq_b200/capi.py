@@ -64,6 +64,7 @@ def _load():
         "mmq_prop_summaries": (i32, [vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
         "mmq_unique_hits_sets": (i32, [vp, vp, i64, vp]),
         "mmq_sokal_batch": (i32, [i32, i64, i32, vp, vp, vp, vp, vp]),
+        "mmq_prior_draws": (i32, [i32, i64, vp, vp, dbl, u32, i32, vp]),
         "mmq_launch_count": (i64, []),
         "mmq_version": (C.c_char_p, []),
     }
@@ -89,7 +90,7 @@ EXPORTS = [
     "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
     "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
-    "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_launch_count", "mmq_version",
+    "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_version",
 ]
 
 
@@ -129,6 +130,16 @@ def sokal_batch(x, device=0):
     if rc:
         raise MmqError("mmq_sokal_batch: " + lib().mmq_last_error(None).decode())
     return var, tau, win, status
+
+
+def prior_draws(ids, rate, alpha, seed, trace_len, device=0):
+    """src/mmseq.cpp:971-978 on the device: (len(ids), trace_len) Gamma(alpha, rate) draws."""
+    ids = _c(ids, np.int64); rate = _c(rate, np.float64)
+    out = np.zeros((len(ids), trace_len))
+    rc = lib().mmq_prior_draws(device, len(ids), _ptr(ids), _ptr(rate), alpha, seed, trace_len, _ptr(out))
+    if rc:
+        raise MmqError("mmq_prior_draws: " + lib().mmq_last_error(None).decode())
+    return out
 
 
 class Handle:

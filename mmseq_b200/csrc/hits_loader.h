@@ -75,4 +75,12 @@ int scaled_lengths(const HitsHeader& hdr, const HitClasses& cls, std::vector<dou
 
 }  // namespace mmq
 
+
+/* host_special.cpp */
+extern "C" {
+double mmq_host_ndtri(double p);
+double mmq_host_digamma(double x);
+double mmq_host_trigamma(double x);
+}
+
 #endif

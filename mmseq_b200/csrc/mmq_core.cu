@@ -902,7 +902,8 @@ int mmq_em(mmq_handle* h, int max_iter, double eps, int* iters_out, double* logl
   if (rc) return rc;
   rc = mmq_loglik(h, &loglik); /* also leaves rterm = k/D(mu) */
   if (rc) return rc;
-  double llr = eps + 1.0;
+  double llr = eps + 1.0; /* src/mmseq.cpp:756 */
+  if (!(llr > eps)) llr = INFINITY; /* eps so negative that eps + 1 == eps (callers stepping one iteration at a time) */
   int iter = 0;
   const int grid_w = mmq_grid_for(h->n * 32, 256, h->num_sms * 8);
   const int grid_t = mmq_grid_for(h->n, 256, h->partial_cap);

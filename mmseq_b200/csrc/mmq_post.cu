@@ -220,6 +220,18 @@ __global__ void k_uh_sets(const int64_t* __restrict__ row_ptr, const int32_t* __
   }
 }
 
+/* Gamma(alpha, rate_u) prior draws, one thread per (transcript, slot). src/mmseq.cpp:971-978. */
+__global__ void k_prior(const int64_t* __restrict__ ids, const double* __restrict__ rate, int64_t count, int L,
+                        double alpha, uint32_t seed, double* __restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count * L; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t u = i / L;
+    const int s = (int)(i - u * L);
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_PRIOR, (uint64_t)ids[u], (uint32_t)s);
+    out[i] = mmq_gamma(&g, alpha, rate[u]);
+  }
+}
+
 /* ------------------------------------------------------------------ host */
 
 static bool pow2_ok(int len) { return len >= 4 && len <= MMQ_MAX_ROW_LEN && (len & (len - 1)) == 0; }
@@ -415,6 +427,30 @@ int mmq_unique_hits_sets(mmq_handle* h, const int32_t* set_of, int64_t nsets, in
   if (e != cudaSuccess) ret = mmq_cuda_fail(h, e, "mmq_unique_hits_sets", __FILE__, __LINE__);
   cudaFree(d_set); cudaFree(d_out);
   return ret;
+}
+
+int mmq_prior_draws(int device, int64_t count, const int64_t* ids, const double* rate, double alpha, uint32_t seed,
+                    int trace_len, double* out) {
+  if (count < 0 || trace_len <= 0 || (count > 0 && (!ids || !rate || !out)) || !(alpha > 0.0))
+    return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_prior_draws: bad arguments");
+  if (count == 0) return MMQ_OK;
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return mmq_cuda_fail(nullptr, e, "cudaSetDevice", __FILE__, __LINE__);
+  int64_t* d_ids = nullptr; double *d_rate = nullptr, *d_out = nullptr;
+  auto A = [&](void** p, size_t b) { if (e == cudaSuccess) e = cudaMalloc(p, b); };
+  A((void**)&d_ids, sizeof(int64_t) * count); A((void**)&d_rate, sizeof(double) * count);
+  A((void**)&d_out, sizeof(double) * count * trace_len);
+  if (e == cudaSuccess) e = cudaMemcpy(d_ids, ids, sizeof(int64_t) * count, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_rate, rate, sizeof(double) * count, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    k_prior<<<mmq_grid_for(count * trace_len, 128, 148 * 16), 128>>>(d_ids, d_rate, count, trace_len, alpha, seed, d_out);
+    g_mmq_launches.fetch_add(1);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * count * trace_len, cudaMemcpyDeviceToHost);
+  cudaFree(d_ids); cudaFree(d_rate); cudaFree(d_out);
+  if (e != cudaSuccess) return mmq_cuda_fail(nullptr, e, "mmq_prior_draws", __FILE__, __LINE__);
+  return MMQ_OK;
 }
 
 int mmq_sokal_batch(int device, int64_t rows, int len, const double* x, double* var, double* tau, int32_t* win, int32_t* status) {

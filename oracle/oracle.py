@@ -339,7 +339,7 @@ def summaries_transcripts(trace, pct=(5, 25, 50, 75, 95)):
     (src/mmseq.cpp:1111-1146, :1203-1227, :1308-1324)."""
     trace = np.asarray(trace, np.float64)
     rows, L = trace.shape
-    idx = [int(round(p / 100.0 * (L - 1))) for p in pct]  # :1113 (C round: half away from zero)
+    idx = [int(np.floor(p / 100.0 * (L - 1) + 0.5)) for p in pct]  # :1113 (C round(): half away from zero)
     srt = np.sort(trace, axis=1)
     with np.errstate(divide="ignore", invalid="ignore"):
         lg = np.log(trace)

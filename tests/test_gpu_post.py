@@ -94,3 +94,17 @@ def test_summaries_groups_props_uh(small_problem, small_synth):
     # uh(): literal restatement of src/uh.cpp on the same sets
     uh_o = orc.uh_literal(h.row_ptr, h.col, h.k, gptr, members)
     assert np.array_equal(uh, uh_o)
+
+
+def test_prior_draws_bit_exact_and_distributed():
+    """mmq_prior_draws (src/mmseq.cpp:971-978 on the device) equals the CPU replay bit for bit
+    and follows Gamma(alpha, rate)."""
+    from scipy import stats
+    ids = np.array([3, 17, 123456], np.int64)
+    ls = np.array([1e-3, 5.0, 2e-5])
+    alpha, beta = 0.1, 0.1
+    got = capi.prior_draws(ids, beta + ls, alpha, 1234, 1024)
+    want = orc.prior_replay(ids, ls, alpha, beta, 1234, 1024)
+    assert np.array_equal(got, want)
+    big = capi.prior_draws(np.arange(64, dtype=np.int64), np.full(64, 2.5), 0.7, 99, 1024).ravel()
+    assert stats.kstest(big, "gamma", args=(0.7, 0, 1 / 2.5)).pvalue > 1e-4

@@ -103,3 +103,19 @@ def test_missing_file(tmp_path):
     with pytest.raises(RuntimeError) as e:
         hostlib.load_hits(str(tmp_path / "nope.hits"))
     assert "Error reading hits file" in str(e.value)
+
+
+def test_host_special_functions_match_scipy():
+    """psi, psi_1 and the probit used for the closed-form rows of features without hits
+    (src/mmseq.cpp:1372-1373, :1286; GSL gsl_sf_psi / gsl_sf_psi_n / gsl_cdf_ugaussian_Pinv)."""
+    import ctypes as C
+    from scipy import special
+    L = hostlib.lib()
+    for f in (L.mmq_host_digamma, L.mmq_host_trigamma, L.mmq_host_ndtri):
+        f.restype = C.c_double
+        f.argtypes = [C.c_double]
+    for x in (0.01, 0.1, 0.5, 1.0, 2.5, 9.99, 10.0, 37.0, 1e4):
+        assert np.isclose(L.mmq_host_digamma(x), special.digamma(x), rtol=1e-13, atol=1e-14)
+        assert np.isclose(L.mmq_host_trigamma(x), special.polygamma(1, x), rtol=1e-13)
+    for p in (1e-9, 0.01, 0.3, 0.5, 0.999999999):
+        assert np.isclose(L.mmq_host_ndtri(p), special.ndtri(p), rtol=1e-13, atol=1e-15)
