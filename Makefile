@@ -19,11 +19,11 @@ synth: $(SYNTH)
 hostlib: $(HOSTLIB)
 cli: $(CLI)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/mmq_internal.h include/mmq.h include/mmq_sampler.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/mmq_internal.h $(CSRC)/mmq_device.cuh include/mmq.h include/mmq_sampler.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
-$(LIB): build/mmq_core.o build/mmq_post.o
+$(LIB): build/mmq_core.o build/mmq_post.o build/mmq_seg.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ldl
 
 $(SYNTH): $(CSRC)/mmq_synth.cpp

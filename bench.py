@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--transcripts", type=int, default=T_C2)
     ap.add_argument("--fragments", type=int, default=N_C2, help="fragments per GPU")
-    ap.add_argument("--layout", default="perfragment", choices=["perfragment", "perfragment_unsorted", "collapsed"])
+    ap.add_argument("--layout", default="perfragment", choices=["perfragment", "perfragment_byclass", "perfragment_unsorted", "collapsed"])
+    ap.add_argument("--first-appearance-columns", action="store_true", help="number transcripts as the reference does (src/mmseq.cpp:403) instead of in header order")
     ap.add_argument("--weights", action="store_true", help="fp32 per-hit weights (config 4's extension)")
     ap.add_argument("--transposed", action="store_true", help="materialise X + atomic-free transposed reduction")
     ap.add_argument("--cpu-sweeps", type=int, default=4, help="sweeps of the CPU baseline sample")
@@ -68,10 +69,13 @@ def make_workload(args, rank, world):
     t0 = time.time()
     s = synth.Synth(SYNTH_SEED, args.transcripts, args.fragments, weights=args.weights, frag_seed=rank)
     t1 = time.time()
-    layout = {"perfragment": hostlib.LAYOUT_PER_FRAGMENT_SORTED, "perfragment_unsorted": hostlib.LAYOUT_PER_FRAGMENT,
+    layout = {"perfragment": hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH, "perfragment_byclass": hostlib.LAYOUT_PER_FRAGMENT_SORTED,
+              "perfragment_unsorted": hostlib.LAYOUT_PER_FRAGMENT,
               "collapsed": hostlib.LAYOUT_COLLAPSED}[args.layout]
     if world > 1:
         layout |= hostlib.LAYOUT_IDENTITY_COLUMNS
+    elif not args.first_appearance_columns:
+        layout |= hostlib.LAYOUT_HEADER_ORDER_COLUMNS
     h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=s.frag_w if args.weights else None, layout=layout)
     t2 = time.time()
     # l[t] = efflen * N_total / 1e9 over the whole (all-rank) sample, src/mmseq.cpp:603

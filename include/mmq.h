@@ -112,6 +112,8 @@ int mmq_em(mmq_handle* h, int max_iter, double eps, int* iters_out, double* logl
 #define MMQ_GIBBS_GENERIC_KERNEL 8 /* k == 1 shards: use the general multinomial
                                   kernel instead of the categorical fast path
                                   (same results; for tests and comparison)   */
+#define MMQ_GIBBS_RAGGED_KERNEL 16 /* k == 1 shards: use the row-pointer driven (TMA-staged)
+                                  kernel even when the by-length segment plan exists */
 int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweeps, int stride,
               int trace_len, int flags);
 

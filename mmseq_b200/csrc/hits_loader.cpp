@@ -132,6 +132,7 @@ inline uint64_t mix64(uint64_t x) {
 
 struct ClassBuilder::Impl {
   int layout;
+  bool header_order = false;
   bool weighted;
   int64_t N = 0;
   std::vector<int32_t> hdr2col, col2hdr, doublehits;
@@ -162,6 +163,7 @@ struct ClassBuilder::Impl {
 
 ClassBuilder::ClassBuilder(int64_t T, int layout, bool weighted) : p_(new Impl()) {
   p_->layout = layout & 15;
+  p_->header_order = (layout & LAYOUT_HEADER_ORDER_COLUMNS) != 0 && !(layout & LAYOUT_IDENTITY_COLUMNS);
   p_->weighted = weighted;
   p_->hdr2col.assign((size_t)T, -1);
   if (layout & LAYOUT_IDENTITY_COLUMNS) {
@@ -235,6 +237,40 @@ void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
 
 void ClassBuilder::finish(HitClasses& out) {
   Impl& P = *p_;
+  if (P.header_order) {
+    /* renumber the observed transcripts by header index; members of a class stay ascending */
+    const int64_t n0 = (int64_t)P.col2hdr.size();
+    std::vector<int32_t> by((size_t)n0), newcol((size_t)n0);
+    for (int64_t c = 0; c < n0; ++c) by[(size_t)c] = (int32_t)c;
+    std::sort(by.begin(), by.end(), [&](int32_t a, int32_t b) { return P.col2hdr[(size_t)a] < P.col2hdr[(size_t)b]; });
+    for (int64_t i = 0; i < n0; ++i) newcol[(size_t)by[(size_t)i]] = (int32_t)i;
+    std::vector<int32_t> c2h((size_t)n0), dh((size_t)n0);
+    for (int64_t c = 0; c < n0; ++c) { c2h[(size_t)newcol[(size_t)c]] = P.col2hdr[(size_t)c]; dh[(size_t)newcol[(size_t)c]] = P.doublehits[(size_t)c]; }
+    P.col2hdr.swap(c2h);
+    P.doublehits.swap(dh);
+    for (size_t hI = 0; hI < P.hdr2col.size(); ++hI) if (P.hdr2col[hI] >= 0) P.hdr2col[hI] = newcol[(size_t)P.hdr2col[hI]];
+    const int64_t C = (int64_t)P.cls_hash.size();
+    std::vector<std::pair<int32_t, int32_t>> tmp; /* (new column, old position) */
+    std::vector<std::vector<int32_t>> perm_of_class;
+    if (P.weighted) perm_of_class.resize((size_t)C);
+    for (int64_t c = 0; c < C; ++c) {
+      const int64_t b = P.cls_ptr[(size_t)c], e = P.cls_ptr[(size_t)c + 1];
+      tmp.clear();
+      for (int64_t q = b; q < e; ++q) tmp.emplace_back(newcol[(size_t)P.cls_col[(size_t)q]], (int32_t)(q - b));
+      std::sort(tmp.begin(), tmp.end());
+      for (int64_t q = b; q < e; ++q) P.cls_col[(size_t)q] = tmp[(size_t)(q - b)].first;
+      if (P.weighted) { auto& pm = perm_of_class[(size_t)c]; pm.resize(tmp.size()); for (size_t j = 0; j < tmp.size(); ++j) pm[j] = tmp[j].second; }
+    }
+    if (P.weighted) {
+      std::vector<float> t2;
+      for (size_t r = 0; r < P.rec_class.size(); ++r) {
+        const auto& pm = perm_of_class[(size_t)P.rec_class[r]];
+        float* wr = P.rec_w.data() + P.rec_wptr[r];
+        t2.assign(wr, wr + pm.size());
+        for (size_t j = 0; j < pm.size(); ++j) wr[j] = t2[(size_t)pm[j]];
+      }
+    }
+  }
   out.layout = P.layout;
   out.N = P.N;
   out.n = (int64_t)P.col2hdr.size();
@@ -252,11 +288,28 @@ void ClassBuilder::finish(HitClasses& out) {
   }
   const int64_t R = (int64_t)P.rec_class.size();
   std::vector<int64_t> order((size_t)R);
-  if (P.layout == LAYOUT_PER_FRAGMENT_SORTED) { /* stable counting sort of records by class */
+  if (P.layout == LAYOUT_PER_FRAGMENT_SORTED || P.layout == LAYOUT_PER_FRAGMENT_BY_LENGTH) {
+    /* stable counting sort of records by class, classes ranked by (size,) first appearance */
+    std::vector<int64_t> rank((size_t)out.n_classes);
+    for (int64_t c = 0; c < out.n_classes; ++c) rank[(size_t)c] = c;
+    if (P.layout == LAYOUT_PER_FRAGMENT_BY_LENGTH) {
+      std::vector<int64_t> by((size_t)out.n_classes);
+      for (int64_t c = 0; c < out.n_classes; ++c) by[(size_t)c] = c;
+      /* by class size, then by the member columns lexicographically: neighbouring rows gather
+       * the same or neighbouring mu entries */
+      std::stable_sort(by.begin(), by.end(), [&](int64_t a, int64_t b) {
+        const int64_t da = P.cls_ptr[(size_t)a + 1] - P.cls_ptr[(size_t)a], db = P.cls_ptr[(size_t)b + 1] - P.cls_ptr[(size_t)b];
+        if (da != db) return da < db;
+        const int32_t* pa = P.cls_col.data() + P.cls_ptr[(size_t)a];
+        const int32_t* pb = P.cls_col.data() + P.cls_ptr[(size_t)b];
+        return std::lexicographical_compare(pa, pa + da, pb, pb + db);
+      });
+      for (int64_t i = 0; i < out.n_classes; ++i) rank[(size_t)by[(size_t)i]] = i;
+    }
     std::vector<int64_t> start((size_t)out.n_classes + 1, 0);
-    for (int64_t r = 0; r < R; ++r) start[(size_t)P.rec_class[(size_t)r] + 1]++;
+    for (int64_t r = 0; r < R; ++r) start[(size_t)rank[(size_t)P.rec_class[(size_t)r]] + 1]++;
     for (int64_t c = 0; c < out.n_classes; ++c) start[(size_t)c + 1] += start[(size_t)c];
-    for (int64_t r = 0; r < R; ++r) order[(size_t)start[(size_t)P.rec_class[(size_t)r]]++] = r;
+    for (int64_t r = 0; r < R; ++r) order[(size_t)start[(size_t)rank[(size_t)P.rec_class[(size_t)r]]]++] = r;
   } else {
     for (int64_t r = 0; r < R; ++r) order[(size_t)r] = r;
   }

@@ -33,10 +33,19 @@ enum Layout {
   LAYOUT_COLLAPSED = 0,        /* reference semantics: distinct sets + k */
   LAYOUT_PER_FRAGMENT = 1,     /* one row per record, record order, k == 1 */
   LAYOUT_PER_FRAGMENT_SORTED = 2, /* one row per record, rows grouped by class */
+  LAYOUT_PER_FRAGMENT_BY_LENGTH = 3, /* one row per record, rows grouped by class size, then by
+                                        class: the device layout of choice (runs of equal length
+                                        need no row pointers, singletons are skipped) */
   /* OR-ed in: columns are header transcript indices (n = T) instead of
    * first-appearance indices — a column space shared by independently loaded
    * shards of one transcriptome (multi-GPU harness) */
-  LAYOUT_IDENTITY_COLUMNS = 16
+  LAYOUT_IDENTITY_COLUMNS = 16,
+  /* OR-ed in: the n observed transcripts are numbered in HEADER order instead of
+   * first-appearance order.  Headers list a gene's isoforms together, so the mu of
+   * co-mapping transcripts share cache lines on the device.  (The reference's .M / .k
+   * dumps use first-appearance numbering; the host program writes those from a
+   * first-appearance load.) */
+  LAYOUT_HEADER_ORDER_COLUMNS = 32
 };
 
 struct HitClasses {

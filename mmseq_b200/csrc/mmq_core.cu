@@ -21,6 +21,7 @@
 
 #include "../../include/mmq_sampler.h"
 #include "mmq_internal.h"
+#include "mmq_device.cuh"
 
 std::atomic<long long> g_mmq_launches{0};
 thread_local std::string g_mmq_create_err;
@@ -346,13 +347,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   } while (!ok);
 }
 
-/* (j + 1/2) 2^-52 for the 52-bit integer j = (hi:lo) >> 12 — the value of mmq_uniform —
- * built without an int->double conversion: [1,2) mantissa trick, both steps exact. */
-__device__ __forceinline__ double cat_u52(uint32_t hi, uint32_t lo) {
-  const uint64_t j = (((uint64_t)hi << 32) | (uint64_t)lo) >> 12;
-  return (__longlong_as_double((long long)(0x3ff0000000000000ull | j)) - 1.0) + 1.1102230246251565404e-16; /* + 2^-53 */
-}
-
 /* The two k == 1 classes of one lane: categorical draws with the arithmetic, and its order,
  * of the k == 1 branch of mmq_alloc_row (include/mmq_sampler.h): running sums S_j = p_0 + ... + p_j
  * left to right, target = u * S_{d-1}, chosen = first j with target < S_j.
@@ -424,15 +418,6 @@ __device__ __forceinline__ void cat_draw2(const int32_t* ca, const float* wa, in
 #undef MMQ_PJ
   out_a = da > 0 ? ca[cha] : -1;
   out_b = db > 0 ? cb[chb] : -1;
-}
-
-/* counts[c] += 1 for every lane with c >= 0, one reduction per distinct column in the warp */
-__device__ __forceinline__ void cat_red(int32_t* __restrict__ counts, int32_t c, int lane) {
-  const unsigned act = __ballot_sync(0xffffffffu, c >= 0);
-  if (c >= 0) {
-    const unsigned grp = __match_any_sync(act, c);
-    if (lane == __ffs(grp) - 1) atomicAdd(counts + c, __popc(grp));
-  }
 }
 
 /* K2 for the per-fragment layout (k == 1, no X kept).  A warp owns chunks of 64 consecutive
@@ -574,12 +559,12 @@ __global__ void k_count_reduce(const int64_t* __restrict__ tptr, const uint32_t*
 /* K4 (+K5 capture): mu[t] ~ Gamma(alpha + counts[t], rate beta + l[t]); counts
  * are cleared for the next sweep; trace_col (= trace + slot, or null) receives
  * mu at stride trace_len.  src/mmseq.cpp:904-917. */
-__global__ void k_gamma(int32_t* __restrict__ counts, const double* __restrict__ len,
+__global__ void k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
                         double* __restrict__ mu, double* __restrict__ trace_col, int trace_len, int64_t n,
                         double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     const int32_t c = counts[t];
-    counts[t] = 0;
+    counts[t] = counts_base ? counts_base[t] : 0; /* classes skipped by the segmented kernel (singletons) */
     if (counts_copy) counts_copy[t] = c;
     mmq_rng g;
     mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
@@ -759,6 +744,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
     h->rows_per_tile = r;
     h->n_tiles = (p->m + r - 1) / r;
   }
+  if (!h->has_k) CREATE_TRY(mmq_seg_plan(h, p->row_ptr));
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
 #undef CREATE_TRY
   *out = h;
@@ -979,7 +965,10 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       MMQ_LAUNCHED(h);
     } else {
       mark(h->ev_alloc);
-      if (!h->has_k && !(flags & MMQ_GIBBS_GENERIC_KERNEL)) {
+      if (h->seg_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
+        if ((rc = mmq_seg_launch(h, seed, sweep))) return rc;
+      } else if (!h->has_k && !(flags & MMQ_GIBBS_GENERIC_KERNEL)) {
+        if (h->seg_ready && (rc = mmq_seg_add_base(h, false))) return rc; /* this kernel visits the singletons itself */
         const int64_t n_chunks = (h->m + MMQ_CAT_ROWS - 1) / MMQ_CAT_ROWS;
         const int64_t want = (n_chunks + MMQ_CAT_WARPS - 1) / MMQ_CAT_WARPS;
         if (h->has_w) {
@@ -994,6 +983,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
           k_alloc_cat<false, MMQ_CAT_SLAB><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n);
         }
       } else {
+        if (h->seg_ready && (rc = mmq_seg_add_base(h, false))) return rc;
         launch_alloc_t<false>(h, grid, seed, sweep);
       }
       MMQ_LAUNCHED(h);
@@ -1002,10 +992,11 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
   }
   if ((rc = mmq_allreduce(h, h->counts, (size_t)h->n, 0))) return rc;
   mark(h->ev_gamma);
-  k_gamma<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->counts, h->len, h->mu, trace_col, h->trace_len, h->n,
+  k_gamma<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, trace_col, h->trace_len, h->n,
                                                                           h->alpha, h->beta, seed, sweep, counts_copy);
   MMQ_LAUNCHED(h);
   mark(h->ev_gamma);
+  if (h->seg_base) h->seg_base_in_counts = true; /* k_gamma restarted counts[] from seg_base */
   return MMQ_OK;
 }
 

@@ -70,6 +70,19 @@ struct mmq_handle {
   void* comm = nullptr; /* ncclComm_t */
   int rank = 0, nranks = 1;
 
+  /* segmented plan for k == 1 shards whose rows come in few runs of equal length
+   * (the loader's by-length layout): packed, aligned copies of col / weight, a segment
+   * table, and the constant counts of the singleton classes the sweep kernel skips */
+  bool seg_ready = false;
+  void* seg_table = nullptr; /* mmq_seg[] on the device */
+  int seg_count = 0;
+  int64_t seg_chunks = 0;
+  int32_t* seg_col = nullptr;
+  float* seg_w = nullptr;
+  int32_t* seg_base = nullptr; /* [n] or null */
+  bool seg_base_in_counts = true; /* counts[] currently starts from seg_base */
+  int64_t seg_entries = 0, seg_rows = 0, seg_singletons = 0;
+
   /* MMQ_GIBBS_TIME_KERNELS: (start, stop) event pairs around each launch */
   std::vector<cudaEvent_t> ev_alloc, ev_gamma;
 
@@ -87,6 +100,9 @@ int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes);
 void mmq_dev_free(mmq_handle* h, void* p);
 int mmq_allreduce(mmq_handle* h, void* buf, size_t count, int is_double);
 int mmq_ensure_trace_groups(mmq_handle* h);
+int mmq_seg_plan(mmq_handle* h, const int64_t* row_ptr_host);
+int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep);
+int mmq_seg_add_base(mmq_handle* h, bool want_in_counts);
 
 #define MMQ_CUDA(h, call)                                                              \
   do {                                                                                 \

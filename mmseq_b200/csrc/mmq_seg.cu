@@ -1,0 +1,313 @@
+/* mmq_seg.cu — K2 for k == 1 shards laid out BY LENGTH (the loader's
+ * LAYOUT_PER_FRAGMENT_BY_LENGTH): the rows of the shard come in a few long runs of equal
+ * class size d.  Replaces, for such shards, the allocation loop of src/mmseq.cpp:862-891.
+ *
+ * What the plan (built once in mmq_create) buys every sweep:
+ *   - no row pointers are read at all: inside a run, row r starts at e0 + r*d;
+ *   - classes with a single member (d == 1) are not visited: their allocation is
+ *     deterministic (x = k, no random number — include/mmq_sampler.h), so their counts
+ *     are summed once into seg_base[] and the Gamma kernel restarts counts[] from it;
+ *   - every warp works on 64 consecutive classes of ONE length, two per lane, with
+ *     straight-line code specialised on d (2..8): 8- or 16-byte vector loads of the lane's
+ *     2d contiguous columns (runs are re-packed 16-byte aligned), 2d independent mu
+ *     gathers in flight, left-to-right running sums in registers, no divergence, no shared
+ *     memory; one Philox block per lane serves both classes.
+ * Arithmetic and its order are those of the k == 1 branch of mmq_alloc_row, so the counts
+ * equal the CPU replay's bit for bit (tests/test_gpu_parity.py).
+ *
+ * Algorithmic HBM bytes per sweep: 4 B (+4 B weight) per CSR entry of the classes with
+ * d >= 2 — nothing else is streamed.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "mmq_device.cuh"
+#include "mmq_internal.h"
+
+#define MMQ_SEG_MAX 96    /* more runs than this: not a by-length layout, use the ragged kernel */
+#define MMQ_SEG_WARPS 8
+#define MMQ_SEG_ROWS 64
+
+struct mmq_seg {
+  int64_t e_virtual;   /* packed-array offset of the (possibly dummy) virtual first row; multiple of 4 */
+  int64_t cid_virtual; /* class id of the virtual first row; EVEN, so lane pairs are Philox pairs */
+  int32_t row_lo;      /* 0, or 1 when the virtual first row is a dummy */
+  int32_t rows;        /* virtual row count (dummy included) */
+  int32_t d;           /* class size of the run */
+  int32_t pad_;
+  int64_t chunk0;      /* first 64-row chunk of this run in the global chunk numbering */
+};
+
+__global__ void k_fill_i32(int32_t* __restrict__ p, int64_t count, int32_t v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_axpy_i32(int32_t* __restrict__ y, const int32_t* __restrict__ x, int64_t count, int sign) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) y[i] += sign * x[i];
+}
+/* base[col[q]] += 1 over the CSR entries [q0, q1) of a run of singleton classes */
+__global__ void k_count_singletons(const int32_t* __restrict__ col, int64_t q0, int64_t q1, int32_t* __restrict__ base) {
+  for (int64_t q = q0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < q1; q += (int64_t)gridDim.x * blockDim.x) atomicAdd(base + col[q], 1);
+}
+
+/* Both classes of a lane, class size D known at compile time.  c[0..D) / c[D..2D) are the
+ * columns of class a / b (sentinel for an absent class), p the matching probabilities.
+ * Same arithmetic and order as mmq_alloc_row's k == 1 branch. */
+template <int D>
+__device__ __forceinline__ int32_t seg_pick(const int32_t* c, const double* p, double u) {
+  double S[D];
+  S[0] = p[0];
+#pragma unroll
+  for (int j = 1; j < D; ++j) S[j] = S[j - 1] + p[j];
+  const double target = u * S[D - 1];
+  int chosen = -1;
+#pragma unroll
+  for (int j = D - 1; j >= 0; --j)
+    if (target < S[j]) chosen = j; /* descending: the smallest hit index wins */
+  if (chosen < 0) { /* rounding at the top end or an all-zero row: last member with p > 0, else the last */
+    chosen = D - 1;
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (p[j] > 0.0) chosen = j;
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < D; ++j) any |= p[j] > 0.0;
+    if (!any) chosen = D - 1;
+  }
+  int32_t out = c[0];
+#pragma unroll
+  for (int j = 1; j < D; ++j)
+    if (chosen == j) out = c[j];
+  return out;
+}
+
+template <int D, bool HAS_W>
+__device__ __forceinline__ void seg_chunk_fixed(const int32_t* __restrict__ colp, const float* __restrict__ wp, int64_t e,
+                                                bool va, bool vb, double ua, double ub, const double* __restrict__ mu,
+                                                int32_t sentinel, int32_t& out_a, int32_t& out_b) {
+  int32_t c[2 * D];
+  float wv[2 * D];
+  if (va || vb) { /* the lane's 2D columns are contiguous and 8-byte aligned (16-byte when D is even) */
+    if (D % 2 == 0) {
+#pragma unroll
+      for (int j = 0; j < 2 * D; j += 4) {
+        const int4 v = *reinterpret_cast<const int4*>(colp + e + j);
+        c[j] = v.x; c[j + 1] = v.y; c[j + 2] = v.z; c[j + 3] = v.w;
+        if (HAS_W) {
+          const float4 f = *reinterpret_cast<const float4*>(wp + e + j);
+          wv[j] = f.x; wv[j + 1] = f.y; wv[j + 2] = f.z; wv[j + 3] = f.w;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 2 * D; j += 2) {
+        const int2 v = *reinterpret_cast<const int2*>(colp + e + j);
+        c[j] = v.x; c[j + 1] = v.y;
+        if (HAS_W) {
+          const float2 f = *reinterpret_cast<const float2*>(wp + e + j);
+          wv[j] = f.x; wv[j + 1] = f.y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < D; ++j) { /* absent classes (dummy first row, tail of the run) gather the sentinel: p = 0 */
+    if (!va) { c[j] = sentinel; if (HAS_W) wv[j] = 0.f; }
+    if (!vb) { c[D + j] = sentinel; if (HAS_W) wv[D + j] = 0.f; }
+  }
+  double p[2 * D];
+#pragma unroll
+  for (int j = 0; j < 2 * D; ++j) p[j] = HAS_W ? mu[c[j]] * (double)wv[j] : mu[c[j]];
+  out_a = va ? seg_pick<D>(c, p, ua) : -1;
+  out_b = vb ? seg_pick<D>(c + D, p + D, ub) : -1;
+}
+
+/* Any class size: two passes with batched gathers straight from global memory. */
+template <bool HAS_W>
+__device__ __forceinline__ int32_t seg_row_generic(const int32_t* __restrict__ c, const float* __restrict__ wv, int d,
+                                                   const double* __restrict__ mu, double u) {
+#define MMQ_PG(j) (HAS_W ? mu[c[j]] * (double)wv[j] : mu[c[j]])
+  double norm = 0.0;
+  int j = 0;
+  for (; j + 4 <= d; j += 4) {
+    const double a0 = MMQ_PG(j), a1 = MMQ_PG(j + 1), a2 = MMQ_PG(j + 2), a3 = MMQ_PG(j + 3);
+    norm += a0; norm += a1; norm += a2; norm += a3;
+  }
+  for (; j < d; ++j) norm += MMQ_PG(j);
+  const double target = u * norm;
+  double acc = 0.0;
+  int chosen = -1;
+  for (j = 0; j + 4 <= d && chosen < 0; j += 4) {
+    const double a0 = MMQ_PG(j), a1 = MMQ_PG(j + 1), a2 = MMQ_PG(j + 2), a3 = MMQ_PG(j + 3);
+    acc += a0; if (chosen < 0 && target < acc) chosen = j;
+    acc += a1; if (chosen < 0 && target < acc) chosen = j + 1;
+    acc += a2; if (chosen < 0 && target < acc) chosen = j + 2;
+    acc += a3; if (chosen < 0 && target < acc) chosen = j + 3;
+  }
+  for (; j < d && chosen < 0; ++j) { acc += MMQ_PG(j); if (target < acc) chosen = j; }
+  if (chosen < 0) {
+    chosen = d - 1;
+    for (j = d - 1; j >= 0; --j)
+      if (MMQ_PG(j) > 0.0) { chosen = j; break; }
+  }
+#undef MMQ_PG
+  return c[chosen];
+}
+
+template <bool HAS_W, int MAXD>
+__global__ void __launch_bounds__(MMQ_SEG_WARPS * 32, MAXD > 6 ? 2 : 3)
+k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, const int32_t* __restrict__ colp,
+            const float* __restrict__ wp, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
+            uint32_t sweep, int32_t sentinel) {
+  __shared__ mmq_seg s_seg[MMQ_SEG_MAX];
+  for (int i = threadIdx.x; i < nsegs; i += blockDim.x) s_seg[i] = segs[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * MMQ_SEG_WARPS + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * MMQ_SEG_WARPS;
+  int si = 0;
+  for (int64_t chunk = warp0; chunk < total_chunks; chunk += nwarps) {
+    while (si + 1 < nsegs && chunk >= s_seg[si + 1].chunk0) ++si; /* warp-uniform */
+    const mmq_seg sg = s_seg[si];
+    const int D = sg.d;
+    const int rv = (int)(chunk - sg.chunk0) * MMQ_SEG_ROWS + 2 * lane; /* virtual row of class a */
+    const bool va = rv >= sg.row_lo && rv < sg.rows;
+    const bool vb = rv + 1 < sg.rows; /* rv + 1 >= 1 >= row_lo always */
+    const int64_t e = sg.e_virtual + (int64_t)rv * D;
+    /* one Philox block per lane: classes cid (even) and cid + 1 */
+    const uint64_t cid = (uint64_t)(sg.cid_virtual + rv);
+    uint32_t wd[4] = {(uint32_t)(cid >> 1), (uint32_t)(cid >> 33), sweep, 0u};
+    mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
+    const double ua = cat_u52(wd[0], wd[1]), ub = cat_u52(wd[2], wd[3]);
+    int32_t ca = -1, cb = -1;
+    /* warp-uniform dispatch on the class size */
+    if (D == 2) seg_chunk_fixed<2, HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    else if (D == 3) seg_chunk_fixed<3, HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    else if (D == 4) seg_chunk_fixed<4, HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    else if (MAXD >= 6 && D == 5) seg_chunk_fixed<(MAXD >= 6 ? 5 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    else if (MAXD >= 6 && D == 6) seg_chunk_fixed<(MAXD >= 6 ? 6 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    else if (MAXD >= 8 && D == 7) seg_chunk_fixed<(MAXD >= 8 ? 7 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    else if (MAXD >= 8 && D == 8) seg_chunk_fixed<(MAXD >= 8 ? 8 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    else {
+      if (va) ca = seg_row_generic<HAS_W>(colp + e, wp + e, D, mu, ua);
+      if (vb) cb = seg_row_generic<HAS_W>(colp + e + D, wp + e + D, D, mu, ub);
+    }
+    cat_red(counts, ca, lane);
+    cat_red(counts, cb, lane);
+  }
+}
+
+/* ------------------------------------------------------------------ host */
+
+int mmq_seg_add_base(mmq_handle* h, bool want_in_counts) {
+  if (!h->seg_base || h->seg_base_in_counts == want_in_counts) return MMQ_OK;
+  k_axpy_i32<<<mmq_grid_for(h->n, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->counts, h->seg_base, h->n, want_in_counts ? 1 : -1);
+  MMQ_LAUNCHED(h);
+  h->seg_base_in_counts = want_in_counts;
+  return MMQ_OK;
+}
+
+int mmq_seg_plan(mmq_handle* h, const int64_t* rp) {
+  h->seg_ready = false;
+  const int64_t m = h->m;
+  if (m == 0 || h->has_k) return MMQ_OK;
+  /* runs of equal class size */
+  struct Run { int64_t r0, r1; int d; };
+  std::vector<Run> runs;
+  for (int64_t i = 0; i < m;) {
+    const int64_t d = rp[i + 1] - rp[i];
+    if (d > 0x7fffffff) return MMQ_OK;
+    int64_t j = i + 1;
+    while (j < m && rp[j + 1] - rp[j] == d) ++j;
+    runs.push_back({i, j, (int)d});
+    if ((int)runs.size() > MMQ_SEG_MAX) return MMQ_OK; /* ragged shard: the row-pointer kernel handles it */
+    i = j;
+  }
+  std::vector<mmq_seg> segs;
+  int64_t packed = 0, chunks = 0, entries = 0, rows = 0, singles = 0;
+  for (const Run& r : runs) {
+    if (r.d == 1) { singles += r.r1 - r.r0; continue; }
+    if ((r.r1 - r.r0 + 1) > 0x7ffffff0ll) return MMQ_OK;
+    mmq_seg sg;
+    const int parity = (int)((h->class_id_base + r.r0) & 1);
+    packed = (packed + 3) & ~(int64_t)3;
+    sg.e_virtual = packed;
+    sg.cid_virtual = h->class_id_base + r.r0 - parity;
+    sg.row_lo = parity;
+    sg.rows = (int32_t)(r.r1 - r.r0 + parity);
+    sg.d = r.d;
+    sg.pad_ = 0;
+    sg.chunk0 = chunks;
+    packed += (int64_t)sg.rows * r.d;
+    chunks += (sg.rows + MMQ_SEG_ROWS - 1) / MMQ_SEG_ROWS;
+    entries += (r.r1 - r.r0) * r.d;
+    rows += r.r1 - r.r0;
+    segs.push_back(sg);
+  }
+  if (segs.empty() && singles == 0) return MMQ_OK;
+  packed = ((packed + 3) & ~(int64_t)3) + 64; /* slack: the last lane of a tail chunk never reads, but keep loads in bounds */
+  int rc;
+  if ((rc = mmq_dev_alloc(h, (void**)&h->seg_col, sizeof(int32_t) * (size_t)packed))) return rc;
+  k_fill_i32<<<mmq_grid_for(packed, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->seg_col, packed, (int32_t)h->n);
+  MMQ_LAUNCHED(h);
+  if (h->has_w) {
+    if ((rc = mmq_dev_alloc(h, (void**)&h->seg_w, sizeof(float) * (size_t)packed))) return rc;
+    MMQ_CUDA(h, cudaMemsetAsync(h->seg_w, 0, sizeof(float) * (size_t)packed, h->stream));
+  }
+  size_t si = 0;
+  for (const Run& r : runs) {
+    if (r.d == 1) continue;
+    const mmq_seg& sg = segs[si++];
+    const int64_t dst = sg.e_virtual + (int64_t)sg.row_lo * r.d;
+    const size_t cnt = (size_t)(r.r1 - r.r0) * (size_t)r.d;
+    MMQ_CUDA(h, cudaMemcpyAsync(h->seg_col + dst, h->col + rp[r.r0], sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->has_w) MMQ_CUDA(h, cudaMemcpyAsync(h->seg_w + dst, h->w + rp[r.r0], sizeof(float) * cnt, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (singles > 0) {
+    if ((rc = mmq_dev_alloc(h, (void**)&h->seg_base, sizeof(int32_t) * (size_t)h->n))) return rc;
+    MMQ_CUDA(h, cudaMemsetAsync(h->seg_base, 0, sizeof(int32_t) * (size_t)h->n, h->stream));
+    for (const Run& r : runs)
+      if (r.d == 1) {
+        k_count_singletons<<<mmq_grid_for(r.r1 - r.r0, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->col, rp[r.r0], rp[r.r1], h->seg_base);
+        MMQ_LAUNCHED(h);
+      }
+    MMQ_CUDA(h, cudaMemcpyAsync(h->counts, h->seg_base, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    h->seg_base_in_counts = true;
+  }
+  if (!segs.empty()) {
+    if ((rc = mmq_dev_alloc(h, &h->seg_table, sizeof(mmq_seg) * segs.size()))) return rc;
+    MMQ_CUDA(h, cudaMemcpyAsync(h->seg_table, segs.data(), sizeof(mmq_seg) * segs.size(), cudaMemcpyHostToDevice, h->stream));
+  }
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream)); /* segs is a host temporary */
+  h->seg_count = (int)segs.size();
+  h->seg_chunks = chunks;
+  h->seg_entries = entries;
+  h->seg_rows = rows;
+  h->seg_singletons = singles;
+  h->seg_ready = true;
+  return MMQ_OK;
+}
+
+int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep) {
+  int rc = mmq_seg_add_base(h, true);
+  if (rc) return rc;
+  if (h->seg_count == 0) return MMQ_OK; /* only singletons: nothing random to do */
+  const int64_t want = (h->seg_chunks + MMQ_SEG_WARPS - 1) / MMQ_SEG_WARPS;
+  static const int maxd_env = [] { const char* e = getenv("MMQ_SEG_MAXD"); return e ? atoi(e) : 0; }(); /* tuning knob */
+  const int maxd = maxd_env ? maxd_env : (h->has_w ? 4 : 6); /* largest class size with a register-resident specialisation */
+  const int occ = maxd > 6 ? 2 : 3;
+  const int grid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * occ);
+#define MMQ_SEG_ARGS (const mmq_seg*)h->seg_table, h->seg_count, h->seg_chunks, h->seg_col, h->seg_w, h->mu, h->counts, seed, sweep, (int32_t)h->n
+  if (h->has_w) {
+    if (maxd > 6) k_alloc_seg<true, 8><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else if (maxd > 4) k_alloc_seg<true, 6><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else k_alloc_seg<true, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+  } else {
+    if (maxd > 6) k_alloc_seg<false, 8><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else if (maxd > 4) k_alloc_seg<false, 6><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else k_alloc_seg<false, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+  }
+#undef MMQ_SEG_ARGS
+  return MMQ_OK;
+}

@@ -12,7 +12,9 @@ LIB_PATH = os.path.join(_HERE, "libmmq_host.so")
 LAYOUT_COLLAPSED = 0
 LAYOUT_PER_FRAGMENT = 1
 LAYOUT_PER_FRAGMENT_SORTED = 2
+LAYOUT_PER_FRAGMENT_BY_LENGTH = 3
 LAYOUT_IDENTITY_COLUMNS = 16
+LAYOUT_HEADER_ORDER_COLUMNS = 32
 
 _lib = None
 

@@ -102,6 +102,38 @@ def test_categorical_fast_path_edges(weighted, cid_base):
                 assert np.array_equal(mu_g, mu_o)
 
 
+@pytest.mark.parametrize("weighted", [False, True])
+@pytest.mark.parametrize("cid_base", [0, 5])
+def test_by_length_layout_segment_kernel(small_synth, weighted, cid_base):
+    """The loader's by-length layout: runs of equal class size, singletons skipped, no row
+    pointers read — same integers and the same chain as the CPU replay and as the other kernels."""
+    s = small_synth
+    w = None
+    if weighted:
+        w = np.exp(0.5 * np.random.default_rng(8).standard_normal(len(s.frag_tid))).astype(np.float32)
+    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=w, layout=hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH)
+    d = np.diff(h.row_ptr)
+    assert (np.diff(d) >= 0).all() and d[0] == 1 and d.max() > 8          # singletons first, long rows last
+    P = orc.Problem(h.row_ptr, h.col, None, h.len, weight=h.w)
+    mu, _, _ = P.init_mu()
+    with capi.Handle(h.row_ptr, h.col, None, h.len, weight=h.w, class_id_base=cid_base) as H:
+        for sweep in range(3):
+            _, c_o, mu_o = P.sweep_replay(mu, SEED, sweep, class_id_base=cid_base)
+            for flags in (capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_RAGGED_KERNEL, capi.MMQ_GIBBS_GENERIC_KERNEL,
+                          capi.MMQ_GIBBS_TRANSPOSED, capi.MMQ_GIBBS_DEFAULT):
+                H.set_mu(mu)
+                _, c, mu_g = H.sweep_debug(SEED, sweep, flags, want_x=False)
+                assert np.array_equal(c, c_o), (sweep, flags)
+                assert c.sum() == h.m and np.array_equal(mu_g, mu_o)
+            mu = mu_o
+        # a multi-sweep run on the default (segment) path reproduces the replayed chain
+        H.set_mu(mu)
+        H.gibbs(SEED, 3, 29, stride=4, trace_len=8)
+        mu_end, tr_o = P.gibbs_replay(mu, SEED, 3, 29, 4, 8) if cid_base == 0 else (None, None)
+        if cid_base == 0:
+            assert np.array_equal(H.get_mu(), mu_end) and np.array_equal(H.get_trace()[:, 1:], tr_o[:, 1:])
+
+
 def test_weighted_rows_bit_exact(small_synth):
     s = small_synth
     rng = np.random.default_rng(3)

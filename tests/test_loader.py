@@ -52,7 +52,7 @@ def test_text_and_binary_and_in_memory_agree(tmp_path, small_synth):
 def test_per_fragment_layouts_expand_the_same_classes(small_synth):
     s = small_synth
     c = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_COLLAPSED)
-    for layout in (hostlib.LAYOUT_PER_FRAGMENT, hostlib.LAYOUT_PER_FRAGMENT_SORTED):
+    for layout in (hostlib.LAYOUT_PER_FRAGMENT, hostlib.LAYOUT_PER_FRAGMENT_SORTED, hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH):
         p = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=layout)
         assert p.m == s.N and p.k is None and p.n == c.n and p.n_classes == c.m
         # every per-fragment row is one of the classes; multiplicities equal k
@@ -64,6 +64,11 @@ def test_per_fragment_layouts_expand_the_same_classes(small_synth):
         assert np.array_equal(cnt, c.k)
         if layout == hostlib.LAYOUT_PER_FRAGMENT_SORTED:
             assert ids == sorted(ids)
+        if layout == hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH:
+            d = np.diff(p.row_ptr)
+            assert (np.diff(d) >= 0).all()                         # grouped by class size ...
+            rows = [key(p.row_ptr, p.col, i) for i in range(p.m)]
+            assert all(rows[i] <= rows[i + 1] for i in range(p.m - 1) if d[i] == d[i + 1])   # ... then by member columns
 
 
 def test_duplicates_and_first_appearance_order(tmp_path):
@@ -119,3 +124,27 @@ def test_host_special_functions_match_scipy():
         assert np.isclose(L.mmq_host_trigamma(x), special.polygamma(1, x), rtol=1e-13)
     for p in (1e-9, 0.01, 0.3, 0.5, 0.999999999):
         assert np.isclose(L.mmq_host_ndtri(p), special.ndtri(p), rtol=1e-13, atol=1e-15)
+
+
+def test_header_order_columns_is_a_pure_renumbering(small_synth):
+    """LAYOUT_HEADER_ORDER_COLUMNS: same classes and counts, transcripts numbered by header index."""
+    s = small_synth
+    rng = np.random.default_rng(1)
+    w = rng.uniform(0.5, 2.0, len(s.frag_tid)).astype(np.float32)
+    for layout, fw in ((hostlib.LAYOUT_COLLAPSED, None), (hostlib.LAYOUT_PER_FRAGMENT, w), (hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH, None)):
+        a = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=fw, layout=layout)
+        b = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=fw, layout=layout | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
+        assert (np.diff(b.col2hdr) > 0).all() and sorted(a.col2hdr) == list(b.col2hdr)
+        assert a.m == b.m and a.n == b.n and np.array_equal(np.diff(a.row_ptr) if layout != hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH else np.sort(np.diff(a.row_ptr)), np.diff(b.row_ptr) if layout != hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH else np.sort(np.diff(b.row_ptr)))
+        for i in range(0, b.m, 97):   # rows ascending in the new numbering
+            seg = b.col[b.row_ptr[i]:b.row_ptr[i + 1]]
+            assert (np.diff(seg) > 0).all()
+        if layout != hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH:
+            # same header transcripts row by row (and the weights travel with their transcript)
+            for i in range(0, a.m, 53):
+                ha = a.col2hdr[a.col[a.row_ptr[i]:a.row_ptr[i + 1]]]; hb = b.col2hdr[b.col[b.row_ptr[i]:b.row_ptr[i + 1]]]
+                assert sorted(ha) == sorted(hb)
+                if fw is not None:
+                    wa = dict(zip(ha, a.w[a.row_ptr[i]:a.row_ptr[i + 1]])); wb = dict(zip(hb, b.w[b.row_ptr[i]:b.row_ptr[i + 1]]))
+                    assert wa == wb
+        assert np.allclose(np.sort(a.len), np.sort(b.len))
