@@ -138,13 +138,20 @@ def physical_gpu_index(local):
     return local
 
 
-def algorithmic_bytes(h, n, weights, transposed, stride):
-    """Compulsory HBM bytes of the implemented data flow (DESIGN.md section 'Roofline').
-    k_alloc: every CSR array once — 8 B row_ptr per class, 4 B column per entry (+4 B weight,
-    +4 B k when present).  mu gathers and count reductions stay in L2 (not counted).
-    The transposed variant adds X written + permutation read + X read (12 B per entry)."""
+def algorithmic_bytes(h, n, weights, transposed, stride, layout):
+    """Compulsory HBM bytes of the implemented data flow ('Roofline'); every array
+    once, L2-resident mu gathers and count reductions not counted.
+      segment kernel (by-length k == 1 shards): 4 B column (+4 B weight) per CSR entry of the
+        classes with >= 2 members; no row pointers, singleton classes are not visited;
+      row-pointer kernels: + 8 B row pointer per class, all entries (+4 B k when present);
+      transposed variant: + X written, + permutation and X read back (12 B per entry)."""
     m, nnz = h.m, h.nnz
-    alloc = 8 * (m + 1) + 4 * nnz + (4 * nnz if weights else 0) + (4 * m if h.k is not None else 0)
+    d = np.diff(h.row_ptr)
+    per_entry = 4 + (4 if weights else 0)
+    if layout == "perfragment" and h.k is None and not transposed:
+        alloc = per_entry * int(d[d >= 2].sum())
+    else:
+        alloc = 8 * (m + 1) + per_entry * nnz + (4 * m if h.k is not None else 0)
     if transposed:
         alloc += 4 * nnz
     reduce_ = (8 * nnz + 8 * (n + 1) + 4 * n) if transposed else 0
@@ -283,15 +290,11 @@ def main():
     if not args.no_e2e:
         pin = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
         rp, col, kk, ww, ll, mu_h = pin(h.row_ptr), pin(h.col), pin(h.k), pin(h.w), pin(length), pin(mu0)
-        H.close()
-        torch.cuda.empty_cache()
         barrier()
         t0 = time.perf_counter()
         H2 = capi.Handle(rp, col, kk, ll, weight=ww, class_id_base=cid_base, device=local)   # H2D of the CSR shard
         if world > 1:
-            uid = [capi.comm_id() if rank == 0 else None]
-            dist.broadcast_object_list(uid, src=0)
-            H2.comm_init(uid[0], rank, world)
+            H.comm_move_to(H2)   # the process keeps its NCCL communicator across samples
         H2.set_mu(mu_h)                                                                        # H2D
         H2.gibbs(SEED, 0, K * S, stride=S, trace_len=K, flags=flags)
         mu_out = H2.get_mu()                                                                   # D2H
@@ -309,8 +312,7 @@ def main():
                "what": "mmq_create(H2D shard) + mmq_set_mu + steps*16 sweeps + mmq_get_mu + mmq_get_trace, pinned host buffers"}
         assert np.isfinite(tr).all() and (tr > 0).any()
         H2.close()
-    else:
-        H.close()
+    H.close()
 
     # ---- roofline of the dominant kernel (k_alloc), device time from CUDA events on its stream
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -318,7 +320,7 @@ def main():
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
-    b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S)
+    b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S, args.layout)
     alloc_ms_avg = alloc_ms / max(alloc_n, 1)
     achieved = b_alloc / (alloc_ms_avg * 1e-3) / 1e9 if alloc_n else None
     roofline = {"kernel": "k_alloc", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -81,6 +81,9 @@ int64_t mmq_device_bytes(const mmq_handle* h);
  * for EM).  libnccl.so.2 is dlopen'ed on first use. */
 int mmq_comm_id(char id[128]);
 int mmq_comm_init(mmq_handle* h, const char id[128], int rank, int nranks);
+/* Hand the communicator of `from` (which keeps none) to `to`: lets a long-lived process load
+ * the next sample's shard without paying NCCL initialisation again. */
+int mmq_comm_move(mmq_handle* from, mmq_handle* to);
 
 /* mu0[t] = (sum_{i containing t} k[i]/|i|)/l[t] and unique_hits[t] =
  * counts_shared[t][0]; src/mmseq.cpp:617-638.  Leaves mu0 as the current mu.

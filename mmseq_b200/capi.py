@@ -49,6 +49,7 @@ def _load():
         "mmq_device_bytes": (i64, [vp]),
         "mmq_comm_id": (i32, [C.c_char_p]),
         "mmq_comm_init": (i32, [vp, C.c_char_p, i32, i32]),
+        "mmq_comm_move": (i32, [vp, vp]),
         "mmq_init_mu": (i32, [vp, vp]),
         "mmq_set_mu": (i32, [vp, vp]),
         "mmq_get_mu": (i32, [vp, vp]),
@@ -88,7 +89,7 @@ def lib():
 
 EXPORTS = [
     "mmq_create", "mmq_destroy", "mmq_last_error", "mmq_set_stream", "mmq_get_stream", "mmq_synchronize",
-    "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
+    "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
     "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
     "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_version",
@@ -199,6 +200,9 @@ class Handle:
 
     def comm_init(self, uid, rank, nranks):
         self._check(lib().mmq_comm_init(self._h, uid, rank, nranks), "mmq_comm_init")
+
+    def comm_move_to(self, other):
+        self._check(lib().mmq_comm_move(self._h, other._h), "mmq_comm_move")
 
     def init_mu(self):
         uh = np.zeros(self.n, np.int32)

@@ -810,6 +810,17 @@ int mmq_comm_init(mmq_handle* h, const char id[128], int rank, int nranks) {
   return MMQ_OK;
 }
 
+int mmq_comm_move(mmq_handle* from, mmq_handle* to) {
+  if (!from || !to || from == to) return mmq_fail(to, MMQ_ERR_ARG, "mmq_comm_move: bad arguments");
+  if (to->comm) return mmq_fail(to, MMQ_ERR_STATE, "mmq_comm_move: destination already has a communicator");
+  if (from->device != to->device) return mmq_fail(to, MMQ_ERR_ARG, "mmq_comm_move: handles are on different devices");
+  MMQ_CUDA(from, cudaSetDevice(from->device));
+  MMQ_CUDA(from, cudaStreamSynchronize(from->stream));
+  to->comm = from->comm; to->rank = from->rank; to->nranks = from->nranks;
+  from->comm = nullptr; from->rank = 0; from->nranks = 1;
+  return MMQ_OK;
+}
+
 /* ---- initial mu ---- */
 int mmq_init_mu(mmq_handle* h, int32_t* unique_hits_out) {
   if (!h) return MMQ_ERR_ARG;

@@ -175,6 +175,21 @@ k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, c
     const bool va = rv >= sg.row_lo && rv < sg.rows;
     const bool vb = rv + 1 < sg.rows; /* rv + 1 >= 1 >= row_lo always */
     const int64_t e = sg.e_virtual + (int64_t)rv * D;
+    { /* pull this warp's NEXT chunk of columns (and weights) towards L2 while this one is processed */
+      const int64_t nchunk = chunk + nwarps;
+      if (nchunk < total_chunks) {
+        int sj = si;
+        while (sj + 1 < nsegs && nchunk >= s_seg[sj + 1].chunk0) ++sj;
+        const int64_t e2 = s_seg[sj].e_virtual + ((nchunk - s_seg[sj].chunk0) * MMQ_SEG_ROWS + 2 * lane) * (int64_t)s_seg[sj].d;
+        const int bytes = 8 * s_seg[sj].d;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(colp + e2));
+        if (bytes > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(colp + e2) + bytes - 4));
+        if (HAS_W) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + e2));
+          if (bytes > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(wp + e2) + bytes - 4));
+        }
+      }
+    }
     /* one Philox block per lane: classes cid (even) and cid + 1 */
     const uint64_t cid = (uint64_t)(sg.cid_virtual + rv);
     uint32_t wd[4] = {(uint32_t)(cid >> 1), (uint32_t)(cid >> 33), sweep, 0u};
