@@ -236,7 +236,13 @@ def main():
 
     stream = torch.cuda.Stream(device=dev)
     cid_base = rank * args.fragments
-    H = capi.Handle(h.row_ptr, h.col, h.k, length, weight=h.w, class_id_base=cid_base, device=local)
+    class_id = None
+    if args.layout == "collapsed":   # device order by cost, Philox counters stay canonical (as the host program does)
+        from mmseq_b200 import hostlib
+        rp_s, col_s, k_s, class_id = hostlib.sort_classes_by_cost(h)
+        class_id = class_id + cid_base
+        h.row_ptr, h.col, h.k = rp_s, col_s, k_s
+    H = capi.Handle(h.row_ptr, h.col, h.k, length, weight=h.w, class_id_base=cid_base, device=local, class_id=class_id)
     H.set_stream(stream.cuda_stream)
     if world > 1:
         uid = [capi.comm_id() if rank == 0 else None]
@@ -292,7 +298,7 @@ def main():
         rp, col, kk, ww, ll, mu_h = pin(h.row_ptr), pin(h.col), pin(h.k), pin(h.w), pin(length), pin(mu0)
         barrier()
         t0 = time.perf_counter()
-        H2 = capi.Handle(rp, col, kk, ll, weight=ww, class_id_base=cid_base, device=local)   # H2D of the CSR shard
+        H2 = capi.Handle(rp, col, kk, ll, weight=ww, class_id_base=cid_base, device=local, class_id=class_id)   # H2D of the CSR shard
         if world > 1:
             H.comm_move_to(H2)   # the process keeps its NCCL communicator across samples
         H2.set_mu(mu_h)                                                                        # H2D

@@ -57,6 +57,10 @@ typedef struct mmq_problem {
   double alpha, beta;     /* Gamma prior on mu, :184-185                       */
   int64_t class_id_base;  /* global index of this shard's row 0: the Philox
                              counter of row i is class_id_base + i             */
+  const int64_t* class_id; /* [m] explicit Philox counters, or NULL.  Lets the caller
+                             hand the classes over in any order (e.g. sorted by cost so
+                             that a warp's classes do similar work) and still get the
+                             chain of the canonical order.  k != NULL only.       */
 } mmq_problem;
 
 /* Upload a shard (H2D), build the transcript-major transpose on the device

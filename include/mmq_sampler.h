@@ -40,6 +40,7 @@
 #define MMQ_STREAM_ALLOC 0x414c4c4fu /* per hit class, per sweep   */
 #define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
 #define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
+#define MMQ_SMALL_K 8 /* classes with 2..MMQ_SMALL_K fragments: categorical draws instead of binomials */
 #define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per PAIR of classes */
 
 /* ------------------------------------------------------------------ bits */
@@ -375,7 +376,8 @@ MMQ_HD int64_t mmq_binomial(mmq_rng* g, int64_t n, double p) {
  *         weight when weights are present); read twice, never written
  *   x[j]  out: number of fragments given to member j; sum_j x[j] == k
  * d == 1 consumes no random numbers (x = k).  k == 1 is one categorical draw
- * (one uniform: chosen = first j with u * sum_p < p_0 + ... + p_j).  k > 1 is gsl_ran_multinomial's chain of conditional
+ * (one uniform: chosen = first j with u * sum_p < p_0 + ... + p_j); 2 <= k <= MMQ_SMALL_K is k
+ * such draws from the class's own stream.  k > 1 is gsl_ran_multinomial's chain of conditional
  * binomials x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)).
  * The arithmetic order (left-to-right sums) is part of the contract: the CPU
  * replay and every kernel variant walk the row in the same order. */
@@ -416,6 +418,30 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
     return;
   }
   mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, class_id, sweep);
+  if (k <= MMQ_SMALL_K) {
+    /* few fragments: k independent categorical draws (one uniform each, no log/exp) — the
+     * same Multinomial(k; p) as the binomial chain below */
+    int ch[MMQ_SMALL_K];
+    for (int t = 0; t < MMQ_SMALL_K; ++t) {
+      ch[t] = -1;
+      if (t < (int)k) {
+        const double target = mmq_uniform(&g) * norm;
+        double acc = 0.0;
+        int chosen = -1;
+        for (int j = 0; j < d; ++j) {
+          acc += p[j];
+          if (chosen < 0 && target < acc) chosen = j;
+        }
+        ch[t] = chosen < 0 ? last_pos : chosen;
+      }
+    }
+    for (int j = 0; j < d; ++j) {
+      int32_t v = 0;
+      for (int t = 0; t < MMQ_SMALL_K; ++t) v += (ch[t] == j) ? 1 : 0;
+      x[j] = v;
+    }
+    return;
+  }
   int64_t rem = k;
   double sum_p = 0.0;
   for (int j = 0; j < d; ++j) {

@@ -29,6 +29,7 @@ class _Problem(C.Structure):
         ("row_ptr", C.c_void_p), ("col", C.c_void_p), ("k", C.c_void_p),
         ("weight", C.c_void_p), ("len", C.c_void_p),
         ("alpha", C.c_double), ("beta", C.c_double), ("class_id_base", C.c_int64),
+        ("class_id", C.c_void_p),
     ]
 
 
@@ -148,18 +149,19 @@ class Handle:
     """One shard of hit classes resident on one GPU (mmq_handle)."""
 
     def __init__(self, row_ptr, col, k, length, alpha=0.1, beta=0.1, weight=None, n=None,
-                 class_id_base=0, device=0):
+                 class_id_base=0, device=0, class_id=None):
         self._h = C.c_void_p()
         self.row_ptr = _c(row_ptr, np.int64)
         self.col = _c(col, np.int32)
         self.k = _c(k, np.int32)
         self.weight = _c(weight, np.float32)
         self.len = _c(length, np.float64)
+        self.class_id = _c(class_id, np.int64)
         self.n = int(len(self.len) if n is None else n)
         self.m = int(len(self.row_ptr) - 1)
         self.nnz = int(self.row_ptr[-1]) if self.m >= 0 and len(self.row_ptr) else 0
         p = _Problem(self.n, self.m, self.nnz, _ptr(self.row_ptr), _ptr(self.col), _ptr(self.k),
-                     _ptr(self.weight), _ptr(self.len), alpha, beta, class_id_base)
+                     _ptr(self.weight), _ptr(self.len), alpha, beta, class_id_base, _ptr(self.class_id))
         rc = lib().mmq_create(C.byref(p), device, C.byref(self._h))
         if rc:
             self._h = C.c_void_p()

@@ -260,7 +260,8 @@ struct PGlobal {
 };
 
 /* K2: allocate the k_i fragments of every hit class among its transcripts.
- * A CTA takes a tile of `rows_per_tile` consecutive classes, stages the tile's
+ * A CTA takes a tile of consecutive classes (as many as fit the staging buffer, at
+ * most one per thread; boundaries precomputed in mmq_create), stages the tile's
  * contiguous CSR segment (columns, and p = mu[col] * weight gathered once) in
  * shared memory with coalesced loads, then one thread per class runs
  * mmq_alloc_row on its slice.  MATERIALIZE writes x into the X array (CSR
@@ -270,16 +271,16 @@ template <bool MATERIALIZE, bool HAS_K, bool HAS_W>
 __global__ void __launch_bounds__(MMQ_ALLOC_THREADS)
 k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
         const int32_t* __restrict__ kk, const float* __restrict__ w, const double* __restrict__ mu,
-        int32_t* __restrict__ counts, int32_t* __restrict__ xout, int64_t m, int rows_per_tile,
-        int64_t n_tiles, uint32_t seed, uint32_t sweep, int64_t class_id_base) {
+        int32_t* __restrict__ counts, int32_t* __restrict__ xout, int64_t m, const int64_t* __restrict__ tile_start,
+        int64_t n_tiles, uint32_t seed, uint32_t sweep, int64_t class_id_base, const int64_t* __restrict__ class_id) {
   __shared__ double s_p[MMQ_ALLOC_CAP];
   __shared__ int32_t s_c[MMQ_ALLOC_CAP];
   __shared__ int32_t s_x[MATERIALIZE ? MMQ_ALLOC_CAP : 1];
   __shared__ int64_t s_rp[MMQ_ALLOC_THREADS + 1];
   const int tid = threadIdx.x;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t r0 = tile * rows_per_tile;
-    const int nrows = (int)((m - r0 < rows_per_tile) ? (m - r0) : rows_per_tile);
+    const int64_t r0 = tile_start[tile];
+    const int nrows = (int)(tile_start[tile + 1] - r0);
     for (int i = tid; i <= nrows; i += MMQ_ALLOC_THREADS) s_rp[i] = row_ptr[r0 + i];
     __syncthreads();
     const int64_t base = s_rp[0];
@@ -299,7 +300,7 @@ k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
       const int64_t rb = s_rp[tid];
       const int d = (int)(s_rp[tid + 1] - rb);
       const int64_t kv = HAS_K ? (int64_t)kk[r0 + tid] : 1;
-      const uint64_t cid = (uint64_t)(class_id_base + r0 + tid);
+      const uint64_t cid = (uint64_t)(class_id ? class_id[r0 + tid] : class_id_base + r0 + tid);
       if (staged) {
         const int off = (int)(rb - base);
         if (MATERIALIZE) mmq_alloc_row(s_p + off, s_x + off, d, kv, seed, cid, sweep);
@@ -323,29 +324,6 @@ k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
 #define MMQ_CAT_ROWS 64   /* classes per warp chunk: two consecutive classes per lane */
 #define MMQ_CAT_SLAB 640  /* staged CSR entries per warp and buffer (unweighted) */
 #define MMQ_CAT_SLAB_W 384 /* ... with per-hit weights (two arrays are staged) */
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
-}
-/* TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP) */
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(b))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-                 : "=r"(ok)
-                 : "r"(smem_u32(b)), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
 
 /* The two k == 1 classes of one lane: categorical draws with the arithmetic, and its order,
  * of the k == 1 branch of mmq_alloc_row (include/mmq_sampler.h): running sums S_j = p_0 + ... + p_j
@@ -628,6 +606,36 @@ static int upload(mmq_handle* h, void** dst, const void* src, size_t bytes, size
   return MMQ_OK;
 }
 
+/* Tiles of the general allocation kernel: greedily as many consecutive classes as fit the
+ * staging buffer (and one per thread); a class longer than the buffer is a tile of its own.
+ * rp_host may be null: the row pointers are then read back from the device. */
+static int build_tiles(mmq_handle* h, const int64_t* rp_host) {
+  if (h->tile_start) return MMQ_OK;
+  std::vector<int64_t> tmp;
+  if (!rp_host) {
+    tmp.resize((size_t)h->m + 1);
+    MMQ_CUDA(h, cudaMemcpyAsync(tmp.data(), h->row_ptr, sizeof(int64_t) * tmp.size(), cudaMemcpyDeviceToHost, h->stream));
+    MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    rp_host = tmp.data();
+  }
+  std::vector<int64_t> ts;
+  ts.reserve((size_t)(h->m / 128 + 2));
+  int64_t r = 0;
+  while (r < h->m) {
+    ts.push_back(r);
+    int64_t e = r + 1;
+    while (e < h->m && e - r < MMQ_ALLOC_THREADS && rp_host[e + 1] - rp_host[r] <= MMQ_ALLOC_CAP) ++e;
+    r = e;
+  }
+  ts.push_back(h->m);
+  h->n_tiles = (int64_t)ts.size() - 1;
+  int rc = mmq_dev_alloc(h, (void**)&h->tile_start, sizeof(int64_t) * ts.size());
+  if (rc) return rc;
+  MMQ_CUDA(h, cudaMemcpyAsync(h->tile_start, ts.data(), sizeof(int64_t) * ts.size(), cudaMemcpyHostToDevice, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream)); /* ts is a host temporary */
+  return MMQ_OK;
+}
+
 static int build_transpose(mmq_handle* h) {
   if (h->tptr) return MMQ_OK; /* built on first use: the fused Gibbs path never needs it */
   const int64_t nnz = h->nnz, n = h->n, m = h->m;
@@ -710,6 +718,10 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   CREATE_TRY(upload(h, (void**)&h->row_ptr, p->row_ptr, sizeof(int64_t) * (size_t)(p->m + 1)));
   CREATE_TRY(upload(h, (void**)&h->col, p->col, sizeof(int32_t) * (size_t)p->nnz, 16)); /* +4 entries: aligned 128-bit staging may over-read */
   if (h->has_k) CREATE_TRY(upload(h, (void**)&h->k, p->k, sizeof(int32_t) * (size_t)p->m));
+  if (p->class_id) {
+    if (!h->has_k) { h->err = "mmq_create: class_id needs k (the k == 1 kernels pair consecutive class ids)"; CREATE_TRY(MMQ_ERR_ARG); }
+    CREATE_TRY(upload(h, (void**)&h->class_id, p->class_id, sizeof(int64_t) * (size_t)p->m));
+  }
   if (h->has_w) CREATE_TRY(upload(h, (void**)&h->w, p->weight, sizeof(float) * (size_t)p->nnz, 16));
   CREATE_TRY(upload(h, (void**)&h->len, p->len, sizeof(double) * (size_t)p->n));
   CREATE_TRY(mmq_dev_alloc(h, (void**)&h->mu, sizeof(double) * (size_t)(p->n + 1))); /* mu[n] == 0: gather sentinel */
@@ -736,14 +748,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
     if (flags & 2) { h->err = "mmq_create: column index out of range"; CREATE_TRY(MMQ_ERR_ARG); }
     if (flags & 4) { h->err = "mmq_create: columns must be strictly ascending within a class (src/mmseq.cpp:412)"; CREATE_TRY(MMQ_ERR_ARG); }
   }
-  /* tile shape: as many classes per CTA as keeps the mean tile inside the staging buffer */
-  {
-    const double mean_d = p->m > 0 ? (double)p->nnz / (double)p->m : 1.0;
-    int r = MMQ_ALLOC_THREADS;
-    while (r > 32 && (double)r * mean_d * 1.25 > (double)MMQ_ALLOC_CAP) r >>= 1;
-    h->rows_per_tile = r;
-    h->n_tiles = (p->m + r - 1) / r;
-  }
+  if (h->has_k) CREATE_TRY(build_tiles(h, p->row_ptr)); /* k == 1 shards build them on first use of the general kernel */
   if (!h->has_k) CREATE_TRY(mmq_seg_plan(h, p->row_ptr));
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
 #undef CREATE_TRY
@@ -939,7 +944,7 @@ static int ensure_x(mmq_handle* h) {
 } /* extern "C" */
 template <bool MAT>
 static void launch_alloc_t(mmq_handle* h, int grid, uint32_t seed, uint32_t sweep) {
-#define MMQ_ALLOC_ARGS h->row_ptr, h->col, h->k, h->w, h->mu, h->counts, h->x, h->m, h->rows_per_tile, h->n_tiles, seed, sweep, h->class_id_base
+#define MMQ_ALLOC_ARGS h->row_ptr, h->col, h->k, h->w, h->mu, h->counts, h->x, h->m, h->tile_start, h->n_tiles, seed, sweep, h->class_id_base, h->class_id
   if (h->has_k) {
     if (h->has_w) k_alloc<MAT, true, true><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
     else k_alloc<MAT, true, false><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
@@ -964,7 +969,9 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
     v.push_back(e);
   };
   if (h->m > 0) {
-    const int grid = (int)std::min<int64_t>(h->n_tiles, (int64_t)h->num_sms * 6);
+    const bool needs_tiles = transposed || h->has_k || (flags & MMQ_GIBBS_GENERIC_KERNEL);
+    if (needs_tiles && (rc = build_tiles(h, nullptr))) return rc;
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(h->n_tiles, 1), (int64_t)h->num_sms * 6);
     if (transposed) {
       if ((rc = ensure_x(h))) return rc;
       if ((rc = build_transpose(h))) return rc;

@@ -35,13 +35,14 @@ struct mmq_handle {
   int64_t n = 0, m = 0, nnz = 0, class_id_base = 0;
   double alpha = 0.1, beta = 0.1;
   bool has_k = false, has_w = false;
-  int rows_per_tile = MMQ_ALLOC_THREADS;
+  int64_t* tile_start = nullptr; /* [n_tiles+1] class ranges of the general allocation kernel */
   int64_t n_tiles = 0;
 
   /* class-major CSR */
   int64_t* row_ptr = nullptr; /* [m+1] */
   int32_t* col = nullptr;     /* [nnz] */
   int32_t* k = nullptr;       /* [m] or null */
+  int64_t* class_id = nullptr; /* [m] or null */
   float* w = nullptr;         /* [nnz] or null */
   double* len = nullptr;      /* [n] */
   /* transcript-major transpose */

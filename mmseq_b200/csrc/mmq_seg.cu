@@ -155,8 +155,8 @@ __device__ __forceinline__ int32_t seg_row_generic(const int32_t* __restrict__ c
   return c[chosen];
 }
 
-template <bool HAS_W, int MAXD>
-__global__ void __launch_bounds__(MMQ_SEG_WARPS * 32, MAXD > 6 ? 2 : 3)
+template <bool HAS_W, int MAXD, int OCC>
+__global__ void __launch_bounds__(MMQ_SEG_WARPS * 32, OCC)
 k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, const int32_t* __restrict__ colp,
             const float* __restrict__ wp, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
             uint32_t sweep, int32_t sentinel) {
@@ -213,6 +213,156 @@ k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, c
   }
 }
 
+
+/* ---- entry-parallel variant -------------------------------------------------------------
+ * Same plan, other mapping of work to lanes.  The chunk's 64*D contiguous columns are fetched
+ * by ONE TMA bulk copy into the warp's shared-memory double buffer (issued one chunk ahead).
+ * Phase E: lane l takes entries l, l+32, ... of the chunk: neighbouring lanes read neighbouring
+ *   entries, i.e. the members of the same few classes, whose mu lie in the same one or two
+ *   cache lines (header-order numbering keeps a gene's isoforms adjacent) — a gather request
+ *   costs 1-3 L1 wavefronts instead of one per lane — and stores p = mu[col]*w to shared memory.
+ * Phase R: lane l owns classes 2l, 2l+1: running sums left to right from shared memory, one
+ *   Philox block for both, chosen column read back from the staged columns.
+ * Row pitch in the p buffer is odd (D | 1) so the owners' strided reads stay 2-way conflicted
+ * at worst. */
+#define MMQ_SEG2_DMAX 6
+#define MMQ_SEG2_WARPS 8
+
+template <int D, bool HAS_W>
+__device__ __forceinline__ void seg2_chunk(const int32_t* __restrict__ sc, const float* __restrict__ sw, double* __restrict__ sp,
+                                           int row_lo, int row_hi, double ua, double ub, const double* __restrict__ mu,
+                                           int32_t sentinel, int lane, int32_t& out_a, int32_t& out_b) {
+  constexpr int PITCH = D | 1;
+  /* phase E */
+#pragma unroll
+  for (int q = 0; q < 2 * D; ++q) {
+    const int e = q * 32 + lane;
+    const int r = e / D;
+    const int j = e - r * D;
+    int32_t c = sc[e];
+    if (r < row_lo || r >= row_hi) c = sentinel; /* dummy first row / rows past the end of the run */
+    double p = mu[c];
+    if (HAS_W) p *= (double)sw[e];
+    sp[r * PITCH + j] = p;
+  }
+  __syncwarp();
+  /* phase R */
+  const int ra = 2 * lane, rb = ra + 1;
+  double S[2 * D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) { S[j] = sp[ra * PITCH + j]; S[D + j] = sp[rb * PITCH + j]; }
+  auto pick = [&](const double* p, double u) -> int {
+    double R[D];
+    R[0] = p[0];
+#pragma unroll
+    for (int j = 1; j < D; ++j) R[j] = R[j - 1] + p[j];
+    const double target = u * R[D - 1];
+    int chosen = -1;
+#pragma unroll
+    for (int j = D - 1; j >= 0; --j)
+      if (target < R[j]) chosen = j;
+    if (chosen < 0) { /* rounding at the top end or all-zero row: last member with p > 0, else the last */
+      chosen = D - 1;
+#pragma unroll
+      for (int j = 0; j < D; ++j)
+        if (p[j] > 0.0) chosen = j;
+      bool any = false;
+#pragma unroll
+      for (int j = 0; j < D; ++j) any |= p[j] > 0.0;
+      if (!any) chosen = D - 1;
+    }
+    return chosen;
+  };
+  const bool va = ra >= row_lo && ra < row_hi, vb = rb >= row_lo && rb < row_hi;
+  out_a = va ? sc[ra * D + pick(S, ua)] : -1;
+  out_b = vb ? sc[rb * D + pick(S + D, ub)] : -1;
+  __syncwarp(); /* sp is reused by the next chunk */
+}
+
+template <bool HAS_W>
+__global__ void __launch_bounds__(MMQ_SEG2_WARPS * 32, 3)
+k_alloc_seg2(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, const int32_t* __restrict__ colp,
+             const float* __restrict__ wp, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
+             uint32_t sweep, int32_t sentinel) {
+  constexpr int CAP = MMQ_SEG_ROWS * MMQ_SEG2_DMAX;                  /* staged entries per buffer */
+  constexpr int PCAP = MMQ_SEG_ROWS * (MMQ_SEG2_DMAX | 1);           /* p buffer, doubles */
+  constexpr int PER_WARP = 16 + PCAP * 8 + 2 * CAP * 4 * (HAS_W ? 2 : 1);
+  extern __shared__ __align__(16) unsigned char seg2_smem[];
+  __shared__ mmq_seg s_seg[MMQ_SEG_MAX];
+  for (int i = threadIdx.x; i < nsegs; i += blockDim.x) s_seg[i] = segs[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  unsigned char* wbase = seg2_smem + wib * PER_WARP;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(wbase);
+  double* sp = reinterpret_cast<double*>(wbase + 16);
+  int32_t* sc = reinterpret_cast<int32_t*>(wbase + 16 + PCAP * 8);            /* [2][CAP] */
+  float* sw = reinterpret_cast<float*>(wbase + 16 + PCAP * 8 + 2 * CAP * 4);  /* [2][CAP] when HAS_W */
+  const int64_t warp0 = (int64_t)blockIdx.x * MMQ_SEG2_WARPS + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * MMQ_SEG2_WARPS;
+  if (warp0 >= total_chunks) return;
+  if (lane == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  struct Desc { int64_t e0, cid0; int d, row_lo, row_hi; bool staged; };
+  int si = 0;
+  auto describe = [&](int64_t chunk, int buf) -> Desc { /* also launches the bulk copy of a staged chunk */
+    while (si + 1 < nsegs && chunk >= s_seg[si + 1].chunk0) ++si;
+    const mmq_seg& sg = s_seg[si];
+    Desc ds;
+    const int r0 = (int)(chunk - sg.chunk0) * MMQ_SEG_ROWS;
+    ds.d = sg.d;
+    ds.e0 = sg.e_virtual + (int64_t)r0 * sg.d;
+    ds.cid0 = sg.cid_virtual + r0;
+    ds.row_lo = r0 == 0 ? sg.row_lo : 0;
+    ds.row_hi = sg.rows - r0 < MMQ_SEG_ROWS ? sg.rows - r0 : MMQ_SEG_ROWS;
+    ds.staged = sg.d <= MMQ_SEG2_DMAX;
+    if (ds.staged && lane == 0) {
+      const uint32_t bytes = (uint32_t)(MMQ_SEG_ROWS * sg.d * 4); /* 256*d: a multiple of 16; the packed array has slack */
+      mbar_expect_tx(&mbar[buf], HAS_W ? 2 * bytes : bytes);
+      bulk_g2s(sc + buf * CAP, colp + ds.e0, bytes, &mbar[buf]);
+      if (HAS_W) bulk_g2s(sw + buf * CAP, wp + ds.e0, bytes, &mbar[buf]);
+    }
+    return ds;
+  };
+  uint32_t uses0 = 0, uses1 = 0;
+  Desc cur = describe(warp0, 0);
+  int it = 0;
+  for (int64_t chunk = warp0; chunk < total_chunks; chunk += nwarps, ++it) {
+    const int buf = it & 1;
+    Desc next = cur;
+    if (chunk + nwarps < total_chunks) next = describe(chunk + nwarps, buf ^ 1);
+    const int D = cur.d;
+    const uint64_t cid = (uint64_t)(cur.cid0 + 2 * lane);
+    uint32_t wd[4] = {(uint32_t)(cid >> 1), (uint32_t)(cid >> 33), sweep, 0u};
+    mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
+    const double ua = cat_u52(wd[0], wd[1]), ub = cat_u52(wd[2], wd[3]);
+    int32_t ca = -1, cb = -1;
+    if (cur.staged) {
+      mbar_wait(&mbar[buf], (buf ? uses1 : uses0) & 1u);
+      if (buf) ++uses1; else ++uses0;
+      const int32_t* c0 = sc + buf * CAP;
+      const float* w0 = sw + buf * CAP;
+      if (D == 2) seg2_chunk<2, HAS_W>(c0, w0, sp, cur.row_lo, cur.row_hi, ua, ub, mu, sentinel, lane, ca, cb);
+      else if (D == 3) seg2_chunk<3, HAS_W>(c0, w0, sp, cur.row_lo, cur.row_hi, ua, ub, mu, sentinel, lane, ca, cb);
+      else if (D == 4) seg2_chunk<4, HAS_W>(c0, w0, sp, cur.row_lo, cur.row_hi, ua, ub, mu, sentinel, lane, ca, cb);
+      else if (D == 5) seg2_chunk<5, HAS_W>(c0, w0, sp, cur.row_lo, cur.row_hi, ua, ub, mu, sentinel, lane, ca, cb);
+      else seg2_chunk<6, HAS_W>(c0, w0, sp, cur.row_lo, cur.row_hi, ua, ub, mu, sentinel, lane, ca, cb);
+    } else {
+      const int ra = 2 * lane;
+      const int64_t e = cur.e0 + (int64_t)ra * D;
+      if (ra >= cur.row_lo && ra < cur.row_hi) ca = seg_row_generic<HAS_W>(colp + e, wp + e, D, mu, ua);
+      if (ra + 1 < cur.row_hi) cb = seg_row_generic<HAS_W>(colp + e + D, wp + e + D, D, mu, ub);
+    }
+    cat_red(counts, ca, lane);
+    cat_red(counts, cb, lane);
+    __syncwarp();
+    cur = next;
+  }
+}
+
 /* ------------------------------------------------------------------ host */
 
 int mmq_seg_add_base(mmq_handle* h, bool want_in_counts) {
@@ -261,7 +411,7 @@ int mmq_seg_plan(mmq_handle* h, const int64_t* rp) {
     segs.push_back(sg);
   }
   if (segs.empty() && singles == 0) return MMQ_OK;
-  packed = ((packed + 3) & ~(int64_t)3) + 64; /* slack: the last lane of a tail chunk never reads, but keep loads in bounds */
+  packed = ((packed + 3) & ~(int64_t)3) + 64 * 8 + 64; /* slack: the bulk copy of a run's last chunk always moves 64 rows */
   int rc;
   if ((rc = mmq_dev_alloc(h, (void**)&h->seg_col, sizeof(int32_t) * (size_t)packed))) return rc;
   k_fill_i32<<<mmq_grid_for(packed, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->seg_col, packed, (int32_t)h->n);
@@ -308,20 +458,39 @@ int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep) {
   int rc = mmq_seg_add_base(h, true);
   if (rc) return rc;
   if (h->seg_count == 0) return MMQ_OK; /* only singletons: nothing random to do */
+  static const int variant = [] { const char* e = getenv("MMQ_SEG_KERNEL"); return e ? atoi(e) : 1; }(); /* 1 row-parallel, 2 entry-parallel */
+#define MMQ_SEG_ARGS (const mmq_seg*)h->seg_table, h->seg_count, h->seg_chunks, h->seg_col, h->seg_w, h->mu, h->counts, seed, sweep, (int32_t)h->n
+  if (variant == 2) {
+    const int64_t want2 = (h->seg_chunks + MMQ_SEG2_WARPS - 1) / MMQ_SEG2_WARPS;
+    const int grid2 = (int)std::min<int64_t>(want2, (int64_t)h->num_sms * 3);
+    constexpr int CAP = MMQ_SEG_ROWS * MMQ_SEG2_DMAX, PCAP = MMQ_SEG_ROWS * (MMQ_SEG2_DMAX | 1);
+    if (h->has_w) {
+      constexpr int SM = MMQ_SEG2_WARPS * (16 + PCAP * 8 + 2 * CAP * 4 * 2);
+      MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_seg2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+      k_alloc_seg2<true><<<grid2, MMQ_SEG2_WARPS * 32, SM, h->stream>>>(MMQ_SEG_ARGS);
+    } else {
+      constexpr int SM = MMQ_SEG2_WARPS * (16 + PCAP * 8 + 2 * CAP * 4);
+      MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_seg2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
+      k_alloc_seg2<false><<<grid2, MMQ_SEG2_WARPS * 32, SM, h->stream>>>(MMQ_SEG_ARGS);
+    }
+    return MMQ_OK;
+  }
   const int64_t want = (h->seg_chunks + MMQ_SEG_WARPS - 1) / MMQ_SEG_WARPS;
   static const int maxd_env = [] { const char* e = getenv("MMQ_SEG_MAXD"); return e ? atoi(e) : 0; }(); /* tuning knob */
   const int maxd = maxd_env ? maxd_env : (h->has_w ? 4 : 6); /* largest class size with a register-resident specialisation */
-  const int occ = maxd > 6 ? 2 : 3;
+  static const int occ_env = [] { const char* e = getenv("MMQ_SEG_OCC"); return e ? atoi(e) : 0; }();
+  const int occ = maxd > 6 ? 2 : (occ_env == 4 && maxd <= 4 ? 4 : 3);
   const int grid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * occ);
-#define MMQ_SEG_ARGS (const mmq_seg*)h->seg_table, h->seg_count, h->seg_chunks, h->seg_col, h->seg_w, h->mu, h->counts, seed, sweep, (int32_t)h->n
   if (h->has_w) {
-    if (maxd > 6) k_alloc_seg<true, 8><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else if (maxd > 4) k_alloc_seg<true, 6><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else k_alloc_seg<true, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    if (maxd > 6) k_alloc_seg<true, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else if (maxd > 4) k_alloc_seg<true, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else if (occ == 4) k_alloc_seg<true, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else k_alloc_seg<true, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
   } else {
-    if (maxd > 6) k_alloc_seg<false, 8><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else if (maxd > 4) k_alloc_seg<false, 6><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else k_alloc_seg<false, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    if (maxd > 6) k_alloc_seg<false, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else if (maxd > 4) k_alloc_seg<false, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else if (occ == 4) k_alloc_seg<false, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    else k_alloc_seg<false, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
   }
 #undef MMQ_SEG_ARGS
   return MMQ_OK;

@@ -275,36 +275,57 @@ int main(int argc, char** argv) {
     if (mmq::scaled_lengths(hdr, cls, l, err)) die(err);
   }
 
-  /* ---- shards on the GPUs: contiguous class blocks balanced by CSR entries */
-  vector<Shard> shards((size_t)ngpus);
+  /* ---- device order of the classes: sorted by the work their allocation needs (no draw for
+   * singletons; one categorical draw for k == 1; k draws for 2 <= k <= 8; a binomial chain above),
+   * then by size and count, so that the classes a warp works on are alike.  The Philox counter of
+   * a class stays its first-appearance index (mmq_problem.class_id): the chain is the one of the
+   * canonical order, whatever the device order and the number of GPUs.  Shard g takes every
+   * ngpus-th class of the sorted order (equal mix of cheap and expensive classes per GPU). */
+  vector<int64_t> order((size_t)m);
+  for (int64_t i = 0; i < m; ++i) order[(size_t)i] = i;
   {
-    const int64_t nnz = cls.row_ptr[(size_t)m];
-    int64_t r = 0;
-    for (int g = 0; g < ngpus; ++g) {
-      shards[(size_t)g].device = g;
-      shards[(size_t)g].row0 = r;
-      const int64_t target = nnz * (g + 1) / ngpus;
-      while (r < m && cls.row_ptr[(size_t)r + 1] <= target) ++r;
-      if (g == ngpus - 1) r = m;
-      shards[(size_t)g].row1 = r;
-    }
+    auto kind = [&](int64_t i) {
+      const int64_t d = cls.row_ptr[(size_t)i + 1] - cls.row_ptr[(size_t)i];
+      const int32_t kk = cls.k[(size_t)i];
+      return d == 1 ? 0 : (kk == 1 ? 1 : (kk <= 8 ? 2 : 3));
+    };
+    stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+      const int ka = kind(a), kb = kind(b);
+      if (ka != kb) return ka < kb;
+      const int64_t da = cls.row_ptr[(size_t)a + 1] - cls.row_ptr[(size_t)a], db = cls.row_ptr[(size_t)b + 1] - cls.row_ptr[(size_t)b];
+      if (da != db) return da < db;
+      return cls.k[(size_t)a] < cls.k[(size_t)b];
+    });
   }
-  vector<vector<int64_t>> shard_rp((size_t)ngpus);
+  vector<Shard> shards((size_t)ngpus);
+  vector<vector<int64_t>> shard_rp((size_t)ngpus), shard_id((size_t)ngpus);
+  vector<vector<int32_t>> shard_col((size_t)ngpus), shard_k((size_t)ngpus);
   for (int g = 0; g < ngpus; ++g) {
     Shard& S = shards[(size_t)g];
+    S.device = g;
     auto& rp = shard_rp[(size_t)g];
-    rp.resize((size_t)(S.row1 - S.row0) + 1);
-    const int64_t off = cls.row_ptr[(size_t)S.row0];
-    for (int64_t i = S.row0; i <= S.row1; ++i) rp[(size_t)(i - S.row0)] = cls.row_ptr[(size_t)i] - off;
+    auto& id = shard_id[(size_t)g];
+    auto& cc = shard_col[(size_t)g];
+    auto& kk = shard_k[(size_t)g];
+    rp.push_back(0);
+    for (int64_t j = g; j < m; j += ngpus) {
+      const int64_t i = order[(size_t)j];
+      id.push_back(i);
+      kk.push_back(cls.k[(size_t)i]);
+      for (int64_t q = cls.row_ptr[(size_t)i]; q < cls.row_ptr[(size_t)i + 1]; ++q) cc.push_back(cls.col[(size_t)q]);
+      rp.push_back((int64_t)cc.size());
+    }
+    S.row0 = 0; S.row1 = (int64_t)id.size();
     mmq_problem p;
     memset(&p, 0, sizeof p);
-    p.n = n; p.m = S.row1 - S.row0; p.nnz = rp.back();
+    p.n = n; p.m = (int64_t)id.size(); p.nnz = rp.back();
     p.row_ptr = rp.data();
-    p.col = cls.col.data() + off;
-    p.k = cls.k.data() + S.row0;
+    p.col = cc.data();
+    p.k = kk.data();
     p.weight = nullptr;
     p.len = l.data();
-    p.alpha = alpha; p.beta = beta; p.class_id_base = S.row0;
+    p.alpha = alpha; p.beta = beta; p.class_id_base = 0;
+    p.class_id = id.data();
     int rc = mmq_create(&p, S.device, &S.h);
     if (rc) die(string("Error: mmq_create: ") + mmq_last_error(nullptr));
   }

@@ -105,3 +105,17 @@ def from_records(T, efflen, frag_ptr, frag_tid, frag_w=None, layout=LAYOUT_COLLA
     if not h:
         raise RuntimeError(err.value.decode())
     return Hits(h, with_names=False)
+
+
+def sort_classes_by_cost(h):
+    """Device order of collapsed classes (as mmseq_main.cpp): by kind of draw (singleton, k == 1,
+    2..8, binomial chain), then size, then count.  Returns (row_ptr, col, k, class_id) where
+    class_id[i] is the canonical (first-appearance) index to hand to mmq_problem.class_id."""
+    d = np.diff(h.row_ptr)
+    kind = np.where(d == 1, 0, np.where(h.k == 1, 1, np.where(h.k <= 8, 2, 3)))
+    order = np.lexsort((h.k, d, kind))
+    dd = d[order]
+    rp = np.concatenate([[0], np.cumsum(dd)]).astype(np.int64)
+    starts = h.row_ptr[:-1][order]
+    idx = np.repeat(starts - rp[:-1], dd) + np.arange(int(rp[-1]))
+    return rp, h.col[idx], h.k[order], order.astype(np.int64)

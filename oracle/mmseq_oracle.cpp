@@ -184,10 +184,10 @@ int orc_em(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const in
  *   counts[t] = sum_i x_it                             (:887, :895-899)
  *   mu[t] ~ Gamma(alpha + counts[t], 1/(beta + l[t]))  (:904-908)
  * x (nnz ints, CSR order) and counts are optional outputs of this sweep. */
-void orc_sweep_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+static void sweep_replay_impl(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
                       const float* w, const double* l, double alpha, double beta, uint32_t seed,
                       uint32_t sweep, int64_t class_id_base, double* mu, int32_t* x_out,
-                      int32_t* counts_out, int do_gamma) {
+                      int32_t* counts_out, int do_gamma, const int64_t* class_id) {
   std::vector<int32_t> counts((size_t)n, 0);
   std::vector<double> p;
   std::vector<int32_t> x;
@@ -199,7 +199,7 @@ void orc_sweep_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* co
       const int64_t q = rp[i] + j;
       p[(size_t)j] = w ? mu[col[q]] * (double)w[q] : mu[col[q]];
     }
-    mmq_alloc_row(p.data(), x.data(), d, (int64_t)(k ? k[i] : 1), seed, (uint64_t)(class_id_base + i), sweep);
+    mmq_alloc_row(p.data(), x.data(), d, (int64_t)(k ? k[i] : 1), seed, (uint64_t)(class_id ? class_id[i] : class_id_base + i), sweep);
     for (int j = 0; j < d; ++j) {
       const int64_t q = rp[i] + j;
       counts[(size_t)col[q]] += x[(size_t)j];
@@ -213,6 +213,21 @@ void orc_sweep_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* co
       mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
       mu[t] = mmq_gamma(&g, alpha + (double)counts[(size_t)t], beta + l[t]);
     }
+}
+
+void orc_sweep_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+                      const float* w, const double* l, double alpha, double beta, uint32_t seed,
+                      uint32_t sweep, int64_t class_id_base, double* mu, int32_t* x_out,
+                      int32_t* counts_out, int do_gamma) {
+  sweep_replay_impl(m, n, rp, col, k, w, l, alpha, beta, seed, sweep, class_id_base, mu, x_out, counts_out, do_gamma, nullptr);
+}
+
+/* Same sweep with explicit Philox counters per class (classes handed over in any order). */
+void orc_sweep_replay_ids(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k,
+                          const float* w, const double* l, double alpha, double beta, uint32_t seed,
+                          uint32_t sweep, const int64_t* class_id, double* mu, int32_t* x_out,
+                          int32_t* counts_out, int do_gamma) {
+  sweep_replay_impl(m, n, rp, col, k, w, l, alpha, beta, seed, sweep, 0, mu, x_out, counts_out, do_gamma, class_id);
 }
 
 /* Gamma step alone from given counts (used for the multi-shard replay). */

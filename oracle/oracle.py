@@ -48,6 +48,7 @@ def lib():
         L.orc_em.restype = i32
         L.orc_em.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, i32, dbl, vp, vp]
         L.orc_sweep_replay.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, u32, i64, vp, vp, vp, i32]
+        L.orc_sweep_replay_ids.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, u32, vp, vp, vp, vp, i32]
         L.orc_gamma_replay.argtypes = [i64, vp, vp, dbl, dbl, u32, u32, vp]
         L.orc_gibbs_replay.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, i64, i64, i32, i32, vp, vp]
         L.orc_prior_replay.argtypes = [i64, vp, vp, dbl, dbl, u32, i32, vp]
@@ -165,6 +166,14 @@ class Problem:
         x = np.zeros(int(rp[-1]), np.int32); counts = np.zeros(self.n, np.int32)
         lib().orc_sweep_replay(m, self.n, _p(rp), _p(col), _p(k), _p(w), _p(self.len), self.alpha, self.beta,
                                seed, sweep, class_id_base, _p(mu), _p(x), _p(counts), int(do_gamma))
+        return x, counts, mu
+
+    def sweep_replay_ids(self, mu, seed, sweep, class_id, do_gamma=True):
+        """One sweep with explicit Philox counters per class (any class order)."""
+        mu = np.array(mu, np.float64); cid = _c(class_id, np.int64)
+        x = np.zeros(self.nnz, np.int32); counts = np.zeros(self.n, np.int32)
+        lib().orc_sweep_replay_ids(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(self.w), _p(self.len), self.alpha,
+                                   self.beta, seed, sweep, _p(cid), _p(mu), _p(x), _p(counts), int(do_gamma))
         return x, counts, mu
 
     def gamma_replay(self, counts, seed, sweep):

@@ -211,6 +211,35 @@ def test_class_id_base_shards_reproduce_the_whole(small_problem):
     assert np.array_equal(parts[0] + parts[1], c_o)
 
 
+def test_explicit_class_ids_make_the_chain_order_independent(small_problem):
+    """mmq_problem.class_id: classes handed over sorted by cost (what the host program does) give
+    the counts and the chain of the canonical order, bit for bit."""
+    h = small_problem
+    P = _oracle(h)
+    mu, _, _ = P.init_mu()
+    rp, col, k, cid = hostlib.sort_classes_by_cost(h)
+    assert not np.array_equal(cid, np.arange(h.m))
+    with capi.Handle(rp, col, k, h.len, class_id=cid) as H:
+        for sweep in range(3):
+            x_o, c_o, mu_o = P.sweep_replay(mu, SEED, sweep)
+            for flags in (capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_TRANSPOSED):
+                H.set_mu(mu)
+                x, c, mu_g = H.sweep_debug(SEED, sweep, flags)
+                assert np.array_equal(c, c_o) and np.array_equal(mu_g, mu_o)
+                if x is not None:   # X comes back in the order the classes were handed over
+                    d = np.diff(h.row_ptr)[cid]
+                    starts = h.row_ptr[:-1][cid]
+                    idx = np.repeat(starts - rp[:-1], d) + np.arange(int(rp[-1]))
+                    assert np.array_equal(x, x_o[idx])
+            mu = mu_o
+        H.init_mu()
+        it, ll, _ = H.em(1000, 0.1)
+        mu_em, it_o, ll_o, _ = P.em(P.init_mu()[0], 1000, 0.1)
+        assert it == it_o and np.max(np.abs(H.get_mu() / mu_em - 1)) <= 1e-6
+    with pytest.raises(capi.MmqError):
+        capi.Handle(rp, col, None, h.len, class_id=cid)      # k == 1 shards pair consecutive ids
+
+
 def test_posterior_matches_reference_like_chain(small_problem):
     """north_star (c): log_mu within the stated Monte-Carlo standard error of the GSL-style
     MT19937 chain, and the sd of log mu no further from it than a second, independently
