@@ -329,8 +329,15 @@ def main():
     b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S, args.layout)
     alloc_ms_avg = alloc_ms / max(alloc_n, 1)
     achieved = b_alloc / (alloc_ms_avg * 1e-3) / 1e9 if alloc_n else None
-    roofline = {"kernel": "k_alloc", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+    kernel_name = "k_alloc_seg" if (args.layout == "perfragment" and not args.transposed) else ("k_alloc_cat" if h.k is None and not args.transposed else "k_alloc")
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.fragments == N_C2 and args.transcripts == T_C2 and not args.weights:
+        tj = json.load(open(tpath)).get(kernel_name)
+        if tj and tj.get("workload") == f"C2-{args.layout}":
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]   # per launch, from one ncu --set full capture
+    roofline = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(b_alloc), "avg_launch_ms": alloc_ms_avg, "launches_timed": int(alloc_n),
                 "share_of_step": alloc_ms / ms if ms > 0 else None,
                 "gamma_avg_launch_ms": gamma_ms / max(gamma_n, 1),

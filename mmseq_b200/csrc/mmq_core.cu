@@ -260,34 +260,43 @@ struct PGlobal {
 };
 
 /* K2: allocate the k_i fragments of every hit class among its transcripts.
- * A CTA takes a tile of consecutive classes (as many as fit the staging buffer, at
- * most one per thread; boundaries precomputed in mmq_create), stages the tile's
+ * A warp takes a tile of consecutive classes (as many as fit its staging slab, at
+ * most one per lane; boundaries precomputed in mmq_create), stages the tile's
  * contiguous CSR segment (columns, and p = mu[col] * weight gathered once) in
  * shared memory with coalesced loads, then one thread per class runs
  * mmq_alloc_row on its slice.  MATERIALIZE writes x into the X array (CSR
  * order) for k_count_reduce; otherwise each non-zero x goes straight to
  * counts[] as a reduction (the fused path).  Persistent over tiles. */
 template <bool MATERIALIZE, bool HAS_K, bool HAS_W>
-__global__ void __launch_bounds__(MMQ_ALLOC_THREADS)
+__global__ void __launch_bounds__(MMQ_ALLOC_WARPS * 32, 3)
 k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
         const int32_t* __restrict__ kk, const float* __restrict__ w, const double* __restrict__ mu,
         int32_t* __restrict__ counts, int32_t* __restrict__ xout, int64_t m, const int64_t* __restrict__ tile_start,
         int64_t n_tiles, uint32_t seed, uint32_t sweep, int64_t class_id_base, const int64_t* __restrict__ class_id) {
-  __shared__ double s_p[MMQ_ALLOC_CAP];
-  __shared__ int32_t s_c[MMQ_ALLOC_CAP];
-  __shared__ int32_t s_x[MATERIALIZE ? MMQ_ALLOC_CAP : 1];
-  __shared__ int64_t s_rp[MMQ_ALLOC_THREADS + 1];
-  const int tid = threadIdx.x;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  /* every warp owns its tiles and its staging slab: no block-level barrier, the warps of an SM
+   * overlap each other's load latency */
+  __shared__ double s_p_all[MMQ_ALLOC_WARPS][MMQ_ALLOC_CAP];
+  __shared__ int32_t s_c_all[MMQ_ALLOC_WARPS][MMQ_ALLOC_CAP];
+  __shared__ int32_t s_x_all[MATERIALIZE ? MMQ_ALLOC_WARPS : 1][MATERIALIZE ? MMQ_ALLOC_CAP : 1];
+  __shared__ int64_t s_rp_all[MMQ_ALLOC_WARPS][33];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  double* s_p = s_p_all[wib];
+  int32_t* s_c = s_c_all[wib];
+  int32_t* s_x = s_x_all[MATERIALIZE ? wib : 0];
+  int64_t* s_rp = s_rp_all[wib];
+  const int64_t warp0 = (int64_t)blockIdx.x * MMQ_ALLOC_WARPS + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * MMQ_ALLOC_WARPS;
+  for (int64_t tile = warp0; tile < n_tiles; tile += nwarps) {
     const int64_t r0 = tile_start[tile];
-    const int nrows = (int)(tile_start[tile + 1] - r0);
-    for (int i = tid; i <= nrows; i += MMQ_ALLOC_THREADS) s_rp[i] = row_ptr[r0 + i];
-    __syncthreads();
+    const int nrows = (int)(tile_start[tile + 1] - r0); /* <= 32 */
+    if (lane <= nrows) s_rp[lane] = row_ptr[r0 + lane];
+    if (lane == 0 && nrows == 32) s_rp[32] = row_ptr[r0 + 32];
+    __syncwarp();
     const int64_t base = s_rp[0];
     const int64_t cnt = s_rp[nrows] - base;
     const bool staged = cnt <= MMQ_ALLOC_CAP;
     if (staged) {
-      for (int q = tid; q < (int)cnt; q += MMQ_ALLOC_THREADS) {
+      for (int q = lane; q < (int)cnt; q += 32) {
         const int32_t c = col[base + q];
         double p = mu[c];
         if (HAS_W) p *= (double)w[base + q];
@@ -295,12 +304,12 @@ k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
         s_p[q] = p;
       }
     }
-    __syncthreads();
-    if (tid < nrows) {
-      const int64_t rb = s_rp[tid];
-      const int d = (int)(s_rp[tid + 1] - rb);
-      const int64_t kv = HAS_K ? (int64_t)kk[r0 + tid] : 1;
-      const uint64_t cid = (uint64_t)(class_id ? class_id[r0 + tid] : class_id_base + r0 + tid);
+    __syncwarp();
+    if (lane < nrows) {
+      const int64_t rb = s_rp[lane];
+      const int d = (int)(s_rp[lane + 1] - rb);
+      const int64_t kv = HAS_K ? (int64_t)kk[r0 + lane] : 1;
+      const uint64_t cid = (uint64_t)(class_id ? class_id[r0 + lane] : class_id_base + r0 + lane);
       if (staged) {
         const int off = (int)(rb - base);
         if (MATERIALIZE) mmq_alloc_row(s_p + off, s_x + off, d, kv, seed, cid, sweep);
@@ -311,9 +320,10 @@ k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
         else mmq_alloc_row(pg, XRed{col + rb, counts}, d, kv, seed, cid, sweep);
       }
     }
-    __syncthreads();
+    __syncwarp();
     if (MATERIALIZE && staged)
-      for (int q = tid; q < (int)cnt; q += MMQ_ALLOC_THREADS) xout[base + q] = s_x[q];
+      for (int q = lane; q < (int)cnt; q += 32) xout[base + q] = s_x[q];
+    __syncwarp();
   }
 }
 
@@ -607,7 +617,7 @@ static int upload(mmq_handle* h, void** dst, const void* src, size_t bytes, size
 }
 
 /* Tiles of the general allocation kernel: greedily as many consecutive classes as fit the
- * staging buffer (and one per thread); a class longer than the buffer is a tile of its own.
+ * warp's staging slab (and one per lane); a class longer than the slab is a tile of its own.
  * rp_host may be null: the row pointers are then read back from the device. */
 static int build_tiles(mmq_handle* h, const int64_t* rp_host) {
   if (h->tile_start) return MMQ_OK;
@@ -619,12 +629,12 @@ static int build_tiles(mmq_handle* h, const int64_t* rp_host) {
     rp_host = tmp.data();
   }
   std::vector<int64_t> ts;
-  ts.reserve((size_t)(h->m / 128 + 2));
+  ts.reserve((size_t)(h->m / 16 + 2));
   int64_t r = 0;
   while (r < h->m) {
     ts.push_back(r);
     int64_t e = r + 1;
-    while (e < h->m && e - r < MMQ_ALLOC_THREADS && rp_host[e + 1] - rp_host[r] <= MMQ_ALLOC_CAP) ++e;
+    while (e < h->m && e - r < 32 && rp_host[e + 1] - rp_host[r] <= MMQ_ALLOC_CAP) ++e;
     r = e;
   }
   ts.push_back(h->m);
@@ -736,6 +746,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   CREATE_TRY(cuda_try(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * (size_t)p->n, h->stream), "memset counts"));
   CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu, 0, sizeof(double) * (size_t)(p->n + 1), h->stream), "memset mu"));
   CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu_tmp, 0, sizeof(double) * (size_t)(p->n + 1), h->stream), "memset mu_tmp"));
+  if (!h->has_k) CREATE_TRY(mmq_seg_scan(h, p->row_ptr)); /* host scan, overlapped with the queued H2D copies */
   if (p->m > 0) { /* structural checks on the device: no O(nnz) host loop in front of the upload */
     int* d_flags = (int*)h->scalars;
     CREATE_TRY(cuda_try(cudaMemsetAsync(d_flags, 0, sizeof(int), h->stream), "memset flags"));
@@ -749,7 +760,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
     if (flags & 4) { h->err = "mmq_create: columns must be strictly ascending within a class (src/mmseq.cpp:412)"; CREATE_TRY(MMQ_ERR_ARG); }
   }
   if (h->has_k) CREATE_TRY(build_tiles(h, p->row_ptr)); /* k == 1 shards build them on first use of the general kernel */
-  if (!h->has_k) CREATE_TRY(mmq_seg_plan(h, p->row_ptr));
+  if (!h->has_k) CREATE_TRY(mmq_seg_plan(h));
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
 #undef CREATE_TRY
   *out = h;
@@ -946,11 +957,11 @@ template <bool MAT>
 static void launch_alloc_t(mmq_handle* h, int grid, uint32_t seed, uint32_t sweep) {
 #define MMQ_ALLOC_ARGS h->row_ptr, h->col, h->k, h->w, h->mu, h->counts, h->x, h->m, h->tile_start, h->n_tiles, seed, sweep, h->class_id_base, h->class_id
   if (h->has_k) {
-    if (h->has_w) k_alloc<MAT, true, true><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
-    else k_alloc<MAT, true, false><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+    if (h->has_w) k_alloc<MAT, true, true><<<grid, MMQ_ALLOC_WARPS * 32, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+    else k_alloc<MAT, true, false><<<grid, MMQ_ALLOC_WARPS * 32, 0, h->stream>>>(MMQ_ALLOC_ARGS);
   } else {
-    if (h->has_w) k_alloc<MAT, false, true><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
-    else k_alloc<MAT, false, false><<<grid, MMQ_ALLOC_THREADS, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+    if (h->has_w) k_alloc<MAT, false, true><<<grid, MMQ_ALLOC_WARPS * 32, 0, h->stream>>>(MMQ_ALLOC_ARGS);
+    else k_alloc<MAT, false, false><<<grid, MMQ_ALLOC_WARPS * 32, 0, h->stream>>>(MMQ_ALLOC_ARGS);
   }
 #undef MMQ_ALLOC_ARGS
 }
@@ -971,7 +982,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
   if (h->m > 0) {
     const bool needs_tiles = transposed || h->has_k || (flags & MMQ_GIBBS_GENERIC_KERNEL);
     if (needs_tiles && (rc = build_tiles(h, nullptr))) return rc;
-    const int grid = (int)std::min<int64_t>(std::max<int64_t>(h->n_tiles, 1), (int64_t)h->num_sms * 6);
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>((h->n_tiles + MMQ_ALLOC_WARPS - 1) / MMQ_ALLOC_WARPS, 1), (int64_t)h->num_sms * 3);
     if (transposed) {
       if ((rc = ensure_x(h))) return rc;
       if ((rc = build_transpose(h))) return rc;

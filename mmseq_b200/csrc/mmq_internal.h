@@ -12,10 +12,11 @@
 
 #include "../../include/mmq.h"
 
-/* Tiling of the allocation kernel: a CTA of MMQ_ALLOC_THREADS threads stages up
- * to MMQ_ALLOC_CAP CSR entries of up to MMQ_ALLOC_THREADS consecutive classes. */
+/* Tiling of the general allocation kernel: each of the MMQ_ALLOC_WARPS warps of a CTA
+ * stages up to MMQ_ALLOC_CAP CSR entries of up to 32 consecutive classes. */
 #define MMQ_ALLOC_THREADS 256
-#define MMQ_ALLOC_CAP 2048
+#define MMQ_ALLOC_WARPS 8
+#define MMQ_ALLOC_CAP 320 /* staged CSR entries per warp tile */
 
 struct mmq_group_set {
   int64_t ngroups = 0;
@@ -74,6 +75,9 @@ struct mmq_handle {
   /* segmented plan for k == 1 shards whose rows come in few runs of equal length
    * (the loader's by-length layout): packed, aligned copies of col / weight, a segment
    * table, and the constant counts of the singleton classes the sweep kernel skips */
+  struct seg_run { int64_t r0, r1, q0; int d; };
+  std::vector<seg_run> seg_runs; /* host scan of the row pointers */
+  bool seg_scan_ok = false;
   bool seg_ready = false;
   void* seg_table = nullptr; /* mmq_seg[] on the device */
   int seg_count = 0;
@@ -101,7 +105,8 @@ int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes);
 void mmq_dev_free(mmq_handle* h, void* p);
 int mmq_allreduce(mmq_handle* h, void* buf, size_t count, int is_double);
 int mmq_ensure_trace_groups(mmq_handle* h);
-int mmq_seg_plan(mmq_handle* h, const int64_t* row_ptr_host);
+int mmq_seg_scan(mmq_handle* h, const int64_t* row_ptr_host);
+int mmq_seg_plan(mmq_handle* h);
 int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep);
 int mmq_seg_add_base(mmq_handle* h, bool want_in_counts);
 

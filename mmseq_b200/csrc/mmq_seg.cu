@@ -116,9 +116,19 @@ __device__ __forceinline__ void seg_chunk_fixed(const int32_t* __restrict__ colp
     if (!va) { c[j] = sentinel; if (HAS_W) wv[j] = 0.f; }
     if (!vb) { c[D + j] = sentinel; if (HAS_W) wv[D + j] = 0.f; }
   }
+  /* rows are grouped by class: the lane's two classes usually have the same members, and then the
+   * second one reuses the first one's mu (weights stay per row) instead of gathering again */
+  bool same = true;
+#pragma unroll
+  for (int j = 0; j < D; ++j) same &= c[j] == c[D + j];
+  double g[2 * D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) g[j] = mu[c[j]];
+#pragma unroll
+  for (int j = 0; j < D; ++j) g[D + j] = same ? g[j] : mu[c[D + j]];
   double p[2 * D];
 #pragma unroll
-  for (int j = 0; j < 2 * D; ++j) p[j] = HAS_W ? mu[c[j]] * (double)wv[j] : mu[c[j]];
+  for (int j = 0; j < 2 * D; ++j) p[j] = HAS_W ? g[j] * (double)wv[j] : g[j];
   out_a = va ? seg_pick<D>(c, p, ua) : -1;
   out_b = vb ? seg_pick<D>(c + D, p + D, ub) : -1;
 }
@@ -159,7 +169,7 @@ template <bool HAS_W, int MAXD, int OCC>
 __global__ void __launch_bounds__(MMQ_SEG_WARPS * 32, OCC)
 k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, const int32_t* __restrict__ colp,
             const float* __restrict__ wp, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
-            uint32_t sweep, int32_t sentinel) {
+            uint32_t sweep, int32_t sentinel, int red_mode, int dbg_dmin, int dbg_dmax) {
   __shared__ mmq_seg s_seg[MMQ_SEG_MAX];
   for (int i = threadIdx.x; i < nsegs; i += blockDim.x) s_seg[i] = segs[i];
   __syncthreads();
@@ -171,6 +181,7 @@ k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, c
     while (si + 1 < nsegs && chunk >= s_seg[si + 1].chunk0) ++si; /* warp-uniform */
     const mmq_seg sg = s_seg[si];
     const int D = sg.d;
+    if (D < dbg_dmin || D > dbg_dmax) continue; /* timing experiments only (MMQ_DEBUG_DMIN / _DMAX) */
     const int rv = (int)(chunk - sg.chunk0) * MMQ_SEG_ROWS + 2 * lane; /* virtual row of class a */
     const bool va = rv >= sg.row_lo && rv < sg.rows;
     const bool vb = rv + 1 < sg.rows; /* rv + 1 >= 1 >= row_lo always */
@@ -373,22 +384,32 @@ int mmq_seg_add_base(mmq_handle* h, bool want_in_counts) {
   return MMQ_OK;
 }
 
-int mmq_seg_plan(mmq_handle* h, const int64_t* rp) {
-  h->seg_ready = false;
+/* Host-only part of the plan: runs of equal class size.  Called right after the H2D copies are
+ * queued, so the scan overlaps the DMA. */
+int mmq_seg_scan(mmq_handle* h, const int64_t* rp) {
+  h->seg_runs.clear();
+  h->seg_scan_ok = false;
   const int64_t m = h->m;
   if (m == 0 || h->has_k) return MMQ_OK;
-  /* runs of equal class size */
-  struct Run { int64_t r0, r1; int d; };
-  std::vector<Run> runs;
   for (int64_t i = 0; i < m;) {
     const int64_t d = rp[i + 1] - rp[i];
-    if (d > 0x7fffffff) return MMQ_OK;
+    if (d > 0x7fffffff || d <= 0) return MMQ_OK;
     int64_t j = i + 1;
     while (j < m && rp[j + 1] - rp[j] == d) ++j;
-    runs.push_back({i, j, (int)d});
-    if ((int)runs.size() > MMQ_SEG_MAX) return MMQ_OK; /* ragged shard: the row-pointer kernel handles it */
+    h->seg_runs.push_back({i, j, rp[i], (int)d});
+    if ((int)h->seg_runs.size() > MMQ_SEG_MAX) { h->seg_runs.clear(); return MMQ_OK; } /* ragged shard: the row-pointer kernel handles it */
     i = j;
   }
+  h->seg_scan_ok = true;
+  return MMQ_OK;
+}
+
+int mmq_seg_plan(mmq_handle* h) {
+  h->seg_ready = false;
+  if (!h->seg_scan_ok) return MMQ_OK;
+  struct Run { int64_t r0, r1, q0; int d; };
+  std::vector<Run> runs;
+  for (const auto& r : h->seg_runs) runs.push_back({r.r0, r.r1, r.q0, r.d});
   std::vector<mmq_seg> segs;
   int64_t packed = 0, chunks = 0, entries = 0, rows = 0, singles = 0;
   for (const Run& r : runs) {
@@ -426,15 +447,15 @@ int mmq_seg_plan(mmq_handle* h, const int64_t* rp) {
     const mmq_seg& sg = segs[si++];
     const int64_t dst = sg.e_virtual + (int64_t)sg.row_lo * r.d;
     const size_t cnt = (size_t)(r.r1 - r.r0) * (size_t)r.d;
-    MMQ_CUDA(h, cudaMemcpyAsync(h->seg_col + dst, h->col + rp[r.r0], sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, h->stream));
-    if (h->has_w) MMQ_CUDA(h, cudaMemcpyAsync(h->seg_w + dst, h->w + rp[r.r0], sizeof(float) * cnt, cudaMemcpyDeviceToDevice, h->stream));
+    MMQ_CUDA(h, cudaMemcpyAsync(h->seg_col + dst, h->col + r.q0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->has_w) MMQ_CUDA(h, cudaMemcpyAsync(h->seg_w + dst, h->w + r.q0, sizeof(float) * cnt, cudaMemcpyDeviceToDevice, h->stream));
   }
   if (singles > 0) {
     if ((rc = mmq_dev_alloc(h, (void**)&h->seg_base, sizeof(int32_t) * (size_t)h->n))) return rc;
     MMQ_CUDA(h, cudaMemsetAsync(h->seg_base, 0, sizeof(int32_t) * (size_t)h->n, h->stream));
     for (const Run& r : runs)
       if (r.d == 1) {
-        k_count_singletons<<<mmq_grid_for(r.r1 - r.r0, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->col, rp[r.r0], rp[r.r1], h->seg_base);
+        k_count_singletons<<<mmq_grid_for(r.r1 - r.r0, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->col, r.q0, r.q0 + (r.r1 - r.r0), h->seg_base);
         MMQ_LAUNCHED(h);
       }
     MMQ_CUDA(h, cudaMemcpyAsync(h->counts, h->seg_base, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
@@ -460,6 +481,7 @@ int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep) {
   if (h->seg_count == 0) return MMQ_OK; /* only singletons: nothing random to do */
   static const int variant = [] { const char* e = getenv("MMQ_SEG_KERNEL"); return e ? atoi(e) : 1; }(); /* 1 row-parallel, 2 entry-parallel */
 #define MMQ_SEG_ARGS (const mmq_seg*)h->seg_table, h->seg_count, h->seg_chunks, h->seg_col, h->seg_w, h->mu, h->counts, seed, sweep, (int32_t)h->n
+#define MMQ_SEG_ARGS1 MMQ_SEG_ARGS, red_mode, dbg_dmin, dbg_dmax
   if (variant == 2) {
     const int64_t want2 = (h->seg_chunks + MMQ_SEG2_WARPS - 1) / MMQ_SEG2_WARPS;
     const int grid2 = (int)std::min<int64_t>(want2, (int64_t)h->num_sms * 3);
@@ -476,22 +498,26 @@ int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep) {
     return MMQ_OK;
   }
   const int64_t want = (h->seg_chunks + MMQ_SEG_WARPS - 1) / MMQ_SEG_WARPS;
+  static const int red_mode = [] { const char* e = getenv("MMQ_DEBUG_RED"); return e ? atoi(e) : 2; }(); /* 2 = aggregated (product) */
+  static const int dbg_dmin = [] { const char* e = getenv("MMQ_DEBUG_DMIN"); return e ? atoi(e) : 0; }();
+  static const int dbg_dmax = [] { const char* e = getenv("MMQ_DEBUG_DMAX"); return e ? atoi(e) : 0x7fffffff; }();
   static const int maxd_env = [] { const char* e = getenv("MMQ_SEG_MAXD"); return e ? atoi(e) : 0; }(); /* tuning knob */
   const int maxd = maxd_env ? maxd_env : (h->has_w ? 4 : 6); /* largest class size with a register-resident specialisation */
   static const int occ_env = [] { const char* e = getenv("MMQ_SEG_OCC"); return e ? atoi(e) : 0; }();
   const int occ = maxd > 6 ? 2 : (occ_env == 4 && maxd <= 4 ? 4 : 3);
   const int grid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * occ);
   if (h->has_w) {
-    if (maxd > 6) k_alloc_seg<true, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else if (maxd > 4) k_alloc_seg<true, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else if (occ == 4) k_alloc_seg<true, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else k_alloc_seg<true, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    if (maxd > 6) k_alloc_seg<true, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    else if (maxd > 4) k_alloc_seg<true, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    else if (occ == 4) k_alloc_seg<true, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    else k_alloc_seg<true, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
   } else {
-    if (maxd > 6) k_alloc_seg<false, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else if (maxd > 4) k_alloc_seg<false, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else if (occ == 4) k_alloc_seg<false, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
-    else k_alloc_seg<false, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS);
+    if (maxd > 6) k_alloc_seg<false, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    else if (maxd > 4) k_alloc_seg<false, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    else if (occ == 4) k_alloc_seg<false, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    else k_alloc_seg<false, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
   }
 #undef MMQ_SEG_ARGS
+#undef MMQ_SEG_ARGS1
   return MMQ_OK;
 }

@@ -1,0 +1,23 @@
+#!/bin/bash
+# what the driver does at round end, plus the profiles we commit
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log; tail -3 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -1 gpurun_out/smoke.log
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks.csv &
+SMI=$!
+timeout 900 python bench.py --impl reference --steps 6 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+timeout 900 python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err
+kill $SMI
+timeout 600 python bench.py --weights --no-cpu-baseline > gpurun_out/bench_weighted.json 2>> gpurun_out/bench_ours.err
+timeout 600 python bench.py --layout collapsed --no-cpu-baseline > gpurun_out/bench_collapsed.json 2>> gpurun_out/bench_ours.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_alloc_seg -s 5 -c 1 -o gpurun_out/prof_r01_k_alloc_seg python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu.log 2>&1
+python - <<'PY'
+import json
+for f in ("reference","ours","weighted","collapsed"):
+    try:
+        d=json.loads(open(f"gpurun_out/bench_{f}.json").read().strip().split("\n")[-1])
+        r=d.get("roofline") or {}
+        print(f, "value %.4g"%d["value"], "sweeps/s", round(d["sweeps_per_s"],1), "alloc_ms", r.get("avg_launch_ms"), "frac", r.get("frac"), "e2e", d["e2e"] and round(d["e2e"].get("sweeps_per_s",0),1), "cpu", d.get("cpu_baseline",{}).get("sweeps_per_s"), "clocks", d.get("clocks"))
+    except Exception as e: print(f,"failed",e)
+PY
