@@ -272,7 +272,9 @@ __global__ void __launch_bounds__(MMQ_ALLOC_WARPS * 32, 3)
 k_alloc(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
         const int32_t* __restrict__ kk, const float* __restrict__ w, const double* __restrict__ mu,
         int32_t* __restrict__ counts, int32_t* __restrict__ xout, int64_t m, const int64_t* __restrict__ tile_start,
-        int64_t n_tiles, uint32_t seed, uint32_t sweep, int64_t class_id_base, const int64_t* __restrict__ class_id) {
+        int64_t n_tiles, uint32_t seed, uint32_t sweep, int64_t class_id_base, const int64_t* __restrict__ class_id,
+        const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base; /* CUDA-graph replays: the sweep counter lives on the device */
   /* every warp owns its tiles and its staging slab: no block-level barrier, the warps of an SM
    * overlap each other's load latency */
   __shared__ double s_p_all[MMQ_ALLOC_WARPS][MMQ_ALLOC_CAP];
@@ -422,7 +424,8 @@ template <bool HAS_W, int SLAB>
 __global__ void __launch_bounds__(MMQ_CAT_WARPS * 32, 3)
 k_alloc_cat(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const float* __restrict__ w,
             const double* __restrict__ mu, int32_t* __restrict__ counts, int64_t m, int64_t n_chunks,
-            uint32_t seed, uint32_t sweep, int64_t class_id_base, int32_t sentinel) {
+            uint32_t seed, uint32_t sweep, int64_t class_id_base, int32_t sentinel, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base;
   extern __shared__ __align__(16) unsigned char cat_smem[];
   constexpr int PER_WARP = 16 + 2 * SLAB * 4 * (HAS_W ? 2 : 1);
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -548,8 +551,13 @@ __global__ void k_count_reduce(const int64_t* __restrict__ tptr, const uint32_t*
  * are cleared for the next sweep; trace_col (= trace + slot, or null) receives
  * mu at stride trace_len.  src/mmseq.cpp:904-917. */
 __global__ void k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
-                        double* __restrict__ mu, double* __restrict__ trace_col, int trace_len, int64_t n,
-                        double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
+                        double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
+                        double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy,
+                        const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base;
+  /* sweep s with s % stride == 0 is recorded in slot s / stride (src/mmseq.cpp:911-917) */
+  double* trace_col = nullptr;
+  if (trace && stride > 0 && sweep % (uint32_t)stride == 0 && sweep / (uint32_t)stride < (uint32_t)trace_len) trace_col = trace + sweep / (uint32_t)stride;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     const int32_t c = counts[t];
     counts[t] = counts_base ? counts_base[t] : 0; /* classes skipped by the segmented kernel (singletons) */
@@ -561,6 +569,9 @@ __global__ void k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict_
     if (trace_col) trace_col[t * (int64_t)trace_len] = v;
   }
 }
+
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+__global__ void k_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 
 /* -------------------------------------------------------------- NCCL */
 
@@ -608,6 +619,8 @@ const char* mmq_version(void) { return "mmseq-b200 0.1 (hot path of eturro/mmseq
 int64_t mmq_launch_count(void) { return (int64_t)g_mmq_launches.load(); }
 
 const char* mmq_last_error(const mmq_handle* h) { return h ? h->err.c_str() : g_mmq_create_err.c_str(); }
+
+static void drop_graph(mmq_handle* h);
 
 static int upload(mmq_handle* h, void** dst, const void* src, size_t bytes, size_t pad = 0) {
   int rc = mmq_dev_alloc(h, dst, bytes + pad);
@@ -771,6 +784,7 @@ void mmq_destroy(mmq_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  drop_graph(h);
   for (cudaEvent_t e : h->ev_alloc) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_gamma) cudaEventDestroy(e);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
@@ -954,8 +968,8 @@ static int ensure_x(mmq_handle* h) {
 
 } /* extern "C" */
 template <bool MAT>
-static void launch_alloc_t(mmq_handle* h, int grid, uint32_t seed, uint32_t sweep) {
-#define MMQ_ALLOC_ARGS h->row_ptr, h->col, h->k, h->w, h->mu, h->counts, h->x, h->m, h->tile_start, h->n_tiles, seed, sweep, h->class_id_base, h->class_id
+static void launch_alloc_t(mmq_handle* h, int grid, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base) {
+#define MMQ_ALLOC_ARGS h->row_ptr, h->col, h->k, h->w, h->mu, h->counts, h->x, h->m, h->tile_start, h->n_tiles, seed, sweep, h->class_id_base, h->class_id, sweep_base
   if (h->has_k) {
     if (h->has_w) k_alloc<MAT, true, true><<<grid, MMQ_ALLOC_WARPS * 32, 0, h->stream>>>(MMQ_ALLOC_ARGS);
     else k_alloc<MAT, true, false><<<grid, MMQ_ALLOC_WARPS * 32, 0, h->stream>>>(MMQ_ALLOC_ARGS);
@@ -968,7 +982,7 @@ static void launch_alloc_t(mmq_handle* h, int grid, uint32_t seed, uint32_t swee
 extern "C" {
 
 /* One sweep on the stream.  trace_col = device address of trace[0*L + slot] or null. */
-static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags, double* trace_col, int32_t* counts_copy) {
+static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags, int stride, int32_t* counts_copy, const uint32_t* sweep_base) {
   const bool transposed = (flags & MMQ_GIBBS_TRANSPOSED) != 0;
   const bool timed = (flags & MMQ_GIBBS_TIME_KERNELS) != 0;
   int rc;
@@ -987,7 +1001,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       if ((rc = ensure_x(h))) return rc;
       if ((rc = build_transpose(h))) return rc;
       mark(h->ev_alloc);
-      launch_alloc_t<true>(h, grid, seed, sweep);
+      launch_alloc_t<true>(h, grid, seed, sweep, sweep_base);
       MMQ_LAUNCHED(h);
       mark(h->ev_alloc);
       k_count_reduce<<<mmq_grid_for(h->n * 32, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->tptr, h->perm, h->x, h->counts, h->n);
@@ -995,7 +1009,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
     } else {
       mark(h->ev_alloc);
       if (h->seg_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
-        if ((rc = mmq_seg_launch(h, seed, sweep))) return rc;
+        if ((rc = mmq_seg_launch(h, seed, sweep, sweep_base))) return rc;
       } else if (!h->has_k && !(flags & MMQ_GIBBS_GENERIC_KERNEL)) {
         if (h->seg_ready && (rc = mmq_seg_add_base(h, false))) return rc; /* this kernel visits the singletons itself */
         const int64_t n_chunks = (h->m + MMQ_CAT_ROWS - 1) / MMQ_CAT_ROWS;
@@ -1004,16 +1018,16 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
           constexpr int SM = MMQ_CAT_WARPS * (16 + 2 * MMQ_CAT_SLAB_W * 4 * 2);
           MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_cat<true, MMQ_CAT_SLAB_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
           const int cgrid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * 3);
-          k_alloc_cat<true, MMQ_CAT_SLAB_W><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n);
+          k_alloc_cat<true, MMQ_CAT_SLAB_W><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n, sweep_base);
         } else {
           constexpr int SM = MMQ_CAT_WARPS * (16 + 2 * MMQ_CAT_SLAB * 4);
           MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_cat<false, MMQ_CAT_SLAB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
           const int cgrid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * 3);
-          k_alloc_cat<false, MMQ_CAT_SLAB><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n);
+          k_alloc_cat<false, MMQ_CAT_SLAB><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n, sweep_base);
         }
       } else {
         if (h->seg_ready && (rc = mmq_seg_add_base(h, false))) return rc;
-        launch_alloc_t<false>(h, grid, seed, sweep);
+        launch_alloc_t<false>(h, grid, seed, sweep, sweep_base);
       }
       MMQ_LAUNCHED(h);
       mark(h->ev_alloc);
@@ -1021,8 +1035,8 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
   }
   if ((rc = mmq_allreduce(h, h->counts, (size_t)h->n, 0))) return rc;
   mark(h->ev_gamma);
-  k_gamma<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, trace_col, h->trace_len, h->n,
-                                                                          h->alpha, h->beta, seed, sweep, counts_copy);
+  k_gamma<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride, h->trace_len, h->n,
+                                                                          h->alpha, h->beta, seed, sweep, counts_copy, sweep_base);
   MMQ_LAUNCHED(h);
   mark(h->ev_gamma);
   if (h->seg_base) h->seg_base_in_counts = true; /* k_gamma restarted counts[] from seg_base */
@@ -1041,6 +1055,38 @@ static int ensure_trace(mmq_handle* h, int trace_len) {
   return MMQ_OK;
 }
 
+static void drop_graph(mmq_handle* h) {
+  if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+  if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+  h->graph_flags = -1;
+}
+
+/* Capture MMQ_GRAPH_SWEEPS sweeps (sweep = *graph_base + j) followed by graph_base += MMQ_GRAPH_SWEEPS. */
+static int capture_graph(mmq_handle* h, uint32_t seed, int flags, int stride) {
+  drop_graph(h);
+  if (!h->graph_base) {
+    int rc = mmq_dev_alloc(h, (void**)&h->graph_base, sizeof(uint32_t));
+    if (rc) return rc;
+  }
+  MMQ_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = MMQ_OK;
+  for (int j = 0; j < MMQ_GRAPH_SWEEPS && rc == MMQ_OK; ++j) rc = enqueue_sweep(h, seed, (uint32_t)j, flags, stride, nullptr, h->graph_base);
+  if (rc == MMQ_OK) {
+    k_add_u32<<<1, 1, 0, h->stream>>>(h->graph_base, MMQ_GRAPH_SWEEPS);
+    g_mmq_launches.fetch_add(1);
+  }
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  if (rc != MMQ_OK) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaStreamEndCapture", __FILE__, __LINE__);
+  h->graph = g;
+  e = cudaGraphInstantiate(&h->graph_exec, g, 0);
+  if (e != cudaSuccess) { drop_graph(h); return mmq_cuda_fail(h, e, "cudaGraphInstantiate", __FILE__, __LINE__); }
+  h->graph_seed = seed; h->graph_flags = flags; h->graph_stride = stride; h->graph_trace_len = h->trace_len;
+  h->graph_trace = h->trace; h->graph_stream = h->stream;
+  return MMQ_OK;
+}
+
 int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweeps, int stride, int trace_len, int flags) {
   if (!h) return MMQ_ERR_ARG;
   if (first_sweep < 0 || n_sweeps < 0 || first_sweep + n_sweeps > (int64_t)0xffffffffll) return mmq_fail(h, MMQ_ERR_ARG, "mmq_gibbs: sweep range out of bounds");
@@ -1049,11 +1095,29 @@ int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweep
   int rc = ensure_trace(h, trace_len);
   if (rc) return rc;
   for (auto& g : h->groups) g.trace_valid = false;
-  for (int64_t s = first_sweep; s < first_sweep + n_sweeps; ++s) {
-    double* tc = nullptr;
-    if (trace_len > 0 && s % stride == 0 && s / stride < trace_len) tc = h->trace + s / stride;
-    if ((rc = enqueue_sweep(h, seed, (uint32_t)s, flags, tc, nullptr))) return rc;
+  const int st = trace_len > 0 ? stride : 0;
+  int64_t s = first_sweep;
+  const int64_t end = first_sweep + n_sweeps;
+  /* CUDA graph for the bulk of a long run (single GPU; the timed mode needs per-launch events):
+   * the first sweep goes out as plain launches (it builds lazily allocated state), then whole
+   * graphs of MMQ_GRAPH_SWEEPS sweeps, then the remainder as plain launches */
+  const bool use_graph = !(flags & (MMQ_GIBBS_NO_GRAPH | MMQ_GIBBS_TIME_KERNELS)) && h->nranks == 1 && n_sweeps >= 1 + 2 * MMQ_GRAPH_SWEEPS;
+  if (use_graph) {
+    if ((rc = enqueue_sweep(h, seed, (uint32_t)s, flags, st, nullptr, nullptr))) return rc;
+    ++s;
+    const bool reuse = h->graph_exec && h->graph_seed == seed && h->graph_flags == flags && h->graph_stride == st &&
+                       h->graph_trace_len == h->trace_len && h->graph_trace == h->trace && h->graph_stream == h->stream;
+    if (!reuse && (rc = capture_graph(h, seed, flags, st))) return rc;
+    k_set_u32<<<1, 1, 0, h->stream>>>(h->graph_base, (uint32_t)s);
+    MMQ_LAUNCHED(h);
+    while (end - s >= MMQ_GRAPH_SWEEPS) {
+      MMQ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
+      g_mmq_launches.fetch_add(2 * MMQ_GRAPH_SWEEPS + 1, std::memory_order_relaxed);
+      s += MMQ_GRAPH_SWEEPS;
+    }
   }
+  for (; s < end; ++s)
+    if ((rc = enqueue_sweep(h, seed, (uint32_t)s, flags, st, nullptr, nullptr))) return rc;
   return MMQ_OK;
 }
 
@@ -1063,7 +1127,7 @@ int mmq_sweep_debug(mmq_handle* h, uint32_t seed, int64_t sweep, int flags, int3
   if (x_out && !(flags & MMQ_GIBBS_TRANSPOSED)) return mmq_fail(h, MMQ_ERR_ARG, "mmq_sweep_debug: x_out needs MMQ_GIBBS_TRANSPOSED (the fused path keeps no X)");
   int32_t* counts_copy = nullptr;
   MMQ_CUDA(h, cudaMalloc(&counts_copy, sizeof(int32_t) * (size_t)h->n));
-  int rc = enqueue_sweep(h, seed, (uint32_t)sweep, flags, nullptr, counts_copy);
+  int rc = enqueue_sweep(h, seed, (uint32_t)sweep, flags, 0, counts_copy, nullptr);
   if (rc) { cudaFree(counts_copy); return rc; }
   cudaError_t e = cudaSuccess;
   if (x_out) e = cudaMemcpyAsync(x_out, h->x, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream);

@@ -17,6 +17,7 @@
 #define MMQ_ALLOC_THREADS 256
 #define MMQ_ALLOC_WARPS 8
 #define MMQ_ALLOC_CAP 320 /* staged CSR entries per warp tile */
+#define MMQ_GRAPH_SWEEPS 16 /* sweeps per captured CUDA graph */
 
 struct mmq_group_set {
   int64_t ngroups = 0;
@@ -88,6 +89,16 @@ struct mmq_handle {
   bool seg_base_in_counts = true; /* counts[] currently starts from seg_base */
   int64_t seg_entries = 0, seg_rows = 0, seg_singletons = 0;
 
+  /* CUDA graph of MMQ_GRAPH_SWEEPS consecutive sweeps; the sweep counter is read from
+   * graph_base on the device, so one instantiated graph serves the whole chain */
+  uint32_t* graph_base = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  uint32_t graph_seed = 0;
+  int graph_flags = -1, graph_stride = 0, graph_trace_len = 0;
+  const double* graph_trace = nullptr;
+  cudaStream_t graph_stream = nullptr;
+
   /* MMQ_GIBBS_TIME_KERNELS: (start, stop) event pairs around each launch */
   std::vector<cudaEvent_t> ev_alloc, ev_gamma;
 
@@ -107,7 +118,7 @@ int mmq_allreduce(mmq_handle* h, void* buf, size_t count, int is_double);
 int mmq_ensure_trace_groups(mmq_handle* h);
 int mmq_seg_scan(mmq_handle* h, const int64_t* row_ptr_host);
 int mmq_seg_plan(mmq_handle* h);
-int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep);
+int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base);
 int mmq_seg_add_base(mmq_handle* h, bool want_in_counts);
 
 #define MMQ_CUDA(h, call)                                                              \

@@ -169,7 +169,8 @@ template <bool HAS_W, int MAXD, int OCC>
 __global__ void __launch_bounds__(MMQ_SEG_WARPS * 32, OCC)
 k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, const int32_t* __restrict__ colp,
             const float* __restrict__ wp, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
-            uint32_t sweep, int32_t sentinel, int red_mode, int dbg_dmin, int dbg_dmax) {
+            uint32_t sweep, int32_t sentinel, int red_mode, int dbg_dmin, int dbg_dmax, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base; /* CUDA-graph replays: the sweep counter lives on the device */
   __shared__ mmq_seg s_seg[MMQ_SEG_MAX];
   for (int i = threadIdx.x; i < nsegs; i += blockDim.x) s_seg[i] = segs[i];
   __syncthreads();
@@ -294,7 +295,8 @@ template <bool HAS_W>
 __global__ void __launch_bounds__(MMQ_SEG2_WARPS * 32, 3)
 k_alloc_seg2(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, const int32_t* __restrict__ colp,
              const float* __restrict__ wp, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
-             uint32_t sweep, int32_t sentinel) {
+             uint32_t sweep, int32_t sentinel, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base;
   constexpr int CAP = MMQ_SEG_ROWS * MMQ_SEG2_DMAX;                  /* staged entries per buffer */
   constexpr int PCAP = MMQ_SEG_ROWS * (MMQ_SEG2_DMAX | 1);           /* p buffer, doubles */
   constexpr int PER_WARP = 16 + PCAP * 8 + 2 * CAP * 4 * (HAS_W ? 2 : 1);
@@ -475,13 +477,13 @@ int mmq_seg_plan(mmq_handle* h) {
   return MMQ_OK;
 }
 
-int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep) {
+int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base) {
   int rc = mmq_seg_add_base(h, true);
   if (rc) return rc;
   if (h->seg_count == 0) return MMQ_OK; /* only singletons: nothing random to do */
   static const int variant = [] { const char* e = getenv("MMQ_SEG_KERNEL"); return e ? atoi(e) : 1; }(); /* 1 row-parallel, 2 entry-parallel */
 #define MMQ_SEG_ARGS (const mmq_seg*)h->seg_table, h->seg_count, h->seg_chunks, h->seg_col, h->seg_w, h->mu, h->counts, seed, sweep, (int32_t)h->n
-#define MMQ_SEG_ARGS1 MMQ_SEG_ARGS, red_mode, dbg_dmin, dbg_dmax
+#define MMQ_SEG_ARGS1 MMQ_SEG_ARGS, red_mode, dbg_dmin, dbg_dmax, sweep_base
   if (variant == 2) {
     const int64_t want2 = (h->seg_chunks + MMQ_SEG2_WARPS - 1) / MMQ_SEG2_WARPS;
     const int grid2 = (int)std::min<int64_t>(want2, (int64_t)h->num_sms * 3);
@@ -489,11 +491,11 @@ int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep) {
     if (h->has_w) {
       constexpr int SM = MMQ_SEG2_WARPS * (16 + PCAP * 8 + 2 * CAP * 4 * 2);
       MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_seg2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
-      k_alloc_seg2<true><<<grid2, MMQ_SEG2_WARPS * 32, SM, h->stream>>>(MMQ_SEG_ARGS);
+      k_alloc_seg2<true><<<grid2, MMQ_SEG2_WARPS * 32, SM, h->stream>>>(MMQ_SEG_ARGS, sweep_base);
     } else {
       constexpr int SM = MMQ_SEG2_WARPS * (16 + PCAP * 8 + 2 * CAP * 4);
       MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_seg2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));
-      k_alloc_seg2<false><<<grid2, MMQ_SEG2_WARPS * 32, SM, h->stream>>>(MMQ_SEG_ARGS);
+      k_alloc_seg2<false><<<grid2, MMQ_SEG2_WARPS * 32, SM, h->stream>>>(MMQ_SEG_ARGS, sweep_base);
     }
     return MMQ_OK;
   }

@@ -170,6 +170,32 @@ def test_trace_bit_exact_over_many_sweeps(small_problem):
             assert np.array_equal(H.get_mu(), mu_o)
 
 
+@pytest.mark.parametrize("layout", ["collapsed", "by_length"])
+def test_cuda_graph_replay_equals_plain_launches(small_synth, layout):
+    """Long runs are replayed from one CUDA graph of 16 sweeps whose sweep counter lives on the
+    device; the chain must equal the plain-launch chain and the CPU replay, also when the run is
+    split into unaligned pieces and when the stride does not divide the graph length."""
+    s = small_synth
+    lay = hostlib.LAYOUT_COLLAPSED if layout == "collapsed" else hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH
+    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=lay)
+    P = _oracle(h)
+    mu0, _, _ = P.init_mu()
+    n_sw, stride, L = 150, 6, 32
+    mu_o, tr_o = P.gibbs_replay(mu0, SEED, 0, n_sw, stride, L)
+    with _handle(h) as H:
+        H.set_mu(mu0)
+        H.gibbs(SEED, 0, n_sw, stride=stride, trace_len=L, flags=capi.MMQ_GIBBS_NO_GRAPH)
+        tr_plain, mu_plain = H.get_trace(), H.get_mu()
+        H.set_mu(mu0)
+        l0 = capi.launch_count()
+        H.gibbs(SEED, 0, 100, stride=stride, trace_len=L)            # graph: 1 + 6*16 + 3
+        H.gibbs(SEED, 100, 50, stride=stride, trace_len=L)           # graph reused: 1 + 3*16 + 1
+        tr_g, mu_g = H.get_trace(), H.get_mu()
+        assert capi.launch_count() - l0 >= 2 * n_sw
+    assert np.array_equal(tr_plain, tr_o) and np.array_equal(mu_plain, mu_o)
+    assert np.array_equal(tr_g, tr_o) and np.array_equal(mu_g, mu_o)
+
+
 def test_ragged_and_extreme_rows():
     """Singletons, a row longer than the staging tile, huge k, tiny mu."""
     rng = np.random.default_rng(11)
