@@ -27,7 +27,7 @@ $(LIB): build/mmq_core.o build/mmq_post.o build/mmq_seg.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -ldl
 
 $(SYNTH): $(CSRC)/mmq_synth.cpp
-	$(HOST_CXX) -O3 -std=c++17 -fPIC -fopenmp -shared -o $@ $<
+	$(HOST_CXX) -O3 -std=c++17 -fPIC -fopenmp -shared -o $@ $< -lz
 
 $(HOSTLIB): $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h include/mmq_sampler.h
 	$(HOST_CXX) -O3 -std=c++17 -fPIC -ffp-contract=off -shared -o $@ $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp -lz

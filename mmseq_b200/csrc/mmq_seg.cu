@@ -116,26 +116,88 @@ __device__ __forceinline__ void seg_chunk_fixed(const int32_t* __restrict__ colp
     if (!va) { c[j] = sentinel; if (HAS_W) wv[j] = 0.f; }
     if (!vb) { c[D + j] = sentinel; if (HAS_W) wv[D + j] = 0.f; }
   }
-  /* rows are grouped by class: the lane's two classes usually have the same members, and then the
-   * second one reuses the first one's mu (weights stay per row) instead of gathering again */
+  /* Class a first, then class b in the same registers.  Rows are grouped by class, so the lane's two
+   * classes usually have the same members: b then reuses a's mu (weights stay per row) instead of
+   * gathering again.  Running sums are recomputed in the scan instead of being kept: D doubles of mu
+   * are all the state a class needs, which lets sizes up to 12 stay in registers. */
   bool same = true;
 #pragma unroll
   for (int j = 0; j < D; ++j) same &= c[j] == c[D + j];
-  double g[2 * D];
+  double g[D];
 #pragma unroll
   for (int j = 0; j < D; ++j) g[j] = mu[c[j]];
+  auto pick = [&](const int32_t* cc, const float* ww, double u) -> int32_t {
+    double norm = 0.0;
 #pragma unroll
-  for (int j = 0; j < D; ++j) g[D + j] = same ? g[j] : mu[c[D + j]];
-  double p[2 * D];
+    for (int j = 0; j < D; ++j) norm += HAS_W ? g[j] * (double)ww[j] : g[j];
+    const double target = u * norm;
+    double acc = 0.0;
+    int chosen = -1, lastpos = -1;
 #pragma unroll
-  for (int j = 0; j < 2 * D; ++j) p[j] = HAS_W ? g[j] * (double)wv[j] : g[j];
-  out_a = va ? seg_pick<D>(c, p, ua) : -1;
-  out_b = vb ? seg_pick<D>(c + D, p + D, ub) : -1;
+    for (int j = 0; j < D; ++j) {
+      const double pj = HAS_W ? g[j] * (double)ww[j] : g[j];
+      acc += pj;
+      if (chosen < 0 && target < acc) chosen = j;
+      if (pj > 0.0) lastpos = j;
+    }
+    if (chosen < 0) chosen = lastpos >= 0 ? lastpos : D - 1; /* rounding at the top end / all-zero row */
+    int32_t out = cc[0];
+#pragma unroll
+    for (int j = 1; j < D; ++j)
+      if (chosen == j) out = cc[j];
+    return out;
+  };
+  out_a = va ? pick(c, wv, ua) : -1;
+#pragma unroll
+  for (int j = 0; j < D; ++j)
+    if (!same) g[j] = mu[c[D + j]];
+  out_b = vb ? pick(c + D, wv + D, ub) : -1;
+}
+
+/* One class of compile-time size D (7..12), everything in registers: D columns by vector loads,
+ * D independent mu gathers, sum, scan.  The chosen column is re-read (an L1 hit) instead of being
+ * selected from registers. */
+template <int D, bool HAS_W>
+__device__ __noinline__ int32_t seg_row_fixed(const int32_t* __restrict__ cp, const float* __restrict__ wq,
+                                                 const double* __restrict__ mu, double u) {
+  int32_t c[D];
+  float wv[HAS_W ? D : 1];
+  if (D % 2 == 0) { /* the row start is 8-byte aligned for even D (two rows of a lane start 16-byte aligned) */
+#pragma unroll
+    for (int j = 0; j < D; j += 2) {
+      const int2 v = *reinterpret_cast<const int2*>(cp + j);
+      c[j] = v.x; c[j + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < D; ++j) c[j] = cp[j];
+  }
+  if (HAS_W) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) wv[j] = wq[j];
+  }
+  double g[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) g[j] = HAS_W ? mu[c[j]] * (double)wv[j] : mu[c[j]];
+  double norm = 0.0;
+#pragma unroll
+  for (int j = 0; j < D; ++j) norm += g[j];
+  const double target = u * norm;
+  double acc = 0.0;
+  int chosen = -1, lastpos = -1;
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    acc += g[j];
+    if (chosen < 0 && target < acc) chosen = j;
+    if (g[j] > 0.0) lastpos = j;
+  }
+  if (chosen < 0) chosen = lastpos >= 0 ? lastpos : D - 1;
+  return cp[chosen];
 }
 
 /* Any class size: two passes with batched gathers straight from global memory. */
 template <bool HAS_W>
-__device__ __forceinline__ int32_t seg_row_generic(const int32_t* __restrict__ c, const float* __restrict__ wv, int d,
+__device__ __noinline__ int32_t seg_row_generic(const int32_t* __restrict__ c, const float* __restrict__ wv, int d,
                                                    const double* __restrict__ mu, double u) {
 #define MMQ_PG(j) (HAS_W ? mu[c[j]] * (double)wv[j] : mu[c[j]])
   double norm = 0.0;
@@ -187,21 +249,6 @@ k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, c
     const bool va = rv >= sg.row_lo && rv < sg.rows;
     const bool vb = rv + 1 < sg.rows; /* rv + 1 >= 1 >= row_lo always */
     const int64_t e = sg.e_virtual + (int64_t)rv * D;
-    { /* pull this warp's NEXT chunk of columns (and weights) towards L2 while this one is processed */
-      const int64_t nchunk = chunk + nwarps;
-      if (nchunk < total_chunks) {
-        int sj = si;
-        while (sj + 1 < nsegs && nchunk >= s_seg[sj + 1].chunk0) ++sj;
-        const int64_t e2 = s_seg[sj].e_virtual + ((nchunk - s_seg[sj].chunk0) * MMQ_SEG_ROWS + 2 * lane) * (int64_t)s_seg[sj].d;
-        const int bytes = 8 * s_seg[sj].d;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(colp + e2));
-        if (bytes > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(colp + e2) + bytes - 4));
-        if (HAS_W) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(wp + e2));
-          if (bytes > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(wp + e2) + bytes - 4));
-        }
-      }
-    }
     /* one Philox block per lane: classes cid (even) and cid + 1 */
     const uint64_t cid = (uint64_t)(sg.cid_virtual + rv);
     uint32_t wd[4] = {(uint32_t)(cid >> 1), (uint32_t)(cid >> 33), sweep, 0u};
@@ -209,13 +256,17 @@ k_alloc_seg(const mmq_seg* __restrict__ segs, int nsegs, int64_t total_chunks, c
     const double ua = cat_u52(wd[0], wd[1]), ub = cat_u52(wd[2], wd[3]);
     int32_t ca = -1, cb = -1;
     /* warp-uniform dispatch on the class size */
+#define MMQ_SEG_CASE(DD) else if (MAXD >= DD && D == DD) seg_chunk_fixed<(MAXD >= DD ? DD : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+#define MMQ_SEG_ROWCASE(DD)                                                                            \
+  else if (MAXD >= DD && D == DD) {                                                                    \
+    if (va) ca = seg_row_fixed<(MAXD >= DD ? DD : 7), HAS_W>(colp + e, wp + e, mu, ua);               \
+    if (vb) cb = seg_row_fixed<(MAXD >= DD ? DD : 7), HAS_W>(colp + e + DD, wp + e + DD, mu, ub);     \
+  }
     if (D == 2) seg_chunk_fixed<2, HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
-    else if (D == 3) seg_chunk_fixed<3, HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
-    else if (D == 4) seg_chunk_fixed<4, HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
-    else if (MAXD >= 6 && D == 5) seg_chunk_fixed<(MAXD >= 6 ? 5 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
-    else if (MAXD >= 6 && D == 6) seg_chunk_fixed<(MAXD >= 6 ? 6 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
-    else if (MAXD >= 8 && D == 7) seg_chunk_fixed<(MAXD >= 8 ? 7 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
-    else if (MAXD >= 8 && D == 8) seg_chunk_fixed<(MAXD >= 8 ? 8 : 2), HAS_W>(colp, wp, e, va, vb, ua, ub, mu, sentinel, ca, cb);
+    MMQ_SEG_CASE(3) MMQ_SEG_CASE(4) MMQ_SEG_CASE(5) MMQ_SEG_CASE(6)
+    MMQ_SEG_ROWCASE(7) MMQ_SEG_ROWCASE(8) MMQ_SEG_ROWCASE(9) MMQ_SEG_ROWCASE(10) MMQ_SEG_ROWCASE(11) MMQ_SEG_ROWCASE(12)
+#undef MMQ_SEG_CASE
+#undef MMQ_SEG_ROWCASE
     else {
       if (va) ca = seg_row_generic<HAS_W>(colp + e, wp + e, D, mu, ua);
       if (vb) cb = seg_row_generic<HAS_W>(colp + e + D, wp + e + D, D, mu, ub);
@@ -504,21 +555,25 @@ int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
   static const int dbg_dmin = [] { const char* e = getenv("MMQ_DEBUG_DMIN"); return e ? atoi(e) : 0; }();
   static const int dbg_dmax = [] { const char* e = getenv("MMQ_DEBUG_DMAX"); return e ? atoi(e) : 0x7fffffff; }();
   static const int maxd_env = [] { const char* e = getenv("MMQ_SEG_MAXD"); return e ? atoi(e) : 0; }(); /* tuning knob */
-  const int maxd = maxd_env ? maxd_env : (h->has_w ? 4 : 6); /* largest class size with a register-resident specialisation */
+  const int maxd = maxd_env ? maxd_env : (h->has_w ? 8 : 12); /* largest class size with a register-resident specialisation */
   static const int occ_env = [] { const char* e = getenv("MMQ_SEG_OCC"); return e ? atoi(e) : 0; }();
-  const int occ = maxd > 6 ? 2 : (occ_env == 4 && maxd <= 4 ? 4 : 3);
+  const int occ = occ_env ? occ_env : (h->has_w ? 3 : 4);
   const int grid = (int)std::min<int64_t>(want, (int64_t)h->num_sms * occ);
+#define MMQ_SEG_GO(W, MD, OC) k_alloc_seg<W, MD, OC><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1)
   if (h->has_w) {
-    if (maxd > 6) k_alloc_seg<true, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
-    else if (maxd > 4) k_alloc_seg<true, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
-    else if (occ == 4) k_alloc_seg<true, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
-    else k_alloc_seg<true, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    if (maxd > 8) MMQ_SEG_GO(true, 12, 2);
+    else if (maxd > 6) MMQ_SEG_GO(true, 8, 3);
+    else if (maxd > 4) MMQ_SEG_GO(true, 6, 3);
+    else if (occ == 4) MMQ_SEG_GO(true, 4, 4);
+    else MMQ_SEG_GO(true, 4, 3);
   } else {
-    if (maxd > 6) k_alloc_seg<false, 8, 2><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
-    else if (maxd > 4) k_alloc_seg<false, 6, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
-    else if (occ == 4) k_alloc_seg<false, 4, 4><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
-    else k_alloc_seg<false, 4, 3><<<grid, MMQ_SEG_WARPS * 32, 0, h->stream>>>(MMQ_SEG_ARGS1);
+    if (maxd > 8) { if (occ == 2) MMQ_SEG_GO(false, 12, 2); else if (occ == 4) MMQ_SEG_GO(false, 12, 4); else if (occ == 5) MMQ_SEG_GO(false, 12, 5); else MMQ_SEG_GO(false, 12, 3); }
+    else if (maxd > 6) MMQ_SEG_GO(false, 8, 3);
+    else if (maxd > 4) MMQ_SEG_GO(false, 6, 3);
+    else if (occ == 4) MMQ_SEG_GO(false, 4, 4);
+    else MMQ_SEG_GO(false, 4, 3);
   }
+#undef MMQ_SEG_GO
 #undef MMQ_SEG_ARGS
 #undef MMQ_SEG_ARGS1
   return MMQ_OK;

@@ -13,8 +13,12 @@
  * haplo = 1: every transcript exists as copies _A and _B (T = 2 x base); a
  * fragment's hit on a transcript also hits the other copy w.p. 0.9.
  */
+#include <zlib.h>
+
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <string>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -185,6 +189,77 @@ void* mmq_synth_create(uint64_t seed, uint64_t frag_seed, int64_t T_base, int64_
     }
   }
   return S;
+}
+
+/* Fast writers for large hits files (the Python writers in synth.py are for small cases).
+ * schema 0 = text (src/hitsio.cpp:162-187), schema 1 = zlib-binary (:189-240), names as synth.py. */
+static void tname(char* buf, int64_t t, int haplo) {
+  if (haplo) snprintf(buf, 40, "T%07lld_%c", (long long)(t / 2), "AB"[t % 2]);
+  else snprintf(buf, 40, "T%07lld", (long long)t);
+}
+int mmq_synth_write_hits(void* p, const char* path, int schema, int haplo) {
+  Synth* S = (Synth*)p;
+  std::string out;
+  out.reserve((size_t)64 << 20);
+  char nm[48], tmp[128];
+  z_stream zs;
+  FILE* f = fopen(path, "wb");
+  if (!f) return 1;
+  std::vector<unsigned char> zbuf((size_t)8 << 20);
+  if (schema == 1) { memset(&zs, 0, sizeof zs); if (deflateInit(&zs, 1) != Z_OK) { fclose(f); return 2; } }
+  auto flush = [&](bool finish) {
+    if (schema == 0) { fwrite(out.data(), 1, out.size(), f); out.clear(); return; }
+    zs.next_in = (Bytef*)out.data(); zs.avail_in = (uInt)out.size();
+    do {
+      zs.next_out = zbuf.data(); zs.avail_out = (uInt)zbuf.size();
+      deflate(&zs, finish ? Z_FINISH : Z_NO_FLUSH);
+      fwrite(zbuf.data(), 1, zbuf.size() - zs.avail_out, f);
+    } while (zs.avail_out == 0);
+    out.clear();
+  };
+  auto u32 = [&](uint32_t v) { out.append((const char*)&v, 4); };
+  if (schema == 0) {
+    for (int64_t t = 0; t < S->T; ++t) { tname(nm, t, haplo); snprintf(tmp, sizeof tmp, "@TranscriptMetaData\t%s\t%g\t%d\n", nm, S->efflen[(size_t)t], S->truelen[(size_t)t]); out += tmp; }
+    for (int64_t g = 0; g < S->G; ++g) {
+      snprintf(tmp, sizeof tmp, "@GeneIsoforms\tG%07lld", (long long)g); out += tmp;
+      for (int64_t t = S->gene_ptr[(size_t)g]; t < S->gene_ptr[(size_t)g + 1]; ++t) { tname(nm, t, haplo); out += "\t"; out += nm; }
+      out += "\n";
+    }
+    for (int64_t r = 0; r < S->N; ++r) {
+      snprintf(tmp, sizeof tmp, ">r%lld\n", (long long)r); out += tmp;
+      for (int64_t q = S->frag_ptr[(size_t)r]; q < S->frag_ptr[(size_t)r + 1]; ++q) { tname(nm, S->frag_tid[(size_t)q], haplo); out += nm; out += "\n"; }
+      if (out.size() > ((size_t)48 << 20)) flush(false);
+    }
+  } else {
+    out += "MMSEQ_HITSFILE\n"; u32(1); u32((uint32_t)S->T);
+    for (int64_t t = 0; t < S->T; ++t) { tname(nm, t, haplo); out += nm; out += "\n"; snprintf(tmp, sizeof tmp, "%g\n", S->efflen[(size_t)t]); out += tmp; u32((uint32_t)S->truelen[(size_t)t]); }
+    u32((uint32_t)S->G);
+    for (int64_t g = 0; g < S->G; ++g) {
+      snprintf(tmp, sizeof tmp, "G%07lld\n", (long long)g); out += tmp;
+      u32((uint32_t)(S->gene_ptr[(size_t)g + 1] - S->gene_ptr[(size_t)g]));
+      for (int64_t t = S->gene_ptr[(size_t)g]; t < S->gene_ptr[(size_t)g + 1]; ++t) { tname(nm, t, haplo); out += nm; out += "\n"; }
+    }
+    u32(0); /* no identical sets */
+    std::string prev, name;
+    for (int64_t r = 0; r < S->N; ++r) {
+      snprintf(tmp, sizeof tmp, "r%lld", (long long)r); name = tmp;
+      size_t nb = 0, ne = 0, mn = std::min(prev.size(), name.size());
+      while (nb < mn && prev[nb] == name[nb]) ++nb;
+      while (nb + ne < mn && prev[prev.size() - 1 - ne] == name[name.size() - 1 - ne]) ++ne;
+      auto small = [&](size_t v) { if (v < 255) out.push_back((char)v); else { out.push_back((char)255); u32((uint32_t)v); } };
+      if (nb == 0 && ne == 0) { out += name; out += "\n"; }
+      else { out += "\n"; small(nb); out.append(name, nb, name.size() - nb - ne); out += "\n"; small(ne); }
+      prev = name;
+      const int64_t b = S->frag_ptr[(size_t)r], e = S->frag_ptr[(size_t)r + 1];
+      u32((uint32_t)(e - b));
+      for (int64_t q = b; q < e; ++q) u32((uint32_t)S->frag_tid[(size_t)q]);
+      if (out.size() > ((size_t)48 << 20)) flush(false);
+    }
+  }
+  flush(true);
+  if (schema == 1) deflateEnd(&zs);
+  fclose(f);
+  return 0;
 }
 
 void mmq_synth_destroy(void* p) { delete (Synth*)p; }

@@ -23,6 +23,8 @@ def lib():
         L.mmq_synth_create.restype = C.c_void_p
         L.mmq_synth_create.argtypes = [C.c_uint64, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_int]
         L.mmq_synth_destroy.argtypes = [C.c_void_p]
+        L.mmq_synth_write_hits.restype = C.c_int
+        L.mmq_synth_write_hits.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
         for nm in ["T", "G", "N", "nhits"]:
             f = getattr(L, "mmq_synth_" + nm)
             f.restype = C.c_int64
@@ -57,8 +59,19 @@ class Synth:
         self.frag_ptr = _arr(L.mmq_synth_frag_ptr(h), self.N + 1, C.c_int64, np.int64)
         self.frag_tid = _arr(L.mmq_synth_frag_tid(h), nh, C.c_int32, np.int32)
         self.frag_w = _arr(L.mmq_synth_frag_w(h), nh, C.c_float, np.float32)
+        self._keep = None
         L.mmq_synth_destroy(h)
         self.haplo = haplo
+        self._args = (seed, frag_seed, T // (2 if haplo else 1), N, int(haplo), int(weights), threads)
+
+    def write_hits_fast(self, path, binary=True):
+        """C++ writer for large files (no identical-transcript records); same bytes as the Python writers."""
+        L = lib()
+        h = L.mmq_synth_create(*self._args)
+        rc = L.mmq_synth_write_hits(h, os.fsencode(path), 1 if binary else 0, int(self.haplo))
+        L.mmq_synth_destroy(h)
+        if rc:
+            raise RuntimeError(f"cannot write {path}")
 
     # names: gene ids are zero-padded so that std::map (byte-wise) order == numeric order
     def transcript_name(self, t):
