@@ -6,10 +6,17 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <sstream>
+#include <thread>
 #include <unordered_map>
 
 namespace mmq {
@@ -17,7 +24,9 @@ namespace mmq {
 namespace {
 
 /* Buffered byte stream over a file, transparently zlib-inflated when the file
- * starts with 0x78 (src/hitsio.cpp:258: "lazy but sufficient" detection). */
+ * starts with 0x78 (src/hitsio.cpp:258: "lazy but sufficient" detection).  Reading and
+ * inflating run in a producer thread that hands 4 MB blocks to the parser through a small
+ * queue, so decompression overlaps parsing and class building. */
 class ByteSource {
  public:
   ~ByteSource() { close(); }
@@ -33,12 +42,18 @@ class ByteSource {
       zinit_ = true;
       in_.resize(1 << 20);
     }
-    buf_.resize(1 << 20);
     pos_ = len_ = 0;
-    hit_eof_ = false;
+    producer_done_ = false;
+    stop_ = false;
+    prod_ = std::thread([this] { produce(); });
     return true;
   }
   void close() {
+    if (prod_.joinable()) {
+      { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+      cv_.notify_all();
+      prod_.join();
+    }
     if (zinit_) { inflateEnd(&zs_); zinit_ = false; }
     if (f_) { fclose(f_); f_ = nullptr; }
   }
@@ -69,6 +84,16 @@ class ByteSource {
       pos_ = len_;
     }
   }
+  /* a line as a view into the current block (no copy) unless it straddles two blocks */
+  bool getline_view(const char*& p, size_t& n) {
+    if (pos_ == len_ && !fill()) return false;
+    const char* b = buf_.data() + pos_;
+    const char* nl = (const char*)memchr(b, '\n', len_ - pos_);
+    if (nl) { p = b; n = (size_t)(nl - b); pos_ += n + 1; return true; }
+    if (!getline(carry_)) return false;
+    p = carry_.data(); n = carry_.size();
+    return true;
+  }
   bool read_bytes(void* dst, size_t n) {
     char* d = (char*)dst;
     while (n) {
@@ -79,7 +104,10 @@ class ByteSource {
     }
     return true;
   }
-  bool read_u32(uint32_t& v) { return read_bytes(&v, 4); } /* raw little-endian, src/hitsio.cpp:22-34 */
+  bool read_u32(uint32_t& v) { /* raw little-endian, src/hitsio.cpp:22-34 */
+    if (len_ - pos_ >= 4) { memcpy(&v, buf_.data() + pos_, 4); pos_ += 4; return true; }
+    return read_bytes(&v, 4);
+  }
   /* one byte, or 0xFF followed by a uint32 (src/hitsio.cpp:36-55) */
   bool read_small(uint32_t& v) {
     int c = get();
@@ -90,35 +118,67 @@ class ByteSource {
   }
 
  private:
-  bool fill() {
-    if (hit_eof_) return false;
-    pos_ = len_ = 0;
-    if (!compressed_) {
-      len_ = fread(buf_.data(), 1, buf_.size(), f_);
-      if (len_ == 0) { hit_eof_ = true; return false; }
-      return true;
-    }
-    while (len_ == 0) {
-      if (zs_.avail_in == 0) {
-        size_t got = fread(in_.data(), 1, in_.size(), f_);
-        if (got == 0) { hit_eof_ = true; return false; }
-        zs_.next_in = (Bytef*)in_.data();
-        zs_.avail_in = (uInt)got;
+  static constexpr size_t BLOCK = (size_t)4 << 20;
+  /* producer thread: read (and inflate) the file into blocks */
+  void produce() {
+    for (;;) {
+      std::vector<char> blk(BLOCK);
+      size_t got = 0;
+      bool last = false;
+      if (!compressed_) {
+        got = fread(blk.data(), 1, blk.size(), f_);
+        last = got < blk.size();
+      } else {
+        while (got < blk.size() && !last) {
+          if (zs_.avail_in == 0) {
+            size_t r = fread(in_.data(), 1, in_.size(), f_);
+            if (r == 0) { last = true; break; }
+            zs_.next_in = (Bytef*)in_.data();
+            zs_.avail_in = (uInt)r;
+          }
+          zs_.next_out = (Bytef*)blk.data() + got;
+          zs_.avail_out = (uInt)(blk.size() - got);
+          int rc = inflate(&zs_, Z_NO_FLUSH);
+          got = blk.size() - zs_.avail_out;
+          if (rc == Z_STREAM_END) { last = true; break; }
+          if (rc != Z_OK && rc != Z_BUF_ERROR) { corrupt_ = true; last = true; break; }
+        }
       }
-      zs_.next_out = (Bytef*)buf_.data();
-      zs_.avail_out = (uInt)buf_.size();
-      int rc = inflate(&zs_, Z_NO_FLUSH);
-      len_ = buf_.size() - zs_.avail_out;
-      if (rc == Z_STREAM_END) { if (len_ == 0) { hit_eof_ = true; return false; } hit_eof_ = (zs_.avail_in == 0); zend_ = true; return true; }
-      if (rc != Z_OK && rc != Z_BUF_ERROR) { corrupt_ = true; hit_eof_ = true; return len_ > 0; }
+      blk.resize(got);
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return q_.size() < 4 || stop_; });
+        if (stop_) return;
+        if (got) q_.push_back(std::move(blk));
+        if (last) producer_done_ = true;
+      }
+      cv_.notify_all();
+      if (last) return;
     }
-    return true;
+  }
+  bool fill() {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !q_.empty() || producer_done_; });
+    if (q_.empty()) return false;
+    buf_ = std::move(q_.front());
+    q_.pop_front();
+    lk.unlock();
+    cv_.notify_all();
+    pos_ = 0;
+    len_ = buf_.size();
+    return len_ > 0;
   }
   FILE* f_ = nullptr;
-  bool compressed_ = false, zinit_ = false, hit_eof_ = false, corrupt_ = false, zend_ = false;
+  bool compressed_ = false, zinit_ = false, corrupt_ = false;
   z_stream zs_;
   std::vector<char> buf_, in_;
+  std::string carry_;
   size_t pos_ = 0, len_ = 0;
+  std::thread prod_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::vector<char>> q_;
+  bool producer_done_ = false, stop_ = false;
 };
 
 inline uint64_t mix64(uint64_t x) {
@@ -149,6 +209,135 @@ struct ClassBuilder::Impl {
   std::vector<int64_t> rec_wptr{0};
   std::vector<std::pair<int32_t, float>> comb;
 
+  /* ---- parallel ingestion (unweighted): add_record() does the sequential part (column
+   * numbering, de-duplication, sort, hash) and hands the class key to one of K shard workers
+   * chosen by the hash; each worker owns a hash table.  finish() merges the shards' classes in
+   * order of their first record, which is exactly the sequential first-appearance numbering. */
+  struct Batch {
+    std::vector<int64_t> rec;
+    std::vector<uint64_t> hash;
+    std::vector<uint32_t> off{0};
+    std::vector<int32_t> cols;
+    void clear() { rec.clear(); hash.clear(); off.assign(1, 0); cols.clear(); }
+  };
+  struct Shard {
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<std::unique_ptr<Batch>> q;
+    bool done = false;
+    std::thread th;
+    std::unique_ptr<Batch> cur;
+    /* worker-owned */
+    std::vector<int32_t> table;
+    std::vector<uint64_t> hash;
+    std::vector<int64_t> ptr{0};
+    std::vector<int32_t> col, k;
+    std::vector<int64_t> first_rec;
+    std::vector<std::pair<int64_t, int32_t>> rec_cls; /* per-fragment layouts */
+  };
+  std::vector<std::unique_ptr<Shard>> shards;
+  int64_t n_records_keyed = 0; /* records that carry a class (non-empty) */
+  static constexpr size_t BATCH_RECORDS = 16384;
+
+  void worker(Shard& S, bool keep_rec) {
+    S.table.assign((size_t)1 << 16, -1);
+    for (;;) {
+      std::unique_ptr<Batch> b;
+      {
+        std::unique_lock<std::mutex> lk(S.mu);
+        S.cv.wait(lk, [&] { return !S.q.empty() || S.done; });
+        if (S.q.empty()) return;
+        b = std::move(S.q.front());
+        S.q.pop_front();
+      }
+      S.cv.notify_all();
+      const size_t nb = b->rec.size();
+      for (size_t i = 0; i < nb; ++i) {
+        const int32_t* c = b->cols.data() + b->off[i];
+        const size_t d = b->off[i + 1] - b->off[i];
+        const uint64_t hsh = b->hash[i];
+        size_t mask = S.table.size() - 1, s = (size_t)hsh & mask;
+        int32_t cid = -1;
+        for (;;) {
+          const int32_t t = S.table[s];
+          if (t < 0) break;
+          if (S.hash[(size_t)t] == hsh && (size_t)(S.ptr[(size_t)t + 1] - S.ptr[(size_t)t]) == d &&
+              std::memcmp(S.col.data() + S.ptr[(size_t)t], c, d * sizeof(int32_t)) == 0) { cid = t; break; }
+          s = (s + 1) & mask;
+        }
+        if (cid < 0) {
+          cid = (int32_t)S.hash.size();
+          S.col.insert(S.col.end(), c, c + d);
+          S.ptr.push_back((int64_t)S.col.size());
+          S.k.push_back(0);
+          S.hash.push_back(hsh);
+          S.first_rec.push_back(b->rec[i]);
+          S.table[s] = cid;
+          if (S.hash.size() * 2 > S.table.size()) {
+            const size_t nsz = S.table.size() * 2;
+            std::vector<int32_t> nt(nsz, -1);
+            for (size_t t = 0; t < S.hash.size(); ++t) {
+              size_t z = (size_t)S.hash[t] & (nsz - 1);
+              while (nt[z] >= 0) z = (z + 1) & (nsz - 1);
+              nt[z] = (int32_t)t;
+            }
+            S.table.swap(nt);
+          }
+        }
+        S.k[(size_t)cid]++;
+        if (keep_rec) S.rec_cls.emplace_back(b->rec[i], cid);
+      }
+    }
+  }
+  void push(Shard& S) {
+    {
+      std::unique_lock<std::mutex> lk(S.mu);
+      S.cv.wait(lk, [&] { return S.q.size() < 8; }); /* bounded: the parser cannot run away from the workers */
+      S.q.push_back(std::move(S.cur));
+    }
+    S.cv.notify_all();
+    S.cur.reset(new Batch());
+  }
+  void start_workers(int K) {
+    const bool keep_rec = layout != LAYOUT_COLLAPSED;
+    for (int i = 0; i < K; ++i) {
+      shards.emplace_back(new Shard());
+      shards.back()->cur.reset(new Batch());
+    }
+    for (auto& sp : shards) { Shard* S = sp.get(); S->th = std::thread([this, S, keep_rec] { worker(*S, keep_rec); }); }
+  }
+  /* drain the workers and lay the classes out in first-appearance order (cls_*, rec_class) */
+  void merge_shards() {
+    for (auto& sp : shards) { if (!sp->cur->rec.empty()) push(*sp); }
+    for (auto& sp : shards) { { std::lock_guard<std::mutex> lk(sp->mu); sp->done = true; } sp->cv.notify_all(); }
+    for (auto& sp : shards) sp->th.join();
+    struct Ref { int64_t first; int32_t shard, local; };
+    std::vector<Ref> refs;
+    for (size_t s = 0; s < shards.size(); ++s)
+      for (size_t c = 0; c < shards[s]->hash.size(); ++c) refs.push_back({shards[s]->first_rec[c], (int32_t)s, (int32_t)c});
+    std::sort(refs.begin(), refs.end(), [](const Ref& a, const Ref& b) { return a.first < b.first; });
+    std::vector<std::vector<int32_t>> l2g(shards.size());
+    for (size_t s = 0; s < shards.size(); ++s) l2g[s].resize(shards[s]->hash.size());
+    cls_ptr.assign(1, 0); cls_col.clear(); cls_k.clear(); cls_hash.clear();
+    cls_k.reserve(refs.size()); cls_hash.reserve(refs.size());
+    for (size_t g = 0; g < refs.size(); ++g) {
+      const Shard& S = *shards[(size_t)refs[g].shard];
+      const int32_t c = refs[g].local;
+      l2g[(size_t)refs[g].shard][(size_t)c] = (int32_t)g;
+      cls_col.insert(cls_col.end(), S.col.begin() + S.ptr[(size_t)c], S.col.begin() + S.ptr[(size_t)c + 1]);
+      cls_ptr.push_back((int64_t)cls_col.size());
+      cls_k.push_back(S.k[(size_t)c]);
+      cls_hash.push_back(S.hash[(size_t)c]);
+    }
+    if (layout != LAYOUT_COLLAPSED) {
+      /* records were numbered densely over the keyed ones, in stream order */
+      rec_class.assign((size_t)n_records_keyed, -1);
+      for (size_t s = 0; s < shards.size(); ++s)
+        for (auto& rc : shards[s]->rec_cls) rec_class[(size_t)rc.first] = l2g[s][(size_t)rc.second];
+    }
+    shards.clear();
+  }
+
   void grow_table() {
     size_t nsz = table.empty() ? (size_t)1 << 16 : table.size() * 2;
     std::vector<int32_t> nt(nsz, -1);
@@ -172,8 +361,18 @@ ClassBuilder::ClassBuilder(int64_t T, int layout, bool weighted) : p_(new Impl()
     for (int64_t t = 0; t < T; ++t) { p_->hdr2col[(size_t)t] = (int32_t)t; p_->col2hdr[(size_t)t] = (int32_t)t; }
   }
   p_->grow_table();
+  if (!weighted) {
+    int K = 3;
+    if (const char* e = getenv("MMQ_LOADER_THREADS")) K = atoi(e);
+    const unsigned hc = std::thread::hardware_concurrency();
+    if (hc && (int)hc - 2 < K) K = std::max(0, (int)hc - 2);
+    if (K > 0) p_->start_workers(K);
+  }
 }
-ClassBuilder::~ClassBuilder() { delete p_; }
+ClassBuilder::~ClassBuilder() {
+  if (!p_->shards.empty()) p_->merge_shards();
+  delete p_;
+}
 
 void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
   Impl& P = *p_;
@@ -199,6 +398,16 @@ void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
   std::sort(comb.begin(), comb.end(), [](const std::pair<int32_t, float>& a, const std::pair<int32_t, float>& b) { return a.first < b.first; });
   uint64_t hsh = 0x9e3779b97f4a7c15ull ^ (uint64_t)comb.size();
   for (auto& e : comb) hsh = mix64(hsh ^ (uint64_t)(uint32_t)e.first) + 0x632be59bd9b4e019ull;
+  if (!P.shards.empty()) { /* parallel ingestion: the table work happens in the shard's worker */
+    Impl::Shard& S = *P.shards[(size_t)((hsh >> 40) % P.shards.size())];
+    Impl::Batch& B = *S.cur;
+    B.rec.push_back(P.n_records_keyed++);
+    B.hash.push_back(hsh);
+    for (auto& e : comb) B.cols.push_back(e.first);
+    B.off.push_back((uint32_t)B.cols.size());
+    if (B.rec.size() >= Impl::BATCH_RECORDS) P.push(S);
+    return;
+  }
   size_t mask = P.table.size() - 1;
   size_t s = (size_t)hsh & mask;
   int32_t cid = -1;
@@ -237,6 +446,7 @@ void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
 
 void ClassBuilder::finish(HitClasses& out) {
   Impl& P = *p_;
+  if (!P.shards.empty()) P.merge_shards();
   if (P.header_order) {
     /* renumber the observed transcripts by header index; members of a class stay ascending */
     const int64_t n0 = (int64_t)P.col2hdr.size();
@@ -361,6 +571,37 @@ struct NameIndex {
   int32_t find(const std::string& s) const {
     auto it = map.find(s);
     return it == map.end() ? -1 : it->second;
+  }
+  /* allocation-free lookup for the record loop of the text schema (one call per alignment):
+   * open addressing over FNV-1a, names compared in place */
+  const std::vector<std::string>* names = nullptr;
+  std::vector<uint32_t> slots; /* header index + 1, 0 = empty */
+  static uint64_t fnv(const char* p, size_t n) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t i = 0; i < n; ++i) { h ^= (unsigned char)p[i]; h *= 0x100000001b3ull; }
+    return h ^ (h >> 29);
+  }
+  void build_fast(const std::vector<std::string>& nm) {
+    names = &nm;
+    size_t sz = 64;
+    while (sz < nm.size() * 2 + 8) sz <<= 1;
+    slots.assign(sz, 0);
+    for (size_t i = 0; i < nm.size(); ++i) {
+      size_t s = (size_t)fnv(nm[i].data(), nm[i].size()) & (sz - 1);
+      bool dup = false;
+      while (slots[s]) { if ((*names)[slots[s] - 1] == nm[i]) { dup = true; break; } s = (s + 1) & (sz - 1); }
+      if (!dup) slots[s] = (uint32_t)i + 1; /* first wins, as map::insert */
+    }
+  }
+  int32_t find_fast(const char* p, size_t n) const {
+    const size_t mask = slots.size() - 1;
+    size_t s = (size_t)fnv(p, n) & mask;
+    while (slots[s]) {
+      const std::string& cand = (*names)[slots[s] - 1];
+      if (cand.size() == n && memcmp(cand.data(), p, n) == 0) return (int32_t)slots[s] - 1;
+      s = (s + 1) & mask;
+    }
+    return -1;
   }
 };
 
@@ -490,23 +731,28 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
   std::vector<std::string> all_names = hdr.names;
   if (finish_header(hdr, genes_raw, ident_raw, idx, err)) return 1;
   const int64_t T = (int64_t)hdr.names.size();
+  const bool timing = getenv("MMQ_LOADER_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_hdr = now();
   ClassBuilder cb(T, layout, false);
   std::vector<int32_t> tids;
   if (hdr.schema == 0) {
     /* records, src/hitsio.cpp:331-347 */
+    idx.build_fast(hdr.names);
+    const char* lp; size_t ln;
     for (;;) {
       if (src.peek() == EOF) break;
-      if (!src.getline(line)) break;
-      if (line.empty() || line[0] != '>') { err = "Hits file looks malformed."; return 1; }
+      if (!src.getline_view(lp, ln)) break;
+      if (ln == 0 || lp[0] != '>') { err = "Hits file looks malformed."; return 1; }
       if (src.peek() == EOF) {
         fprintf(stderr, "Warning: read record without any mapping transcripts found at the end of the hits file. The hits file may be corrupted.\n");
         break;
       }
       tids.clear();
       while (src.peek() != EOF && src.peek() != '>') {
-        if (!src.getline(line)) break;
-        int32_t h = idx.find(line);
-        if (h < 0) { err = "Error: transcript '" + line + "' has no length."; return 1; } /* src/mmseq.cpp:599-601 */
+        if (!src.getline_view(lp, ln)) break;
+        int32_t h = idx.find_fast(lp, ln);
+        if (h < 0) { err = "Error: transcript '" + std::string(lp, ln) + "' has no length."; return 1; } /* src/mmseq.cpp:599-601 */
         tids.push_back(h);
       }
       cb.add_record(tids.data(), nullptr, (int)tids.size());
@@ -515,11 +761,12 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
     /* records, src/hitsio.cpp:413-439; read names are delta-coded (:101-115) and unused here */
     std::string mid;
     for (;;) {
-      if (!src.getline(line)) break;
-      if (line.empty()) {
+      const char* lp; size_t ln;
+      if (!src.getline_view(lp, ln)) break;
+      if (ln == 0) {
         uint32_t nb = 0, ne = 0;
         if (!src.read_small(nb)) break;
-        if (!src.getline(mid)) break;
+        if (!src.getline_view(lp, ln)) break;
         if (!src.read_small(ne)) break;
       }
       uint32_t cnt = 0;
@@ -537,7 +784,9 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
     }
   }
   if (src.corrupt()) { err = "Error: zlib stream of \"" + path + "\" is corrupt."; return 1; }
+  const double t_rec = now();
   cb.finish(cls);
+  if (timing) fprintf(stderr, "[loader] records %.2f s, finish (merge + layout) %.2f s\n", t_rec - t_hdr, now() - t_rec);
   return 0;
 }
 
