@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--weights", action="store_true", help="fp32 per-hit weights (config 4's extension)")
     ap.add_argument("--transposed", action="store_true", help="materialise X + atomic-free transposed reduction")
     ap.add_argument("--cpu-sweeps", type=int, default=4, help="sweeps of the CPU baseline sample")
+    ap.add_argument("--nccl-only", action="store_true", help="N > 1: exchange counts with ncclAllReduce instead of the fused peer-memory kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extra", action="store_true", help="also time the collapsed layout and EM (extra keys)")
@@ -199,6 +200,7 @@ def workload_config(args, h, world, sweeps_per_step=SWEEPS_PER_STEP):
         "n_columns": int(h.n), "classes_per_gpu": int(h.m), "nnz_per_gpu": int(h.nnz), "distinct_classes_per_gpu": int(h.n_classes),
         "sweeps_per_step": sweeps_per_step, "trace_stride": SWEEPS_PER_STEP, "seed": SEED,
         "count_path": "transposed" if args.transposed else "fused_reduction",
+        "count_exchange": ("none" if world == 1 else ("nccl_allreduce" if getattr(args, "nccl_only", False) else "fused_p2p_gamma")),
         "l2": "inputs_exceed_l2" if (4 * h.nnz + 8 * h.m) > 200e6 else "inputs_fit_l2_flush_between_steps",
     }
 
@@ -248,6 +250,10 @@ def main():
         uid = [capi.comm_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         H.comm_init(uid[0], rank, world)
+        if not args.nccl_only:   # count exchange fused into the Gamma kernel over NVLink peer memory
+            hs = [None] * world
+            dist.all_gather_object(hs, H.p2p_export())
+            H.p2p_attach(hs, rank, world)
     H.init_mu()
     mu0 = H.get_mu()
 
@@ -301,6 +307,10 @@ def main():
         H2 = capi.Handle(rp, col, kk, ll, weight=ww, class_id_base=cid_base, device=local, class_id=class_id)   # H2D of the CSR shard
         if world > 1:
             H.comm_move_to(H2)   # the process keeps its NCCL communicator across samples
+            if not args.nccl_only:
+                hs = [None] * world
+                dist.all_gather_object(hs, H2.p2p_export())
+                H2.p2p_attach(hs, rank, world)
         H2.set_mu(mu_h)                                                                        # H2D
         H2.gibbs(SEED, 0, K * S, stride=S, trace_len=K, flags=flags)
         mu_out = H2.get_mu()                                                                   # D2H

@@ -89,6 +89,20 @@ int mmq_comm_init(mmq_handle* h, const char id[128], int rank, int nranks);
  * the next sample's shard without paying NCCL initialisation again. */
 int mmq_comm_move(mmq_handle* from, mmq_handle* to);
 
+/* Fused count exchange over NVLink peer memory (optional, on top of the communicator).
+ * After mmq_p2p_attach the Gibbs sweep makes no NCCL call: the Gamma kernel of every rank
+ * signals "my allocation is done" into its peers' flag words, waits for theirs, then reads the
+ * count vectors of ALL ranks straight from peer memory (P2P loads), sums them and draws —
+ * the all-reduce (src/mmseq.cpp:895-899) and the Gamma update (:904-908) are ONE kernel.
+ * Counts are double-buffered by sweep parity so no second barrier is needed.
+ *   multi-process: every rank calls mmq_p2p_export (64-byte cudaIpcMemHandle), the caller
+ *     gathers the handles of all ranks (rank order) and passes them to mmq_p2p_attach;
+ *   single process, one handle per GPU: mmq_p2p_attach_local with the handles in rank order.
+ * All ranks must then issue the same sequence of sweeps (they already must, for NCCL). */
+int mmq_p2p_export(mmq_handle* h, char ipc_handle[64]);
+int mmq_p2p_attach(mmq_handle* h, const char* ipc_handles, int rank, int nranks);
+int mmq_p2p_attach_local(mmq_handle** handles, int nranks);
+
 /* mu0[t] = (sum_{i containing t} k[i]/|i|)/l[t] and unique_hits[t] =
  * counts_shared[t][0]; src/mmseq.cpp:617-638.  Leaves mu0 as the current mu.
  * unique_hits_out (int32[n]) may be NULL. */

@@ -51,6 +51,9 @@ def _load():
         "mmq_comm_id": (i32, [C.c_char_p]),
         "mmq_comm_init": (i32, [vp, C.c_char_p, i32, i32]),
         "mmq_comm_move": (i32, [vp, vp]),
+        "mmq_p2p_export": (i32, [vp, C.c_char_p]),
+        "mmq_p2p_attach": (i32, [vp, C.c_char_p, i32, i32]),
+        "mmq_p2p_attach_local": (i32, [C.POINTER(vp), i32]),
         "mmq_init_mu": (i32, [vp, vp]),
         "mmq_set_mu": (i32, [vp, vp]),
         "mmq_get_mu": (i32, [vp, vp]),
@@ -90,7 +93,7 @@ def lib():
 
 EXPORTS = [
     "mmq_create", "mmq_destroy", "mmq_last_error", "mmq_set_stream", "mmq_get_stream", "mmq_synchronize",
-    "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
+    "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_p2p_export", "mmq_p2p_attach", "mmq_p2p_attach_local", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
     "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
     "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_version",
@@ -143,6 +146,14 @@ def prior_draws(ids, rate, alpha, seed, trace_len, device=0):
     if rc:
         raise MmqError("mmq_prior_draws: " + lib().mmq_last_error(None).decode())
     return out
+
+
+def p2p_attach_local(handles):
+    """Single process, one Handle per GPU (rank order)."""
+    arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+    rc = lib().mmq_p2p_attach_local(arr, len(handles))
+    if rc:
+        raise MmqError("mmq_p2p_attach_local: " + lib().mmq_last_error(handles[0]._h).decode())
 
 
 class Handle:
@@ -205,6 +216,17 @@ class Handle:
 
     def comm_move_to(self, other):
         self._check(lib().mmq_comm_move(self._h, other._h), "mmq_comm_move")
+
+    def p2p_export(self):
+        buf = C.create_string_buffer(64)
+        self._check(lib().mmq_p2p_export(self._h, buf), "mmq_p2p_export")
+        return buf.raw
+
+    def p2p_attach(self, handles, rank, nranks):
+        """handles: the 64-byte exports of all ranks, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        self._check(lib().mmq_p2p_attach(self._h, blob, rank, nranks), "mmq_p2p_attach")
 
     def init_mu(self):
         uh = np.zeros(self.n, np.int32)

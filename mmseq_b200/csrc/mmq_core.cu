@@ -570,6 +570,48 @@ __global__ void k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict_
   }
 }
 
+/* K3 + K4 fused over NVLink peer memory.  Block 0 publishes this rank's epoch into every peer's
+ * flag word (its allocation kernel has completed: stream order), every block waits until all
+ * ranks have published this epoch, then each thread sums the count vectors of all ranks with
+ * P2P loads and draws the Gamma variate — identical on every rank (same counter-based stream).
+ * The other parity buffer (nobody reads it any more: everyone passed this epoch's barrier only
+ * after finishing the previous Gamma kernel) is reset for the next sweep. */
+struct mmq_p2p_args {
+  const int32_t* counts[MMQ_P2P_MAX]; /* this epoch's parity buffer of every rank */
+  int32_t* flags[MMQ_P2P_MAX];        /* flag array of every rank */
+  int32_t* reset;                      /* own buffer of the other parity */
+  int32_t* local_flags;
+  int nranks, rank, epoch;
+};
+__global__ void k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
+                            double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
+                            double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
+  if (blockIdx.x == 0 && threadIdx.x < a.nranks) {
+    __threadfence_system();
+    *reinterpret_cast<volatile int32_t*>(a.flags[threadIdx.x] + a.rank) = a.epoch;
+  }
+  if (threadIdx.x == 0) {
+    for (int r = 0; r < a.nranks; ++r) /* own allocation is complete by stream order: no wait on self */
+      if (r != a.rank)
+        while (*reinterpret_cast<volatile int32_t*>(a.local_flags + r) < a.epoch) { }
+    __threadfence_system();
+  }
+  __syncthreads();
+  double* trace_col = nullptr;
+  if (trace && stride > 0 && sweep % (uint32_t)stride == 0 && sweep / (uint32_t)stride < (uint32_t)trace_len) trace_col = trace + sweep / (uint32_t)stride;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t c = 0;
+    for (int r = 0; r < a.nranks; ++r) c += __ldcv(a.counts[r] + t);
+    a.reset[t] = counts_base ? counts_base[t] : 0;
+    if (counts_copy) counts_copy[t] = c;
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
+    const double v = mmq_gamma(&g, alpha + (double)c, beta + len[t]);
+    mu[t] = v;
+    if (trace_col) trace_col[t * (int64_t)trace_len] = v;
+  }
+}
+
 __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
 __global__ void k_add_u32(uint32_t* p, uint32_t v) { *p += v; }
 
@@ -785,6 +827,7 @@ void mmq_destroy(mmq_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   drop_graph(h);
+  for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->ev_alloc) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_gamma) cudaEventDestroy(e);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
@@ -848,6 +891,93 @@ int mmq_comm_move(mmq_handle* from, mmq_handle* to) {
   MMQ_CUDA(from, cudaStreamSynchronize(from->stream));
   to->comm = from->comm; to->rank = from->rank; to->nranks = from->nranks;
   from->comm = nullptr; from->rank = 0; from->nranks = 1;
+  return MMQ_OK;
+}
+
+/* ---- fused count exchange over peer memory ---- */
+static int p2p_alloc(mmq_handle* h) {
+  if (h->p2p_buf) return MMQ_OK;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  const size_t head = 256;
+  const size_t bytes = head + 2 * sizeof(int32_t) * (size_t)h->n;
+  int rc = mmq_dev_alloc(h, &h->p2p_buf, bytes);
+  if (rc) return rc;
+  h->p2p_flags = (int32_t*)h->p2p_buf;
+  h->p2p_counts[0] = (int32_t*)((char*)h->p2p_buf + head);
+  h->p2p_counts[1] = h->p2p_counts[0] + h->n;
+  MMQ_CUDA(h, cudaMemsetAsync(h->p2p_buf, 0, head, h->stream));
+  /* both parity buffers start from the current counts (zero, or the singleton base of a segment plan) */
+  for (int b = 0; b < 2; ++b)
+    MMQ_CUDA(h, cudaMemcpyAsync(h->p2p_counts[b], h->counts, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  return MMQ_OK;
+}
+
+int mmq_p2p_export(mmq_handle* h, char ipc_handle[64]) {
+  if (!h || !ipc_handle) return mmq_fail(h, MMQ_ERR_ARG, "mmq_p2p_export: NULL argument");
+  int rc = p2p_alloc(h);
+  if (rc) return rc;
+  cudaIpcMemHandle_t mh;
+  static_assert(sizeof(mh) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  MMQ_CUDA(h, cudaIpcGetMemHandle(&mh, h->p2p_buf));
+  memcpy(ipc_handle, &mh, 64);
+  return MMQ_OK;
+}
+
+static void p2p_finish_attach(mmq_handle* h, int rank, int nranks) {
+  h->p2p_rank = rank;
+  h->p2p_n = nranks;
+  h->p2p_epoch = 0;
+  h->counts_own = h->counts;
+  h->counts = h->p2p_counts[0];
+}
+
+int mmq_p2p_attach(mmq_handle* h, const char* ipc_handles, int rank, int nranks) {
+  if (!h || !ipc_handles || nranks < 1 || nranks > MMQ_P2P_MAX || rank < 0 || rank >= nranks) return mmq_fail(h, MMQ_ERR_ARG, "mmq_p2p_attach: bad arguments");
+  if (h->p2p_n > 1) return mmq_fail(h, MMQ_ERR_STATE, "mmq_p2p_attach: already attached");
+  int rc = p2p_alloc(h);
+  if (rc) return rc;
+  const size_t head = 256;
+  for (int r = 0; r < nranks; ++r) {
+    void* base = h->p2p_buf;
+    if (r != rank) {
+      cudaIpcMemHandle_t mh;
+      memcpy(&mh, ipc_handles + 64 * r, 64);
+      MMQ_CUDA(h, cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
+      h->p2p_opened[r] = base;
+    }
+    h->p2p_peer_flags[r] = (int32_t*)base;
+    h->p2p_peer_counts[r][0] = (const int32_t*)((char*)base + head);
+    h->p2p_peer_counts[r][1] = h->p2p_peer_counts[r][0] + h->n;
+  }
+  p2p_finish_attach(h, rank, nranks);
+  return MMQ_OK;
+}
+
+int mmq_p2p_attach_local(mmq_handle** hs, int nranks) {
+  if (!hs || nranks < 1 || nranks > MMQ_P2P_MAX) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_p2p_attach_local: bad arguments");
+  for (int r = 0; r < nranks; ++r) {
+    if (!hs[r] || hs[r]->n != hs[0]->n) return mmq_fail(hs[0], MMQ_ERR_ARG, "mmq_p2p_attach_local: handles must share n");
+    int rc = p2p_alloc(hs[r]);
+    if (rc) return rc;
+  }
+  const size_t head = 256;
+  for (int r = 0; r < nranks; ++r) {
+    mmq_handle* h = hs[r];
+    MMQ_CUDA(h, cudaSetDevice(h->device));
+    for (int q = 0; q < nranks; ++q) {
+      if (q != r && hs[q]->device != h->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(hs[q]->device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+        else if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+      }
+      h->p2p_peer_flags[q] = (int32_t*)hs[q]->p2p_buf;
+      h->p2p_peer_counts[q][0] = (const int32_t*)((char*)hs[q]->p2p_buf + head);
+      h->p2p_peer_counts[q][1] = h->p2p_peer_counts[q][0] + h->n;
+    }
+    p2p_finish_attach(h, r, nranks);
+  }
   return MMQ_OK;
 }
 
@@ -1033,6 +1163,22 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       mark(h->ev_alloc);
     }
   }
+  if (h->p2p_n > 1) { /* all-reduce and Gamma update fused over peer memory */
+    const int b = h->p2p_epoch & 1;
+    mmq_p2p_args a;
+    for (int r = 0; r < h->p2p_n; ++r) { a.counts[r] = h->p2p_peer_counts[r][b]; a.flags[r] = h->p2p_peer_flags[r]; }
+    a.reset = h->p2p_counts[b ^ 1];
+    a.local_flags = h->p2p_flags;
+    a.nranks = h->p2p_n; a.rank = h->p2p_rank; a.epoch = ++h->p2p_epoch;
+    mark(h->ev_gamma);
+    k_gamma_p2p<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
+                                                                              h->trace_len, h->n, h->alpha, h->beta, seed, sweep, counts_copy);
+    MMQ_LAUNCHED(h);
+    mark(h->ev_gamma);
+    h->counts = h->p2p_counts[h->p2p_epoch & 1]; /* the next sweep reduces into the other parity buffer */
+    if (h->seg_base) h->seg_base_in_counts = true;
+    return MMQ_OK;
+  }
   if ((rc = mmq_allreduce(h, h->counts, (size_t)h->n, 0))) return rc;
   mark(h->ev_gamma);
   k_gamma<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride, h->trace_len, h->n,
@@ -1101,7 +1247,7 @@ int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweep
   /* CUDA graph for the bulk of a long run (single GPU; the timed mode needs per-launch events):
    * the first sweep goes out as plain launches (it builds lazily allocated state), then whole
    * graphs of MMQ_GRAPH_SWEEPS sweeps, then the remainder as plain launches */
-  const bool use_graph = !(flags & (MMQ_GIBBS_NO_GRAPH | MMQ_GIBBS_TIME_KERNELS)) && h->nranks == 1 && n_sweeps >= 1 + 2 * MMQ_GRAPH_SWEEPS;
+  const bool use_graph = !(flags & (MMQ_GIBBS_NO_GRAPH | MMQ_GIBBS_TIME_KERNELS)) && h->nranks == 1 && h->p2p_n <= 1 && n_sweeps >= 1 + 2 * MMQ_GRAPH_SWEEPS;
   if (use_graph) {
     if ((rc = enqueue_sweep(h, seed, (uint32_t)s, flags, st, nullptr, nullptr))) return rc;
     ++s;

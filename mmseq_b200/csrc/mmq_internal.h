@@ -18,6 +18,7 @@
 #define MMQ_ALLOC_WARPS 8
 #define MMQ_ALLOC_CAP 320 /* staged CSR entries per warp tile */
 #define MMQ_GRAPH_SWEEPS 16 /* sweeps per captured CUDA graph */
+#define MMQ_P2P_MAX 8      /* ranks of one NVSwitch box */
 
 struct mmq_group_set {
   int64_t ngroups = 0;
@@ -88,6 +89,17 @@ struct mmq_handle {
   int32_t* seg_base = nullptr; /* [n] or null */
   bool seg_base_in_counts = true; /* counts[] currently starts from seg_base */
   int64_t seg_entries = 0, seg_rows = 0, seg_singletons = 0;
+
+  /* fused count exchange over peer memory: [flags int32[MMQ_P2P_MAX] | pad | counts A[n] | counts B[n]] */
+  void* p2p_buf = nullptr;
+  int32_t* p2p_flags = nullptr;
+  int32_t* p2p_counts[2] = {nullptr, nullptr};
+  int32_t* p2p_peer_flags[MMQ_P2P_MAX] = {};
+  const int32_t* p2p_peer_counts[MMQ_P2P_MAX][2] = {};
+  void* p2p_opened[MMQ_P2P_MAX] = {}; /* cudaIpcOpenMemHandle mappings to close */
+  int p2p_n = 0, p2p_rank = 0;
+  int32_t p2p_epoch = 0;
+  int32_t* counts_own = nullptr; /* the single-GPU counts buffer (counts points into p2p_buf when attached) */
 
   /* CUDA graph of MMQ_GRAPH_SWEEPS consecutive sweeps; the sweep counter is read from
    * graph_base on the device, so one instantiated graph serves the whole chain */

@@ -340,6 +340,11 @@ int main(int argc, char** argv) {
     if (mmq_comm_id(uid)) die(string("Error: mmq_comm_id: ") + mmq_last_error(nullptr));
     on_all([&](int g) { check(mmq_comm_init(shards[(size_t)g].h, uid, g, ngpus), shards[(size_t)g].h, "mmq_comm_init"); });
   }
+  if (ngpus > 1) { /* Gibbs: all-reduce + Gamma update fused over NVLink peer memory (no NCCL call per sweep) */
+    vector<mmq_handle*> hs;
+    for (auto& S : shards) hs.push_back(S.h);
+    if (mmq_p2p_attach_local(hs.data(), ngpus)) cerr << "Note: peer access unavailable (" << mmq_last_error(hs[0]) << "); using NCCL for the count exchange." << endl;
+  }
   mmq_handle* H0 = shards[0].h;
 
   /* ---- initial mu, unique hits (src/mmseq.cpp:610-638) */

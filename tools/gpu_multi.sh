@@ -17,3 +17,4 @@ try:
 except Exception as e: print("N",N,"failed",e)
 PY
 done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --steps 10 --warmup 3 --nccl-only --no-e2e 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('N 2 nccl-only sweeps/s', round(d['sweeps_per_s'],1), 'step_ms', round(d['ms_per_step'],3))"
