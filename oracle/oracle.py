@@ -11,7 +11,8 @@ Contents
     (src/hitsio.cpp:250-447), of class construction (src/mmseq.cpp:395-441)
     and of the posterior summaries (src/mmseq.cpp:938-1395).
 
-PARITY STATUS: unpinned except sokal (see the header of mmseq_oracle.cpp).
+PARITY STATUS: see the header of mmseq_oracle.cpp — pinned against the reference's own sources
+(sokal.cc directly; mmseq.cpp/hitsio.cpp/uh.cpp through oracle/shim) except for GSL's arithmetic.
 """
 import ctypes as C
 import os

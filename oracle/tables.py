@@ -6,8 +6,9 @@ compared with the CUDA program cell by cell.
 
 Returned tables are lists of rows of strings, formatted as the reference's
 operator<< would (default precision 6 == "%g"; "nan"/"-nan"/"inf"/"-inf"; literal
-"NA", "0", "1" where the reference writes literals).  PARITY STATUS: unpinned (the
-reference cannot be built here; see mmseq_oracle.cpp)."""
+"NA", "0", "1" where the reference writes literals).  PARITY STATUS: pinned against the outputs of
+the reference's own main() (oracle/_ref/mmseq_ref, tests/golden/ref_small/) for every column that does
+not depend on the random stream; see mmseq_oracle.cpp."""
 import gzip
 
 import numpy as np

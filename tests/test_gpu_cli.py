@@ -73,6 +73,23 @@ def test_cli_outputs_match_oracle(tmp_path, fmt):
     assert ids == [want["identical_ids"][s] for s in keep] and np.allclose(itr, want["ident_trace"][keep], rtol=2e-5)
 
 
+def test_cli_matches_reference_run(tmp_path):
+    """The host program on the GPU against the outputs of the REFERENCE's own main() (unmodified
+    sources + oracle/shim, tests/golden/ref_small): .k / .M byte for byte, every column that does not
+    depend on the random stream cell for cell, log_mu within Monte-Carlo standard error (north_star c)."""
+    from tests.ref_case import make_case
+    from tests.test_reference_run import GOLD, compare_with_reference
+    path = make_case(tmp_path, "text")
+    base = str(tmp_path / "ours")
+    r = subprocess.run([BIN, "-gibbs_iter", "4096", "-seed", "99", "-percentiles", "5,50,95", "-notraces", path, base],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    assert open(base + ".k").read() == open(os.path.join(GOLD, "ref.k")).read()
+    assert open(base + ".M").read() == open(os.path.join(GOLD, "ref.M")).read()
+    for kind, ext in (("mmseq", ".mmseq"), ("identical", ".identical.mmseq"), ("gene", ".gene.mmseq")):
+        compare_with_reference(tables.read_table(os.path.join(GOLD, "ref" + ext)), tables.read_table(base + ext), kind)
+
+
 def test_cli_debug_files_and_notraces(tmp_path):
     path = _make_hits(tmp_path, "text")
     base = str(tmp_path / "dbg")
