@@ -12,6 +12,14 @@ timeout 600 python bench.py --weights --no-cpu-baseline > gpurun_out/bench_weigh
 timeout 600 python bench.py --layout collapsed --no-cpu-baseline > gpurun_out/bench_collapsed.json 2>> gpurun_out/bench_ours.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:k_alloc_seg -s 5 -c 1 -o gpurun_out/prof_r01_k_alloc_seg python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu.log 2>&1
+# config 1 end to end: the reference's own main() (unmodified sources + oracle/shim) on the host cores vs the host program on the GPU
+python - <<'PY'
+from mmseq_b200 import synth
+synth.Synth(20260101 + 1, 1000, 100000).write_hits_fast("/tmp/c1.bin.hits", True)
+PY
+( /usr/bin/time -f "reference mmseq_ref wall %e s (threads $(nproc))" env OMP_NUM_THREADS=$(nproc) oracle/_ref/mmseq_ref /tmp/c1.bin.hits /tmp/c1_ref > /dev/null 2>/tmp/t_ref.txt; tail -1 /tmp/t_ref.txt ) > gpurun_out/c1_compare.txt 2>&1
+( /usr/bin/time -f "mmseq_b200 mmseq wall %e s (1 GPU)" mmseq_b200/bin/mmseq /tmp/c1.bin.hits /tmp/c1_ours > /dev/null 2>/tmp/t_ours.txt; grep -E "Gibbs:|EM:" /tmp/t_ours.txt; tail -1 /tmp/t_ours.txt ) >> gpurun_out/c1_compare.txt 2>&1
+cat gpurun_out/c1_compare.txt
 python - <<'PY'
 import json
 for f in ("reference","ours","weighted","collapsed"):
