@@ -63,8 +63,9 @@ typedef struct mmq_problem {
                              chain of the canonical order.  k != NULL only.       */
 } mmq_problem;
 
-/* Upload a shard (H2D), build the transcript-major transpose on the device
- * (replaces Mt = trans(M), src/mmseq.cpp:578, and Mrowsum/Mcolsum :582-589). */
+/* Upload a shard (H2D) and validate it on the device.  The transcript-major transpose
+ * (replaces Mt = trans(M), src/mmseq.cpp:578, and Mrowsum/Mcolsum :582-589) is built on the
+ * device by the first call that needs it (mmq_init_mu, mmq_em, a TRANSPOSED sweep). */
 int mmq_create(const mmq_problem* problem, int device, mmq_handle** out);
 void mmq_destroy(mmq_handle* h);
 /* Message of the last failure on h (h may be NULL: failure of mmq_create). */

@@ -17,8 +17,8 @@ python - <<'PY'
 from mmseq_b200 import synth
 synth.Synth(20260101 + 1, 1000, 100000).write_hits_fast("/tmp/c1.bin.hits", True)
 PY
-( /usr/bin/time -f "reference mmseq_ref wall %e s (threads $(nproc))" env OMP_NUM_THREADS=$(nproc) oracle/_ref/mmseq_ref /tmp/c1.bin.hits /tmp/c1_ref > /dev/null 2>/tmp/t_ref.txt; tail -1 /tmp/t_ref.txt ) > gpurun_out/c1_compare.txt 2>&1
-( /usr/bin/time -f "mmseq_b200 mmseq wall %e s (1 GPU)" mmseq_b200/bin/mmseq /tmp/c1.bin.hits /tmp/c1_ours > /dev/null 2>/tmp/t_ours.txt; grep -E "Gibbs:|EM:" /tmp/t_ours.txt; tail -1 /tmp/t_ours.txt ) >> gpurun_out/c1_compare.txt 2>&1
+( s=$(date +%s.%N); OMP_NUM_THREADS=$(nproc) oracle/_ref/mmseq_ref /tmp/c1.bin.hits /tmp/c1_ref > /dev/null 2>&1; e=$(date +%s.%N); echo "reference mmseq_ref (unmodified sources + oracle/shim) wall $(python -c "print(round($e - $s, 2))") s on $(nproc) threads" ) > gpurun_out/c1_compare.txt 2>&1
+( s=$(date +%s.%N); mmseq_b200/bin/mmseq /tmp/c1.bin.hits /tmp/c1_ours > /dev/null 2>/tmp/t_ours.txt; e=$(date +%s.%N); grep -E "Gibbs:|EM:" /tmp/t_ours.txt; echo "mmseq_b200 mmseq wall $(python -c "print(round($e - $s, 2))") s on 1 GPU" ) >> gpurun_out/c1_compare.txt 2>&1
 cat gpurun_out/c1_compare.txt
 python - <<'PY'
 import json
