@@ -41,7 +41,7 @@
 #define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
 #define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
 #define MMQ_SMALL_K 8 /* classes with 2..MMQ_SMALL_K fragments: categorical draws instead of binomials */
-#define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per PAIR of classes */
+#define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per QUAD of classes (one 32-bit word each) */
 
 /* ------------------------------------------------------------------ bits */
 
@@ -127,6 +127,19 @@ MMQ_HD double mmq_uniform(mmq_rng* g) {
   g->left -= 1;
   uint64_t j = (((uint64_t)hi << 32) | (uint64_t)lo) >> 12;
   return ((double)j + 0.5) * 2.220446049250313080847263336181640625e-16; /* 2^-52 */
+}
+
+/* Uniform on (0,1) from ONE 32-bit word: (w + 1/2) * 2^-32.  Used by the k == 1 categorical
+ * draw only: 2^-32 is the granularity of gsl_rng_uniform on mt19937, i.e. of every draw the
+ * reference's gsl_ran_multinomial makes (src/mmseq.cpp:872), and it lets one Philox block serve
+ * four classes.  All three steps are exact, so host and device agree bit for bit. */
+MMQ_HD double mmq_uniform32(uint32_t w) {
+#if defined(__CUDA_ARCH__)
+  /* the same number without a conversion instruction: (1 + w 2^-32) - 1 + 2^-33, every step exact */
+  return (__hiloint2double((int)(0x3ff00000u | (w >> 12)), (int)(w << 20)) - 1.0) + 1.16415321826934814453125e-10;
+#else
+  return ((double)w + 0.5) * 2.3283064365386962890625e-10; /* 2^-32 */
+#endif
 }
 
 /* ------------------------------------------------------- log / exp kernels */
@@ -376,7 +389,7 @@ MMQ_HD int64_t mmq_binomial(mmq_rng* g, int64_t n, double p) {
  *         weight when weights are present); read twice, never written
  *   x[j]  out: number of fragments given to member j; sum_j x[j] == k
  * d == 1 consumes no random numbers (x = k).  k == 1 is one categorical draw
- * (one uniform: chosen = first j with u * sum_p < p_0 + ... + p_j); 2 <= k <= MMQ_SMALL_K is k
+ * (one 32-bit uniform of the CAT stream: chosen = first j with u * sum_p < p_0 + ... + p_j); 2 <= k <= MMQ_SMALL_K is k
  * such draws from the class's own stream.  k > 1 is gsl_ran_multinomial's chain of conditional
  * binomials x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)).
  * The arithmetic order (left-to-right sums) is part of the contract: the CPU
@@ -399,12 +412,13 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
   }
   mmq_rng g;
   if (k == 1) {
-    /* one categorical draw needs one uniform; a Philox block holds two, so classes
-     * 2c and 2c+1 share block c of the CAT stream (first / second uniform).  A
-     * kernel thread that owns two consecutive classes runs Philox once. */
-    mmq_rng_init(&g, seed, MMQ_STREAM_CAT, class_id >> 1, sweep);
-    double u = mmq_uniform(&g);
-    if (class_id & 1) u = mmq_uniform(&g);
+    /* one categorical draw needs one uniform of 32 bits; a Philox block holds four words, so
+     * classes 4c .. 4c+3 share block c of the CAT stream (word class_id & 3).  A kernel thread
+     * that owns four consecutive classes runs Philox once. */
+    uint32_t wd[4] = {(uint32_t)(class_id >> 2), (uint32_t)(class_id >> 34), sweep, 0u};
+    mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
+    const uint32_t sel = (uint32_t)(class_id & 3);
+    const double u = mmq_uniform32(sel == 0 ? wd[0] : sel == 1 ? wd[1] : sel == 2 ? wd[2] : wd[3]);
     const double target = u * norm;
     double acc = 0.0;
     int chosen = -1;

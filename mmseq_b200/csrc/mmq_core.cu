@@ -417,7 +417,7 @@ __device__ __forceinline__ void cat_draw2(const int32_t* ca, const float* wa, in
  *     copy (cp.async.bulk, 16-byte aligned, completion on a per-warp mbarrier) into the
  *     other half of the warp's shared-memory double buffer,
  *   - chunk i is processed from shared memory: every lane gathers mu for its two classes,
- *     draws both with ONE Philox block (classes 2c, 2c+1 share block c of the CAT stream)
+ *     draws both from ONE Philox block (classes 4c .. 4c+3 share block c of the CAT stream)
  *     and the chosen columns are added to counts[], aggregated across the warp first.
  * Chunks whose segment exceeds the buffer are read straight from global memory. */
 template <bool HAS_W, int SLAB>
@@ -499,18 +499,18 @@ k_alloc_cat(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col
 
     /* uniforms of this lane's two classes (independent of the data in flight) */
     const uint64_t ca = (uint64_t)(class_id_base + chunk * MMQ_CAT_ROWS + 2 * lane);
-    uint32_t wd[4] = {(uint32_t)(ca >> 1), (uint32_t)(ca >> 33), sweep, 0u};
+    uint32_t wd[4] = {(uint32_t)(ca >> 2), (uint32_t)(ca >> 34), sweep, 0u};
     mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
-    double ua, ub;
-    if ((ca & 1) == 0) { /* warp-uniform: parity of class_id_base */
-      ua = cat_u52(wd[0], wd[1]);
-      ub = cat_u52(wd[2], wd[3]);
-    } else {
-      ua = cat_u52(wd[2], wd[3]);
+    const uint32_t sa = (uint32_t)(ca & 3); /* word of class a in block ca >> 2; class b takes the next one */
+    const double ua = mmq_uniform32(sa == 0 ? wd[0] : sa == 1 ? wd[1] : sa == 2 ? wd[2] : wd[3]);
+    double ub;
+    if (sa != 3) {
+      ub = mmq_uniform32(sa == 0 ? wd[1] : sa == 1 ? wd[2] : wd[3]);
+    } else { /* odd class_id_base only: class b opens the next block */
       const uint64_t cb = ca + 1;
-      uint32_t w2[4] = {(uint32_t)(cb >> 1), (uint32_t)(cb >> 33), sweep, 0u};
+      uint32_t w2[4] = {(uint32_t)(cb >> 2), (uint32_t)(cb >> 34), sweep, 0u};
       mmq_philox4x32_10(w2, seed, MMQ_STREAM_CAT);
-      ub = cat_u52(w2[0], w2[1]);
+      ub = mmq_uniform32(w2[0]);
     }
     const int da = cur.ob - cur.oa, db = cur.oe - cur.ob;
     int32_t ca_col, cb_col;

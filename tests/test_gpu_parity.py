@@ -76,7 +76,7 @@ def test_sweep_bit_exact_vs_cpu_replay(small_problem, small_problem_pf, layout):
 @pytest.mark.parametrize("cid_base", [0, 7])
 def test_categorical_fast_path_edges(weighted, cid_base):
     """k == 1 kernel: ragged tail (m % 64 != 0), rows longer than the warp slab, singletons,
-    odd class-id base (pairs straddle lanes), zero and tiny mu — against the CPU replay and
+    class-id base that is not a multiple of 4 (Philox quads straddle lanes), zero and tiny mu — against the CPU replay and
     against the general kernel."""
     rng = np.random.default_rng(5)
     n = 4000
@@ -103,7 +103,7 @@ def test_categorical_fast_path_edges(weighted, cid_base):
 
 
 @pytest.mark.parametrize("weighted", [False, True])
-@pytest.mark.parametrize("cid_base", [0, 5])
+@pytest.mark.parametrize("cid_base", [0, 5, 2, 7])
 def test_by_length_layout_segment_kernel(small_synth, weighted, cid_base):
     """The loader's by-length layout: runs of equal class size, singletons skipped, no row
     pointers read — same integers and the same chain as the CPU replay and as the other kernels."""
