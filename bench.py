@@ -339,7 +339,7 @@ def main():
     b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S, args.layout)
     alloc_ms_avg = alloc_ms / max(alloc_n, 1)
     achieved = b_alloc / (alloc_ms_avg * 1e-3) / 1e9 if alloc_n else None
-    kernel_name = "k_alloc_seg" if (args.layout == "perfragment" and not args.transposed) else ("k_alloc_cat" if h.k is None and not args.transposed else "k_alloc")
+    kernel_name = "k_alloc_seg4" if (args.layout == "perfragment" and not args.transposed) else ("k_alloc_cat" if h.k is None and not args.transposed else "k_alloc")
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.fragments == N_C2 and args.transcripts == T_C2 and not args.weights:
