@@ -188,7 +188,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": "allocations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "oracle port of src/mmseq.cpp:851-918 (MT19937 per OpenMP thread, GSL-style samplers, dense per-thread "
-                "partials); the reference itself needs Boost+GSL and cannot be built in this image",
+                "partials); the reference's own main() builds here only against the stand-in Boost/GSL of oracle/shim and needs minutes per sweep at this size (DESIGN.md section 9)",
     }
     print(json.dumps(line), flush=True)
 
@@ -290,8 +290,12 @@ def main():
     ms = ev0.elapsed_time(ev1)
     alloc_ms, alloc_n, gamma_ms, gamma_n = H.kernel_times()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pr = [None] * world   # average kernel times of every rank: shows which rank the others wait for
+        dist.all_gather_object(pr, [round(alloc_ms / max(alloc_n, 1), 5), round(gamma_ms / max(gamma_n, 1), 5), round(ms / K, 4)])
+        per_rank = {"alloc_ms": [p[0] for p in pr], "gamma_ms": [p[1] for p in pr], "step_ms": [p[2] for p in pr]}
     ms_max = float(t.item())
     sweeps_per_s = K * S / (ms_max / 1000.0)
     m_total = h.m * world  # every rank holds fragments_per_gpu rows (weak scaling)
@@ -352,6 +356,8 @@ def main():
                 "share_of_step": alloc_ms / ms if ms > 0 else None,
                 "gamma_avg_launch_ms": gamma_ms / max(gamma_n, 1),
                 "sweep_bytes": int(b_sweep), "sweep_gbs": b_sweep * sweeps_per_s / 1e9}
+    if per_rank:
+        roofline["per_rank"] = per_rank
 
     line = {
         "metric": "gibbs_hit_class_allocations_per_s", "value": value, "unit": "allocations/s",

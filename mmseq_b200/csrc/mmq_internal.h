@@ -99,6 +99,7 @@ struct mmq_handle {
   void* p2p_opened[MMQ_P2P_MAX] = {}; /* cudaIpcOpenMemHandle mappings to close */
   int p2p_n = 0, p2p_rank = 0;
   int32_t p2p_epoch = 0;
+  unsigned long long* p2p_dbg = nullptr; /* MMQ_P2P_TRACE=1: wait-time accumulator, printed by mmq_destroy */
   int32_t* counts_own = nullptr; /* the single-GPU counts buffer (counts points into p2p_buf when attached) */
 
   /* CUDA graph of MMQ_GRAPH_SWEEPS consecutive sweeps; the sweep counter is read from
