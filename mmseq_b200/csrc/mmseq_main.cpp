@@ -111,17 +111,71 @@ struct GzText {
   ~GzText() { flush(); if (f) gzclose(f); }
 };
 
-/* one (rows x L) trace as the reference writes it: ids each followed by a space, then L lines */
+/* "%g" text of one trace line range -> one complete gzip member.  A gzip file is a sequence of
+ * members (RFC 1952 2.2); zlib's gzread, gzip(1), R's gzfile and Boost's gzip_decompressor all
+ * read the concatenation as one stream, so the members can be produced in parallel. */
+static void gz_member(const string& text, vector<unsigned char>& out) {
+  z_stream zs;
+  memset(&zs, 0, sizeof zs);
+  static const int level = [] { const char* e = getenv("MMQ_GZIP_LEVEL"); return e ? atoi(e) : Z_DEFAULT_COMPRESSION; }(); /* the reference: zlib default */
+  if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("Error: deflateInit2 failed.");
+  out.resize(deflateBound(&zs, (uLong)text.size()) + 64);
+  zs.next_in = (Bytef*)text.data();
+  zs.avail_in = (uInt)text.size();
+  zs.next_out = out.data();
+  zs.avail_out = (uInt)out.size();
+  if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die("Error: deflate failed.");
+  out.resize(zs.total_out);
+  deflateEnd(&zs);
+}
+
+/* one (rows x L) trace as the reference writes it (src/mmseq.cpp:1033-1108): ids each followed by a
+ * space, then L lines of values.  Formatting and compression run on all host threads, a block of
+ * lines per thread and round; the members are written in order. */
 static void write_trace_gz(const string& path, const vector<string>& ids, const vector<char>& keep, const double* tr, int L) {
-  GzText g(path);
+  FILE* f = fopen(path.c_str(), "wb");
+  if (!f) die("Error: cannot open " + path + " for writing.");
+  vector<size_t> rows;
   for (size_t r = 0; r < ids.size(); ++r)
-    if (keep.empty() || keep[r]) { g.put(ids[r]); g.put(" "); }
-  g.put("\n");
-  for (int i = 0; i < L; ++i) {
-    for (size_t r = 0; r < ids.size(); ++r)
-      if (keep.empty() || keep[r]) { g.put(tr[r * (size_t)L + i]); g.put(" "); }
-    g.put("\n");
+    if (keep.empty() || keep[r]) rows.push_back(r);
+  {
+    string head;
+    for (size_t r : rows) { head += ids[r]; head += ' '; }
+    head += '\n';
+    vector<unsigned char> z;
+    gz_member(head, z);
+    fwrite(z.data(), 1, z.size(), f);
   }
+  const int T = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+  /* lines per block: every thread gets one, at most about 4 MB of text each, at least one line */
+  const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)(L + T - 1) / (size_t)T, (4u << 20) / (rows.size() * 12 + 1)));
+  vector<vector<unsigned char>> z((size_t)T);
+  for (int base = 0; base < L; base += T * B) {
+    vector<std::thread> th;
+    for (int t = 0; t < T; ++t) {
+      const int i0 = base + t * B, i1 = std::min(L, i0 + B);
+      z[(size_t)t].clear();
+      if (i0 >= i1) continue;
+      th.emplace_back([&, t, i0, i1] {
+        string text;
+        text.reserve((size_t)(i1 - i0) * (rows.size() * 12 + 1));
+        char tmp[40];
+        for (int i = i0; i < i1; ++i) {
+          for (size_t r : rows) {
+            const int k = snprintf(tmp, sizeof tmp, "%g", tr[r * (size_t)L + (size_t)i]);
+            text.append(tmp, (size_t)k);
+            text += ' ';
+          }
+          text += '\n';
+        }
+        gz_member(text, z[(size_t)t]);
+      });
+    }
+    for (auto& x : th) x.join();
+    for (int t = 0; t < T; ++t)
+      if (!z[(size_t)t].empty()) fwrite(z[(size_t)t].data(), 1, z[(size_t)t].size(), f);
+  }
+  if (fclose(f) != 0) die("Error: cannot write " + path + ".");
 }
 
 static void write_pcts(ostream& ofs, const double* v, size_t np, char last) {
@@ -137,7 +191,20 @@ struct Shard {
   mmq_handle* h = nullptr;
 };
 
+/* MMQ_TIMING=1: wall-clock of the host program's phases on stderr */
+static void phase(const char* name) {
+  static const bool on = getenv("MMQ_TIMING") != nullptr;
+  static auto t_start = chrono::steady_clock::now();
+  static auto t_last = t_start;
+  if (!on) return;
+  const auto now = chrono::steady_clock::now();
+  fprintf(stderr, "[mmseq timing] %-28s %8.3f s  (+%.3f)\n", name, chrono::duration<double>(now - t_start).count(),
+          chrono::duration<double>(now - t_last).count());
+  t_last = now;
+}
+
 int main(int argc, char** argv) {
+  phase("start");
   /* DEFAULT PARAMETER VALUES (src/mmseq.cpp:183-205) */
   double alpha = 0.1, beta = 0.1;
   int max_em_iter = 1000;
@@ -266,6 +333,7 @@ int main(int argc, char** argv) {
   const int64_t N = cls.N;
   const int64_t G = (int64_t)hdr.gene_names.size(), I = (int64_t)hdr.identical.size();
   const int L = trace_length;
+  phase("hits file loaded");
   cout << "Found " << n << " transcripts in " << m << " transcript combinations.\r" << endl;
   if (n == 0 || m == 0) die("Error: no mapped fragments in the hits file.");
 
@@ -354,6 +422,7 @@ int main(int argc, char** argv) {
   /* ---- unique hits of identical sets and genes (src/mmseq.cpp:643-680, src/uh.cpp) */
   vector<int32_t> identical_unique_hits((size_t)I, 0), gene_unique_hits((size_t)G, 0);
   {
+    phase("shards on the GPUs");
     cerr << "Counting unique hits to sets of identical transcripts...";
     vector<int32_t> set_of((size_t)n, -1);
     for (int64_t s = 0; s < I; ++s)
@@ -469,6 +538,7 @@ int main(int argc, char** argv) {
          << " hit-class allocations/s)" << endl;
   }
 
+  phase("EM + Gibbs");
   cout << "Amalgamating transcripts and calculating summary statistics..." << flush;
 
   /* ---- prior-simulated traces for isoforms without hits (src/mmseq.cpp:971-978), on the device */
@@ -605,6 +675,7 @@ int main(int argc, char** argv) {
     }
   }
 
+  phase("summaries");
   /* ---- trace dumps (:829-831, :911-917, :1033-1108) */
   if (!notraces) {
     vector<double> tr((size_t)n * (size_t)L);
@@ -633,6 +704,7 @@ int main(int argc, char** argv) {
     write_trace_gz(output_base + ".gene.trace_gibbs.gz", hdr.gene_names, gkeep, gene_trace.data(), L);
   }
 
+  phase("trace files");
   /* ---- closed forms for unobserved features and gene lengths (:1372-1395) */
   const double digalpha = mmq_host_digamma(alpha);
   const double sqrtpolygalpha = sqrt(mmq_host_trigamma(alpha));
@@ -743,6 +815,7 @@ int main(int argc, char** argv) {
   cout << "done." << endl;
   for (auto& S : shards) mmq_destroy(S.h);
 
+  phase("tables");
   cout << "Output files: " << endl
        << "  " << output_base << ".mmseq" << endl
        << "  " << output_base << ".identical.mmseq" << endl
