@@ -139,7 +139,7 @@ def physical_gpu_index(local):
     return local
 
 
-def algorithmic_bytes(h, n, weights, transposed, stride, layout):
+def algorithmic_bytes(h, n, weights, transposed, stride, layout, cls=None):
     """Compulsory HBM bytes of the implemented data flow ('Roofline'); every array
     once, L2-resident mu gathers and count reductions not counted.
       segment kernel (by-length k == 1 shards): 4 B column (+4 B weight) per CSR entry of the
@@ -149,7 +149,11 @@ def algorithmic_bytes(h, n, weights, transposed, stride, layout):
     m, nnz = h.m, h.nnz
     d = np.diff(h.row_ptr)
     per_entry = 4 + (4 if weights else 0)
-    if layout == "perfragment" and h.k is None and not transposed:
+    if cls and cls["in_use"] and not transposed:
+        # class plan (mmq_cls.cu): packed columns (4 B) + draws/slot number (2 B) + class id (4 B) per slot of the small
+        # set; row pointer, k, class id (8 + 4 + 8 B) per class and 4 B per entry of the sub-CSR left to k_alloc
+        alloc = 4 * cls["packed_slots"] + 6 * cls["class_slots"] + 20 * cls["rest_classes"] + 4 * cls["rest_nnz"]
+    elif layout == "perfragment" and h.k is None and not transposed:
         alloc = per_entry * int(d[d >= 2].sum())
     else:
         alloc = 8 * (m + 1) + per_entry * nnz + (4 * m if h.k is not None else 0)
@@ -256,6 +260,7 @@ def main():
             H.p2p_attach(hs, rank, world)
     H.init_mu()
     mu0 = H.get_mu()
+    cls = H.cls_stats() if h.k is not None else None
 
     K, W, S = args.steps, args.warmup, SWEEPS_PER_STEP
     L = K + W + 1
@@ -340,10 +345,12 @@ def main():
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
-    b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S, args.layout)
+    b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S, args.layout, cls)
     alloc_ms_avg = alloc_ms / max(alloc_n, 1)
     achieved = b_alloc / (alloc_ms_avg * 1e-3) / 1e9 if alloc_n else None
     kernel_name = "k_alloc_seg4" if (args.layout == "perfragment" and not args.transposed) else ("k_alloc_cat" if h.k is None and not args.transposed else "k_alloc")
+    if cls and cls["in_use"] and not args.transposed:
+        kernel_name = "k_alloc_cls"
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.fragments == N_C2 and args.transcripts == T_C2 and not args.weights:
@@ -358,6 +365,8 @@ def main():
                 "sweep_bytes": int(b_sweep), "sweep_gbs": b_sweep * sweeps_per_s / 1e9}
     if per_rank:
         roofline["per_rank"] = per_rank
+    if cls:
+        roofline["class_plan"] = cls
 
     line = {
         "metric": "gibbs_hit_class_allocations_per_s", "value": value, "unit": "allocations/s",

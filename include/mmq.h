@@ -139,6 +139,14 @@ int mmq_em(mmq_handle* h, int max_iter, double eps, int* iters_out, double* logl
 int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweeps, int stride,
               int trace_len, int flags);
 
+/* What the class plan of a collapsed shard (classes with counts k; built by mmq_create) holds:
+ * out[0] 1 if the plan is in use, out[1] classes of the small set (k <= 64 fragments: categorical
+ * draws, replaces the multinomial of src/mmseq.cpp:880 for those classes), out[2] packed column
+ * slots and out[3] class slots streamed per sweep for them, out[4] classes and out[5] CSR entries
+ * left to the general kernel (conditional-binomial chains).  Used by bench.py for the
+ * algorithmic-bytes figure. */
+int mmq_cls_stats(const mmq_handle* h, int64_t out[6]);
+
 /* Device time of the launches made under MMQ_GIBBS_TIME_KERNELS since the last
  * call (waits for the stream): total milliseconds and launch count of the
  * allocation kernel and of the Gamma kernel.  Any output may be NULL. */

@@ -40,7 +40,8 @@
 #define MMQ_STREAM_ALLOC 0x414c4c4fu /* per hit class, per sweep   */
 #define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
 #define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
-#define MMQ_SMALL_K 8 /* classes with 2..MMQ_SMALL_K fragments: categorical draws instead of binomials */
+#define MMQ_CAT_K 1024 /* classes with 2..MMQ_CAT_K fragments: categorical draws (four 32-bit uniforms per Philox block) instead of binomials */
+#define MMQ_CAT_GROUP 64 /* ... generated 64 at a time (16 blocks): the unit of work of the class-plan kernel */
 #define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per QUAD of classes (one 32-bit word each) */
 
 /* ------------------------------------------------------------------ bits */
@@ -384,13 +385,25 @@ MMQ_HD int64_t mmq_binomial(mmq_rng* g, int64_t n, double p) {
 
 /* ---------------------------------------------------- one hit class */
 
+/* How mmq_alloc_row accumulates into its output: plain arrays are zeroed and added to; an output
+ * that is itself a reduction (the kernels' counts[] adaptor) overloads these two. */
+template <typename XIt>
+MMQ_HD void mmq_x_zero(XIt x, int d) {
+  for (int j = 0; j < d; ++j) x[j] = 0;
+}
+template <typename XIt>
+MMQ_HD void mmq_x_add(XIt x, int j, int32_t v) {
+  x[j] = x[j] + v;
+}
+
+
 /* Allocate the k fragments of one hit class among its d member transcripts.
  *   p[j]  unnormalised probability of member j (mu[col_j], times the per-hit
  *         weight when weights are present); read twice, never written
  *   x[j]  out: number of fragments given to member j; sum_j x[j] == k
  * d == 1 consumes no random numbers (x = k).  k == 1 is one categorical draw
- * (one 32-bit uniform of the CAT stream: chosen = first j with u * sum_p < p_0 + ... + p_j); 2 <= k <= MMQ_SMALL_K is k
- * such draws from the class's own stream.  k > 1 is gsl_ran_multinomial's chain of conditional
+ * (one 32-bit uniform of the CAT stream: chosen = first j with u * sum_p < p_0 + ... + p_j); 2 <= k <= MMQ_CAT_K is k
+ * such draws from the class's own stream (32-bit uniforms, four per block).  Larger k is gsl_ran_multinomial's chain of conditional
  * binomials x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)).
  * The arithmetic order (left-to-right sums) is part of the contract: the CPU
  * replay and every kernel variant walk the row in the same order. */
@@ -432,27 +445,38 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
     return;
   }
   mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, class_id, sweep);
-  if (k <= MMQ_SMALL_K) {
-    /* few fragments: k independent categorical draws (one uniform each, no log/exp) — the
-     * same Multinomial(k; p) as the binomial chain below */
-    int ch[MMQ_SMALL_K];
-    for (int t = 0; t < MMQ_SMALL_K; ++t) {
-      ch[t] = -1;
-      if (t < (int)k) {
-        const double target = mmq_uniform(&g) * norm;
+  if (k <= MMQ_CAT_K) {
+    /* k independent categorical draws — the same Multinomial(k; p) as the binomial chain below,
+     * without log/exp and without a serial dependence between members.  Draw t uses word t & 3 of
+     * block t >> 2 of the class's own stream as one 32-bit uniform (the granularity of the k == 1
+     * draw), so a kernel thread runs Philox once per four fragments and the draws of a large class
+     * can be shared out between threads in groups of MMQ_CAT_GROUP (mmq_cls.cu). */
+    mmq_x_zero(x, d);
+    for (int t0 = 0; t0 < (int)k; t0 += MMQ_CAT_GROUP) {
+      const int cnt = ((int)k - t0 < MMQ_CAT_GROUP) ? (int)k - t0 : MMQ_CAT_GROUP;
+      int32_t ch[MMQ_CAT_GROUP];
+      uint32_t wd[4] = {0u, 0u, 0u, 0u};
+      for (int q = 0; q < cnt; ++q) {
+        const int t = t0 + q;
+        if ((t & 3) == 0) {
+          wd[0] = g.id_lo; wd[1] = g.id_hi; wd[2] = sweep; wd[3] = (uint32_t)(t >> 2);
+          mmq_philox4x32_10(wd, seed, MMQ_STREAM_ALLOC);
+        }
+        const int r = t & 3;
+        const double target = mmq_uniform32(r == 0 ? wd[0] : r == 1 ? wd[1] : r == 2 ? wd[2] : wd[3]) * norm;
         double acc = 0.0;
         int chosen = -1;
         for (int j = 0; j < d; ++j) {
           acc += p[j];
           if (chosen < 0 && target < acc) chosen = j;
         }
-        ch[t] = chosen < 0 ? last_pos : chosen;
+        ch[q] = chosen < 0 ? last_pos : chosen;
       }
-    }
-    for (int j = 0; j < d; ++j) {
-      int32_t v = 0;
-      for (int t = 0; t < MMQ_SMALL_K; ++t) v += (ch[t] == j) ? 1 : 0;
-      x[j] = v;
+      for (int j = 0; j < d; ++j) {
+        int32_t v = 0;
+        for (int q = 0; q < cnt; ++q) v += (ch[q] == j) ? 1 : 0;
+        mmq_x_add(x, j, v);
+      }
     }
     return;
   }

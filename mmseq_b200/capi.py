@@ -62,6 +62,7 @@ def _load():
         "mmq_gibbs": (i32, [vp, u32, i64, i64, i32, i32, i32]),
         "mmq_sweep_debug": (i32, [vp, u32, i64, i32, vp, vp, vp]),
         "mmq_kernel_times": (i32, [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl), C.POINTER(i64)]),
+        "mmq_cls_stats": (i32, [vp, C.POINTER(i64)]),
         "mmq_get_trace": (i32, [vp, vp]),
         "mmq_trace_len": (i32, [vp]),
         "mmq_set_groups": (i32, [vp, i32, i64, vp, vp, vp]),
@@ -94,7 +95,7 @@ def lib():
 EXPORTS = [
     "mmq_create", "mmq_destroy", "mmq_last_error", "mmq_set_stream", "mmq_get_stream", "mmq_synchronize",
     "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_p2p_export", "mmq_p2p_attach", "mmq_p2p_attach_local", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
-    "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_get_trace", "mmq_trace_len",
+    "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_cls_stats", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
     "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_version",
 ]
@@ -261,6 +262,12 @@ class Handle:
         a = C.c_double(); an = C.c_int64(); g = C.c_double(); gn = C.c_int64()
         self._check(lib().mmq_kernel_times(self._h, C.byref(a), C.byref(an), C.byref(g), C.byref(gn)), "mmq_kernel_times")
         return a.value, an.value, g.value, gn.value
+
+    def cls_stats(self):
+        """Class plan of a collapsed shard: dict(in_use, small_classes, packed_slots, class_slots, rest_classes, rest_nnz)."""
+        out = (C.c_int64 * 6)()
+        self._check(lib().mmq_cls_stats(self._h, out), "mmq_cls_stats")
+        return dict(zip(["in_use", "small_classes", "packed_slots", "class_slots", "rest_classes", "rest_nnz"], [int(v) for v in out]))
 
     def sweep_debug(self, seed, sweep, flags=MMQ_GIBBS_TRANSPOSED, want_x=True):
         x = np.zeros(self.nnz, np.int32) if (want_x and (flags & MMQ_GIBBS_TRANSPOSED)) else None

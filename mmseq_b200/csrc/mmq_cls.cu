@@ -1,0 +1,452 @@
+/* mmq_cls.cu — K2 for COLLAPSED shards (distinct hit classes with fragment counts k, the
+ * reference's own representation: src/mmseq.cpp:395-441 builds it, :862-891 allocates it).
+ *
+ * The general kernel (k_alloc, mmq_core.cu) gives every class to one lane and lets that lane
+ * run whatever mmq_alloc_row needs; with k between 1 and 10^5 and 2..30 members in one warp the
+ * lanes diverge and the sweep is an order of magnitude away from the memory roofline.  The
+ * plan below (built once in mmq_create) sorts the classes by what a sweep has to do for them:
+ *
+ *   d == 1              nothing: x = k is deterministic, summed once into seg_base[] (the Gamma
+ *                       kernel restarts counts[] from it);
+ *   k <= MMQ_CAT_K and  the "small" set: k categorical draws, four per Philox block
+ *   d <= MMQ_CLS_DMAX   (include/mmq_sampler.h).  Classes are ordered by (d, blocks) and packed
+ *                       in chunks of 32 — one class per lane, member-major inside the chunk
+ *                       (entry (j, lane) at chunk_base + 32 j + lane), so that every column load
+ *                       of a warp is one fully used 128-byte line and no row pointers, no
+ *                       shared-memory staging and no shuffles are needed.  A lane gathers its d
+ *                       mu once, keeps the running sums S_j in registers and, per draw, counts
+ *                       A_j += (u S_{d-1} < S_j); x_j = A_j - A_{j-1} (S is non-decreasing, so
+ *                       that is "first j with target < S_j").  All lanes of a warp have the same
+ *                       d and (almost always) the same number of blocks: no divergence;
+ *   the rest            (k > MMQ_CAT_K: conditional-binomial chain; or very long classes) a small
+ *                       sub-CSR handed to k_alloc on a second stream, concurrently.
+ *
+ * The integers are those of mmq_alloc_row on the same (seed, class id, sweep) — bit for bit
+ * (tests/test_gpu_parity.py) — because the order of the floating-point sums is the same.
+ *
+ * Algorithmic HBM bytes per sweep: 4 B per packed column slot + 5 B per class slot (k as one
+ * byte, low word of the class id) of the small set + the sub-CSR of the rest.
+ */
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "mmq_device.cuh"
+#include "mmq_internal.h"
+
+#define MMQ_CLS_DMAX 64  /* longer classes go to the general kernel */
+#define MMQ_CLS_DLO 8    /* class sizes 2..8: the 64-register instance (32 warps per SM) */
+#define MMQ_CLS_DREG 16  /* class sizes up to this are register-resident template instances */
+#define MMQ_CLS_WARPS 4
+#define MMQ_CLS_NQ 17    /* sort positions inside a run of equal d: 16 - blocks (k >= 2), then 16: k == 1 */
+
+struct mmq_cls_run {
+  int64_t e0;     /* pcol offset of the run's first chunk */
+  int32_t chunk0; /* first chunk of the run in the global numbering */
+  int32_t d;      /* class size */
+};
+
+/* Philox block b of a class's own ALLOC stream */
+__device__ __forceinline__ void cls_block(uint32_t (&wd)[4], uint32_t cid, uint32_t cid_hi, uint32_t sweep, uint32_t b, uint32_t seed) {
+  wd[0] = cid; wd[1] = cid_hi; wd[2] = sweep; wd[3] = b;
+  mmq_philox4x32_10(wd, seed, MMQ_STREAM_ALLOC);
+}
+/* the 32-bit word of a k == 1 class: word cid & 3 of the CAT stream's block cid >> 2 (shared by four classes) */
+__device__ __forceinline__ uint32_t cls_word1(uint32_t cid, uint32_t cid_hi, uint32_t sweep, uint32_t seed) {
+  uint32_t wd[4] = {(cid >> 2) | (cid_hi << 30), cid_hi >> 2, sweep, 0u};
+  mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
+  const uint32_t s = cid & 3u;
+  return s == 0 ? wd[0] : s == 1 ? wd[1] : s == 2 ? wd[2] : wd[3];
+}
+
+/* One chunk: 32 slots of compile-time class size D, everything in registers.  A slot is a class
+ * with its first block b0 and the number of draws kq <= 64 it makes (classes with more than 64
+ * fragments occupy several slots). */
+template <int D>
+__device__ __forceinline__ void cls_chunk(const int32_t* __restrict__ pc, int kq, uint32_t b0, uint32_t cid, uint32_t cid_hi,
+                                          const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
+                                          uint32_t sweep, int lane) {
+  /* the columns are not kept: the few that receive fragments are re-read (L1 hits) at the end,
+   * which leaves the registers to the running sums and buys resident warps */
+  double S[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) S[j] = mu[__ldg(pc + 32 * j)];
+#pragma unroll
+  for (int j = 1; j < D; ++j) S[j] = S[j - 1] + S[j];
+  const double norm = S[D - 1];
+  if (__all_sync(0xffffffffu, kq <= 1 && b0 == 0u)) { /* a warp of single-fragment classes: one draw, one increment */
+    const double target = mmq_uniform32(cls_word1(cid, cid_hi, sweep, seed)) * norm;
+    int chosen = D - 1;
+#pragma unroll
+    for (int j = 0; j < D - 1; ++j) chosen -= (target < S[j]) ? 1 : 0; /* S is non-decreasing: first j with target < S_j */
+    cat_red(counts, kq == 1 ? __ldg(pc + 32 * chosen) : -1, lane);
+    return;
+  }
+  int A[D - 1];
+#pragma unroll
+  for (int j = 0; j < D - 1; ++j) A[j] = 0;
+  const int nb = (kq + 3) >> 2;
+  const int nbmax = __reduce_max_sync(0xffffffffu, nb);
+  const bool is1 = kq == 1 && b0 == 0u; /* the class has exactly one fragment: CAT stream */
+#pragma unroll 1
+  for (int b = 0; b < nbmax; ++b) {
+    if (b < nb) {
+      uint32_t wd[4];
+      if (is1) {
+        wd[0] = cls_word1(cid, cid_hi, sweep, seed);
+        wd[1] = wd[2] = wd[3] = 0u;
+      } else {
+        cls_block(wd, cid, cid_hi, sweep, b0 + (uint32_t)b, seed);
+      }
+      const int nd = kq - 4 * b; /* draws of this block: min(4, nd) */
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const double target = mmq_uniform32(wd[r]) * norm;
+        const bool live = r < nd;
+#pragma unroll
+        for (int j = 0; j < D - 1; ++j) A[j] += (live && target < S[j]) ? 1 : 0;
+      }
+    }
+  }
+  int prev = 0;
+#pragma unroll
+  for (int j = 0; j < D - 1; ++j) {
+    const int x = A[j] - prev;
+    prev = A[j];
+    if (x) atomicAdd(counts + __ldg(pc + 32 * j), x);
+  }
+  if (kq - prev) atomicAdd(counts + __ldg(pc + 32 * (D - 1)), kq - prev);
+}
+
+/* any class size: members are re-read (L1/L2 hits) for every block of four draws */
+__device__ __noinline__ void cls_chunk_any(const int32_t* __restrict__ pc, int D, int kq, uint32_t b0, uint32_t cid, uint32_t cid_hi,
+                                           const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
+                                           uint32_t sweep) {
+  double norm = 0.0;
+  for (int j = 0; j < D; ++j) norm += mu[pc[32 * j]];
+  const int nb = (kq + 3) >> 2;
+  const bool is1 = kq == 1 && b0 == 0u;
+  for (int b = 0; b < nb; ++b) {
+    uint32_t wd[4];
+    if (is1) {
+      wd[0] = cls_word1(cid, cid_hi, sweep, seed);
+      wd[1] = wd[2] = wd[3] = 0u;
+    } else {
+      cls_block(wd, cid, cid_hi, sweep, b0 + (uint32_t)b, seed);
+    }
+    const int nd = min(4, kq - 4 * b);
+    double t[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) t[r] = mmq_uniform32(wd[r]) * norm;
+    double s = 0.0;
+    int prev = 0;
+    for (int j = 0; j < D; ++j) {
+      const int32_t cj = pc[32 * j];
+      s += mu[cj];
+      int a = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) a += (r < nd && t[r] < s) ? 1 : 0;
+      if (j == D - 1) a = nd;
+      if (a - prev) atomicAdd(counts + cj, a - prev);
+      prev = a;
+    }
+  }
+}
+
+/* LO: the instance for class sizes 2..MMQ_CLS_DLO (chunks [0, total_chunks) are all such runs);
+ * otherwise sizes above MMQ_CLS_DLO. */
+template <bool LO, int MINB>
+__global__ void __launch_bounds__(MMQ_CLS_WARPS * 32, MINB)
+k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol,
+            const uint16_t* __restrict__ pk, const uint32_t* __restrict__ pcid, uint32_t cid_hi, const double* __restrict__ mu,
+            int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base; /* CUDA-graph replays: the sweep counter lives on the device */
+  __shared__ mmq_cls_run s_run[MMQ_CLS_DMAX];
+  for (int i = threadIdx.x; i < nruns; i += blockDim.x) s_run[i] = runs[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * MMQ_CLS_WARPS;
+  int ri = 0;
+  for (int chunk = chunk_begin + blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5); chunk < chunk_end; chunk += nwarps) {
+    while (ri + 1 < nruns && chunk >= s_run[ri + 1].chunk0) ++ri; /* warp-uniform */
+    const int D = s_run[ri].d;
+    const int32_t* pc = pcol + s_run[ri].e0 + (int64_t)(chunk - s_run[ri].chunk0) * (32 * D) + lane;
+    const uint32_t meta = pk[(int64_t)chunk * 32 + lane]; /* draws of the slot | slot number within its class << 8 */
+    const int kq = (int)(meta & 0xffu);
+    const uint32_t b0 = (meta >> 8) * (MMQ_CAT_GROUP / 4);
+    const uint32_t cid = pcid[(int64_t)chunk * 32 + lane];
+#define MMQ_CLS_CASE(DD) case DD: cls_chunk<DD>(pc, kq, b0, cid, cid_hi, mu, counts, seed, sweep, lane); break;
+    if (LO) {
+      switch (D) {
+        MMQ_CLS_CASE(2) MMQ_CLS_CASE(3) MMQ_CLS_CASE(4) MMQ_CLS_CASE(5) MMQ_CLS_CASE(6) MMQ_CLS_CASE(7) MMQ_CLS_CASE(8)
+        default: break;
+      }
+    } else {
+      switch (D) {
+        MMQ_CLS_CASE(9) MMQ_CLS_CASE(10) MMQ_CLS_CASE(11) MMQ_CLS_CASE(12) MMQ_CLS_CASE(13) MMQ_CLS_CASE(14)
+        MMQ_CLS_CASE(15) MMQ_CLS_CASE(16)
+        default: cls_chunk_any(pc, D, kq, b0, cid, cid_hi, mu, counts, seed, sweep); break;
+      }
+    }
+#undef MMQ_CLS_CASE
+  }
+}
+
+__global__ void k_cls_singletons(const int32_t* __restrict__ col1, const int32_t* __restrict__ k1, int64_t count,
+                                 int32_t* __restrict__ base) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(base + col1[i], k1[i]);
+}
+
+/* ------------------------------------------------------------------ host */
+
+template <typename F>
+static void cls_parallel_for(int64_t count, F&& f) {
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 16u), count / 65536));
+  if (nt <= 1) { f((int64_t)0, count); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { f(count * t / nt, count * (t + 1) / nt); });
+  for (auto& x : th) x.join();
+}
+
+template <typename T>
+static int cls_upload(mmq_handle* h, T** dst, const std::vector<T>& v) {
+  int rc = mmq_dev_alloc(h, (void**)dst, sizeof(T) * std::max<size_t>(v.size(), 1));
+  if (rc) return rc;
+  if (!v.empty()) MMQ_CUDA(h, cudaMemcpyAsync(*dst, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice, h->stream));
+  return MMQ_OK;
+}
+
+int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
+  h->cls_ready = false;
+  static const bool off = [] { const char* e = getenv("MMQ_CLS_OFF"); return e && atoi(e) != 0; }();
+  if (off || !h->has_k || h->has_w || h->m == 0) return MMQ_OK;
+  const int64_t m = h->m;
+  const int64_t* rp = p->row_ptr;
+  const int32_t* col = p->col;
+  const int32_t* kk = p->k;
+  auto cid_of = [&](int64_t i) -> uint64_t { return (uint64_t)(p->class_id ? p->class_id[i] : p->class_id_base + i); };
+  const uint32_t cid_hi = (uint32_t)(cid_of(0) >> 32);
+
+  /* classify.  Slots of the small set are keyed (d, q): q = 16 - blocks for classes with k >= 2 (a run of
+   * equal d starts with its most expensive slots), q = 16 for single-fragment classes (whole warps of
+   * them take the one-draw path). */
+  const int NKEY = (MMQ_CLS_DMAX + 1) * MMQ_CLS_NQ;
+  std::vector<int64_t> key_count(NKEY + 1, 0);
+  std::vector<int8_t> kind(m); /* 0 small, 1 singleton / empty, 2 rest */
+  int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small_classes = 0;
+  bool ok = true;
+  for (int64_t i = 0; i < m; ++i) {
+    const int64_t d = rp[i + 1] - rp[i];
+    const int64_t kv = kk[i];
+    if ((uint32_t)(cid_of(i) >> 32) != cid_hi) ok = false;
+    if (kv < 0) ok = false;
+    if (d == 1 || kv == 0) { kind[i] = 1; ++n_single; } /* k == 0: nothing to allocate */
+    else if (kv <= MMQ_CAT_K && d <= MMQ_CLS_DMAX) {
+      kind[i] = 0;
+      ++small_classes;
+      if (kv == 1) ++key_count[d * MMQ_CLS_NQ + 16];
+      else {
+        const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
+        key_count[d * MMQ_CLS_NQ + 0] += full; /* 16 blocks */
+        if (tail) ++key_count[d * MMQ_CLS_NQ + (16 - (int)((tail + 3) >> 2))];
+      }
+    } else { kind[i] = 2; ++n_rest; nnz_rest += d; }
+  }
+  if (!ok) return MMQ_OK; /* class ids spread over several 2^32 blocks: the general kernel handles it */
+
+  /* runs of equal d, chunks of 32 slots */
+  std::vector<mmq_cls_run> runs;
+  std::vector<int64_t> key_slot(NKEY + 1, 0); /* first slot (global numbering, 32 per chunk) of each key */
+  int64_t chunks = 0, packed = 0, chunks_lo = 0;
+  for (int d = 2; d <= MMQ_CLS_DMAX; ++d) {
+    int64_t cnt = 0;
+    for (int q = 0; q < MMQ_CLS_NQ; ++q) { key_slot[d * MMQ_CLS_NQ + q] = chunks * 32 + cnt; cnt += key_count[d * MMQ_CLS_NQ + q]; }
+    if (cnt == 0) continue;
+    mmq_cls_run r;
+    r.e0 = packed; r.chunk0 = (int32_t)chunks; r.d = d;
+    runs.push_back(r);
+    const int64_t nch = (cnt + 31) / 32;
+    chunks += nch;
+    packed += nch * 32 * d;
+    if (d <= MMQ_CLS_DLO) chunks_lo = chunks;
+    if (chunks > 0x7fff0000ll) return MMQ_OK;
+  }
+  std::vector<int32_t> run_of_d(MMQ_CLS_DMAX + 1, -1);
+  for (size_t r = 0; r < runs.size(); ++r) run_of_d[runs[r].d] = (int32_t)r;
+
+  /* first slot of every small class within each of its (at most two) keys; stable within a key: the
+   * caller's order (e.g. cost-sorted) is kept */
+  std::vector<int64_t> slot_full(m), slot_tail(m);
+  {
+    std::vector<int64_t> next(key_slot);
+    for (int64_t i = 0; i < m; ++i) {
+      if (kind[i] != 0) continue;
+      const int d = (int)(rp[i + 1] - rp[i]);
+      const int64_t kv = kk[i];
+      if (kv == 1) { slot_tail[i] = next[d * MMQ_CLS_NQ + 16]++; continue; }
+      const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
+      slot_full[i] = next[d * MMQ_CLS_NQ + 0];
+      next[d * MMQ_CLS_NQ + 0] += full;
+      if (tail) slot_tail[i] = next[d * MMQ_CLS_NQ + (16 - (int)((tail + 3) >> 2))]++;
+    }
+  }
+  std::vector<int32_t> pcol((size_t)packed, (int32_t)h->n); /* padding: the sentinel column (mu[n] == 0) */
+  std::vector<uint16_t> pk((size_t)chunks * 32, 0);
+  std::vector<uint32_t> pcid((size_t)chunks * 32, 0u);
+  cls_parallel_for(m, [&](int64_t a, int64_t b) {
+    for (int64_t i = a; i < b; ++i) {
+      if (kind[i] != 0) continue;
+      const int d = (int)(rp[i + 1] - rp[i]);
+      const mmq_cls_run& r = runs[run_of_d[d]];
+      const int32_t* src = col + rp[i];
+      const uint32_t cid = (uint32_t)cid_of(i);
+      auto put = [&](int64_t s, int draws, int slot_no) {
+        const int64_t ch = s >> 5;
+        int32_t* dst = pcol.data() + r.e0 + (ch - r.chunk0) * 32 * d + (s & 31);
+        for (int j = 0; j < d; ++j) dst[32 * j] = src[j];
+        pk[s] = (uint16_t)(draws | (slot_no << 8));
+        pcid[s] = cid;
+      };
+      const int64_t kv = kk[i];
+      if (kv == 1) { put(slot_tail[i], 1, 0); continue; }
+      const int full = (int)(kv / MMQ_CAT_GROUP), tail = (int)(kv % MMQ_CAT_GROUP);
+      for (int q = 0; q < full; ++q) put(slot_full[i] + q, MMQ_CAT_GROUP, q);
+      if (tail) put(slot_tail[i], tail, full);
+    }
+  });
+
+  /* the rest: a sub-CSR for the general kernel, longest chains first, ONE class per warp tile (a
+   * chain of binomials is serial: what matters is when the slowest warp ends, not lane use) */
+  std::vector<int64_t> rest;
+  rest.reserve((size_t)n_rest);
+  for (int64_t i = 0; i < m; ++i)
+    if (kind[i] == 2) rest.push_back(i);
+  std::stable_sort(rest.begin(), rest.end(), [&](int64_t a, int64_t b) { return rp[a + 1] - rp[a] > rp[b + 1] - rp[b]; });
+  std::vector<int64_t> o_rp((size_t)n_rest + 1, 0), o_cid((size_t)n_rest), o_tiles((size_t)n_rest + 1);
+  std::vector<int32_t> o_col((size_t)nnz_rest + 4, 0), o_k((size_t)n_rest);
+  for (int64_t q = 0; q < n_rest; ++q) {
+    const int64_t i = rest[q];
+    const int64_t d = rp[i + 1] - rp[i];
+    memcpy(o_col.data() + o_rp[q], col + rp[i], sizeof(int32_t) * (size_t)d);
+    o_rp[q + 1] = o_rp[q] + d;
+    o_k[q] = kk[i];
+    o_cid[q] = (int64_t)cid_of(i);
+    o_tiles[q] = q;
+  }
+  o_tiles[n_rest] = n_rest;
+
+  /* singletons: constant counts */
+  std::vector<int32_t> s_col, s_k;
+  s_col.reserve((size_t)n_single); s_k.reserve((size_t)n_single);
+  for (int64_t i = 0; i < m; ++i)
+    if (kind[i] == 1 && kk[i] > 0) { s_col.push_back(col[rp[i]]); s_k.push_back(kk[i]); }
+
+  int rc;
+  if ((rc = cls_upload(h, &h->cls_pcol, pcol))) return rc;
+  if ((rc = cls_upload(h, &h->cls_pk, pk))) return rc;
+  if ((rc = cls_upload(h, &h->cls_pcid, pcid))) return rc;
+  if ((rc = cls_upload(h, (mmq_cls_run**)&h->cls_runs, runs))) return rc;
+  if (n_rest > 0) {
+    if ((rc = cls_upload(h, &h->cls_o_rp, o_rp))) return rc;
+    if ((rc = cls_upload(h, &h->cls_o_col, o_col))) return rc;
+    if ((rc = cls_upload(h, &h->cls_o_k, o_k))) return rc;
+    if ((rc = cls_upload(h, &h->cls_o_cid, o_cid))) return rc;
+    if ((rc = cls_upload(h, &h->cls_o_tiles, o_tiles))) return rc;
+  }
+  if (!s_col.empty()) {
+    int32_t *d_col = nullptr, *d_k = nullptr;
+    if ((rc = cls_upload(h, &d_col, s_col))) return rc;
+    if ((rc = cls_upload(h, &d_k, s_k))) return rc;
+    if ((rc = mmq_dev_alloc(h, (void**)&h->seg_base, sizeof(int32_t) * (size_t)h->n))) return rc;
+    MMQ_CUDA(h, cudaMemsetAsync(h->seg_base, 0, sizeof(int32_t) * (size_t)h->n, h->stream));
+    k_cls_singletons<<<mmq_grid_for((int64_t)s_col.size(), 256, h->num_sms * 8), 256, 0, h->stream>>>(d_col, d_k, (int64_t)s_col.size(), h->seg_base);
+    MMQ_LAUNCHED(h);
+    MMQ_CUDA(h, cudaMemcpyAsync(h->counts, h->seg_base, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+    h->seg_base_in_counts = true;
+    MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+    mmq_dev_free(h, d_col);
+    mmq_dev_free(h, d_k);
+  }
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream)); /* the vectors are host temporaries */
+  if (!h->stream2) {
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
+  }
+  h->cls_nruns = (int)runs.size();
+  h->cls_chunks = chunks;
+  h->cls_chunks_lo = chunks_lo;
+  h->cls_cid_hi = cid_hi;
+  h->cls_small = small_classes;
+  h->cls_rest = n_rest;
+  h->cls_rest_nnz = nnz_rest;
+  h->cls_rest_tiles = n_rest;
+  h->cls_packed = packed;
+  h->cls_ready = true;
+  return MMQ_OK;
+}
+
+extern "C" int mmq_cls_stats(const mmq_handle* h, int64_t out[6]) {
+  if (!h || !out) return MMQ_ERR_ARG;
+  out[0] = h->cls_ready ? 1 : 0;
+  out[1] = h->cls_small;
+  out[2] = h->cls_packed;
+  out[3] = h->cls_chunks * 32;
+  out[4] = h->cls_rest;
+  out[5] = h->cls_rest_nnz;
+  return MMQ_OK;
+}
+
+int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base) {
+  int rc = mmq_seg_add_base(h, true);
+  if (rc) return rc;
+  static const int skip = [] { const char* e = getenv("MMQ_DEBUG_CLS_SKIP"); return e ? atoi(e) : 0; }(); /* timing experiments only: 1 no LO, 2 no rest, 4 no HI */
+  /* geometry (tuning knob): CTAs per SM of the two instances; 0 = the measured best */
+  static const int geo_lo = [] { const char* e = getenv("MMQ_CLS_GEO_LO"); return e ? atoi(e) : 0; }();
+  static const int geo_hi = [] { const char* e = getenv("MMQ_CLS_GEO_HI"); return e ? atoi(e) : 0; }();
+  const bool do_rest = h->cls_rest > 0 && !(skip & 2);
+  const bool do_hi = h->cls_chunks > h->cls_chunks_lo && !(skip & 4);
+  const bool do_lo = h->cls_chunks_lo > 0 && !(skip & 1);
+  /* three independent pieces, concurrently: the long chains first (their latency is the longest) */
+  if (do_rest || (do_hi && do_lo)) MMQ_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+  if (do_rest) {
+    MMQ_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
+    const int grid = (int)std::min<int64_t>((h->cls_rest_tiles + MMQ_ALLOC_WARPS - 1) / MMQ_ALLOC_WARPS, (int64_t)h->num_sms * 3);
+    mmq_launch_alloc_general(h, h->stream2, grid, h->cls_o_rp, h->cls_o_col, h->cls_o_k, h->cls_rest, h->cls_o_tiles, h->cls_rest_tiles,
+                             h->cls_o_cid, seed, sweep, sweep_base);
+    MMQ_LAUNCHED(h);
+    MMQ_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
+  }
+#define MMQ_CLS_ARGS(c0, c1) (const mmq_cls_run*)h->cls_runs, h->cls_nruns, (int)(c0), (int)(c1), h->cls_pcol, h->cls_pk, h->cls_pcid, h->cls_cid_hi, h->mu, h->counts, seed, sweep, sweep_base
+  if (do_hi) {
+    cudaStream_t st = do_lo ? h->stream3 : h->stream;
+    if (do_lo) MMQ_CUDA(h, cudaStreamWaitEvent(st, h->ev_fork, 0));
+#define MMQ_CLS_GO(LO, MINB, c0, c1, st)                                                                                  \
+  do {                                                                                                                    \
+    const int grid = (int)std::min<int64_t>(((c1) - (c0) + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, (int64_t)h->num_sms * MINB); \
+    k_alloc_cls<LO, MINB><<<grid, MMQ_CLS_WARPS * 32, 0, st>>>(MMQ_CLS_ARGS(c0, c1));                                      \
+  } while (0)
+    if (geo_hi == 4) MMQ_CLS_GO(false, 4, h->cls_chunks_lo, h->cls_chunks, st);
+    else if (geo_hi == 6) MMQ_CLS_GO(false, 6, h->cls_chunks_lo, h->cls_chunks, st);
+    else MMQ_CLS_GO(false, 5, h->cls_chunks_lo, h->cls_chunks, st); /* 96 registers, no spills */
+    MMQ_LAUNCHED(h);
+    if (do_lo) MMQ_CUDA(h, cudaEventRecord(h->ev_join3, h->stream3));
+  }
+  if (do_lo) {
+    if (geo_lo == 10) MMQ_CLS_GO(true, 10, 0, h->cls_chunks_lo, h->stream);
+    else if (geo_lo == 12) MMQ_CLS_GO(true, 12, 0, h->cls_chunks_lo, h->stream);
+    else MMQ_CLS_GO(true, 8, 0, h->cls_chunks_lo, h->stream); /* 64 registers, no spills, 32 warps per SM */
+    MMQ_LAUNCHED(h);
+  }
+#undef MMQ_CLS_GO
+#undef MMQ_CLS_ARGS
+  if (do_hi && do_lo) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join3, 0));
+  if (do_rest) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  return MMQ_OK;
+}

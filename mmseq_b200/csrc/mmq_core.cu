@@ -247,6 +247,8 @@ struct XRed {
   };
   __device__ __forceinline__ Ref operator[](int j) const { return Ref{counts + c[j]}; }
 };
+__device__ __forceinline__ void mmq_x_zero(const XRed&, int) {}
+__device__ __forceinline__ void mmq_x_add(const XRed& x, int j, int32_t v) { x[j] = v; }
 
 /* p[j] straight from global memory, for tiles too large to stage. */
 template <bool HAS_W>
@@ -839,6 +841,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   }
   if (h->has_k) CREATE_TRY(build_tiles(h, p->row_ptr)); /* k == 1 shards build them on first use of the general kernel */
   if (!h->has_k) CREATE_TRY(mmq_seg_plan(h));
+  if (h->has_k) CREATE_TRY(mmq_cls_plan(h, p));
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
 #undef CREATE_TRY
   *out = h;
@@ -859,6 +862,11 @@ void mmq_destroy(mmq_handle* h) {
   for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->ev_alloc) cudaEventDestroy(e);
   for (cudaEvent_t e : h->ev_gamma) cudaEventDestroy(e);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_join3) cudaEventDestroy(h->ev_join3);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
   for (void* p : h->allocs) cudaFree(p);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
@@ -1139,6 +1147,12 @@ static void launch_alloc_t(mmq_handle* h, int grid, uint32_t seed, uint32_t swee
   }
 #undef MMQ_ALLOC_ARGS
 }
+void mmq_launch_alloc_general(mmq_handle* h, cudaStream_t stream, int grid, const int64_t* row_ptr, const int32_t* col, const int32_t* k,
+                              int64_t m, const int64_t* tile_start, int64_t n_tiles, const int64_t* class_id, uint32_t seed,
+                              uint32_t sweep, const uint32_t* sweep_base) {
+  k_alloc<false, true, false><<<grid, MMQ_ALLOC_WARPS * 32, 0, stream>>>(row_ptr, col, k, nullptr, h->mu, h->counts, nullptr, m, tile_start, n_tiles,
+                                                                        seed, sweep, 0, class_id, sweep_base);
+}
 extern "C" {
 
 /* One sweep on the stream.  trace_col = device address of trace[0*L + slot] or null. */
@@ -1170,8 +1184,11 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       mark(h->ev_alloc);
       if (h->seg_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
         if ((rc = mmq_seg_launch(h, seed, sweep, sweep_base))) return rc;
+      } else if (h->cls_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
+        if ((rc = mmq_cls_launch(h, seed, sweep, sweep_base))) return rc;
+        g_mmq_launches.fetch_sub(1, std::memory_order_relaxed); /* counted inside; MMQ_LAUNCHED below adds one */
       } else if (!h->has_k && !(flags & MMQ_GIBBS_GENERIC_KERNEL)) {
-        if (h->seg_ready && (rc = mmq_seg_add_base(h, false))) return rc; /* this kernel visits the singletons itself */
+        if ((rc = mmq_seg_add_base(h, false))) return rc; /* this kernel visits the singletons itself */
         const int64_t n_chunks = (h->m + MMQ_CAT_ROWS - 1) / MMQ_CAT_ROWS;
         const int64_t want = (n_chunks + MMQ_CAT_WARPS - 1) / MMQ_CAT_WARPS;
         if (h->has_w) {
@@ -1186,7 +1203,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
           k_alloc_cat<false, MMQ_CAT_SLAB><<<cgrid, MMQ_CAT_WARPS * 32, SM, h->stream>>>(h->row_ptr, h->col, h->w, h->mu, h->counts, h->m, n_chunks, seed, sweep, h->class_id_base, (int32_t)h->n, sweep_base);
         }
       } else {
-        if (h->seg_ready && (rc = mmq_seg_add_base(h, false))) return rc;
+        if ((rc = mmq_seg_add_base(h, false))) return rc;
         launch_alloc_t<false>(h, grid, seed, sweep, sweep_base);
       }
       MMQ_LAUNCHED(h);

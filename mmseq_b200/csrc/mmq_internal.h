@@ -90,6 +90,21 @@ struct mmq_handle {
   bool seg_base_in_counts = true; /* counts[] currently starts from seg_base */
   int64_t seg_entries = 0, seg_rows = 0, seg_singletons = 0;
 
+  /* class plan for collapsed shards (mmq_cls.cu): the classes with few fragments packed in
+   * member-major chunks of 32, the rest as a sub-CSR for the general kernel on stream2 */
+  bool cls_ready = false;
+  void* cls_runs = nullptr; /* mmq_cls_run[] on the device */
+  int cls_nruns = 0;
+  int64_t cls_chunks = 0, cls_chunks_lo = 0, cls_small = 0, cls_packed = 0, cls_rest = 0, cls_rest_nnz = 0, cls_rest_tiles = 0;
+  uint32_t cls_cid_hi = 0;
+  int32_t* cls_pcol = nullptr;
+  uint16_t* cls_pk = nullptr; /* draws of the slot | slot number within its class << 8 */
+  uint32_t* cls_pcid = nullptr;
+  int64_t *cls_o_rp = nullptr, *cls_o_cid = nullptr, *cls_o_tiles = nullptr;
+  int32_t *cls_o_col = nullptr, *cls_o_k = nullptr;
+  cudaStream_t stream2 = nullptr, stream3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
+
   /* fused count exchange over peer memory: [flags int32[MMQ_P2P_MAX] | pad | counts A[n] | counts B[n]] */
   void* p2p_buf = nullptr;
   int32_t* p2p_flags = nullptr;
@@ -133,6 +148,12 @@ int mmq_seg_scan(mmq_handle* h, const int64_t* row_ptr_host);
 int mmq_seg_plan(mmq_handle* h);
 int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base);
 int mmq_seg_add_base(mmq_handle* h, bool want_in_counts);
+int mmq_cls_plan(mmq_handle* h, const mmq_problem* p);
+int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base);
+/* the general allocation kernel (fused reduction, with k, no weights) on an arbitrary sub-CSR and stream */
+void mmq_launch_alloc_general(mmq_handle* h, cudaStream_t stream, int grid, const int64_t* row_ptr, const int32_t* col, const int32_t* k,
+                              int64_t m, const int64_t* tile_start, int64_t n_tiles, const int64_t* class_id, uint32_t seed,
+                              uint32_t sweep, const uint32_t* sweep_base);
 
 #define MMQ_CUDA(h, call)                                                              \
   do {                                                                                 \

@@ -221,6 +221,58 @@ def test_ragged_and_extreme_rows():
             assert np.array_equal(c_f, c_o)
 
 
+@pytest.mark.parametrize("cid_base", [0, (1 << 32) * 5 + 3])
+def test_class_plan_kernel_bit_exact(cid_base):
+    """Collapsed shards (mmq_cls.cu): every regime of the plan against the CPU replay — k = 0, 1,
+    2..1024 (categorical draws, four per Philox block, 64 per slot; block and slot boundaries),
+    k > 1024 (binomial chains on the second stream), class sizes 1, 2..8 and 9..16 (the two
+    register instances), 17..64 (generic), > 64 (general kernel), all-zero and partly-zero mu
+    rows, class ids above 2^32, chunks that end inside a warp."""
+    rng = np.random.default_rng(5)
+    n = 4000
+    sizes = np.concatenate([rng.integers(1, 17, 5000), rng.integers(17, 65, 300), rng.integers(65, 200, 20), [2] * 37, [16] * 33])
+    rows = [np.sort(rng.choice(n, size=int(d), replace=False)) for d in sizes]
+    rows[10] = np.array([0, 1, 2]); rows[11] = np.array([0, 1]); rows[12] = np.array([1, 2, 3, 5])
+    m = len(rows)
+    k = np.where(rng.random(m) < 0.5, 1, rng.integers(0, 70, m))
+    big = rng.random(m) < 0.05
+    k[big] = rng.integers(65, 100000, big.sum())
+    k[:64] = np.arange(64) + 1                       # every k of the small set at least once
+    k[100:120] = [4, 5, 8, 61, 62, 63, 64, 65, 66, 127, 128, 129, 512, 1000, 1021, 1023, 1024, 1025, 1026, 4096]
+    k = k.astype(np.int32)
+    row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
+    col = np.concatenate(rows).astype(np.int32)
+    l = rng.uniform(1e-6, 1e-2, n)
+    mu = rng.gamma(0.3, 100.0, n)
+    mu[0:3] = 0.0                                    # rows 10, 11: all-zero; row 12: zeros in front
+    mu[3990:] = 1e-300
+    P = orc.Problem(row_ptr, col, k, l)
+    with capi.Handle(row_ptr, col, k, l, class_id_base=cid_base) as H:
+        st = H.cls_stats()
+        assert st["in_use"] == 1 and st["small_classes"] > 4000 and st["rest_classes"] > 20 and st["class_slots"] > st["small_classes"]
+        for sweep in (0, 1, 7):
+            H.set_mu(mu)
+            x_o, c_o, mu_o = P.sweep_replay(mu, 4321, sweep, class_id_base=cid_base)
+            _, c_f, mu_f = H.sweep_debug(4321, sweep, capi.MMQ_GIBBS_DEFAULT)
+            assert np.array_equal(c_f, c_o) and np.array_equal(mu_f, mu_o)
+            assert c_f.sum() == k.sum()
+            H.set_mu(mu)                             # the X-materialising path follows the same contract
+            x, c, _ = H.sweep_debug(4321, sweep, capi.MMQ_GIBBS_TRANSPOSED)
+            assert np.array_equal(x, x_o) and np.array_equal(c, c_o)
+            H.set_mu(mu)                             # and so does the general kernel on the whole shard
+            _, c_g, _ = H.sweep_debug(4321, sweep, capi.MMQ_GIBBS_GENERIC_KERNEL)
+            assert np.array_equal(c_g, c_o)
+        # a chain that alternates the three paths stays on the replay's trajectory (counts[] restarts
+        # from the singleton base or from zero as each kernel expects)
+        H.set_mu(mu)
+        mu_c = mu
+        for sweep, flags in enumerate([capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_GENERIC_KERNEL, capi.MMQ_GIBBS_DEFAULT,
+                                       capi.MMQ_GIBBS_TRANSPOSED, capi.MMQ_GIBBS_DEFAULT]):
+            _, c_o, mu_c = P.sweep_replay(mu_c, 4321, sweep, class_id_base=cid_base)
+            _, c_x, mu_x = H.sweep_debug(4321, sweep, flags)
+            assert np.array_equal(c_x, c_o) and np.array_equal(mu_x, mu_c)
+
+
 def test_class_id_base_shards_reproduce_the_whole(small_problem):
     """Two shards on one GPU (handles are independent): summed counts == unsharded counts."""
     h = small_problem
