@@ -126,7 +126,14 @@ __device__ __noinline__ void cls_chunk_any(const int32_t* __restrict__ pc, int D
                                            const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
                                            uint32_t sweep) {
   double norm = 0.0;
-  for (int j = 0; j < D; ++j) norm += mu[pc[32 * j]];
+  {
+    int j = 0;
+    for (; j + 4 <= D; j += 4) { /* four independent gathers in flight; the sum stays left to right */
+      const double a0 = mu[pc[32 * j]], a1 = mu[pc[32 * (j + 1)]], a2 = mu[pc[32 * (j + 2)]], a3 = mu[pc[32 * (j + 3)]];
+      norm += a0; norm += a1; norm += a2; norm += a3;
+    }
+    for (; j < D; ++j) norm += mu[pc[32 * j]];
+  }
   const int nb = (kq + 3) >> 2;
   const bool is1 = kq == 1 && b0 == 0u;
   for (int b = 0; b < nb; ++b) {
@@ -143,15 +150,24 @@ __device__ __noinline__ void cls_chunk_any(const int32_t* __restrict__ pc, int D
     for (int r = 0; r < 4; ++r) t[r] = mmq_uniform32(wd[r]) * norm;
     double s = 0.0;
     int prev = 0;
-    for (int j = 0; j < D; ++j) {
-      const int32_t cj = pc[32 * j];
-      s += mu[cj];
+    auto member = [&](int j, int32_t cj, double pj) {
+      s += pj;
       int a = 0;
 #pragma unroll
       for (int r = 0; r < 4; ++r) a += (r < nd && t[r] < s) ? 1 : 0;
       if (j == D - 1) a = nd;
       if (a - prev) atomicAdd(counts + cj, a - prev);
       prev = a;
+    };
+    int j = 0;
+    for (; j + 4 <= D && prev < nd; j += 4) {
+      const int32_t c0 = pc[32 * j], c1 = pc[32 * (j + 1)], c2 = pc[32 * (j + 2)], c3 = pc[32 * (j + 3)];
+      const double a0 = mu[c0], a1 = mu[c1], a2 = mu[c2], a3 = mu[c3];
+      member(j, c0, a0); member(j + 1, c1, a1); member(j + 2, c2, a2); member(j + 3, c3, a3);
+    }
+    for (; j < D && prev < nd; ++j) { /* prev == nd: every draw of the block has found its member */
+      const int32_t cj = pc[32 * j];
+      member(j, cj, mu[cj]);
     }
   }
 }
@@ -169,9 +185,12 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * MMQ_CLS_WARPS;
-  int ri = 0;
-  for (int chunk = chunk_begin + blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5); chunk < chunk_end; chunk += nwarps) {
+  int ri = LO ? 0 : nruns - 1;
+  for (int i = blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5); i < chunk_end - chunk_begin; i += nwarps) {
+    /* the long classes (the generic path above all) first: they must not be the tail of the launch */
+    const int chunk = LO ? chunk_begin + i : chunk_end - 1 - i;
     while (ri + 1 < nruns && chunk >= s_run[ri + 1].chunk0) ++ri; /* warp-uniform */
+    while (ri > 0 && chunk < s_run[ri].chunk0) --ri;
     const int D = s_run[ri].d;
     const int32_t* pc = pcol + s_run[ri].e0 + (int64_t)(chunk - s_run[ri].chunk0) * (32 * D) + lane;
     const uint32_t meta = pk[(int64_t)chunk * 32 + lane]; /* draws of the slot | slot number within its class << 8 */
@@ -278,13 +297,22 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   std::vector<int32_t> run_of_d(MMQ_CLS_DMAX + 1, -1);
   for (size_t r = 0; r < runs.size(); ++r) run_of_d[runs[r].d] = (int32_t)r;
 
-  /* first slot of every small class within each of its (at most two) keys; stable within a key: the
-   * caller's order (e.g. cost-sorted) is kept */
+  /* first slot of every small class within each of its (at most two) keys.  Within a key the classes
+   * are placed by their first member (a stable counting sort): members are ascending and the
+   * isoforms of a gene are neighbours in the header, so the lanes of a warp and the warps of an SM
+   * gather neighbouring mu — L1 hits instead of one L2 sector per 8-byte gather. */
   std::vector<int64_t> slot_full(m), slot_tail(m);
   {
+    std::vector<int64_t> first_pos((size_t)h->n + 2, 0);
+    for (int64_t i = 0; i < m; ++i)
+      if (kind[i] == 0) ++first_pos[(size_t)col[rp[i]] + 1];
+    for (int64_t t = 0; t <= h->n; ++t) first_pos[t + 1] += first_pos[t];
+    std::vector<int64_t> order((size_t)small_classes);
+    for (int64_t i = 0; i < m; ++i)
+      if (kind[i] == 0) order[first_pos[col[rp[i]]]++] = i;
     std::vector<int64_t> next(key_slot);
-    for (int64_t i = 0; i < m; ++i) {
-      if (kind[i] != 0) continue;
+    for (int64_t o = 0; o < small_classes; ++o) {
+      const int64_t i = order[o];
       const int d = (int)(rp[i + 1] - rp[i]);
       const int64_t kv = kk[i];
       if (kv == 1) { slot_tail[i] = next[d * MMQ_CLS_NQ + 16]++; continue; }
@@ -433,8 +461,8 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
     k_alloc_cls<LO, MINB><<<grid, MMQ_CLS_WARPS * 32, 0, st>>>(MMQ_CLS_ARGS(c0, c1));                                      \
   } while (0)
     if (geo_hi == 4) MMQ_CLS_GO(false, 4, h->cls_chunks_lo, h->cls_chunks, st);
-    else if (geo_hi == 6) MMQ_CLS_GO(false, 6, h->cls_chunks_lo, h->cls_chunks, st);
-    else MMQ_CLS_GO(false, 5, h->cls_chunks_lo, h->cls_chunks, st); /* 96 registers, no spills */
+    else if (geo_hi == 5) MMQ_CLS_GO(false, 5, h->cls_chunks_lo, h->cls_chunks, st);
+    else MMQ_CLS_GO(false, 6, h->cls_chunks_lo, h->cls_chunks, st); /* 80 registers */
     MMQ_LAUNCHED(h);
     if (do_lo) MMQ_CUDA(h, cudaEventRecord(h->ev_join3, h->stream3));
   }
