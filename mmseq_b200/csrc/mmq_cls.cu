@@ -28,9 +28,12 @@
  * byte, low word of the class id) of the small set + the sub-CSR of the rest.
  */
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -247,39 +250,61 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   const int64_t* rp = p->row_ptr;
   const int32_t* col = p->col;
   const int32_t* kk = p->k;
+  static const bool timing = [] { const char* e = getenv("MMQ_CREATE_TIMING"); return e && atoi(e) != 0; }();
+  auto t_last = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mmq_cls_plan] %-26s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
   auto cid_of = [&](int64_t i) -> uint64_t { return (uint64_t)(p->class_id ? p->class_id[i] : p->class_id_base + i); };
   const uint32_t cid_hi = (uint32_t)(cid_of(0) >> 32);
 
-  /* classify.  Slots of the small set are keyed (d, q): q = 16 - blocks for classes with k >= 2 (a run of
-   * equal d starts with its most expensive slots), q = 16 for single-fragment classes (whole warps of
-   * them take the one-draw path). */
+  /* classify (host threads).  Slots of the small set are keyed (d, q): q = 16 - blocks for classes with
+   * k >= 2 (a run of equal d starts with its most expensive slots), q = 16 for single-fragment classes
+   * (whole warps of them take the one-draw path).  key16[i]: the key of the class's last (partial) slot,
+   * or of its full slots when k is a multiple of 64; -1 singleton / empty, -2 rest. */
   const int NKEY = (MMQ_CLS_DMAX + 1) * MMQ_CLS_NQ;
+  std::vector<int16_t> key16(m);
+  struct Tally { std::vector<int64_t> key_count; int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small = 0; bool ok = true; };
+  std::vector<Tally> tally;
+  std::mutex tally_mu;
+  cls_parallel_for(m, [&](int64_t a0, int64_t b0) {
+    Tally t;
+    t.key_count.assign(NKEY + 1, 0);
+    for (int64_t i = a0; i < b0; ++i) {
+      const int64_t d = rp[i + 1] - rp[i];
+      const int64_t kv = kk[i];
+      if ((uint32_t)(cid_of(i) >> 32) != cid_hi || kv < 0) t.ok = false;
+      if (d == 1 || kv <= 0) { key16[i] = -1; ++t.n_single; } /* k == 0: nothing to allocate */
+      else if (kv <= MMQ_CAT_K && d <= MMQ_CLS_DMAX) {
+        ++t.small;
+        if (kv == 1) { key16[i] = (int16_t)(d * MMQ_CLS_NQ + 16); ++t.key_count[key16[i]]; }
+        else {
+          const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
+          t.key_count[d * MMQ_CLS_NQ + 0] += full; /* 16 blocks */
+          key16[i] = (int16_t)(d * MMQ_CLS_NQ + (tail ? 16 - (int)((tail + 3) >> 2) : 0));
+          if (tail) ++t.key_count[key16[i]];
+        }
+      } else { key16[i] = -2; ++t.n_rest; t.nnz_rest += d; }
+    }
+    std::lock_guard<std::mutex> g(tally_mu);
+    tally.push_back(std::move(t));
+  });
+  tick("classify");
   std::vector<int64_t> key_count(NKEY + 1, 0);
-  std::vector<int8_t> kind(m); /* 0 small, 1 singleton / empty, 2 rest */
   int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small_classes = 0;
-  bool ok = true;
-  for (int64_t i = 0; i < m; ++i) {
-    const int64_t d = rp[i + 1] - rp[i];
-    const int64_t kv = kk[i];
-    if ((uint32_t)(cid_of(i) >> 32) != cid_hi) ok = false;
-    if (kv < 0) ok = false;
-    if (d == 1 || kv == 0) { kind[i] = 1; ++n_single; } /* k == 0: nothing to allocate */
-    else if (kv <= MMQ_CAT_K && d <= MMQ_CLS_DMAX) {
-      kind[i] = 0;
-      ++small_classes;
-      if (kv == 1) ++key_count[d * MMQ_CLS_NQ + 16];
-      else {
-        const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
-        key_count[d * MMQ_CLS_NQ + 0] += full; /* 16 blocks */
-        if (tail) ++key_count[d * MMQ_CLS_NQ + (16 - (int)((tail + 3) >> 2))];
-      }
-    } else { kind[i] = 2; ++n_rest; nnz_rest += d; }
+  for (const Tally& t : tally) {
+    if (!t.ok) return MMQ_OK; /* class ids spread over several 2^32 blocks (or k < 0): the general kernel handles it */
+    for (int q = 0; q <= NKEY; ++q) key_count[q] += t.key_count[q];
+    n_single += t.n_single; n_rest += t.n_rest; nnz_rest += t.nnz_rest; small_classes += t.small;
   }
-  if (!ok) return MMQ_OK; /* class ids spread over several 2^32 blocks: the general kernel handles it */
 
   /* runs of equal d, chunks of 32 slots */
   std::vector<mmq_cls_run> runs;
   std::vector<int64_t> key_slot(NKEY + 1, 0); /* first slot (global numbering, 32 per chunk) of each key */
+  std::vector<int64_t> run_slots; /* slots in use per run: the rest of its last chunk is padding */
   int64_t chunks = 0, packed = 0, chunks_lo = 0;
   for (int d = 2; d <= MMQ_CLS_DMAX; ++d) {
     int64_t cnt = 0;
@@ -288,6 +313,7 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
     mmq_cls_run r;
     r.e0 = packed; r.chunk0 = (int32_t)chunks; r.d = d;
     runs.push_back(r);
+    run_slots.push_back(cnt);
     const int64_t nch = (cnt + 31) / 32;
     chunks += nch;
     packed += nch * 32 * d;
@@ -297,62 +323,71 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   std::vector<int32_t> run_of_d(MMQ_CLS_DMAX + 1, -1);
   for (size_t r = 0; r < runs.size(); ++r) run_of_d[runs[r].d] = (int32_t)r;
 
-  /* first slot of every small class within each of its (at most two) keys.  Within a key the classes
-   * are placed by their first member (a stable counting sort): members are ascending and the
-   * isoforms of a gene are neighbours in the header, so the lanes of a warp and the warps of an SM
-   * gather neighbouring mu — L1 hits instead of one L2 sector per 8-byte gather. */
-  std::vector<int64_t> slot_full(m), slot_tail(m);
+  /* Within a key the classes are placed by their first member (a stable counting sort): members are
+   * ascending and the isoforms of a gene are neighbours in the header, so the lanes of a warp and the
+   * warps of an SM gather neighbouring mu — L1 hits instead of one L2 sector per 8-byte gather. */
+  static_assert(MMQ_CAT_K / MMQ_CAT_GROUP <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
+  struct Ord { int32_t i; int16_t key; uint8_t full, tail; }; /* key: of the partial slot (tail draws) when there is one */
+  std::vector<Ord> order((size_t)small_classes);
   {
     std::vector<int64_t> first_pos((size_t)h->n + 2, 0);
     for (int64_t i = 0; i < m; ++i)
-      if (kind[i] == 0) ++first_pos[(size_t)col[rp[i]] + 1];
+      if (key16[i] >= 0) ++first_pos[(size_t)col[rp[i]] + 1];
     for (int64_t t = 0; t <= h->n; ++t) first_pos[t + 1] += first_pos[t];
-    std::vector<int64_t> order((size_t)small_classes);
     for (int64_t i = 0; i < m; ++i)
-      if (kind[i] == 0) order[first_pos[col[rp[i]]]++] = i;
+      if (key16[i] >= 0) order[(size_t)first_pos[col[rp[i]]]++] = Ord{(int32_t)i, key16[i], (uint8_t)(kk[i] / MMQ_CAT_GROUP), (uint8_t)(kk[i] % MMQ_CAT_GROUP)};
+  }
+  tick("order by first member");
+  /* first slot of every small class within each of its (at most two) keys, in placement order */
+  std::vector<int64_t> slot_full((size_t)small_classes), slot_tail((size_t)small_classes);
+  {
     std::vector<int64_t> next(key_slot);
     for (int64_t o = 0; o < small_classes; ++o) {
-      const int64_t i = order[o];
-      const int d = (int)(rp[i + 1] - rp[i]);
-      const int64_t kv = kk[i];
-      if (kv == 1) { slot_tail[i] = next[d * MMQ_CLS_NQ + 16]++; continue; }
-      const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
-      slot_full[i] = next[d * MMQ_CLS_NQ + 0];
-      next[d * MMQ_CLS_NQ + 0] += full;
-      if (tail) slot_tail[i] = next[d * MMQ_CLS_NQ + (16 - (int)((tail + 3) >> 2))]++;
+      const Ord& e = order[(size_t)o];
+      const int d = e.key / MMQ_CLS_NQ;
+      slot_full[(size_t)o] = next[d * MMQ_CLS_NQ + 0];
+      next[d * MMQ_CLS_NQ + 0] += e.full;
+      slot_tail[(size_t)o] = e.tail ? next[e.key]++ : -1; /* -1: k is a multiple of 64, no partial slot */
     }
   }
-  std::vector<int32_t> pcol((size_t)packed, (int32_t)h->n); /* padding: the sentinel column (mu[n] == 0) */
+  tick("slots");
+  std::unique_ptr<int32_t[]> pcol(new int32_t[(size_t)std::max<int64_t>(packed, 1)]); /* every entry is written below */
   std::vector<uint16_t> pk((size_t)chunks * 32, 0);
   std::vector<uint32_t> pcid((size_t)chunks * 32, 0u);
-  cls_parallel_for(m, [&](int64_t a, int64_t b) {
-    for (int64_t i = a; i < b; ++i) {
-      if (kind[i] != 0) continue;
-      const int d = (int)(rp[i + 1] - rp[i]);
+  for (size_t r = 0; r < runs.size(); ++r) { /* padding slots of a run's last chunk: the sentinel column (mu[n] == 0), no draws */
+    const int d = runs[r].d;
+    const int64_t used = run_slots[r], nch = (used + 31) / 32;
+    int32_t* last = pcol.get() + runs[r].e0 + (nch - 1) * 32 * d;
+    for (int lane = (int)(used - (nch - 1) * 32); lane < 32; ++lane)
+      for (int j = 0; j < d; ++j) last[32 * j + lane] = (int32_t)h->n;
+  }
+  cls_parallel_for(small_classes, [&](int64_t a0, int64_t b0) {
+    for (int64_t o = a0; o < b0; ++o) {
+      const Ord& e = order[(size_t)o];
+      const int64_t i = e.i;
+      const int d = e.key / MMQ_CLS_NQ;
       const mmq_cls_run& r = runs[run_of_d[d]];
       const int32_t* src = col + rp[i];
       const uint32_t cid = (uint32_t)cid_of(i);
       auto put = [&](int64_t s, int draws, int slot_no) {
         const int64_t ch = s >> 5;
-        int32_t* dst = pcol.data() + r.e0 + (ch - r.chunk0) * 32 * d + (s & 31);
+        int32_t* dst = pcol.get() + r.e0 + (ch - r.chunk0) * 32 * d + (s & 31);
         for (int j = 0; j < d; ++j) dst[32 * j] = src[j];
         pk[s] = (uint16_t)(draws | (slot_no << 8));
         pcid[s] = cid;
       };
-      const int64_t kv = kk[i];
-      if (kv == 1) { put(slot_tail[i], 1, 0); continue; }
-      const int full = (int)(kv / MMQ_CAT_GROUP), tail = (int)(kv % MMQ_CAT_GROUP);
-      for (int q = 0; q < full; ++q) put(slot_full[i] + q, MMQ_CAT_GROUP, q);
-      if (tail) put(slot_tail[i], tail, full);
+      for (int q = 0; q < (int)e.full; ++q) put(slot_full[(size_t)o] + q, MMQ_CAT_GROUP, q);
+      if (e.tail) put(slot_tail[(size_t)o], (int)e.tail, (int)e.full);
     }
   });
 
+  tick("fill");
   /* the rest: a sub-CSR for the general kernel, longest chains first, ONE class per warp tile (a
    * chain of binomials is serial: what matters is when the slowest warp ends, not lane use) */
   std::vector<int64_t> rest;
   rest.reserve((size_t)n_rest);
   for (int64_t i = 0; i < m; ++i)
-    if (kind[i] == 2) rest.push_back(i);
+    if (key16[i] == -2) rest.push_back(i);
   std::stable_sort(rest.begin(), rest.end(), [&](int64_t a, int64_t b) { return rp[a + 1] - rp[a] > rp[b + 1] - rp[b]; });
   std::vector<int64_t> o_rp((size_t)n_rest + 1, 0), o_cid((size_t)n_rest), o_tiles((size_t)n_rest + 1);
   std::vector<int32_t> o_col((size_t)nnz_rest + 4, 0), o_k((size_t)n_rest);
@@ -371,10 +406,12 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   std::vector<int32_t> s_col, s_k;
   s_col.reserve((size_t)n_single); s_k.reserve((size_t)n_single);
   for (int64_t i = 0; i < m; ++i)
-    if (kind[i] == 1 && kk[i] > 0) { s_col.push_back(col[rp[i]]); s_k.push_back(kk[i]); }
+    if (key16[i] == -1 && kk[i] > 0) { s_col.push_back(col[rp[i]]); s_k.push_back(kk[i]); }
 
+  tick("rest, singletons");
   int rc;
-  if ((rc = cls_upload(h, &h->cls_pcol, pcol))) return rc;
+  if ((rc = mmq_dev_alloc(h, (void**)&h->cls_pcol, sizeof(int32_t) * (size_t)std::max<int64_t>(packed, 1)))) return rc;
+  if (packed > 0) MMQ_CUDA(h, cudaMemcpyAsync(h->cls_pcol, pcol.get(), sizeof(int32_t) * (size_t)packed, cudaMemcpyHostToDevice, h->stream));
   if ((rc = cls_upload(h, &h->cls_pk, pk))) return rc;
   if ((rc = cls_upload(h, &h->cls_pcid, pcid))) return rc;
   if ((rc = cls_upload(h, (mmq_cls_run**)&h->cls_runs, runs))) return rc;
@@ -407,6 +444,7 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
   }
+  tick("uploads");
   h->cls_nruns = (int)runs.size();
   h->cls_chunks = chunks;
   h->cls_chunks_lo = chunks_lo;

@@ -16,6 +16,7 @@
 #include <nccl.h> /* types only; the library is dlopen'ed */
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 
@@ -42,6 +43,13 @@ int mmq_cuda_fail(mmq_handle* h, cudaError_t e, const char* what, const char* fi
 int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
+  const size_t rounded = (bytes + 255) & ~(size_t)255;
+  if (h->arena && h->arena_off + rounded <= h->arena_cap) {
+    *p = h->arena + h->arena_off;
+    h->arena_off += rounded;
+    h->bytes += (int64_t)bytes;
+    return MMQ_OK;
+  }
   cudaError_t e = cudaMalloc(p, bytes);
   if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaMalloc", __FILE__, __LINE__);
   h->bytes += (int64_t)bytes;
@@ -51,6 +59,7 @@ int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes) {
 
 void mmq_dev_free(mmq_handle* h, void* p) {
   if (!p) return;
+  if (h->arena && (char*)p >= h->arena && (char*)p < h->arena + h->arena_cap) return; /* released with the arena */
   auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
   if (it != h->allocs.end()) h->allocs.erase(it);
   cudaFree(p);
@@ -782,6 +791,15 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   if (device < 0 || device >= ndev) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_create: device index out of range");
   mmq_handle* h = new mmq_handle();
   h->device = device;
+  /* MMQ_CREATE_TIMING=1: host wall clock of the phases below on stderr (no extra synchronisation) */
+  static const bool timing = [] { const char* e = getenv("MMQ_CREATE_TIMING"); return e && atoi(e) != 0; }();
+  auto t_last = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    if (!timing) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[mmq_create] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+    t_last = now;
+  };
 #define CREATE_TRY(expr)                      \
   do {                                        \
     int rc__ = (expr);                        \
@@ -797,14 +815,25 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   CREATE_TRY(cuda_try(cudaSetDevice(device), "cudaSetDevice"));
   CREATE_TRY(cuda_try(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
   h->own_stream = true;
-  cudaDeviceProp prop;
-  CREATE_TRY(cuda_try(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties"));
-  h->num_sms = prop.multiProcessorCount;
+  CREATE_TRY(cuda_try(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device), "cudaDeviceGetAttribute")); /* cudaGetDeviceProperties takes ~10 ms */
+  tick("device, stream");
   h->n = p->n; h->m = p->m; h->nnz = p->nnz; h->class_id_base = p->class_id_base;
   h->alpha = p->alpha; h->beta = p->beta;
   h->has_k = p->k != nullptr; h->has_w = p->weight != nullptr;
   for (int64_t t = 0; t < p->n; ++t)
     if (!(p->len[t] > 0.0)) { h->err = "mmq_create: transcript length must be > 0 (src/mmseq.cpp:604-607)"; CREATE_TRY(MMQ_ERR_ARG); }
+  tick("length check");
+  {
+    const size_t n = (size_t)p->n, m = (size_t)p->m, nnz = (size_t)p->nnz;
+    size_t want = 8 * (m + 1) + 4 * nnz + 16 + (h->has_k ? 4 * m : 0) + (p->class_id ? 8 * m : 0) + (h->has_w ? 4 * nnz + 16 : 0) +
+                  8 * n + 2 * 8 * (n + 1) + 8 * n + 4 * n + 4 * n + 8 * std::max<size_t>(m, 1) + 8 * (size_t)h->num_sms * 8 + 32;
+    if (!h->has_k) want += (h->has_w ? 2 : 1) * 4 * (nnz + 128 * 12 + 128) + 4 * n + 4096; /* the segment plan's packed copies */
+    else if (!h->has_w) want += 4 * (nnz + nnz / 8) + 6 * (m + m / 4) + 4 * n + (1 << 16);     /* the class plan's (an estimate: what does not fit is allocated separately) */
+    want += 64 * 256;                                                                      /* alignment of the pieces */
+    void* a = nullptr;
+    if (cudaMalloc(&a, want) == cudaSuccess) { h->arena = (char*)a; h->arena_cap = want; }
+    else cudaGetLastError(); /* fall back to separate allocations */
+  }
   CREATE_TRY(upload(h, (void**)&h->row_ptr, p->row_ptr, sizeof(int64_t) * (size_t)(p->m + 1)));
   CREATE_TRY(upload(h, (void**)&h->col, p->col, sizeof(int32_t) * (size_t)p->nnz, 16)); /* +4 entries: aligned 128-bit staging may over-read */
   if (h->has_k) CREATE_TRY(upload(h, (void**)&h->k, p->k, sizeof(int32_t) * (size_t)p->m));
@@ -826,7 +855,9 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   CREATE_TRY(cuda_try(cudaMemsetAsync(h->counts, 0, sizeof(int32_t) * (size_t)p->n, h->stream), "memset counts"));
   CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu, 0, sizeof(double) * (size_t)(p->n + 1), h->stream), "memset mu"));
   CREATE_TRY(cuda_try(cudaMemsetAsync(h->mu_tmp, 0, sizeof(double) * (size_t)(p->n + 1), h->stream), "memset mu_tmp"));
+  tick("allocations, copies queued");
   if (!h->has_k) CREATE_TRY(mmq_seg_scan(h, p->row_ptr)); /* host scan, overlapped with the queued H2D copies */
+  tick("segment scan (host)");
   if (p->m > 0) { /* structural checks on the device: no O(nnz) host loop in front of the upload */
     int* d_flags = (int*)h->scalars;
     CREATE_TRY(cuda_try(cudaMemsetAsync(d_flags, 0, sizeof(int), h->stream), "memset flags"));
@@ -839,10 +870,14 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
     if (flags & 2) { h->err = "mmq_create: column index out of range"; CREATE_TRY(MMQ_ERR_ARG); }
     if (flags & 4) { h->err = "mmq_create: columns must be strictly ascending within a class (src/mmseq.cpp:412)"; CREATE_TRY(MMQ_ERR_ARG); }
   }
+  tick("H2D copies + validation");
   if (h->has_k) CREATE_TRY(build_tiles(h, p->row_ptr)); /* k == 1 shards build them on first use of the general kernel */
+  tick("tiles");
   if (!h->has_k) CREATE_TRY(mmq_seg_plan(h));
   if (h->has_k) CREATE_TRY(mmq_cls_plan(h, p));
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
+  tick("segment / class plan");
+  h->arena_cap = h->arena_off; /* closed: later allocations (trace, transpose, peer buffers) are their own */
 #undef CREATE_TRY
   *out = h;
   return MMQ_OK;
@@ -869,6 +904,7 @@ void mmq_destroy(mmq_handle* h) {
   if (h->ev_join3) cudaEventDestroy(h->ev_join3);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
   for (void* p : h->allocs) cudaFree(p);
+  if (h->arena) cudaFree(h->arena);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -133,6 +133,10 @@ struct mmq_handle {
   int64_t bytes = 0;
   std::string err;
   std::vector<void*> allocs;
+  /* one device allocation behind the arrays mmq_create makes (a dozen cudaMalloc calls cost
+   * milliseconds each at these sizes); later allocations are separate */
+  char* arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0;
 };
 
 extern std::atomic<long long> g_mmq_launches;

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 #include <vector>
 
 #include "mmq_device.cuh"
@@ -407,14 +408,36 @@ int mmq_seg_scan(mmq_handle* h, const int64_t* rp) {
   h->seg_scan_ok = false;
   const int64_t m = h->m;
   if (m == 0 || h->has_k) return MMQ_OK;
-  for (int64_t i = 0; i < m;) {
-    const int64_t d = rp[i + 1] - rp[i];
-    if (d > 0x7fffffff || d <= 0) return MMQ_OK;
-    int64_t j = i + 1;
-    while (j < m && rp[j + 1] - rp[j] == d) ++j;
-    h->seg_runs.push_back({i, j, rp[i], (int)d});
-    if ((int)h->seg_runs.size() > MMQ_SEG_MAX) { h->seg_runs.clear(); return MMQ_OK; } /* ragged shard: the row-pointer kernel handles it */
-    i = j;
+  /* 8 bytes per class to read: split between host threads (the H2D copies of the shard are in flight meanwhile) */
+  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 16u), m / (1 << 20)));
+  std::vector<std::vector<mmq_handle::seg_run>> part((size_t)nt);
+  std::vector<char> bad((size_t)nt, 0);
+  auto scan = [&](int t) {
+    const int64_t a = m * t / nt, b = m * (t + 1) / nt;
+    auto& out = part[(size_t)t];
+    for (int64_t i = a; i < b;) {
+      const int64_t d = rp[i + 1] - rp[i];
+      if (d > 0x7fffffff || d <= 0) { bad[(size_t)t] = 1; return; }
+      int64_t j = i + 1;
+      while (j < b && rp[j + 1] - rp[j] == d) ++j;
+      out.push_back({i, j, rp[i], (int)d});
+      if ((int)out.size() > MMQ_SEG_MAX + 1) { bad[(size_t)t] = 2; return; } /* ragged shard */
+      i = j;
+    }
+  };
+  if (nt == 1) scan(0);
+  else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; ++t) th.emplace_back(scan, t);
+    for (auto& x : th) x.join();
+  }
+  for (int t = 0; t < nt; ++t) {
+    if (bad[(size_t)t]) { h->seg_runs.clear(); return MMQ_OK; } /* not a by-length layout: the row-pointer kernel handles it */
+    for (const auto& r : part[(size_t)t]) {
+      if (!h->seg_runs.empty() && h->seg_runs.back().d == r.d && h->seg_runs.back().r1 == r.r0) h->seg_runs.back().r1 = r.r1; /* a run cut by the split */
+      else h->seg_runs.push_back(r);
+      if ((int)h->seg_runs.size() > MMQ_SEG_MAX) { h->seg_runs.clear(); return MMQ_OK; }
+    }
   }
   h->seg_scan_ok = true;
   return MMQ_OK;
