@@ -52,7 +52,7 @@ def parse():
     ap.add_argument("--nccl-only", action="store_true", help="N > 1: exchange counts with ncclAllReduce instead of the fused peer-memory kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extra", action="store_true", help="also time the collapsed layout and EM (extra keys)")
+    ap.add_argument("--no-collapsed", action="store_true", help="skip the extra line on the collapsed (reference-semantics) layout of the same sample")
     return ap.parse_args()
 
 
@@ -207,6 +207,44 @@ def workload_config(args, h, world, sweeps_per_step=SWEEPS_PER_STEP):
         "count_exchange": ("none" if world == 1 else ("nccl_allreduce" if getattr(args, "nccl_only", False) else "fused_p2p_gamma")),
         "l2": "inputs_exceed_l2" if (4 * h.nnz + 8 * h.m) > 200e6 else "inputs_fit_l2_flush_between_steps",
     }
+
+
+def collapsed_line(args, s, dev, stream, length_full=None, steps=5, warmup=3):
+    """Sweeps/s of the collapsed layout of the same synthetic sample (device-timed, CUDA events)."""
+    import torch
+    from mmseq_b200 import capi, hostlib
+    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_COLLAPSED | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
+    length = s.efflen[h.col2hdr] * args.fragments / 1e9
+    rp_s, col_s, k_s, class_id = hostlib.sort_classes_by_cost(h)
+    H = capi.Handle(rp_s, col_s, k_s, length, class_id=class_id, device=dev.index)
+    H.set_stream(stream.cuda_stream)
+    H.init_mu()
+    cls = H.cls_stats()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # the packed classes fit the L2: flush between steps
+    sweep = 0
+    S = SWEEPS_PER_STEP
+
+    def step(flags):
+        nonlocal sweep
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        H.gibbs(SEED, sweep, S, stride=S, trace_len=steps + warmup + 1, flags=flags)
+        sweep += S
+
+    for _ in range(warmup):
+        step(capi.MMQ_GIBBS_DEFAULT)
+    H.synchronize()
+    for _ in range(steps):
+        step(capi.MMQ_GIBBS_TIME_KERNELS)
+    alloc_ms, alloc_n, gamma_ms, gamma_n = H.kernel_times()
+    H.close()
+    per_sweep = alloc_ms / max(alloc_n, 1) + gamma_ms / max(gamma_n, 1)
+    b = 4 * cls["packed_slots"] + 6 * cls["class_slots"] + 20 * cls["rest_classes"] + 4 * cls["rest_nnz"]
+    return {"workload": "C2-collapsed", "classes": int(h.m), "nnz": int(h.nnz), "kernel": "k_alloc_cls",
+            "alloc_avg_launch_ms": alloc_ms / max(alloc_n, 1), "gamma_avg_launch_ms": gamma_ms / max(gamma_n, 1),
+            "sweeps_per_s_kernels": 1000.0 / per_sweep, "fragments_per_s_kernels": 1000.0 / per_sweep * args.fragments,
+            "algorithmic_bytes_per_launch": int(b), "class_plan": cls,
+            "note": "kernel time per sweep (allocation + Gamma, CUDA events), launch gaps not included; python bench.py --layout collapsed gives the full line"}
 
 
 def main():
@@ -376,6 +414,11 @@ def main():
         "config": workload_config(args, h, world), "clocks": sampler.result(),
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "prep": prep,
     }
+
+    # ---- the same sample in the reference's own representation (distinct classes + counts k, what the
+    # host program feeds the GPU): class-plan kernel, reported beside the headline (N = 1 only)
+    if rank == 0 and world == 1 and args.layout == "perfragment" and not args.no_collapsed and not args.weights:
+        line["collapsed_layout"] = collapsed_line(args, s, dev, stream, length_full=None)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

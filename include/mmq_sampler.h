@@ -40,7 +40,7 @@
 #define MMQ_STREAM_ALLOC 0x414c4c4fu /* per hit class, per sweep   */
 #define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
 #define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
-#define MMQ_CAT_K 1024 /* classes with 2..MMQ_CAT_K fragments: categorical draws (four 32-bit uniforms per Philox block) instead of binomials */
+#define MMQ_CAT_K 8192 /* classes with 2..MMQ_CAT_K fragments: categorical draws (four 32-bit uniforms per Philox block) instead of binomials */
 #define MMQ_CAT_GROUP 64 /* ... generated 64 at a time (16 blocks): the unit of work of the class-plan kernel */
 #define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per QUAD of classes (one 32-bit word each) */
 

@@ -189,17 +189,30 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * MMQ_CLS_WARPS;
   int ri = LO ? 0 : nruns - 1;
-  for (int i = blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5); i < chunk_end - chunk_begin; i += nwarps) {
-    /* the long classes (the generic path above all) first: they must not be the tail of the launch */
-    const int chunk = LO ? chunk_begin + i : chunk_end - 1 - i;
+  const int count = chunk_end - chunk_begin;
+  /* the long classes (the generic path above all) first in the 9..16 instance: they must not be the tail of the launch */
+  auto chunk_of = [&](int i) { return LO ? chunk_begin + i : chunk_end - 1 - i; };
+  int i = blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5);
+  /* draw counts and class ids are fetched one chunk ahead (two registers): their latency is off the critical path */
+  uint32_t meta_n = 0, cid_n = 0;
+  if (i < count) {
+    meta_n = pk[(int64_t)chunk_of(i) * 32 + lane];
+    cid_n = pcid[(int64_t)chunk_of(i) * 32 + lane];
+  }
+  for (; i < count; i += nwarps) {
+    const int chunk = chunk_of(i);
     while (ri + 1 < nruns && chunk >= s_run[ri + 1].chunk0) ++ri; /* warp-uniform */
     while (ri > 0 && chunk < s_run[ri].chunk0) --ri;
     const int D = s_run[ri].d;
     const int32_t* pc = pcol + s_run[ri].e0 + (int64_t)(chunk - s_run[ri].chunk0) * (32 * D) + lane;
-    const uint32_t meta = pk[(int64_t)chunk * 32 + lane]; /* draws of the slot | slot number within its class << 8 */
+    const uint32_t meta = meta_n; /* draws of the slot | slot number within its class << 8 */
+    const uint32_t cid = cid_n;
+    if (i + nwarps < count) {
+      meta_n = pk[(int64_t)chunk_of(i + nwarps) * 32 + lane];
+      cid_n = pcid[(int64_t)chunk_of(i + nwarps) * 32 + lane];
+    }
     const int kq = (int)(meta & 0xffu);
     const uint32_t b0 = (meta >> 8) * (MMQ_CAT_GROUP / 4);
-    const uint32_t cid = pcid[(int64_t)chunk * 32 + lane];
 #define MMQ_CLS_CASE(DD) case DD: cls_chunk<DD>(pc, kq, b0, cid, cid_hi, mu, counts, seed, sweep, lane); break;
     if (LO) {
       switch (D) {
@@ -499,8 +512,8 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
     k_alloc_cls<LO, MINB><<<grid, MMQ_CLS_WARPS * 32, 0, st>>>(MMQ_CLS_ARGS(c0, c1));                                      \
   } while (0)
     if (geo_hi == 4) MMQ_CLS_GO(false, 4, h->cls_chunks_lo, h->cls_chunks, st);
-    else if (geo_hi == 5) MMQ_CLS_GO(false, 5, h->cls_chunks_lo, h->cls_chunks, st);
-    else MMQ_CLS_GO(false, 6, h->cls_chunks_lo, h->cls_chunks, st); /* 80 registers */
+    else if (geo_hi == 6) MMQ_CLS_GO(false, 6, h->cls_chunks_lo, h->cls_chunks, st);
+    else MMQ_CLS_GO(false, 5, h->cls_chunks_lo, h->cls_chunks, st); /* 96 registers, no spills */
     MMQ_LAUNCHED(h);
     if (do_lo) MMQ_CUDA(h, cudaEventRecord(h->ev_join3, h->stream3));
   }

@@ -224,8 +224,8 @@ def test_ragged_and_extreme_rows():
 @pytest.mark.parametrize("cid_base", [0, (1 << 32) * 5 + 3])
 def test_class_plan_kernel_bit_exact(cid_base):
     """Collapsed shards (mmq_cls.cu): every regime of the plan against the CPU replay — k = 0, 1,
-    2..1024 (categorical draws, four per Philox block, 64 per slot; block and slot boundaries),
-    k > 1024 (binomial chains on the second stream), class sizes 1, 2..8 and 9..16 (the two
+    2..8192 (categorical draws, four per Philox block, 64 per slot; block and slot boundaries),
+    k > 8192 (binomial chains on the second stream), class sizes 1, 2..8 and 9..16 (the two
     register instances), 17..64 (generic), > 64 (general kernel), all-zero and partly-zero mu
     rows, class ids above 2^32, chunks that end inside a warp."""
     rng = np.random.default_rng(5)
@@ -238,7 +238,7 @@ def test_class_plan_kernel_bit_exact(cid_base):
     big = rng.random(m) < 0.05
     k[big] = rng.integers(65, 100000, big.sum())
     k[:64] = np.arange(64) + 1                       # every k of the small set at least once
-    k[100:120] = [4, 5, 8, 61, 62, 63, 64, 65, 66, 127, 128, 129, 512, 1000, 1021, 1023, 1024, 1025, 1026, 4096]
+    k[100:120] = [4, 5, 8, 61, 62, 63, 64, 65, 66, 127, 128, 129, 512, 1000, 1024, 1025, 8191, 8192, 8193, 8194]
     k = k.astype(np.int32)
     row_ptr = np.concatenate([[0], np.cumsum([len(r) for r in rows])]).astype(np.int64)
     col = np.concatenate(rows).astype(np.int32)

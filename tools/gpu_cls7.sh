@@ -13,5 +13,4 @@ run "MMQ_X=0" "--layout collapsed"
 run "MMQ_DEBUG_CLS_SKIP=6" "--layout collapsed"
 run "MMQ_DEBUG_CLS_SKIP=3" "--layout collapsed"
 run "MMQ_CLS_GEO_HI=5" "--layout collapsed"
-timeout 600 ncu --section SpeedOfLight --section WarpStateStats --section SchedulerStats --section LaunchStats --section Occupancy --clock-control none -k regex:k_alloc -s 15 -c 3 --csv --page raw --log-file gpurun_out/cls7_raw.csv python bench.py --layout collapsed --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_cls.log 2>&1
-tail -2 gpurun_out/ncu_cls.log
+run "MMQ_CLS_GEO_LO=10" "--layout collapsed"

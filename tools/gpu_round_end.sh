@@ -10,8 +10,10 @@ timeout 900 python bench.py > gpurun_out/bench_ours.json 2> gpurun_out/bench_our
 kill $SMI
 timeout 600 python bench.py --weights --no-cpu-baseline > gpurun_out/bench_weighted.json 2>> gpurun_out/bench_ours.err
 timeout 600 python bench.py --layout collapsed --no-cpu-baseline > gpurun_out/bench_collapsed.json 2>> gpurun_out/bench_ours.err
-ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_alloc_seg4 -s 5 -c 1 -o gpurun_out/prof_r01_k_alloc_seg4 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-collapsed > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_alloc_seg4 -s 5 -c 1 -o gpurun_out/prof_r01_k_alloc_seg4 -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-collapsed > gpurun_out/ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_alloc_cls -s 10 -c 2 -o gpurun_out/prof_r01_k_alloc_cls -f python bench.py --layout collapsed --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_cls.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file gpurun_out/launches_r01_collapsed.csv python bench.py --layout collapsed --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > /dev/null 2>&1
 # config 1 end to end: the reference's own main() (unmodified sources + oracle/shim) on the host cores vs the host program on the GPU
 python - <<'PY'
 from mmseq_b200 import synth
