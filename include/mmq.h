@@ -140,8 +140,8 @@ int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweep
               int trace_len, int flags);
 
 /* What the class plan of a collapsed shard (classes with counts k; built by mmq_create) holds:
- * out[0] 1 if the plan is in use, out[1] classes of the small set (k <= 64 fragments: categorical
- * draws, replaces the multinomial of src/mmseq.cpp:880 for those classes), out[2] packed column
+ * out[0] 1 if the plan is in use, out[1] classes of the small set (k <= MMQ_CAT_K fragments, at most
+ * 64 members: categorical draws, stands in for the multinomial of src/mmseq.cpp:880 for those classes), out[2] packed column
  * slots and out[3] class slots streamed per sweep for them, out[4] classes and out[5] CSR entries
  * left to the general kernel (conditional-binomial chains).  Used by bench.py for the
  * algorithmic-bytes figure. */
@@ -214,6 +214,10 @@ int mmq_sokal_batch(int device, int64_t rows, int len, const double* x, double* 
 
 /* Kernel launches issued by this process through the library so far. */
 int64_t mmq_launch_count(void);
+/* Bring up the CUDA context of `device` (the first CUDA call of a process costs 1-2 s): a host
+ * program calls this from a side thread while it parses its input.  No reference counterpart. */
+int mmq_warmup(int device);
+
 const char* mmq_version(void);
 
 #ifdef __cplusplus

@@ -73,6 +73,7 @@ def _load():
         "mmq_sokal_batch": (i32, [i32, i64, i32, vp, vp, vp, vp, vp]),
         "mmq_prior_draws": (i32, [i32, i64, vp, vp, dbl, u32, i32, vp]),
         "mmq_launch_count": (i64, []),
+        "mmq_warmup": (i32, [i32]),
         "mmq_version": (C.c_char_p, []),
     }
     for name, (res, args) in sig.items():
@@ -97,7 +98,7 @@ EXPORTS = [
     "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_p2p_export", "mmq_p2p_attach", "mmq_p2p_attach_local", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
     "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_cls_stats", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
-    "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_version",
+    "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_warmup", "mmq_version",
 ]
 
 

@@ -1395,6 +1395,11 @@ int mmq_kernel_times(mmq_handle* h, double* alloc_ms, int64_t* alloc_launches, d
 
 int mmq_trace_len(const mmq_handle* h) { return h ? h->trace_len : 0; }
 
+int mmq_warmup(int device) {
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return MMQ_ERR_CUDA; }
+  return cudaFree(nullptr) == cudaSuccess ? MMQ_OK : MMQ_ERR_CUDA;
+}
+
 int mmq_get_trace(mmq_handle* h, double* out) {
   if (!h || !out) return mmq_fail(h, MMQ_ERR_ARG, "mmq_get_trace: NULL argument");
   if (!h->trace) return mmq_fail(h, MMQ_ERR_STATE, "mmq_get_trace: no trace recorded (run mmq_gibbs with trace_len > 0)");

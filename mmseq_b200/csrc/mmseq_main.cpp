@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <limits>
 #include <map>
@@ -311,13 +312,17 @@ int main(int argc, char** argv) {
   const string hits_file = arguments[0];
   const string output_base(arguments[1]);
 
+  /* the CUDA contexts come up (1-2 s) while the hits file is being parsed */
+  thread warmup([ngpus] { for (int g = 0; g < ngpus; ++g) mmq_warmup(g); });
+
   /* ---- load: header + records -> hit classes (src/hitsio.cpp, src/mmseq.cpp:312-441) */
   mmq::HitsHeader hdr;
   mmq::HitClasses cls;
   {
     string err;
-    if (mmq::load_hits_file(hits_file, mmq::LAYOUT_COLLAPSED, hdr, cls, err)) die(err);
+    if (mmq::load_hits_file(hits_file, mmq::LAYOUT_COLLAPSED, hdr, cls, err)) { warmup.join(); die(err); }
   }
+  warmup.join();
   cout << "Running mmseq with parameters:\n"
        << "  alpha:         " << alpha << endl
        << "  beta:          " << beta << endl
@@ -343,57 +348,48 @@ int main(int argc, char** argv) {
     if (mmq::scaled_lengths(hdr, cls, l, err)) die(err);
   }
 
-  /* ---- device order of the classes: sorted by the work their allocation needs (no draw for
-   * singletons; one categorical draw for k == 1; k draws for 2 <= k <= 8; a binomial chain above),
-   * then by size and count, so that the classes a warp works on are alike.  The Philox counter of
-   * a class stays its first-appearance index (mmq_problem.class_id): the chain is the one of the
-   * canonical order, whatever the device order and the number of GPUs.  Shard g takes every
-   * ngpus-th class of the sorted order (equal mix of cheap and expensive classes per GPU). */
-  vector<int64_t> order((size_t)m);
-  for (int64_t i = 0; i < m; ++i) order[(size_t)i] = i;
-  {
-    auto kind = [&](int64_t i) {
-      const int64_t d = cls.row_ptr[(size_t)i + 1] - cls.row_ptr[(size_t)i];
-      const int32_t kk = cls.k[(size_t)i];
-      return d == 1 ? 0 : (kk == 1 ? 1 : (kk <= 8 ? 2 : 3));
-    };
-    stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
-      const int ka = kind(a), kb = kind(b);
-      if (ka != kb) return ka < kb;
-      const int64_t da = cls.row_ptr[(size_t)a + 1] - cls.row_ptr[(size_t)a], db = cls.row_ptr[(size_t)b + 1] - cls.row_ptr[(size_t)b];
-      if (da != db) return da < db;
-      return cls.k[(size_t)a] < cls.k[(size_t)b];
-    });
-  }
+  /* ---- shards.  The library orders the classes of a shard itself (class plan, mmq_cls.cu), so the
+   * host hands them over as they are: one GPU takes the loader's arrays in place; several GPUs take
+   * every ngpus-th class (first-appearance order is unrelated to the cost of a class, so the deal is
+   * an equal mix).  The Philox counter of a class is its first-appearance index either way
+   * (mmq_problem.class_id): the chain does not depend on the number of GPUs. */
   vector<Shard> shards((size_t)ngpus);
   vector<vector<int64_t>> shard_rp((size_t)ngpus), shard_id((size_t)ngpus);
   vector<vector<int32_t>> shard_col((size_t)ngpus), shard_k((size_t)ngpus);
   for (int g = 0; g < ngpus; ++g) {
     Shard& S = shards[(size_t)g];
     S.device = g;
-    auto& rp = shard_rp[(size_t)g];
-    auto& id = shard_id[(size_t)g];
-    auto& cc = shard_col[(size_t)g];
-    auto& kk = shard_k[(size_t)g];
-    rp.push_back(0);
-    for (int64_t j = g; j < m; j += ngpus) {
-      const int64_t i = order[(size_t)j];
-      id.push_back(i);
-      kk.push_back(cls.k[(size_t)i]);
-      for (int64_t q = cls.row_ptr[(size_t)i]; q < cls.row_ptr[(size_t)i + 1]; ++q) cc.push_back(cls.col[(size_t)q]);
-      rp.push_back((int64_t)cc.size());
-    }
-    S.row0 = 0; S.row1 = (int64_t)id.size();
     mmq_problem p;
     memset(&p, 0, sizeof p);
-    p.n = n; p.m = (int64_t)id.size(); p.nnz = rp.back();
-    p.row_ptr = rp.data();
-    p.col = cc.data();
-    p.k = kk.data();
+    p.n = n;
+    if (ngpus == 1) {
+      p.m = m; p.nnz = cls.row_ptr[(size_t)m];
+      p.row_ptr = cls.row_ptr.data();
+      p.col = cls.col.data();
+      p.k = cls.k.data();
+      p.class_id = nullptr; /* class i is row i */
+    } else {
+      auto& rp = shard_rp[(size_t)g];
+      auto& id = shard_id[(size_t)g];
+      auto& cc = shard_col[(size_t)g];
+      auto& kk = shard_k[(size_t)g];
+      rp.push_back(0);
+      for (int64_t i = g; i < m; i += ngpus) {
+        id.push_back(i);
+        kk.push_back(cls.k[(size_t)i]);
+        for (int64_t q = cls.row_ptr[(size_t)i]; q < cls.row_ptr[(size_t)i + 1]; ++q) cc.push_back(cls.col[(size_t)q]);
+        rp.push_back((int64_t)cc.size());
+      }
+      p.m = (int64_t)id.size(); p.nnz = rp.back();
+      p.row_ptr = rp.data();
+      p.col = cc.data();
+      p.k = kk.data();
+      p.class_id = id.data();
+    }
+    S.row0 = 0; S.row1 = p.m;
     p.weight = nullptr;
     p.len = l.data();
     p.alpha = alpha; p.beta = beta; p.class_id_base = 0;
-    p.class_id = id.data();
     int rc = mmq_create(&p, S.device, &S.h);
     if (rc) die(string("Error: mmq_create: ") + mmq_last_error(nullptr));
   }
@@ -435,19 +431,47 @@ int main(int argc, char** argv) {
     cerr << "done." << endl;
   }
 
-  /* ---- .k and .M (src/mmseq.cpp:682-695) */
+  /* ---- .k and .M (src/mmseq.cpp:682-695): one integer per line / "row<TAB>col" per nonzero.  The
+   * reference streams them through operator<< with endl; the same bytes are formatted here by all
+   * host threads into blocks that are written in order. */
+  {
+    auto put_int = [](string& out, int64_t v) {
+      char buf[24];
+      int len = 0;
+      if (v < 0) { out.push_back('-'); v = -v; }
+      do { buf[len++] = (char)('0' + v % 10); v /= 10; } while (v);
+      while (len) out.push_back(buf[--len]);
+    };
+    auto write_blocks = [&](const string& path, const string& head, int64_t rows, const function<void(string&, int64_t)>& row) {
+      FILE* f = fopen(path.c_str(), "wb");
+      if (!f) die("Error: cannot write " + path);
+      if (!head.empty()) fwrite(head.data(), 1, head.size(), f);
+      const int nt = (int)max<int64_t>(1, min<int64_t>(min(32u, max(1u, thread::hardware_concurrency())), rows / 65536));
+      vector<string> part((size_t)nt);
+      vector<thread> th;
+      for (int t = 0; t < nt; ++t)
+        th.emplace_back([&, t] {
+          string& out = part[(size_t)t];
+          const int64_t a = rows * t / nt, b = rows * (t + 1) / nt;
+          for (int64_t i = a; i < b; ++i) row(out, i);
+        });
+      for (auto& x : th) x.join();
+      for (const string& blk : part) fwrite(blk.data(), 1, blk.size(), f);
+      fclose(f);
+    };
+    write_blocks(output_base + ".k", "", m, [&](string& out, int64_t i) { put_int(out, cls.k[(size_t)i]); out.push_back('\n'); });
+    string head = "#";
+    for (int64_t t = 0; t < n; t++) { head += "\t"; head += hdr.names[(size_t)cls.col2hdr[(size_t)t]]; }
+    head += "\n";
+    write_blocks(output_base + ".M", head, m, [&](string& out, int64_t i) {
+      for (int64_t q = cls.row_ptr[(size_t)i]; q < cls.row_ptr[(size_t)i + 1]; ++q) {
+        put_int(out, i); out.push_back('\t'); put_int(out, cls.col[(size_t)q]); out.push_back('\n');
+      }
+    });
+  }
   ofstream ofs;
-  ofs.open((output_base + ".k").c_str());
-  for (int64_t i = 0; i < m; i++) ofs << cls.k[(size_t)i] << endl;
-  ofs.close(); ofs.clear();
-  ofs.open((output_base + ".M").c_str());
-  ofs << "#";
-  for (int64_t t = 0; t < n; t++) ofs << "\t" << hdr.names[(size_t)cls.col2hdr[(size_t)t]];
-  ofs << endl;
-  for (int64_t i = 0; i < m; ++i)
-    for (int64_t q = cls.row_ptr[(size_t)i]; q < cls.row_ptr[(size_t)i + 1]; ++q) ofs << i << "\t" << cls.col[(size_t)q] << endl;
-  ofs.close(); ofs.clear();
 
+  phase(".k and .M written");
   if (debug) { /* src/mmseq.cpp:697-731 */
     vector<vector<int>> counts_shared((size_t)n, vector<int>(100, 0));
     for (int64_t i = 0; i < m; ++i) {
