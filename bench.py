@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--layout", default="perfragment", choices=["perfragment", "perfragment_byclass", "perfragment_unsorted", "collapsed"])
     ap.add_argument("--first-appearance-columns", action="store_true", help="number transcripts as the reference does (src/mmseq.cpp:403) instead of in header order")
     ap.add_argument("--weights", action="store_true", help="fp32 per-hit weights (config 4's extension)")
+    ap.add_argument("--haplo", action="store_true", help="config 3: haplotype-specific transcriptome (every transcript as _A/_B copies: 360k haplo-transcripts, deep multi-mapping)")
     ap.add_argument("--transposed", action="store_true", help="materialise X + atomic-free transposed reduction")
     ap.add_argument("--cpu-sweeps", type=int, default=4, help="sweeps of the CPU baseline sample")
     ap.add_argument("--nccl-only", action="store_true", help="N > 1: exchange counts with ncclAllReduce instead of the fused peer-memory kernel")
@@ -68,7 +69,7 @@ def make_workload(args, rank, world):
     when world > 1 (one column space across shards)."""
     from mmseq_b200 import hostlib, synth
     t0 = time.time()
-    s = synth.Synth(SYNTH_SEED, args.transcripts, args.fragments, weights=args.weights, frag_seed=rank)
+    s = synth.Synth(SYNTH_SEED + (1 if args.haplo else 0), args.transcripts * (2 if args.haplo else 1), args.fragments, haplo=args.haplo, weights=args.weights, frag_seed=rank)
     t1 = time.time()
     layout = {"perfragment": hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH, "perfragment_byclass": hostlib.LAYOUT_PER_FRAGMENT_SORTED,
               "perfragment_unsorted": hostlib.LAYOUT_PER_FRAGMENT,
@@ -199,7 +200,7 @@ def run_reference(args, rank, world):
 
 def workload_config(args, h, world, sweeps_per_step=SWEEPS_PER_STEP):
     return {
-        "workload": f"C2-{args.layout}" + ("-weighted" if args.weights else ""),
+        "workload": ("C3-haplotype-" if getattr(args, "haplo", False) else "C2-") + args.layout + ("-weighted" if args.weights else ""),
         "transcripts": args.transcripts, "fragments_per_gpu": args.fragments, "fragments_total": args.fragments * world,
         "n_columns": int(h.n), "classes_per_gpu": int(h.m), "nnz_per_gpu": int(h.nnz), "distinct_classes_per_gpu": int(h.n_classes),
         "sweeps_per_step": sweeps_per_step, "trace_stride": SWEEPS_PER_STEP, "seed": SEED,
@@ -393,7 +394,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.fragments == N_C2 and args.transcripts == T_C2 and not args.weights:
         tj = json.load(open(tpath)).get(kernel_name)
-        if tj and tj.get("workload") == f"C2-{args.layout}":
+        if tj and tj.get("workload") == f"C2-{args.layout}" and not args.haplo:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]   # per launch, from one ncu --set full capture
     roofline = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
@@ -417,7 +418,7 @@ def main():
 
     # ---- the same sample in the reference's own representation (distinct classes + counts k, what the
     # host program feeds the GPU): class-plan kernel, reported beside the headline (N = 1 only)
-    if rank == 0 and world == 1 and args.layout == "perfragment" and not args.no_collapsed and not args.weights:
+    if rank == 0 and world == 1 and args.layout == "perfragment" and not args.no_collapsed and not args.weights and not args.haplo:
         line["collapsed_layout"] = collapsed_line(args, s, dev, stream, length_full=None)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores
