@@ -238,9 +238,16 @@ __global__ void k_cls_singletons(const int32_t* __restrict__ col1, const int32_t
 
 /* ------------------------------------------------------------------ host */
 
+/* host threads for a loop over `count` items (MMQ_PLAN_THREADS overrides: the tests run the threaded paths on small shards) */
+static int cls_threads(int64_t count) {
+  const char* e = getenv("MMQ_PLAN_THREADS");
+  if (e && atoi(e) > 0) return (int)std::max<int64_t>(1, std::min<int64_t>(atoi(e), count));
+  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 16u), count / 65536));
+}
+
 template <typename F>
 static void cls_parallel_for(int64_t count, F&& f) {
-  const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 16u), count / 65536));
+  const int nt = cls_threads(count);
   if (nt <= 1) { f((int64_t)0, count); return; }
   std::vector<std::thread> th;
   for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { f(count * t / nt, count * (t + 1) / nt); });
@@ -342,26 +349,60 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   static_assert(MMQ_CAT_K / MMQ_CAT_GROUP <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
   struct Ord { int32_t i; int16_t key; uint8_t full, tail; }; /* key: of the partial slot (tail draws) when there is one */
   std::vector<Ord> order((size_t)small_classes);
+  /* parallel stable counting sort: thread t owns classes [m t / T, m (t+1) / T) and, per first member, a
+   * contiguous piece of that member's bucket */
+  const int T = cls_threads(std::min<int64_t>(m, std::max<int64_t>(small_classes, 1)));
+  auto on_threads = [&](auto&& fn) {
+    if (T == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back([&, t] { fn(t); });
+    for (auto& x : th) x.join();
+  };
   {
-    std::vector<int64_t> first_pos((size_t)h->n + 2, 0);
-    for (int64_t i = 0; i < m; ++i)
-      if (key16[i] >= 0) ++first_pos[(size_t)col[rp[i]] + 1];
-    for (int64_t t = 0; t <= h->n; ++t) first_pos[t + 1] += first_pos[t];
-    for (int64_t i = 0; i < m; ++i)
-      if (key16[i] >= 0) order[(size_t)first_pos[col[rp[i]]]++] = Ord{(int32_t)i, key16[i], (uint8_t)(kk[i] / MMQ_CAT_GROUP), (uint8_t)(kk[i] % MMQ_CAT_GROUP)};
+    const size_t nb = (size_t)h->n + 1;
+    std::vector<int64_t> hist((size_t)T * nb, 0); /* [thread][first member] */
+    on_threads([&](int t) {
+      int64_t* c = hist.data() + (size_t)t * nb;
+      for (int64_t i = m * t / T; i < m * (t + 1) / T; ++i)
+        if (key16[i] >= 0) ++c[col[rp[i]]];
+    });
+    int64_t run = 0;
+    for (size_t v = 0; v < nb; ++v) /* exclusive prefix in (member, thread) order */
+      for (int t = 0; t < T; ++t) { const int64_t c = hist[(size_t)t * nb + v]; hist[(size_t)t * nb + v] = run; run += c; }
+    on_threads([&](int t) {
+      int64_t* c = hist.data() + (size_t)t * nb;
+      for (int64_t i = m * t / T; i < m * (t + 1) / T; ++i)
+        if (key16[i] >= 0) order[(size_t)c[col[rp[i]]]++] = Ord{(int32_t)i, key16[i], (uint8_t)(kk[i] / MMQ_CAT_GROUP), (uint8_t)(kk[i] % MMQ_CAT_GROUP)};
+    });
   }
   tick("order by first member");
-  /* first slot of every small class within each of its (at most two) keys, in placement order */
+  /* first slot of every small class within each of its (at most two) keys, in placement order: thread t
+   * takes a contiguous piece of the order; the keys' running positions are prefixed over the threads */
   std::vector<int64_t> slot_full((size_t)small_classes), slot_tail((size_t)small_classes);
   {
-    std::vector<int64_t> next(key_slot);
-    for (int64_t o = 0; o < small_classes; ++o) {
-      const Ord& e = order[(size_t)o];
-      const int d = e.key / MMQ_CLS_NQ;
-      slot_full[(size_t)o] = next[d * MMQ_CLS_NQ + 0];
-      next[d * MMQ_CLS_NQ + 0] += e.full;
-      slot_tail[(size_t)o] = e.tail ? next[e.key]++ : -1; /* -1: k is a multiple of 64, no partial slot */
+    std::vector<int64_t> used((size_t)T * (NKEY + 1), 0); /* [thread][key]: slots the piece needs */
+    on_threads([&](int t) {
+      int64_t* u = used.data() + (size_t)t * (NKEY + 1);
+      for (int64_t o = small_classes * t / T; o < small_classes * (t + 1) / T; ++o) {
+        const Ord& e = order[(size_t)o];
+        u[(e.key / MMQ_CLS_NQ) * MMQ_CLS_NQ + 0] += e.full;
+        if (e.tail) ++u[e.key];
+      }
+    });
+    for (int q = 0; q <= NKEY; ++q) {
+      int64_t run = key_slot[q];
+      for (int t = 0; t < T; ++t) { const int64_t c = used[(size_t)t * (NKEY + 1) + q]; used[(size_t)t * (NKEY + 1) + q] = run; run += c; }
     }
+    on_threads([&](int t) {
+      int64_t* next = used.data() + (size_t)t * (NKEY + 1);
+      for (int64_t o = small_classes * t / T; o < small_classes * (t + 1) / T; ++o) {
+        const Ord& e = order[(size_t)o];
+        const int d = e.key / MMQ_CLS_NQ;
+        slot_full[(size_t)o] = next[d * MMQ_CLS_NQ + 0];
+        next[d * MMQ_CLS_NQ + 0] += e.full;
+        slot_tail[(size_t)o] = e.tail ? next[e.key]++ : -1; /* -1: k is a multiple of 64, no partial slot */
+      }
+    });
   }
   tick("slots");
   std::unique_ptr<int32_t[]> pcol(new int32_t[(size_t)std::max<int64_t>(packed, 1)]); /* every entry is written below */

@@ -190,6 +190,21 @@ static void write_pcts(ostream& ofs, const double* v, size_t np, char last) {
   }
 }
 
+/* Rows of a table formatted by all host threads (each into a string stream with the file stream's
+ * formatting state), written in order: the bytes are those of one loop over `ofs`. */
+static void write_rows(ostream& ofs, int64_t rows, const function<void(ostream&, int64_t)>& row) {
+  const int T = (int)max<int64_t>(1, min<int64_t>(min(32u, max(1u, thread::hardware_concurrency())), rows / 64));
+  if (T == 1) { for (int64_t r = 0; r < rows; ++r) row(ofs, r); return; }
+  vector<ostringstream> part((size_t)T);
+  vector<thread> th;
+  for (int t = 0; t < T; ++t) {
+    part[(size_t)t].copyfmt(ofs);
+    th.emplace_back([&, t] { for (int64_t r = rows * t / T; r < rows * (t + 1) / T; ++r) row(part[(size_t)t], r); });
+  }
+  for (auto& x : th) x.join();
+  for (auto& p : part) { const string blk = p.str(); ofs.write(blk.data(), (streamsize)blk.size()); }
+}
+
 struct Shard {
   int device = 0;
   int64_t row0 = 0, row1 = 0;
@@ -763,7 +778,7 @@ int main(int argc, char** argv) {
   write_pcts(ofs, percentiles.data(), NP, '\t');
   ofs << "percentiles_proportion";
   write_pcts(ofs, percentiles.data(), NP, '\n');
-  for (int64_t hI = 0; hI < T; ++hI) {
+  write_rows(ofs, T, [&](ostream& ofs, int64_t hI) {
     const string& name = hdr.names[(size_t)hI];
     const int32_t c = cls.hdr2col[(size_t)hI];
     const size_t ntr = hdr.gene_members[(size_t)hdr.gene_of[(size_t)hI]].size();
@@ -782,7 +797,7 @@ int main(int argc, char** argv) {
       write_pcts(ofs, pct_simu.data() + u * NP, NP, '\t');
       write_pcts(ofs, pct_prop_simu.data() + u * NP, NP, '\n');
     }
-  }
+  });
   ofs.close(); ofs.clear();
 
   /* ---- .identical.mmseq (:1556-1613) */
@@ -825,7 +840,7 @@ int main(int argc, char** argv) {
   ofs << "feature_id\tlog_mu\tsd\tmcse\tiact\teffective_length\ttrue_length\tunique_hits\tntranscripts\tobserved\t";
   ofs << "percentiles";
   write_pcts(ofs, percentiles.data(), NP, '\n');
-  for (int64_t g = 0; g < G; ++g) {
+  write_rows(ofs, G, [&](ostream& ofs, int64_t g) {
     bool obs = false;
     for (int32_t hidx : hdr.gene_members[(size_t)g]) if (cls.hdr2col[(size_t)hidx] >= 0) { obs = true; break; }
     if (obs) {
@@ -837,7 +852,7 @@ int main(int argc, char** argv) {
           << "\t" << 1 << "\t" << gene_lengths[(size_t)g] << "\t" << "NA" << "\t" << "0" << "\t" << hdr.gene_members[(size_t)g].size() << "\t" << "0" << "\t";
     }
     write_pcts(ofs, Sg.pct.data() + (size_t)g * NP, NP, '\n');
-  }
+  });
   ofs.close(); ofs.clear();
 
   cout << "done." << endl;
