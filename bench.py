@@ -119,7 +119,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.02)
+                time.sleep(0.005)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 

@@ -136,8 +136,9 @@ MMQ_HD double mmq_uniform(mmq_rng* g) {
  * four classes.  All three steps are exact, so host and device agree bit for bit. */
 MMQ_HD double mmq_uniform32(uint32_t w) {
 #if defined(__CUDA_ARCH__)
-  /* the same number without a conversion instruction: (1 + w 2^-32) - 1 + 2^-33, every step exact */
-  return (__hiloint2double((int)(0x3ff00000u | (w >> 12)), (int)(w << 20)) - 1.0) + 1.16415321826934814453125e-10;
+  /* the same number without a conversion instruction and with one addition: (1 + w 2^-32) - (1 - 2^-33)
+   * = (2w + 1) 2^-33 has 33 significant bits, so the subtraction is exact */
+  return __hiloint2double((int)(0x3ff00000u | (w >> 12)), (int)(w << 20)) - 0.99999999988358467817306518554688;
 #else
   return ((double)w + 0.5) * 2.3283064365386962890625e-10; /* 2^-32 */
 #endif
