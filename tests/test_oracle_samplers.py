@@ -86,20 +86,28 @@ def test_alloc_row_is_multinomial_and_conserves():
     assert (orc.draw_alloc(5, 10, np.zeros(3), 4)[:, 2] == 4).all()
 
 
-def test_alloc_matches_gsl_style_multinomial_in_distribution():
+@pytest.mark.parametrize("k,reps", [(30, 100000), (700, 20000), (8192, 4000), (8193, 4000)])
+def test_alloc_matches_gsl_style_multinomial_in_distribution(k, reps):
+    """Every regime of mmq_alloc_row against the GSL-style chain of binomials (the reference's
+    gsl_ran_multinomial, src/mmseq.cpp:880): categorical draws with 32-bit uniforms four to a Philox
+    block (k <= MMQ_CAT_K = 8192, across several groups of 64 draws), binomial chain above."""
     p = np.array([0.5, 2.5, 1.0, 4.0])
-    k = 30
-    a = orc.draw_alloc(9, 100000, p, k)
-    b = orc.gsl_multinomial(9, 100000, p, k)
-    assert (b.sum(axis=1) == k).all()
+    a = orc.draw_alloc(9, reps, p, k)
+    b = orc.gsl_multinomial(9, reps, p, k)
+    assert (a.sum(axis=1) == k).all() and (b.sum(axis=1) == k).all()
     for j in range(len(p)):
-        ha = np.bincount(a[:, j], minlength=k + 1); hb = np.bincount(b[:, j], minlength=k + 1)
+        if k <= 100:
+            ha = np.bincount(a[:, j], minlength=k + 1); hb = np.bincount(b[:, j], minlength=k + 1)
+        else:   # coarse bins around the mean for the large counts
+            q = p[j] / p.sum()
+            edges = k * q + np.sqrt(k * q * (1 - q)) * np.linspace(-3, 3, 13)
+            ha = np.histogram(a[:, j], bins=np.concatenate([[-1], edges, [k + 1]]))[0]; hb = np.histogram(b[:, j], bins=np.concatenate([[-1], edges, [k + 1]]))[0]
         keep = (ha + hb) > 20
         assert stats.chi2_contingency(np.vstack([ha[keep], hb[keep]]))[1] > 1e-5
     # covariance structure: cov(x_i, x_j) = -k p_i p_j
     q = p / p.sum()
-    cov = np.cov(a.T)
-    assert np.allclose(cov, k * (np.diag(q) - np.outer(q, q)), atol=0.15)
+    cov = np.cov(a.T) / k
+    assert np.allclose(cov, np.diag(q) - np.outer(q, q), atol=0.15 / 30 if k == 30 else 0.02)
 
 
 @pytest.mark.parametrize("n,p", [(20, 0.3), (500, 0.2), (100000, 0.7)])
