@@ -9,23 +9,30 @@
  *   d == 1              nothing: x = k is deterministic, summed once into seg_base[] (the Gamma
  *                       kernel restarts counts[] from it);
  *   k <= MMQ_CAT_K and  the "small" set: k categorical draws, four per Philox block
- *   d <= MMQ_CLS_DMAX   (include/mmq_sampler.h).  Classes are ordered by (d, blocks) and packed
- *                       in chunks of 32 — one class per lane, member-major inside the chunk
+ *   d <= MMQ_CLS_DMAX   (include/mmq_sampler.h).  A class becomes ceil(k / 64) SLOTS of at most 64
+ *                       draws (16 blocks), so a class with thousands of fragments is shared out
+ *                       between lanes.  Slots are ordered by (d, blocks, first member) and packed
+ *                       in chunks of 32 — one slot per lane, member-major inside the chunk
  *                       (entry (j, lane) at chunk_base + 32 j + lane), so that every column load
  *                       of a warp is one fully used 128-byte line and no row pointers, no
  *                       shared-memory staging and no shuffles are needed.  A lane gathers its d
  *                       mu once, keeps the running sums S_j in registers and, per draw, counts
  *                       A_j += (u S_{d-1} < S_j); x_j = A_j - A_{j-1} (S is non-decreasing, so
  *                       that is "first j with target < S_j").  All lanes of a warp have the same
- *                       d and (almost always) the same number of blocks: no divergence;
- *   the rest            (k > MMQ_CAT_K: conditional-binomial chain; or very long classes) a small
- *                       sub-CSR handed to k_alloc on a second stream, concurrently.
+ *                       d and (almost always) the same number of blocks: no divergence.  The
+ *                       order by first member keeps the mu gathers of a warp, and of the warps of
+ *                       an SM, in neighbouring cache lines;
+ *   the rest            (k > MMQ_CAT_K: conditional-binomial chain; or more than 64 members) a
+ *                       small sub-CSR handed to k_alloc, one class per warp, on a second stream.
+ *
+ * Two instances of the kernel (class sizes 2..8 in 64 registers, 9..16 and a generic loop up to 64
+ * in 96) run concurrently on two streams.
  *
  * The integers are those of mmq_alloc_row on the same (seed, class id, sweep) — bit for bit
  * (tests/test_gpu_parity.py) — because the order of the floating-point sums is the same.
  *
- * Algorithmic HBM bytes per sweep: 4 B per packed column slot + 5 B per class slot (k as one
- * byte, low word of the class id) of the small set + the sub-CSR of the rest.
+ * Algorithmic HBM bytes per sweep: 4 B per packed column slot + 6 B per slot (draw count and slot
+ * number in two bytes, low word of the class id) of the small set + the sub-CSR of the rest.
  */
 #include <algorithm>
 #include <chrono>
@@ -47,7 +54,7 @@
 #define MMQ_CLS_NQ 17    /* sort positions inside a run of equal d: 16 - blocks (k >= 2), then 16: k == 1 */
 
 struct mmq_cls_run {
-  int64_t e0;     /* pcol offset of the run's first chunk */
+  int64_t e0;     /* offset in pcol of the run's first chunk */
   int32_t chunk0; /* first chunk of the run in the global numbering */
   int32_t d;      /* class size */
 };
