@@ -44,20 +44,9 @@
 #include <thread>
 #include <vector>
 
+#include "mmq_cls_plan.h"
 #include "mmq_device.cuh"
 #include "mmq_internal.h"
-
-#define MMQ_CLS_DMAX 64  /* longer classes go to the general kernel */
-#define MMQ_CLS_DLO 8    /* class sizes 2..8: the 64-register instance (32 warps per SM) */
-#define MMQ_CLS_DREG 16  /* class sizes up to this are register-resident template instances */
-#define MMQ_CLS_WARPS 4
-#define MMQ_CLS_NQ 17    /* sort positions inside a run of equal d: 16 - blocks (k >= 2), then 16: k == 1 */
-
-struct mmq_cls_run {
-  int64_t e0;     /* offset in pcol of the run's first chunk */
-  int32_t chunk0; /* first chunk of the run in the global numbering */
-  int32_t d;      /* class size */
-};
 
 /* Philox block b of a class's own ALLOC stream */
 __device__ __forceinline__ void cls_block(uint32_t (&wd)[4], uint32_t cid, uint32_t cid_hi, uint32_t sweep, uint32_t b, uint32_t seed) {
@@ -245,22 +234,6 @@ __global__ void k_cls_singletons(const int32_t* __restrict__ col1, const int32_t
 
 /* ------------------------------------------------------------------ host */
 
-/* host threads for a loop over `count` items (MMQ_PLAN_THREADS overrides: the tests run the threaded paths on small shards) */
-static int cls_threads(int64_t count) {
-  const char* e = getenv("MMQ_PLAN_THREADS");
-  if (e && atoi(e) > 0) return (int)std::max<int64_t>(1, std::min<int64_t>(atoi(e), count));
-  return (int)std::max<int64_t>(1, std::min<int64_t>(std::min<unsigned>(std::thread::hardware_concurrency(), 16u), count / 65536));
-}
-
-template <typename F>
-static void cls_parallel_for(int64_t count, F&& f) {
-  const int nt = cls_threads(count);
-  if (nt <= 1) { f((int64_t)0, count); return; }
-  std::vector<std::thread> th;
-  for (int t = 0; t < nt; ++t) th.emplace_back([&, t] { f(count * t / nt, count * (t + 1) / nt); });
-  for (auto& x : th) x.join();
-}
-
 template <typename T>
 static int cls_upload(mmq_handle* h, T** dst, const std::vector<T>& v) {
   int rc = mmq_dev_alloc(h, (void**)dst, sizeof(T) * std::max<size_t>(v.size(), 1));
@@ -273,203 +246,21 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   h->cls_ready = false;
   static const bool off = [] { const char* e = getenv("MMQ_CLS_OFF"); return e && atoi(e) != 0; }();
   if (off || !h->has_k || h->has_w || h->m == 0) return MMQ_OK;
-  const int64_t m = h->m;
-  const int64_t* rp = p->row_ptr;
-  const int32_t* col = p->col;
-  const int32_t* kk = p->k;
-  static const bool timing = [] { const char* e = getenv("MMQ_CREATE_TIMING"); return e && atoi(e) != 0; }();
-  auto t_last = std::chrono::steady_clock::now();
+  mmq_cls_host_plan P;
+  if (!mmq_cls_build_host(h->n, h->m, p->row_ptr, p->col, p->k, p->class_id, p->class_id_base, P)) return MMQ_OK;
+  const auto t_up = std::chrono::steady_clock::now();
+  const std::vector<mmq_cls_run>& runs = P.runs;
+  const std::vector<uint16_t>& pk = P.pk;
+  const std::vector<uint32_t>& pcid = P.pcid;
+  const std::vector<int64_t>&o_rp = P.o_rp, &o_cid = P.o_cid, &o_tiles = P.o_tiles;
+  const std::vector<int32_t>&o_col = P.o_col, &o_k = P.o_k, &s_col = P.s_col, &s_k = P.s_k;
+  const std::unique_ptr<int32_t[]>& pcol = P.pcol;
+  const int64_t packed = P.packed, chunks = P.chunks, chunks_lo = P.chunks_lo, small_classes = P.small_classes, n_rest = P.n_rest, nnz_rest = P.nnz_rest;
+  const uint32_t cid_hi = P.cid_hi;
   auto tick = [&](const char* what) {
-    if (!timing) return;
-    const auto now = std::chrono::steady_clock::now();
-    fprintf(stderr, "[mmq_cls_plan] %-26s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
-    t_last = now;
+    static const bool timing = [] { const char* e = getenv("MMQ_CREATE_TIMING"); return e && atoi(e) != 0; }();
+    if (timing) fprintf(stderr, "[mmq_cls_plan] %-26s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_up).count());
   };
-  auto cid_of = [&](int64_t i) -> uint64_t { return (uint64_t)(p->class_id ? p->class_id[i] : p->class_id_base + i); };
-  const uint32_t cid_hi = (uint32_t)(cid_of(0) >> 32);
-
-  /* classify (host threads).  Slots of the small set are keyed (d, q): q = 16 - blocks for classes with
-   * k >= 2 (a run of equal d starts with its most expensive slots), q = 16 for single-fragment classes
-   * (whole warps of them take the one-draw path).  key16[i]: the key of the class's last (partial) slot,
-   * or of its full slots when k is a multiple of 64; -1 singleton / empty, -2 rest. */
-  const int NKEY = (MMQ_CLS_DMAX + 1) * MMQ_CLS_NQ;
-  std::vector<int16_t> key16(m);
-  struct Tally { std::vector<int64_t> key_count; int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small = 0; bool ok = true; };
-  std::vector<Tally> tally;
-  std::mutex tally_mu;
-  cls_parallel_for(m, [&](int64_t a0, int64_t b0) {
-    Tally t;
-    t.key_count.assign(NKEY + 1, 0);
-    for (int64_t i = a0; i < b0; ++i) {
-      const int64_t d = rp[i + 1] - rp[i];
-      const int64_t kv = kk[i];
-      if ((uint32_t)(cid_of(i) >> 32) != cid_hi || kv < 0) t.ok = false;
-      if (d == 1 || kv <= 0) { key16[i] = -1; ++t.n_single; } /* k == 0: nothing to allocate */
-      else if (kv <= MMQ_CAT_K && d <= MMQ_CLS_DMAX) {
-        ++t.small;
-        if (kv == 1) { key16[i] = (int16_t)(d * MMQ_CLS_NQ + 16); ++t.key_count[key16[i]]; }
-        else {
-          const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
-          t.key_count[d * MMQ_CLS_NQ + 0] += full; /* 16 blocks */
-          key16[i] = (int16_t)(d * MMQ_CLS_NQ + (tail ? 16 - (int)((tail + 3) >> 2) : 0));
-          if (tail) ++t.key_count[key16[i]];
-        }
-      } else { key16[i] = -2; ++t.n_rest; t.nnz_rest += d; }
-    }
-    std::lock_guard<std::mutex> g(tally_mu);
-    tally.push_back(std::move(t));
-  });
-  tick("classify");
-  std::vector<int64_t> key_count(NKEY + 1, 0);
-  int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small_classes = 0;
-  for (const Tally& t : tally) {
-    if (!t.ok) return MMQ_OK; /* class ids spread over several 2^32 blocks (or k < 0): the general kernel handles it */
-    for (int q = 0; q <= NKEY; ++q) key_count[q] += t.key_count[q];
-    n_single += t.n_single; n_rest += t.n_rest; nnz_rest += t.nnz_rest; small_classes += t.small;
-  }
-
-  /* runs of equal d, chunks of 32 slots */
-  std::vector<mmq_cls_run> runs;
-  std::vector<int64_t> key_slot(NKEY + 1, 0); /* first slot (global numbering, 32 per chunk) of each key */
-  std::vector<int64_t> run_slots; /* slots in use per run: the rest of its last chunk is padding */
-  int64_t chunks = 0, packed = 0, chunks_lo = 0;
-  for (int d = 2; d <= MMQ_CLS_DMAX; ++d) {
-    int64_t cnt = 0;
-    for (int q = 0; q < MMQ_CLS_NQ; ++q) { key_slot[d * MMQ_CLS_NQ + q] = chunks * 32 + cnt; cnt += key_count[d * MMQ_CLS_NQ + q]; }
-    if (cnt == 0) continue;
-    mmq_cls_run r;
-    r.e0 = packed; r.chunk0 = (int32_t)chunks; r.d = d;
-    runs.push_back(r);
-    run_slots.push_back(cnt);
-    const int64_t nch = (cnt + 31) / 32;
-    chunks += nch;
-    packed += nch * 32 * d;
-    if (d <= MMQ_CLS_DLO) chunks_lo = chunks;
-    if (chunks > 0x7fff0000ll) return MMQ_OK;
-  }
-  std::vector<int32_t> run_of_d(MMQ_CLS_DMAX + 1, -1);
-  for (size_t r = 0; r < runs.size(); ++r) run_of_d[runs[r].d] = (int32_t)r;
-
-  /* Within a key the classes are placed by their first member (a stable counting sort): members are
-   * ascending and the isoforms of a gene are neighbours in the header, so the lanes of a warp and the
-   * warps of an SM gather neighbouring mu — L1 hits instead of one L2 sector per 8-byte gather. */
-  static_assert(MMQ_CAT_K / MMQ_CAT_GROUP <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
-  struct Ord { int32_t i; int16_t key; uint8_t full, tail; }; /* key: of the partial slot (tail draws) when there is one */
-  std::vector<Ord> order((size_t)small_classes);
-  /* parallel stable counting sort: thread t owns classes [m t / T, m (t+1) / T) and, per first member, a
-   * contiguous piece of that member's bucket */
-  const int T = cls_threads(std::min<int64_t>(m, std::max<int64_t>(small_classes, 1)));
-  auto on_threads = [&](auto&& fn) {
-    if (T == 1) { fn(0); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; ++t) th.emplace_back([&, t] { fn(t); });
-    for (auto& x : th) x.join();
-  };
-  {
-    const size_t nb = (size_t)h->n + 1;
-    std::vector<int64_t> hist((size_t)T * nb, 0); /* [thread][first member] */
-    on_threads([&](int t) {
-      int64_t* c = hist.data() + (size_t)t * nb;
-      for (int64_t i = m * t / T; i < m * (t + 1) / T; ++i)
-        if (key16[i] >= 0) ++c[col[rp[i]]];
-    });
-    int64_t run = 0;
-    for (size_t v = 0; v < nb; ++v) /* exclusive prefix in (member, thread) order */
-      for (int t = 0; t < T; ++t) { const int64_t c = hist[(size_t)t * nb + v]; hist[(size_t)t * nb + v] = run; run += c; }
-    on_threads([&](int t) {
-      int64_t* c = hist.data() + (size_t)t * nb;
-      for (int64_t i = m * t / T; i < m * (t + 1) / T; ++i)
-        if (key16[i] >= 0) order[(size_t)c[col[rp[i]]]++] = Ord{(int32_t)i, key16[i], (uint8_t)(kk[i] / MMQ_CAT_GROUP), (uint8_t)(kk[i] % MMQ_CAT_GROUP)};
-    });
-  }
-  tick("order by first member");
-  /* first slot of every small class within each of its (at most two) keys, in placement order: thread t
-   * takes a contiguous piece of the order; the keys' running positions are prefixed over the threads */
-  std::vector<int64_t> slot_full((size_t)small_classes), slot_tail((size_t)small_classes);
-  {
-    std::vector<int64_t> used((size_t)T * (NKEY + 1), 0); /* [thread][key]: slots the piece needs */
-    on_threads([&](int t) {
-      int64_t* u = used.data() + (size_t)t * (NKEY + 1);
-      for (int64_t o = small_classes * t / T; o < small_classes * (t + 1) / T; ++o) {
-        const Ord& e = order[(size_t)o];
-        u[(e.key / MMQ_CLS_NQ) * MMQ_CLS_NQ + 0] += e.full;
-        if (e.tail) ++u[e.key];
-      }
-    });
-    for (int q = 0; q <= NKEY; ++q) {
-      int64_t run = key_slot[q];
-      for (int t = 0; t < T; ++t) { const int64_t c = used[(size_t)t * (NKEY + 1) + q]; used[(size_t)t * (NKEY + 1) + q] = run; run += c; }
-    }
-    on_threads([&](int t) {
-      int64_t* next = used.data() + (size_t)t * (NKEY + 1);
-      for (int64_t o = small_classes * t / T; o < small_classes * (t + 1) / T; ++o) {
-        const Ord& e = order[(size_t)o];
-        const int d = e.key / MMQ_CLS_NQ;
-        slot_full[(size_t)o] = next[d * MMQ_CLS_NQ + 0];
-        next[d * MMQ_CLS_NQ + 0] += e.full;
-        slot_tail[(size_t)o] = e.tail ? next[e.key]++ : -1; /* -1: k is a multiple of 64, no partial slot */
-      }
-    });
-  }
-  tick("slots");
-  std::unique_ptr<int32_t[]> pcol(new int32_t[(size_t)std::max<int64_t>(packed, 1)]); /* every entry is written below */
-  std::vector<uint16_t> pk((size_t)chunks * 32, 0);
-  std::vector<uint32_t> pcid((size_t)chunks * 32, 0u);
-  for (size_t r = 0; r < runs.size(); ++r) { /* padding slots of a run's last chunk: the sentinel column (mu[n] == 0), no draws */
-    const int d = runs[r].d;
-    const int64_t used = run_slots[r], nch = (used + 31) / 32;
-    int32_t* last = pcol.get() + runs[r].e0 + (nch - 1) * 32 * d;
-    for (int lane = (int)(used - (nch - 1) * 32); lane < 32; ++lane)
-      for (int j = 0; j < d; ++j) last[32 * j + lane] = (int32_t)h->n;
-  }
-  cls_parallel_for(small_classes, [&](int64_t a0, int64_t b0) {
-    for (int64_t o = a0; o < b0; ++o) {
-      const Ord& e = order[(size_t)o];
-      const int64_t i = e.i;
-      const int d = e.key / MMQ_CLS_NQ;
-      const mmq_cls_run& r = runs[run_of_d[d]];
-      const int32_t* src = col + rp[i];
-      const uint32_t cid = (uint32_t)cid_of(i);
-      auto put = [&](int64_t s, int draws, int slot_no) {
-        const int64_t ch = s >> 5;
-        int32_t* dst = pcol.get() + r.e0 + (ch - r.chunk0) * 32 * d + (s & 31);
-        for (int j = 0; j < d; ++j) dst[32 * j] = src[j];
-        pk[s] = (uint16_t)(draws | (slot_no << 8));
-        pcid[s] = cid;
-      };
-      for (int q = 0; q < (int)e.full; ++q) put(slot_full[(size_t)o] + q, MMQ_CAT_GROUP, q);
-      if (e.tail) put(slot_tail[(size_t)o], (int)e.tail, (int)e.full);
-    }
-  });
-
-  tick("fill");
-  /* the rest: a sub-CSR for the general kernel, longest chains first, ONE class per warp tile (a
-   * chain of binomials is serial: what matters is when the slowest warp ends, not lane use) */
-  std::vector<int64_t> rest;
-  rest.reserve((size_t)n_rest);
-  for (int64_t i = 0; i < m; ++i)
-    if (key16[i] == -2) rest.push_back(i);
-  std::stable_sort(rest.begin(), rest.end(), [&](int64_t a, int64_t b) { return rp[a + 1] - rp[a] > rp[b + 1] - rp[b]; });
-  std::vector<int64_t> o_rp((size_t)n_rest + 1, 0), o_cid((size_t)n_rest), o_tiles((size_t)n_rest + 1);
-  std::vector<int32_t> o_col((size_t)nnz_rest + 4, 0), o_k((size_t)n_rest);
-  for (int64_t q = 0; q < n_rest; ++q) {
-    const int64_t i = rest[q];
-    const int64_t d = rp[i + 1] - rp[i];
-    memcpy(o_col.data() + o_rp[q], col + rp[i], sizeof(int32_t) * (size_t)d);
-    o_rp[q + 1] = o_rp[q] + d;
-    o_k[q] = kk[i];
-    o_cid[q] = (int64_t)cid_of(i);
-    o_tiles[q] = q;
-  }
-  o_tiles[n_rest] = n_rest;
-
-  /* singletons: constant counts */
-  std::vector<int32_t> s_col, s_k;
-  s_col.reserve((size_t)n_single); s_k.reserve((size_t)n_single);
-  for (int64_t i = 0; i < m; ++i)
-    if (key16[i] == -1 && kk[i] > 0) { s_col.push_back(col[rp[i]]); s_k.push_back(kk[i]); }
-
-  tick("rest, singletons");
   int rc;
   if ((rc = mmq_dev_alloc(h, (void**)&h->cls_pcol, sizeof(int32_t) * (size_t)std::max<int64_t>(packed, 1)))) return rc;
   if (packed > 0) MMQ_CUDA(h, cudaMemcpyAsync(h->cls_pcol, pcol.get(), sizeof(int32_t) * (size_t)packed, cudaMemcpyHostToDevice, h->stream));

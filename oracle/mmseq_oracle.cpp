@@ -52,6 +52,8 @@
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
+
+#include "../mmseq_b200/csrc/mmq_cls_plan.h" /* the product's host-side class plan: built and replayed here for the CPU tests */
 #endif
 
 #include "../include/mmq_sampler.h"
@@ -437,6 +439,23 @@ void orc_uh_literal(int64_t m, const int64_t* rp, const int32_t* col, const int3
       if (uniq) out[s] += k ? k[i] : 1;
     }
   }
+}
+
+
+/* The product's class plan (mmseq_b200/csrc/mmq_cls_plan.h: how mmq_create re-orders a collapsed
+ * shard into slots and chunks for k_alloc_cls) built on the CPU and replayed with the shared
+ * sampler: the counts must equal orc_sweep_replay's.  Lets the CPU test suite check the host side
+ * of the plan (slot splitting, ordering, padding, the rest / singleton lists) without a GPU.
+ * stats: [applied, small classes, column slots, class slots, rest classes, rest entries]. */
+int orc_cls_plan_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k, const int64_t* class_id,
+                        int64_t class_id_base, const double* mu, uint32_t seed, uint32_t sweep, int32_t* counts, int64_t* stats) {
+  mmq_cls_host_plan P;
+  if (m == 0 || !mmq_cls_build_host(n, m, rp, col, k, class_id, class_id_base, P)) { if (stats) stats[0] = 0; return 1; }
+  mmq_cls_replay_host(P, n, mu, seed, sweep, counts);
+  if (stats) {
+    stats[0] = 1; stats[1] = P.small_classes; stats[2] = P.packed; stats[3] = P.chunks * 32; stats[4] = P.n_rest; stats[5] = P.nnz_rest;
+  }
+  return 0;
 }
 
 } /* extern "C" */

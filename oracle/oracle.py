@@ -51,6 +51,8 @@ def lib():
         L.orc_sweep_replay.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, u32, i64, vp, vp, vp, i32]
         L.orc_sweep_replay_ids.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, u32, vp, vp, vp, vp, i32]
         L.orc_gamma_replay.argtypes = [i64, vp, vp, dbl, dbl, u32, u32, vp]
+        L.orc_cls_plan_replay.restype = C.c_int
+        L.orc_cls_plan_replay.argtypes = [i64, i64, vp, vp, vp, vp, i64, vp, u32, u32, vp, vp]
         L.orc_gibbs_replay.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, i64, i64, i32, i32, vp, vp]
         L.orc_prior_replay.argtypes = [i64, vp, vp, dbl, dbl, u32, i32, vp]
         L.orc_gsl_binomial.argtypes = [u32, i64, i64, dbl, vp]
@@ -168,6 +170,18 @@ class Problem:
         lib().orc_sweep_replay(m, self.n, _p(rp), _p(col), _p(k), _p(w), _p(self.len), self.alpha, self.beta,
                                seed, sweep, class_id_base, _p(mu), _p(x), _p(counts), int(do_gamma))
         return x, counts, mu
+
+    def cls_plan_replay(self, mu, seed, sweep, class_id=None, class_id_base=0):
+        """Counts of one sweep through the product's class plan built on the CPU (collapsed shards):
+        returns (counts, stats dict) or (None, None) when the plan does not apply."""
+        mu = np.array(mu, np.float64)
+        cid = None if class_id is None else _c(class_id, np.int64)
+        counts = np.zeros(self.n, np.int32); stats = np.zeros(6, np.int64)
+        rc = lib().orc_cls_plan_replay(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(cid), class_id_base,
+                                       _p(mu), seed, sweep, _p(counts), _p(stats))
+        if rc:
+            return None, None
+        return counts, dict(zip(["in_use", "small_classes", "packed_slots", "class_slots", "rest_classes", "rest_nnz"], [int(v) for v in stats]))
 
     def sweep_replay_ids(self, mu, seed, sweep, class_id, do_gamma=True):
         """One sweep with explicit Philox counters per class (any class order)."""
