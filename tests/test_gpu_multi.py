@@ -74,23 +74,28 @@ def test_two_ranks_reproduce_single_gpu_chain(use_p2p):
         assert np.array_equal(r[6], tr) and np.array_equal(r[7], c) and np.array_equal(r[8], mu_dbg)
 
 
-def test_single_process_peer_attach_matches_single_gpu():
+@pytest.mark.parametrize("weighted", [False, True])
+def test_single_process_peer_attach_matches_single_gpu(weighted):
     """mmq_p2p_attach_local (what the host program uses for -gpus N): two handles in one process,
-    sweeps issued from two threads; the fused peer-memory Gamma kernel gives the single-GPU chain."""
+    sweeps issued from two threads; the fused peer-memory Gamma kernel gives the single-GPU chain.
+    weighted = BASELINE config 4 at parity-test size: per-fragment shards with fp32 per-hit weights
+    (sequence-specific / insert-size likelihoods) over several GPUs."""
     import threading
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from mmseq_b200 import capi, hostlib, synth
-    s = synth.Synth(20260101 + 1, 300, 20000)
-    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
+    s = synth.Synth(20260101 + 4, 300, 20000, weights=weighted)
+    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=s.frag_w if weighted else None,
+                             layout=hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
+    assert (h.w is not None) == weighted
     cut = [0, (h.m // 2) & ~1, h.m]
     mu0 = np.random.default_rng(0).gamma(0.5, 50.0, h.n)
     hs = []
     for r in range(2):
         a, b = cut[r], cut[r + 1]
         lo, hi = h.row_ptr[a], h.row_ptr[b]
-        hs.append(capi.Handle(h.row_ptr[a:b + 1] - lo, h.col[lo:hi], None, h.len, class_id_base=a, device=r))
+        hs.append(capi.Handle(h.row_ptr[a:b + 1] - lo, h.col[lo:hi], None, h.len, weight=None if h.w is None else h.w[lo:hi], class_id_base=a, device=r))
     capi.p2p_attach_local(hs)
     out = [None, None]
 
@@ -106,7 +111,7 @@ def test_single_process_peer_attach_matches_single_gpu():
         t.join()
     for H in hs:
         H.close()
-    with capi.Handle(h.row_ptr, h.col, None, h.len) as H:
+    with capi.Handle(h.row_ptr, h.col, None, h.len, weight=h.w) as H:
         H.set_mu(mu0)
         H.gibbs(1234, 0, 40, stride=4, trace_len=10)
         tr, mu = H.get_trace(), H.get_mu()
