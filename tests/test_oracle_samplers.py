@@ -72,6 +72,19 @@ def test_binomial_distribution(n, p):
     assert stats.chi2.sf(chi2, len(exp) - 1) > 1e-5, (n, p, chi2)
 
 
+def test_alloc_known_answers():
+    """The random-stream contract of mmq_alloc_row is pinned by committed vectors
+    (tools/make_golden_alloc.py): k = 1 (CAT stream, quad-shared block), categorical draws across
+    block and 64-draw group boundaries up to MMQ_CAT_K = 8192, binomial chains above."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "alloc_kat.npz"))
+    assert int(g["n_cases"]) >= 9
+    for i in range(int(g["n_cases"])):
+        x = orc.draw_alloc(int(g[f"seed_{i}"]), 8, g[f"p_{i}"], int(g[f"k_{i}"]))
+        assert np.array_equal(x, g[f"x_{i}"]), f"case {i}: the allocation contract moved"
+        assert (x.sum(axis=1) == int(g[f"k_{i}"])).all()
+
+
 def test_alloc_row_is_multinomial_and_conserves():
     p = np.array([3.0, 0.0, 1.0, 1e-30, 6.0])
     for k in (1, 2, 5, 40, 100000):
