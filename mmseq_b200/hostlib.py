@@ -108,11 +108,13 @@ def from_records(T, efflen, frag_ptr, frag_tid, frag_w=None, layout=LAYOUT_COLLA
 
 
 def sort_classes_by_cost(h):
-    """Device order of collapsed classes (as mmseq_main.cpp): by kind of draw (singleton, k == 1,
-    2..8, binomial chain), then size, then count.  Returns (row_ptr, col, k, class_id) where
-    class_id[i] is the canonical (first-appearance) index to hand to mmq_problem.class_id."""
+    """A device order of collapsed classes other than the loader's: by kind of draw (singleton, k == 1,
+    categorical draws up to MMQ_CAT_K = 8192, binomial chain), then size, then count — what suits the
+    general kernel (the class plan of mmq_create orders a shard itself).  Returns (row_ptr, col, k,
+    class_id) where class_id[i] is the canonical (first-appearance) index to hand to
+    mmq_problem.class_id; tests and bench.py use it to exercise explicit class ids."""
     d = np.diff(h.row_ptr)
-    kind = np.where(d == 1, 0, np.where(h.k == 1, 1, np.where(h.k <= 8, 2, 3)))
+    kind = np.where(d == 1, 0, np.where(h.k == 1, 1, np.where(h.k <= 8192, 2, 3)))
     order = np.lexsort((h.k, d, kind))
     dd = d[order]
     rp = np.concatenate([[0], np.cumsum(dd)]).astype(np.int64)
