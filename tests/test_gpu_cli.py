@@ -63,6 +63,11 @@ def test_cli_outputs_match_oracle(tmp_path, fmt):
     ids, tr = tables.read_trace_gz(base + ".trace_gibbs.gz")
     assert ids == want["names_by_col"] and tr.shape == want["trace"].shape
     assert np.allclose(tr, want["trace"], rtol=2e-5, atol=1e-300)
+    # ... and as text: every value is printf's "%g" (operator<< at precision 6) of the bit-exact replay's mu
+    import gzip
+    lines = gzip.open(base + ".trace_gibbs.gz", "rt").read().split("\n")
+    for i in (0, 1, want["trace"].shape[1] - 1):
+        assert lines[1 + i].split() == ["%g" % v for v in want["trace"][:, i]]
     ids, ptr = tables.read_trace_gz(base + ".prop.trace_gibbs.gz")
     assert ids == want["names_by_col"] and np.allclose(ptr, want["prop_trace"], rtol=2e-5, atol=1e-300)
     ids, gtr = tables.read_trace_gz(base + ".gene.trace_gibbs.gz")
