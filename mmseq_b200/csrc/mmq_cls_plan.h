@@ -36,6 +36,7 @@ struct mmq_cls_host_plan {
   std::unique_ptr<int32_t[]> pcol; /* [packed] member-major chunks of 32 slots */
   std::vector<uint16_t> pk;        /* [chunks * 32] draws of the slot | slot number within its class << 8 */
   std::vector<uint32_t> pcid;      /* [chunks * 32] low word of the class id */
+  std::vector<unsigned long long> cdesc; /* [chunks] offset of the chunk in pcol << 8 | class size */
   int64_t chunks = 0, chunks_lo = 0, packed = 0, small_classes = 0, n_rest = 0, nnz_rest = 0;
   uint32_t cid_hi = 0;
   std::vector<int64_t> o_rp, o_cid, o_tiles; /* the rest: sub-CSR for the general kernel, one class per tile */
@@ -134,6 +135,12 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
     packed += nch * 32 * d;
     if (d <= MMQ_CLS_DLO) chunks_lo = chunks;
     if (chunks > 0x7fff0000ll) return false;
+  }
+  P.cdesc.assign((size_t)chunks, 0ull);
+  for (size_t r = 0; r < runs.size(); ++r) {
+    const int64_t c1 = r + 1 < runs.size() ? runs[r + 1].chunk0 : chunks;
+    for (int64_t c = runs[r].chunk0; c < c1; ++c)
+      P.cdesc[(size_t)c] = ((unsigned long long)(runs[r].e0 + (c - runs[r].chunk0) * 32 * runs[r].d) << 8) | (unsigned long long)runs[r].d;
   }
   std::vector<int32_t> run_of_d(MMQ_CLS_DMAX + 1, -1);
   for (size_t r = 0; r < runs.size(); ++r) run_of_d[runs[r].d] = (int32_t)r;

@@ -100,6 +100,7 @@ struct mmq_handle {
   int32_t* cls_pcol = nullptr;
   uint16_t* cls_pk = nullptr; /* draws of the slot | slot number within its class << 8 */
   uint32_t* cls_pcid = nullptr;
+  unsigned long long* cls_cdesc = nullptr; /* [chunks] offset of the chunk in cls_pcol << 8 | class size */
   int64_t *cls_o_rp = nullptr, *cls_o_cid = nullptr, *cls_o_tiles = nullptr;
   int32_t *cls_o_col = nullptr, *cls_o_k = nullptr;
   cudaStream_t stream2 = nullptr, stream3 = nullptr;
