@@ -419,7 +419,10 @@ def main():
     # ---- the same sample in the reference's own representation (distinct classes + counts k, what the
     # host program feeds the GPU): class-plan kernel, reported beside the headline (N = 1 only)
     if rank == 0 and world == 1 and args.layout == "perfragment" and not args.no_collapsed and not args.weights and not args.haplo:
-        line["collapsed_layout"] = collapsed_line(args, s, dev, stream, length_full=None)
+        try:
+            line["collapsed_layout"] = collapsed_line(args, s, dev, stream, length_full=None)
+        except Exception as e:   # an extra: never at the expense of the headline line
+            line["collapsed_layout"] = {"error": repr(e)}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
