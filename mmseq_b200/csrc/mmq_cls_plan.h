@@ -66,6 +66,7 @@ static void cls_parallel_for(int64_t count, F&& f) {
  * over several 2^32 blocks, negative counts, too many chunks): the general kernel handles the shard. */
 static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const int32_t* col, const int32_t* kk, const int64_t* class_id,
                                int64_t class_id_base, mmq_cls_host_plan& P) {
+  if (m <= 0) return false;
   static const bool timing = [] { const char* e = getenv("MMQ_CREATE_TIMING"); return e && atoi(e) != 0; }();
   auto t_last = std::chrono::steady_clock::now();
   auto tick = [&](const char* what) {
