@@ -85,18 +85,30 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
   const int NKEY = (MMQ_CLS_DMAX + 1) * MMQ_CLS_NQ;
   std::vector<int16_t> key16(m);
   struct Tally { std::vector<int64_t> key_count; int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small = 0; bool ok = true; };
-  std::vector<Tally> tally;
-  std::mutex tally_mu;
-  cls_parallel_for(m, [&](int64_t a0, int64_t b0) {
-    Tally t;
+  /* thread t owns classes [m t / T, m (t+1) / T) in this pass and in the placement pass below; it also counts
+   * its small classes per first member (the buckets of the counting sort) */
+  const int T = cls_threads(m);
+  auto on_threads = [&](auto&& fn) {
+    if (T == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; ++t) th.emplace_back([&, t] { fn(t); });
+    for (auto& x : th) x.join();
+  };
+  const size_t nb = (size_t)n + 1;
+  std::vector<int64_t> hist((size_t)T * nb, 0); /* [thread][first member] */
+  std::vector<Tally> tally((size_t)T);
+  on_threads([&](int tt) {
+    Tally& t = tally[(size_t)tt];
+    int64_t* hc = hist.data() + (size_t)tt * nb;
     t.key_count.assign(NKEY + 1, 0);
-    for (int64_t i = a0; i < b0; ++i) {
+    for (int64_t i = m * tt / T; i < m * (tt + 1) / T; ++i) {
       const int64_t d = rp[i + 1] - rp[i];
       const int64_t kv = kk[i];
       if ((uint32_t)(cid_of(i) >> 32) != cid_hi || kv < 0) t.ok = false;
       if (d == 1 || kv <= 0) { key16[i] = -1; ++t.n_single; } /* k == 0: nothing to allocate */
       else if (kv <= MMQ_CAT_K && d <= MMQ_CLS_DMAX) {
         ++t.small;
+        ++hc[col[rp[i]]];
         if (kv == 1) { key16[i] = (int16_t)(d * MMQ_CLS_NQ + 16); ++t.key_count[key16[i]]; }
         else {
           const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
@@ -106,8 +118,6 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
         }
       } else { key16[i] = -2; ++t.n_rest; t.nnz_rest += d; }
     }
-    std::lock_guard<std::mutex> g(tally_mu);
-    tally.push_back(std::move(t));
   });
   tick("classify");
   std::vector<int64_t> key_count(NKEY + 1, 0);
@@ -152,23 +162,9 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
   static_assert(MMQ_CAT_K / MMQ_CAT_GROUP <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
   struct Ord { int32_t i; int16_t key; uint8_t full, tail; }; /* key: of the partial slot (tail draws) when there is one */
   std::vector<Ord> order((size_t)small_classes);
-  /* parallel stable counting sort: thread t owns classes [m t / T, m (t+1) / T) and, per first member, a
-   * contiguous piece of that member's bucket */
-  const int T = cls_threads(std::min<int64_t>(m, std::max<int64_t>(small_classes, 1)));
-  auto on_threads = [&](auto&& fn) {
-    if (T == 1) { fn(0); return; }
-    std::vector<std::thread> th;
-    for (int t = 0; t < T; ++t) th.emplace_back([&, t] { fn(t); });
-    for (auto& x : th) x.join();
-  };
+  /* parallel stable counting sort (counts taken in the classification pass): per first member, thread t gets
+   * a contiguous piece of that member's bucket */
   {
-    const size_t nb = (size_t)n + 1;
-    std::vector<int64_t> hist((size_t)T * nb, 0); /* [thread][first member] */
-    on_threads([&](int t) {
-      int64_t* c = hist.data() + (size_t)t * nb;
-      for (int64_t i = m * t / T; i < m * (t + 1) / T; ++i)
-        if (key16[i] >= 0) ++c[col[rp[i]]];
-    });
     int64_t run = 0;
     for (size_t v = 0; v < nb; ++v) /* exclusive prefix in (member, thread) order */
       for (int t = 0; t < T; ++t) { const int64_t c = hist[(size_t)t * nb + v]; hist[(size_t)t * nb + v] = run; run += c; }
