@@ -19,7 +19,7 @@ synth: $(SYNTH)
 hostlib: $(HOSTLIB)
 cli: $(CLI)
 
-build/%.o: $(CSRC)/%.cu $(CSRC)/mmq_internal.h $(CSRC)/mmq_device.cuh include/mmq.h include/mmq_sampler.h
+build/%.o: $(CSRC)/%.cu $(CSRC)/mmq_internal.h $(CSRC)/mmq_device.cuh $(CSRC)/mmq_cls_plan.h include/mmq.h include/mmq_sampler.h
 	@mkdir -p build
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
 
@@ -29,7 +29,7 @@ $(LIB): build/mmq_core.o build/mmq_post.o build/mmq_seg.o build/mmq_cls.o
 $(SYNTH): $(CSRC)/mmq_synth.cpp
 	$(HOST_CXX) -O3 -std=c++17 -fPIC -fopenmp -shared -o $@ $< -lz
 
-$(HOSTLIB): $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h include/mmq_sampler.h
+$(HOSTLIB): $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h $(CSRC)/mmq_cls_plan.h include/mmq_sampler.h
 	$(HOST_CXX) -O3 -std=c++17 -fPIC -ffp-contract=off -shared -o $@ $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp -lz
 
 $(CLI): $(CSRC)/mmseq_main.cpp $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h include/mmq.h $(LIB)

@@ -40,8 +40,10 @@
 #define MMQ_STREAM_ALLOC 0x414c4c4fu /* per hit class, per sweep   */
 #define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
 #define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
-#define MMQ_CAT_K 8192 /* classes with 2..MMQ_CAT_K fragments: categorical draws (four 32-bit uniforms per Philox block) instead of binomials */
-#define MMQ_CAT_GROUP 64 /* ... generated 64 at a time (16 blocks): the unit of work of the class-plan kernel */
+#define MMQ_CAT_K 64 /* classes with 2..MMQ_CAT_K fragments: categorical draws (four 32-bit uniforms per Philox block), O(k d);
+                        more fragments: gsl_ran_multinomial's chain of conditional binomials, O(d) (round 1 drew up to 8192
+                        categoricals: 54 % of a sweep's draws on the config-2 sample belonged to classes above 64) */
+#define MMQ_CAT_GROUP 64 /* categorical draws are generated in groups of at most 64 (16 blocks): one slot of the class-plan kernel */
 #define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per QUAD of classes (one 32-bit word each) */
 
 /* ------------------------------------------------------------------ bits */
@@ -386,6 +388,31 @@ MMQ_HD int64_t mmq_binomial(mmq_rng* g, int64_t n, double p) {
 
 /* ---------------------------------------------------- one hit class */
 
+/* gsl_ran_multinomial's chain of conditional binomials (src/mmseq.cpp:880): x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)),
+ * members with zero probability skipped, the last member with p > 0 takes what is left.  norm = p_0 + ... + p_{d-1} summed
+ * left to right and last_pos = the last member with p > 0 (d - 1 if none) come from the caller's first pass over the row;
+ * g is the class's ALLOC stream (52-bit uniforms).  p is read once more, x[j] is assigned exactly once per member. */
+template <typename PIt, typename XIt>
+MMQ_HD void mmq_alloc_chain(PIt p, XIt x, int d, int64_t k, double norm, int last_pos, mmq_rng* g) {
+  int64_t rem = k;
+  double sum_p = 0.0;
+  for (int j = 0; j < d; ++j) {
+    int64_t xj = 0;
+    const double pj = p[j];
+    if (j == last_pos) {
+      xj = rem; /* zero-probability members never receive fragments */
+    } else if (rem > 0 && pj > 0.0) {
+      const double denom = norm - sum_p;
+      double pr = (denom > 0.0) ? pj / denom : 1.0;
+      if (pr > 1.0) pr = 1.0;
+      xj = mmq_binomial(g, rem, pr);
+    }
+    x[j] = (int32_t)xj;
+    rem -= xj;
+    sum_p += pj;
+  }
+}
+
 /* How mmq_alloc_row accumulates into its output: plain arrays are zeroed and added to; an output
  * that is itself a reduction (the kernels' counts[] adaptor) overloads these two. */
 template <typename XIt>
@@ -481,23 +508,7 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
     }
     return;
   }
-  int64_t rem = k;
-  double sum_p = 0.0;
-  for (int j = 0; j < d; ++j) {
-    int64_t xj = 0;
-    const double pj = p[j];
-    if (j == last_pos) {
-      xj = rem; /* zero-probability members never receive fragments */
-    } else if (rem > 0 && pj > 0.0) {
-      const double denom = norm - sum_p;
-      double pr = (denom > 0.0) ? pj / denom : 1.0;
-      if (pr > 1.0) pr = 1.0;
-      xj = mmq_binomial(&g, rem, pr);
-    }
-    x[j] = (int32_t)xj;
-    rem -= xj;
-    sum_p += pj;
-  }
+  mmq_alloc_chain(p, x, d, k, norm, last_pos, &g);
 }
 
 #endif /* MMQ_SAMPLER_H */

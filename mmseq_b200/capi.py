@@ -265,10 +265,11 @@ class Handle:
         return a.value, an.value, g.value, gn.value
 
     def cls_stats(self):
-        """Class plan of a collapsed shard: dict(in_use, small_classes, packed_slots, class_slots, rest_classes, rest_nnz)."""
-        out = (C.c_int64 * 6)()
+        """Class plan of a collapsed shard: dict(in_use, small_classes, packed_slots, class_slots, rest_classes, rest_nnz,
+        chain_classes, chain_slots)."""
+        out = (C.c_int64 * 8)()
         self._check(lib().mmq_cls_stats(self._h, out), "mmq_cls_stats")
-        return dict(zip(["in_use", "small_classes", "packed_slots", "class_slots", "rest_classes", "rest_nnz"], [int(v) for v in out]))
+        return dict(zip(["in_use", "small_classes", "packed_slots", "class_slots", "rest_classes", "rest_nnz", "chain_classes", "chain_slots"], [int(v) for v in out]))
 
     def sweep_debug(self, seed, sweep, flags=MMQ_GIBBS_TRANSPOSED, want_x=True):
         x = np.zeros(self.nnz, np.int32) if (want_x and (flags & MMQ_GIBBS_TRANSPOSED)) else None

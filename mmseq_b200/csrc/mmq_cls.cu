@@ -241,6 +241,60 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
   }
 }
 
+/* The chain set: classes with more than MMQ_CAT_K fragments — gsl_ran_multinomial's chain of conditional binomials
+ * (src/mmseq.cpp:880), O(d) per class whatever k is.  One class per lane, 32 classes of equal size per chunk (member-major
+ * like the small set, so every column load of the warp is one 128-byte line), longest classes first.  The lane sums its
+ * row left to right (norm, last member with p > 0), then walks it once more: x_j ~ Bin(rem, p_j / (norm - sum_{<j} p)) with
+ * BINV below a mean of 10 and BTRS above (mmq_binomial, fp64, shared with the CPU replay) and adds x_j to counts[].
+ * A few tens of thousands of classes (49k of 3.6M on the config-2 sample, holding 55 % of its fragments): latency-bound,
+ * launched first on its own stream so that it overlaps the two k_alloc_cls instances. */
+struct ChainP {
+  const int32_t* pc;
+  const double* mu;
+  __device__ __forceinline__ double operator[](int j) const { return mu[__ldg(pc + 32 * j)]; }
+};
+struct ChainX {
+  const int32_t* pc;
+  int32_t* counts;
+  struct Ref {
+    const int32_t* c;
+    int32_t* counts;
+    __device__ __forceinline__ void operator=(int32_t v) const { if (v != 0) atomicAdd(counts + __ldg(c), v); }
+  };
+  __device__ __forceinline__ Ref operator[](int j) const { return Ref{pc + 32 * j, counts}; }
+};
+__global__ void __launch_bounds__(MMQ_CLS_WARPS * 32)
+k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __restrict__ ck, const uint32_t* __restrict__ ccid,
+              const unsigned long long* __restrict__ cdesc, uint32_t cid_hi, const double* __restrict__ mu,
+              int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * MMQ_CLS_WARPS;
+  for (int chunk = blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5); chunk < chunks; chunk += nwarps) {
+    const unsigned long long desc = cdesc[chunk];
+    const int D = (int)(desc & 0xffull);
+    const int32_t* pc = pcol + (desc >> 8) + lane;
+    const int64_t kv = ck[(int64_t)chunk * 32 + lane];
+    const uint32_t cid = ccid[(int64_t)chunk * 32 + lane];
+    if (kv <= 0) continue; /* padding lane */
+    const ChainP p{pc, mu};
+    double norm = 0.0;
+    int last_pos = D - 1;
+    {
+      int lp = -1;
+      for (int j = 0; j < D; ++j) {
+        const double pj = p[j];
+        norm += pj;
+        if (pj > 0.0) lp = j;
+      }
+      if (lp >= 0) last_pos = lp;
+    }
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | cid, sweep);
+    mmq_alloc_chain(p, ChainX{pc, counts}, D, kv, norm, last_pos, &g);
+  }
+}
+
 __global__ void k_cls_singletons(const int32_t* __restrict__ col1, const int32_t* __restrict__ k1, int64_t count,
                                  int32_t* __restrict__ base) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
@@ -283,6 +337,13 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   if ((rc = cls_upload(h, &h->cls_pcid, pcid))) return rc;
   if ((rc = cls_upload(h, (mmq_cls_run**)&h->cls_runs, runs))) return rc;
   if ((rc = cls_upload(h, &h->cls_cdesc, P.cdesc))) return rc;
+  if (P.c_chunks > 0) {
+    if ((rc = mmq_dev_alloc(h, (void**)&h->cls_c_pcol, sizeof(int32_t) * (size_t)P.c_packed))) return rc;
+    MMQ_CUDA(h, cudaMemcpyAsync(h->cls_c_pcol, P.c_pcol.get(), sizeof(int32_t) * (size_t)P.c_packed, cudaMemcpyHostToDevice, h->stream));
+    if ((rc = cls_upload(h, &h->cls_c_k, P.c_k))) return rc;
+    if ((rc = cls_upload(h, &h->cls_c_cid, P.c_cid))) return rc;
+    if ((rc = cls_upload(h, &h->cls_c_desc, P.c_desc))) return rc;
+  }
   if (n_rest > 0) {
     if ((rc = cls_upload(h, &h->cls_o_rp, o_rp))) return rc;
     if ((rc = cls_upload(h, &h->cls_o_col, o_col))) return rc;
@@ -308,6 +369,8 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   if (!h->stream2) {
     MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
     MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
@@ -322,11 +385,14 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   h->cls_rest_nnz = nnz_rest;
   h->cls_rest_tiles = n_rest;
   h->cls_packed = packed;
+  h->cls_c_chunks = P.c_chunks;
+  h->cls_c_packed = P.c_packed;
+  h->cls_chain = P.n_chain;
   h->cls_ready = true;
   return MMQ_OK;
 }
 
-extern "C" int mmq_cls_stats(const mmq_handle* h, int64_t out[6]) {
+extern "C" int mmq_cls_stats(const mmq_handle* h, int64_t out[8]) {
   if (!h || !out) return MMQ_ERR_ARG;
   out[0] = h->cls_ready ? 1 : 0;
   out[1] = h->cls_small;
@@ -334,6 +400,8 @@ extern "C" int mmq_cls_stats(const mmq_handle* h, int64_t out[6]) {
   out[3] = h->cls_chunks * 32;
   out[4] = h->cls_rest;
   out[5] = h->cls_rest_nnz;
+  out[6] = h->cls_chain;
+  out[7] = h->cls_c_packed;
   return MMQ_OK;
 }
 
@@ -346,11 +414,20 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
   static const int geo_hi = [] { const char* e = getenv("MMQ_CLS_GEO_HI"); return e ? atoi(e) : 0; }();
   const char* desc_env = getenv("MMQ_CLS_DESC"); /* chunk descriptors instead of the run table; read per launch (A/B runs) */
   const bool use_desc = desc_env ? atoi(desc_env) != 0 : true; /* measured: 0.101 against 0.106 ms per sweep on the C2 sample */
+  const bool do_chain = h->cls_c_chunks > 0 && !(skip & 8);
   const bool do_rest = h->cls_rest > 0 && !(skip & 2);
   const bool do_hi = h->cls_chunks > h->cls_chunks_lo && !(skip & 4);
   const bool do_lo = h->cls_chunks_lo > 0 && !(skip & 1);
   /* three independent pieces, concurrently: the long chains first (their latency is the longest) */
-  if (do_rest || (do_hi && do_lo)) MMQ_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+  if (do_rest || do_chain || (do_hi && do_lo)) MMQ_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+  if (do_chain) {
+    MMQ_CUDA(h, cudaStreamWaitEvent(h->stream4, h->ev_fork, 0));
+    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, (int64_t)h->num_sms * 4);
+    k_alloc_chain<<<grid, MMQ_CLS_WARPS * 32, 0, h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
+                                                              h->mu, h->counts, seed, sweep, sweep_base);
+    MMQ_LAUNCHED(h);
+    MMQ_CUDA(h, cudaEventRecord(h->ev_join4, h->stream4));
+  }
   if (do_rest) {
     MMQ_CUDA(h, cudaStreamWaitEvent(h->stream2, h->ev_fork, 0));
     const int grid = (int)std::min<int64_t>((h->cls_rest_tiles + MMQ_ALLOC_WARPS - 1) / MMQ_ALLOC_WARPS, (int64_t)h->num_sms * 3);
@@ -385,5 +462,6 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
 #undef MMQ_CLS_ARGS
   if (do_hi && do_lo) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join3, 0));
   if (do_rest) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+  if (do_chain) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join4, 0));
   return MMQ_OK;
 }

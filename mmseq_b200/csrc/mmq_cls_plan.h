@@ -39,6 +39,13 @@ struct mmq_cls_host_plan {
   std::vector<unsigned long long> cdesc; /* [chunks] offset of the chunk in pcol << 8 | class size */
   int64_t chunks = 0, chunks_lo = 0, packed = 0, small_classes = 0, n_rest = 0, nnz_rest = 0;
   uint32_t cid_hi = 0;
+  /* the chain set: classes with more than MMQ_CAT_K fragments and at most MMQ_CLS_DMAX members (conditional-binomial
+   * chains, one class per lane of k_alloc_chain): member-major chunks of 32 like the small set, longest classes first */
+  std::unique_ptr<int32_t[]> c_pcol;       /* [c_packed] */
+  std::vector<int32_t> c_k;                /* [c_chunks * 32] fragments of the class (0: padding lane) */
+  std::vector<uint32_t> c_cid;             /* [c_chunks * 32] low word of the class id */
+  std::vector<unsigned long long> c_desc;  /* [c_chunks] offset of the chunk in c_pcol << 8 | class size */
+  int64_t c_chunks = 0, c_packed = 0, n_chain = 0;
   std::vector<int64_t> o_rp, o_cid, o_tiles; /* the rest: sub-CSR for the general kernel, one class per tile */
   std::vector<int32_t> o_col, o_k;
   std::vector<int32_t> s_col, s_k;           /* singleton classes: column and count */
@@ -84,7 +91,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
    * or of its full slots when k is a multiple of 64; -1 singleton / empty, -2 rest. */
   const int NKEY = (MMQ_CLS_DMAX + 1) * MMQ_CLS_NQ;
   std::vector<int16_t> key16(m);
-  struct Tally { std::vector<int64_t> key_count; int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small = 0; bool ok = true; };
+  struct Tally { std::vector<int64_t> key_count; int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small = 0, n_chain = 0; bool ok = true; };
   /* thread t owns classes [m t / T, m (t+1) / T) in this pass and in the placement pass below; it also counts
    * its small classes per first member (the buckets of the counting sort) */
   const int T = cls_threads(m);
@@ -116,13 +123,15 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
           key16[i] = (int16_t)(d * MMQ_CLS_NQ + (tail ? 16 - (int)((tail + 3) >> 2) : 0));
           if (tail) ++t.key_count[key16[i]];
         }
-      } else { key16[i] = -2; ++t.n_rest; t.nnz_rest += d; }
+      } else if (d <= MMQ_CLS_DMAX) { key16[i] = -3; ++t.n_chain; }
+      else { key16[i] = -2; ++t.n_rest; t.nnz_rest += d; }
     }
   });
   tick("classify");
   std::vector<int64_t> key_count(NKEY + 1, 0);
-  int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small_classes = 0;
+  int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small_classes = 0, n_chain = 0;
   for (const Tally& t : tally) {
+    n_chain += t.n_chain;
     if (!t.ok) return false; /* class ids spread over several 2^32 blocks (or k < 0): the general kernel handles it */
     for (int q = 0; q <= NKEY; ++q) key_count[q] += t.key_count[q];
     n_single += t.n_single; n_rest += t.n_rest; nnz_rest += t.nnz_rest; small_classes += t.small;
@@ -238,6 +247,50 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
   });
 
   tick("fill");
+  /* the chain set: by class size (longest first: a chain is serial in its members, the long ones must not be the tail of
+   * the launch), then by first member; 32 classes per chunk, member-major, padding lanes have k = 0 and the sentinel column */
+  {
+    std::vector<int64_t> chain;
+    chain.reserve((size_t)n_chain);
+    for (int64_t i = 0; i < m; ++i)
+      if (key16[i] == -3) chain.push_back(i);
+    std::stable_sort(chain.begin(), chain.end(), [&](int64_t a, int64_t b) {
+      const int64_t da = rp[a + 1] - rp[a], db = rp[b + 1] - rp[b];
+      return da != db ? da > db : col[rp[a]] < col[rp[b]];
+    });
+    int64_t c_chunks = 0, c_packed = 0;
+    for (size_t a = 0; a < chain.size();) { /* runs of equal d */
+      const int64_t d = rp[chain[a] + 1] - rp[chain[a]];
+      size_t b = a;
+      while (b < chain.size() && rp[chain[b] + 1] - rp[chain[b]] == d) ++b;
+      const int64_t nch = ((int64_t)(b - a) + 31) / 32;
+      for (int64_t c = 0; c < nch; ++c) P.c_desc.push_back(((unsigned long long)(c_packed + c * 32 * d) << 8) | (unsigned long long)d);
+      c_chunks += nch;
+      c_packed += nch * 32 * d;
+      a = b;
+    }
+    P.c_pcol.reset(new int32_t[(size_t)std::max<int64_t>(c_packed, 1)]);
+    for (int64_t q = 0; q < c_packed; ++q) P.c_pcol[(size_t)q] = (int32_t)n;
+    P.c_k.assign((size_t)c_chunks * 32, 0);
+    P.c_cid.assign((size_t)c_chunks * 32, 0u);
+    int64_t chunk = 0;
+    for (size_t a = 0; a < chain.size();) {
+      const int64_t d = rp[chain[a] + 1] - rp[chain[a]];
+      size_t b = a;
+      while (b < chain.size() && rp[chain[b] + 1] - rp[chain[b]] == d) ++b;
+      for (size_t q = a; q < b; ++q) {
+        const int64_t i = chain[q], s = chunk * 32 + (int64_t)(q - a);
+        int32_t* dst = P.c_pcol.get() + (P.c_desc[(size_t)(s >> 5)] >> 8) + (s & 31);
+        for (int64_t j = 0; j < d; ++j) dst[32 * j] = col[rp[i] + j];
+        P.c_k[(size_t)s] = kk[i];
+        P.c_cid[(size_t)s] = (uint32_t)cid_of(i);
+      }
+      chunk += ((int64_t)(b - a) + 31) / 32;
+      a = b;
+    }
+    P.c_chunks = c_chunks; P.c_packed = c_packed; P.n_chain = n_chain;
+  }
+  tick("chain set");
   /* the rest: a sub-CSR for the general kernel, longest chains first, ONE class per warp tile (a
    * chain of binomials is serial: what matters is when the slowest warp ends, not lane use) */
   std::vector<int64_t> rest;
@@ -316,6 +369,16 @@ static void mmq_cls_replay_host(const mmq_cls_host_plan& P, int64_t n, const dou
   }
   std::vector<double> p;
   std::vector<int32_t> x;
+  for (int64_t s = 0; s < P.c_chunks * 32; ++s) { /* the chain set, lane by lane */
+    const int64_t kv = P.c_k[(size_t)s];
+    if (kv <= 0) continue;
+    const int d = (int)(P.c_desc[(size_t)(s >> 5)] & 0xffull);
+    const int32_t* pc = P.c_pcol.get() + (P.c_desc[(size_t)(s >> 5)] >> 8) + (s & 31);
+    p.resize((size_t)d); x.assign((size_t)d, 0);
+    for (int j = 0; j < d; ++j) p[(size_t)j] = mu[pc[32 * j]];
+    mmq_alloc_row(p.data(), x.data(), d, kv, seed, ((uint64_t)P.cid_hi << 32) | P.c_cid[(size_t)s], sweep);
+    for (int j = 0; j < d; ++j) counts[pc[32 * j]] += x[(size_t)j];
+  }
   for (int64_t q = 0; q < P.n_rest; ++q) {
     const int d = (int)(P.o_rp[(size_t)q + 1] - P.o_rp[(size_t)q]);
     p.resize((size_t)d); x.assign((size_t)d, 0);

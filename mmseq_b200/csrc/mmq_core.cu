@@ -899,6 +899,8 @@ void mmq_destroy(mmq_handle* h) {
   for (cudaEvent_t e : h->ev_gamma) cudaEventDestroy(e);
   if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
   if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
+  if (h->stream4) { cudaStreamSynchronize(h->stream4); cudaStreamDestroy(h->stream4); }
+  if (h->ev_join4) cudaEventDestroy(h->ev_join4);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_join3) cudaEventDestroy(h->ev_join3);

@@ -103,8 +103,14 @@ struct mmq_handle {
   unsigned long long* cls_cdesc = nullptr; /* [chunks] offset of the chunk in cls_pcol << 8 | class size */
   int64_t *cls_o_rp = nullptr, *cls_o_cid = nullptr, *cls_o_tiles = nullptr;
   int32_t *cls_o_col = nullptr, *cls_o_k = nullptr;
-  cudaStream_t stream2 = nullptr, stream3 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr;
+  /* the chain set (more than MMQ_CAT_K fragments): k_alloc_chain, one class per lane */
+  int32_t* cls_c_pcol = nullptr;
+  int32_t* cls_c_k = nullptr;
+  uint32_t* cls_c_cid = nullptr;
+  unsigned long long* cls_c_desc = nullptr;
+  int64_t cls_c_chunks = 0, cls_c_packed = 0, cls_chain = 0;
+  cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
 
   /* fused count exchange over peer memory: [flags int32[MMQ_P2P_MAX] | pad | counts A[n] | counts B[n]] */
   void* p2p_buf = nullptr;

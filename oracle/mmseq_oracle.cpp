@@ -446,7 +446,7 @@ void orc_uh_literal(int64_t m, const int64_t* rp, const int32_t* col, const int3
  * shard into slots and chunks for k_alloc_cls) built on the CPU and replayed with the shared
  * sampler: the counts must equal orc_sweep_replay's.  Lets the CPU test suite check the host side
  * of the plan (slot splitting, ordering, padding, the rest / singleton lists) without a GPU.
- * stats: [applied, small classes, column slots, class slots, rest classes, rest entries]. */
+ * stats: [applied, small classes, column slots, class slots, rest classes, rest entries, chain classes, chain column slots]. */
 int orc_cls_plan_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k, const int64_t* class_id,
                         int64_t class_id_base, const double* mu, uint32_t seed, uint32_t sweep, int32_t* counts, int64_t* stats) {
   mmq_cls_host_plan P;
@@ -454,6 +454,7 @@ int orc_cls_plan_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* 
   mmq_cls_replay_host(P, n, mu, seed, sweep, counts);
   if (stats) {
     stats[0] = 1; stats[1] = P.small_classes; stats[2] = P.packed; stats[3] = P.chunks * 32; stats[4] = P.n_rest; stats[5] = P.nnz_rest;
+    stats[6] = P.n_chain; stats[7] = P.c_packed;
   }
   return 0;
 }

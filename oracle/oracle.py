@@ -176,12 +176,12 @@ class Problem:
         returns (counts, stats dict) or (None, None) when the plan does not apply."""
         mu = np.array(mu, np.float64)
         cid = None if class_id is None else _c(class_id, np.int64)
-        counts = np.zeros(self.n, np.int32); stats = np.zeros(6, np.int64)
+        counts = np.zeros(self.n, np.int32); stats = np.zeros(8, np.int64)
         rc = lib().orc_cls_plan_replay(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(cid), class_id_base,
                                        _p(mu), seed, sweep, _p(counts), _p(stats))
         if rc:
             return None, None
-        return counts, dict(zip(["in_use", "small_classes", "packed_slots", "class_slots", "rest_classes", "rest_nnz"], [int(v) for v in stats]))
+        return counts, dict(zip(["in_use", "small_classes", "packed_slots", "class_slots", "rest_classes", "rest_nnz", "chain_classes", "chain_slots"], [int(v) for v in stats]))
 
     def sweep_replay_ids(self, mu, seed, sweep, class_id, do_gamma=True):
         """One sweep with explicit Philox counters per class (any class order)."""
