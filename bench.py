@@ -1,23 +1,36 @@
 #!/usr/bin/env python
-"""bench.py — Gibbs sweep throughput of the mmseq hot path on B200.
+"""bench.py — Gibbs sweep throughput of the mmseq hot path on B200, with its correctness gates.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (config.workload "C2-perfragment"): BASELINE.json configs[1] — a synthetic
-Ensembl-sized sample, 180k transcripts / 30M paired fragments per GPU, one CSR row
-per fragment (k == 1), rows grouped by hit class by the loader.  A "step" is
-SWEEPS_PER_STEP (= 16, the reference's trace stride, src/mmseq.cpp:192) full Gibbs
-sweeps: allocation of every hit class (k_alloc), [NCCL all-reduce of the count
-vector when N > 1], Gamma update of every transcript (k_gamma), with one trace
-capture per step.  Weak scaling: every rank holds its own 30M-fragment shard of the
-same transcriptome; the aggregate metric is hit-class allocations/s.
+Workload (config.workload "C2-collapsed"): BASELINE.json configs[1] — a synthetic Ensembl-sized
+sample, 180k transcripts / 30M paired fragments per GPU, in the REFERENCE'S OWN REPRESENTATION:
+distinct hit classes with fragment counts k (src/mmseq.cpp:395-441), what the `mmseq` host
+program feeds the GPU.  Both arms (ours and `--impl reference`) run the same sample in the same
+representation, so value = distinct hit classes x sweeps/s is an equal-work number.
 
-Printed by rank 0: ONE JSON line (see README / DESIGN.md for the keys).
-`--impl reference` times the reference's own algorithm and data flow on the host
-cores (oracle/: MT19937 per OpenMP thread, GSL-style samplers, dense per-thread
-partials; the reference itself needs Boost + GSL and cannot be built here).
+A "step" is SWEEPS_PER_STEP (= 16, the reference's trace stride, src/mmseq.cpp:192) full Gibbs
+sweeps — allocation of every hit class, [count exchange when N > 1], Gamma update of every
+transcript — with one trace capture per step, issued through mmq_gibbs exactly as the host program
+does (CUDA graph of 16 sweeps).  Weak scaling: every rank holds its own 30M-fragment shard of the
+same transcriptome.  `--scaling strong --fragments-total F` splits ONE sample of F fragments over
+the ranks (config 4: `--weights --layout perfragment --fragments-total 200000000`).
+
+After the timed region every rank runs the correctness gates of SURVEY.md section 8(d) at the
+benchmark shape and rank 0 prints them in the JSON line ("gates"); a failed gate exits non-zero:
+  (a) >= 3 sweeps of mmq_sweep_debug on the full shard: counts and mu bit for bit against the CPU
+      replay on the shared Philox stream (every rank replays its shard, the integer counts are
+      summed over ranks), and the X matrix of one sweep entry by entry;
+  (b) EM: |mu_gpu / mu_oracle - 1| <= 1e-6 and equal iteration count;
+  (c) N = 1: posterior mean of log mu against the reference-like GSL chain (MT19937, GSL samplers)
+      within 4 Monte-Carlo standard errors for >= 99.9 % of the transcripts.
+
+`--impl reference` times the reference's own algorithm and data flow on ALL host cores (oracle/:
+MT19937 per OpenMP thread, GSL-style samplers, dense per-thread partials; the reference itself
+needs Boost + GSL and cannot be built here), on the same N shards' worth of work.
 """
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -43,47 +56,75 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--transcripts", type=int, default=T_C2)
-    ap.add_argument("--fragments", type=int, default=N_C2, help="fragments per GPU")
-    ap.add_argument("--layout", default="perfragment", choices=["perfragment", "perfragment_byclass", "perfragment_unsorted", "collapsed"])
-    ap.add_argument("--first-appearance-columns", action="store_true", help="number transcripts as the reference does (src/mmseq.cpp:403) instead of in header order")
-    ap.add_argument("--weights", action="store_true", help="fp32 per-hit weights (config 4's extension)")
-    ap.add_argument("--haplo", action="store_true", help="config 3: haplotype-specific transcriptome (every transcript as _A/_B copies: 360k haplo-transcripts, deep multi-mapping)")
+    ap.add_argument("--fragments", type=int, default=N_C2, help="fragments per GPU (weak scaling)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--fragments-total", type=int, default=0, help="strong scaling: fragments of the one sample that is split over the ranks")
+    ap.add_argument("--layout", default="collapsed", choices=["collapsed", "perfragment"],
+                    help="collapsed = distinct classes + counts (reference semantics, default); perfragment = one row per fragment "
+                         "(the only layout that can carry per-hit weights)")
+    ap.add_argument("--weights", action="store_true", help="fp32 per-hit weights (config 4's extension); implies --layout perfragment")
+    ap.add_argument("--haplo", action="store_true", help="config 3: haplotype-specific transcriptome (360k haplo-transcripts, deep multi-mapping)")
     ap.add_argument("--transposed", action="store_true", help="materialise X + atomic-free transposed reduction")
-    ap.add_argument("--cpu-sweeps", type=int, default=4, help="sweeps of the CPU baseline sample")
+    ap.add_argument("--cpu-sweeps", type=int, default=128, help="sweeps of the CPU baseline / posterior-gate chain (rank 0, N = 1)")
     ap.add_argument("--nccl-only", action="store_true", help="N > 1: exchange counts with ncclAllReduce instead of the fused peer-memory kernel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-collapsed", action="store_true", help="skip the extra line on the collapsed (reference-semantics) layout of the same sample")
-    return ap.parse_args()
+    ap.add_argument("--no-gates", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra lines (weighted per-fragment stream of the same sample)")
+    ap.add_argument("--gate-sweeps", type=int, default=3)
+    args = ap.parse_args()
+    if args.weights:
+        args.layout = "perfragment"
+    return args
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def make_workload(args, rank, world):
-    """This rank's shard: its own fragments of the shared transcriptome, columns = header indices
-    when world > 1 (one column space across shards)."""
+def host_threads():
+    """Host cores this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def fragments_of(args, rank, world):
+    """(fragments of this rank's shard, fragments of the whole job)."""
+    if args.scaling == "strong":
+        tot = args.fragments_total or args.fragments
+        lo, hi = tot * rank // world, tot * (rank + 1) // world
+        return hi - lo, tot
+    return args.fragments, args.fragments * world
+
+
+class Workload:
+    pass
+
+
+def make_workload(args, rank, world, weights=None, layout=None):
+    """This rank's shard: its own fragments of the shared transcriptome; columns = header indices when world > 1
+    (one column space across shards), header order otherwise."""
     from mmseq_b200 import hostlib, synth
+    weights = args.weights if weights is None else weights
+    layout = layout or args.layout
+    nfrag, ntot = fragments_of(args, rank, world)
     t0 = time.time()
-    s = synth.Synth(SYNTH_SEED + (1 if args.haplo else 0), args.transcripts * (2 if args.haplo else 1), args.fragments, haplo=args.haplo, weights=args.weights, frag_seed=rank)
+    s = synth.Synth(SYNTH_SEED + (1 if args.haplo else 0), args.transcripts * (2 if args.haplo else 1), nfrag, haplo=args.haplo,
+                    weights=weights, frag_seed=rank)
     t1 = time.time()
-    layout = {"perfragment": hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH, "perfragment_byclass": hostlib.LAYOUT_PER_FRAGMENT_SORTED,
-              "perfragment_unsorted": hostlib.LAYOUT_PER_FRAGMENT,
-              "collapsed": hostlib.LAYOUT_COLLAPSED}[args.layout]
-    if world > 1:
-        layout |= hostlib.LAYOUT_IDENTITY_COLUMNS
-    elif not args.first_appearance_columns:
-        layout |= hostlib.LAYOUT_HEADER_ORDER_COLUMNS
-    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=s.frag_w if args.weights else None, layout=layout)
+    lay = hostlib.LAYOUT_COLLAPSED if layout == "collapsed" else hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH
+    lay |= hostlib.LAYOUT_IDENTITY_COLUMNS if world > 1 else hostlib.LAYOUT_HEADER_ORDER_COLUMNS
+    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=s.frag_w if weights else None, layout=lay)
     t2 = time.time()
-    # l[t] = efflen * N_total / 1e9 over the whole (all-rank) sample, src/mmseq.cpp:603
-    n_total = args.fragments * world
-    length = s.efflen[h.col2hdr] * n_total / 1e9
-    return s, h, length, dict(gen_s=round(t1 - t0, 2), load_s=round(t2 - t1, 2))
+    w = Workload()
+    w.s, w.h, w.layout, w.weights = s, h, layout, weights
+    w.length = s.efflen[h.col2hdr] * ntot / 1e9   # l[t] = efflen * N_total / 1e9 over the whole job's sample, src/mmseq.cpp:603
+    w.cid_base = rank * (1 << 28)                  # Philox counters of the shards do not overlap
+    w.nfrag, w.ntot = nfrag, ntot
+    w.prep = dict(gen_s=round(t1 - t0, 2), load_s=round(t2 - t1, 2))
+    return w
 
 
 class ClockSampler(threading.Thread):
@@ -140,20 +181,21 @@ def physical_gpu_index(local):
     return local
 
 
-def algorithmic_bytes(h, n, weights, transposed, stride, layout, cls=None):
-    """Compulsory HBM bytes of the implemented data flow ('Roofline'); every array
-    once, L2-resident mu gathers and count reductions not counted.
-      segment kernel (by-length k == 1 shards): 4 B column (+4 B weight) per CSR entry of the
-        classes with >= 2 members; no row pointers, singleton classes are not visited;
-      row-pointer kernels: + 8 B row pointer per class, all entries (+4 B k when present);
-      transposed variant: + X written, + permutation and X read back (12 B per entry)."""
+def algorithmic_bytes(h, n, weights, transposed, stride, layout, cls=None, rows=None):
+    """Compulsory HBM bytes of the implemented data flow ('Roofline'); every array once, L2-resident mu
+    gathers and count reductions not counted.  Returns (allocation launch, whole sweep)."""
     m, nnz = h.m, h.nnz
     d = np.diff(h.row_ptr)
     per_entry = 4 + (4 if weights else 0)
-    if cls and cls["in_use"] and not transposed:
-        # class plan (mmq_cls.cu): packed columns (4 B) + draws/slot number (2 B) + class id (4 B) per slot of the small
-        # set; row pointer, k, class id (8 + 4 + 8 B) per class and 4 B per entry of the sub-CSR left to k_alloc
-        alloc = 4 * cls["packed_slots"] + 6 * cls["class_slots"] + 20 * cls["rest_classes"] + 4 * cls["rest_nnz"]
+    if rows and rows.get("in_use") and not transposed:
+        # row plan (mmq_rows.cu): columns once per distinct class, weights once per fragment, 16 B of run marks per 128 rows
+        alloc = rows["bytes_per_sweep"]
+    elif cls and cls["in_use"] and not transposed:
+        # class plan (mmq_cls.cu): packed columns (4 B) + draws (2 B) + class id (4 B) per slot of the small set; the same
+        # with a 4-byte count for the chain set, 8 B per chunk descriptor; row pointer, k, class id (8 + 4 + 8 B) per class
+        # and 4 B per entry of the sub-CSR left to k_alloc
+        alloc = (4 * cls["packed_slots"] + 6 * cls["class_slots"] + cls["class_slots"] // 4 + 4 * cls["chain_slots"]
+                 + 8 * ((cls["chain_classes"] + 31) // 32 * 32) + 20 * cls["rest_classes"] + 4 * cls["rest_nnz"])
     elif layout == "perfragment" and h.k is None and not transposed:
         alloc = per_entry * int(d[d >= 2].sum())
     else:
@@ -162,90 +204,280 @@ def algorithmic_bytes(h, n, weights, transposed, stride, layout, cls=None):
         alloc += 4 * nnz
     reduce_ = (8 * nnz + 8 * (n + 1) + 4 * n) if transposed else 0
     gamma = n * (4 + 4 + 8 + 8) + (8 * n) // stride
-    return alloc, alloc + reduce_ + gamma
+    return int(alloc), int(alloc + reduce_ + gamma)
+
+
+def workload_name(args, layout=None, weights=None):
+    layout = layout or args.layout
+    weights = args.weights if weights is None else weights
+    base = "C3-haplotype-" if args.haplo else ("C4-" if (args.scaling == "strong" and weights) else "C2-")
+    return base + layout + ("-weighted" if weights else "")
+
+
+def workload_config(args, world, totals):
+    """Identical in both arms (ours / reference) for the same command line."""
+    nfrag, ntot = fragments_of(args, 0, world)
+    return {
+        "workload": workload_name(args), "transcripts": args.transcripts * (2 if args.haplo else 1),
+        "fragments_per_gpu": int(nfrag), "fragments_total": int(ntot),
+        "representation": "distinct hit classes with fragment counts k (src/mmseq.cpp:395-441)" if args.layout == "collapsed"
+                          else "one row per fragment (k == 1)" + (", fp32 per-hit weights" if args.weights else ""),
+        "n_columns": int(totals["n"]), "hit_classes_total": int(totals["m"]), "nnz_total": int(totals["nnz"]),
+        "trace_stride": SWEEPS_PER_STEP, "seed": SEED, "scaling": args.scaling,
+        "l2": "inputs_exceed_l2" if totals["nnz"] / world * 4 > 200e6 else "inputs_near_l2_size_flush_between_steps",
+    }
+
+
+def value_classes(args, w):
+    """Hit classes of a shard as the metric counts them: DISTINCT transcript sets (the reference's definition of a hit
+    class, src/mmseq.cpp:395-441) whatever the layout — a per-fragment shard has the same classes as its collapsed form."""
+    return int(w.h.n_classes)
+
+
+# ----------------------------------------------------------------------------- reference arm
+
+def union_problem(args, world):
+    """The N shards of the weak-scaling job (or the one sample of a strong-scaling job) as one problem: what a
+    single CPU box has to sweep to do the same work."""
+    from oracle import oracle as orc
+    if args.scaling == "strong":
+        sav = (args.fragments, args.scaling)
+        args.fragments, args.scaling = (args.fragments_total or args.fragments), "weak"
+        w = make_workload(args, 0, 1)
+        args.fragments, args.scaling = sav
+        return [w], orc.Problem(w.h.row_ptr, w.h.col, w.h.k, w.length, weight=w.h.w), w.h.n
+    ws = [make_workload(args, r, world) for r in range(world)]
+    if world == 1:
+        w = ws[0]
+        return ws, orc.Problem(w.h.row_ptr, w.h.col, w.h.k, w.length, weight=w.h.w), w.h.n
+    n = ws[0].h.n
+    rp = [np.zeros(1, np.int64)]
+    off = 0
+    for w in ws:
+        assert w.h.n == n
+        rp.append(w.h.row_ptr[1:] + off)
+        off += w.h.nnz
+    k = None if ws[0].h.k is None else np.concatenate([w.h.k for w in ws])
+    P = orc.Problem(np.concatenate(rp), np.concatenate([w.h.col for w in ws]), k, ws[0].length)
+    return ws, P, n
 
 
 def run_reference(args, rank, world):
-    """The reference's algorithm on the host cores (oracle/ port), same workload and metric."""
+    """The reference's algorithm on the host cores (oracle/ port): the same job — all N shards — in the same
+    (collapsed) representation, on every host core of the box."""
     if rank != 0:
         return
-    from oracle import oracle as orc
-    s, h, length, prep = make_workload(args, 0, 1)
-    P = orc.Problem(h.row_ptr, h.col, h.k, length)
+    if args.weights:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference has no per-hit weights (M is boolean, src/mmseq.cpp:72); "
+                          "config 4's weighted stream has no CPU reference arm"}), flush=True)
+        return
+    ws, P, n = union_problem(args, world)
+    totals = {"n": n, "m": sum(value_classes(args, w) for w in ws), "nnz": P.nnz}
     mu, _, _ = P.init_mu()
-    threads = orc.max_threads()
+    threads = host_threads()
     mu, _, _ = P.gibbs_gsl(mu, SEED, max(1, args.warmup), threads=threads)  # warm-up sweeps
     secs = []
     for _ in range(args.steps):
-        mu, _, sec = P.gibbs_gsl(mu, SEED, 1, threads=threads)  # one step of the reference arm = ONE sweep
+        mu, _, sec = P.gibbs_gsl(mu, SEED, 1, threads=threads)  # one step of the reference arm = ONE sweep (bounded sample)
         secs.append(sec)
     tot = float(np.sum(secs))
     sweeps_per_s = args.steps / tot
-    value = sweeps_per_s * h.m
+    value = sweeps_per_s * totals["m"]
     line = {
         "impl": "reference", "metric": "gibbs_hit_class_allocations_per_s", "value": value, "unit": "allocations/s",
         "sweeps_per_s": sweeps_per_s, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1000.0 * tot / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, h, 1, sweeps_per_step=1),
-        "cpu_baseline": {"value": value, "unit": "allocations/s", "cores": threads, "kind": "port",
-                         "sample": f"{args.steps} full sweeps over all {h.m} classes of one shard (1 sweep per step)"},
+        "ms_per_step": 1000.0 * tot / args.steps, "sweeps_per_step": 1, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world, totals),
+        "cpu_baseline": {"value": value, "unit": "allocations/s", "sweeps_per_s": sweeps_per_s, "cores": threads, "kind": "port",
+                         "layout": args.layout,
+                         "sample": f"{args.steps} full sweeps (1 per step) over all {totals['m']} hit classes of the {world} shard(s)"},
         "e2e": {"value": value, "unit": "allocations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "oracle port of src/mmseq.cpp:851-918 (MT19937 per OpenMP thread, GSL-style samplers, dense per-thread "
-                "partials); the reference's own main() builds here only against the stand-in Boost/GSL of oracle/shim and needs minutes per sweep at this size (DESIGN.md section 9)",
+        "note": "oracle port of src/mmseq.cpp:851-918 (MT19937 per OpenMP thread, GSL-style samplers, dense per-thread partials) on "
+                f"{threads} host threads; the denominator depends on the box's core count. The reference's own main() builds here only "
+                "against the stand-in Boost/GSL of oracle/shim and needs minutes per sweep at this size (DESIGN.md section 9)",
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_config(args, h, world, sweeps_per_step=SWEEPS_PER_STEP):
-    return {
-        "workload": ("C3-haplotype-" if getattr(args, "haplo", False) else "C2-") + args.layout + ("-weighted" if args.weights else ""),
-        "transcripts": args.transcripts, "fragments_per_gpu": args.fragments, "fragments_total": args.fragments * world,
-        "n_columns": int(h.n), "classes_per_gpu": int(h.m), "nnz_per_gpu": int(h.nnz), "distinct_classes_per_gpu": int(h.n_classes),
-        "sweeps_per_step": sweeps_per_step, "trace_stride": SWEEPS_PER_STEP, "seed": SEED,
-        "count_path": "transposed" if args.transposed else "fused_reduction",
-        "count_exchange": ("none" if world == 1 else ("nccl_allreduce" if getattr(args, "nccl_only", False) else "fused_p2p_gamma")),
-        "l2": "inputs_exceed_l2" if (4 * h.nnz + 8 * h.m) > 200e6 else "inputs_fit_l2_flush_between_steps",
-    }
+# ----------------------------------------------------------------------------- gates
+
+def run_gates(args, H, w, mu0_gpu, mu_em_gpu, em_iters_gpu, rank, world, dev, allreduce):
+    """Correctness gates at the benchmark shape.  `allreduce(np array) -> np array` sums over ranks.
+    Returns the dict printed as "gates" (rank 0) — every rank computes the same verdict."""
+    from mmseq_b200 import capi
+    from oracle import oracle as orc
+    h = w.h
+    P = orc.Problem(h.row_ptr, h.col, h.k, w.length, weight=h.w)
+    threads = max(1, host_threads() // max(1, world if world <= 8 else 8))
+    g = {"shape": f"{h.m} rows / {h.nnz} entries per rank, {world} rank(s)"}
+    t0 = time.time()
+    # initial mu (src/mmseq.cpp:617-638): every shard's sum of k/|i|, summed over the ranks, over l
+    mu0, _, _ = P.init_mu()
+    if world > 1:
+        mu0 = allreduce(mu0 * w.length) / w.length
+    rel0 = float(np.max(np.abs(mu0_gpu / mu0 - 1.0)))
+    g["init_mu"] = {"max_rel_err": rel0, "tol": 1e-12, "ok": bool(rel0 <= 1e-12)}
+    # (b) EM from the same start: oracle iteration split over the shards (orc_em_partial = one shard's part of src/mmseq.cpp:781-802)
+    mu = mu0_gpu.copy()
+    acc, ll = P.em_partial(mu)
+    loglik = float(allreduce(np.array([ll]))[0]) - float((mu * w.length).sum())
+    llr, it = 1.1, 0
+    while it < 1000 and llr > 0.1:
+        acc = allreduce(P.em_partial(mu)[0])
+        mu2 = mu * acc / w.length
+        ll2 = float(allreduce(np.array([P.em_partial(mu2)[1]]))[0]) - float((mu2 * w.length).sum())
+        llr, loglik, mu = ll2 - loglik, ll2, mu2
+        it += 1
+    rel = float(np.max(np.abs(mu_em_gpu / mu - 1.0)))
+    g["em"] = {"iters_gpu": int(em_iters_gpu), "iters_oracle": int(it), "max_rel_err": rel, "tol": 1e-6,
+               "ok": bool(it == em_iters_gpu and rel <= 1e-6)}
+    g["em_s"] = round(time.time() - t0, 2)
+    # (a) bit-exact sweeps from the EM estimate
+    t0 = time.time()
+    H.set_mu(mu)
+    cur = mu.copy()
+    ok_counts = ok_mu = True
+    base_sweep = 900000
+    for s in range(args.gate_sweeps):
+        _, c_gpu, mu_gpu = H.sweep_debug(SEED, base_sweep + s, capi.MMQ_GIBBS_DEFAULT, want_x=False)
+        c_cpu = allreduce(P.sweep_counts(cur, SEED, base_sweep + s, class_id_base=w.cid_base, threads=threads).astype(np.int64)).astype(np.int32)
+        mu_cpu = P.gamma_replay(c_cpu, SEED, base_sweep + s)
+        ok_counts &= bool(np.array_equal(c_gpu, c_cpu))
+        ok_mu &= bool(np.array_equal(mu_gpu, mu_cpu))
+        cur = mu_cpu
+        H.set_mu(cur)
+    sha = hashlib.sha256(H.get_mu().tobytes()).hexdigest()[:16]
+    g["sweeps"] = {"n": args.gate_sweeps, "counts_bit_exact": ok_counts, "mu_bit_exact": ok_mu, "mu_sha256_16": sha,
+                   "fragments_conserved": bool(int(c_gpu.astype(np.int64).sum()) == int(allreduce(np.array([float(w.nfrag)]))[0]))}
+    # X of one sweep, entry by entry (the X-materialising kernel + transposed reduction): own shard vs own replay
+    ok_x = True
+    if h.nnz <= 150_000_000:
+        x_cpu, _, _ = P.sweep_replay(cur, SEED, base_sweep + 100, class_id_base=w.cid_base, do_gamma=False)
+        x_gpu, c2, _ = H.sweep_debug(SEED, base_sweep + 100, capi.MMQ_GIBBS_TRANSPOSED)
+        ok_x = bool(np.array_equal(x_gpu, x_cpu))
+    ok_all = allreduce(np.array([float(ok_x), float(ok_counts), float(ok_mu)]))
+    g["sweeps"]["x_bit_exact"] = bool(ok_all[0] == world) if h.nnz <= 150_000_000 else "skipped (shard above 150M entries)"
+    g["sweeps"]["ok"] = bool(ok_all.min() == world and g["sweeps"]["fragments_conserved"])
+    g["sweeps_s"] = round(time.time() - t0, 2)
+    g["ok"] = bool(g["init_mu"]["ok"] and g["em"]["ok"] and g["sweeps"]["ok"])
+    g["mu_em"] = mu
+    return g
 
 
-def collapsed_line(args, s, dev, stream, length_full=None, steps=5, warmup=3):
-    """Sweeps/s of the collapsed layout of the same synthetic sample (device-timed, CUDA events)."""
-    import torch
-    from mmseq_b200 import capi, hostlib
-    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_COLLAPSED | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
-    length = s.efflen[h.col2hdr] * args.fragments / 1e9
-    rp_s, col_s, k_s, class_id = hostlib.sort_classes_by_cost(h)
-    H = capi.Handle(rp_s, col_s, k_s, length, class_id=class_id, device=dev.index)
-    H.set_stream(stream.cuda_stream)
-    H.init_mu()
-    cls = H.cls_stats()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # the packed classes fit the L2: flush between steps
-    sweep = 0
+def posterior_gate(args, H, w, mu_em, cpu_sweeps, threads):
+    """(c) posterior mean of log mu: GPU chain vs the reference-like GSL chain on the host cores, both from the EM
+    estimate; also the CPU baseline (the same run is timed).  N = 1 only."""
+    from oracle import oracle as orc
+    h = w.h
+    P = orc.Problem(h.row_ptr, h.col, h.k, w.length)
     S = SWEEPS_PER_STEP
+    burn = S  # one stride of burn-in on both chains (they start at the mode)
+    Lc = max(1, cpu_sweeps // S)
+    mu_c, _, _ = P.gibbs_gsl(mu_em, SEED, burn, threads=threads)
+    t_cpu = 0.0
+    tr_c = np.zeros((h.n, Lc))
+    for j in range(Lc):   # stride S: slot j = state after S more sweeps
+        mu_c, _, sec = P.gibbs_gsl(mu_c, SEED + 1 + j, S, threads=threads)
+        t_cpu += sec
+        tr_c[:, j] = mu_c
+    cpu_sps = Lc * S / t_cpu
+    Lg = 256
+    H.set_mu(mu_em)
+    H.gibbs(SEED, 0, burn + Lg * S, stride=S, trace_len=Lg + 1)
+    tr_g = H.get_trace()[:, 1:]   # slot 0 is sweep 0
+    with np.errstate(divide="ignore"):
+        lg, lc = np.log(tr_g), np.log(tr_c)
+    sd = lg.std(axis=1, ddof=1)
+    # lag-1 autocorrelation of the GPU chain at this stride -> integrated autocorrelation time (AR(1) form), floor 1
+    x = lg - lg.mean(axis=1, keepdims=True)
+    rho = np.clip((x[:, 1:] * x[:, :-1]).sum(axis=1) / np.maximum((x * x).sum(axis=1), 1e-300), 0.0, 0.95)
+    tau = (1 + rho) / (1 - rho)
+    se = sd * np.sqrt(tau) * np.sqrt(1.0 / Lg + 1.0 / Lc)
+    diff = np.abs(lg.mean(axis=1) - lc.mean(axis=1))
+    finite = np.isfinite(diff) & np.isfinite(se) & (se > 0)
+    frac = float((diff[finite] <= 4.0 * se[finite]).mean())
+    sd_c = lc.std(axis=1, ddof=1) if Lc > 2 else None
+    sd_ratio = float(np.median(sd_c[finite] / sd[finite])) if sd_c is not None else None
+    gate = {"chains": f"GPU {Lg} samples, CPU (GSL-like, {threads} threads) {Lc} samples, stride {S}, both from the EM estimate after {burn} sweeps",
+            "frac_within_4se": frac, "need": 0.999, "median_sd_ratio_cpu_over_gpu": sd_ratio, "features": int(finite.sum()),
+            "ok": bool(frac >= 0.999), "hard_fail_below": 0.99}
+    base = {"value": cpu_sps * value_classes(args, w), "unit": "allocations/s", "sweeps_per_s": cpu_sps, "cores": threads, "kind": "port",
+            "layout": w.layout, "sample": f"{Lc * S} full sweeps of the same shard (collapsed representation) after {burn} warm-up sweeps"}
+    return gate, base
 
-    def step(flags):
+
+# ----------------------------------------------------------------------------- ours
+
+def timed_run(args, H, w, stream, dev, barrier, K, W, flush_buf, flags):
+    """W warm-up steps, K timed steps through mmq_gibbs (the production launch path), then the same K steps once more
+    with per-launch events for the kernel shares.  Returns (ms, alloc_ms, alloc_n, gamma_ms, gamma_n, launches, clocks)."""
+    import torch
+    from mmseq_b200 import capi
+    S = SWEEPS_PER_STEP
+    L = 2 * K + W + 1
+    sweep = 0
+
+    def step(fl):
         nonlocal sweep
-        with torch.cuda.stream(stream):
-            flush.zero_()
-        H.gibbs(SEED, sweep, S, stride=S, trace_len=steps + warmup + 1, flags=flags)
+        if flush_buf is not None:
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+        H.gibbs(SEED, sweep, S, stride=S, trace_len=L, flags=fl)
         sweep += S
 
-    for _ in range(warmup):
-        step(capi.MMQ_GIBBS_DEFAULT)
+    for _ in range(W):
+        step(flags)
     H.synchronize()
-    for _ in range(steps):
-        step(capi.MMQ_GIBBS_TIME_KERNELS)
+    launches0 = capi.launch_count()
+    sampler = ClockSampler(physical_gpu_index(dev.index))
+    barrier()
+    sampler.start()
+    # one event pair per step: the L2 flush between steps (collapsed shards are about the size of the L2) is outside
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    for a, b in evs:
+        if flush_buf is not None:
+            with torch.cuda.stream(stream):
+                flush_buf.zero_()
+        a.record(stream)
+        H.gibbs(SEED, sweep, S, stride=S, trace_len=L, flags=flags)
+        b.record(stream)
+        sweep += S
+    H.synchronize()
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    launches = capi.launch_count() - launches0
+    ms = float(sum(a.elapsed_time(b) for a, b in evs))
+    H.kernel_times()   # drop anything pending
+    for _ in range(K):
+        step(flags | capi.MMQ_GIBBS_TIME_KERNELS)
     alloc_ms, alloc_n, gamma_ms, gamma_n = H.kernel_times()
+    return ms, alloc_ms, alloc_n, gamma_ms, gamma_n, launches, sampler.result()
+
+
+def extra_weighted_line(args, dev, stream, peak):
+    """The same sample one row per fragment with fp32 per-hit weights (config 4's stream: the only compulsory
+    per-fragment traffic), device-timed, with its own roofline."""
+    import torch
+    from mmseq_b200 import capi
+    w = make_workload(args, 0, 1, weights=True, layout="perfragment")
+    h = w.h
+    H = capi.Handle(h.row_ptr, h.col, None, w.length, weight=h.w, device=dev.index)
+    H.set_stream(stream.cuda_stream)
+    H.init_mu()
+    rows = H.rows_stats() if hasattr(H, "rows_stats") else None
+    barrier = lambda: torch.cuda.synchronize()
+    ms, alloc_ms, alloc_n, gamma_ms, gamma_n, launches, clocks = timed_run(args, H, w, stream, dev, barrier, 5, 3, None, capi.MMQ_GIBBS_DEFAULT)
     H.close()
-    per_sweep = alloc_ms / max(alloc_n, 1) + gamma_ms / max(gamma_n, 1)
-    b = 4 * cls["packed_slots"] + 6 * cls["class_slots"] + 20 * cls["rest_classes"] + 4 * cls["rest_nnz"]
-    return {"workload": "C2-collapsed", "classes": int(h.m), "nnz": int(h.nnz), "kernel": "k_alloc_cls",
-            "alloc_avg_launch_ms": alloc_ms / max(alloc_n, 1), "gamma_avg_launch_ms": gamma_ms / max(gamma_n, 1),
-            "sweeps_per_s_kernels": 1000.0 / per_sweep, "fragments_per_s_kernels": 1000.0 / per_sweep * args.fragments,
-            "algorithmic_bytes_per_launch": int(b), "class_plan": cls,
-            "note": "kernel time per sweep (allocation + Gamma, CUDA events), launch gaps not included; python bench.py --layout collapsed gives the full line"}
+    b_alloc, _ = algorithmic_bytes(h, h.n, True, False, SWEEPS_PER_STEP, "perfragment", rows=rows)
+    a = alloc_ms / max(alloc_n, 1)
+    return {"workload": workload_name(args, "perfragment", True), "rows": int(h.m), "nnz": int(h.nnz),
+            "kernel": "k_alloc_rows" if rows and rows.get("in_use") else "k_alloc_seg4",
+            "sweeps_per_s": 5 * SWEEPS_PER_STEP / (ms / 1e3), "alloc_avg_launch_ms": a, "gamma_avg_launch_ms": gamma_ms / max(gamma_n, 1),
+            "algorithmic_bytes_per_launch": b_alloc,
+            "roofline": {"bound": "hbm", "achieved": b_alloc / (a * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": b_alloc / (a * 1e-3) / 1e9 / peak}, "plan": rows}
 
 
 def main():
@@ -273,66 +505,49 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    s, h, length, prep = make_workload(args, rank, world)
-    n = h.n
-    flags = capi.MMQ_GIBBS_TRANSPOSED if args.transposed else capi.MMQ_GIBBS_DEFAULT
-    small = (4 * h.nnz + 8 * h.m) <= 200e6
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
+    def allreduce(a):
+        """Sum of a host array over the ranks (through the GPUs: the process group is NCCL)."""
+        if world == 1:
+            return a
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        dist.all_reduce(t)
+        return t.cpu().numpy()
 
+    w = make_workload(args, rank, world)
+    h, n = w.h, w.h.n
+    flags = capi.MMQ_GIBBS_TRANSPOSED if args.transposed else capi.MMQ_GIBBS_DEFAULT
+    near_l2 = (4 * h.nnz) <= 200e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if near_l2 else None
     stream = torch.cuda.Stream(device=dev)
-    cid_base = rank * args.fragments
-    class_id = None
-    if args.layout == "collapsed":   # device order by cost, Philox counters stay canonical (as the host program does)
-        from mmseq_b200 import hostlib
-        rp_s, col_s, k_s, class_id = hostlib.sort_classes_by_cost(h)
-        class_id = class_id + cid_base
-        h.row_ptr, h.col, h.k = rp_s, col_s, k_s
-    H = capi.Handle(h.row_ptr, h.col, h.k, length, weight=h.w, class_id_base=cid_base, device=local, class_id=class_id)
-    H.set_stream(stream.cuda_stream)
-    if world > 1:
-        uid = [capi.comm_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        H.comm_init(uid[0], rank, world)
-        if not args.nccl_only:   # count exchange fused into the Gamma kernel over NVLink peer memory
+
+    def attach(Hx, reuse_from=None):
+        if world == 1:
+            return
+        if reuse_from is not None:
+            reuse_from.comm_move_to(Hx)   # the process keeps its NCCL communicator across samples
+        else:
+            uid = [capi.comm_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            Hx.comm_init(uid[0], rank, world)
+        if not args.nccl_only and not Hx.p2p_attached():   # count exchange fused into the Gamma kernel over NVLink peer memory
             hs = [None] * world
-            dist.all_gather_object(hs, H.p2p_export())
-            H.p2p_attach(hs, rank, world)
+            dist.all_gather_object(hs, Hx.p2p_export())
+            Hx.p2p_attach(hs, rank, world)
+
+    H = capi.Handle(h.row_ptr, h.col, h.k, w.length, weight=h.w, class_id_base=w.cid_base, device=local)
+    H.set_stream(stream.cuda_stream)
+    attach(H)
     H.init_mu()
     mu0 = H.get_mu()
+    t0 = time.perf_counter()
+    em_iters, em_ll, _ = H.em(1000, 0.1)
+    em_s = time.perf_counter() - t0
+    mu_em = H.get_mu()
     cls = H.cls_stats() if h.k is not None else None
+    rows = H.rows_stats() if (h.k is None and hasattr(H, "rows_stats")) else None
 
     K, W, S = args.steps, args.warmup, SWEEPS_PER_STEP
-    L = K + W + 1
-    sweep = 0
-
-    def step(timed_flags):
-        nonlocal sweep
-        if flush_buf is not None:
-            with torch.cuda.stream(stream):
-                flush_buf.zero_()
-        H.gibbs(SEED, sweep, S, stride=S, trace_len=L, flags=timed_flags)
-        sweep += S
-
-    for _ in range(W):
-        step(flags)
-    H.synchronize()
-    launches0 = capi.launch_count()
-    sampler = ClockSampler(physical_gpu_index(local))
-    barrier()
-    sampler.start()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(K):
-        step(flags | capi.MMQ_GIBBS_TIME_KERNELS)
-    ev1.record(stream)
-    H.synchronize()
-    barrier()
-    sampler.stop_flag = True
-    sampler.join()
-    launches = capi.launch_count() - launches0
-    ms = ev0.elapsed_time(ev1)
-    alloc_ms, alloc_n, gamma_ms, gamma_n = H.kernel_times()
+    ms, alloc_ms, alloc_n, gamma_ms, gamma_n, launches, clocks = timed_run(args, H, w, stream, dev, barrier, K, W, flush_buf, flags)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
@@ -342,23 +557,18 @@ def main():
         per_rank = {"alloc_ms": [p[0] for p in pr], "gamma_ms": [p[1] for p in pr], "step_ms": [p[2] for p in pr]}
     ms_max = float(t.item())
     sweeps_per_s = K * S / (ms_max / 1000.0)
-    m_total = h.m * world  # every rank holds fragments_per_gpu rows (weak scaling)
-    value = sweeps_per_s * m_total
+    totals = {"n": n, "m": int(allreduce(np.array([float(value_classes(args, w))]))[0]), "nnz": int(allreduce(np.array([float(h.nnz)]))[0])}
+    value = sweeps_per_s * totals["m"]
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
         pin = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
-        rp, col, kk, ww, ll, mu_h = pin(h.row_ptr), pin(h.col), pin(h.k), pin(h.w), pin(length), pin(mu0)
+        rp, col, kk, ww, ll, mu_h = pin(h.row_ptr), pin(h.col), pin(h.k), pin(h.w), pin(w.length), pin(mu_em)
         barrier()
         t0 = time.perf_counter()
-        H2 = capi.Handle(rp, col, kk, ll, weight=ww, class_id_base=cid_base, device=local, class_id=class_id)   # H2D of the CSR shard
-        if world > 1:
-            H.comm_move_to(H2)   # the process keeps its NCCL communicator across samples
-            if not args.nccl_only:
-                hs = [None] * world
-                dist.all_gather_object(hs, H2.p2p_export())
-                H2.p2p_attach(hs, rank, world)
+        H2 = capi.Handle(rp, col, kk, ll, weight=ww, class_id_base=w.cid_base, device=local)   # H2D of the CSR shard
+        attach(H2, reuse_from=H)
         H2.set_mu(mu_h)                                                                        # H2D
         H2.gibbs(SEED, 0, K * S, stride=S, trace_len=K, flags=flags)
         mu_out = H2.get_mu()                                                                   # D2H
@@ -371,73 +581,113 @@ def main():
         wall = float(tw.item())
         h2d = rp.nbytes + col.nbytes + (kk.nbytes if kk is not None else 0) + (ww.nbytes if ww is not None else 0) + ll.nbytes + mu_h.nbytes
         d2h = mu_out.nbytes + tr.nbytes
-        e2e = {"value": K * S / wall * m_total, "unit": "allocations/s", "sweeps_per_s": K * S / wall,
+        e2e = {"value": K * S / wall * totals["m"], "unit": "allocations/s", "sweeps_per_s": K * S / wall,
                "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K), "wall_s": wall,
-               "what": "mmq_create(H2D shard) + mmq_set_mu + steps*16 sweeps + mmq_get_mu + mmq_get_trace, pinned host buffers"}
+               "what": "mmq_create(H2D shard, plan) + mmq_set_mu + steps*16 sweeps + mmq_get_mu + mmq_get_trace, pinned host buffers"}
         assert np.isfinite(tr).all() and (tr > 0).any()
+        H, H2 = H2, H   # keep the handle that owns the communicator
         H2.close()
-    H.close()
 
-    # ---- roofline of the dominant kernel (k_alloc), device time from CUDA events on its stream
+    # ---- roofline of the dominant kernel (the allocation), device time from CUDA events on its stream
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak = float(json.load(open(peaks_path))["hbm_gbs"]); peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak = 6650.0; peak_src = "fallback (B200_PROFILING.md 6.65 TB/s)"
-    b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S, args.layout, cls)
+    b_alloc, b_sweep = algorithmic_bytes(h, n, args.weights, args.transposed, S, args.layout, cls, rows)
     alloc_ms_avg = alloc_ms / max(alloc_n, 1)
+    gamma_ms_avg = gamma_ms / max(gamma_n, 1)
     achieved = b_alloc / (alloc_ms_avg * 1e-3) / 1e9 if alloc_n else None
-    kernel_name = "k_alloc_seg4" if (args.layout == "perfragment" and not args.transposed) else ("k_alloc_cat" if h.k is None and not args.transposed else "k_alloc")
-    if cls and cls["in_use"] and not args.transposed:
+    if args.transposed:
+        kernel_name = "k_alloc"
+    elif cls and cls["in_use"]:
         kernel_name = "k_alloc_cls"
+    elif rows and rows.get("in_use"):
+        kernel_name = "k_alloc_rows"
+    else:
+        kernel_name = "k_alloc_seg4" if h.k is None else "k_alloc"
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and args.fragments == N_C2 and args.transcripts == T_C2 and not args.weights:
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath) and args.fragments == N_C2 and args.transcripts == T_C2:
         tj = json.load(open(tpath)).get(kernel_name)
-        if tj and tj.get("workload") == f"C2-{args.layout}" and not args.haplo:
+        if tj and tj.get("workload") == workload_name(args):
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]   # per launch, from one ncu --set full capture
+    per_sweep_ms = ms_max / (K * S)
     roofline = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(b_alloc), "avg_launch_ms": alloc_ms_avg, "launches_timed": int(alloc_n),
-                "share_of_step": alloc_ms / ms if ms > 0 else None,
-                "gamma_avg_launch_ms": gamma_ms / max(gamma_n, 1),
-                "sweep_bytes": int(b_sweep), "sweep_gbs": b_sweep * sweeps_per_s / 1e9}
+                "share_of_sweep": alloc_ms_avg / per_sweep_ms if per_sweep_ms > 0 else None,
+                "gamma_avg_launch_ms": gamma_ms_avg, "sweep_ms": per_sweep_ms,
+                "launch_gap_us_per_sweep": 1e3 * (per_sweep_ms - alloc_ms_avg - gamma_ms_avg),
+                "sweep_bytes": int(b_sweep), "sweep_gbs": b_sweep / (per_sweep_ms * 1e-3) / 1e9,
+                "how": "value: K steps through mmq_gibbs (CUDA graph of 16 sweeps), CUDA events on the handle's stream; kernel "
+                       "durations: the same K steps repeated with MMQ_GIBBS_TIME_KERNELS (events around every allocation / Gamma "
+                       "launch; a collapsed shard's allocation is up to four concurrent kernels timed as one)"}
     if per_rank:
         roofline["per_rank"] = per_rank
     if cls:
         roofline["class_plan"] = cls
+    if rows:
+        roofline["row_plan"] = rows
 
     line = {
         "metric": "gibbs_hit_class_allocations_per_s", "value": value, "unit": "allocations/s",
-        "sweeps_per_s": sweeps_per_s, "fragments_per_s": sweeps_per_s * args.fragments * world,
-        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, h, world), "clocks": sampler.result(),
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "prep": prep,
+        "sweeps_per_s": sweeps_per_s, "fragments_per_s": sweeps_per_s * w.ntot,
+        "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_max / K, "sweeps_per_step": S, "higher_is_better": True,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world, totals), "clocks": clocks,
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "prep": w.prep,
+        "em": {"iters": int(em_iters), "loglik": em_ll, "wall_s": round(em_s, 4)},
+        "count_path": "transposed" if args.transposed else "fused_reduction",
+        "count_exchange": ("none" if world == 1 else ("nccl_allreduce" if args.nccl_only else "fused_p2p_gamma")),
     }
 
-    # ---- the same sample in the reference's own representation (distinct classes + counts k, what the
-    # host program feeds the GPU): class-plan kernel, reported beside the headline (N = 1 only)
-    if rank == 0 and world == 1 and args.layout == "perfragment" and not args.no_collapsed and not args.weights and not args.haplo:
-        try:
-            line["collapsed_layout"] = collapsed_line(args, s, dev, stream, length_full=None)
-        except Exception as e:   # an extra: never at the expense of the headline line
-            line["collapsed_layout"] = {"error": repr(e)}
-
-    # ---- CPU baseline beside it (rank 0, N = 1 only): the oracle port on the host cores
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # ---- correctness gates at the benchmark shape, every rank
+    gates_ok = True
+    if not args.no_gates:
+        g = run_gates(args, H, w, mu0, mu_em, em_iters, rank, world, dev, allreduce)
+        mu_oracle_em = g.pop("mu_em")
+        if world == 1 and not args.no_cpu_baseline and not args.weights:
+            # (c) + CPU baseline: the reference-like chain on the collapsed representation of the same sample
+            wc = w if w.layout == "collapsed" else make_workload(args, 0, 1, weights=False, layout="collapsed")
+            if wc is w:
+                pg, base = posterior_gate(args, H, wc, mu_oracle_em, args.cpu_sweeps, host_threads())
+                g["posterior"] = pg   # statistical: reported against 0.999, the run only FAILS on a gross miss
+                g["ok"] = bool(g["ok"] and pg["frac_within_4se"] >= pg["hard_fail_below"])
+            else:
+                from oracle import oracle as orc
+                Pc = orc.Problem(wc.h.row_ptr, wc.h.col, wc.h.k, wc.length)
+                mu_c, _, _ = Pc.init_mu()
+                mu_c, _, _ = Pc.gibbs_gsl(mu_c, SEED, 1, threads=host_threads())
+                _, _, sec = Pc.gibbs_gsl(mu_c, SEED, 8, threads=host_threads())
+                base = {"value": 8 / sec * value_classes(args, wc), "unit": "allocations/s", "sweeps_per_s": 8 / sec, "cores": host_threads(),
+                        "kind": "port", "layout": "collapsed", "sample": "8 full sweeps of the collapsed form of the same sample after 1 warm-up sweep"}
+            line["cpu_baseline"] = base
+        line["gates"] = g
+        gates_ok = g["ok"]
+    elif rank == 0 and world == 1 and not args.no_cpu_baseline and not args.weights:
         from oracle import oracle as orc
-        P = orc.Problem(h.row_ptr, h.col, h.k, length)
-        threads = orc.max_threads()
-        mu_c, _, _ = P.gibbs_gsl(mu0, SEED, 1, threads=threads)
-        _, _, sec = P.gibbs_gsl(mu_c, SEED, args.cpu_sweeps, threads=threads)
-        cpu_sps = args.cpu_sweeps / sec
-        line["cpu_baseline"] = {"value": cpu_sps * h.m, "unit": "allocations/s", "sweeps_per_s": cpu_sps, "cores": threads,
-                                "kind": "port", "sample": f"{args.cpu_sweeps} full sweeps of the same shard after 1 warm-up sweep"}
+        P = orc.Problem(h.row_ptr, h.col, h.k, w.length)
+        mu_c, _, _ = P.gibbs_gsl(mu0, SEED, 1, threads=host_threads())
+        _, _, sec = P.gibbs_gsl(mu_c, SEED, 8, threads=host_threads())
+        line["cpu_baseline"] = {"value": 8 / sec * value_classes(args, w), "unit": "allocations/s", "sweeps_per_s": 8 / sec,
+                                "cores": host_threads(), "kind": "port", "layout": w.layout,
+                                "sample": "8 full sweeps of the same shard after 1 warm-up sweep"}
+    H.close()
+
+    # ---- the compulsory per-fragment stream of the same sample (fp32 per-hit weights), N = 1 default run only
+    if rank == 0 and world == 1 and args.layout == "collapsed" and not args.no_extras and not args.haplo and args.scaling == "weak":
+        try:
+            line["perfragment_weighted"] = extra_weighted_line(args, dev, stream, peak)
+        except Exception as e:   # an extra: never at the expense of the headline line
+            line["perfragment_weighted"] = {"error": repr(e)}
+
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    if not gates_ok:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

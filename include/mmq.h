@@ -87,7 +87,9 @@ int64_t mmq_device_bytes(const mmq_handle* h);
 int mmq_comm_id(char id[128]);
 int mmq_comm_init(mmq_handle* h, const char id[128], int rank, int nranks);
 /* Hand the communicator of `from` (which keeps none) to `to`: lets a long-lived process load
- * the next sample's shard without paying NCCL initialisation again. */
+ * the next sample's shard without paying NCCL initialisation again.  A peer-memory attachment
+ * (mmq_p2p_attach*) moves along when both handles have the same n; every rank must then make the
+ * same move between the same two sweeps. */
 int mmq_comm_move(mmq_handle* from, mmq_handle* to);
 
 /* Fused count exchange over NVLink peer memory (optional, on top of the communicator).
@@ -103,6 +105,8 @@ int mmq_comm_move(mmq_handle* from, mmq_handle* to);
 int mmq_p2p_export(mmq_handle* h, char ipc_handle[64]);
 int mmq_p2p_attach(mmq_handle* h, const char* ipc_handles, int rank, int nranks);
 int mmq_p2p_attach_local(mmq_handle** handles, int nranks);
+/* Ranks attached through mmq_p2p_attach*(), 0 when the handle exchanges counts through NCCL (or is alone). */
+int mmq_p2p_attached(const mmq_handle* h);
 
 /* mu0[t] = (sum_{i containing t} k[i]/|i|)/l[t] and unique_hits[t] =
  * counts_shared[t][0]; src/mmseq.cpp:617-638.  Leaves mu0 as the current mu.

@@ -54,6 +54,7 @@ def _load():
         "mmq_p2p_export": (i32, [vp, C.c_char_p]),
         "mmq_p2p_attach": (i32, [vp, C.c_char_p, i32, i32]),
         "mmq_p2p_attach_local": (i32, [C.POINTER(vp), i32]),
+        "mmq_p2p_attached": (i32, [vp]),
         "mmq_init_mu": (i32, [vp, vp]),
         "mmq_set_mu": (i32, [vp, vp]),
         "mmq_get_mu": (i32, [vp, vp]),
@@ -95,7 +96,7 @@ def lib():
 
 EXPORTS = [
     "mmq_create", "mmq_destroy", "mmq_last_error", "mmq_set_stream", "mmq_get_stream", "mmq_synchronize",
-    "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_p2p_export", "mmq_p2p_attach", "mmq_p2p_attach_local", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
+    "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_p2p_export", "mmq_p2p_attach", "mmq_p2p_attach_local", "mmq_p2p_attached", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
     "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_cls_stats", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
     "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_warmup", "mmq_version",
@@ -229,6 +230,9 @@ class Handle:
         blob = b"".join(handles)
         assert len(blob) == 64 * nranks
         self._check(lib().mmq_p2p_attach(self._h, blob, rank, nranks), "mmq_p2p_attach")
+
+    def p2p_attached(self):
+        return int(lib().mmq_p2p_attached(self._h))
 
     def init_mu(self):
         uh = np.zeros(self.n, np.int32)

@@ -581,62 +581,47 @@ __global__ void k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict_
   }
 }
 
-/* K3 + K4 fused over NVLink peer memory.  Block 0 publishes this rank's epoch into every peer's
- * flag word (its allocation kernel has completed: stream order), every block waits until all
- * ranks have published this epoch, then each thread sums the count vectors of all ranks with
- * P2P loads and draws the Gamma variate — identical on every rank (same counter-based stream).
- * The other parity buffer (nobody reads it any more: everyone passed this epoch's barrier only
- * after finishing the previous Gamma kernel) is reset for the next sweep. */
+/* ---- K3 + K4 fused over NVLink peer memory -------------------------------------------------------
+ * Every rank owns a peer-mapped block (mmq_internal.h: MMQ_P2P_*): two flag arrays, the two parity
+ * buffers of its count vector and its mu vector.  Flags are written with st.release.sys into the
+ * peers' blocks and polled locally with ld.acquire.sys. */
+__device__ __forceinline__ void p2p_publish(int32_t* flag, int32_t epoch) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void p2p_wait(const int32_t* flag, int32_t epoch) {
+  int32_t v;
+  do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory"); } while (v < epoch);
+}
 struct mmq_p2p_args {
-  const int32_t* counts[MMQ_P2P_MAX]; /* this epoch's parity buffer of every rank */
-  int32_t* flags[MMQ_P2P_MAX];        /* flag array of every rank */
-  int32_t* reset;                      /* own buffer of the other parity */
-  int32_t* local_flags;
-  unsigned long long* dbg; /* MMQ_P2P_TRACE: [0] ns block 0 waited for the peers' flags, [1] launches */
-  int nranks, rank, epoch;
-  int mode; /* flag handshake: 2 (default) st.release.sys / ld.acquire.sys; MMQ_P2P_MODE=0: membar.sys on both sides
-               (measured +8 us per sweep on B200/NVSwitch), 1: plain volatile accesses */
+  char* base[MMQ_P2P_MAX]; /* peer-mapped block of every rank (own block included) */
+  int64_t off_counts;      /* this epoch's parity buffer inside a block */
+  int64_t off_reset;       /* the other parity buffer (own block only) */
+  int64_t off_mu;
+  int nranks, rank;
+  int32_t epoch;                /* + *epoch_base when replayed from a CUDA graph */
+  const int32_t* epoch_base;
 };
+
+/* Debug / parity variant (mmq_sweep_debug): a full all-reduce — every rank reads the count vectors of
+ * ALL ranks, draws every Gamma variate and keeps the summed counts.  One barrier. */
 __global__ void k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
                             double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
                             double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
-  if (blockIdx.x == 0 && threadIdx.x < a.nranks) {
-    int32_t* f = a.flags[threadIdx.x] + a.rank;
-    if (a.mode == 0) __threadfence_system();
-    if (a.mode == 2) asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(f), "r"(a.epoch) : "memory");
-    else *reinterpret_cast<volatile int32_t*>(f) = a.epoch;
-  }
-  if (threadIdx.x == 0) {
-    unsigned long long t0 = 0;
-    if (a.dbg && blockIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  const int32_t epoch = a.epoch + (a.epoch_base ? *a.epoch_base : 0);
+  int32_t* own = reinterpret_cast<int32_t*>(a.base[a.rank]);
+  if (blockIdx.x == 0 && threadIdx.x < a.nranks)
+    p2p_publish(reinterpret_cast<int32_t*>(a.base[threadIdx.x]) + MMQ_P2P_FLAG_ALLOC + 8 * a.rank, epoch);
+  if (threadIdx.x == 0)
     for (int r = 0; r < a.nranks; ++r) /* own allocation is complete by stream order: no wait on self */
-      if (r != a.rank) {
-        if (a.mode == 2) {
-          int32_t v;
-          do { asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(a.local_flags + r) : "memory"); } while (v < a.epoch);
-        } else {
-          while (*reinterpret_cast<volatile int32_t*>(a.local_flags + r) < a.epoch) { }
-        }
-      }
-    if (a.mode == 0) __threadfence_system();
-    if (a.dbg && blockIdx.x == 0) {
-      unsigned long long t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      atomicAdd(a.dbg, t1 - t0);
-      atomicAdd(a.dbg + 1, 1ull);
-      atomicMax(a.dbg + 2, t1 - t0);
-      if (t1 - t0 < 2000ull) atomicAdd(a.dbg + 3, 1ull);
-      if (t1 - t0 < 6000ull) atomicAdd(a.dbg + 4, 1ull);
-      if (t1 - t0 < 12000ull) atomicAdd(a.dbg + 5, 1ull);
-    }
-  }
+      if (r != a.rank) p2p_wait(own + MMQ_P2P_FLAG_ALLOC + 8 * r, epoch);
   __syncthreads();
   double* trace_col = nullptr;
   if (trace && stride > 0 && sweep % (uint32_t)stride == 0 && sweep / (uint32_t)stride < (uint32_t)trace_len) trace_col = trace + sweep / (uint32_t)stride;
+  int32_t* reset = reinterpret_cast<int32_t*>(a.base[a.rank] + a.off_reset);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     int32_t c = 0;
-    for (int r = 0; r < a.nranks; ++r) c += __ldcv(a.counts[r] + t);
-    a.reset[t] = counts_base ? counts_base[t] : 0;
+    for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
+    reset[t] = counts_base ? counts_base[t] : 0;
     if (counts_copy) counts_copy[t] = c;
     mmq_rng g;
     mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
@@ -644,10 +629,69 @@ __global__ void k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_b
     mu[t] = v;
     if (trace_col) trace_col[t * (int64_t)trace_len] = v;
   }
+  /* the mu flags advance too, so that a later k_gamma_rs (which waits for them) sees a monotone epoch: every rank
+   * wrote its own mu, nothing to wait for */
+  if (blockIdx.x == 0 && threadIdx.x < a.nranks)
+    p2p_publish(reinterpret_cast<int32_t*>(a.base[threadIdx.x]) + MMQ_P2P_FLAG_MU + 8 * a.rank, epoch);
 }
 
-__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
-__global__ void k_add_u32(uint32_t* p, uint32_t v) { *p += v; }
+/* Production variant: reduce-scatter + Gamma + all-gather in ONE kernel.  Rank r owns the transcripts
+ * [n r / N, n (r+1) / N): after the "allocation done" barrier it sums the N count vectors for its slice
+ * only ((N-1) 4n/N bytes over NVLink instead of (N-1) 4n), draws n/N Gamma variates instead of n, and
+ * stores each new mu into the mu vector of EVERY rank (P2P stores).  The last block to finish publishes
+ * "mu slice written" to the peers and waits for theirs, so that when the kernel completes the whole mu
+ * vector is in place on this rank: the next allocation kernel needs no other synchronisation than stream
+ * order.  The other parity buffer of the own counts is reset for the next sweep (all of it, by all blocks). */
+__global__ void k_gamma_rs(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len, int64_t n,
+                           double alpha, double beta, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base;
+  const int32_t epoch = a.epoch + (a.epoch_base ? *a.epoch_base : 0);
+  int32_t* own = reinterpret_cast<int32_t*>(a.base[a.rank]);
+  if (blockIdx.x == 0 && threadIdx.x < a.nranks)
+    p2p_publish(reinterpret_cast<int32_t*>(a.base[threadIdx.x]) + MMQ_P2P_FLAG_ALLOC + 8 * a.rank, epoch);
+  if (threadIdx.x == 0)
+    for (int r = 0; r < a.nranks; ++r)
+      if (r != a.rank) p2p_wait(own + MMQ_P2P_FLAG_ALLOC + 8 * r, epoch);
+  __syncthreads();
+  const int64_t t0 = n * a.rank / a.nranks, t1 = n * (a.rank + 1) / a.nranks;
+  for (int64_t t = t0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < t1; t += (int64_t)gridDim.x * blockDim.x) {
+    int32_t c = 0;
+    for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
+    const double v = mmq_gamma(&g, alpha + (double)c, beta + len[t]);
+    for (int r = 0; r < a.nranks; ++r) reinterpret_cast<double*>(a.base[r] + a.off_mu)[t] = v;
+  }
+  int32_t* reset = reinterpret_cast<int32_t*>(a.base[a.rank] + a.off_reset);
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    reset[t] = counts_base ? counts_base[t] : 0;
+  __threadfence_system(); /* this thread's peer stores are visible system-wide before the block signs off */
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int* done = reinterpret_cast<unsigned int*>(own + MMQ_P2P_DONE);
+    if (atomicAdd(done, 1u) == gridDim.x - 1) { /* last block of this rank */
+      *done = 0u;
+      __threadfence_system();
+      for (int r = 0; r < a.nranks; ++r)
+        p2p_publish(reinterpret_cast<int32_t*>(a.base[r]) + MMQ_P2P_FLAG_MU + 8 * a.rank, epoch);
+      for (int r = 0; r < a.nranks; ++r)
+        if (r != a.rank) p2p_wait(own + MMQ_P2P_FLAG_MU + 8 * r, epoch);
+    }
+  }
+}
+
+/* trace capture of a multi-GPU sweep: after k_gamma_rs has completed mu holds the values of all ranks */
+__global__ void k_trace_capture(const double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
+                                uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base;
+  if (sweep % (uint32_t)stride != 0 || sweep / (uint32_t)stride >= (uint32_t)trace_len) return;
+  double* col = trace + sweep / (uint32_t)stride;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+    col[t * (int64_t)trace_len] = mu[t];
+}
+
+__global__ void k_set2_u32(uint32_t* p, uint32_t a, uint32_t b) { p[0] = a; p[1] = b; }
+__global__ void k_add2_u32(uint32_t* p, uint32_t v) { p[0] += v; p[1] += v; }
 
 /* -------------------------------------------------------------- NCCL */
 
@@ -697,6 +741,7 @@ int64_t mmq_launch_count(void) { return (int64_t)g_mmq_launches.load(); }
 const char* mmq_last_error(const mmq_handle* h) { return h ? h->err.c_str() : g_mmq_create_err.c_str(); }
 
 static void drop_graph(mmq_handle* h);
+static int p2p_adopt(mmq_handle* h, int rank, int nranks);
 
 static int upload(mmq_handle* h, void** dst, const void* src, size_t bytes, size_t pad = 0) {
   int rc = mmq_dev_alloc(h, dst, bytes + pad);
@@ -887,12 +932,6 @@ void mmq_destroy(mmq_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  if (h->p2p_dbg) {
-    unsigned long long d[6] = {0, 0, 0, 0, 0, 0};
-    if (cudaMemcpy(d, h->p2p_dbg, sizeof(d), cudaMemcpyDeviceToHost) == cudaSuccess && d[1])
-      fprintf(stderr, "[mmq p2p trace] rank %d: %llu fused Gamma launches, %.2f us average wait for the peers' flags (max %.1f us; %llu < 2 us, %llu < 6 us, %llu < 12 us)\n",
-              h->p2p_rank, d[1], (double)d[0] / (double)d[1] / 1000.0, (double)d[2] / 1000.0, d[3], d[4], d[5]);
-  }
   drop_graph(h);
   for (void* p : h->p2p_opened) if (p) cudaIpcCloseMemHandle(p);
   for (cudaEvent_t e : h->ev_alloc) cudaEventDestroy(e);
@@ -960,32 +999,48 @@ int mmq_comm_init(mmq_handle* h, const char id[128], int rank, int nranks) {
 
 int mmq_comm_move(mmq_handle* from, mmq_handle* to) {
   if (!from || !to || from == to) return mmq_fail(to, MMQ_ERR_ARG, "mmq_comm_move: bad arguments");
-  if (to->comm) return mmq_fail(to, MMQ_ERR_STATE, "mmq_comm_move: destination already has a communicator");
+  if (to->comm || to->p2p_n > 1) return mmq_fail(to, MMQ_ERR_STATE, "mmq_comm_move: destination already has a communicator");
   if (from->device != to->device) return mmq_fail(to, MMQ_ERR_ARG, "mmq_comm_move: handles are on different devices");
   MMQ_CUDA(from, cudaSetDevice(from->device));
   MMQ_CUDA(from, cudaStreamSynchronize(from->stream));
   to->comm = from->comm; to->rank = from->rank; to->nranks = from->nranks;
   from->comm = nullptr; from->rank = 0; from->nranks = 1;
+  if (from->p2p_n > 1 && from->n == to->n) {
+    /* the peer mapping goes along (no cudaIpc round trip per sample): the block, the peers' mappings and the epoch
+     * counter move to `to`, whose counts and mu are copied into the block; `from` returns to its own buffers.
+     * Every rank must make the same move between the same two sweeps. */
+    drop_graph(from);
+    MMQ_CUDA(to, cudaStreamSynchronize(to->stream));
+    auto it = std::find(from->allocs.begin(), from->allocs.end(), from->p2p_buf);
+    if (it != from->allocs.end()) { from->allocs.erase(it); to->allocs.push_back(from->p2p_buf); }
+    if (to->p2p_buf) mmq_dev_free(to, to->p2p_buf);
+    to->p2p_buf = from->p2p_buf;
+    for (int r = 0; r < MMQ_P2P_MAX; ++r) { to->p2p_base[r] = from->p2p_base[r]; to->p2p_opened[r] = from->p2p_opened[r]; from->p2p_opened[r] = nullptr; from->p2p_base[r] = nullptr; }
+    to->p2p_epoch = from->p2p_epoch;
+    const int rank = from->p2p_rank, nranks = from->p2p_n;
+    MMQ_CUDA(from, cudaMemcpyAsync(from->mu_own, from->mu, sizeof(double) * (size_t)(from->n + 1), cudaMemcpyDeviceToDevice, from->stream));
+    MMQ_CUDA(from, cudaStreamSynchronize(from->stream));
+    from->mu = from->mu_own; from->counts = from->counts_own;
+    from->p2p_buf = nullptr; from->p2p_n = 0; from->p2p_rank = 0; from->p2p_epoch = 0;
+    int rc = p2p_adopt(to, rank, nranks);
+    if (rc) return rc;
+  }
   return MMQ_OK;
 }
 
 /* ---- fused count exchange over peer memory ---- */
+static inline size_t p2p_r256(size_t v) { return (v + 255) & ~(size_t)255; }
+static inline size_t p2p_off_counts(const mmq_handle* h, int parity) { return MMQ_P2P_HEAD + (size_t)parity * p2p_r256(sizeof(int32_t) * (size_t)h->n); }
+static inline size_t p2p_off_mu(const mmq_handle* h) { return MMQ_P2P_HEAD + 2 * p2p_r256(sizeof(int32_t) * (size_t)h->n); }
+
 static int p2p_alloc(mmq_handle* h) {
   if (h->p2p_buf) return MMQ_OK;
   MMQ_CUDA(h, cudaSetDevice(h->device));
   MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
-  const size_t head = 256;
-  const size_t bytes = head + 2 * sizeof(int32_t) * (size_t)h->n;
+  const size_t bytes = p2p_off_mu(h) + sizeof(double) * (size_t)(h->n + 1);
   int rc = mmq_dev_alloc(h, &h->p2p_buf, bytes);
   if (rc) return rc;
-  h->p2p_flags = (int32_t*)h->p2p_buf;
-  h->p2p_counts[0] = (int32_t*)((char*)h->p2p_buf + head);
-  h->p2p_counts[1] = h->p2p_counts[0] + h->n;
-  if (getenv("MMQ_P2P_TRACE")) h->p2p_dbg = (unsigned long long*)((char*)h->p2p_buf + 128);
-  MMQ_CUDA(h, cudaMemsetAsync(h->p2p_buf, 0, head, h->stream));
-  /* both parity buffers start from the current counts (zero, or the singleton base of a segment plan) */
-  for (int b = 0; b < 2; ++b)
-    MMQ_CUDA(h, cudaMemcpyAsync(h->p2p_counts[b], h->counts, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+  MMQ_CUDA(h, cudaMemsetAsync(h->p2p_buf, 0, bytes, h->stream));
   MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
   return MMQ_OK;
 }
@@ -1001,12 +1056,22 @@ int mmq_p2p_export(mmq_handle* h, char ipc_handle[64]) {
   return MMQ_OK;
 }
 
-static void p2p_finish_attach(mmq_handle* h, int rank, int nranks) {
-  h->p2p_rank = rank;
-  h->p2p_n = nranks;
-  h->p2p_epoch = 0;
-  h->counts_own = h->counts;
-  h->counts = h->p2p_counts[0];
+/* Point the handle's counts and mu into its peer-mapped block (keeping their current contents). */
+static int p2p_adopt(mmq_handle* h, int rank, int nranks) {
+  drop_graph(h);
+  char* own = (char*)h->p2p_buf;
+  int32_t* c[2] = {(int32_t*)(own + p2p_off_counts(h, 0)), (int32_t*)(own + p2p_off_counts(h, 1))};
+  double* pmu = (double*)(own + p2p_off_mu(h));
+  /* both parity buffers start from the current counts (zero, or the constant base of a segment / class plan) */
+  for (int b = 0; b < 2; ++b) MMQ_CUDA(h, cudaMemcpyAsync(c[b], h->counts, sizeof(int32_t) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
+  MMQ_CUDA(h, cudaMemcpyAsync(pmu, h->mu, sizeof(double) * (size_t)(h->n + 1), cudaMemcpyDeviceToDevice, h->stream));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  h->counts_own = h->counts; h->mu_own = h->mu;
+  h->p2p_counts[0] = c[0]; h->p2p_counts[1] = c[1];
+  h->p2p_rank = rank; h->p2p_n = nranks;
+  h->counts = c[h->p2p_epoch & 1];
+  h->mu = pmu;
+  return MMQ_OK;
 }
 
 int mmq_p2p_attach(mmq_handle* h, const char* ipc_handles, int rank, int nranks) {
@@ -1014,48 +1079,58 @@ int mmq_p2p_attach(mmq_handle* h, const char* ipc_handles, int rank, int nranks)
   if (h->p2p_n > 1) return mmq_fail(h, MMQ_ERR_STATE, "mmq_p2p_attach: already attached");
   int rc = p2p_alloc(h);
   if (rc) return rc;
-  const size_t head = 256;
-  for (int r = 0; r < nranks; ++r) {
-    void* base = h->p2p_buf;
-    if (r != rank) {
-      cudaIpcMemHandle_t mh;
-      memcpy(&mh, ipc_handles + 64 * r, 64);
-      MMQ_CUDA(h, cudaIpcOpenMemHandle(&base, mh, cudaIpcMemLazyEnablePeerAccess));
-      h->p2p_opened[r] = base;
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  void* opened[MMQ_P2P_MAX] = {};
+  for (int r = 0; r < nranks; ++r) { /* map every peer first: a failure leaves the handle detached */
+    if (r == rank) continue;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, ipc_handles + 64 * r, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&opened[r], mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; ++q) if (opened[q]) cudaIpcCloseMemHandle(opened[q]);
+      return mmq_cuda_fail(h, e, "cudaIpcOpenMemHandle", __FILE__, __LINE__);
     }
-    h->p2p_peer_flags[r] = (int32_t*)base;
-    h->p2p_peer_counts[r][0] = (const int32_t*)((char*)base + head);
-    h->p2p_peer_counts[r][1] = h->p2p_peer_counts[r][0] + h->n;
   }
-  p2p_finish_attach(h, rank, nranks);
-  return MMQ_OK;
+  for (int r = 0; r < nranks; ++r) {
+    h->p2p_opened[r] = opened[r];
+    h->p2p_base[r] = r == rank ? (char*)h->p2p_buf : (char*)opened[r];
+  }
+  h->p2p_epoch = 0;
+  return p2p_adopt(h, rank, nranks);
 }
 
 int mmq_p2p_attach_local(mmq_handle** hs, int nranks) {
   if (!hs || nranks < 1 || nranks > MMQ_P2P_MAX) return mmq_fail(nullptr, MMQ_ERR_ARG, "mmq_p2p_attach_local: bad arguments");
-  for (int r = 0; r < nranks; ++r) {
+  for (int r = 0; r < nranks; ++r)
     if (!hs[r] || hs[r]->n != hs[0]->n) return mmq_fail(hs[0], MMQ_ERR_ARG, "mmq_p2p_attach_local: handles must share n");
-    int rc = p2p_alloc(hs[r]);
-    if (rc) return rc;
-  }
-  const size_t head = 256;
+  for (int r = 0; r < nranks; ++r)
+    if (hs[r]->p2p_n > 1) return mmq_fail(hs[r], MMQ_ERR_STATE, "mmq_p2p_attach_local: already attached");
+  /* two phases, all or nothing: peer access and buffers for EVERY rank first; only then are the handles switched
+   * over (a rank attached while another one still uses NCCL would spin on flags that never come) */
   for (int r = 0; r < nranks; ++r) {
     mmq_handle* h = hs[r];
     MMQ_CUDA(h, cudaSetDevice(h->device));
-    for (int q = 0; q < nranks; ++q) {
+    for (int q = 0; q < nranks; ++q)
       if (q != r && hs[q]->device != h->device) {
         cudaError_t e = cudaDeviceEnablePeerAccess(hs[q]->device, 0);
         if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-        else if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        else if (e != cudaSuccess) return mmq_cuda_fail(hs[0], e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
       }
-      h->p2p_peer_flags[q] = (int32_t*)hs[q]->p2p_buf;
-      h->p2p_peer_counts[q][0] = (const int32_t*)((char*)hs[q]->p2p_buf + head);
-      h->p2p_peer_counts[q][1] = h->p2p_peer_counts[q][0] + h->n;
-    }
-    p2p_finish_attach(h, r, nranks);
+    int rc = p2p_alloc(h);
+    if (rc) { if (h != hs[0]) hs[0]->err = h->err; return rc; }
+  }
+  for (int r = 0; r < nranks; ++r) {
+    mmq_handle* h = hs[r];
+    MMQ_CUDA(h, cudaSetDevice(h->device));
+    for (int q = 0; q < nranks; ++q) h->p2p_base[q] = (char*)hs[q]->p2p_buf;
+    h->p2p_epoch = 0;
+    int rc = p2p_adopt(h, r, nranks);
+    if (rc) return rc;
   }
   return MMQ_OK;
 }
+
+int mmq_p2p_attached(const mmq_handle* h) { return h && h->p2p_n > 1 ? h->p2p_n : 0; }
 
 /* ---- initial mu ---- */
 int mmq_init_mu(mmq_handle* h, int32_t* unique_hits_out) {
@@ -1152,8 +1227,9 @@ int mmq_em(mmq_handle* h, int max_iter, double eps, int* iters_out, double* logl
     if ((rc = launch_rowterm(h, h->mu_tmp))) return rc;
     double s[2];
     MMQ_CUDA(h, cudaMemcpyAsync(s, h->scalars, sizeof s, cudaMemcpyDeviceToHost, h->stream));
+    /* mu keeps its address for the life of the handle (captured CUDA graphs and the peers of a multi-GPU run hold it) */
+    MMQ_CUDA(h, cudaMemcpyAsync(h->mu, h->mu_tmp, sizeof(double) * (size_t)h->n, cudaMemcpyDeviceToDevice, h->stream));
     MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
-    std::swap(h->mu, h->mu_tmp);
     const double ll2 = s[0] - s[1];
     llr = ll2 - loglik;
     loglik = ll2;
@@ -1193,8 +1269,22 @@ void mmq_launch_alloc_general(mmq_handle* h, cudaStream_t stream, int grid, cons
 }
 extern "C" {
 
+/* State a sweep builds on first use (synchronising copies, allocations): done ahead of a graph capture. */
+static int prepare_sweep(mmq_handle* h, int flags) {
+  if (h->m <= 0) return MMQ_OK;
+  int rc;
+  const bool transposed = (flags & MMQ_GIBBS_TRANSPOSED) != 0;
+  if ((transposed || h->has_k || (flags & MMQ_GIBBS_GENERIC_KERNEL)) && (rc = build_tiles(h, nullptr))) return rc;
+  if (transposed) {
+    if ((rc = ensure_x(h))) return rc;
+    if ((rc = build_transpose(h))) return rc;
+  }
+  return MMQ_OK;
+}
+
 /* One sweep on the stream.  trace_col = device address of trace[0*L + slot] or null. */
-static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags, int stride, int32_t* counts_copy, const uint32_t* sweep_base) {
+static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags, int stride, int32_t* counts_copy, const uint32_t* sweep_base,
+                         const int32_t* epoch_base = nullptr) {
   const bool transposed = (flags & MMQ_GIBBS_TRANSPOSED) != 0;
   const bool timed = (flags & MMQ_GIBBS_TIME_KERNELS) != 0;
   int rc;
@@ -1248,20 +1338,37 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       mark(h->ev_alloc);
     }
   }
-  if (h->p2p_n > 1) { /* all-reduce and Gamma update fused over peer memory */
+  if (h->p2p_n > 1) { /* count exchange and Gamma update fused over peer memory */
     const int b = h->p2p_epoch & 1;
     mmq_p2p_args a;
-    for (int r = 0; r < h->p2p_n; ++r) { a.counts[r] = h->p2p_peer_counts[r][b]; a.flags[r] = h->p2p_peer_flags[r]; }
-    a.reset = h->p2p_counts[b ^ 1];
-    a.local_flags = h->p2p_flags;
-    a.dbg = h->p2p_dbg;
-    static const int p2p_mode = [] { const char* e = getenv("MMQ_P2P_MODE"); return e ? atoi(e) : 2; }();
-    a.mode = p2p_mode;
-    a.nranks = h->p2p_n; a.rank = h->p2p_rank; a.epoch = ++h->p2p_epoch;
+    for (int r = 0; r < MMQ_P2P_MAX; ++r) a.base[r] = r < h->p2p_n ? h->p2p_base[r] : nullptr;
+    a.off_counts = (int64_t)p2p_off_counts(h, b);
+    a.off_reset = (int64_t)p2p_off_counts(h, b ^ 1);
+    a.off_mu = (int64_t)p2p_off_mu(h);
+    a.nranks = h->p2p_n; a.rank = h->p2p_rank;
+    ++h->p2p_epoch;
+    /* inside a graph capture the epoch is relative to the device counter that the graph advances */
+    a.epoch = epoch_base ? (int32_t)(h->p2p_epoch - h->graph_epoch0) : (int32_t)h->p2p_epoch;
+    a.epoch_base = epoch_base;
     mark(h->ev_gamma);
-    k_gamma_p2p<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
-                                                                              h->trace_len, h->n, h->alpha, h->beta, seed, sweep, counts_copy);
-    MMQ_LAUNCHED(h);
+    if (counts_copy) { /* debug / parity: full all-reduce, summed counts kept */
+      k_gamma_p2p<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
+                                                                                h->trace_len, h->n, h->alpha, h->beta, seed, sweep, counts_copy);
+      MMQ_LAUNCHED(h);
+    } else {
+      const int64_t slice = (h->n + h->p2p_n - 1) / h->p2p_n;
+      /* the grid must be co-resident (its last block waits for the peers while the others finish): <= 8 blocks of 128 per SM */
+      k_gamma_rs<<<mmq_grid_for(std::max<int64_t>(slice, h->n / 8), 128, h->num_sms * 8), 128, 0, h->stream>>>(a, h->seg_base, h->len, h->n, h->alpha, h->beta, seed, sweep, sweep_base);
+      MMQ_LAUNCHED(h);
+      /* is this sweep recorded?  plain launch: the host knows; graph capture: sweep = j, the replays start at
+       * sweeps congruent to capture_phase modulo the stride (the kernel re-checks against the real sweep number) */
+      const bool recorded = sweep_base ? (((uint32_t)h->capture_phase + sweep) % (uint32_t)std::max(stride, 1) == 0)
+                                       : (sweep % (uint32_t)std::max(stride, 1) == 0 && sweep / (uint32_t)std::max(stride, 1) < (uint32_t)h->trace_len);
+      if (stride > 0 && h->trace && recorded) {
+        k_trace_capture<<<mmq_grid_for(h->n, 256, h->num_sms * 4), 256, 0, h->stream>>>(h->mu, h->trace, stride, h->trace_len, h->n, sweep, sweep_base);
+        MMQ_LAUNCHED(h);
+      }
+    }
     mark(h->ev_gamma);
     h->counts = h->p2p_counts[h->p2p_epoch & 1]; /* the next sweep reduces into the other parity buffer */
     if (h->seg_base) h->seg_base_in_counts = true;
@@ -1295,29 +1402,42 @@ static void drop_graph(mmq_handle* h) {
   h->graph_flags = -1;
 }
 
-/* Capture MMQ_GRAPH_SWEEPS sweeps (sweep = *graph_base + j) followed by graph_base += MMQ_GRAPH_SWEEPS. */
-static int capture_graph(mmq_handle* h, uint32_t seed, int flags, int stride) {
+/* Capture MMQ_GRAPH_SWEEPS sweeps (sweep = graph_base[0] + j; peer-memory epoch = graph_base[1] + j + 1) followed by
+ * graph_base[0..1] += MMQ_GRAPH_SWEEPS.  `phase` = first sweep of a replay modulo the trace stride (decides which of the
+ * captured sweeps carry the multi-GPU trace-capture kernel). */
+static int capture_graph(mmq_handle* h, uint32_t seed, int flags, int stride, int phase) {
   drop_graph(h);
   if (!h->graph_base) {
-    int rc = mmq_dev_alloc(h, (void**)&h->graph_base, sizeof(uint32_t));
+    int rc = mmq_dev_alloc(h, (void**)&h->graph_base, 2 * sizeof(uint32_t));
     if (rc) return rc;
   }
+  const long long launches_before = g_mmq_launches.load();
+  const int32_t epoch0 = h->p2p_epoch;
+  int32_t* const counts0 = h->counts;
+  h->graph_epoch0 = epoch0;
+  h->capture_phase = phase;
   MMQ_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
   int rc = MMQ_OK;
-  for (int j = 0; j < MMQ_GRAPH_SWEEPS && rc == MMQ_OK; ++j) rc = enqueue_sweep(h, seed, (uint32_t)j, flags, stride, nullptr, h->graph_base);
+  for (int j = 0; j < MMQ_GRAPH_SWEEPS && rc == MMQ_OK; ++j)
+    rc = enqueue_sweep(h, seed, (uint32_t)j, flags, stride, nullptr, h->graph_base, h->p2p_n > 1 ? (const int32_t*)(h->graph_base + 1) : nullptr);
   if (rc == MMQ_OK) {
-    k_add_u32<<<1, 1, 0, h->stream>>>(h->graph_base, MMQ_GRAPH_SWEEPS);
+    k_add2_u32<<<1, 1, 0, h->stream>>>(h->graph_base, MMQ_GRAPH_SWEEPS);
     g_mmq_launches.fetch_add(1);
   }
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  h->capture_phase = -1;
+  h->p2p_epoch = epoch0; /* nothing ran: the host mirror of the epoch and the parity buffer go back */
+  h->counts = counts0;
+  h->graph_launches = g_mmq_launches.load() - launches_before; /* kernel nodes of one replay */
+  g_mmq_launches.store(launches_before);                       /* capturing launched nothing */
   if (rc != MMQ_OK) { if (g) cudaGraphDestroy(g); return rc; }
   if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaStreamEndCapture", __FILE__, __LINE__);
   h->graph = g;
   e = cudaGraphInstantiate(&h->graph_exec, g, 0);
   if (e != cudaSuccess) { drop_graph(h); return mmq_cuda_fail(h, e, "cudaGraphInstantiate", __FILE__, __LINE__); }
   h->graph_seed = seed; h->graph_flags = flags; h->graph_stride = stride; h->graph_trace_len = h->trace_len;
-  h->graph_trace = h->trace; h->graph_stream = h->stream;
+  h->graph_trace = h->trace; h->graph_stream = h->stream; h->graph_phase = phase; h->graph_mu = h->mu; h->graph_counts = h->counts;
   return MMQ_OK;
 }
 
@@ -1332,22 +1452,31 @@ int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweep
   const int st = trace_len > 0 ? stride : 0;
   int64_t s = first_sweep;
   const int64_t end = first_sweep + n_sweeps;
-  /* CUDA graph for the bulk of a long run (single GPU; the timed mode needs per-launch events):
-   * the first sweep goes out as plain launches (it builds lazily allocated state), then whole
-   * graphs of MMQ_GRAPH_SWEEPS sweeps, then the remainder as plain launches */
-  const bool use_graph = !(flags & (MMQ_GIBBS_NO_GRAPH | MMQ_GIBBS_TIME_KERNELS)) && h->nranks == 1 && h->p2p_n <= 1 && n_sweeps >= 1 + 2 * MMQ_GRAPH_SWEEPS;
+  /* CUDA graph of MMQ_GRAPH_SWEEPS sweeps for every call that long — single GPU and the fused peer-memory exchange
+   * (the NCCL exchange and the per-kernel timing mode go out as plain launches): whole graphs first, the remainder as
+   * plain launches.  Sweep number and peer-memory epoch are read from graph_base on the device, so one instantiated
+   * graph serves the whole chain and later calls. */
+  const bool p2p = h->p2p_n > 1;
+  const bool use_graph = !(flags & (MMQ_GIBBS_NO_GRAPH | MMQ_GIBBS_TIME_KERNELS)) && (h->nranks == 1 || p2p) && n_sweeps >= MMQ_GRAPH_SWEEPS + (p2p ? 1 : 0);
   if (use_graph) {
-    if ((rc = enqueue_sweep(h, seed, (uint32_t)s, flags, st, nullptr, nullptr))) return rc;
-    ++s;
+    if ((rc = prepare_sweep(h, flags))) return rc;
+    if (p2p && (h->p2p_epoch & 1)) { /* the captured sweeps alternate the parity buffers starting from an even epoch */
+      if ((rc = enqueue_sweep(h, seed, (uint32_t)s, flags, st, nullptr, nullptr))) return rc;
+      ++s;
+    }
+    const int phase = st > 0 ? (int)(s % st) : 0;
     const bool reuse = h->graph_exec && h->graph_seed == seed && h->graph_flags == flags && h->graph_stride == st &&
-                       h->graph_trace_len == h->trace_len && h->graph_trace == h->trace && h->graph_stream == h->stream;
-    if (!reuse && (rc = capture_graph(h, seed, flags, st))) return rc;
-    k_set_u32<<<1, 1, 0, h->stream>>>(h->graph_base, (uint32_t)s);
+                       h->graph_trace_len == h->trace_len && h->graph_trace == h->trace && h->graph_stream == h->stream &&
+                       h->graph_mu == h->mu && h->graph_counts == h->counts && (!p2p || st == 0 || h->graph_phase == phase);
+    if (!reuse && (rc = capture_graph(h, seed, flags, st, phase))) return rc;
+    k_set2_u32<<<1, 1, 0, h->stream>>>(h->graph_base, (uint32_t)s, (uint32_t)h->p2p_epoch);
     MMQ_LAUNCHED(h);
     while (end - s >= MMQ_GRAPH_SWEEPS) {
+      if (p2p && st > 0 && (int)(s % st) != h->graph_phase) break; /* stride does not divide the graph length: plain launches */
       MMQ_CUDA(h, cudaGraphLaunch(h->graph_exec, h->stream));
-      g_mmq_launches.fetch_add(2 * MMQ_GRAPH_SWEEPS + 1, std::memory_order_relaxed);
+      g_mmq_launches.fetch_add(h->graph_launches, std::memory_order_relaxed);
       s += MMQ_GRAPH_SWEEPS;
+      if (p2p) h->p2p_epoch += MMQ_GRAPH_SWEEPS;
     }
   }
   for (; s < end; ++s)

@@ -19,6 +19,11 @@
 #define MMQ_ALLOC_CAP 320 /* staged CSR entries per warp tile */
 #define MMQ_GRAPH_SWEEPS 16 /* sweeps per captured CUDA graph */
 #define MMQ_P2P_MAX 8      /* ranks of one NVSwitch box */
+/* head of a rank's peer-mapped block, in int32 units: one flag per rank, each in its own 32-byte sector */
+#define MMQ_P2P_HEAD 1024         /* bytes */
+#define MMQ_P2P_FLAG_ALLOC 0      /* [8 r]: rank r has finished the allocation of epoch e */
+#define MMQ_P2P_FLAG_MU 64        /* [64 + 8 r]: rank r has stored its slice of mu of epoch e everywhere */
+#define MMQ_P2P_DONE 128          /* blocks of the own Gamma kernel that have finished */
 
 struct mmq_group_set {
   int64_t ngroups = 0;
@@ -112,23 +117,27 @@ struct mmq_handle {
   cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
 
-  /* fused count exchange over peer memory: [flags int32[MMQ_P2P_MAX] | pad | counts A[n] | counts B[n]] */
+  /* fused count exchange over peer memory: one peer-mapped block per rank, laid out as
+   * [flags MMQ_P2P_HEAD bytes | counts parity 0 | counts parity 1 | mu] (offsets: p2p_off_* in mmq_core.cu) */
   void* p2p_buf = nullptr;
-  int32_t* p2p_flags = nullptr;
   int32_t* p2p_counts[2] = {nullptr, nullptr};
-  int32_t* p2p_peer_flags[MMQ_P2P_MAX] = {};
-  const int32_t* p2p_peer_counts[MMQ_P2P_MAX][2] = {};
+  char* p2p_base[MMQ_P2P_MAX] = {};   /* block of every rank as mapped here (own block included) */
   void* p2p_opened[MMQ_P2P_MAX] = {}; /* cudaIpcOpenMemHandle mappings to close */
   int p2p_n = 0, p2p_rank = 0;
-  int32_t p2p_epoch = 0;
-  unsigned long long* p2p_dbg = nullptr; /* MMQ_P2P_TRACE=1: wait-time accumulator, printed by mmq_destroy */
-  int32_t* counts_own = nullptr; /* the single-GPU counts buffer (counts points into p2p_buf when attached) */
+  int32_t p2p_epoch = 0;              /* host mirror: sweeps exchanged so far */
+  int32_t* counts_own = nullptr;      /* the single-GPU buffers (counts / mu point into p2p_buf when attached) */
+  double* mu_own = nullptr;
 
   /* CUDA graph of MMQ_GRAPH_SWEEPS consecutive sweeps; the sweep counter is read from
    * graph_base on the device, so one instantiated graph serves the whole chain */
   uint32_t* graph_base = nullptr;
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
+  long long graph_launches = 0; /* kernels one replay of the graph launches */
+  int32_t graph_epoch0 = 0;     /* p2p_epoch when the capture began */
+  int capture_phase = -1, graph_phase = 0; /* first sweep of a replay modulo the trace stride */
+  const double* graph_mu = nullptr;
+  const int32_t* graph_counts = nullptr;
   uint32_t graph_seed = 0;
   int graph_flags = -1, graph_stride = 0, graph_trace_len = 0;
   const double* graph_trace = nullptr;

@@ -242,6 +242,66 @@ void orc_sweep_replay_ids(int64_t m, int64_t n, const int64_t* rp, const int32_t
   sweep_replay_impl(m, n, rp, col, k, w, l, alpha, beta, seed, sweep, 0, mu, x_out, counts_out, do_gamma, class_id);
 }
 
+/* Allocation step of one sweep on `threads` host threads: counts only (integer sums, so the result does not depend on the
+ * thread count).  Same draws as orc_sweep_replay; used by bench.py's correctness gates at full size. */
+void orc_sweep_counts(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k, const float* w,
+                      uint32_t seed, uint32_t sweep, int64_t class_id_base, const int64_t* class_id, const double* mu,
+                      int32_t* counts_out, int threads) {
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#else
+  threads = 1;
+#endif
+  std::vector<int32_t> part((size_t)n * (size_t)threads, 0);
+#pragma omp parallel num_threads(threads)
+  {
+#ifdef _OPENMP
+    int32_t* c = part.data() + (size_t)n * (size_t)omp_get_thread_num();
+#else
+    int32_t* c = part.data();
+#endif
+    std::vector<double> p;
+    std::vector<int32_t> x;
+#pragma omp for schedule(dynamic, 4096)
+    for (int64_t i = 0; i < m; ++i) {
+      const int d = (int)(rp[i + 1] - rp[i]);
+      p.resize((size_t)d);
+      x.resize((size_t)d);
+      for (int j = 0; j < d; ++j) {
+        const int64_t q = rp[i] + j;
+        p[(size_t)j] = w ? mu[col[q]] * (double)w[q] : mu[col[q]];
+      }
+      mmq_alloc_row(p.data(), x.data(), d, (int64_t)(k ? k[i] : 1), seed, (uint64_t)(class_id ? class_id[i] : class_id_base + i), sweep);
+      for (int j = 0; j < d; ++j) c[col[rp[i] + j]] += x[(size_t)j];
+    }
+  }
+  for (int64_t t = 0; t < n; ++t) {
+    int32_t v = 0;
+    for (int q = 0; q < threads; ++q) v += part[(size_t)t + (size_t)n * (size_t)q];
+    counts_out[t] = v;
+  }
+}
+
+/* One shard's part of an EM iteration (src/mmseq.cpp:781-802 split over row blocks): acc[t] = sum over the shard's classes
+ * containing t of k_i w_it / D_i (classes in ascending row order, as orc_em), returns sum_i k_i log D_i.  The caller
+ * (bench.py's EM gate) sums acc and the return value over shards and applies mu' = mu acc / l. */
+double orc_em_partial(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k, const float* w,
+                      const double* mu, double* acc) {
+  std::vector<double> D((size_t)m);
+  double ll = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : ll)
+  for (int64_t i = 0; i < m; ++i) {
+    D[(size_t)i] = row_dot(rp, col, w, mu, i);
+    ll += (double)(k ? k[i] : 1) * std::log(D[(size_t)i]);
+  }
+  for (int64_t t = 0; t < n; ++t) acc[t] = 0.0;
+  for (int64_t i = 0; i < m; ++i) {
+    const double ki = (double)(k ? k[i] : 1);
+    for (int64_t q = rp[i]; q < rp[i + 1]; ++q) acc[col[q]] += (w ? ki * (double)w[q] : ki) / D[(size_t)i];
+  }
+  return ll;
+}
+
 /* Gamma step alone from given counts (used for the multi-shard replay). */
 void orc_gamma_replay(int64_t n, const int32_t* counts, const double* l, double alpha, double beta,
                       uint32_t seed, uint32_t sweep, double* mu) {

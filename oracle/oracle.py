@@ -51,6 +51,9 @@ def lib():
         L.orc_sweep_replay.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, u32, i64, vp, vp, vp, i32]
         L.orc_sweep_replay_ids.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, u32, vp, vp, vp, vp, i32]
         L.orc_gamma_replay.argtypes = [i64, vp, vp, dbl, dbl, u32, u32, vp]
+        L.orc_sweep_counts.argtypes = [i64, i64, vp, vp, vp, vp, u32, u32, i64, vp, vp, vp, i32]
+        L.orc_em_partial.restype = dbl
+        L.orc_em_partial.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp]
         L.orc_cls_plan_replay.restype = C.c_int
         L.orc_cls_plan_replay.argtypes = [i64, i64, vp, vp, vp, vp, i64, vp, u32, u32, vp, vp]
         L.orc_gibbs_replay.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, i64, i64, i32, i32, vp, vp]
@@ -190,6 +193,20 @@ class Problem:
         lib().orc_sweep_replay_ids(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(self.w), _p(self.len), self.alpha,
                                    self.beta, seed, sweep, _p(cid), _p(mu), _p(x), _p(counts), int(do_gamma))
         return x, counts, mu
+
+    def sweep_counts(self, mu, seed, sweep, class_id_base=0, class_id=None, threads=0):
+        """Allocation step of one sweep on the shared Philox stream, on `threads` host threads: counts only."""
+        mu = _c(mu, np.float64); cid = None if class_id is None else _c(class_id, np.int64)
+        counts = np.zeros(self.n, np.int32)
+        lib().orc_sweep_counts(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(self.w), seed, sweep, class_id_base,
+                               _p(cid), _p(mu), _p(counts), threads)
+        return counts
+
+    def em_partial(self, mu):
+        """This shard's part of one EM iteration: (acc[n], sum_i k_i log D_i)."""
+        mu = _c(mu, np.float64); acc = np.zeros(self.n)
+        ll = lib().orc_em_partial(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(self.w), _p(mu), _p(acc))
+        return acc, ll
 
     def gamma_replay(self, counts, seed, sweep):
         counts = _c(counts, np.int32); mu = np.zeros(self.n)

@@ -225,9 +225,9 @@ def test_ragged_and_extreme_rows():
 @pytest.mark.parametrize("cid_base", [0, (1 << 32) * 5 + 3])
 def test_class_plan_kernel_bit_exact(monkeypatch, cid_base, plan_threads):
     """Collapsed shards (mmq_cls.cu): every regime of the plan against the CPU replay — k = 0, 1,
-    2..8192 (categorical draws, four per Philox block, 64 per slot; block and slot boundaries),
-    k > 8192 (binomial chains on the second stream), class sizes 1, 2..8 and 9..16 (the two
-    register instances), 17..64 (generic), > 64 (general kernel), all-zero and partly-zero mu
+    2..64 (categorical draws, four per Philox block; block boundaries and the full 64-draw slot),
+    k > 64 (conditional-binomial chains, one class per lane of k_alloc_chain, BINV and BTRS regimes), class sizes 1,
+    2..8 and 9..16 (the two register instances), 17..64 (generic), > 64 (general kernel), all-zero and partly-zero mu
     rows, class ids above 2^32, chunks that end inside a warp; the plan built by one host thread and
     by several (MMQ_PLAN_THREADS)."""
     monkeypatch.setenv("MMQ_PLAN_THREADS", plan_threads)
@@ -252,7 +252,8 @@ def test_class_plan_kernel_bit_exact(monkeypatch, cid_base, plan_threads):
     P = orc.Problem(row_ptr, col, k, l)
     with capi.Handle(row_ptr, col, k, l, class_id_base=cid_base) as H:
         st = H.cls_stats()
-        assert st["in_use"] == 1 and st["small_classes"] > 4000 and st["rest_classes"] > 20 and st["class_slots"] > st["small_classes"]
+        assert st["in_use"] == 1 and st["small_classes"] > 4000 and st["rest_classes"] == 20 and st["chain_classes"] > 200
+        assert st["class_slots"] >= st["small_classes"] and st["chain_slots"] % 32 == 0
         for sweep in (0, 1, 7):
             H.set_mu(mu)
             x_o, c_o, mu_o = P.sweep_replay(mu, 4321, sweep, class_id_base=cid_base)

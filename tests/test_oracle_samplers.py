@@ -75,7 +75,7 @@ def test_binomial_distribution(n, p):
 def test_alloc_known_answers():
     """The random-stream contract of mmq_alloc_row is pinned by committed vectors
     (tools/make_golden_alloc.py): k = 1 (CAT stream, quad-shared block), categorical draws across
-    block and 64-draw group boundaries up to MMQ_CAT_K = 8192, binomial chains above."""
+    block boundaries up to MMQ_CAT_K = 64, binomial chains above."""
     import os
     g = np.load(os.path.join(os.path.dirname(__file__), "golden", "alloc_kat.npz"))
     assert int(g["n_cases"]) >= 9
@@ -99,11 +99,11 @@ def test_alloc_row_is_multinomial_and_conserves():
     assert (orc.draw_alloc(5, 10, np.zeros(3), 4)[:, 2] == 4).all()
 
 
-@pytest.mark.parametrize("k,reps", [(30, 100000), (700, 20000), (8192, 4000), (8193, 4000)])
+@pytest.mark.parametrize("k,reps", [(30, 100000), (64, 50000), (65, 50000), (700, 20000), (8193, 4000)])
 def test_alloc_matches_gsl_style_multinomial_in_distribution(k, reps):
     """Every regime of mmq_alloc_row against the GSL-style chain of binomials (the reference's
     gsl_ran_multinomial, src/mmseq.cpp:880): categorical draws with 32-bit uniforms four to a Philox
-    block (k <= MMQ_CAT_K = 8192, across several groups of 64 draws), binomial chain above."""
+    block (k <= MMQ_CAT_K = 64), binomial chain above."""
     p = np.array([0.5, 2.5, 1.0, 4.0])
     a = orc.draw_alloc(9, reps, p, k)
     b = orc.gsl_multinomial(9, reps, p, k)
