@@ -269,38 +269,102 @@ MMQ_HD double mmq_ndtri(double p) {
   return (q < 0.0) ? -val : val;
 }
 
-/* Standard normal variate by inversion of one 52-bit uniform. */
-MMQ_HD double mmq_normal(mmq_rng* g) { return mmq_ndtri(mmq_uniform(g)); }
+/* ---------------------------------------------------- attempt-indexed blocks */
+
+/* Every rejection sampler below numbers its attempts and takes the random numbers of attempt r from ONE Philox
+ * block whose index is a function of r alone (not of how many numbers earlier attempts consumed).  An attempt is
+ * then a pure function of (seed, stream, id, sweep, block): a kernel may run the attempts of many draws in any
+ * order, re-queue the rejected ones and process them densely (mmq_cls.cu: k_alloc_chain, mmq_core.cu: k_gamma)
+ * and still produce, bit for bit, what the sequential loops of mmq_gamma / mmq_binomial produce on the CPU. */
+MMQ_HD void mmq_rng_block(const mmq_rng* g, uint32_t block, uint32_t w[4]) {
+  w[0] = g->id_lo; w[1] = g->id_hi; w[2] = g->sweep; w[3] = block;
+  mmq_philox4x32_10(w, g->seed, g->stream);
+}
+/* 52-bit uniform on (0,1) from two words: (j + 1/2) 2^-52 */
+MMQ_HD double mmq_uniform52(uint32_t hi, uint32_t lo) {
+  const uint64_t j = (((uint64_t)hi << 32) | (uint64_t)lo) >> 12;
+  return ((double)j + 0.5) * 2.220446049250313080847263336181640625e-16; /* 2^-52 */
+}
+
+/* ------------------------------------------------------------- normal */
+
+/* cos(2 pi (w + 1/2) / 2^32) from the 32-bit word itself: the top three bits pick the octant, the other 29 the
+ * position inside it, mirrored in the odd octants so that the polynomial argument is phi = (q + 1/2) 2^-30 pi/2
+ * with an integer q in [0, 2^30): cos(phi) on (0, pi/2) by its Taylor polynomial in phi^2 up to phi^24
+ * (truncation error 3e-22), Horner form, no branches.  Only IEEE add / mul: identical on host and device. */
+MMQ_HD double mmq_cos2pi_u32(uint32_t w) {
+  const uint32_t o = w >> 29, f = w & 0x1fffffffu;
+  const uint32_t fm = (o & 1u) ? (0x1fffffffu - f) : f;             /* distance to the nearer octant boundary */
+  const uint32_t use_sin = ((o + 1u) >> 1) & 1u, neg = ((o + 2u) >> 2) & 1u;
+  const uint32_t q = use_sin ? (0x3fffffffu - fm) : fm;              /* sin(t) = cos(pi/2 - t) */
+  const double phi = ((double)q + 0.5) * 1.4629180792671596e-09;     /* 2^-30 pi/2 */
+  const double z = phi * phi;
+  double c = 1.6117375710961184e-24;                                  /* 1/24! */
+  c = c * z + -8.8967913924505741e-22;                                /* -1/22! */
+  c = c * z + 4.1103176233121648e-19;                                 /* 1/20! */
+  c = c * z + -1.5619206968586225e-16;                                /* -1/18! */
+  c = c * z + 4.7794773323873853e-14;                                 /* 1/16! */
+  c = c * z + -1.1470745597729725e-11;                                /* -1/14! */
+  c = c * z + 2.08767569878681e-09;                                   /* 1/12! */
+  c = c * z + -2.7557319223985888e-07;                                /* -1/10! */
+  c = c * z + 2.48015873015873e-05;                                   /* 1/8! */
+  c = c * z + -0.001388888888888889;                                  /* -1/6! */
+  c = c * z + 0.041666666666666664;                                   /* 1/4! */
+  c = c * z + -0.5;
+  c = c * z + 1.0;
+  return neg ? -c : c;
+}
+
+/* Standard normal variate, Box-Muller: sqrt(-2 log u) cos(2 pi v) with u a 52-bit uniform (words 0, 1 of a block)
+ * and v a 32-bit one (word 2).  Branch-free, unlike an inverse-CDF with separate tail formulas: all lanes of a
+ * warp do the same work. */
+MMQ_HD double mmq_normal_bm(uint32_t w0, uint32_t w1, uint32_t w2) {
+  return sqrt(-2.0 * mmq_log(mmq_uniform52(w0, w1))) * mmq_cos2pi_u32(w2);
+}
 
 /* -------------------------------------------------------------- gamma */
 
-/* Gamma(shape a > 0, rate b > 0): Marsaglia & Tsang (2000), with the
- * Gamma(a+1) * U^(1/a) boost for a < 1 — the algorithm of gsl_ran_gamma, which
- * the reference calls as gsl_ran_gamma(rg, alpha + Xcolsum[t], 1/(beta+l[t]))
- * at src/mmseq.cpp:907. */
-MMQ_HD double mmq_gamma(mmq_rng* g, double a, double rate) {
+/* Gamma(shape a > 0, rate b > 0): Marsaglia & Tsang (2000), with the Gamma(a+1) U^(1/a) boost for a < 1 — the
+ * algorithm of gsl_ran_gamma, which the reference calls as gsl_ran_gamma(rg, alpha + Xcolsum[t], 1/(beta+l[t]))
+ * at src/mmseq.cpp:907.  Blocks of the draw's stream: 0 = the boost uniform (words 0, 1; only read when a < 1),
+ * 1 + r = attempt r (words 0, 1, 2: the normal; word 3: the acceptance uniform, 32 bits like gsl_rng_uniform). */
+typedef struct { double d, c; } mmq_gamma_par;
+MMQ_HD mmq_gamma_par mmq_gamma_setup(double a_ge_1) {
+  mmq_gamma_par q;
+  q.d = a_ge_1 - 1.0 / 3.0;
+  q.c = (1.0 / 3.0) / sqrt(q.d);
+  return q;
+}
+/* attempt r: returns 1 and *v_out = v^3 when accepted */
+MMQ_HD int mmq_gamma_attempt(const mmq_rng* g, uint32_t r, mmq_gamma_par q, double* v_out) {
+  uint32_t w[4];
+  mmq_rng_block(g, 1u + r, w);
+  const double x = mmq_normal_bm(w[0], w[1], w[2]);
+  double v = 1.0 + q.c * x;
+  if (v <= 0.0) return 0;
+  v = v * v * v;
+  const double u = mmq_uniform32(w[3]);
+  const double x2 = x * x;
+  *v_out = v;
+  if (u < 1.0 - 0.0331 * x2 * x2) return 1;
+  return mmq_log(u) < 0.5 * x2 + q.d * (1.0 - v + mmq_log(v));
+}
+/* U^(1/a) for a < 1 */
+MMQ_HD double mmq_gamma_boost(const mmq_rng* g, double a_lt_1) {
+  uint32_t w[4];
+  mmq_rng_block(g, 0u, w);
+  return mmq_exp(mmq_log(mmq_uniform52(w[0], w[1])) / a_lt_1);
+}
+MMQ_HD double mmq_gamma(const mmq_rng* g, double a, double rate) {
   double boost = 1.0;
   if (a < 1.0) {
-    double u = mmq_uniform(g);
-    boost = mmq_exp(mmq_log(u) / a);
+    boost = mmq_gamma_boost(g, a);
     a += 1.0;
   }
-  const double d = a - 1.0 / 3.0;
-  const double c = (1.0 / 3.0) / sqrt(d);
-  double v;
-  for (;;) {
-    double x;
-    do {
-      x = mmq_normal(g);
-      v = 1.0 + c * x;
-    } while (v <= 0.0);
-    v = v * v * v;
-    double u = mmq_uniform(g);
-    double x2 = x * x;
-    if (u < 1.0 - 0.0331 * x2 * x2) break;
-    if (mmq_log(u) < 0.5 * x2 + d * (1.0 - v + mmq_log(v))) break;
-  }
-  return boost * d * v / rate;
+  const mmq_gamma_par q = mmq_gamma_setup(a);
+  double v = 0.0;
+  for (uint32_t r = 0; !mmq_gamma_attempt(g, r, q, &v); ++r) { }
+  return boost * q.d * v / rate;
 }
 
 /* ------------------------------------------------------------ binomial */
@@ -326,74 +390,101 @@ MMQ_HD double mmq_stirling_tail(double k) {
   return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / kp1;
 }
 
-/* Binomial(n, p) for 0 <= p <= 1/2.
+/* Binomial(n, p) for 0 <= p <= 1/2, n >= 2.
  *   n*p <  10 : sequential inversion (BINV, Kachitvichyanukul & Schmeiser 1988)
  *   n*p >= 10 : transformed rejection BTRS (Hoermann 1993)
- * Both are exact samplers; GSL's gsl_ran_binomial (BTPE + inversion) samples
- * the same distribution. */
-MMQ_HD int64_t mmq_binomial_half(mmq_rng* g, int64_t n, double p) {
+ * Both are exact samplers; GSL's gsl_ran_binomial (BTPE + inversion) samples the same distribution.
+ * Attempt r of a draw reads block block0 + r of the stream: words 0, 1 = the first 52-bit uniform, words 2, 3 the
+ * second (BTRS only). */
+#define MMQ_BINV_MEAN 10.0
+MMQ_HD int64_t mmq_binv(const mmq_rng* g, uint32_t block0, int64_t n, double p) {
   const double dn = (double)n;
-  if (dn * p < 10.0) {
-    const double q = 1.0 - p;
-    const double s = p / q;
-    const double a = (dn + 1.0) * s;
-    const double r0 = mmq_exp(dn * mmq_log1p(-p));
-    for (;;) {
-      double r = r0;
-      double u = mmq_uniform(g);
-      int64_t x = 0;
-      while (u > r) {
-        u -= r;
-        x += 1;
-        if (x > n) break;
-        r *= (a / (double)x - s);
-      }
-      if (x <= n) return x;
-    }
-  }
   const double q = 1.0 - p;
-  const double spq = sqrt(dn * p * q);
-  const double b = 1.15 + 2.53 * spq;
-  const double a = -0.0873 + 0.0248 * b + 0.01 * p;
-  const double c = dn * p + 0.5;
-  const double vr = 0.92 - 4.2 / b;
-  const double r = p / q;
-  const double alpha = (2.83 + 5.1 / b) * spq;
-  const double m = floor((dn + 1.0) * p);
-  for (;;) {
-    double u = mmq_uniform(g) - 0.5;
-    double v = mmq_uniform(g);
-    double us = 0.5 - fabs(u);
-    double kk = floor((2.0 * a / us + b) * u + c);
-    if (kk < 0.0 || kk > dn) continue;
-    if (us >= 0.07 && v <= vr) return (int64_t)kk;
-    double lv = mmq_log(v * alpha / (a / (us * us) + b));
-    double ub = (m + 0.5) * mmq_log((m + 1.0) / (r * (dn - m + 1.0))) +
-                (dn + 1.0) * mmq_log((dn - m + 1.0) / (dn - kk + 1.0)) +
-                (kk + 0.5) * mmq_log(r * (dn - kk + 1.0) / (kk + 1.0)) +
-                mmq_stirling_tail(m) + mmq_stirling_tail(dn - m) -
-                mmq_stirling_tail(kk) - mmq_stirling_tail(dn - kk);
-    if (lv <= ub) return (int64_t)kk;
+  const double s = p / q;
+  const double a = (dn + 1.0) * s;
+  const double r0 = mmq_exp(dn * mmq_log1p(-p));
+  for (uint32_t att = 0;; ++att) {
+    uint32_t w[4];
+    mmq_rng_block(g, block0 + att, w);
+    double r = r0;
+    double u = mmq_uniform52(w[0], w[1]);
+    int64_t x = 0;
+    while (u > r) {
+      u -= r;
+      x += 1;
+      if (x > n) break;
+      r *= (a / (double)x - s);
+    }
+    if (x <= n) return x;
   }
 }
+typedef struct { double dn, b, a, c, vr, r, alpha, m; } mmq_btrs_par;
+MMQ_HD mmq_btrs_par mmq_btrs_setup(int64_t n, double p) {
+  mmq_btrs_par t;
+  t.dn = (double)n;
+  const double q = 1.0 - p;
+  const double spq = sqrt(t.dn * p * q);
+  t.b = 1.15 + 2.53 * spq;
+  t.a = -0.0873 + 0.0248 * t.b + 0.01 * p;
+  t.c = t.dn * p + 0.5;
+  t.vr = 0.92 - 4.2 / t.b;
+  t.r = p / q;
+  t.alpha = (2.83 + 5.1 / t.b) * spq;
+  t.m = floor((t.dn + 1.0) * p);
+  return t;
+}
+/* one BTRS attempt from block `block`: returns 1 and *x_out when accepted */
+MMQ_HD int mmq_btrs_attempt(const mmq_rng* g, uint32_t block, const mmq_btrs_par t, int64_t* x_out) {
+  uint32_t w[4];
+  mmq_rng_block(g, block, w);
+  const double u = mmq_uniform52(w[0], w[1]) - 0.5;
+  const double v = mmq_uniform52(w[2], w[3]);
+  const double us = 0.5 - fabs(u);
+  const double kk = floor((2.0 * t.a / us + t.b) * u + t.c);
+  if (kk < 0.0 || kk > t.dn) return 0;
+  *x_out = (int64_t)kk;
+  if (us >= 0.07 && v <= t.vr) return 1;
+  const double lv = mmq_log(v * t.alpha / (t.a / (us * us) + t.b));
+  const double ub = (t.m + 0.5) * mmq_log((t.m + 1.0) / (t.r * (t.dn - t.m + 1.0))) +
+                    (t.dn + 1.0) * mmq_log((t.dn - t.m + 1.0) / (t.dn - kk + 1.0)) +
+                    (kk + 0.5) * mmq_log(t.r * (t.dn - kk + 1.0) / (kk + 1.0)) +
+                    mmq_stirling_tail(t.m) + mmq_stirling_tail(t.dn - t.m) -
+                    mmq_stirling_tail(kk) - mmq_stirling_tail(t.dn - kk);
+  return lv <= ub;
+}
+MMQ_HD int64_t mmq_binomial_half(const mmq_rng* g, uint32_t block0, int64_t n, double p) {
+  if ((double)n * p < MMQ_BINV_MEAN) return mmq_binv(g, block0, n, p);
+  const mmq_btrs_par t = mmq_btrs_setup(n, p);
+  int64_t x = 0;
+  for (uint32_t r = 0; !mmq_btrs_attempt(g, block0 + r, t, &x); ++r) { }
+  return x;
+}
 
-/* Binomial(n, p), any p in [0,1]. */
-MMQ_HD int64_t mmq_binomial(mmq_rng* g, int64_t n, double p) {
+/* Binomial(n, p), any p in [0,1], from the blocks block0, block0 + 1, ... of the stream. */
+MMQ_HD int64_t mmq_binomial(const mmq_rng* g, uint32_t block0, int64_t n, double p) {
   if (n <= 0 || !(p > 0.0)) return 0;
   if (p >= 1.0) return n;
-  if (n == 1) return (mmq_uniform(g) < p) ? 1 : 0;
-  if (p > 0.5) return n - mmq_binomial_half(g, n, 1.0 - p);
-  return mmq_binomial_half(g, n, p);
+  if (n == 1) {
+    uint32_t w[4];
+    mmq_rng_block(g, block0, w);
+    return (mmq_uniform52(w[0], w[1]) < p) ? 1 : 0;
+  }
+  if (p > 0.5) return n - mmq_binomial_half(g, block0, n, 1.0 - p);
+  return mmq_binomial_half(g, block0, n, p);
 }
 
 /* ---------------------------------------------------- one hit class */
 
+/* blocks of member j of a chain class: (j << 8) + attempt */
+#define MMQ_CHAIN_BLOCK(j) ((uint32_t)(j) << 8)
+
 /* gsl_ran_multinomial's chain of conditional binomials (src/mmseq.cpp:880): x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)),
  * members with zero probability skipped, the last member with p > 0 takes what is left.  norm = p_0 + ... + p_{d-1} summed
  * left to right and last_pos = the last member with p > 0 (d - 1 if none) come from the caller's first pass over the row;
- * g is the class's ALLOC stream (52-bit uniforms).  p is read once more, x[j] is assigned exactly once per member. */
+ * g is the class's ALLOC stream; the binomial of member j reads the blocks MMQ_CHAIN_BLOCK(j) + attempt.  p is read once
+ * more, x[j] is assigned exactly once per member. */
 template <typename PIt, typename XIt>
-MMQ_HD void mmq_alloc_chain(PIt p, XIt x, int d, int64_t k, double norm, int last_pos, mmq_rng* g) {
+MMQ_HD void mmq_alloc_chain(PIt p, XIt x, int d, int64_t k, double norm, int last_pos, const mmq_rng* g) {
   int64_t rem = k;
   double sum_p = 0.0;
   for (int j = 0; j < d; ++j) {
@@ -405,7 +496,7 @@ MMQ_HD void mmq_alloc_chain(PIt p, XIt x, int d, int64_t k, double norm, int las
       const double denom = norm - sum_p;
       double pr = (denom > 0.0) ? pj / denom : 1.0;
       if (pr > 1.0) pr = 1.0;
-      xj = mmq_binomial(g, rem, pr);
+      xj = mmq_binomial(g, MMQ_CHAIN_BLOCK(j), rem, pr);
     }
     x[j] = (int32_t)xj;
     rem -= xj;

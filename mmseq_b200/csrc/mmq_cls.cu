@@ -243,55 +243,134 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
 
 /* The chain set: classes with more than MMQ_CAT_K fragments — gsl_ran_multinomial's chain of conditional binomials
  * (src/mmseq.cpp:880), O(d) per class whatever k is.  One class per lane, 32 classes of equal size per chunk (member-major
- * like the small set, so every column load of the warp is one 128-byte line), longest classes first.  The lane sums its
- * row left to right (norm, last member with p > 0), then walks it once more: x_j ~ Bin(rem, p_j / (norm - sum_{<j} p)) with
- * BINV below a mean of 10 and BTRS above (mmq_binomial, fp64, shared with the CPU replay) and adds x_j to counts[].
- * A few tens of thousands of classes (49k of 3.6M on the config-2 sample, holding 55 % of its fragments): latency-bound,
- * launched first on its own stream so that it overlaps the two k_alloc_cls instances. */
-struct ChainP {
-  const int32_t* pc;
-  const double* mu;
-  __device__ __forceinline__ double operator[](int j) const { return mu[__ldg(pc + 32 * j)]; }
+ * like the small set, so every column load of a warp is one 128-byte line), longest classes first, 8 chunks per block.
+ * The lane sums its row left to right (norm, last member with p > 0), then the block walks the members in step:
+ * x_j ~ Bin(rem, p_j / (norm - sum_{<j} p)).
+ *
+ * A binomial is a rejection sampler (BTRS above a mean of 10) or an inversion loop of data-dependent length (BINV
+ * below): with every lane running its own, a warp pays for the union of the regimes and for its slowest lane — the first
+ * version of this kernel kept 5.5 of 32 lanes busy (ncu, round 2) and took 117 us for the 49k classes of the config-2
+ * sample.  An attempt being a pure function of (class, sweep, member, attempt number) (include/mmq_sampler.h), the
+ * block instead QUEUES the binomials of a step in shared memory by regime and runs each queue densely: BTRS attempts
+ * in rounds (the rejected ones re-queued), then the inversions.  Same integers as the CPU replay's mmq_alloc_chain. */
+#define MMQ_CHAIN_THREADS 256
+struct chain_req { double p; int n; int owner; }; /* owner: thread | flip << 16 (x = n - x' for p > 1/2) */
+struct chain_smem {
+  chain_req qt[2][MMQ_CHAIN_THREADS]; /* BTRS, ping-pong over attempts */
+  chain_req qi[MMQ_CHAIN_THREADS];    /* inversions and the trivial cases */
+  uint32_t cid[MMQ_CHAIN_THREADS];
+  int result[MMQ_CHAIN_THREADS];
+  int n[3];
+  int dmax;
 };
-struct ChainX {
-  const int32_t* pc;
-  int32_t* counts;
-  struct Ref {
-    const int32_t* c;
-    int32_t* counts;
-    __device__ __forceinline__ void operator=(int32_t v) const { if (v != 0) atomicAdd(counts + __ldg(c), v); }
-  };
-  __device__ __forceinline__ Ref operator[](int j) const { return Ref{pc + 32 * j, counts}; }
-};
-__global__ void __launch_bounds__(MMQ_CLS_WARPS * 32)
+__global__ void __launch_bounds__(MMQ_CHAIN_THREADS)
 k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __restrict__ ck, const uint32_t* __restrict__ ccid,
               const unsigned long long* __restrict__ cdesc, uint32_t cid_hi, const double* __restrict__ mu,
               int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+  __shared__ chain_smem S;
   if (sweep_base) sweep += *sweep_base;
-  const int lane = threadIdx.x & 31;
-  const int nwarps = gridDim.x * MMQ_CLS_WARPS;
-  for (int chunk = blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5); chunk < chunks; chunk += nwarps) {
-    const unsigned long long desc = cdesc[chunk];
-    const int D = (int)(desc & 0xffull);
-    const int32_t* pc = pcol + (desc >> 8) + lane;
-    const int64_t kv = ck[(int64_t)chunk * 32 + lane];
-    const uint32_t cid = ccid[(int64_t)chunk * 32 + lane];
-    if (kv <= 0) continue; /* padding lane */
-    const ChainP p{pc, mu};
-    double norm = 0.0;
+  const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+  constexpr int WARPS = MMQ_CHAIN_THREADS / 32;
+  for (int chunk0 = blockIdx.x * WARPS; chunk0 < chunks; chunk0 += gridDim.x * WARPS) {
+    const int chunk = chunk0 + wib;
+    int D = 0;
+    const int32_t* pc = pcol;
+    int64_t rem = 0;
+    uint32_t cid = 0;
+    if (chunk < chunks) {
+      const unsigned long long desc = cdesc[chunk];
+      D = (int)(desc & 0xffull);
+      pc = pcol + (desc >> 8) + lane;
+      rem = ck[(int64_t)chunk * 32 + lane];
+      cid = ccid[(int64_t)chunk * 32 + lane];
+    }
+    if (rem <= 0) D = 0; /* padding lane */
+    double norm = 0.0, sum_p = 0.0;
     int last_pos = D - 1;
     {
       int lp = -1;
       for (int j = 0; j < D; ++j) {
-        const double pj = p[j];
+        const double pj = mu[__ldg(pc + 32 * j)];
         norm += pj;
         if (pj > 0.0) lp = j;
       }
       if (lp >= 0) last_pos = lp;
     }
-    mmq_rng g;
-    mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | cid, sweep);
-    mmq_alloc_chain(p, ChainX{pc, counts}, D, kv, norm, last_pos, &g);
+    __syncthreads(); /* the previous pass is done with S */
+    if (tid == 0) S.dmax = 0;
+    S.cid[tid] = cid;
+    __syncthreads();
+    {
+      const int dm = __reduce_max_sync(0xffffffffu, D);
+      if (lane == 0 && dm > 0) atomicMax(&S.dmax, dm);
+    }
+    __syncthreads();
+    const int dmax = S.dmax;
+    for (int j = 0; j < dmax; ++j) {
+      /* ---- what does this lane's class need for member j? */
+      int64_t x = 0;
+      bool pending = false, btrs = false;
+      double pj = 0.0, pr = 0.0;
+      int32_t cj = -1;
+      if (tid < 3) S.n[tid] = 0;
+      if (j < D) {
+        cj = __ldg(pc + 32 * j);
+        pj = mu[cj];
+        if (j == last_pos) x = rem; /* zero-probability members never receive fragments */
+        else if (rem > 0 && pj > 0.0) {
+          const double denom = norm - sum_p;
+          pr = (denom > 0.0) ? pj / denom : 1.0;
+          if (pr > 1.0) pr = 1.0;
+          pending = true;
+          const double ph = pr > 0.5 ? 1.0 - pr : pr;
+          btrs = rem >= 2 && pr < 1.0 && (double)rem * ph >= MMQ_BINV_MEAN;
+        }
+      }
+      __syncthreads();
+      {
+        const int pt = queue_slot(&S.n[0], pending && btrs, lane);
+        if (pt >= 0) { S.qt[0][pt].p = pr > 0.5 ? 1.0 - pr : pr; S.qt[0][pt].n = (int)rem; S.qt[0][pt].owner = tid | (pr > 0.5 ? 1 << 16 : 0); }
+        const int pi = queue_slot(&S.n[2], pending && !btrs, lane);
+        if (pi >= 0) { S.qi[pi].p = pr; S.qi[pi].n = (int)rem; S.qi[pi].owner = tid; }
+      }
+      __syncthreads();
+      /* ---- BTRS: attempt r of every queued binomial, densely; the rejected ones go round again */
+      for (uint32_t r = 0;; ++r) {
+        const int ncur = S.n[r & 1];
+        if (ncur == 0) break;
+        __syncthreads();
+        if (tid == 0) S.n[(r + 1) & 1] = 0;
+        __syncthreads();
+        if ((tid & ~31) < ncur) {
+          bool ok = true;
+          chain_req q = {0.0, 0, 0};
+          if (tid < ncur) {
+            q = S.qt[r & 1][tid];
+            const int owner = q.owner & 0xffff;
+            mmq_rng g;
+            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[owner], sweep);
+            int64_t xb = 0;
+            ok = mmq_btrs_attempt(&g, MMQ_CHAIN_BLOCK(j) + r, mmq_btrs_setup(q.n, q.p), &xb) != 0;
+            if (ok) S.result[owner] = (q.owner >> 16) ? q.n - (int)xb : (int)xb;
+          }
+          const int pos = queue_slot(&S.n[(r + 1) & 1], !ok, lane);
+          if (pos >= 0) S.qt[(r + 1) & 1][pos] = q;
+        }
+        __syncthreads();
+      }
+      /* ---- inversions (mean below 10), single fragments left, p == 1 */
+      if (tid < S.n[2]) {
+        const chain_req q = S.qi[tid];
+        mmq_rng g;
+        mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner], sweep);
+        S.result[q.owner] = (int)mmq_binomial(&g, MMQ_CHAIN_BLOCK(j), q.n, q.p);
+      }
+      __syncthreads();
+      if (pending) x = S.result[tid];
+      if (x != 0) atomicAdd(counts + cj, (int32_t)x);
+      rem -= x;
+      sum_p += pj;
+    }
   }
 }
 
@@ -422,8 +501,9 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
   if (do_rest || do_chain || (do_hi && do_lo)) MMQ_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
   if (do_chain) {
     MMQ_CUDA(h, cudaStreamWaitEvent(h->stream4, h->ev_fork, 0));
-    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, (int64_t)h->num_sms * 4);
-    k_alloc_chain<<<grid, MMQ_CLS_WARPS * 32, 0, h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
+    constexpr int CW = MMQ_CHAIN_THREADS / 32;
+    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, (int64_t)h->num_sms * 2);
+    k_alloc_chain<<<grid, MMQ_CHAIN_THREADS, 0, h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
                                                               h->mu, h->counts, seed, sweep, sweep_base);
     MMQ_LAUNCHED(h);
     MMQ_CUDA(h, cudaEventRecord(h->ev_join4, h->stream4));

@@ -558,26 +558,107 @@ __global__ void k_count_reduce(const int64_t* __restrict__ tptr, const uint32_t*
   }
 }
 
+/* ---- K4: the Gamma update, 256 transcripts per block pass, rejections regrouped ----------------------------
+ * Marsaglia-Tsang is a rejection sampler and the a < 1 boost an extra branch: with one transcript per lane running its
+ * own loop, a warp pays for its slowest lane (measured in round 1: 13 of 32 lanes active on average).  Here an attempt
+ * is a pure function of (transcript, sweep, attempt number) (include/mmq_sampler.h), so the block runs attempt 0 of all
+ * its transcripts densely, queues the rejected ones (~5 %) in shared memory and runs attempt 1 of those densely, and so
+ * on; the boosts (transcripts without fragments: shape alpha < 1) are queued and done densely too.  Same values, bit
+ * for bit, as the sequential mmq_gamma of the CPU replay. */
+#define MMQ_GAMMA_THREADS 256
+struct gamma_smem {
+  double d[MMQ_GAMMA_THREADS], c[MMQ_GAMMA_THREADS], v[MMQ_GAMMA_THREADS], boost[MMQ_GAMMA_THREADS];
+  int32_t id[MMQ_GAMMA_THREADS], cnt_t[MMQ_GAMMA_THREADS];
+  int q[2][MMQ_GAMMA_THREADS], qb[MMQ_GAMMA_THREADS];
+  int n[3];
+};
+/* Every thread of the block calls this with its transcript t (or t < 0: none) and its count c; returns the new mu[t]. */
+__device__ __forceinline__ double gamma_block(gamma_smem& S, int64_t t, int32_t c, double rate, double alpha, uint32_t seed, uint32_t sweep) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool valid = t >= 0;
+  double a = alpha + (double)c;
+  const bool boosted = valid && a < 1.0;
+  if (a < 1.0) a += 1.0;
+  const mmq_gamma_par par = mmq_gamma_setup(a);
+  __syncthreads(); /* the previous pass is done with S */
+  S.d[tid] = par.d; S.c[tid] = par.c; S.id[tid] = (int32_t)t; S.cnt_t[tid] = c; S.boost[tid] = 1.0;
+  if (tid < 3) S.n[tid] = 0;
+  __syncthreads();
+  {
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
+    double v = 0.0;
+    const bool ok = valid ? mmq_gamma_attempt(&g, 0u, par, &v) != 0 : true;
+    if (ok) S.v[tid] = v;
+    const int pos = queue_slot(&S.n[0], !ok, lane);
+    if (pos >= 0) S.q[0][pos] = tid;
+    const int pb = queue_slot(&S.n[2], boosted, lane);
+    if (pb >= 0) S.qb[pb] = tid;
+  }
+  __syncthreads();
+  for (uint32_t r = 1;; ++r) {
+    const int ncur = S.n[(r - 1) & 1];
+    if (ncur == 0) break;
+    __syncthreads();
+    if (tid == 0) S.n[r & 1] = 0;
+    __syncthreads();
+    if ((tid & ~31) < ncur) {
+      bool ok = true;
+      int item = 0;
+      if (tid < ncur) {
+        item = S.q[(r - 1) & 1][tid];
+        mmq_rng g;
+        mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)S.id[item], sweep);
+        mmq_gamma_par q;
+        q.d = S.d[item]; q.c = S.c[item];
+        double v = 0.0;
+        ok = mmq_gamma_attempt(&g, r, q, &v) != 0;
+        if (ok) S.v[item] = v;
+      }
+      const int pos = queue_slot(&S.n[r & 1], !ok, lane);
+      if (pos >= 0) S.q[r & 1][pos] = item;
+    }
+    __syncthreads();
+  }
+  const int nb = S.n[2];
+  if (tid < nb) {
+    const int item = S.qb[tid];
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)S.id[item], sweep);
+    S.boost[item] = mmq_gamma_boost(&g, alpha + (double)S.cnt_t[item]);
+  }
+  __syncthreads();
+  return S.boost[tid] * par.d * S.v[tid] / rate;
+}
+
 /* K4 (+K5 capture): mu[t] ~ Gamma(alpha + counts[t], rate beta + l[t]); counts
  * are cleared for the next sweep; trace_col (= trace + slot, or null) receives
  * mu at stride trace_len.  src/mmseq.cpp:904-917. */
-__global__ void k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
-                        double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
-                        double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy,
-                        const uint32_t* __restrict__ sweep_base) {
+__global__ void __launch_bounds__(MMQ_GAMMA_THREADS)
+k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
+        double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
+        double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy,
+        const uint32_t* __restrict__ sweep_base) {
+  __shared__ gamma_smem S;
   if (sweep_base) sweep += *sweep_base;
   /* sweep s with s % stride == 0 is recorded in slot s / stride (src/mmseq.cpp:911-917) */
   double* trace_col = nullptr;
   if (trace && stride > 0 && sweep % (uint32_t)stride == 0 && sweep / (uint32_t)stride < (uint32_t)trace_len) trace_col = trace + sweep / (uint32_t)stride;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-    const int32_t c = counts[t];
-    counts[t] = counts_base ? counts_base[t] : 0; /* classes skipped by the segmented kernel (singletons) */
-    if (counts_copy) counts_copy[t] = c;
-    mmq_rng g;
-    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
-    const double v = mmq_gamma(&g, alpha + (double)c, beta + len[t]);
-    mu[t] = v;
-    if (trace_col) trace_col[t * (int64_t)trace_len] = v;
+  for (int64_t t0 = (int64_t)blockIdx.x * MMQ_GAMMA_THREADS; t0 < n; t0 += (int64_t)gridDim.x * MMQ_GAMMA_THREADS) {
+    const int64_t t = t0 + threadIdx.x < n ? t0 + threadIdx.x : -1;
+    int32_t c = 0;
+    double rate = 1.0;
+    if (t >= 0) {
+      c = counts[t];
+      counts[t] = counts_base ? counts_base[t] : 0; /* classes the allocation kernels skip (singletons) */
+      if (counts_copy) counts_copy[t] = c;
+      rate = beta + len[t];
+    }
+    const double v = gamma_block(S, t, c, rate, alpha, seed, sweep);
+    if (t >= 0) {
+      mu[t] = v;
+      if (trace_col) trace_col[t * (int64_t)trace_len] = v;
+    }
   }
 }
 
@@ -604,9 +685,11 @@ struct mmq_p2p_args {
 
 /* Debug / parity variant (mmq_sweep_debug): a full all-reduce — every rank reads the count vectors of
  * ALL ranks, draws every Gamma variate and keeps the summed counts.  One barrier. */
-__global__ void k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
-                            double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
-                            double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
+__global__ void __launch_bounds__(MMQ_GAMMA_THREADS)
+k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
+            double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
+            double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
+  __shared__ gamma_smem S;
   const int32_t epoch = a.epoch + (a.epoch_base ? *a.epoch_base : 0);
   int32_t* own = reinterpret_cast<int32_t*>(a.base[a.rank]);
   if (blockIdx.x == 0 && threadIdx.x < a.nranks)
@@ -618,16 +701,21 @@ __global__ void k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_b
   double* trace_col = nullptr;
   if (trace && stride > 0 && sweep % (uint32_t)stride == 0 && sweep / (uint32_t)stride < (uint32_t)trace_len) trace_col = trace + sweep / (uint32_t)stride;
   int32_t* reset = reinterpret_cast<int32_t*>(a.base[a.rank] + a.off_reset);
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t t0 = (int64_t)blockIdx.x * MMQ_GAMMA_THREADS; t0 < n; t0 += (int64_t)gridDim.x * MMQ_GAMMA_THREADS) {
+    const int64_t t = t0 + threadIdx.x < n ? t0 + threadIdx.x : -1;
     int32_t c = 0;
-    for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
-    reset[t] = counts_base ? counts_base[t] : 0;
-    if (counts_copy) counts_copy[t] = c;
-    mmq_rng g;
-    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
-    const double v = mmq_gamma(&g, alpha + (double)c, beta + len[t]);
-    mu[t] = v;
-    if (trace_col) trace_col[t * (int64_t)trace_len] = v;
+    double rate = 1.0;
+    if (t >= 0) {
+      for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
+      reset[t] = counts_base ? counts_base[t] : 0;
+      if (counts_copy) counts_copy[t] = c;
+      rate = beta + len[t];
+    }
+    const double v = gamma_block(S, t, c, rate, alpha, seed, sweep);
+    if (t >= 0) {
+      mu[t] = v;
+      if (trace_col) trace_col[t * (int64_t)trace_len] = v;
+    }
   }
   /* the mu flags advance too, so that a later k_gamma_rs (which waits for them) sees a monotone epoch: every rank
    * wrote its own mu, nothing to wait for */
@@ -642,8 +730,10 @@ __global__ void k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_b
  * "mu slice written" to the peers and waits for theirs, so that when the kernel completes the whole mu
  * vector is in place on this rank: the next allocation kernel needs no other synchronisation than stream
  * order.  The other parity buffer of the own counts is reset for the next sweep (all of it, by all blocks). */
-__global__ void k_gamma_rs(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len, int64_t n,
-                           double alpha, double beta, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+__global__ void __launch_bounds__(MMQ_GAMMA_THREADS)
+k_gamma_rs(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len, int64_t n,
+           double alpha, double beta, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+  __shared__ gamma_smem S;
   if (sweep_base) sweep += *sweep_base;
   const int32_t epoch = a.epoch + (a.epoch_base ? *a.epoch_base : 0);
   int32_t* own = reinterpret_cast<int32_t*>(a.base[a.rank]);
@@ -653,14 +743,18 @@ __global__ void k_gamma_rs(mmq_p2p_args a, const int32_t* __restrict__ counts_ba
     for (int r = 0; r < a.nranks; ++r)
       if (r != a.rank) p2p_wait(own + MMQ_P2P_FLAG_ALLOC + 8 * r, epoch);
   __syncthreads();
-  const int64_t t0 = n * a.rank / a.nranks, t1 = n * (a.rank + 1) / a.nranks;
-  for (int64_t t = t0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < t1; t += (int64_t)gridDim.x * blockDim.x) {
+  const int64_t s0 = n * a.rank / a.nranks, s1 = n * (a.rank + 1) / a.nranks;
+  for (int64_t t0 = s0 + (int64_t)blockIdx.x * MMQ_GAMMA_THREADS; t0 < s1; t0 += (int64_t)gridDim.x * MMQ_GAMMA_THREADS) {
+    const int64_t t = t0 + threadIdx.x < s1 ? t0 + threadIdx.x : -1;
     int32_t c = 0;
-    for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
-    mmq_rng g;
-    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
-    const double v = mmq_gamma(&g, alpha + (double)c, beta + len[t]);
-    for (int r = 0; r < a.nranks; ++r) reinterpret_cast<double*>(a.base[r] + a.off_mu)[t] = v;
+    double rate = 1.0;
+    if (t >= 0) {
+      for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
+      rate = beta + len[t];
+    }
+    const double v = gamma_block(S, t, c, rate, alpha, seed, sweep);
+    if (t >= 0)
+      for (int r = 0; r < a.nranks; ++r) reinterpret_cast<double*>(a.base[r] + a.off_mu)[t] = v;
   }
   int32_t* reset = reinterpret_cast<int32_t*>(a.base[a.rank] + a.off_reset);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
@@ -1352,13 +1446,13 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
     a.epoch_base = epoch_base;
     mark(h->ev_gamma);
     if (counts_copy) { /* debug / parity: full all-reduce, summed counts kept */
-      k_gamma_p2p<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
+      k_gamma_p2p<<<mmq_grid_for(h->n, MMQ_GAMMA_THREADS, h->num_sms * 4), MMQ_GAMMA_THREADS, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
                                                                                 h->trace_len, h->n, h->alpha, h->beta, seed, sweep, counts_copy);
       MMQ_LAUNCHED(h);
     } else {
       const int64_t slice = (h->n + h->p2p_n - 1) / h->p2p_n;
       /* the grid must be co-resident (its last block waits for the peers while the others finish): <= 8 blocks of 128 per SM */
-      k_gamma_rs<<<mmq_grid_for(std::max<int64_t>(slice, h->n / 8), 128, h->num_sms * 8), 128, 0, h->stream>>>(a, h->seg_base, h->len, h->n, h->alpha, h->beta, seed, sweep, sweep_base);
+      k_gamma_rs<<<mmq_grid_for(std::max<int64_t>(slice, h->n / 8), MMQ_GAMMA_THREADS, h->num_sms * 4), MMQ_GAMMA_THREADS, 0, h->stream>>>(a, h->seg_base, h->len, h->n, h->alpha, h->beta, seed, sweep, sweep_base);
       MMQ_LAUNCHED(h);
       /* is this sweep recorded?  plain launch: the host knows; graph capture: sweep = j, the replays start at
        * sweeps congruent to capture_phase modulo the stride (the kernel re-checks against the real sweep number) */
@@ -1376,7 +1470,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
   }
   if ((rc = mmq_allreduce(h, h->counts, (size_t)h->n, 0))) return rc;
   mark(h->ev_gamma);
-  k_gamma<<<mmq_grid_for(h->n, 128, h->num_sms * 16), 128, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride, h->trace_len, h->n,
+  k_gamma<<<mmq_grid_for(h->n, MMQ_GAMMA_THREADS, h->num_sms * 6), MMQ_GAMMA_THREADS, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride, h->trace_len, h->n,
                                                                           h->alpha, h->beta, seed, sweep, counts_copy, sweep_base);
   MMQ_LAUNCHED(h);
   mark(h->ev_gamma);

@@ -15,6 +15,18 @@ __device__ __forceinline__ void cat_red(int32_t* __restrict__ counts, int32_t c,
   }
 }
 
+/* Position of this lane's item in a shared-memory queue (counter in shared memory), -1 when pred is false:
+ * one atomic per warp.  Every lane of the warp must call it. */
+__device__ __forceinline__ int queue_slot(int* counter, bool pred, int lane) {
+  const unsigned m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0u) return -1;
+  const int leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
 /* ---- mbarrier + TMA 1-D bulk copy (SASS: SYNCS.*, UBLKCP) ---- */
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {

@@ -77,6 +77,15 @@ void orc_draw_uniform(uint32_t seed, int64_t cnt, double* out) {
     out[i] = mmq_uniform(&g);
   }
 }
+void orc_draw_normal(uint32_t seed, int64_t cnt, double* out) {
+  for (int64_t i = 0; i < cnt; ++i) {
+    mmq_rng g;
+    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)i, 0);
+    uint32_t w[4];
+    mmq_rng_block(&g, 1u, w);
+    out[i] = mmq_normal_bm(w[0], w[1], w[2]);
+  }
+}
 void orc_draw_gamma(uint32_t seed, int64_t cnt, double a, double rate, double* out) {
   for (int64_t i = 0; i < cnt; ++i) {
     mmq_rng g;
@@ -88,7 +97,7 @@ void orc_draw_binomial(uint32_t seed, int64_t cnt, int64_t n, double p, int64_t*
   for (int64_t i = 0; i < cnt; ++i) {
     mmq_rng g;
     mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, (uint64_t)i, 0);
-    out[i] = mmq_binomial(&g, n, p);
+    out[i] = mmq_binomial(&g, 0u, n, p);
   }
 }
 void orc_draw_alloc(uint32_t seed, int64_t cnt, int d, const double* p, int64_t k, int32_t* out) {
@@ -96,7 +105,8 @@ void orc_draw_alloc(uint32_t seed, int64_t cnt, int d, const double* p, int64_t 
 }
 void orc_math(int which, int64_t cnt, const double* in, double* out) {
   for (int64_t i = 0; i < cnt; ++i)
-    out[i] = which == 0 ? mmq_log(in[i]) : which == 1 ? mmq_exp(in[i]) : which == 2 ? mmq_ndtri(in[i]) : mmq_log1p(in[i]);
+    out[i] = which == 0 ? mmq_log(in[i]) : which == 1 ? mmq_exp(in[i]) : which == 2 ? mmq_ndtri(in[i]) : which == 3 ? mmq_log1p(in[i])
+           : mmq_cos2pi_u32((uint32_t)in[i]); /* 4: cos(2 pi (w + 1/2) / 2^32), w passed as a double */
 }
 
 /* ------------------------------------------------------------------------

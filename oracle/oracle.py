@@ -40,6 +40,7 @@ def lib():
         L.orc_philox4x32_10.argtypes = [vp, vp, vp]
         L.orc_draw_uniform.argtypes = [u32, i64, vp]
         L.orc_draw_gamma.argtypes = [u32, i64, dbl, dbl, vp]
+        L.orc_draw_normal.argtypes = [u32, i64, vp]
         L.orc_draw_binomial.argtypes = [u32, i64, i64, dbl, vp]
         L.orc_draw_alloc.argtypes = [u32, i64, i32, vp, i64, vp]
         L.orc_math.argtypes = [i32, i64, vp, vp]
@@ -102,6 +103,10 @@ def draw_uniform(seed, cnt):
     o = np.zeros(cnt); lib().orc_draw_uniform(seed, cnt, _p(o)); return o
 
 
+def draw_normal(seed, cnt):
+    o = np.zeros(cnt); lib().orc_draw_normal(seed, cnt, _p(o)); return o
+
+
 def draw_gamma(seed, cnt, a, rate):
     o = np.zeros(cnt); lib().orc_draw_gamma(seed, cnt, a, rate, _p(o)); return o
 
@@ -117,7 +122,7 @@ def draw_alloc(seed, cnt, p, k):
 
 def math_fn(which, x):
     x = _c(x, np.float64); o = np.zeros_like(x)
-    lib().orc_math({"log": 0, "exp": 1, "ndtri": 2, "log1p": 3}[which], x.size, _p(x), _p(o)); return o
+    lib().orc_math({"log": 0, "exp": 1, "ndtri": 2, "log1p": 3, "cos2pi_u32": 4}[which], x.size, _p(x), _p(o)); return o
 
 
 def gsl_binomial(seed, cnt, n, p):
