@@ -144,11 +144,11 @@ int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweep
               int trace_len, int flags);
 
 /* What the class plan of a collapsed shard (classes with counts k; built by mmq_create) holds:
- * out[0] 1 if the plan is in use, out[1] classes of the small set (k <= MMQ_CAT_K fragments, at most
+ * out[0] 1 if the plan is in use, out[1] classes of the small set (k <= mmq_cat_limit(d) fragments, at most
  * 64 members: categorical draws, stands in for the multinomial of src/mmseq.cpp:880 for those classes), out[2] packed column
  * slots and out[3] class slots streamed per sweep for them, out[4] classes and out[5] CSR entries
  * left to the general kernel (more than 64 members), out[6] classes of the chain set (more than
- * MMQ_CAT_K fragments: gsl_ran_multinomial's conditional-binomial chain, one class per lane) and out[7]
+ * mmq_cat_limit(d) fragments: gsl_ran_multinomial's conditional-binomial chain, one class per lane) and out[7]
  * their packed column slots.  Used by bench.py for the algorithmic-bytes figure. */
 int mmq_cls_stats(const mmq_handle* h, int64_t out[8]);
 

@@ -40,13 +40,33 @@
 #define MMQ_STREAM_ALLOC 0x414c4c4fu /* per hit class, per sweep   */
 #define MMQ_STREAM_GAMMA 0x47414d4du /* per transcript, per sweep  */
 #define MMQ_STREAM_PRIOR 0x5052494fu /* per unobserved transcript, per trace slot */
-#define MMQ_CAT_K 64 /* classes with 2..MMQ_CAT_K fragments: categorical draws (four 32-bit uniforms per Philox block), O(k d);
-                        more fragments: gsl_ran_multinomial's chain of conditional binomials, O(d) (round 1 drew up to 8192
-                        categoricals: 54 % of a sweep's draws on the config-2 sample belonged to classes above 64) */
+/* A class with d members and k fragments: k categorical draws (four 32-bit uniforms per Philox block), O(k d), up to
+ * mmq_cat_limit(d) fragments; above that gsl_ran_multinomial's chain of d - 1 conditional binomials, O(d).  The limit
+ * grows with d because a chain is serial in the members (a binomial costs about as much as 32 categorical draws):
+ * 32 (d - 1), at least 32 and at most MMQ_CAT_KMAX.  Round 1 drew up to 8192 categoricals whatever d: 54 % of a sweep's
+ * draws on the config-2 sample belonged to classes above 64. */
+#define MMQ_CAT_KMAX 512
 #define MMQ_CAT_GROUP 64 /* categorical draws are generated in groups of at most 64 (16 blocks): one slot of the class-plan kernel */
 #define MMQ_STREAM_CAT 0x43415431u   /* k == 1 classes: one block per QUAD of classes (one 32-bit word each) */
 
+MMQ_HD int64_t mmq_cat_limit(int d) {
+  const int64_t v = 32 * (int64_t)(d - 1);
+  return v < 32 ? 32 : v > MMQ_CAT_KMAX ? MMQ_CAT_KMAX : v;
+}
+
 /* ------------------------------------------------------------------ bits */
+
+/* Fused multiply-add, spelled out: the sources are compiled with contraction OFF (nvcc -fmad=false, gcc
+ * -ffp-contract=off) so that a * b + c rounds twice on both sides; where one rounding is wanted (polynomial
+ * evaluation: half the instructions and half the dependent latency on the GPU) it is asked for explicitly.  IEEE fma
+ * is correctly rounded everywhere (DFMA on the device; the FMA unit, or glibc's exact software fma, on the host). */
+MMQ_HD double mmq_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+  return __fma_rn(a, b, c);
+#else
+  return __builtin_fma(a, b, c);
+#endif
+}
 
 MMQ_HD uint64_t mmq_d2u(double x) {
 #if defined(__CUDA_ARCH__)
@@ -180,11 +200,11 @@ MMQ_HD double mmq_log(double x) {
   double s = f / (2.0 + f);
   double z = s * s;
   double w = z * z;
-  double t1 = w * (Lg2 + w * (Lg4 + w * Lg6));
-  double t2 = z * (Lg1 + w * (Lg3 + w * (Lg5 + w * Lg7)));
+  double t1 = w * mmq_fma(w, mmq_fma(w, Lg6, Lg4), Lg2);
+  double t2 = z * mmq_fma(w, mmq_fma(w, mmq_fma(w, Lg7, Lg5), Lg3), Lg1);
   double R = t2 + t1;
   double dk = (double)k;
-  return s * (hfsq + R) + dk * ln2_lo - hfsq + f + dk * ln2_hi;
+  return mmq_fma(dk, ln2_hi, mmq_fma(s, hfsq + R, dk * ln2_lo) - hfsq + f);
 }
 
 /* log(1+x) for |x| < 1 through log(): log(u) * x / (u - 1), u = 1 + x
@@ -215,7 +235,7 @@ MMQ_HD double mmq_exp(double x) {
   double lo = fk * ln2_lo;
   double r = hi - lo;
   double t = r * r;
-  double c = r - t * (P1 + t * (P2 + t * (P3 + t * (P4 + t * P5))));
+  double c = r - t * mmq_fma(t, mmq_fma(t, mmq_fma(t, mmq_fma(t, P5, P4), P3), P2), P1);
   double y = 1.0 - ((lo - (r * c) / (2.0 - c)) - hi);
   if (k >= -1021 && k <= 1023) return y * mmq_pow2i(k);
   if (k > 1023) return y * mmq_pow2i(1023) * mmq_pow2i(k - 1023);
@@ -291,7 +311,7 @@ MMQ_HD double mmq_uniform52(uint32_t hi, uint32_t lo) {
 /* cos(2 pi (w + 1/2) / 2^32) from the 32-bit word itself: the top three bits pick the octant, the other 29 the
  * position inside it, mirrored in the odd octants so that the polynomial argument is phi = (q + 1/2) 2^-30 pi/2
  * with an integer q in [0, 2^30): cos(phi) on (0, pi/2) by its Taylor polynomial in phi^2 up to phi^24
- * (truncation error 3e-22), Horner form, no branches.  Only IEEE add / mul: identical on host and device. */
+ * (truncation error 3e-22), Horner form with explicit fused multiply-adds, no branches: identical on host and device. */
 MMQ_HD double mmq_cos2pi_u32(uint32_t w) {
   const uint32_t o = w >> 29, f = w & 0x1fffffffu;
   const uint32_t fm = (o & 1u) ? (0x1fffffffu - f) : f;             /* distance to the nearer octant boundary */
@@ -300,18 +320,18 @@ MMQ_HD double mmq_cos2pi_u32(uint32_t w) {
   const double phi = ((double)q + 0.5) * 1.4629180792671596e-09;     /* 2^-30 pi/2 */
   const double z = phi * phi;
   double c = 1.6117375710961184e-24;                                  /* 1/24! */
-  c = c * z + -8.8967913924505741e-22;                                /* -1/22! */
-  c = c * z + 4.1103176233121648e-19;                                 /* 1/20! */
-  c = c * z + -1.5619206968586225e-16;                                /* -1/18! */
-  c = c * z + 4.7794773323873853e-14;                                 /* 1/16! */
-  c = c * z + -1.1470745597729725e-11;                                /* -1/14! */
-  c = c * z + 2.08767569878681e-09;                                   /* 1/12! */
-  c = c * z + -2.7557319223985888e-07;                                /* -1/10! */
-  c = c * z + 2.48015873015873e-05;                                   /* 1/8! */
-  c = c * z + -0.001388888888888889;                                  /* -1/6! */
-  c = c * z + 0.041666666666666664;                                   /* 1/4! */
-  c = c * z + -0.5;
-  c = c * z + 1.0;
+  c = mmq_fma(c, z, -8.8967913924505741e-22);                         /* -1/22! */
+  c = mmq_fma(c, z, 4.1103176233121648e-19);                          /* 1/20! */
+  c = mmq_fma(c, z, -1.5619206968586225e-16);                         /* -1/18! */
+  c = mmq_fma(c, z, 4.7794773323873853e-14);                          /* 1/16! */
+  c = mmq_fma(c, z, -1.1470745597729725e-11);                         /* -1/14! */
+  c = mmq_fma(c, z, 2.08767569878681e-09);                            /* 1/12! */
+  c = mmq_fma(c, z, -2.7557319223985888e-07);                         /* -1/10! */
+  c = mmq_fma(c, z, 2.48015873015873e-05);                            /* 1/8! */
+  c = mmq_fma(c, z, -0.001388888888888889);                           /* -1/6! */
+  c = mmq_fma(c, z, 0.041666666666666664);                            /* 1/4! */
+  c = mmq_fma(c, z, -0.5);
+  c = mmq_fma(c, z, 1.0);
   return neg ? -c : c;
 }
 
@@ -335,8 +355,9 @@ MMQ_HD mmq_gamma_par mmq_gamma_setup(double a_ge_1) {
   q.c = (1.0 / 3.0) / sqrt(q.d);
   return q;
 }
-/* attempt r: returns 1 and *v_out = v^3 when accepted */
-MMQ_HD int mmq_gamma_attempt(const mmq_rng* g, uint32_t r, mmq_gamma_par q, double* v_out) {
+/* attempt r, first part: 1 accepted (squeeze), 0 rejected (v <= 0), 2 undecided: mmq_gamma_logtest(u, x2, v, d) decides.
+ * *v_out = v^3.  The two parts are separate so that a kernel can run the (rare, expensive) log tests of a block densely. */
+MMQ_HD int mmq_gamma_try(const mmq_rng* g, uint32_t r, mmq_gamma_par q, double* v_out, double* x2_out, double* u_out) {
   uint32_t w[4];
   mmq_rng_block(g, 1u + r, w);
   const double x = mmq_normal_bm(w[0], w[1], w[2]);
@@ -345,9 +366,16 @@ MMQ_HD int mmq_gamma_attempt(const mmq_rng* g, uint32_t r, mmq_gamma_par q, doub
   v = v * v * v;
   const double u = mmq_uniform32(w[3]);
   const double x2 = x * x;
-  *v_out = v;
-  if (u < 1.0 - 0.0331 * x2 * x2) return 1;
-  return mmq_log(u) < 0.5 * x2 + q.d * (1.0 - v + mmq_log(v));
+  *v_out = v; *x2_out = x2; *u_out = u;
+  return (u < 1.0 - 0.0331 * x2 * x2) ? 1 : 2;
+}
+MMQ_HD int mmq_gamma_logtest(double u, double x2, double v, double d) {
+  return mmq_log(u) < 0.5 * x2 + d * (1.0 - v + mmq_log(v));
+}
+MMQ_HD int mmq_gamma_attempt(const mmq_rng* g, uint32_t r, mmq_gamma_par q, double* v_out) {
+  double x2 = 0.0, u = 0.0;
+  const int st = mmq_gamma_try(g, r, q, v_out, &x2, &u);
+  return st == 2 ? mmq_gamma_logtest(u, x2, *v_out, q.d) : st;
 }
 /* U^(1/a) for a < 1 */
 MMQ_HD double mmq_gamma_boost(const mmq_rng* g, double a_lt_1) {
@@ -397,6 +425,22 @@ MMQ_HD double mmq_stirling_tail(double k) {
  * Attempt r of a draw reads block block0 + r of the stream: words 0, 1 = the first 52-bit uniform, words 2, 3 the
  * second (BTRS only). */
 #define MMQ_BINV_MEAN 10.0
+/* 1/x for x = 1..63, correctly rounded (the compiler folds the divisions): the inversion loop multiplies instead of
+ * dividing (a division is ~20 dependent instructions on the GPU) */
+#define MMQ_INV_ROW(b) 1.0 / ((b) + 0), 1.0 / ((b) + 1), 1.0 / ((b) + 2), 1.0 / ((b) + 3), 1.0 / ((b) + 4), 1.0 / ((b) + 5), 1.0 / ((b) + 6), 1.0 / ((b) + 7)
+#define MMQ_INV_INIT {0.0, 1.0 / 1, 1.0 / 2, 1.0 / 3, 1.0 / 4, 1.0 / 5, 1.0 / 6, 1.0 / 7, MMQ_INV_ROW(8), MMQ_INV_ROW(16), MMQ_INV_ROW(24), \
+                      MMQ_INV_ROW(32), MMQ_INV_ROW(40), MMQ_INV_ROW(48), MMQ_INV_ROW(56)}
+#if defined(__CUDACC__)
+static __constant__ double mmq_inv_dev[64] = MMQ_INV_INIT;
+#endif
+static const double mmq_inv_host[64] = MMQ_INV_INIT;
+MMQ_HD double mmq_inv_small(int64_t x) { /* 1 <= x */
+#if defined(__CUDA_ARCH__)
+  return x < 64 ? mmq_inv_dev[x] : 1.0 / (double)x;
+#else
+  return x < 64 ? mmq_inv_host[x] : 1.0 / (double)x;
+#endif
+}
 MMQ_HD int64_t mmq_binv(const mmq_rng* g, uint32_t block0, int64_t n, double p) {
   const double dn = (double)n;
   const double q = 1.0 - p;
@@ -413,7 +457,7 @@ MMQ_HD int64_t mmq_binv(const mmq_rng* g, uint32_t block0, int64_t n, double p) 
       u -= r;
       x += 1;
       if (x > n) break;
-      r *= (a / (double)x - s);
+      r *= (a * mmq_inv_small(x) - s);
     }
     if (x <= n) return x;
   }
@@ -521,7 +565,7 @@ MMQ_HD void mmq_x_add(XIt x, int j, int32_t v) {
  *         weight when weights are present); read twice, never written
  *   x[j]  out: number of fragments given to member j; sum_j x[j] == k
  * d == 1 consumes no random numbers (x = k).  k == 1 is one categorical draw
- * (one 32-bit uniform of the CAT stream: chosen = first j with u * sum_p < p_0 + ... + p_j); 2 <= k <= MMQ_CAT_K is k
+ * (one 32-bit uniform of the CAT stream: chosen = first j with u * sum_p < p_0 + ... + p_j); 2 <= k <= mmq_cat_limit(d) is k
  * such draws from the class's own stream (32-bit uniforms, four per block).  Larger k is gsl_ran_multinomial's chain of conditional
  * binomials x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)).
  * The arithmetic order (left-to-right sums) is part of the contract: the CPU
@@ -564,7 +608,7 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
     return;
   }
   mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, class_id, sweep);
-  if (k <= MMQ_CAT_K) {
+  if (k <= mmq_cat_limit(d)) {
     /* k independent categorical draws — the same Multinomial(k; p) as the binomial chain below,
      * without log/exp and without a serial dependence between members.  Draw t uses word t & 3 of
      * block t >> 2 of the class's own stream as one 32-bit uniform (the granularity of the k == 1

@@ -8,7 +8,7 @@
  *
  *   d == 1              nothing: x = k is deterministic, summed once into seg_base[] (the Gamma
  *                       kernel restarts counts[] from it);
- *   k <= MMQ_CAT_K and  the "small" set: k categorical draws, four per Philox block
+ *   k <= mmq_cat_limit(d),  the "small" set: k categorical draws, four per Philox block
  *   d <= MMQ_CLS_DMAX   (include/mmq_sampler.h).  A class becomes ceil(k / 64) SLOTS of at most 64
  *                       draws (16 blocks), so a class with thousands of fragments is shared out
  *                       between lanes.  Slots are ordered by (d, blocks, first member) and packed
@@ -22,7 +22,7 @@
  *                       d and (almost always) the same number of blocks: no divergence.  The
  *                       order by first member keeps the mu gathers of a warp, and of the warps of
  *                       an SM, in neighbouring cache lines;
- *   the rest            (k > MMQ_CAT_K: conditional-binomial chain; or more than 64 members) a
+ *   the rest            (k > mmq_cat_limit(d): conditional-binomial chain; or more than 64 members) a
  *                       small sub-CSR handed to k_alloc, one class per warp, on a second stream.
  *
  * Two instances of the kernel (class sizes 2..8 in 64 registers, 9..16 and a generic loop up to 64
@@ -241,9 +241,9 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
   }
 }
 
-/* The chain set: classes with more than MMQ_CAT_K fragments — gsl_ran_multinomial's chain of conditional binomials
+/* The chain set: classes with more than mmq_cat_limit(d) fragments — gsl_ran_multinomial's chain of conditional binomials
  * (src/mmseq.cpp:880), O(d) per class whatever k is.  One class per lane, 32 classes of equal size per chunk (member-major
- * like the small set, so every column load of a warp is one 128-byte line), longest classes first, 8 chunks per block.
+ * like the small set, so every column load of a warp is one 128-byte line), longest classes first, 4 chunks per block.
  * The lane sums its row left to right (norm, last member with p > 0), then the block walks the members in step:
  * x_j ~ Bin(rem, p_j / (norm - sum_{<j} p)).
  *
@@ -253,7 +253,7 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
  * sample.  An attempt being a pure function of (class, sweep, member, attempt number) (include/mmq_sampler.h), the
  * block instead QUEUES the binomials of a step in shared memory by regime and runs each queue densely: BTRS attempts
  * in rounds (the rejected ones re-queued), then the inversions.  Same integers as the CPU replay's mmq_alloc_chain. */
-#define MMQ_CHAIN_THREADS 256
+#define MMQ_CHAIN_THREADS 128
 struct chain_req { double p; int n; int owner; }; /* owner: thread | flip << 16 (x = n - x' for p > 1/2) */
 struct chain_smem {
   chain_req qt[2][MMQ_CHAIN_THREADS]; /* BTRS, ping-pong over attempts */
@@ -502,7 +502,7 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
   if (do_chain) {
     MMQ_CUDA(h, cudaStreamWaitEvent(h->stream4, h->ev_fork, 0));
     constexpr int CW = MMQ_CHAIN_THREADS / 32;
-    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, (int64_t)h->num_sms * 2);
+    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, (int64_t)h->num_sms * 4);
     k_alloc_chain<<<grid, MMQ_CHAIN_THREADS, 0, h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
                                                               h->mu, h->counts, seed, sweep, sweep_base);
     MMQ_LAUNCHED(h);

@@ -39,7 +39,7 @@ struct mmq_cls_host_plan {
   std::vector<unsigned long long> cdesc; /* [chunks] offset of the chunk in pcol << 8 | class size */
   int64_t chunks = 0, chunks_lo = 0, packed = 0, small_classes = 0, n_rest = 0, nnz_rest = 0;
   uint32_t cid_hi = 0;
-  /* the chain set: classes with more than MMQ_CAT_K fragments and at most MMQ_CLS_DMAX members (conditional-binomial
+  /* the chain set: classes with more than mmq_cat_limit(d) fragments and at most MMQ_CLS_DMAX members (conditional-binomial
    * chains, one class per lane of k_alloc_chain): member-major chunks of 32 like the small set, longest classes first */
   std::unique_ptr<int32_t[]> c_pcol;       /* [c_packed] */
   std::vector<int32_t> c_k;                /* [c_chunks * 32] fragments of the class (0: padding lane) */
@@ -113,7 +113,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
       const int64_t kv = kk[i];
       if ((uint32_t)(cid_of(i) >> 32) != cid_hi || kv < 0) t.ok = false;
       if (d == 1 || kv <= 0) { key16[i] = -1; ++t.n_single; } /* k == 0: nothing to allocate */
-      else if (kv <= MMQ_CAT_K && d <= MMQ_CLS_DMAX) {
+      else if (d <= MMQ_CLS_DMAX && kv <= mmq_cat_limit((int)d)) {
         ++t.small;
         ++hc[col[rp[i]]];
         if (kv == 1) { key16[i] = (int16_t)(d * MMQ_CLS_NQ + 16); ++t.key_count[key16[i]]; }
@@ -168,7 +168,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
   /* Within a key the classes are placed by their first member (a stable counting sort): members are
    * ascending and the isoforms of a gene are neighbours in the header, so the lanes of a warp and the
    * warps of an SM gather neighbouring mu — L1 hits instead of one L2 sector per 8-byte gather. */
-  static_assert(MMQ_CAT_K / MMQ_CAT_GROUP <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
+  static_assert(MMQ_CAT_KMAX / MMQ_CAT_GROUP <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
   struct Ord { int32_t i; int16_t key; uint8_t full, tail; }; /* key: of the partial slot (tail draws) when there is one */
   std::vector<Ord> order((size_t)small_classes);
   /* parallel stable counting sort (counts taken in the classification pass): per first member, thread t gets

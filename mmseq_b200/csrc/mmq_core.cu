@@ -568,9 +568,10 @@ __global__ void k_count_reduce(const int64_t* __restrict__ tptr, const uint32_t*
 #define MMQ_GAMMA_THREADS 256
 struct gamma_smem {
   double d[MMQ_GAMMA_THREADS], c[MMQ_GAMMA_THREADS], v[MMQ_GAMMA_THREADS], boost[MMQ_GAMMA_THREADS];
+  double lu[MMQ_GAMMA_THREADS], lx2[MMQ_GAMMA_THREADS], lv[MMQ_GAMMA_THREADS]; /* undecided attempts: the log test's inputs */
   int32_t id[MMQ_GAMMA_THREADS], cnt_t[MMQ_GAMMA_THREADS];
-  int q[2][MMQ_GAMMA_THREADS], qb[MMQ_GAMMA_THREADS];
-  int n[3];
+  int q[2][MMQ_GAMMA_THREADS], ql[MMQ_GAMMA_THREADS], qb[MMQ_GAMMA_THREADS];
+  int n[4]; /* retry queues 0 / 1, boosts, log tests */
 };
 /* Every thread of the block calls this with its transcript t (or t < 0: none) and its count c; returns the new mu[t]. */
 __device__ __forceinline__ double gamma_block(gamma_smem& S, int64_t t, int32_t c, double rate, double alpha, uint32_t seed, uint32_t sweep) {
@@ -582,44 +583,55 @@ __device__ __forceinline__ double gamma_block(gamma_smem& S, int64_t t, int32_t 
   const mmq_gamma_par par = mmq_gamma_setup(a);
   __syncthreads(); /* the previous pass is done with S */
   S.d[tid] = par.d; S.c[tid] = par.c; S.id[tid] = (int32_t)t; S.cnt_t[tid] = c; S.boost[tid] = 1.0;
-  if (tid < 3) S.n[tid] = 0;
+  if (tid < 4) S.n[tid] = 0;
   __syncthreads();
-  {
-    mmq_rng g;
-    mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)t, sweep);
-    double v = 0.0;
-    const bool ok = valid ? mmq_gamma_attempt(&g, 0u, par, &v) != 0 : true;
-    if (ok) S.v[tid] = v;
-    const int pos = queue_slot(&S.n[0], !ok, lane);
-    if (pos >= 0) S.q[0][pos] = tid;
-    const int pb = queue_slot(&S.n[2], boosted, lane);
-    if (pb >= 0) S.qb[pb] = tid;
-  }
-  __syncthreads();
-  for (uint32_t r = 1;; ++r) {
-    const int ncur = S.n[(r - 1) & 1];
+  /* round r: attempt r of the transcripts still open (round 0: all of them, one per thread), then the log tests of
+   * the attempts the squeeze did not decide, both densely; what is rejected goes to the other queue */
+  for (uint32_t r = 0;; ++r) {
+    const int ncur = r == 0 ? MMQ_GAMMA_THREADS : S.n[(r - 1) & 1];
     if (ncur == 0) break;
-    __syncthreads();
-    if (tid == 0) S.n[r & 1] = 0;
-    __syncthreads();
+    if (r > 0) {
+      __syncthreads();
+      if (tid == 0) { S.n[r & 1] = 0; S.n[3] = 0; }
+      __syncthreads();
+    }
     if ((tid & ~31) < ncur) {
-      bool ok = true;
-      int item = 0;
+      int st = 1, item = tid;
+      double v = 0.0, x2 = 0.0, u = 0.0;
       if (tid < ncur) {
-        item = S.q[(r - 1) & 1][tid];
-        mmq_rng g;
-        mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)S.id[item], sweep);
-        mmq_gamma_par q;
-        q.d = S.d[item]; q.c = S.c[item];
-        double v = 0.0;
-        ok = mmq_gamma_attempt(&g, r, q, &v) != 0;
-        if (ok) S.v[item] = v;
+        mmq_gamma_par q = par;
+        if (r > 0) { item = S.q[(r - 1) & 1][tid]; q.d = S.d[item]; q.c = S.c[item]; }
+        if (r > 0 || valid) {
+          mmq_rng g;
+          mmq_rng_init(&g, seed, MMQ_STREAM_GAMMA, (uint64_t)S.id[item], sweep);
+          st = mmq_gamma_try(&g, r, q, &v, &x2, &u);
+        }
+        if (st == 1) S.v[item] = v;
       }
-      const int pos = queue_slot(&S.n[r & 1], !ok, lane);
+      const int pos = queue_slot(&S.n[r & 1], st == 0, lane);
+      if (pos >= 0) S.q[r & 1][pos] = item;
+      const int pl = queue_slot(&S.n[3], st == 2, lane);
+      if (pl >= 0) { S.ql[pl] = item; S.lu[pl] = u; S.lx2[pl] = x2; S.lv[pl] = v; }
+    }
+    __syncthreads();
+    const int nl = S.n[3];
+    if ((tid & ~31) < nl) {
+      bool rej = false;
+      int item = 0;
+      if (tid < nl) {
+        item = S.ql[tid];
+        const double v = S.lv[tid];
+        if (mmq_gamma_logtest(S.lu[tid], S.lx2[tid], v, S.d[item])) S.v[item] = v;
+        else rej = true;
+      }
+      const int pos = queue_slot(&S.n[r & 1], rej, lane);
       if (pos >= 0) S.q[r & 1][pos] = item;
     }
     __syncthreads();
   }
+  const int pb = queue_slot(&S.n[2], boosted, lane);
+  if (pb >= 0) S.qb[pb] = tid;
+  __syncthreads();
   const int nb = S.n[2];
   if (tid < nb) {
     const int item = S.qb[tid];
@@ -634,7 +646,7 @@ __device__ __forceinline__ double gamma_block(gamma_smem& S, int64_t t, int32_t 
 /* K4 (+K5 capture): mu[t] ~ Gamma(alpha + counts[t], rate beta + l[t]); counts
  * are cleared for the next sweep; trace_col (= trace + slot, or null) receives
  * mu at stride trace_len.  src/mmseq.cpp:904-917. */
-__global__ void __launch_bounds__(MMQ_GAMMA_THREADS)
+__global__ void __launch_bounds__(MMQ_GAMMA_THREADS, 5)
 k_gamma(int32_t* __restrict__ counts, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
         double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
         double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy,
@@ -1470,7 +1482,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
   }
   if ((rc = mmq_allreduce(h, h->counts, (size_t)h->n, 0))) return rc;
   mark(h->ev_gamma);
-  k_gamma<<<mmq_grid_for(h->n, MMQ_GAMMA_THREADS, h->num_sms * 6), MMQ_GAMMA_THREADS, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride, h->trace_len, h->n,
+  k_gamma<<<mmq_grid_for(h->n, MMQ_GAMMA_THREADS, h->num_sms * 5), MMQ_GAMMA_THREADS, 0, h->stream>>>(h->counts, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride, h->trace_len, h->n,
                                                                           h->alpha, h->beta, seed, sweep, counts_copy, sweep_base);
   MMQ_LAUNCHED(h);
   mark(h->ev_gamma);

@@ -108,7 +108,7 @@ struct mmq_handle {
   unsigned long long* cls_cdesc = nullptr; /* [chunks] offset of the chunk in cls_pcol << 8 | class size */
   int64_t *cls_o_rp = nullptr, *cls_o_cid = nullptr, *cls_o_tiles = nullptr;
   int32_t *cls_o_col = nullptr, *cls_o_k = nullptr;
-  /* the chain set (more than MMQ_CAT_K fragments): k_alloc_chain, one class per lane */
+  /* the chain set (more than mmq_cat_limit(d) fragments): k_alloc_chain, one class per lane */
   int32_t* cls_c_pcol = nullptr;
   int32_t* cls_c_k = nullptr;
   uint32_t* cls_c_cid = nullptr;
