@@ -76,30 +76,16 @@ __device__ __forceinline__ void cls_chunk(const int32_t* __restrict__ pc, int kq
 #pragma unroll
   for (int j = 1; j < D; ++j) S[j] = S[j - 1] + S[j];
   const double norm = S[D - 1];
-  if (__all_sync(0xffffffffu, kq <= 1 && b0 == 0u)) { /* a warp of single-fragment classes: one draw, one increment */
-    const double target = mmq_uniform32(cls_word1(cid, cid_hi, sweep, seed)) * norm;
-    int chosen = D - 1;
-#pragma unroll
-    for (int j = 0; j < D - 1; ++j) chosen -= (target < S[j]) ? 1 : 0; /* S is non-decreasing: first j with target < S_j */
-    cat_red(counts, kq == 1 ? __ldg(pc + 32 * chosen) : -1, lane);
-    return;
-  }
   int A[D - 1];
 #pragma unroll
   for (int j = 0; j < D - 1; ++j) A[j] = 0;
   const int nb = (kq + 3) >> 2;
   const int nbmax = __reduce_max_sync(0xffffffffu, nb);
-  const bool is1 = kq == 1 && b0 == 0u; /* the class has exactly one fragment: CAT stream */
 #pragma unroll 1
   for (int b = 0; b < nbmax; ++b) {
     if (b < nb) {
       uint32_t wd[4];
-      if (is1) {
-        wd[0] = cls_word1(cid, cid_hi, sweep, seed);
-        wd[1] = wd[2] = wd[3] = 0u;
-      } else {
-        cls_block(wd, cid, cid_hi, sweep, b0 + (uint32_t)b, seed);
-      }
+      cls_block(wd, cid, cid_hi, sweep, b0 + (uint32_t)b, seed);
       const int nd = kq - 4 * b; /* draws of this block: min(4, nd) */
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -134,15 +120,9 @@ __device__ __noinline__ void cls_chunk_any(const int32_t* __restrict__ pc, int D
     for (; j < D; ++j) norm += mu[pc[32 * j]];
   }
   const int nb = (kq + 3) >> 2;
-  const bool is1 = kq == 1 && b0 == 0u;
   for (int b = 0; b < nb; ++b) {
     uint32_t wd[4];
-    if (is1) {
-      wd[0] = cls_word1(cid, cid_hi, sweep, seed);
-      wd[1] = wd[2] = wd[3] = 0u;
-    } else {
-      cls_block(wd, cid, cid_hi, sweep, b0 + (uint32_t)b, seed);
-    }
+    cls_block(wd, cid, cid_hi, sweep, b0 + (uint32_t)b, seed);
     const int nd = min(4, kq - 4 * b);
     double t[4];
 #pragma unroll
@@ -173,23 +153,16 @@ __device__ __noinline__ void cls_chunk_any(const int32_t* __restrict__ pc, int D
 
 /* LO: the instance for class sizes 2..MMQ_CLS_DLO (chunks [0, total_chunks) are all such runs);
  * otherwise sizes above MMQ_CLS_DLO. */
-/* DESC: where a chunk lies and its class size come from one 8-byte descriptor per chunk (fetched a chunk ahead
- * like the slot metadata) instead of the run table: no shared memory, no run lookup, no 64-bit multiply. */
-template <bool LO, int MINB, bool DESC>
+/* Where a chunk lies and its class size come from one 8-byte descriptor per chunk (fetched a chunk ahead like the slot
+ * metadata): no shared memory, no run lookup, no 64-bit multiply. */
+template <bool LO, int MINB>
 __global__ void __launch_bounds__(MMQ_CLS_WARPS * 32, MINB)
-k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol,
-            const uint16_t* __restrict__ pk, const uint32_t* __restrict__ pcid, const unsigned long long* __restrict__ cdesc,
-            uint32_t cid_hi, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep,
-            const uint32_t* __restrict__ sweep_base) {
+k_alloc_cls(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, const uint16_t* __restrict__ pk, const uint32_t* __restrict__ pcid,
+            const unsigned long long* __restrict__ cdesc, uint32_t cid_hi, const double* __restrict__ mu, int32_t* __restrict__ counts,
+            uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
   if (sweep_base) sweep += *sweep_base; /* CUDA-graph replays: the sweep counter lives on the device */
-  __shared__ mmq_cls_run s_run[DESC ? 1 : MMQ_CLS_DMAX];
-  if (!DESC) {
-    for (int i = threadIdx.x; i < nruns; i += blockDim.x) s_run[i] = runs[i];
-    __syncthreads();
-  }
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * MMQ_CLS_WARPS;
-  int ri = LO ? 0 : nruns - 1;
   const int count = chunk_end - chunk_begin;
   /* the long classes (the generic path above all) first in the 9..16 instance: they must not be the tail of the launch */
   auto chunk_of = [&](int i) { return LO ? chunk_begin + i : chunk_end - 1 - i; };
@@ -200,27 +173,17 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
   if (i < count) {
     meta_n = pk[(int64_t)chunk_of(i) * 32 + lane];
     cid_n = pcid[(int64_t)chunk_of(i) * 32 + lane];
-    if (DESC) desc_n = cdesc[chunk_of(i)];
+    desc_n = cdesc[chunk_of(i)];
   }
   for (; i < count; i += nwarps) {
-    const int chunk = chunk_of(i);
-    int D;
-    const int32_t* pc;
-    if (DESC) {
-      D = (int)(desc_n & 0xffull);
-      pc = pcol + (desc_n >> 8) + lane;
-    } else {
-      while (ri + 1 < nruns && chunk >= s_run[ri + 1].chunk0) ++ri; /* warp-uniform */
-      while (ri > 0 && chunk < s_run[ri].chunk0) --ri;
-      D = s_run[ri].d;
-      pc = pcol + s_run[ri].e0 + (int64_t)(chunk - s_run[ri].chunk0) * (32 * D) + lane;
-    }
+    const int D = (int)(desc_n & 0xffull);
+    const int32_t* pc = pcol + (desc_n >> 8) + lane;
     const uint32_t meta = meta_n; /* draws of the slot | slot number within its class << 8 */
     const uint32_t cid = cid_n;
     if (i + nwarps < count) {
       meta_n = pk[(int64_t)chunk_of(i + nwarps) * 32 + lane];
       cid_n = pcid[(int64_t)chunk_of(i + nwarps) * 32 + lane];
-      if (DESC) desc_n = cdesc[chunk_of(i + nwarps)];
+      desc_n = cdesc[chunk_of(i + nwarps)];
     }
     const int kq = (int)(meta & 0xffu);
     const uint32_t b0 = (meta >> 8) * (MMQ_CAT_GROUP / 4);
@@ -241,6 +204,79 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
   }
 }
 
+/* ---- single-fragment classes (k == 1): 64 % of the classes and 70 % of the entries of the config-2 sample ----
+ * Their chunks form the tail of the plan ([chunks_gen, chunks)) and have a kernel of their own: one categorical draw
+ * per class needs the running sums only (no per-member counters, no block loop), so every class size up to 16 fits
+ * 56 registers — twice the resident warps of the general 9..16 instance, which is what hides the column load -> mu
+ * gather -> sum chain of two memory latencies. */
+template <int D>
+__device__ __forceinline__ void cls1_chunk(const int32_t* __restrict__ pc, bool live, uint32_t cid, uint32_t cid_hi, const double* __restrict__ mu,
+                                           int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, int lane) {
+  double S[D];
+#pragma unroll
+  for (int j = 0; j < D; ++j) S[j] = mu[__ldg(pc + 32 * j)];
+  const uint32_t word = cls_word1(cid, cid_hi, sweep, seed); /* independent of the loads in flight */
+#pragma unroll
+  for (int j = 1; j < D; ++j) S[j] = S[j - 1] + S[j];
+  const double target = mmq_uniform32(word) * S[D - 1];
+  int chosen = D - 1;
+#pragma unroll
+  for (int j = 0; j < D - 1; ++j) chosen -= (target < S[j]) ? 1 : 0; /* S is non-decreasing: first j with target < S_j */
+  cat_red(counts, live ? __ldg(pc + 32 * chosen) : -1, lane);
+}
+/* any class size: the members are read twice (the second time from L1) */
+__device__ __noinline__ void cls1_chunk_any(const int32_t* __restrict__ pc, int D, bool live, uint32_t cid, uint32_t cid_hi,
+                                            const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, int lane) {
+  double norm = 0.0;
+  for (int j = 0; j < D; ++j) norm += mu[pc[32 * j]];
+  const double target = mmq_uniform32(cls_word1(cid, cid_hi, sweep, seed)) * norm;
+  double s = 0.0;
+  int chosen = D - 1;
+  for (int j = 0; j < D - 1; ++j) {
+    s += mu[pc[32 * j]];
+    if (target < s) { chosen = j; break; }
+  }
+  cat_red(counts, live ? pc[32 * chosen] : -1, lane);
+}
+__global__ void __launch_bounds__(MMQ_CLS_WARPS * 32, 9)
+k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, const uint16_t* __restrict__ pk, const uint32_t* __restrict__ pcid,
+             const unsigned long long* __restrict__ cdesc, uint32_t cid_hi, const double* __restrict__ mu, int32_t* __restrict__ counts,
+             uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
+  if (sweep_base) sweep += *sweep_base;
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * MMQ_CLS_WARPS;
+  const int count = chunk_end - chunk_begin;
+  /* the largest classes first (the plan orders the chunks by ascending size) */
+  auto chunk_of = [&](int i) { return chunk_end - 1 - i; };
+  int i = blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5);
+  uint32_t meta_n = 0, cid_n = 0;
+  unsigned long long desc_n = 0ull;
+  if (i < count) {
+    meta_n = pk[(int64_t)chunk_of(i) * 32 + lane];
+    cid_n = pcid[(int64_t)chunk_of(i) * 32 + lane];
+    desc_n = cdesc[chunk_of(i)];
+  }
+  for (; i < count; i += nwarps) {
+    const int D = (int)(desc_n & 0xffull);
+    const int32_t* pc = pcol + (desc_n >> 8) + lane;
+    const bool live = (meta_n & 0xffu) != 0u; /* padding lanes make no draw */
+    const uint32_t cid = cid_n;
+    if (i + nwarps < count) { /* metadata one chunk ahead: its latency is off the critical path */
+      meta_n = pk[(int64_t)chunk_of(i + nwarps) * 32 + lane];
+      cid_n = pcid[(int64_t)chunk_of(i + nwarps) * 32 + lane];
+      desc_n = cdesc[chunk_of(i + nwarps)];
+    }
+#define MMQ_CLS1_CASE(DD) case DD: cls1_chunk<DD>(pc, live, cid, cid_hi, mu, counts, seed, sweep, lane); break;
+    switch (D) {
+      MMQ_CLS1_CASE(2) MMQ_CLS1_CASE(3) MMQ_CLS1_CASE(4) MMQ_CLS1_CASE(5) MMQ_CLS1_CASE(6) MMQ_CLS1_CASE(7) MMQ_CLS1_CASE(8)
+      MMQ_CLS1_CASE(9) MMQ_CLS1_CASE(10) MMQ_CLS1_CASE(11) MMQ_CLS1_CASE(12) MMQ_CLS1_CASE(13) MMQ_CLS1_CASE(14) MMQ_CLS1_CASE(15)
+      MMQ_CLS1_CASE(16)
+      default: cls1_chunk_any(pc, D, live, cid, cid_hi, mu, counts, seed, sweep, lane); break;
+    }
+#undef MMQ_CLS1_CASE
+  }
+}
+
 /* The chain set: classes with more than mmq_cat_limit(d) fragments — gsl_ran_multinomial's chain of conditional binomials
  * (src/mmseq.cpp:880), O(d) per class whatever k is.  One class per lane, 32 classes of equal size per chunk (member-major
  * like the small set, so every column load of a warp is one 128-byte line), longest classes first, 4 chunks per block.
@@ -253,14 +289,18 @@ k_alloc_cls(const mmq_cls_run* __restrict__ runs, int nruns, int chunk_begin, in
  * sample.  An attempt being a pure function of (class, sweep, member, attempt number) (include/mmq_sampler.h), the
  * block instead QUEUES the binomials of a step in shared memory by regime and runs each queue densely: BTRS attempts
  * in rounds (the rejected ones re-queued), then the inversions.  Same integers as the CPU replay's mmq_alloc_chain. */
-#define MMQ_CHAIN_THREADS 128
+#define MMQ_CHAIN_THREADS 256 /* threads per block */
+#define MMQ_CHAIN_CLASSES 128 /* classes per block pass: the lanes of warps 0..3 (the other warps only work in the dense phases) */
+#define MMQ_CHAIN_SPEC 2      /* attempts of an open BTRS draw evaluated side by side per round (the lowest accepted one counts) */
 struct chain_req { double p; int n; int owner; }; /* owner: thread | flip << 16 (x = n - x' for p > 1/2) */
 struct chain_smem {
-  chain_req qt[2][MMQ_CHAIN_THREADS]; /* BTRS, ping-pong over attempts */
-  chain_req qi[MMQ_CHAIN_THREADS];    /* inversions and the trivial cases */
-  uint32_t cid[MMQ_CHAIN_THREADS];
-  int result[MMQ_CHAIN_THREADS];
-  int n[3];
+  chain_req qt[MMQ_CHAIN_CLASSES];      /* BTRS draws of this step */
+  chain_req qi[MMQ_CHAIN_CLASSES];      /* inversions and the trivial cases */
+  int open[2][MMQ_CHAIN_CLASSES];       /* BTRS draws not yet accepted (indices into qt), ping-pong over rounds */
+  int att[MMQ_CHAIN_CLASSES][MMQ_CHAIN_SPEC]; /* this round's attempts: x, or -1 rejected */
+  uint32_t cid[MMQ_CHAIN_CLASSES];
+  int result[MMQ_CHAIN_CLASSES];
+  int n[4]; /* BTRS draws, inversions, open[0], open[1] */
   int dmax;
 };
 __global__ void __launch_bounds__(MMQ_CHAIN_THREADS)
@@ -270,14 +310,15 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
   __shared__ chain_smem S;
   if (sweep_base) sweep += *sweep_base;
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-  constexpr int WARPS = MMQ_CHAIN_THREADS / 32;
-  for (int chunk0 = blockIdx.x * WARPS; chunk0 < chunks; chunk0 += gridDim.x * WARPS) {
+  constexpr int CW = MMQ_CHAIN_CLASSES / 32;
+  const bool owner_warp = wib < CW;
+  for (int chunk0 = blockIdx.x * CW; chunk0 < chunks; chunk0 += gridDim.x * CW) {
     const int chunk = chunk0 + wib;
     int D = 0;
     const int32_t* pc = pcol;
     int64_t rem = 0;
     uint32_t cid = 0;
-    if (chunk < chunks) {
+    if (owner_warp && chunk < chunks) {
       const unsigned long long desc = cdesc[chunk];
       D = (int)(desc & 0xffull);
       pc = pcol + (desc >> 8) + lane;
@@ -298,7 +339,7 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
     }
     __syncthreads(); /* the previous pass is done with S */
     if (tid == 0) S.dmax = 0;
-    S.cid[tid] = cid;
+    if (owner_warp) S.cid[tid] = cid;
     __syncthreads();
     {
       const int dm = __reduce_max_sync(0xffffffffu, D);
@@ -312,7 +353,7 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
       bool pending = false, btrs = false;
       double pj = 0.0, pr = 0.0;
       int32_t cj = -1;
-      if (tid < 3) S.n[tid] = 0;
+      if (tid < 4) S.n[tid] = 0;
       if (j < D) {
         cj = __ldg(pc + 32 * j);
         pj = mu[cj];
@@ -327,43 +368,51 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
         }
       }
       __syncthreads();
-      {
+      if (owner_warp) {
         const int pt = queue_slot(&S.n[0], pending && btrs, lane);
-        if (pt >= 0) { S.qt[0][pt].p = pr > 0.5 ? 1.0 - pr : pr; S.qt[0][pt].n = (int)rem; S.qt[0][pt].owner = tid | (pr > 0.5 ? 1 << 16 : 0); }
-        const int pi = queue_slot(&S.n[2], pending && !btrs, lane);
+        if (pt >= 0) { S.qt[pt].p = pr > 0.5 ? 1.0 - pr : pr; S.qt[pt].n = (int)rem; S.qt[pt].owner = tid | (pr > 0.5 ? 1 << 16 : 0); S.open[0][pt] = pt; }
+        const int pi = queue_slot(&S.n[1], pending && !btrs, lane);
         if (pi >= 0) { S.qi[pi].p = pr; S.qi[pi].n = (int)rem; S.qi[pi].owner = tid; }
       }
       __syncthreads();
-      /* ---- BTRS: attempt r of every queued binomial, densely; the rejected ones go round again */
-      for (uint32_t r = 0;; ++r) {
-        const int ncur = S.n[r & 1];
-        if (ncur == 0) break;
+      /* ---- round r: attempts SPEC r .. SPEC r + SPEC - 1 of every open BTRS draw, one per thread; in round 0 the
+       * remaining threads do the inversions (mean below 10), single fragments and p == 1 */
+      const int nt = S.n[0], ni = S.n[1];
+      int nopen = nt;
+      for (uint32_t r = 0; nopen > 0 || (r == 0 && ni > 0); ++r) {
+        const int work = nopen * MMQ_CHAIN_SPEC;
+        if (tid < work) {
+          const int req = S.open[r & 1][tid / MMQ_CHAIN_SPEC];
+          const chain_req q = S.qt[req];
+          mmq_rng g;
+          mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner & 0xffff], sweep);
+          int64_t xb = 0;
+          const bool ok = mmq_btrs_attempt(&g, MMQ_CHAIN_BLOCK(j) + r * MMQ_CHAIN_SPEC + (uint32_t)(tid % MMQ_CHAIN_SPEC), mmq_btrs_setup(q.n, q.p), &xb) != 0;
+          S.att[req][tid % MMQ_CHAIN_SPEC] = ok ? (int)xb : -1;
+        } else if (r == 0 && tid < work + ni) {
+          const chain_req q = S.qi[tid - work];
+          mmq_rng g;
+          mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner], sweep);
+          S.result[q.owner] = (int)mmq_binomial(&g, MMQ_CHAIN_BLOCK(j), q.n, q.p);
+        }
+        if (tid == 0) S.n[2 + ((r + 1) & 1)] = 0;
         __syncthreads();
-        if (tid == 0) S.n[(r + 1) & 1] = 0;
-        __syncthreads();
-        if ((tid & ~31) < ncur) {
-          bool ok = true;
-          chain_req q = {0.0, 0, 0};
-          if (tid < ncur) {
-            q = S.qt[r & 1][tid];
-            const int owner = q.owner & 0xffff;
-            mmq_rng g;
-            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[owner], sweep);
-            int64_t xb = 0;
-            ok = mmq_btrs_attempt(&g, MMQ_CHAIN_BLOCK(j) + r, mmq_btrs_setup(q.n, q.p), &xb) != 0;
-            if (ok) S.result[owner] = (q.owner >> 16) ? q.n - (int)xb : (int)xb;
+        if ((tid & ~31) < nopen) {
+          bool again = false;
+          int req = 0;
+          if (tid < nopen) {
+            req = S.open[r & 1][tid];
+            int xa = -1;
+#pragma unroll
+            for (int sp = MMQ_CHAIN_SPEC - 1; sp >= 0; --sp) if (S.att[req][sp] >= 0) xa = S.att[req][sp]; /* the lowest accepted attempt */
+            if (xa >= 0) { const chain_req q = S.qt[req]; S.result[q.owner & 0xffff] = (q.owner >> 16) ? q.n - xa : xa; }
+            else again = true;
           }
-          const int pos = queue_slot(&S.n[(r + 1) & 1], !ok, lane);
-          if (pos >= 0) S.qt[(r + 1) & 1][pos] = q;
+          const int pos = queue_slot(&S.n[2 + ((r + 1) & 1)], again, lane);
+          if (pos >= 0) S.open[(r + 1) & 1][pos] = req;
         }
         __syncthreads();
-      }
-      /* ---- inversions (mean below 10), single fragments left, p == 1 */
-      if (tid < S.n[2]) {
-        const chain_req q = S.qi[tid];
-        mmq_rng g;
-        mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner], sweep);
-        S.result[q.owner] = (int)mmq_binomial(&g, MMQ_CHAIN_BLOCK(j), q.n, q.p);
+        nopen = S.n[2 + ((r + 1) & 1)];
       }
       __syncthreads();
       if (pending) x = S.result[tid];
@@ -450,6 +499,8 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
     MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
     MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming));
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join5, cudaEventDisableTiming));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
@@ -458,6 +509,7 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   h->cls_nruns = (int)runs.size();
   h->cls_chunks = chunks;
   h->cls_chunks_lo = chunks_lo;
+  h->cls_chunks_gen = P.chunks_gen;
   h->cls_cid_hi = cid_hi;
   h->cls_small = small_classes;
   h->cls_rest = n_rest;
@@ -487,22 +539,19 @@ extern "C" int mmq_cls_stats(const mmq_handle* h, int64_t out[8]) {
 int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base) {
   int rc = mmq_seg_add_base(h, true);
   if (rc) return rc;
-  static const int skip = [] { const char* e = getenv("MMQ_DEBUG_CLS_SKIP"); return e ? atoi(e) : 0; }(); /* timing experiments only: 1 no LO, 2 no rest, 4 no HI */
-  /* geometry (tuning knob): CTAs per SM of the two instances; 0 = the measured best */
-  static const int geo_lo = [] { const char* e = getenv("MMQ_CLS_GEO_LO"); return e ? atoi(e) : 0; }();
-  static const int geo_hi = [] { const char* e = getenv("MMQ_CLS_GEO_HI"); return e ? atoi(e) : 0; }();
-  const char* desc_env = getenv("MMQ_CLS_DESC"); /* chunk descriptors instead of the run table; read per launch (A/B runs) */
-  const bool use_desc = desc_env ? atoi(desc_env) != 0 : true; /* measured: 0.101 against 0.106 ms per sweep on the C2 sample */
-  const bool do_chain = h->cls_c_chunks > 0 && !(skip & 8);
-  const bool do_rest = h->cls_rest > 0 && !(skip & 2);
-  const bool do_hi = h->cls_chunks > h->cls_chunks_lo && !(skip & 4);
-  const bool do_lo = h->cls_chunks_lo > 0 && !(skip & 1);
-  /* three independent pieces, concurrently: the long chains first (their latency is the longest) */
-  if (do_rest || do_chain || (do_hi && do_lo)) MMQ_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
-  if (do_chain) {
+  const bool do_one = h->cls_chunks > h->cls_chunks_gen;
+  const bool do_chain = h->cls_c_chunks > 0;
+  const bool do_rest = h->cls_rest > 0;
+  const bool do_hi = h->cls_chunks_gen > h->cls_chunks_lo;
+  const bool do_lo = h->cls_chunks_lo > 0;
+  /* up to five independent pieces, concurrently on the handle's side streams; the main stream takes the last
+   * one and waits for the others */
+  MMQ_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+#define MMQ_CLS_ARGS(c0, c1) (int)(c0), (int)(c1), h->cls_pcol, h->cls_pk, h->cls_pcid, h->cls_cdesc, h->cls_cid_hi, h->mu, h->counts, seed, sweep, sweep_base
+  if (do_chain) { /* the longest dependent chains: first in */
     MMQ_CUDA(h, cudaStreamWaitEvent(h->stream4, h->ev_fork, 0));
-    constexpr int CW = MMQ_CHAIN_THREADS / 32;
-    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, (int64_t)h->num_sms * 4);
+    constexpr int CW = MMQ_CHAIN_CLASSES / 32;
+    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, (int64_t)h->num_sms * 3);
     k_alloc_chain<<<grid, MMQ_CHAIN_THREADS, 0, h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
                                                               h->mu, h->counts, seed, sweep, sweep_base);
     MMQ_LAUNCHED(h);
@@ -516,31 +565,31 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
     MMQ_LAUNCHED(h);
     MMQ_CUDA(h, cudaEventRecord(h->ev_join, h->stream2));
   }
-#define MMQ_CLS_ARGS(c0, c1) (const mmq_cls_run*)h->cls_runs, h->cls_nruns, (int)(c0), (int)(c1), h->cls_pcol, h->cls_pk, h->cls_pcid, h->cls_cdesc, h->cls_cid_hi, h->mu, h->counts, seed, sweep, sweep_base
-  if (do_hi) {
-    cudaStream_t st = do_lo ? h->stream3 : h->stream;
-    if (do_lo) MMQ_CUDA(h, cudaStreamWaitEvent(st, h->ev_fork, 0));
-#define MMQ_CLS_GO(LO, MINB, c0, c1, st)                                                                                  \
-  do {                                                                                                                    \
-    const int grid = (int)std::min<int64_t>(((c1) - (c0) + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, (int64_t)h->num_sms * MINB); \
-    if (use_desc) k_alloc_cls<LO, MINB, true><<<grid, MMQ_CLS_WARPS * 32, 0, st>>>(MMQ_CLS_ARGS(c0, c1));                 \
-    else k_alloc_cls<LO, MINB, false><<<grid, MMQ_CLS_WARPS * 32, 0, st>>>(MMQ_CLS_ARGS(c0, c1));                         \
-  } while (0)
-    if (geo_hi == 4) MMQ_CLS_GO(false, 4, h->cls_chunks_lo, h->cls_chunks, st);
-    else if (geo_hi == 6) MMQ_CLS_GO(false, 6, h->cls_chunks_lo, h->cls_chunks, st);
-    else MMQ_CLS_GO(false, 5, h->cls_chunks_lo, h->cls_chunks, st); /* 96 registers, no spills */
+  if (do_hi) { /* 96 registers, no spills */
+    MMQ_CUDA(h, cudaStreamWaitEvent(h->stream3, h->ev_fork, 0));
+    const int64_t c0 = h->cls_chunks_lo, c1 = h->cls_chunks_gen;
+    const int grid = (int)std::min<int64_t>((c1 - c0 + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, (int64_t)h->num_sms * 5);
+    k_alloc_cls<false, 5><<<grid, MMQ_CLS_WARPS * 32, 0, h->stream3>>>(MMQ_CLS_ARGS(c0, c1));
     MMQ_LAUNCHED(h);
-    if (do_lo) MMQ_CUDA(h, cudaEventRecord(h->ev_join3, h->stream3));
+    MMQ_CUDA(h, cudaEventRecord(h->ev_join3, h->stream3));
   }
-  if (do_lo) {
-    if (geo_lo == 10) MMQ_CLS_GO(true, 10, 0, h->cls_chunks_lo, h->stream);
-    else if (geo_lo == 12) MMQ_CLS_GO(true, 12, 0, h->cls_chunks_lo, h->stream);
-    else MMQ_CLS_GO(true, 8, 0, h->cls_chunks_lo, h->stream); /* 64 registers, no spills, 32 warps per SM */
+  if (do_lo) { /* 64 registers, no spills, 32 warps per SM */
+    MMQ_CUDA(h, cudaStreamWaitEvent(h->stream5, h->ev_fork, 0));
+    const int64_t c0 = 0, c1 = h->cls_chunks_lo;
+    const int grid = (int)std::min<int64_t>((c1 - c0 + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, (int64_t)h->num_sms * 8);
+    k_alloc_cls<true, 8><<<grid, MMQ_CLS_WARPS * 32, 0, h->stream5>>>(MMQ_CLS_ARGS(c0, c1));
+    MMQ_LAUNCHED(h);
+    MMQ_CUDA(h, cudaEventRecord(h->ev_join5, h->stream5));
+  }
+  if (do_one) { /* the bulk of the entries, on the main stream */
+    const int64_t c0 = h->cls_chunks_gen, c1 = h->cls_chunks;
+    const int grid = (int)std::min<int64_t>((c1 - c0 + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, (int64_t)h->num_sms * 9);
+    k_alloc_cls1<<<grid, MMQ_CLS_WARPS * 32, 0, h->stream>>>(MMQ_CLS_ARGS(c0, c1));
     MMQ_LAUNCHED(h);
   }
-#undef MMQ_CLS_GO
 #undef MMQ_CLS_ARGS
-  if (do_hi && do_lo) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join3, 0));
+  if (do_lo) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join5, 0));
+  if (do_hi) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join3, 0));
   if (do_rest) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
   if (do_chain) MMQ_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join4, 0));
   return MMQ_OK;

@@ -22,7 +22,12 @@
 #define MMQ_CLS_DLO 8    /* class sizes 2..8: the 64-register instance (32 warps per SM) */
 #define MMQ_CLS_DREG 16  /* class sizes up to this are register-resident template instances */
 #define MMQ_CLS_WARPS 4
-#define MMQ_CLS_NQ 17    /* sort positions inside a run of equal d: 16 - blocks (k >= 2), then 16: k == 1 */
+#define MMQ_CLS_NQ 17    /* sort positions inside a run of equal d: 16 - blocks (k >= 2); 16: k == 1 (those form runs of their own) */
+/* runs are numbered by a "pseudo size": d for the classes with k >= 2, MMQ_CLS_DMAX + 1 + d for the single-fragment
+ * classes — their chunks come after all the others and are swept by their own kernel (k_alloc_cls1) */
+#define MMQ_CLS_DP1(d) (MMQ_CLS_DMAX + 1 + (d))
+#define MMQ_CLS_DP_END (2 * MMQ_CLS_DMAX + 2)
+#define MMQ_CLS_D_OF(dp) ((dp) > MMQ_CLS_DMAX ? (dp) - (MMQ_CLS_DMAX + 1) : (dp))
 
 struct mmq_cls_run {
   int64_t e0;     /* offset in pcol of the run's first chunk */
@@ -37,7 +42,8 @@ struct mmq_cls_host_plan {
   std::vector<uint16_t> pk;        /* [chunks * 32] draws of the slot | slot number within its class << 8 */
   std::vector<uint32_t> pcid;      /* [chunks * 32] low word of the class id */
   std::vector<unsigned long long> cdesc; /* [chunks] offset of the chunk in pcol << 8 | class size */
-  int64_t chunks = 0, chunks_lo = 0, packed = 0, small_classes = 0, n_rest = 0, nnz_rest = 0;
+  int64_t chunks = 0, chunks_lo = 0, chunks_gen = 0, packed = 0, small_classes = 0, n_rest = 0, nnz_rest = 0;
+  /* chunks [0, chunks_lo): k >= 2, d <= MMQ_CLS_DLO; [chunks_lo, chunks_gen): k >= 2, larger d; [chunks_gen, chunks): k == 1 */
   uint32_t cid_hi = 0;
   /* the chain set: classes with more than mmq_cat_limit(d) fragments and at most MMQ_CLS_DMAX members (conditional-binomial
    * chains, one class per lane of k_alloc_chain): member-major chunks of 32 like the small set, longest classes first */
@@ -89,7 +95,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
    * k >= 2 (a run of equal d starts with its most expensive slots), q = 16 for single-fragment classes
    * (whole warps of them take the one-draw path).  key16[i]: the key of the class's last (partial) slot,
    * or of its full slots when k is a multiple of 64; -1 singleton / empty, -2 rest. */
-  const int NKEY = (MMQ_CLS_DMAX + 1) * MMQ_CLS_NQ;
+  const int NKEY = MMQ_CLS_DP_END * MMQ_CLS_NQ;
   std::vector<int16_t> key16(m);
   struct Tally { std::vector<int64_t> key_count; int64_t n_single = 0, n_rest = 0, nnz_rest = 0, small = 0, n_chain = 0; bool ok = true; };
   /* thread t owns classes [m t / T, m (t+1) / T) in this pass and in the placement pass below; it also counts
@@ -116,7 +122,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
       else if (d <= MMQ_CLS_DMAX && kv <= mmq_cat_limit((int)d)) {
         ++t.small;
         ++hc[col[rp[i]]];
-        if (kv == 1) { key16[i] = (int16_t)(d * MMQ_CLS_NQ + 16); ++t.key_count[key16[i]]; }
+        if (kv == 1) { key16[i] = (int16_t)(MMQ_CLS_DP1(d) * MMQ_CLS_NQ + 16); ++t.key_count[key16[i]]; }
         else {
           const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
           t.key_count[d * MMQ_CLS_NQ + 0] += full; /* 16 blocks */
@@ -141,20 +147,25 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
   std::vector<mmq_cls_run>& runs = P.runs;
   std::vector<int64_t> key_slot(NKEY + 1, 0); /* first slot (global numbering, 32 per chunk) of each key */
   std::vector<int64_t> run_slots; /* slots in use per run: the rest of its last chunk is padding */
-  int64_t chunks = 0, packed = 0, chunks_lo = 0;
-  for (int d = 2; d <= MMQ_CLS_DMAX; ++d) {
+  int64_t chunks = 0, packed = 0, chunks_lo = 0, chunks_gen = 0;
+  std::vector<int32_t> run_of_d(MMQ_CLS_DP_END, -1); /* by pseudo size */
+  for (int dp = 2; dp < MMQ_CLS_DP_END; ++dp) {
+    const int d = MMQ_CLS_D_OF(dp);
     int64_t cnt = 0;
-    for (int q = 0; q < MMQ_CLS_NQ; ++q) { key_slot[d * MMQ_CLS_NQ + q] = chunks * 32 + cnt; cnt += key_count[d * MMQ_CLS_NQ + q]; }
-    if (cnt == 0) continue;
-    mmq_cls_run r;
-    r.e0 = packed; r.chunk0 = (int32_t)chunks; r.d = d;
-    runs.push_back(r);
-    run_slots.push_back(cnt);
-    const int64_t nch = (cnt + 31) / 32;
-    chunks += nch;
-    packed += nch * 32 * d;
-    if (d <= MMQ_CLS_DLO) chunks_lo = chunks;
-    if (chunks > 0x7fff0000ll) return false;
+    for (int q = 0; q < MMQ_CLS_NQ; ++q) { key_slot[dp * MMQ_CLS_NQ + q] = chunks * 32 + cnt; cnt += key_count[dp * MMQ_CLS_NQ + q]; }
+    if (cnt > 0) {
+      mmq_cls_run r;
+      r.e0 = packed; r.chunk0 = (int32_t)chunks; r.d = d;
+      run_of_d[dp] = (int32_t)runs.size();
+      runs.push_back(r);
+      run_slots.push_back(cnt);
+      const int64_t nch = (cnt + 31) / 32;
+      chunks += nch;
+      packed += nch * 32 * d;
+      if (chunks > 0x7fff0000ll) return false;
+    }
+    if (dp <= MMQ_CLS_DLO) chunks_lo = chunks;
+    if (dp <= MMQ_CLS_DMAX) chunks_gen = chunks;
   }
   P.cdesc.assign((size_t)chunks, 0ull);
   for (size_t r = 0; r < runs.size(); ++r) {
@@ -162,8 +173,6 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
     for (int64_t c = runs[r].chunk0; c < c1; ++c)
       P.cdesc[(size_t)c] = ((unsigned long long)(runs[r].e0 + (c - runs[r].chunk0) * 32 * runs[r].d) << 8) | (unsigned long long)runs[r].d;
   }
-  std::vector<int32_t> run_of_d(MMQ_CLS_DMAX + 1, -1);
-  for (size_t r = 0; r < runs.size(); ++r) run_of_d[runs[r].d] = (int32_t)r;
 
   /* Within a key the classes are placed by their first member (a stable counting sort): members are
    * ascending and the isoforms of a gene are neighbours in the header, so the lanes of a warp and the
@@ -205,9 +214,9 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
       int64_t* next = used.data() + (size_t)t * (NKEY + 1);
       for (int64_t o = small_classes * t / T; o < small_classes * (t + 1) / T; ++o) {
         const Ord& e = order[(size_t)o];
-        const int d = e.key / MMQ_CLS_NQ;
-        slot_full[(size_t)o] = next[d * MMQ_CLS_NQ + 0];
-        next[d * MMQ_CLS_NQ + 0] += e.full;
+        const int dp = e.key / MMQ_CLS_NQ;
+        slot_full[(size_t)o] = next[dp * MMQ_CLS_NQ + 0];
+        next[dp * MMQ_CLS_NQ + 0] += e.full;
         slot_tail[(size_t)o] = e.tail ? next[e.key]++ : -1; /* -1: k is a multiple of 64, no partial slot */
       }
     });
@@ -230,8 +239,8 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
     for (int64_t o = a0; o < b0; ++o) {
       const Ord& e = order[(size_t)o];
       const int64_t i = e.i;
-      const int d = e.key / MMQ_CLS_NQ;
-      const mmq_cls_run& r = runs[run_of_d[d]];
+      const mmq_cls_run& r = runs[run_of_d[e.key / MMQ_CLS_NQ]];
+      const int d = r.d;
       const int32_t* src = col + rp[i];
       const uint32_t cid = (uint32_t)cid_of(i);
       auto put = [&](int64_t s, int draws, int slot_no) {
@@ -321,7 +330,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
     if (key16[i] == -1 && kk[i] > 0) { s_col.push_back(col[rp[i]]); s_k.push_back(kk[i]); }
 
   tick("rest, singletons");
-  P.chunks = chunks; P.chunks_lo = chunks_lo; P.packed = packed; P.cid_hi = cid_hi;
+  P.chunks = chunks; P.chunks_lo = chunks_lo; P.chunks_gen = chunks_gen; P.packed = packed; P.cid_hi = cid_hi;
   P.small_classes = small_classes; P.n_rest = n_rest; P.nnz_rest = nnz_rest;
   return true;
 }

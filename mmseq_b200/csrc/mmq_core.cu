@@ -1046,6 +1046,8 @@ void mmq_destroy(mmq_handle* h) {
   if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
   if (h->stream4) { cudaStreamSynchronize(h->stream4); cudaStreamDestroy(h->stream4); }
   if (h->ev_join4) cudaEventDestroy(h->ev_join4);
+  if (h->stream5) { cudaStreamSynchronize(h->stream5); cudaStreamDestroy(h->stream5); }
+  if (h->ev_join5) cudaEventDestroy(h->ev_join5);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_join3) cudaEventDestroy(h->ev_join3);

@@ -100,6 +100,7 @@ struct mmq_handle {
   bool cls_ready = false;
   void* cls_runs = nullptr; /* mmq_cls_run[] on the device */
   int cls_nruns = 0;
+  int64_t cls_chunks_gen = 0; /* chunks [cls_chunks_gen, cls_chunks): single-fragment classes (k_alloc_cls1) */
   int64_t cls_chunks = 0, cls_chunks_lo = 0, cls_small = 0, cls_packed = 0, cls_rest = 0, cls_rest_nnz = 0, cls_rest_tiles = 0;
   uint32_t cls_cid_hi = 0;
   int32_t* cls_pcol = nullptr;
@@ -114,8 +115,8 @@ struct mmq_handle {
   uint32_t* cls_c_cid = nullptr;
   unsigned long long* cls_c_desc = nullptr;
   int64_t cls_c_chunks = 0, cls_c_packed = 0, cls_chain = 0;
-  cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr;
+  cudaStream_t stream2 = nullptr, stream3 = nullptr, stream4 = nullptr, stream5 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join3 = nullptr, ev_join4 = nullptr, ev_join5 = nullptr;
 
   /* fused count exchange over peer memory: one peer-mapped block per rank, laid out as
    * [flags MMQ_P2P_HEAD bytes | counts parity 0 | counts parity 1 | mu] (offsets: p2p_off_* in mmq_core.cu) */
