@@ -140,6 +140,8 @@ int mmq_em(mmq_handle* h, int max_iter, double eps, int* iters_out, double* logl
                                   (same results; for tests and comparison)   */
 #define MMQ_GIBBS_RAGGED_KERNEL 16 /* k == 1 shards: use the row-pointer driven (TMA-staged)
                                   kernel even when the by-length segment plan exists */
+#define MMQ_GIBBS_SEG_KERNEL 32 /* by-length k == 1 shards: the round-1 segment kernel (8 B per hit streamed) instead
+                                  of the row plan (columns once per run of identical rows); same results          */
 int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweeps, int stride,
               int trace_len, int flags);
 
@@ -151,6 +153,12 @@ int mmq_gibbs(mmq_handle* h, uint32_t seed, int64_t first_sweep, int64_t n_sweep
  * mmq_cat_limit(d) fragments: gsl_ran_multinomial's conditional-binomial chain, one class per lane) and out[7]
  * their packed column slots.  Used by bench.py for the algorithmic-bytes figure. */
 int mmq_cls_stats(const mmq_handle* h, int64_t out[8]);
+
+/* What the row plan of a by-length k == 1 shard holds (mmq_rows.cu; BASELINE config 4's weighted stream):
+ * out[0] 1 if in use, out[1] rows with >= 2 members, out[2] runs of identical rows ("sets"), out[3] set
+ * column entries, out[4] weight slots (0 without weights), out[5] chunks of 128 rows, out[6] bytes streamed
+ * per sweep (4 B per weight slot and set column, 32 B per chunk), out[7] single-member rows (not visited). */
+int mmq_rows_stats(const mmq_handle* h, int64_t out[8]);
 
 /* Device time of the launches made under MMQ_GIBBS_TIME_KERNELS since the last
  * call (waits for the stream): total milliseconds and launch count of the

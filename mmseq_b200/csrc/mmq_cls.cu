@@ -291,7 +291,7 @@ k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, c
  * in rounds (the rejected ones re-queued), then the inversions.  Same integers as the CPU replay's mmq_alloc_chain. */
 #define MMQ_CHAIN_THREADS 256 /* threads per block */
 #define MMQ_CHAIN_CLASSES 128 /* classes per block pass: the lanes of warps 0..3 (the other warps only work in the dense phases) */
-#define MMQ_CHAIN_SPEC 2      /* attempts of an open BTRS draw evaluated side by side per round (the lowest accepted one counts) */
+#define MMQ_CHAIN_SPEC 4      /* attempts of an open BTRS draw evaluated side by side per round (the lowest accepted one counts) */
 struct chain_req { double p; int n; int owner; }; /* owner: thread | flip << 16 (x = n - x' for p > 1/2) */
 struct chain_smem {
   chain_req qt[MMQ_CHAIN_CLASSES];      /* BTRS draws of this step */
@@ -381,19 +381,21 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
       int nopen = nt;
       for (uint32_t r = 0; nopen > 0 || (r == 0 && ni > 0); ++r) {
         const int work = nopen * MMQ_CHAIN_SPEC;
-        if (tid < work) {
-          const int req = S.open[r & 1][tid / MMQ_CHAIN_SPEC];
-          const chain_req q = S.qt[req];
-          mmq_rng g;
-          mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner & 0xffff], sweep);
-          int64_t xb = 0;
-          const bool ok = mmq_btrs_attempt(&g, MMQ_CHAIN_BLOCK(j) + r * MMQ_CHAIN_SPEC + (uint32_t)(tid % MMQ_CHAIN_SPEC), mmq_btrs_setup(q.n, q.p), &xb) != 0;
-          S.att[req][tid % MMQ_CHAIN_SPEC] = ok ? (int)xb : -1;
-        } else if (r == 0 && tid < work + ni) {
-          const chain_req q = S.qi[tid - work];
-          mmq_rng g;
-          mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner], sweep);
-          S.result[q.owner] = (int)mmq_binomial(&g, MMQ_CHAIN_BLOCK(j), q.n, q.p);
+        for (int wi = tid; wi < work + (r == 0 ? ni : 0); wi += MMQ_CHAIN_THREADS) {
+          if (wi < work) {
+            const int req = S.open[r & 1][wi / MMQ_CHAIN_SPEC];
+            const chain_req q = S.qt[req];
+            mmq_rng g;
+            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner & 0xffff], sweep);
+            int64_t xb = 0;
+            const bool ok = mmq_btrs_attempt(&g, MMQ_CHAIN_BLOCK(j) + r * MMQ_CHAIN_SPEC + (uint32_t)(wi % MMQ_CHAIN_SPEC), mmq_btrs_setup(q.n, q.p), &xb) != 0;
+            S.att[req][wi % MMQ_CHAIN_SPEC] = ok ? (int)xb : -1;
+          } else {
+            const chain_req q = S.qi[wi - work];
+            mmq_rng g;
+            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner], sweep);
+            S.result[q.owner] = (int)mmq_binomial(&g, MMQ_CHAIN_BLOCK(j), q.n, q.p);
+          }
         }
         if (tid == 0) S.n[2 + ((r + 1) & 1)] = 0;
         __syncthreads();

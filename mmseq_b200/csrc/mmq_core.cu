@@ -1025,6 +1025,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   if (h->has_k) CREATE_TRY(build_tiles(h, p->row_ptr)); /* k == 1 shards build them on first use of the general kernel */
   tick("tiles");
   if (!h->has_k) CREATE_TRY(mmq_seg_plan(h));
+  if (!h->has_k) CREATE_TRY(mmq_rows_plan(h));
   if (h->has_k) CREATE_TRY(mmq_cls_plan(h, p));
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
   tick("segment / class plan");
@@ -1387,6 +1388,8 @@ static int prepare_sweep(mmq_handle* h, int flags) {
     if ((rc = ensure_x(h))) return rc;
     if ((rc = build_transpose(h))) return rc;
   }
+  if (!transposed && h->seg_ready && (!h->rows_ready || (flags & MMQ_GIBBS_SEG_KERNEL)) && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL)) &&
+      (rc = mmq_seg_pack(h))) return rc; /* the segment kernel's packed copies (allocation: not inside a capture) */
   return MMQ_OK;
 }
 
@@ -1418,7 +1421,9 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       MMQ_LAUNCHED(h);
     } else {
       mark(h->ev_alloc);
-      if (h->seg_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
+      if (h->rows_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL | MMQ_GIBBS_SEG_KERNEL))) {
+        if ((rc = mmq_rows_launch(h, seed, sweep, sweep_base))) return rc;
+      } else if (h->seg_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
         if ((rc = mmq_seg_launch(h, seed, sweep, sweep_base))) return rc;
       } else if (h->cls_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
         if ((rc = mmq_cls_launch(h, seed, sweep, sweep_base))) return rc;

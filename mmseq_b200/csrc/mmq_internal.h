@@ -25,6 +25,16 @@
 #define MMQ_P2P_FLAG_MU 64        /* [64 + 8 r]: rank r has stored its slice of mu of epoch e everywhere */
 #define MMQ_P2P_DONE 128          /* blocks of the own Gamma kernel that have finished */
 
+/* one run of equal class size of the segment plan (mmq_seg.cu) */
+struct mmq_seg {
+  int64_t e_virtual;   /* packed-array offset of the (possibly dummy) virtual first row; multiple of 4 */
+  int64_t cid_virtual; /* class id of the virtual first row; a MULTIPLE OF 4, so a lane's classes are one Philox block */
+  int32_t row_lo;      /* 0..3: the virtual rows in front of the run's first class are dummies */
+  int32_t rows;        /* virtual row count (dummies included) */
+  int32_t d;           /* class size of the run */
+  int32_t chunk0;      /* first chunk of this run in the global chunk numbering */
+};
+
 struct mmq_group_set {
   int64_t ngroups = 0;
   int64_t* ptr_dev = nullptr;     /* [ngroups+1] */
@@ -93,7 +103,17 @@ struct mmq_handle {
   float* seg_w = nullptr;
   int32_t* seg_base = nullptr; /* [n] or null */
   bool seg_base_in_counts = true; /* counts[] currently starts from seg_base */
-  int64_t seg_entries = 0, seg_rows = 0, seg_singletons = 0;
+  int64_t seg_entries = 0, seg_rows = 0, seg_singletons = 0, seg_packed = 0;
+  std::vector<mmq_seg> seg_host; /* the table, kept for the lazy packing (mmq_seg_pack) */
+
+  /* row plan for by-length k == 1 shards (mmq_rows.cu): columns once per run of identical rows, weights member-major */
+  bool rows_ready = false;
+  void* rows_runs = nullptr; /* mmq_rows_run[] */
+  void* rows_meta = nullptr; /* mmq_rows_meta[] */
+  int32_t* rows_set_col = nullptr;
+  float* rows_w = nullptr;
+  int rows_nruns = 0;
+  int64_t rows_chunks = 0, rows_rows = 0, rows_sets = 0, rows_set_cols = 0, rows_wslots = 0;
 
   /* class plan for collapsed shards (mmq_cls.cu): the classes with few fragments packed in
    * member-major chunks of 32, the rest as a sub-CSR for the general kernel on stream2 */
@@ -168,6 +188,9 @@ int mmq_ensure_trace_groups(mmq_handle* h);
 int mmq_seg_scan(mmq_handle* h, const int64_t* row_ptr_host);
 int mmq_seg_plan(mmq_handle* h);
 int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base);
+int mmq_seg_pack(mmq_handle* h);
+int mmq_rows_plan(mmq_handle* h);
+int mmq_rows_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base);
 int mmq_seg_add_base(mmq_handle* h, bool want_in_counts);
 int mmq_cls_plan(mmq_handle* h, const mmq_problem* p);
 int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base);

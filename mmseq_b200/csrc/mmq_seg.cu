@@ -27,14 +27,6 @@
 
 #define MMQ_SEG_MAX 96    /* more runs than this: not a by-length layout, use the ragged kernel */
 
-struct mmq_seg {
-  int64_t e_virtual;   /* packed-array offset of the (possibly dummy) virtual first row; multiple of 4 */
-  int64_t cid_virtual; /* class id of the virtual first row; a MULTIPLE OF 4, so a lane's classes are one Philox block */
-  int32_t row_lo;      /* 0..3: the virtual rows in front of the run's first class are dummies */
-  int32_t rows;        /* virtual row count (dummies included) */
-  int32_t d;           /* class size of the run */
-  int32_t chunk0;      /* first chunk of this run in the global chunk numbering */
-};
 
 __global__ void k_fill_i32(int32_t* __restrict__ p, int64_t count, int32_t v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
@@ -473,23 +465,9 @@ int mmq_seg_plan(mmq_handle* h) {
   }
   if (segs.empty() && singles == 0) return MMQ_OK;
   packed = ((packed + 3) & ~(int64_t)3) + MMQ_SEG4_ROWS * 12 + 64; /* slack: the bulk copy of a run's last chunk always moves 128 rows */
+  h->seg_packed = packed;
+  h->seg_host.assign(segs.begin(), segs.end());
   int rc;
-  if ((rc = mmq_dev_alloc(h, (void**)&h->seg_col, sizeof(int32_t) * (size_t)packed))) return rc;
-  k_fill_i32<<<mmq_grid_for(packed, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->seg_col, packed, (int32_t)h->n);
-  MMQ_LAUNCHED(h);
-  if (h->has_w) {
-    if ((rc = mmq_dev_alloc(h, (void**)&h->seg_w, sizeof(float) * (size_t)packed))) return rc;
-    MMQ_CUDA(h, cudaMemsetAsync(h->seg_w, 0, sizeof(float) * (size_t)packed, h->stream));
-  }
-  size_t si = 0;
-  for (const Run& r : runs) {
-    if (r.d == 1) continue;
-    const mmq_seg& sg = segs[si++];
-    const int64_t dst = sg.e_virtual + (int64_t)sg.row_lo * r.d;
-    const size_t cnt = (size_t)(r.r1 - r.r0) * (size_t)r.d;
-    MMQ_CUDA(h, cudaMemcpyAsync(h->seg_col + dst, h->col + r.q0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, h->stream));
-    if (h->has_w) MMQ_CUDA(h, cudaMemcpyAsync(h->seg_w + dst, h->w + r.q0, sizeof(float) * cnt, cudaMemcpyDeviceToDevice, h->stream));
-  }
   if (singles > 0) {
     if ((rc = mmq_dev_alloc(h, (void**)&h->seg_base, sizeof(int32_t) * (size_t)h->n))) return rc;
     MMQ_CUDA(h, cudaMemsetAsync(h->seg_base, 0, sizeof(int32_t) * (size_t)h->n, h->stream));
@@ -515,9 +493,36 @@ int mmq_seg_plan(mmq_handle* h) {
   return MMQ_OK;
 }
 
+/* The packed, aligned copies of col / weight the segment kernel streams: made on first use (the row plan of
+ * mmq_rows.cu is the default for these shards; k_alloc_seg4 stays as MMQ_GIBBS_SEG_KERNEL and for shards the row plan
+ * declines). */
+int mmq_seg_pack(mmq_handle* h) {
+  if (h->seg_col || h->seg_count == 0) return MMQ_OK;
+  const int64_t packed = h->seg_packed;
+  int rc;
+  if ((rc = mmq_dev_alloc(h, (void**)&h->seg_col, sizeof(int32_t) * (size_t)packed))) return rc;
+  k_fill_i32<<<mmq_grid_for(packed, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->seg_col, packed, (int32_t)h->n);
+  MMQ_LAUNCHED(h);
+  if (h->has_w) {
+    if ((rc = mmq_dev_alloc(h, (void**)&h->seg_w, sizeof(float) * (size_t)packed))) return rc;
+    MMQ_CUDA(h, cudaMemsetAsync(h->seg_w, 0, sizeof(float) * (size_t)packed, h->stream));
+  }
+  size_t si = 0;
+  for (const auto& r : h->seg_runs) {
+    if (r.d == 1) continue;
+    const mmq_seg& sg = h->seg_host[si++];
+    const int64_t dst = sg.e_virtual + (int64_t)sg.row_lo * r.d;
+    const size_t cnt = (size_t)(r.r1 - r.r0) * (size_t)r.d;
+    MMQ_CUDA(h, cudaMemcpyAsync(h->seg_col + dst, h->col + r.q0, sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, h->stream));
+    if (h->has_w) MMQ_CUDA(h, cudaMemcpyAsync(h->seg_w + dst, h->w + r.q0, sizeof(float) * cnt, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  return MMQ_OK;
+}
+
 int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t* sweep_base) {
   int rc = mmq_seg_add_base(h, true);
   if (rc) return rc;
+  if ((rc = mmq_seg_pack(h))) return rc;
   if (h->seg_count == 0) return MMQ_OK; /* only singletons: nothing random to do */
   /* timing experiments only */
   static const int dbg_dmin = [] { const char* e = getenv("MMQ_DEBUG_DMIN"); return e ? atoi(e) : 0; }();

@@ -117,9 +117,12 @@ def test_by_length_layout_segment_kernel(small_synth, weighted, cid_base):
     P = orc.Problem(h.row_ptr, h.col, None, h.len, weight=h.w)
     mu, _, _ = P.init_mu()
     with capi.Handle(h.row_ptr, h.col, None, h.len, weight=h.w, class_id_base=cid_base) as H:
+        st = H.rows_stats()   # the row plan (mmq_rows.cu) is the default for this layout: columns once per run of identical rows
+        assert st["in_use"] == 1 and st["rows"] + st["singleton_rows"] == h.m and 0 < st["sets"] < st["rows"]
+        assert (st["weight_slots"] > 0) == weighted and st["bytes_per_sweep"] < (8 if weighted else 4) * h.nnz
         for sweep in range(3):
             _, c_o, mu_o = P.sweep_replay(mu, SEED, sweep, class_id_base=cid_base)
-            for flags in (capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_RAGGED_KERNEL, capi.MMQ_GIBBS_GENERIC_KERNEL,
+            for flags in (capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_SEG_KERNEL, capi.MMQ_GIBBS_RAGGED_KERNEL, capi.MMQ_GIBBS_GENERIC_KERNEL,
                           capi.MMQ_GIBBS_TRANSPOSED, capi.MMQ_GIBBS_DEFAULT):
                 H.set_mu(mu)
                 _, c, mu_g = H.sweep_debug(SEED, sweep, flags, want_x=False)
@@ -132,6 +135,29 @@ def test_by_length_layout_segment_kernel(small_synth, weighted, cid_base):
         mu_end, tr_o = P.gibbs_replay(mu, SEED, 3, 29, 4, 8) if cid_base == 0 else (None, None)
         if cid_base == 0:
             assert np.array_equal(H.get_mu(), mu_end) and np.array_equal(H.get_trace()[:, 1:], tr_o[:, 1:])
+
+
+def test_row_plan_zero_weights_and_rejected_weights(small_synth):
+    """Weights of exactly 0 are legal (a hit that cannot have produced the fragment); negative, non-finite and
+    denormal weights are refused by mmq_create (the row kernel widens fp32 -> fp64 with integer operations)."""
+    s = small_synth
+    rng = np.random.default_rng(12)
+    w = np.exp(0.5 * rng.standard_normal(len(s.frag_tid))).astype(np.float32)
+    w[rng.random(len(w)) < 0.2] = 0.0
+    h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=w, layout=hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH)
+    P = orc.Problem(h.row_ptr, h.col, None, h.len, weight=h.w)
+    mu = np.random.default_rng(1).gamma(0.5, 10.0, h.n)
+    with capi.Handle(h.row_ptr, h.col, None, h.len, weight=h.w) as H:
+        assert H.rows_stats()["in_use"] == 1
+        for sweep in range(2):
+            H.set_mu(mu)
+            _, c_o, mu_o = P.sweep_replay(mu, SEED, sweep)
+            _, c, mu_g = H.sweep_debug(SEED, sweep, capi.MMQ_GIBBS_DEFAULT, want_x=False)
+            assert np.array_equal(c, c_o) and np.array_equal(mu_g, mu_o)
+    for bad in (-1.0, np.inf, np.nan, 1e-41):
+        wb = h.w.copy(); wb[len(wb) // 2] = bad
+        with pytest.raises(capi.MmqError):
+            capi.Handle(h.row_ptr, h.col, None, h.len, weight=wb)
 
 
 def test_weighted_rows_bit_exact(small_synth):
