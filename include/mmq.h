@@ -160,6 +160,13 @@ int mmq_cls_stats(const mmq_handle* h, int64_t out[8]);
  * per sweep (4 B per weight slot and set column, 32 B per chunk), out[7] single-member rows (not visited). */
 int mmq_rows_stats(const mmq_handle* h, int64_t out[8]);
 
+/* Launch-geometry knobs of the class-plan sweep, for measurements (tools/gpu_tune_cls.py); value 0 restores the
+ * default.  knob 0: bit mask of pieces NOT launched (1 k >= 2 small classes, 2 rest, 4 k >= 2 large classes, 8 chain,
+ * 16 single-fragment classes: timing experiments only, the chain is then wrong); knobs 1..4: resident CTAs per SM the
+ * grid of the chain / large / small / single-fragment kernel is capped at; knob 5: launch order variant.  Results do
+ * not depend on knobs 1..5. */
+int mmq_tune(mmq_handle* h, int knob, int value);
+
 /* Device time of the launches made under MMQ_GIBBS_TIME_KERNELS since the last
  * call (waits for the stream): total milliseconds and launch count of the
  * allocation kernel and of the Gamma kernel.  Any output may be NULL. */

@@ -66,6 +66,7 @@ def _load():
         "mmq_kernel_times": (i32, [vp, C.POINTER(dbl), C.POINTER(i64), C.POINTER(dbl), C.POINTER(i64)]),
         "mmq_cls_stats": (i32, [vp, C.POINTER(i64)]),
         "mmq_rows_stats": (i32, [vp, C.POINTER(i64)]),
+        "mmq_tune": (i32, [vp, i32, i32]),
         "mmq_get_trace": (i32, [vp, vp]),
         "mmq_trace_len": (i32, [vp]),
         "mmq_set_groups": (i32, [vp, i32, i64, vp, vp, vp]),
@@ -99,7 +100,7 @@ def lib():
 EXPORTS = [
     "mmq_create", "mmq_destroy", "mmq_last_error", "mmq_set_stream", "mmq_get_stream", "mmq_synchronize",
     "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_p2p_export", "mmq_p2p_attach", "mmq_p2p_attach_local", "mmq_p2p_attached", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
-    "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_cls_stats", "mmq_rows_stats", "mmq_get_trace", "mmq_trace_len",
+    "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_cls_stats", "mmq_rows_stats", "mmq_tune", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
     "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_warmup", "mmq_version",
 ]
@@ -276,6 +277,9 @@ class Handle:
         out = (C.c_int64 * 8)()
         self._check(lib().mmq_cls_stats(self._h, out), "mmq_cls_stats")
         return dict(zip(["in_use", "small_classes", "packed_slots", "class_slots", "rest_classes", "rest_nnz", "chain_classes", "chain_slots"], [int(v) for v in out]))
+
+    def tune(self, knob, value):
+        self._check(lib().mmq_tune(self._h, knob, value), "mmq_tune")
 
     def rows_stats(self):
         """Row plan of a by-length k == 1 shard (mmq_rows.cu)."""

@@ -1639,6 +1639,15 @@ int mmq_kernel_times(mmq_handle* h, double* alloc_ms, int64_t* alloc_launches, d
 
 int mmq_trace_len(const mmq_handle* h) { return h ? h->trace_len : 0; }
 
+int mmq_tune(mmq_handle* h, int knob, int value) {
+  if (!h || knob < 0 || knob >= 8) return mmq_fail(h, MMQ_ERR_ARG, "mmq_tune: bad knob");
+  MMQ_CUDA(h, cudaSetDevice(h->device));
+  MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
+  drop_graph(h); /* a captured graph has the old geometry baked in */
+  h->tune[knob] = value;
+  return MMQ_OK;
+}
+
 int mmq_warmup(int device) {
   if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return MMQ_ERR_CUDA; }
   return cudaFree(nullptr) == cudaSuccess ? MMQ_OK : MMQ_ERR_CUDA;

@@ -167,6 +167,9 @@ struct mmq_handle {
   /* MMQ_GIBBS_TIME_KERNELS: (start, stop) event pairs around each launch */
   std::vector<cudaEvent_t> ev_alloc, ev_gamma;
 
+  /* launch-geometry knobs of the class-plan sweep (mmq_tune; 0 = the measured default) */
+  int tune[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+
   int64_t bytes = 0;
   std::string err;
   std::vector<void*> allocs;
