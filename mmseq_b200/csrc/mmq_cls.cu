@@ -186,7 +186,7 @@ k_alloc_cls(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, co
       desc_n = cdesc[chunk_of(i + nwarps)];
     }
     const int kq = (int)(meta & 0xffu);
-    const uint32_t b0 = (meta >> 8) * (MMQ_CAT_GROUP / 4);
+    const uint32_t b0 = (meta >> 8) * (uint32_t)(MMQ_CLS_GROUP(D) / 4);
 #define MMQ_CLS_CASE(DD) case DD: cls_chunk<DD>(pc, kq, b0, cid, cid_hi, mu, counts, seed, sweep, lane); break;
     if (LO) {
       switch (D) {

@@ -22,6 +22,11 @@
 #define MMQ_CLS_DLO 8    /* class sizes 2..8: the 64-register instance (32 warps per SM) */
 #define MMQ_CLS_DREG 16  /* class sizes up to this are register-resident template instances */
 #define MMQ_CLS_WARPS 4
+/* draws per slot of a class with d members: 64 (16 Philox blocks) for the small sizes; 16 for the larger ones, whose
+ * slots cost 4 (d - 1) compare-and-add pairs per block — a 64-draw slot of a 16-member class is ~16 us of dependent work
+ * for its warp, and the few such chunks then decide when the launch ends (measured in round 2: 26 us for 3.4 M warp
+ * instructions).  Which draws a slot makes is a plan detail: draw t of a class always reads word t & 3 of block t >> 2. */
+#define MMQ_CLS_GROUP(d) ((d) <= MMQ_CLS_DLO ? MMQ_CAT_GROUP : 16)
 #define MMQ_CLS_NQ 17    /* sort positions inside a run of equal d: 16 - blocks (k >= 2); 16: k == 1 (those form runs of their own) */
 /* runs are numbered by a "pseudo size": d for the classes with k >= 2, MMQ_CLS_DMAX + 1 + d for the single-fragment
  * classes — their chunks come after all the others and are swept by their own kernel (k_alloc_cls1) */
@@ -124,9 +129,10 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
         ++hc[col[rp[i]]];
         if (kv == 1) { key16[i] = (int16_t)(MMQ_CLS_DP1(d) * MMQ_CLS_NQ + 16); ++t.key_count[key16[i]]; }
         else {
-          const int64_t full = kv / MMQ_CAT_GROUP, tail = kv % MMQ_CAT_GROUP;
-          t.key_count[d * MMQ_CLS_NQ + 0] += full; /* 16 blocks */
-          key16[i] = (int16_t)(d * MMQ_CLS_NQ + (tail ? 16 - (int)((tail + 3) >> 2) : 0));
+          const int64_t grp = MMQ_CLS_GROUP(d);
+          const int64_t full = kv / grp, tail = kv % grp;
+          t.key_count[d * MMQ_CLS_NQ + (16 - grp / 4)] += full; /* full slots */
+          key16[i] = (int16_t)(d * MMQ_CLS_NQ + (tail ? 16 - (int)((tail + 3) >> 2) : 16 - (int)(grp / 4)));
           if (tail) ++t.key_count[key16[i]];
         }
       } else if (d <= MMQ_CLS_DMAX) { key16[i] = -3; ++t.n_chain; }
@@ -177,7 +183,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
   /* Within a key the classes are placed by their first member (a stable counting sort): members are
    * ascending and the isoforms of a gene are neighbours in the header, so the lanes of a warp and the
    * warps of an SM gather neighbouring mu — L1 hits instead of one L2 sector per 8-byte gather. */
-  static_assert(MMQ_CAT_KMAX / MMQ_CAT_GROUP <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
+  static_assert(MMQ_CAT_KMAX / 16 <= 255 && MMQ_CAT_GROUP <= 255, "slot counts are kept in bytes");
   struct Ord { int32_t i; int16_t key; uint8_t full, tail; }; /* key: of the partial slot (tail draws) when there is one */
   std::vector<Ord> order((size_t)small_classes);
   /* parallel stable counting sort (counts taken in the classification pass): per first member, thread t gets
@@ -189,7 +195,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
     on_threads([&](int t) {
       int64_t* c = hist.data() + (size_t)t * nb;
       for (int64_t i = m * t / T; i < m * (t + 1) / T; ++i)
-        if (key16[i] >= 0) order[(size_t)c[col[rp[i]]]++] = Ord{(int32_t)i, key16[i], (uint8_t)(kk[i] / MMQ_CAT_GROUP), (uint8_t)(kk[i] % MMQ_CAT_GROUP)};
+        if (key16[i] >= 0) order[(size_t)c[col[rp[i]]]++] = Ord{(int32_t)i, key16[i], (uint8_t)(kk[i] / MMQ_CLS_GROUP(rp[i + 1] - rp[i])), (uint8_t)(kk[i] % MMQ_CLS_GROUP(rp[i + 1] - rp[i]))};
     });
   }
   tick("order by first member");
@@ -202,7 +208,8 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
       int64_t* u = used.data() + (size_t)t * (NKEY + 1);
       for (int64_t o = small_classes * t / T; o < small_classes * (t + 1) / T; ++o) {
         const Ord& e = order[(size_t)o];
-        u[(e.key / MMQ_CLS_NQ) * MMQ_CLS_NQ + 0] += e.full;
+        const int dpu = e.key / MMQ_CLS_NQ;
+        u[dpu * MMQ_CLS_NQ + (16 - MMQ_CLS_GROUP(MMQ_CLS_D_OF(dpu)) / 4)] += e.full;
         if (e.tail) ++u[e.key];
       }
     });
@@ -215,8 +222,9 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
       for (int64_t o = small_classes * t / T; o < small_classes * (t + 1) / T; ++o) {
         const Ord& e = order[(size_t)o];
         const int dp = e.key / MMQ_CLS_NQ;
-        slot_full[(size_t)o] = next[dp * MMQ_CLS_NQ + 0];
-        next[dp * MMQ_CLS_NQ + 0] += e.full;
+        const int qf = 16 - MMQ_CLS_GROUP(MMQ_CLS_D_OF(dp)) / 4; /* the key of the class's full slots */
+        slot_full[(size_t)o] = next[dp * MMQ_CLS_NQ + qf];
+        next[dp * MMQ_CLS_NQ + qf] += e.full;
         slot_tail[(size_t)o] = e.tail ? next[e.key]++ : -1; /* -1: k is a multiple of 64, no partial slot */
       }
     });
@@ -250,7 +258,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
         pk[s] = (uint16_t)(draws | (slot_no << 8));
         pcid[s] = cid;
       };
-      for (int q = 0; q < (int)e.full; ++q) put(slot_full[(size_t)o] + q, MMQ_CAT_GROUP, q);
+      for (int q = 0; q < (int)e.full; ++q) put(slot_full[(size_t)o] + q, MMQ_CLS_GROUP(d), q);
       if (e.tail) put(slot_tail[(size_t)o], (int)e.tail, (int)e.full);
     }
   });
@@ -350,7 +358,7 @@ static void mmq_cls_replay_host(const mmq_cls_host_plan& P, int64_t n, const dou
         const int32_t* pc = P.pcol.get() + P.runs[r].e0 + (ch - c0) * 32 * d + lane;
         const uint32_t meta = P.pk[(size_t)(ch * 32 + lane)];
         const int kq = (int)(meta & 0xffu);
-        const uint32_t b0 = (meta >> 8) * (MMQ_CAT_GROUP / 4);
+        const uint32_t b0 = (meta >> 8) * (uint32_t)(MMQ_CLS_GROUP(d) / 4);
         const uint32_t cid = P.pcid[(size_t)(ch * 32 + lane)];
         if (kq == 0) continue;
         for (int j = 0; j < d; ++j) S[(size_t)j] = (pc[32 * j] == (int32_t)n ? 0.0 : mu[pc[32 * j]]) + (j ? S[(size_t)j - 1] : 0.0);

@@ -113,7 +113,7 @@ struct mmq_handle {
   int32_t* rows_set_col = nullptr;
   float* rows_w = nullptr;
   int rows_nruns = 0;
-  int64_t rows_chunks = 0, rows_rows = 0, rows_sets = 0, rows_set_cols = 0, rows_wslots = 0;
+  int64_t rows_chunks = 0, rows_chunks_small = 0, rows_rows = 0, rows_sets = 0, rows_set_cols = 0, rows_wslots = 0;
 
   /* class plan for collapsed shards (mmq_cls.cu): the classes with few fragments packed in
    * member-major chunks of 32, the rest as a sub-CSR for the general kernel on stream2 */

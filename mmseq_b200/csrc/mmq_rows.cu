@@ -103,38 +103,22 @@ __global__ void k_rows_fill(mmq_rows_run R, int run_index, const int32_t* __rest
   }
 }
 
-/* weights must be 0 or positive normal finite numbers: the kernel widens them to fp64 with integer operations */
-__global__ void k_rows_check_w(const float* __restrict__ w, int64_t nnz, int* __restrict__ bad) {
-  int b = 0;
-  for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nnz; q += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t u = __float_as_uint(w[q]);
-    const uint32_t e = (u >> 23) & 0xffu;
-    if (u != 0u && ((u >> 31) != 0u || e == 0u || e == 0xffu)) b = 1;
-  }
-  if (b) atomicOr(bad, 1);
-}
-
 /* ------------------------------------------------------------------ the sweep kernel */
 
-/* fp32 -> fp64, exact, for 0 and positive normal numbers (validated at plan time): two integer operations on the
- * high word instead of a conversion instruction (conversions issue at an eighth of the integer rate) */
-__device__ __forceinline__ double rows_w2d(float f) {
-  const uint32_t u = __float_as_uint(f);
-  return __hiloint2double(u ? (int)((u >> 3) + 0x38000000u) : 0, (int)(u << 29));
-}
+__device__ __forceinline__ double rows_w2d(float f) { return (double)f; }
 
 template <int D, bool HAS_W>
-__device__ __forceinline__ void rows_chunk(const mmq_rows_run& R, const mmq_rows_meta& M, int s0, unsigned nb, int vrow0, const uint32_t (&wd)[4],
-                                           const int32_t* __restrict__ set_col, const float* __restrict__ w_mm, const double* __restrict__ mu,
+__device__ __forceinline__ void rows_chunk(int row_lo, int vrows, int s0, unsigned nb, int vrow0, uint4 wq4,
+                                           const int32_t* __restrict__ setp, const float* __restrict__ wchunk, const double* __restrict__ mu,
                                            int32_t* __restrict__ counts, int lane) {
   float4 wv[HAS_W ? D : 1];
   if (HAS_W) {
-    const float4* wp = reinterpret_cast<const float4*>(w_mm + M.woff) + lane;
+    const float4* wp = reinterpret_cast<const float4*>(wchunk) + lane;
 #pragma unroll
     for (int j = 0; j < D; ++j) wv[j] = __ldg(wp + j * (MMQ_ROWS_CHUNK / 4));
   }
-  double g[D], S[D];
-  const int32_t* cp = set_col;
+  double g[D], S[HAS_W ? 1 : D];
+  const int32_t* cp = setp;
   int cur = -2; /* no set yet (-1 is the dummy set in front of a run) */
   int s = s0;
 #pragma unroll
@@ -143,41 +127,90 @@ __device__ __forceinline__ void rows_chunk(const mmq_rows_run& R, const mmq_rows
     const bool fresh = s != cur;
     if (fresh) { /* a new set: its columns (a few contiguous words, mostly L1 hits) and mu */
       cur = s;
-      cp = set_col + R.col_base + (int64_t)(s < 0 ? 0 : s) * D;
+      cp = setp + (int64_t)(s < 0 ? 0 : s) * D;
 #pragma unroll
       for (int j = 0; j < D; ++j) g[j] = mu[__ldg(cp + j)];
     }
-    if (HAS_W || fresh) {
+    int chosen = D - 1;
+    if (HAS_W) { /* two passes over the members (the products are formed twice) instead of D stored sums: registers */
+      double norm = 0.0;
 #pragma unroll
       for (int j = 0; j < D; ++j) {
-        const float wf = i == 0 ? wv[HAS_W ? j : 0].x : i == 1 ? wv[HAS_W ? j : 0].y : i == 2 ? wv[HAS_W ? j : 0].z : wv[HAS_W ? j : 0].w;
-        const double p = HAS_W ? g[j] * rows_w2d(wf) : g[j];
-        S[j] = j ? S[j - 1] + p : p;
+        const float wf = i == 0 ? wv[j].x : i == 1 ? wv[j].y : i == 2 ? wv[j].z : wv[j].w;
+        norm += g[j] * rows_w2d(wf);
       }
+      const double target = mmq_uniform32(i == 0 ? wq4.x : i == 1 ? wq4.y : i == 2 ? wq4.z : wq4.w) * norm;
+      double acc = 0.0;
+#pragma unroll
+      for (int j = 0; j < D - 1; ++j) {
+        const float wf = i == 0 ? wv[j].x : i == 1 ? wv[j].y : i == 2 ? wv[j].z : wv[j].w;
+        acc += g[j] * rows_w2d(wf);
+        chosen -= (target < acc) ? 1 : 0; /* the sums are non-decreasing: first j with target < S_j */
+      }
+    } else {
+      if (fresh) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) S[j] = j ? S[j - 1] + g[j] : g[j];
+      }
+      const double target = mmq_uniform32(i == 0 ? wq4.x : i == 1 ? wq4.y : i == 2 ? wq4.z : wq4.w) * S[D - 1];
+#pragma unroll
+      for (int j = 0; j < D - 1; ++j) chosen -= (target < S[j]) ? 1 : 0;
     }
-    const double target = mmq_uniform32(wd[i]) * S[D - 1];
+    const int vr = vrow0 + i;
+    cat_red(counts, (vr >= row_lo && vr < vrows) ? __ldg(cp + chosen) : -1, lane);
+  }
+}
+
+/* class sizes 9..16: mu of the set in registers (reused while the set repeats), the lane's weights read row by row
+ * (the chunk's weight lines stay in L1 between its four rows), two passes over the members instead of stored sums */
+template <int D, bool HAS_W>
+__device__ __forceinline__ void rows_chunk_mid(int D_, int row_lo, int vrows, int s0, unsigned nb, int vrow0, uint4 wq4,
+                                            const int32_t* __restrict__ setp, const float* __restrict__ wchunk, const double* __restrict__ mu,
+                                            int32_t* __restrict__ counts, int lane) {
+  double g[D];
+  const int32_t* cp = setp;
+  int cur = -2;
+  int s = s0;
+#pragma unroll 1
+  for (int i = 0; i < 4; ++i) {
+    if (i > 0) s += (int)((nb >> (i - 1)) & 1u);
+    if (s != cur) {
+      cur = s;
+      cp = setp + (int64_t)(s < 0 ? 0 : s) * D;
+#pragma unroll
+      for (int j = 0; j < D; ++j) g[j] = mu[__ldg(cp + j)];
+    }
+    const float* wp = wchunk + 4 * lane + i;
+    double p[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) p[j] = HAS_W ? g[j] * (double)__ldg(wp + j * MMQ_ROWS_CHUNK) : g[j];
+    double norm = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) norm += p[j];
+    const double target = mmq_uniform32(i == 0 ? wq4.x : i == 1 ? wq4.y : i == 2 ? wq4.z : wq4.w) * norm;
+    double acc = 0.0;
     int chosen = D - 1;
 #pragma unroll
-    for (int j = 0; j < D - 1; ++j) chosen -= (target < S[j]) ? 1 : 0; /* S is non-decreasing: first j with target < S_j */
+    for (int j = 0; j < D - 1; ++j) { acc += p[j]; chosen -= (target < acc) ? 1 : 0; }
     const int vr = vrow0 + i;
-    cat_red(counts, (vr >= R.row_lo && vr < R.vrows) ? __ldg(cp + chosen) : -1, lane);
+    cat_red(counts, (vr >= row_lo && vr < vrows) ? __ldg(cp + chosen) : -1, lane);
   }
 }
 
 /* any class size: members re-read per row (L1 / L2 hits) */
 template <bool HAS_W>
-__device__ __noinline__ void rows_chunk_any(const mmq_rows_run& R, const mmq_rows_meta& M, int s0, unsigned nb, int vrow0, const uint32_t (&wd)[4],
-                                            const int32_t* __restrict__ set_col, const float* __restrict__ w_mm, const double* __restrict__ mu,
+__device__ __noinline__ void rows_chunk_any(int D_, int row_lo, int vrows, int s0, unsigned nb, int vrow0, uint4 wq4,
+                                            const int32_t* __restrict__ setp, const float* __restrict__ wchunk, const double* __restrict__ mu,
                                             int32_t* __restrict__ counts, int lane) {
-  const int D = R.d;
+  const int D = D_;
   int s = s0;
   for (int i = 0; i < 4; ++i) {
     if (i > 0) s += (int)((nb >> (i - 1)) & 1u);
-    const int32_t* cp = set_col + R.col_base + (int64_t)(s < 0 ? 0 : s) * D;
-    const float* wp = w_mm + M.woff + 4 * lane + i;
+    const int32_t* cp = setp + (int64_t)(s < 0 ? 0 : s) * D;
+    const float* wp = wchunk + 4 * lane + i;
     double norm = 0.0;
     for (int j = 0; j < D; ++j) norm += HAS_W ? mu[cp[j]] * rows_w2d(wp[(int64_t)j * MMQ_ROWS_CHUNK]) : mu[cp[j]];
-    const double target = mmq_uniform32(wd[i]) * norm;
+    const double target = mmq_uniform32(i == 0 ? wq4.x : i == 1 ? wq4.y : i == 2 ? wq4.z : wq4.w) * norm;
     double acc = 0.0;
     int chosen = D - 1;
     for (int j = 0; j < D - 1; ++j) {
@@ -185,13 +218,15 @@ __device__ __noinline__ void rows_chunk_any(const mmq_rows_run& R, const mmq_row
       if (target < acc) { chosen = j; break; }
     }
     const int vr = vrow0 + i;
-    cat_red(counts, (vr >= R.row_lo && vr < R.vrows) ? cp[chosen] : -1, lane);
+    cat_red(counts, (vr >= row_lo && vr < vrows) ? cp[chosen] : -1, lane);
   }
 }
 
-template <bool HAS_W, int MINB>
+/* MID = false: the chunks of class sizes 2..MMQ_ROWS_DREG ([chunk_begin, chunk_end) = the front of the plan, runs are in
+ * ascending class size); MID = true: the larger sizes (their own launch: the register budgets differ) */
+template <bool HAS_W, bool MID, int MINB>
 __global__ void __launch_bounds__(MMQ_ROWS_WARPS * 32, MINB)
-k_alloc_rows(const mmq_rows_run* __restrict__ runs, int nruns, int chunks, const mmq_rows_meta* __restrict__ meta,
+k_alloc_rows(const mmq_rows_run* __restrict__ runs, int nruns, int chunk_begin, int chunks, const mmq_rows_meta* __restrict__ meta,
              const int32_t* __restrict__ set_col, const float* __restrict__ w_mm, const double* __restrict__ mu,
              int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
   if (sweep_base) sweep += *sweep_base;
@@ -200,7 +235,7 @@ k_alloc_rows(const mmq_rows_run* __restrict__ runs, int nruns, int chunks, const
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * MMQ_ROWS_WARPS;
-  for (int chunk = blockIdx.x * MMQ_ROWS_WARPS + (threadIdx.x >> 5); chunk < chunks; chunk += nwarps) {
+  for (int chunk = chunk_begin + blockIdx.x * MMQ_ROWS_WARPS + (threadIdx.x >> 5); chunk < chunks; chunk += nwarps) {
     mmq_rows_meta M;
     {
       const uint4* mp = reinterpret_cast<const uint4*>(meta + chunk); /* the same 32 bytes for all lanes: one transaction */
@@ -211,6 +246,9 @@ k_alloc_rows(const mmq_rows_run* __restrict__ runs, int nruns, int chunks, const
     }
     const mmq_rows_run& R = s_run[M.run];
     const int vrow0 = (chunk - R.chunk0) * MMQ_ROWS_CHUNK + 4 * lane;
+    const int row_lo = R.row_lo, vrows = R.vrows, Dr = R.d;
+    const int32_t* setp = set_col + R.col_base;
+    const float* wchunk = w_mm + M.woff;
     /* set of row 4 lane: the chunk's first set + the "new set" bits of rows 1 .. 4 lane */
     const int wq = lane >> 3, bq = (4 * lane) & 31;
     int s0 = M.set_first;
@@ -224,10 +262,19 @@ k_alloc_rows(const mmq_rows_run* __restrict__ runs, int nruns, int chunks, const
     const uint64_t cid = (uint64_t)(R.cid_virtual + vrow0);
     uint32_t wd[4] = {(uint32_t)(cid >> 2), (uint32_t)(cid >> 34), sweep, 0u};
     mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
-#define MMQ_ROWS_CASE(DD) case DD: rows_chunk<DD, HAS_W>(R, M, s0, nb, vrow0, wd, set_col, w_mm, mu, counts, lane); break;
-    switch (R.d) {
-      MMQ_ROWS_CASE(2) MMQ_ROWS_CASE(3) MMQ_ROWS_CASE(4) MMQ_ROWS_CASE(5) MMQ_ROWS_CASE(6) MMQ_ROWS_CASE(7) MMQ_ROWS_CASE(8)
-      default: rows_chunk_any<HAS_W>(R, M, s0, nb, vrow0, wd, set_col, w_mm, mu, counts, lane); break;
+#define MMQ_ROWS_CASE(DD) case DD: rows_chunk<DD, HAS_W>(row_lo, vrows, s0, nb, vrow0, make_uint4(wd[0], wd[1], wd[2], wd[3]), setp, wchunk, mu, counts, lane); break;
+    if (!MID) {
+      switch (Dr) {
+        MMQ_ROWS_CASE(2) MMQ_ROWS_CASE(3) MMQ_ROWS_CASE(4) MMQ_ROWS_CASE(5) MMQ_ROWS_CASE(6) MMQ_ROWS_CASE(7) MMQ_ROWS_CASE(8)
+        default: break;
+      }
+    } else {
+#define MMQ_ROWS_MID(DD) case DD: rows_chunk_mid<DD, HAS_W>(DD, row_lo, vrows, s0, nb, vrow0, make_uint4(wd[0], wd[1], wd[2], wd[3]), setp, wchunk, mu, counts, lane); break;
+      switch (Dr) {
+        MMQ_ROWS_MID(9) MMQ_ROWS_MID(10) MMQ_ROWS_MID(11) MMQ_ROWS_MID(12) MMQ_ROWS_MID(13) MMQ_ROWS_MID(14) MMQ_ROWS_MID(15) MMQ_ROWS_MID(16)
+        default: rows_chunk_any<HAS_W>(Dr, row_lo, vrows, s0, nb, vrow0, make_uint4(wd[0], wd[1], wd[2], wd[3]), setp, wchunk, mu, counts, lane); break;
+      }
+#undef MMQ_ROWS_MID
     }
 #undef MMQ_ROWS_CASE
   }
@@ -241,10 +288,12 @@ int mmq_rows_plan(mmq_handle* h) {
   if (off || !h->seg_scan_ok || h->has_k || h->m == 0) return MMQ_OK;
   std::vector<mmq_rows_run> runs;
   std::vector<int64_t> vbase, wbase;
-  int64_t chunks = 0, vtot = 0, wtot = 0, rows = 0;
+  int64_t chunks = 0, chunks_small = 0, vtot = 0, wtot = 0, rows = 0;
+  int last_d = 0;
   for (const auto& r : h->seg_runs) {
     if (r.d == 1) continue;
-    if (r.d > 0xffff || (r.r1 - r.r0 + 3) > 0x7ffffff0ll) return MMQ_OK;
+    if (r.d > 0xffff || (r.r1 - r.r0 + 3) > 0x7ffffff0ll || r.d < last_d) return MMQ_OK; /* runs must come in ascending class size */
+    last_d = r.d;
     mmq_rows_run R;
     const int lead = (int)((h->class_id_base + r.r0) & 3); /* dummy rows: the virtual first class id is a multiple of 4 */
     R.cid_virtual = h->class_id_base + r.r0 - lead;
@@ -255,6 +304,7 @@ int mmq_rows_plan(mmq_handle* h) {
     R.chunk0 = (int32_t)chunks;
     R.set_base = 0; R.pad = 0;
     const int64_t nch = ((int64_t)R.vrows + MMQ_ROWS_CHUNK - 1) / MMQ_ROWS_CHUNK;
+    if (r.d <= MMQ_ROWS_DREG) chunks_small = chunks + nch;
     vbase.push_back(vtot); wbase.push_back(wtot);
     chunks += nch; vtot += nch * MMQ_ROWS_CHUNK; wtot += nch * MMQ_ROWS_CHUNK * r.d;
     rows += r.r1 - r.r0;
@@ -263,16 +313,6 @@ int mmq_rows_plan(mmq_handle* h) {
   }
   if (runs.empty() || (int)runs.size() > MMQ_ROWS_MAXRUN) return MMQ_OK;
   int rc;
-  if (h->has_w) { /* the integer widening of the weights needs 0 or positive normal numbers */
-    int* d_bad = (int*)h->scalars;
-    MMQ_CUDA(h, cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
-    k_rows_check_w<<<mmq_grid_for(h->nnz, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->w, h->nnz, d_bad);
-    MMQ_LAUNCHED(h);
-    int bad = 0;
-    MMQ_CUDA(h, cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
-    if (bad) return mmq_fail(h, MMQ_ERR_ARG, "mmq_create: per-hit weights must be 0 or positive, finite and not denormal");
-  }
   /* 1. new-set flags, 2. inclusive scan = set numbering, 3. per-run set counts back to the host, 4. fill */
   int32_t *flag = nullptr, *incl = nullptr;
   void* temp = nullptr;
@@ -322,6 +362,7 @@ int mmq_rows_plan(mmq_handle* h) {
   if (e != cudaSuccess) return mmq_cuda_fail(h, e, "row plan fill", __FILE__, __LINE__);
   h->rows_nruns = (int)runs.size();
   h->rows_chunks = chunks;
+  h->rows_chunks_small = chunks_small;
   h->rows_rows = rows;
   h->rows_sets = sets;
   h->rows_set_cols = set_cols;
@@ -347,16 +388,24 @@ int mmq_rows_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t
   int rc = mmq_seg_add_base(h, true);
   if (rc) return rc;
   if (h->rows_chunks == 0) return MMQ_OK;
-  const int chunks = (int)h->rows_chunks;
-#define MMQ_ROWS_GO(W, MINB)                                                                                                     \
+  const int chunks = (int)h->rows_chunks, csmall = (int)h->rows_chunks_small;
+#define MMQ_ROWS_GO(W, MID, MINB, c0, c1)                                                                                        \
   do {                                                                                                                           \
-    const int grid = std::min((chunks + MMQ_ROWS_WARPS - 1) / MMQ_ROWS_WARPS, h->num_sms * MINB);                                 \
-    k_alloc_rows<W, MINB><<<grid, MMQ_ROWS_WARPS * 32, 0, h->stream>>>((const mmq_rows_run*)h->rows_runs, h->rows_nruns, chunks,  \
-                                                                      (const mmq_rows_meta*)h->rows_meta, h->rows_set_col,      \
-                                                                      h->rows_w, h->mu, h->counts, seed, sweep, sweep_base);     \
+    const int grid = std::min(((c1) - (c0) + MMQ_ROWS_WARPS - 1) / MMQ_ROWS_WARPS, h->num_sms * MINB);                             \
+    k_alloc_rows<W, MID, MINB><<<grid, MMQ_ROWS_WARPS * 32, 0, h->stream>>>((const mmq_rows_run*)h->rows_runs, h->rows_nruns, (c0), (c1), \
+                                                                           (const mmq_rows_meta*)h->rows_meta, h->rows_set_col, \
+                                                                           h->rows_w, h->mu, h->counts, seed, sweep, sweep_base); \
+    MMQ_LAUNCHED(h);                                                                                                             \
   } while (0)
-  if (h->has_w) MMQ_ROWS_GO(true, 4);
-  else MMQ_ROWS_GO(false, 5);
+  if (chunks > csmall) { /* the long rows first: few chunks, long dependent work */
+    if (h->has_w) MMQ_ROWS_GO(true, true, 4, csmall, chunks);
+    else MMQ_ROWS_GO(false, true, 4, csmall, chunks);
+  }
+  if (csmall > 0) {
+    if (h->has_w) MMQ_ROWS_GO(true, false, 4, 0, csmall);
+    else MMQ_ROWS_GO(false, false, 5, 0, csmall);
+  }
 #undef MMQ_ROWS_GO
+  g_mmq_launches.fetch_sub(1, std::memory_order_relaxed); /* the caller counts one */
   return MMQ_OK;
 }

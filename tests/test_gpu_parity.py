@@ -137,9 +137,8 @@ def test_by_length_layout_segment_kernel(small_synth, weighted, cid_base):
             assert np.array_equal(H.get_mu(), mu_end) and np.array_equal(H.get_trace()[:, 1:], tr_o[:, 1:])
 
 
-def test_row_plan_zero_weights_and_rejected_weights(small_synth):
-    """Weights of exactly 0 are legal (a hit that cannot have produced the fragment); negative, non-finite and
-    denormal weights are refused by mmq_create (the row kernel widens fp32 -> fp64 with integer operations)."""
+def test_row_plan_zero_weights(small_synth):
+    """Weights of exactly 0 are legal (a hit that cannot have produced the fragment): such a member is never chosen."""
     s = small_synth
     rng = np.random.default_rng(12)
     w = np.exp(0.5 * rng.standard_normal(len(s.frag_tid))).astype(np.float32)
@@ -154,10 +153,6 @@ def test_row_plan_zero_weights_and_rejected_weights(small_synth):
             _, c_o, mu_o = P.sweep_replay(mu, SEED, sweep)
             _, c, mu_g = H.sweep_debug(SEED, sweep, capi.MMQ_GIBBS_DEFAULT, want_x=False)
             assert np.array_equal(c, c_o) and np.array_equal(mu_g, mu_o)
-    for bad in (-1.0, np.inf, np.nan, 1e-41):
-        wb = h.w.copy(); wb[len(wb) // 2] = bad
-        with pytest.raises(capi.MmqError):
-            capi.Handle(h.row_ptr, h.col, None, h.len, weight=wb)
 
 
 def test_weighted_rows_bit_exact(small_synth):
