@@ -519,32 +519,50 @@ MMQ_HD int64_t mmq_binomial(const mmq_rng* g, uint32_t block0, int64_t n, double
 
 /* ---------------------------------------------------- one hit class */
 
-/* blocks of member j of a chain class: (j << 8) + attempt */
+/* blocks of node h (heap index (1 << level) + position) of a chain class: (h << 8) + attempt */
 #define MMQ_CHAIN_BLOCK(j) ((uint32_t)(j) << 8)
 
-/* gsl_ran_multinomial's chain of conditional binomials (src/mmseq.cpp:880): x_j ~ Bin(k - sum_{<j} x, p_j / (P - sum_{<j} p)),
- * members with zero probability skipped, the last member with p > 0 takes what is left.  norm = p_0 + ... + p_{d-1} summed
- * left to right and last_pos = the last member with p > 0 (d - 1 if none) come from the caller's first pass over the row;
- * g is the class's ALLOC stream; the binomial of member j reads the blocks MMQ_CHAIN_BLOCK(j) + attempt.  p is read once
- * more, x[j] is assigned exactly once per member. */
+/* Multinomial(k; p) for a class with many fragments, as gsl_ran_multinomial (src/mmseq.cpp:880) draws it: by conditional
+ * binomials.  GSL walks the members left to right (x_j ~ Bin(rest, p_j / P(j..d-1))): d - 1 binomials that each wait for
+ * the one before.  The same distribution is obtained from any binary splitting of the member range, and a BALANCED one
+ * has depth ceil(log2 d) instead of d - 1 — what bounds the time of a sweep on the GPU, where the binomials of a level
+ * are drawn side by side (mmq_cls.cu: k_alloc_chain).  Node i of level L covers the members [(i d) >> L, ((i+1) d) >> L);
+ * its count n splits into Bin(n, left / (left + right)) for the left half and the rest for the right half, the two
+ * range sums formed left to right.  Members with zero probability never receive fragments (an all-zero node hands
+ * everything to its right half, so an all-zero row ends in its last member).  The binomial of node (L, i) reads the
+ * blocks MMQ_CHAIN_BLOCK((1 << L) + i) + attempt of the class's ALLOC stream, so nodes can be drawn in any order.
+ * x[j] is assigned exactly once per member. */
+#define MMQ_NODE_LO(i, L, d) ((int)(((int64_t)(i) * (int64_t)(d)) >> (L)))
+template <typename PIt>
+MMQ_HD double mmq_node_prob(PIt p, int lo, int mid, int hi) {
+  double left = 0.0, right = 0.0;
+  for (int j = lo; j < mid; ++j) left += p[j];
+  for (int j = mid; j < hi; ++j) right += p[j];
+  const double tot = left + right;
+  double pr = tot > 0.0 ? left / tot : 0.0;
+  return pr > 1.0 ? 1.0 : pr;
+}
 template <typename PIt, typename XIt>
-MMQ_HD void mmq_alloc_chain(PIt p, XIt x, int d, int64_t k, double norm, int last_pos, const mmq_rng* g) {
-  int64_t rem = k;
-  double sum_p = 0.0;
-  for (int j = 0; j < d; ++j) {
-    int64_t xj = 0;
-    const double pj = p[j];
-    if (j == last_pos) {
-      xj = rem; /* zero-probability members never receive fragments */
-    } else if (rem > 0 && pj > 0.0) {
-      const double denom = norm - sum_p;
-      double pr = (denom > 0.0) ? pj / denom : 1.0;
-      if (pr > 1.0) pr = 1.0;
-      xj = mmq_binomial(g, MMQ_CHAIN_BLOCK(j), rem, pr);
-    }
-    x[j] = (int32_t)xj;
-    rem -= xj;
-    sum_p += pj;
+MMQ_HD void mmq_alloc_chain(PIt p, XIt x, int d, int64_t k, const mmq_rng* g) {
+  int sl[40], si[40];
+  int64_t sn[40];
+  int top = 0;
+  sl[0] = 0; si[0] = 0; sn[0] = k; top = 1;
+  while (top > 0) {
+    --top;
+    const int L = sl[top], i = si[top];
+    const int64_t n = sn[top];
+    const int lo = MMQ_NODE_LO(i, L, d), hi = MMQ_NODE_LO(i + 1, L, d);
+    if (hi <= lo) continue;
+    if (hi - lo == 1) { x[lo] = (int32_t)n; continue; }
+    const int mid = MMQ_NODE_LO(2 * i + 1, L + 1, d);
+    int64_t nl;
+    if (mid == lo) nl = 0;
+    else if (mid == hi) nl = n;
+    else if (n == 0) nl = 0;
+    else nl = mmq_binomial(g, MMQ_CHAIN_BLOCK((1u << L) + (uint32_t)i), n, mmq_node_prob(p, lo, mid, hi));
+    sl[top] = L + 1; si[top] = 2 * i + 1; sn[top] = n - nl; ++top;
+    sl[top] = L + 1; si[top] = 2 * i; sn[top] = nl; ++top;
   }
 }
 
@@ -643,7 +661,7 @@ MMQ_HD void mmq_alloc_row(PIt p, XIt x, int d, int64_t k, uint32_t seed, uint64_
     }
     return;
   }
-  mmq_alloc_chain(p, x, d, k, norm, last_pos, &g);
+  mmq_alloc_chain(p, x, d, k, &g);
 }
 
 #endif /* MMQ_SAMPLER_H */

@@ -277,29 +277,35 @@ k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, c
   }
 }
 
-/* The chain set: classes with more than mmq_cat_limit(d) fragments — gsl_ran_multinomial's chain of conditional binomials
- * (src/mmseq.cpp:880), O(d) per class whatever k is.  One class per lane, 32 classes of equal size per chunk (member-major
- * like the small set, so every column load of a warp is one 128-byte line), longest classes first, 4 chunks per block.
- * The lane sums its row left to right (norm, last member with p > 0), then the block walks the members in step:
- * x_j ~ Bin(rem, p_j / (norm - sum_{<j} p)).
+/* The chain set: classes with more than mmq_cat_limit(d) fragments — the multinomial by conditional binomials
+ * (gsl_ran_multinomial, src/mmseq.cpp:880), O(d) binomials per class whatever k is, in the balanced splitting order of
+ * mmq_alloc_chain (include/mmq_sampler.h): ceil(log2 d) levels, the binomials of a level independent of each other.
+ * One class per lane of the block's first four warps, 32 classes of equal size per chunk (member-major like the small
+ * set, so every column load of a warp is one 128-byte line), longest classes first.
  *
  * A binomial is a rejection sampler (BTRS above a mean of 10) or an inversion loop of data-dependent length (BINV
  * below): with every lane running its own, a warp pays for the union of the regimes and for its slowest lane — the first
- * version of this kernel kept 5.5 of 32 lanes busy (ncu, round 2) and took 117 us for the 49k classes of the config-2
- * sample.  An attempt being a pure function of (class, sweep, member, attempt number) (include/mmq_sampler.h), the
- * block instead QUEUES the binomials of a step in shared memory by regime and runs each queue densely: BTRS attempts
- * in rounds (the rejected ones re-queued), then the inversions.  Same integers as the CPU replay's mmq_alloc_chain. */
+ * version of this kernel (a left-to-right chain per lane) kept 5.5 of 32 lanes busy (ncu, round 2) and took 117 us for
+ * the 49k classes of the config-2 sample.  An attempt being a pure function of (class, sweep, node, attempt number),
+ * the block instead QUEUES the binomials of a level in shared memory by regime and runs each queue densely: the BTRS
+ * attempts in rounds, MMQ_CHAIN_SPEC attempts of every open draw side by side (the lowest accepted one counts), the
+ * rejected ones re-queued; the inversions on the remaining threads of the first round.  Same integers as the CPU
+ * replay's mmq_alloc_chain. */
 #define MMQ_CHAIN_THREADS 256 /* threads per block */
 #define MMQ_CHAIN_CLASSES 128 /* classes per block pass: the lanes of warps 0..3 (the other warps only work in the dense phases) */
-#define MMQ_CHAIN_SPEC 4      /* attempts of an open BTRS draw evaluated side by side per round (the lowest accepted one counts) */
-struct chain_req { double p; int n; int owner; }; /* owner: thread | flip << 16 (x = n - x' for p > 1/2) */
+#define MMQ_CHAIN_SPEC 2      /* attempts of an open BTRS draw evaluated side by side per round */
+#define MMQ_CHAIN_NODES 8     /* nodes of a class on the last splitting level: 2^(ceil(log2 MMQ_CLS_CHAIN_DMAX) - 1) */
+#define MMQ_CHAIN_QCAP (MMQ_CHAIN_CLASSES * MMQ_CHAIN_NODES)
+struct chain_req { double p; int n; int owner; }; /* owner: thread | node << 8 | flip << 16 (x = n - x' for p > 1/2) */
 struct chain_smem {
-  chain_req qt[MMQ_CHAIN_CLASSES];      /* BTRS draws of this step */
-  chain_req qi[MMQ_CHAIN_CLASSES];      /* inversions and the trivial cases */
-  int open[2][MMQ_CHAIN_CLASSES];       /* BTRS draws not yet accepted (indices into qt), ping-pong over rounds */
-  int att[MMQ_CHAIN_CLASSES][MMQ_CHAIN_SPEC]; /* this round's attempts: x, or -1 rejected */
+  double p[MMQ_CLS_CHAIN_DMAX][MMQ_CHAIN_CLASSES];      /* mu of the members */
+  int cnt[2 * MMQ_CHAIN_NODES][MMQ_CHAIN_CLASSES];      /* fragments of the nodes of the current level */
+  int res[MMQ_CHAIN_NODES][MMQ_CHAIN_CLASSES];          /* left-half counts drawn on this level */
+  chain_req qt[MMQ_CHAIN_QCAP];                         /* BTRS draws of this level */
+  chain_req qi[MMQ_CHAIN_QCAP];                         /* inversions and the trivial cases */
+  int open[2][MMQ_CHAIN_QCAP];                          /* BTRS draws not yet accepted (indices into qt), ping-pong over rounds */
+  int att[MMQ_CHAIN_THREADS];                           /* this pass's attempts: x, or -1 rejected */
   uint32_t cid[MMQ_CHAIN_CLASSES];
-  int result[MMQ_CHAIN_CLASSES];
   int n[4]; /* BTRS draws, inversions, open[0], open[1] */
   int dmax;
 };
@@ -307,7 +313,8 @@ __global__ void __launch_bounds__(MMQ_CHAIN_THREADS)
 k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __restrict__ ck, const uint32_t* __restrict__ ccid,
               const unsigned long long* __restrict__ cdesc, uint32_t cid_hi, const double* __restrict__ mu,
               int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
-  __shared__ chain_smem S;
+  extern __shared__ __align__(16) unsigned char chain_raw[];
+  chain_smem& S = *reinterpret_cast<chain_smem*>(chain_raw);
   if (sweep_base) sweep += *sweep_base;
   const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
   constexpr int CW = MMQ_CHAIN_CLASSES / 32;
@@ -316,111 +323,137 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
     const int chunk = chunk0 + wib;
     int D = 0;
     const int32_t* pc = pcol;
-    int64_t rem = 0;
+    int kv = 0;
     uint32_t cid = 0;
     if (owner_warp && chunk < chunks) {
       const unsigned long long desc = cdesc[chunk];
       D = (int)(desc & 0xffull);
       pc = pcol + (desc >> 8) + lane;
-      rem = ck[(int64_t)chunk * 32 + lane];
+      kv = ck[(int64_t)chunk * 32 + lane];
       cid = ccid[(int64_t)chunk * 32 + lane];
     }
-    if (rem <= 0) D = 0; /* padding lane */
-    double norm = 0.0, sum_p = 0.0;
-    int last_pos = D - 1;
-    {
-      int lp = -1;
-      for (int j = 0; j < D; ++j) {
-        const double pj = mu[__ldg(pc + 32 * j)];
-        norm += pj;
-        if (pj > 0.0) lp = j;
-      }
-      if (lp >= 0) last_pos = lp;
-    }
-    __syncthreads(); /* the previous pass is done with S */
+    if (kv <= 0) D = 0; /* padding lane */
+    __syncthreads();    /* the previous pass is done with S */
     if (tid == 0) S.dmax = 0;
-    if (owner_warp) S.cid[tid] = cid;
+    if (owner_warp) {
+      S.cid[tid] = cid;
+      S.cnt[0][tid] = kv;
+      for (int j = 0; j < D; ++j) S.p[j][tid] = mu[__ldg(pc + 32 * j)];
+    }
     __syncthreads();
     {
       const int dm = __reduce_max_sync(0xffffffffu, D);
       if (lane == 0 && dm > 0) atomicMax(&S.dmax, dm);
     }
     __syncthreads();
-    const int dmax = S.dmax;
-    for (int j = 0; j < dmax; ++j) {
-      /* ---- what does this lane's class need for member j? */
-      int64_t x = 0;
-      bool pending = false, btrs = false;
-      double pj = 0.0, pr = 0.0;
-      int32_t cj = -1;
+    int levels = 0;
+    while ((1 << levels) < S.dmax) ++levels;
+    for (int L = 0; L < levels; ++L) {
+      const int nodes = 1 << L;
       if (tid < 4) S.n[tid] = 0;
-      if (j < D) {
-        cj = __ldg(pc + 32 * j);
-        pj = mu[cj];
-        if (j == last_pos) x = rem; /* zero-probability members never receive fragments */
-        else if (rem > 0 && pj > 0.0) {
-          const double denom = norm - sum_p;
-          pr = (denom > 0.0) ? pj / denom : 1.0;
-          if (pr > 1.0) pr = 1.0;
-          pending = true;
-          const double ph = pr > 0.5 ? 1.0 - pr : pr;
-          btrs = rem >= 2 && pr < 1.0 && (double)rem * ph >= MMQ_BINV_MEAN;
-        }
-      }
       __syncthreads();
+      /* ---- the nodes of this level: what has to be drawn? */
       if (owner_warp) {
-        const int pt = queue_slot(&S.n[0], pending && btrs, lane);
-        if (pt >= 0) { S.qt[pt].p = pr > 0.5 ? 1.0 - pr : pr; S.qt[pt].n = (int)rem; S.qt[pt].owner = tid | (pr > 0.5 ? 1 << 16 : 0); S.open[0][pt] = pt; }
-        const int pi = queue_slot(&S.n[1], pending && !btrs, lane);
-        if (pi >= 0) { S.qi[pi].p = pr; S.qi[pi].n = (int)rem; S.qi[pi].owner = tid; }
+        for (int i = 0; i < nodes; ++i) {
+          bool pending = false, btrs = false;
+          double pr = 0.0;
+          int n = 0;
+          if (D > 0) {
+            const int lo = MMQ_NODE_LO(i, L, D), hi = MMQ_NODE_LO(i + 1, L, D);
+            n = S.cnt[i][tid];
+            if (hi - lo >= 2) {
+              const int mid = MMQ_NODE_LO(2 * i + 1, L + 1, D);
+              if (mid == lo) S.res[i][tid] = 0;
+              else if (mid == hi) S.res[i][tid] = n;
+              else if (n == 0) S.res[i][tid] = 0;
+              else {
+                double left = 0.0, right = 0.0;
+                for (int j = lo; j < mid; ++j) left += S.p[j][tid];
+                for (int j = mid; j < hi; ++j) right += S.p[j][tid];
+                const double tot = left + right;
+                pr = tot > 0.0 ? left / tot : 0.0;
+                if (pr > 1.0) pr = 1.0;
+                pending = true;
+                const double ph = pr > 0.5 ? 1.0 - pr : pr;
+                btrs = n >= 2 && pr > 0.0 && pr < 1.0 && (double)n * ph >= MMQ_BINV_MEAN;
+              }
+            }
+          }
+          const int pt = queue_slot(&S.n[0], pending && btrs, lane);
+          if (pt >= 0) { S.qt[pt].p = pr > 0.5 ? 1.0 - pr : pr; S.qt[pt].n = n; S.qt[pt].owner = tid | (i << 8) | (pr > 0.5 ? 1 << 16 : 0); S.open[0][pt] = pt; }
+          const int pi = queue_slot(&S.n[1], pending && !btrs, lane);
+          if (pi >= 0) { S.qi[pi].p = pr; S.qi[pi].n = n; S.qi[pi].owner = tid | (i << 8); }
+        }
       }
       __syncthreads();
       /* ---- round r: attempts SPEC r .. SPEC r + SPEC - 1 of every open BTRS draw, one per thread; in round 0 the
-       * remaining threads do the inversions (mean below 10), single fragments and p == 1 */
-      const int nt = S.n[0], ni = S.n[1];
-      int nopen = nt;
+       * threads after them do the inversions (mean below 10), single fragments and p == 0 or 1 */
+      const uint32_t heap = (uint32_t)nodes;
+      const int ni = S.n[1];
+      int nopen = S.n[0];
       for (uint32_t r = 0; nopen > 0 || (r == 0 && ni > 0); ++r) {
-        const int work = nopen * MMQ_CHAIN_SPEC;
-        for (int wi = tid; wi < work + (r == 0 ? ni : 0); wi += MMQ_CHAIN_THREADS) {
+        const int work = nopen * MMQ_CHAIN_SPEC, extra = r == 0 ? ni : 0;
+        if (tid == 0) S.n[2 + ((r + 1) & 1)] = 0;
+        for (int w0 = 0; w0 < work + extra; w0 += MMQ_CHAIN_THREADS) { /* passes of one work item per thread */
+          const int wi = w0 + tid;
           if (wi < work) {
-            const int req = S.open[r & 1][wi / MMQ_CHAIN_SPEC];
-            const chain_req q = S.qt[req];
+            const chain_req q = S.qt[S.open[r & 1][wi / MMQ_CHAIN_SPEC]];
             mmq_rng g;
-            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner & 0xffff], sweep);
+            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner & 0xff], sweep);
             int64_t xb = 0;
-            const bool ok = mmq_btrs_attempt(&g, MMQ_CHAIN_BLOCK(j) + r * MMQ_CHAIN_SPEC + (uint32_t)(wi % MMQ_CHAIN_SPEC), mmq_btrs_setup(q.n, q.p), &xb) != 0;
-            S.att[req][wi % MMQ_CHAIN_SPEC] = ok ? (int)xb : -1;
-          } else {
+            const bool ok = mmq_btrs_attempt(&g, MMQ_CHAIN_BLOCK(heap + ((q.owner >> 8) & 0xff)) + r * MMQ_CHAIN_SPEC + (uint32_t)(wi % MMQ_CHAIN_SPEC),
+                                             mmq_btrs_setup(q.n, q.p), &xb) != 0;
+            S.att[tid] = ok ? (int)xb : -1;
+          } else if (wi < work + extra) {
             const chain_req q = S.qi[wi - work];
             mmq_rng g;
-            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner], sweep);
-            S.result[q.owner] = (int)mmq_binomial(&g, MMQ_CHAIN_BLOCK(j), q.n, q.p);
+            mmq_rng_init(&g, seed, MMQ_STREAM_ALLOC, ((uint64_t)cid_hi << 32) | S.cid[q.owner & 0xff], sweep);
+            S.res[(q.owner >> 8) & 0xff][q.owner & 0xff] = (int)mmq_binomial(&g, MMQ_CHAIN_BLOCK(heap + ((q.owner >> 8) & 0xff)), q.n, q.p);
           }
-        }
-        if (tid == 0) S.n[2 + ((r + 1) & 1)] = 0;
-        __syncthreads();
-        if ((tid & ~31) < nopen) {
-          bool again = false;
-          int req = 0;
-          if (tid < nopen) {
-            req = S.open[r & 1][tid];
-            int xa = -1;
+          __syncthreads();
+          /* the first thread of each draw of this pass takes the lowest accepted attempt, or re-queues the draw */
+          if ((w0 + (tid & ~31)) < work) {
+            bool again = false;
+            int req = 0;
+            if (wi < work && tid % MMQ_CHAIN_SPEC == 0) {
+              req = S.open[r & 1][wi / MMQ_CHAIN_SPEC];
+              int xa = -1;
 #pragma unroll
-            for (int sp = MMQ_CHAIN_SPEC - 1; sp >= 0; --sp) if (S.att[req][sp] >= 0) xa = S.att[req][sp]; /* the lowest accepted attempt */
-            if (xa >= 0) { const chain_req q = S.qt[req]; S.result[q.owner & 0xffff] = (q.owner >> 16) ? q.n - xa : xa; }
-            else again = true;
+              for (int sp = MMQ_CHAIN_SPEC - 1; sp >= 0; --sp) if (S.att[tid + sp] >= 0) xa = S.att[tid + sp];
+              if (xa >= 0) { const chain_req q = S.qt[req]; S.res[(q.owner >> 8) & 0xff][q.owner & 0xff] = (q.owner >> 16) ? q.n - xa : xa; }
+              else again = true;
+            }
+            const int pos = queue_slot(&S.n[2 + ((r + 1) & 1)], again, lane);
+            if (pos >= 0) S.open[(r + 1) & 1][pos] = req;
           }
-          const int pos = queue_slot(&S.n[2 + ((r + 1) & 1)], again, lane);
-          if (pos >= 0) S.open[(r + 1) & 1][pos] = req;
+          __syncthreads();
         }
-        __syncthreads();
         nopen = S.n[2 + ((r + 1) & 1)];
+        __syncthreads();
       }
-      __syncthreads();
-      if (pending) x = S.result[tid];
-      if (x != 0) atomicAdd(counts + cj, (int32_t)x);
-      rem -= x;
-      sum_p += pj;
+      /* ---- split: children 2 i and 2 i + 1 of node i (in place, from the top: 2 i >= i) */
+      if (owner_warp && D > 0) {
+        for (int i = nodes - 1; i >= 0; --i) {
+          const int lo = MMQ_NODE_LO(i, L, D), hi = MMQ_NODE_LO(i + 1, L, D);
+          const int n = S.cnt[i][tid];
+          int nl = 0;
+          if (hi - lo >= 2) nl = S.res[i][tid];
+          else if (hi - lo == 1) nl = MMQ_NODE_LO(2 * i + 1, L + 1, D) == hi ? n : 0; /* a single member: it stays in the half that contains it */
+          S.cnt[2 * i][tid] = nl;
+          S.cnt[2 * i + 1][tid] = n - nl;
+        }
+      }
+    }
+    __syncthreads();
+    if (owner_warp && D > 0) {
+      const int nodes = 1 << levels;
+      for (int i = 0; i < nodes; ++i) {
+        const int lo = MMQ_NODE_LO(i, levels, D), hi = MMQ_NODE_LO(i + 1, levels, D);
+        if (hi > lo) {
+          const int x = S.cnt[i][tid];
+          if (x != 0) atomicAdd(counts + __ldg(pc + 32 * lo), x);
+        }
+      }
     }
   }
 }
@@ -568,7 +601,8 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
     MMQ_CUDA(h, cudaStreamWaitEvent(h->stream4, h->ev_fork, 0));
     constexpr int CW = MMQ_CHAIN_CLASSES / 32;
     const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, cap(1, 3));
-    k_alloc_chain<<<grid, MMQ_CHAIN_THREADS, 0, h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
+    MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain_smem)));
+    k_alloc_chain<<<grid, MMQ_CHAIN_THREADS, sizeof(chain_smem), h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
                                                               h->mu, h->counts, seed, sweep, sweep_base);
     MMQ_LAUNCHED(h);
     MMQ_CUDA(h, cudaEventRecord(h->ev_join4, h->stream4));

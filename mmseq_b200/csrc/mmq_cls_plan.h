@@ -21,6 +21,7 @@
 #define MMQ_CLS_DMAX 64  /* longer classes go to the general kernel */
 #define MMQ_CLS_DLO 8    /* class sizes 2..8: the 64-register instance (32 warps per SM) */
 #define MMQ_CLS_DREG 16  /* class sizes up to this are register-resident template instances */
+#define MMQ_CLS_CHAIN_DMAX 16 /* classes with more fragments than mmq_cat_limit(d): up to this size k_alloc_chain, above it the general kernel */
 #define MMQ_CLS_WARPS 4
 /* draws per slot of a class with d members: 64 (16 Philox blocks) for the small sizes; 16 for the larger ones, whose
  * slots cost 4 (d - 1) compare-and-add pairs per block — a 64-draw slot of a 16-member class is ~16 us of dependent work
@@ -135,7 +136,7 @@ static bool mmq_cls_build_host(int64_t n, int64_t m, const int64_t* rp, const in
           key16[i] = (int16_t)(d * MMQ_CLS_NQ + (tail ? 16 - (int)((tail + 3) >> 2) : 16 - (int)(grp / 4)));
           if (tail) ++t.key_count[key16[i]];
         }
-      } else if (d <= MMQ_CLS_DMAX) { key16[i] = -3; ++t.n_chain; }
+      } else if (d <= MMQ_CLS_CHAIN_DMAX) { key16[i] = -3; ++t.n_chain; }
       else { key16[i] = -2; ++t.n_rest; t.nnz_rest += d; }
     }
   });
