@@ -41,7 +41,7 @@ def test_plan_replay_equals_canonical_replay(monkeypatch, threads, cid_base):
         _, c_o, _ = P.sweep_replay(mu, 4321, sweep, class_id_base=cid_base, do_gamma=False)
         c_p, st = P.cls_plan_replay(mu, 4321, sweep, class_id_base=cid_base)
         # three sets: k <= 64 (one slot each), k > 64 with <= 64 members (chain set), more than 64 members (rest)
-        assert st["in_use"] == 1 and st["small_classes"] > 4000 and st["rest_classes"] == 20 and st["chain_classes"] > 200
+        assert st["in_use"] == 1 and st["small_classes"] > 4000 and st["rest_classes"] >= 20 and st["chain_classes"] > 150
         assert st["class_slots"] % 32 == 0 and st["class_slots"] >= st["small_classes"] and st["chain_slots"] % 32 == 0
         assert c_p.sum() == k.sum()
         assert np.array_equal(c_p, c_o)

@@ -273,7 +273,7 @@ def test_class_plan_kernel_bit_exact(monkeypatch, cid_base, plan_threads):
     P = orc.Problem(row_ptr, col, k, l)
     with capi.Handle(row_ptr, col, k, l, class_id_base=cid_base) as H:
         st = H.cls_stats()
-        assert st["in_use"] == 1 and st["small_classes"] > 4000 and st["rest_classes"] == 20 and st["chain_classes"] > 200
+        assert st["in_use"] == 1 and st["small_classes"] > 4000 and st["rest_classes"] >= 20 and st["chain_classes"] > 150
         assert st["class_slots"] >= st["small_classes"] and st["chain_slots"] % 32 == 0
         for sweep in (0, 1, 7):
             H.set_mu(mu)
