@@ -280,7 +280,7 @@ k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, c
 /* The chain set: classes with more than mmq_cat_limit(d) fragments — the multinomial by conditional binomials
  * (gsl_ran_multinomial, src/mmseq.cpp:880), O(d) binomials per class whatever k is, in the balanced splitting order of
  * mmq_alloc_chain (include/mmq_sampler.h): ceil(log2 d) levels, the binomials of a level independent of each other.
- * One class per lane of the block's first warp, 32 classes of equal size per chunk (member-major like the small
+ * One class per lane of the block's first four warps, 32 classes of equal size per chunk (member-major like the small
  * set, so every column load of a warp is one 128-byte line), longest classes first.
  *
  * A binomial is a rejection sampler (BTRS above a mean of 10) or an inversion loop of data-dependent length (BINV
@@ -291,9 +291,9 @@ k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, c
  * attempts in rounds, MMQ_CHAIN_SPEC attempts of every open draw side by side (the lowest accepted one counts), the
  * rejected ones re-queued; the inversions on the remaining threads of the first round.  Same integers as the CPU
  * replay's mmq_alloc_chain. */
-#define MMQ_CHAIN_THREADS 128 /* threads per block */
-#define MMQ_CHAIN_CLASSES 32  /* classes per block pass: the lanes of warp 0 (the other warps only work in the dense phases) */
-#define MMQ_CHAIN_SPEC 4      /* most attempts of an open BTRS draw evaluated side by side per round (as many as there are idle threads) */
+#define MMQ_CHAIN_THREADS 256 /* threads per block */
+#define MMQ_CHAIN_CLASSES 128 /* classes per block pass: the lanes of warps 0..3 (the other warps only work in the dense phases) */
+#define MMQ_CHAIN_SPEC 2      /* attempts of an open BTRS draw evaluated side by side per round */
 #define MMQ_CHAIN_NODES 8     /* nodes of a class on the last splitting level: 2^(ceil(log2 MMQ_CLS_CHAIN_DMAX) - 1) */
 #define MMQ_CHAIN_QCAP (MMQ_CHAIN_CLASSES * MMQ_CHAIN_NODES)
 struct chain_req { double p; int n; int owner; }; /* owner: thread | node << 8 | flip << 16 (x = n - x' for p > 1/2) */
@@ -393,9 +393,10 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
       int nopen = S.n[0];
       uint32_t rr = 0; /* rounds: open[(rr + 1) & 1] is read, open[rr & 1] written */
       for (uint32_t r = 0; nopen > 0 || (r == 0 && ni > 0); ++r, ++rr) {
-        /* attempts per open draw this round: as many as fit one pass of the block (speculation: only the lowest accepted
-         * attempt counts, so the result does not depend on it) */
-        const int spec = nopen * 4 <= MMQ_CHAIN_THREADS ? 4 : nopen * 2 <= MMQ_CHAIN_THREADS ? 2 : 1;
+        /* attempts per open draw this round (speculation: only the lowest accepted attempt counts, so the result does not
+         * depend on it): measured on the config-2 sample, 2 is the best trade between rounds and issue slots taken from the
+         * concurrent class kernels (4 with 32-class blocks: 11.0 M instead of 7.1 M warp instructions, the sweep 15 % slower) */
+        const int spec = MMQ_CHAIN_SPEC;
         const int work = nopen * spec, extra = r == 0 ? ni : 0;
         if (tid == 0) S.n[2 + (rr & 1)] = 0;
         for (int w0 = 0; w0 < work + extra; w0 += MMQ_CHAIN_THREADS) { /* passes of one work item per thread */
@@ -603,7 +604,7 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
   if (do_chain) { /* the longest dependent chains: first in */
     MMQ_CUDA(h, cudaStreamWaitEvent(h->stream4, h->ev_fork, 0));
     constexpr int CW = MMQ_CHAIN_CLASSES / 32;
-    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, cap(1, 6));
+    const int grid = (int)std::min<int64_t>((h->cls_c_chunks + CW - 1) / CW, cap(1, 3));
     MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain_smem)));
     k_alloc_chain<<<grid, MMQ_CHAIN_THREADS, sizeof(chain_smem), h->stream4>>>((int)h->cls_c_chunks, h->cls_c_pcol, h->cls_c_k, h->cls_c_cid, h->cls_c_desc, h->cls_cid_hi,
                                                               h->mu, h->counts, seed, sweep, sweep_base);
