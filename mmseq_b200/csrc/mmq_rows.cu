@@ -117,45 +117,33 @@ __device__ __forceinline__ void rows_chunk(int row_lo, int vrows, int s0, unsign
 #pragma unroll
     for (int j = 0; j < D; ++j) wv[j] = __ldg(wp + j * (MMQ_ROWS_CHUNK / 4));
   }
-  double g[D], S[HAS_W ? 1 : D];
-  const int32_t* cp = setp;
-  int cur = -2; /* no set yet (-1 is the dummy set in front of a run) */
-  int s = s0;
+  /* the set of each of the lane's four rows; straight-line code: a row always re-reads its set's columns and mu (L1 hits
+   * when the set repeats) — cheaper than branching on "same set as the row before" (measured: the divergent reload
+   * branches and their reconvergence were 12 % of the instructions of the first version) */
+  int sr[4];
+  sr[0] = s0; /* -1: the dummy rows in front of a run (clamped where it is used) */
+#pragma unroll
+  for (int i = 1; i < 4; ++i) sr[i] = sr[i - 1] + (int)((nb >> (i - 1)) & 1u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    if (i > 0) s += (int)((nb >> (i - 1)) & 1u);
-    const bool fresh = s != cur;
-    if (fresh) { /* a new set: its columns (a few contiguous words, mostly L1 hits) and mu */
-      cur = s;
-      cp = setp + (int64_t)(s < 0 ? 0 : s) * D;
+    const int32_t* cp = setp + (int64_t)(sr[i] < 0 ? 0 : sr[i]) * D;
+    double p[D];
 #pragma unroll
-      for (int j = 0; j < D; ++j) g[j] = mu[__ldg(cp + j)];
+    for (int j = 0; j < D; ++j) {
+      const double gj = mu[__ldg(cp + j)];
+      if (HAS_W) {
+        const float wf = i == 0 ? wv[j].x : i == 1 ? wv[j].y : i == 2 ? wv[j].z : wv[j].w;
+        p[j] = gj * rows_w2d(wf);
+      } else {
+        p[j] = gj;
+      }
     }
+#pragma unroll
+    for (int j = 1; j < D; ++j) p[j] = p[j - 1] + p[j]; /* running sums, left to right */
+    const double target = mmq_uniform32(i == 0 ? wq4.x : i == 1 ? wq4.y : i == 2 ? wq4.z : wq4.w) * p[D - 1];
     int chosen = D - 1;
-    if (HAS_W) { /* two passes over the members (the products are formed twice) instead of D stored sums: registers */
-      double norm = 0.0;
 #pragma unroll
-      for (int j = 0; j < D; ++j) {
-        const float wf = i == 0 ? wv[j].x : i == 1 ? wv[j].y : i == 2 ? wv[j].z : wv[j].w;
-        norm += g[j] * rows_w2d(wf);
-      }
-      const double target = mmq_uniform32(i == 0 ? wq4.x : i == 1 ? wq4.y : i == 2 ? wq4.z : wq4.w) * norm;
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < D - 1; ++j) {
-        const float wf = i == 0 ? wv[j].x : i == 1 ? wv[j].y : i == 2 ? wv[j].z : wv[j].w;
-        acc += g[j] * rows_w2d(wf);
-        chosen -= (target < acc) ? 1 : 0; /* the sums are non-decreasing: first j with target < S_j */
-      }
-    } else {
-      if (fresh) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) S[j] = j ? S[j - 1] + g[j] : g[j];
-      }
-      const double target = mmq_uniform32(i == 0 ? wq4.x : i == 1 ? wq4.y : i == 2 ? wq4.z : wq4.w) * S[D - 1];
-#pragma unroll
-      for (int j = 0; j < D - 1; ++j) chosen -= (target < S[j]) ? 1 : 0;
-    }
+    for (int j = 0; j < D - 1; ++j) chosen -= (target < p[j]) ? 1 : 0; /* non-decreasing: first j with target < S_j */
     const int vr = vrow0 + i;
     cat_red(counts, (vr >= row_lo && vr < vrows) ? __ldg(cp + chosen) : -1, lane);
   }
@@ -402,8 +390,8 @@ int mmq_rows_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t
     else MMQ_ROWS_GO(false, true, 4, csmall, chunks);
   }
   if (csmall > 0) {
-    if (h->has_w) MMQ_ROWS_GO(true, false, 4, 0, csmall);
-    else MMQ_ROWS_GO(false, false, 5, 0, csmall);
+    if (h->has_w) MMQ_ROWS_GO(true, false, 5, 0, csmall);
+    else MMQ_ROWS_GO(false, false, 8, 0, csmall);
   }
 #undef MMQ_ROWS_GO
   g_mmq_launches.fetch_sub(1, std::memory_order_relaxed); /* the caller counts one */
