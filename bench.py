@@ -475,7 +475,7 @@ def extra_weighted_line(args, dev, stream, peak):
     H = capi.Handle(h.row_ptr, h.col, None, w.length, weight=h.w, device=dev.index)
     H.set_stream(stream.cuda_stream)
     H.init_mu()
-    rows = H.rows_stats() if hasattr(H, "rows_stats") else None
+    rows = None   # the row plan (MMQ_GIBBS_ROWS_KERNEL) is not the default: measured no faster than the segment kernel
     barrier = lambda: torch.cuda.synchronize()
     ms, alloc_ms, alloc_n, gamma_ms, gamma_n, launches, clocks = timed_run(args, H, w, stream, dev, barrier, 5, 3, None, capi.MMQ_GIBBS_DEFAULT)
     H.close()
@@ -553,7 +553,7 @@ def main():
     em_s = time.perf_counter() - t0
     mu_em = H.get_mu()
     cls = H.cls_stats() if h.k is not None else None
-    rows = H.rows_stats() if (h.k is None and hasattr(H, "rows_stats")) else None
+    rows = None
 
     K, W, S = args.steps, args.warmup, SWEEPS_PER_STEP
     ms, alloc_ms, alloc_n, gamma_ms, gamma_n, launches, clocks = timed_run(args, H, w, stream, dev, barrier, K, W, flush_buf, flags)

@@ -15,7 +15,7 @@ MMQ_GIBBS_NO_GRAPH = 2
 MMQ_GIBBS_TIME_KERNELS = 4
 MMQ_GIBBS_GENERIC_KERNEL = 8
 MMQ_GIBBS_RAGGED_KERNEL = 16
-MMQ_GIBBS_SEG_KERNEL = 32
+MMQ_GIBBS_ROWS_KERNEL = 64
 MMQ_GROUP_IDENTICAL = 0
 MMQ_GROUP_GENE = 1
 

@@ -1025,7 +1025,6 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
   if (h->has_k) CREATE_TRY(build_tiles(h, p->row_ptr)); /* k == 1 shards build them on first use of the general kernel */
   tick("tiles");
   if (!h->has_k) CREATE_TRY(mmq_seg_plan(h));
-  if (!h->has_k) CREATE_TRY(mmq_rows_plan(h));
   if (h->has_k) CREATE_TRY(mmq_cls_plan(h, p));
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
   tick("segment / class plan");
@@ -1388,8 +1387,9 @@ static int prepare_sweep(mmq_handle* h, int flags) {
     if ((rc = ensure_x(h))) return rc;
     if ((rc = build_transpose(h))) return rc;
   }
-  if (!transposed && h->seg_ready && (!h->rows_ready || (flags & MMQ_GIBBS_SEG_KERNEL)) && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL)) &&
-      (rc = mmq_seg_pack(h))) return rc; /* the segment kernel's packed copies (allocation: not inside a capture) */
+  const bool fast = !transposed && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL));
+  if (fast && (flags & MMQ_GIBBS_ROWS_KERNEL) && !h->rows_ready && !h->rows_tried && (rc = mmq_rows_plan(h))) return rc; /* built on first use */
+  if (fast && h->seg_ready && !((flags & MMQ_GIBBS_ROWS_KERNEL) && h->rows_ready) && (rc = mmq_seg_pack(h))) return rc; /* allocations: not inside a capture */
   return MMQ_OK;
 }
 
@@ -1407,8 +1407,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
     v.push_back(e);
   };
   if (h->m > 0) {
-    const bool needs_tiles = transposed || h->has_k || (flags & MMQ_GIBBS_GENERIC_KERNEL);
-    if (needs_tiles && (rc = build_tiles(h, nullptr))) return rc;
+    if (!sweep_base && (rc = prepare_sweep(h, flags))) return rc; /* (a graph capture prepares before it begins) */
     const int grid = (int)std::min<int64_t>(std::max<int64_t>((h->n_tiles + MMQ_ALLOC_WARPS - 1) / MMQ_ALLOC_WARPS, 1), (int64_t)h->num_sms * 3);
     if (transposed) {
       if ((rc = ensure_x(h))) return rc;
@@ -1421,7 +1420,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
       MMQ_LAUNCHED(h);
     } else {
       mark(h->ev_alloc);
-      if (h->rows_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL | MMQ_GIBBS_SEG_KERNEL))) {
+      if (h->rows_ready && (flags & MMQ_GIBBS_ROWS_KERNEL) && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
         if ((rc = mmq_rows_launch(h, seed, sweep, sweep_base))) return rc;
       } else if (h->seg_ready && !(flags & (MMQ_GIBBS_GENERIC_KERNEL | MMQ_GIBBS_RAGGED_KERNEL))) {
         if ((rc = mmq_seg_launch(h, seed, sweep, sweep_base))) return rc;

@@ -107,7 +107,7 @@ struct mmq_handle {
   std::vector<mmq_seg> seg_host; /* the table, kept for the lazy packing (mmq_seg_pack) */
 
   /* row plan for by-length k == 1 shards (mmq_rows.cu): columns once per run of identical rows, weights member-major */
-  bool rows_ready = false;
+  bool rows_ready = false, rows_tried = false;
   void* rows_runs = nullptr; /* mmq_rows_run[] */
   void* rows_meta = nullptr; /* mmq_rows_meta[] */
   int32_t* rows_set_col = nullptr;

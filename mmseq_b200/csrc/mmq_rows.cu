@@ -5,8 +5,8 @@
  *
  * What is compulsory per sweep in such a shard is ONE fp32 weight per hit; the transcript indices are not:
  * the 30 M fragments of the config-2 sample fall into 3.6 M distinct hit classes, so consecutive rows
- * mostly repeat the previous row's columns.  The row plan (built once in mmq_create, on the device)
- * therefore stores
+ * mostly repeat the previous row's columns.  The row plan (built on the device the first time a sweep asks for it:
+ * MMQ_GIBBS_ROWS_KERNEL) therefore stores
  *   - the columns ONCE per run of identical rows ("set"), set-major;
  *   - the weights member-major in chunks of 128 rows (entry (j, r) of a chunk at 128 j + r), so that a lane's
  *     four rows are one 16-byte load per member and a warp's load is 512 contiguous bytes;
@@ -19,7 +19,12 @@
  * replay's bit for bit (tests/test_gpu_parity.py).
  *
  * Algorithmic HBM bytes per sweep: 4 B per weight slot + 4 B per set column + 32 B per chunk
- * (mmq_rows_stats; the round-1 segment kernel streamed 8 B per hit).
+ * (mmq_rows_stats; the segment kernel of mmq_seg.cu streams 8 B per hit).
+ *
+ * STATUS (round 2, measured on the config-2 sample, profiles/README.md): 1.6x fewer bytes than the segment kernel but
+ * no faster — 247 against 245 us per sweep with weights, 177 against 145 us without: the kernel is bound by instruction
+ * issue (about 420 warp instructions per 128 rows), not by HBM.  The segment kernel therefore stays the default for
+ * these shards; this one runs when MMQ_GIBBS_ROWS_KERNEL is passed.
  */
 #include <cub/cub.cuh>
 
@@ -223,14 +228,21 @@ k_alloc_rows(const mmq_rows_run* __restrict__ runs, int nruns, int chunk_begin, 
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int nwarps = gridDim.x * MMQ_ROWS_WARPS;
-  for (int chunk = chunk_begin + blockIdx.x * MMQ_ROWS_WARPS + (threadIdx.x >> 5); chunk < chunks; chunk += nwarps) {
+  /* the chunk's 32 bytes of metadata are fetched one chunk ahead: their latency is off the critical path */
+  int chunk = chunk_begin + blockIdx.x * MMQ_ROWS_WARPS + (threadIdx.x >> 5);
+  uint4 ma = make_uint4(0u, 0u, 0u, 0u), mb = ma;
+  if (chunk < chunks) {
+    const uint4* mp = reinterpret_cast<const uint4*>(meta + chunk); /* the same 32 bytes for all lanes: one transaction */
+    ma = __ldg(mp); mb = __ldg(mp + 1);
+  }
+  for (; chunk < chunks; chunk += nwarps) {
     mmq_rows_meta M;
-    {
-      const uint4* mp = reinterpret_cast<const uint4*>(meta + chunk); /* the same 32 bytes for all lanes: one transaction */
-      const uint4 a = __ldg(mp), b = __ldg(mp + 1);
-      M.mask[0] = a.x; M.mask[1] = a.y; M.mask[2] = a.z; M.mask[3] = a.w;
-      M.set_first = (int32_t)b.x; M.run = (int32_t)b.y;
-      M.woff = (int64_t)(((unsigned long long)b.w << 32) | b.z);
+    M.mask[0] = ma.x; M.mask[1] = ma.y; M.mask[2] = ma.z; M.mask[3] = ma.w;
+    M.set_first = (int32_t)mb.x; M.run = (int32_t)mb.y;
+    M.woff = (int64_t)(((unsigned long long)mb.w << 32) | mb.z);
+    if (chunk + nwarps < chunks) {
+      const uint4* mp = reinterpret_cast<const uint4*>(meta + chunk + nwarps);
+      ma = __ldg(mp); mb = __ldg(mp + 1);
     }
     const mmq_rows_run& R = s_run[M.run];
     const int vrow0 = (chunk - R.chunk0) * MMQ_ROWS_CHUNK + 4 * lane;
@@ -272,6 +284,7 @@ k_alloc_rows(const mmq_rows_run* __restrict__ runs, int nruns, int chunk_begin, 
 
 int mmq_rows_plan(mmq_handle* h) {
   h->rows_ready = false;
+  h->rows_tried = true;
   static const bool off = [] { const char* e = getenv("MMQ_ROWS_OFF"); return e && atoi(e) != 0; }();
   if (off || !h->seg_scan_ok || h->has_k || h->m == 0) return MMQ_OK;
   std::vector<mmq_rows_run> runs;
@@ -359,8 +372,13 @@ int mmq_rows_plan(mmq_handle* h) {
   return MMQ_OK;
 }
 
-extern "C" int mmq_rows_stats(const mmq_handle* h, int64_t out[8]) {
+extern "C" int mmq_rows_stats(mmq_handle* h, int64_t out[8]) {
   if (!h || !out) return MMQ_ERR_ARG;
+  if (!h->rows_ready && !h->rows_tried && !h->has_k) { /* the plan is built on first use */
+    MMQ_CUDA(h, cudaSetDevice(h->device));
+    int rc = mmq_rows_plan(h);
+    if (rc) return rc;
+  }
   out[0] = h->rows_ready ? 1 : 0;
   out[1] = h->rows_rows;
   out[2] = h->rows_sets;

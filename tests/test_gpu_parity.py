@@ -117,12 +117,12 @@ def test_by_length_layout_segment_kernel(small_synth, weighted, cid_base):
     P = orc.Problem(h.row_ptr, h.col, None, h.len, weight=h.w)
     mu, _, _ = P.init_mu()
     with capi.Handle(h.row_ptr, h.col, None, h.len, weight=h.w, class_id_base=cid_base) as H:
-        st = H.rows_stats()   # the row plan (mmq_rows.cu) is the default for this layout: columns once per run of identical rows
+        st = H.rows_stats()   # the row plan (mmq_rows.cu, MMQ_GIBBS_ROWS_KERNEL): columns once per run of identical rows
         assert st["in_use"] == 1 and st["rows"] + st["singleton_rows"] == h.m and 0 < st["sets"] < st["rows"]
         assert (st["weight_slots"] > 0) == weighted and st["bytes_per_sweep"] < (8 if weighted else 4) * h.nnz
         for sweep in range(3):
             _, c_o, mu_o = P.sweep_replay(mu, SEED, sweep, class_id_base=cid_base)
-            for flags in (capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_SEG_KERNEL, capi.MMQ_GIBBS_RAGGED_KERNEL, capi.MMQ_GIBBS_GENERIC_KERNEL,
+            for flags in (capi.MMQ_GIBBS_DEFAULT, capi.MMQ_GIBBS_ROWS_KERNEL, capi.MMQ_GIBBS_RAGGED_KERNEL, capi.MMQ_GIBBS_GENERIC_KERNEL,
                           capi.MMQ_GIBBS_TRANSPOSED, capi.MMQ_GIBBS_DEFAULT):
                 H.set_mu(mu)
                 _, c, mu_g = H.sweep_debug(SEED, sweep, flags, want_x=False)
@@ -151,7 +151,7 @@ def test_row_plan_zero_weights(small_synth):
         for sweep in range(2):
             H.set_mu(mu)
             _, c_o, mu_o = P.sweep_replay(mu, SEED, sweep)
-            _, c, mu_g = H.sweep_debug(SEED, sweep, capi.MMQ_GIBBS_DEFAULT, want_x=False)
+            _, c, mu_g = H.sweep_debug(SEED, sweep, capi.MMQ_GIBBS_ROWS_KERNEL, want_x=False)
             assert np.array_equal(c, c_o) and np.array_equal(mu_g, mu_o)
 
 

@@ -15,7 +15,7 @@ for weights in (False, True):
     H.init_mu()
     mu0 = H.get_mu()
     st = H.rows_stats()
-    for name, flags in (("rows", capi.MMQ_GIBBS_DEFAULT), ("seg4", capi.MMQ_GIBBS_SEG_KERNEL)):
+    for name, flags in (("rows", capi.MMQ_GIBBS_ROWS_KERNEL), ("seg4", capi.MMQ_GIBBS_DEFAULT)):
         H.set_mu(mu0)
         H.gibbs(1234, 0, 16, stride=16, trace_len=8, flags=flags | capi.MMQ_GIBBS_NO_GRAPH)
         H.kernel_times()
