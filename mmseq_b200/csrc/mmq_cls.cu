@@ -34,6 +34,8 @@
  * Algorithmic HBM bytes per sweep: 4 B per packed column slot + 6 B per slot (draw count and slot
  * number in two bytes, low word of the class id) of the small set + the sub-CSR of the rest.
  */
+#include <cub/cub.cuh>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -462,6 +464,12 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
   }
 }
 
+__global__ void k_iota_u32(uint32_t* __restrict__ v, int64_t count) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) v[i] = (uint32_t)i;
+}
+__global__ void k_fill_i32_cls(int32_t* __restrict__ p, int64_t count, int32_t v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
 __global__ void k_cls_singletons(const int32_t* __restrict__ col1, const int32_t* __restrict__ k1, int64_t count,
                                  int32_t* __restrict__ base) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
@@ -478,10 +486,302 @@ static int cls_upload(mmq_handle* h, T** dst, const std::vector<T>& v) {
   return MMQ_OK;
 }
 
+/* ------------------------------------------------------------------ the plan, built on the device
+ * The host builder of mmq_cls_plan.h (kept: the CPU tests replay it, MMQ_CLS_HOST_PLAN=1 selects it) takes ~100 ms for
+ * the 3.6 M classes of the config-2 sample plus the upload of 124 MB from pageable memory — more than the 320 sweeps of
+ * a default bench run.  The CSR is on the device already, so the same plan is made there:
+ *   1. k_clsb_classify: per class its set, its number of slots; singletons are summed into seg_base[];
+ *   2. exclusive scan of the slot counts; k_clsb_slots writes one 64-bit sort key per slot
+ *      (pseudo size | 16 - Philox blocks | first member) — the chain set sorts behind the small set by descending size;
+ *   3. one stable radix sort (cub); run boundaries of equal pseudo size come back to the host (<= 146 integers), which
+ *      lays out runs and chunks;
+ *   4. k_clsb_fill scatters columns, draw counts and class ids into the member-major chunks.
+ * The few classes with more than MMQ_CLS_DMAX members (or above the chain kernel's size) are listed by the host. */
+#define MMQ_CLSB_DPC0 MMQ_CLS_DP_END                         /* pseudo sizes of the chain set: DPC0 + (CHAIN_DMAX - d) */
+#define MMQ_CLSB_NDP (MMQ_CLS_DP_END + MMQ_CLS_CHAIN_DMAX + 1)
+struct clsb_run { long long e0; int first, chunk0, d, pad; }; /* per pseudo size: column offset, first sorted slot, first chunk */
+
+__device__ __forceinline__ int clsb_set_of(int64_t d, int64_t kv) { /* 0 nothing to draw, 1 small, 2 chain, 3 rest */
+  if (d == 1 || kv <= 0) return 0;
+  if (d <= MMQ_CLS_DMAX && kv <= mmq_cat_limit((int)d)) return 1;
+  return d <= MMQ_CLS_CHAIN_DMAX ? 2 : 3;
+}
+__global__ void k_clsb_classify(const int64_t* __restrict__ rp, const int32_t* __restrict__ col, const int32_t* __restrict__ kk,
+                                const int64_t* __restrict__ class_id, int64_t cid_base, uint32_t cid_hi, int64_t m,
+                                int32_t* __restrict__ nslots, int32_t* __restrict__ base, int* __restrict__ info) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t d = rp[i + 1] - rp[i], kv = kk[i];
+    const uint64_t cid = (uint64_t)(class_id ? class_id[i] : cid_base + i);
+    if ((uint32_t)(cid >> 32) != cid_hi || kv < 0) atomicOr(info, 1); /* the plan does not apply */
+    const int set = clsb_set_of(d, kv);
+    int ns = 0;
+    if (set == 0) { if (d == 1 && kv > 0) { atomicAdd(base + col[rp[i]], (int32_t)kv); atomicOr(info + 1, 1); } }
+    else if (set == 1) ns = kv == 1 ? 1 : (int)((kv + MMQ_CLS_GROUP(d) - 1) / MMQ_CLS_GROUP(d));
+    else if (set == 2) ns = 1;
+    else { atomicAdd(info + 2, 1); }
+    nslots[i] = ns;
+  }
+}
+__global__ void k_clsb_slots(const int64_t* __restrict__ rp, const int32_t* __restrict__ col, const int32_t* __restrict__ kk,
+                             const int32_t* __restrict__ nslots, const int32_t* __restrict__ off, int64_t m,
+                             unsigned long long* __restrict__ keys, uint32_t* __restrict__ slot_class, uint8_t* __restrict__ slot_no) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ns = nslots[i];
+    if (ns == 0) continue;
+    const int64_t d = rp[i + 1] - rp[i], kv = kk[i];
+    const unsigned long long first = (unsigned long long)(uint32_t)col[rp[i]];
+    const int set = clsb_set_of(d, kv);
+    for (int s = 0; s < ns; ++s) {
+      unsigned long long dp, q;
+      if (set == 2) { dp = MMQ_CLSB_DPC0 + (MMQ_CLS_CHAIN_DMAX - d); q = 0; }
+      else if (kv == 1) { dp = MMQ_CLS_DP1(d); q = 16; }
+      else {
+        const int64_t grp = MMQ_CLS_GROUP(d);
+        const int64_t draws = (s + 1) * grp <= kv ? grp : kv - s * grp;
+        dp = (unsigned long long)d; q = (unsigned long long)(16 - (draws + 3) / 4);
+      }
+      const int64_t slot = (int64_t)off[i] + s;
+      keys[slot] = (dp << 36) | (q << 31) | first;
+      slot_class[slot] = (uint32_t)i;
+      slot_no[slot] = (uint8_t)s;
+    }
+  }
+}
+/* first[dp] = first sorted position with that pseudo size */
+__global__ void k_clsb_bounds(const unsigned long long* __restrict__ keys, int64_t S, int* __restrict__ first) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < S; p += (int64_t)gridDim.x * blockDim.x) {
+    const int dp = (int)(keys[p] >> 36);
+    if (p == 0 || (int)(keys[p - 1] >> 36) != dp) first[dp] = (int)p;
+  }
+}
+__global__ void k_clsb_fill(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t S,
+                            const clsb_run* __restrict__ runs, const uint32_t* __restrict__ slot_class, const uint8_t* __restrict__ slot_no,
+                            const int64_t* __restrict__ rp, const int32_t* __restrict__ col, const int32_t* __restrict__ kk,
+                            const int64_t* __restrict__ class_id, int64_t cid_base, int32_t* __restrict__ pcol, uint16_t* __restrict__ pk,
+                            uint32_t* __restrict__ pcid, int32_t* __restrict__ c_pcol, int32_t* __restrict__ c_k, uint32_t* __restrict__ c_cid) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < S; p += (int64_t)gridDim.x * blockDim.x) {
+    const int dp = (int)(keys[p] >> 36);
+    const clsb_run R = runs[dp];
+    const uint32_t slot = vals[p];
+    const int64_t i = slot_class[slot];
+    const int sno = slot_no[slot];
+    const int li = (int)p - R.first, d = R.d;
+    const int64_t chunk = R.chunk0 + (li >> 5);
+    const int32_t* src = col + rp[i];
+    const uint32_t cid = (uint32_t)(class_id ? class_id[i] : cid_base + i);
+    const int64_t kv = kk[i];
+    if (dp >= MMQ_CLSB_DPC0) {
+      int32_t* dst = c_pcol + R.e0 + (int64_t)(li >> 5) * 32 * d + (li & 31);
+      for (int j = 0; j < d; ++j) dst[32 * j] = src[j];
+      c_k[chunk * 32 + (li & 31)] = (int32_t)kv;
+      c_cid[chunk * 32 + (li & 31)] = cid;
+    } else {
+      int32_t* dst = pcol + R.e0 + (int64_t)(li >> 5) * 32 * d + (li & 31);
+      for (int j = 0; j < d; ++j) dst[32 * j] = src[j];
+      const int64_t grp = MMQ_CLS_GROUP(d);
+      const int64_t draws = kv == 1 ? 1 : ((sno + 1) * grp <= kv ? grp : kv - sno * grp);
+      pk[chunk * 32 + (li & 31)] = (uint16_t)(draws | (sno << 8));
+      pcid[chunk * 32 + (li & 31)] = cid;
+    }
+  }
+}
+__global__ void k_clsb_desc(const clsb_run* __restrict__ runs, int ndp, const int* __restrict__ nchunks, unsigned long long* __restrict__ cdesc,
+                            unsigned long long* __restrict__ c_desc) {
+  const int dp = blockIdx.x;
+  if (dp >= ndp || nchunks[dp] == 0) return;
+  const clsb_run R = runs[dp];
+  unsigned long long* out = dp >= MMQ_CLSB_DPC0 ? c_desc : cdesc;
+  for (int c = threadIdx.x; c < nchunks[dp]; c += blockDim.x)
+    out[R.chunk0 + c] = ((unsigned long long)(R.e0 + (long long)c * 32 * R.d) << 8) | (unsigned long long)R.d;
+}
+
+/* Returns MMQ_OK with h->cls_ready set, or with it unset when the plan does not apply (the general kernel then). */
+static int cls_plan_device(mmq_handle* h, const mmq_problem* p) {
+  const int64_t m = h->m, n = h->n;
+  const uint64_t cid0 = (uint64_t)(p->class_id ? p->class_id[0] : p->class_id_base);
+  const uint32_t cid_hi = (uint32_t)(cid0 >> 32);
+  int rc;
+  int32_t *nslots = nullptr, *off = nullptr;
+  unsigned long long *keys = nullptr, *keys2 = nullptr;
+  uint32_t *vals = nullptr, *vals2 = nullptr, *slot_class = nullptr;
+  uint8_t* slot_no = nullptr;
+  int *info = nullptr, *first = nullptr, *nch_dev = nullptr;
+  clsb_run* runs_dev = nullptr;
+  void* temp = nullptr;
+  auto cleanup = [&] {
+    for (void* q : {(void*)nslots, (void*)off, (void*)keys, (void*)keys2, (void*)vals, (void*)vals2, (void*)slot_class, (void*)slot_no,
+                    (void*)info, (void*)first, (void*)nch_dev, (void*)runs_dev, temp})
+      if (q) cudaFree(q);
+  };
+#define CLSB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return mmq_cuda_fail(h, e__, #call, __FILE__, __LINE__); } } while (0)
+  CLSB(cudaMalloc(&nslots, sizeof(int32_t) * (size_t)(m + 1)));
+  CLSB(cudaMalloc(&off, sizeof(int32_t) * (size_t)(m + 1)));
+  CLSB(cudaMalloc(&info, sizeof(int) * 4));
+  CLSB(cudaMalloc(&first, sizeof(int) * MMQ_CLSB_NDP));
+  CLSB(cudaMalloc(&nch_dev, sizeof(int) * MMQ_CLSB_NDP));
+  CLSB(cudaMalloc(&runs_dev, sizeof(clsb_run) * MMQ_CLSB_NDP));
+  CLSB(cudaMemsetAsync(info, 0, sizeof(int) * 4, h->stream));
+  CLSB(cudaMemsetAsync(nslots + m, 0, sizeof(int32_t), h->stream));
+  if ((rc = mmq_dev_alloc(h, (void**)&h->seg_base, sizeof(int32_t) * (size_t)n))) { cleanup(); return rc; }
+  CLSB(cudaMemsetAsync(h->seg_base, 0, sizeof(int32_t) * (size_t)n, h->stream));
+  const int grid = mmq_grid_for(m, 256, h->num_sms * 8);
+  k_clsb_classify<<<grid, 256, 0, h->stream>>>(h->row_ptr, h->col, h->k, h->class_id, h->class_id_base, cid_hi, m, nslots, h->seg_base, info);
+  g_mmq_launches.fetch_add(1);
+  size_t tb1 = 0, tb2 = 0;
+  CLSB(cub::DeviceScan::ExclusiveSum(nullptr, tb1, nslots, off, (int)(m + 1), h->stream));
+  int host_info[4] = {0, 0, 0, 0};
+  {
+    void* t1 = nullptr;
+    CLSB(cudaMalloc(&t1, tb1));
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(t1, tb1, nslots, off, (int)(m + 1), h->stream);
+    int total = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&total, off + m, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(t1);
+    if (e != cudaSuccess) { cleanup(); return mmq_cuda_fail(h, e, "class plan scan", __FILE__, __LINE__); }
+    host_info[3] = total;
+  }
+  if (host_info[0]) { cleanup(); mmq_dev_free(h, h->seg_base); h->seg_base = nullptr; return MMQ_OK; } /* class ids spread over several 2^32 blocks (or k < 0) */
+  const int64_t S = host_info[3];
+  std::vector<int> first_h(MMQ_CLSB_NDP, -1), nch(MMQ_CLSB_NDP, 0);
+  std::vector<clsb_run> runs(MMQ_CLSB_NDP);
+  int64_t chunks = 0, packed = 0, chunks_lo = 0, chunks_gen = 0, c_chunks = 0, c_packed = 0, small_slots = 0, n_chain = 0;
+  if (S > 0) {
+    CLSB(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)S));
+    CLSB(cudaMalloc(&keys2, sizeof(unsigned long long) * (size_t)S));
+    CLSB(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)S));
+    CLSB(cudaMalloc(&vals2, sizeof(uint32_t) * (size_t)S));
+    CLSB(cudaMalloc(&slot_class, sizeof(uint32_t) * (size_t)S));
+    CLSB(cudaMalloc(&slot_no, (size_t)S));
+    k_clsb_slots<<<grid, 256, 0, h->stream>>>(h->row_ptr, h->col, h->k, nslots, off, m, keys, slot_class, slot_no);
+    g_mmq_launches.fetch_add(1);
+    k_iota_u32<<<mmq_grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(vals, S);
+    g_mmq_launches.fetch_add(1);
+    CLSB(cub::DeviceRadixSort::SortPairs(nullptr, tb2, keys, keys2, vals, vals2, (int)S, 0, 44, h->stream));
+    CLSB(cudaMalloc(&temp, tb2));
+    CLSB(cub::DeviceRadixSort::SortPairs(temp, tb2, keys, keys2, vals, vals2, (int)S, 0, 44, h->stream));
+    CLSB(cudaMemsetAsync(first, 0xff, sizeof(int) * MMQ_CLSB_NDP, h->stream));
+    k_clsb_bounds<<<mmq_grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(keys2, S, first);
+    g_mmq_launches.fetch_add(1);
+    CLSB(cudaMemcpyAsync(first_h.data(), first, sizeof(int) * MMQ_CLSB_NDP, cudaMemcpyDeviceToHost, h->stream));
+    CLSB(cudaStreamSynchronize(h->stream));
+    /* runs: pseudo sizes in ascending order; the small set's chunks, then (numbered separately) the chain set's */
+    int64_t next_first = S;
+    std::vector<int64_t> cnt(MMQ_CLSB_NDP, 0);
+    for (int dp = MMQ_CLSB_NDP - 1; dp >= 0; --dp)
+      if (first_h[dp] >= 0) { cnt[dp] = next_first - first_h[dp]; next_first = first_h[dp]; }
+    for (int dp = 0; dp < MMQ_CLSB_NDP; ++dp) {
+      const bool chain = dp >= MMQ_CLSB_DPC0;
+      const int d = chain ? MMQ_CLS_CHAIN_DMAX - (dp - MMQ_CLSB_DPC0) : MMQ_CLS_D_OF(dp);
+      runs[dp].first = first_h[dp] < 0 ? 0 : first_h[dp];
+      runs[dp].d = d; runs[dp].pad = 0;
+      const int64_t nc = (cnt[dp] + 31) / 32;
+      nch[dp] = (int)nc;
+      if (!chain) {
+        runs[dp].e0 = packed; runs[dp].chunk0 = (int)chunks;
+        chunks += nc; packed += nc * 32 * d; small_slots += cnt[dp];
+        if (dp <= MMQ_CLS_DLO) chunks_lo = chunks;
+        if (dp <= MMQ_CLS_DMAX) chunks_gen = chunks;
+      } else {
+        runs[dp].e0 = c_packed; runs[dp].chunk0 = (int)c_chunks;
+        c_chunks += nc; c_packed += nc * 32 * d; n_chain += cnt[dp];
+      }
+    }
+    if (chunks > 0x7fff0000ll) { cleanup(); mmq_dev_free(h, h->seg_base); h->seg_base = nullptr; return MMQ_OK; }
+    if ((rc = mmq_dev_alloc(h, (void**)&h->cls_pcol, sizeof(int32_t) * (size_t)std::max<int64_t>(packed, 1)))) { cleanup(); return rc; }
+    if ((rc = mmq_dev_alloc(h, (void**)&h->cls_pk, sizeof(uint16_t) * (size_t)std::max<int64_t>(chunks * 32, 1)))) { cleanup(); return rc; }
+    if ((rc = mmq_dev_alloc(h, (void**)&h->cls_pcid, sizeof(uint32_t) * (size_t)std::max<int64_t>(chunks * 32, 1)))) { cleanup(); return rc; }
+    if ((rc = mmq_dev_alloc(h, (void**)&h->cls_cdesc, sizeof(unsigned long long) * (size_t)std::max<int64_t>(chunks, 1)))) { cleanup(); return rc; }
+    if (c_chunks > 0) {
+      if ((rc = mmq_dev_alloc(h, (void**)&h->cls_c_pcol, sizeof(int32_t) * (size_t)c_packed))) { cleanup(); return rc; }
+      if ((rc = mmq_dev_alloc(h, (void**)&h->cls_c_k, sizeof(int32_t) * (size_t)c_chunks * 32))) { cleanup(); return rc; }
+      if ((rc = mmq_dev_alloc(h, (void**)&h->cls_c_cid, sizeof(uint32_t) * (size_t)c_chunks * 32))) { cleanup(); return rc; }
+      if ((rc = mmq_dev_alloc(h, (void**)&h->cls_c_desc, sizeof(unsigned long long) * (size_t)c_chunks))) { cleanup(); return rc; }
+      k_fill_i32_cls<<<mmq_grid_for(c_packed, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->cls_c_pcol, c_packed, (int32_t)n);
+      CLSB(cudaMemsetAsync(h->cls_c_k, 0, sizeof(int32_t) * (size_t)c_chunks * 32, h->stream));
+      CLSB(cudaMemsetAsync(h->cls_c_cid, 0, sizeof(uint32_t) * (size_t)c_chunks * 32, h->stream));
+    }
+    /* padding lanes: the sentinel column (mu[n] == 0), no draws */
+    if (packed > 0) k_fill_i32_cls<<<mmq_grid_for(packed, 256, h->num_sms * 8), 256, 0, h->stream>>>(h->cls_pcol, packed, (int32_t)n);
+    if (chunks > 0) {
+      CLSB(cudaMemsetAsync(h->cls_pk, 0, sizeof(uint16_t) * (size_t)chunks * 32, h->stream));
+      CLSB(cudaMemsetAsync(h->cls_pcid, 0, sizeof(uint32_t) * (size_t)chunks * 32, h->stream));
+    }
+    CLSB(cudaMemcpyAsync(runs_dev, runs.data(), sizeof(clsb_run) * MMQ_CLSB_NDP, cudaMemcpyHostToDevice, h->stream));
+    CLSB(cudaMemcpyAsync(nch_dev, nch.data(), sizeof(int) * MMQ_CLSB_NDP, cudaMemcpyHostToDevice, h->stream));
+    k_clsb_fill<<<mmq_grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(keys2, vals2, S, runs_dev, slot_class, slot_no, h->row_ptr, h->col, h->k,
+                                                                             h->class_id, h->class_id_base, h->cls_pcol, h->cls_pk, h->cls_pcid,
+                                                                             h->cls_c_pcol, h->cls_c_k, h->cls_c_cid);
+    k_clsb_desc<<<MMQ_CLSB_NDP, 128, 0, h->stream>>>(runs_dev, MMQ_CLSB_NDP, nch_dev, h->cls_cdesc, h->cls_c_desc);
+    g_mmq_launches.fetch_add(4);
+  }
+  /* the rest (more members than the plan's kernels take): listed by the host from the caller's arrays, one class per tile */
+  const int64_t n_rest = host_info[2];
+  int64_t nnz_rest = 0;
+  if (n_rest > 0) {
+    std::vector<int64_t> o_rp(1, 0), o_cid, o_tiles;
+    std::vector<int32_t> o_col, o_k;
+    std::vector<int64_t> rest;
+    for (int64_t i = 0; i < m; ++i) {
+      const int64_t d = p->row_ptr[i + 1] - p->row_ptr[i], kv = p->k[i];
+      if (d != 1 && kv > 0 && !(d <= MMQ_CLS_DMAX && kv <= mmq_cat_limit((int)d)) && d > MMQ_CLS_CHAIN_DMAX) rest.push_back(i);
+    }
+    std::stable_sort(rest.begin(), rest.end(), [&](int64_t a, int64_t b) { return p->row_ptr[a + 1] - p->row_ptr[a] > p->row_ptr[b + 1] - p->row_ptr[b]; });
+    for (size_t q = 0; q < rest.size(); ++q) {
+      const int64_t i = rest[q];
+      o_col.insert(o_col.end(), p->col + p->row_ptr[i], p->col + p->row_ptr[i + 1]);
+      o_rp.push_back((int64_t)o_col.size());
+      o_k.push_back(p->k[i]);
+      o_cid.push_back(p->class_id ? p->class_id[i] : p->class_id_base + i);
+      o_tiles.push_back((int64_t)q);
+    }
+    o_tiles.push_back((int64_t)rest.size());
+    nnz_rest = (int64_t)o_col.size();
+    o_col.resize(o_col.size() + 4, 0);
+    if ((rc = cls_upload(h, &h->cls_o_rp, o_rp)) || (rc = cls_upload(h, &h->cls_o_col, o_col)) || (rc = cls_upload(h, &h->cls_o_k, o_k)) ||
+        (rc = cls_upload(h, &h->cls_o_cid, o_cid)) || (rc = cls_upload(h, &h->cls_o_tiles, o_tiles))) { cleanup(); return rc; }
+    CLSB(cudaStreamSynchronize(h->stream)); /* host temporaries */
+  }
+  if (host_info[1]) { /* singleton classes: counts[] starts from their constant sums */
+    CLSB(cudaMemcpyAsync(h->counts, h->seg_base, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    h->seg_base_in_counts = true;
+  } else {
+    mmq_dev_free(h, h->seg_base);
+    h->seg_base = nullptr;
+  }
+  CLSB(cudaStreamSynchronize(h->stream));
+  cleanup();
+#undef CLSB
+  h->cls_nruns = 0;
+  h->cls_chunks = chunks; h->cls_chunks_lo = chunks_lo; h->cls_chunks_gen = chunks_gen;
+  h->cls_cid_hi = cid_hi;
+  h->cls_small = small_slots; /* slots of the small set (a class above 64 fragments takes several) */
+  h->cls_rest = n_rest; h->cls_rest_nnz = nnz_rest; h->cls_rest_tiles = n_rest;
+  h->cls_packed = packed;
+  h->cls_c_chunks = c_chunks; h->cls_c_packed = c_packed; h->cls_chain = n_chain;
+  h->cls_ready = true;
+  return MMQ_OK;
+}
+
 int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
   h->cls_ready = false;
   static const bool off = [] { const char* e = getenv("MMQ_CLS_OFF"); return e && atoi(e) != 0; }();
   if (off || !h->has_k || h->has_w || h->m == 0) return MMQ_OK;
+  const char* hp_env = getenv("MMQ_CLS_HOST_PLAN"); /* once per mmq_create: the host builder instead of the device one (tests compare the two) */
+  const bool host_plan = hp_env && atoi(hp_env) != 0;
+  if (!h->stream2) {
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming));
+    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join5, cudaEventDisableTiming));
+  }
+  if (!host_plan) return cls_plan_device(h, p);
   mmq_cls_host_plan P;
   if (!mmq_cls_build_host(h->n, h->m, p->row_ptr, p->col, p->k, p->class_id, p->class_id_base, P)) return MMQ_OK;
   const auto t_up = std::chrono::steady_clock::now();
@@ -533,17 +833,6 @@ int mmq_cls_plan(mmq_handle* h, const mmq_problem* p) {
     mmq_dev_free(h, d_k);
   }
   MMQ_CUDA(h, cudaStreamSynchronize(h->stream)); /* the vectors are host temporaries */
-  if (!h->stream2) {
-    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
-    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking));
-    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream4, cudaStreamNonBlocking));
-    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join4, cudaEventDisableTiming));
-    MMQ_CUDA(h, cudaStreamCreateWithFlags(&h->stream5, cudaStreamNonBlocking));
-    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join5, cudaEventDisableTiming));
-    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    MMQ_CUDA(h, cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
-  }
   tick("uploads");
   h->cls_nruns = (int)runs.size();
   h->cls_chunks = chunks;

@@ -242,7 +242,7 @@ def test_ragged_and_extreme_rows():
             assert np.array_equal(c_f, c_o)
 
 
-@pytest.mark.parametrize("plan_threads", ["1", "5"])
+@pytest.mark.parametrize("plan_threads", ["1", "5", "device"])
 @pytest.mark.parametrize("cid_base", [0, (1 << 32) * 5 + 3])
 def test_class_plan_kernel_bit_exact(monkeypatch, cid_base, plan_threads):
     """Collapsed shards (mmq_cls.cu): every regime of the plan against the CPU replay — k = 0, 1,
@@ -251,7 +251,11 @@ def test_class_plan_kernel_bit_exact(monkeypatch, cid_base, plan_threads):
     2..8 and 9..16 (the two register instances), 17..64 (generic), > 64 (general kernel), all-zero and partly-zero mu
     rows, class ids above 2^32, chunks that end inside a warp; the plan built by one host thread and
     by several (MMQ_PLAN_THREADS)."""
-    monkeypatch.setenv("MMQ_PLAN_THREADS", plan_threads)
+    if plan_threads == "device":   # the default: the plan is built on the device (mmq_cls.cu: cls_plan_device)
+        monkeypatch.delenv("MMQ_CLS_HOST_PLAN", raising=False)
+    else:                          # the host builder of mmq_cls_plan.h (what the CPU tests replay)
+        monkeypatch.setenv("MMQ_CLS_HOST_PLAN", "1")
+        monkeypatch.setenv("MMQ_PLAN_THREADS", plan_threads)
     rng = np.random.default_rng(5)
     n = 4000
     sizes = np.concatenate([rng.integers(1, 17, 5000), rng.integers(17, 65, 300), rng.integers(65, 200, 20), [2] * 37, [16] * 33])
