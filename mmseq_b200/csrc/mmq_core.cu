@@ -1022,10 +1022,10 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
     if (flags & 4) { h->err = "mmq_create: columns must be strictly ascending within a class (src/mmseq.cpp:412)"; CREATE_TRY(MMQ_ERR_ARG); }
   }
   tick("H2D copies + validation");
-  if (h->has_k) CREATE_TRY(build_tiles(h, p->row_ptr)); /* k == 1 shards build them on first use of the general kernel */
-  tick("tiles");
   if (!h->has_k) CREATE_TRY(mmq_seg_plan(h));
   if (h->has_k) CREATE_TRY(mmq_cls_plan(h, p));
+  if (h->has_k && !h->cls_ready) CREATE_TRY(build_tiles(h, p->row_ptr)); /* the general kernel's tiles; otherwise on its first use */
+  tick("tiles");
   CREATE_TRY(cuda_try(cudaStreamSynchronize(h->stream), "cudaStreamSynchronize"));
   tick("segment / class plan");
   h->arena_cap = h->arena_off; /* closed: later allocations (trace, transpose, peer buffers) are their own */
@@ -1382,7 +1382,7 @@ static int prepare_sweep(mmq_handle* h, int flags) {
   if (h->m <= 0) return MMQ_OK;
   int rc;
   const bool transposed = (flags & MMQ_GIBBS_TRANSPOSED) != 0;
-  if ((transposed || h->has_k || (flags & MMQ_GIBBS_GENERIC_KERNEL)) && (rc = build_tiles(h, nullptr))) return rc;
+  if ((transposed || (h->has_k && !h->cls_ready) || (flags & MMQ_GIBBS_GENERIC_KERNEL)) && (rc = build_tiles(h, nullptr))) return rc;
   if (transposed) {
     if ((rc = ensure_x(h))) return rc;
     if ((rc = build_transpose(h))) return rc;
