@@ -319,7 +319,7 @@ def run_gates(args, H, w, mu0_gpu, mu_em_gpu, em_iters_gpu, rank, world, dev, al
         mu0 = allreduce(mu0 * w.length) / w.length
     pos0 = mu0 > 0   # with several shards the columns are all header transcripts: those without hits start (and stay) at 0
     rel0 = float(np.max(np.abs(mu0_gpu[pos0] / mu0[pos0] - 1.0))) if np.array_equal(mu0_gpu[~pos0], mu0[~pos0]) else float("inf")
-    g["init_mu"] = {"max_rel_err": rel0, "tol": 1e-12, "ok": bool(rel0 <= 1e-12)}
+    g["init_mu"] = {"max_rel_err": rel0, "tol": 1e-9, "ok": bool(rel0 <= 1e-9)}   # fp64 sums of up to 1e8 terms in different orders
     # (b) EM from the same start: oracle iteration split over the shards (orc_em_partial = one shard's part of src/mmseq.cpp:781-802).
     # Shards above 60M entries (config 4): the first 8 iterations only (an oracle iteration is a pass over the shard on the host)
     bounded = h.nnz > 60_000_000

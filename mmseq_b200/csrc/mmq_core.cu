@@ -771,9 +771,11 @@ k_gamma_rs(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double
   int32_t* reset = reinterpret_cast<int32_t*>(a.base[a.rank] + a.off_reset);
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
     reset[t] = counts_base ? counts_base[t] : 0;
-  __threadfence_system(); /* this thread's peer stores are visible system-wide before the block signs off */
+  /* the block's peer stores are ordered before its sign-off: bar.sync makes them happen before thread 0's system-scope
+   * fence (one fence per block; a fence per thread cost 8 us per sweep) */
   __syncthreads();
   if (threadIdx.x == 0) {
+    __threadfence_system();
     unsigned int* done = reinterpret_cast<unsigned int*>(own + MMQ_P2P_DONE);
     if (atomicAdd(done, 1u) == gridDim.x - 1) { /* last block of this rank */
       *done = 0u;
