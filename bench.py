@@ -73,6 +73,11 @@ def parse():
     ap.add_argument("--no-gates", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra lines (weighted per-fragment stream of the same sample)")
     ap.add_argument("--gate-sweeps", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=0, help="config 5: this many independent C2-sized samples (own synthetic fragments, own chain) dealt to "
+                                                         "the GPUs, each through load -> EM -> --batch-sweeps Gibbs sweeps -> Sokal summaries; reports samples/s")
+    ap.add_argument("--batch-per-gpu", type=int, default=4, help="samples in flight per GPU")
+    ap.add_argument("--batch-sweeps", type=int, default=16384, help="Gibbs sweeps per sample (the reference's default -gibbs_iter)")
+    ap.add_argument("--batch-out", default="/tmp/mmq_batch", help="directory of the per-sample summary tables")
     args = ap.parse_args()
     if args.weights:
         args.layout = "perfragment"
@@ -496,11 +501,106 @@ def extra_weighted_line(args, dev, stream, peak):
                          "frac": b_alloc / (a * 1e-3) / 1e9 / peak}, "plan": rows}
 
 
+def run_batch(args, rank, world, local):
+    """BASELINE config 5: a batch of independent samples, no collective.  Every rank takes the samples rank, rank + N, ...;
+    a producer thread makes the next samples' hit classes (synthetic fragments + the loader's class construction) while
+    --batch-per-gpu worker threads, each with its own handle and stream, run EM, the Gibbs chain (trace of 1024) and the
+    device summaries (log-mean, Sokal variance / IACT / MCSE inputs, percentiles) and write the sample's table."""
+    import queue
+    import torch
+    import torch.distributed as dist
+    from mmseq_b200 import capi, hostlib, synth
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    os.makedirs(args.batch_out, exist_ok=True)
+    mine = [i for i in range(args.batch) if i % world == rank]
+    L = 1024
+    stride = max(1, args.batch_sweeps // L)
+    q = queue.Queue(maxsize=args.batch_per_gpu)
+    done = []
+    lock = threading.Lock()
+
+    def producer():
+        for i in mine:
+            t0 = time.perf_counter()
+            s = synth.Synth(SYNTH_SEED, args.transcripts, args.fragments, frag_seed=1000 + i)
+            h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_COLLAPSED | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
+            length = s.efflen[h.col2hdr] * args.fragments / 1e9
+            q.put((i, h, length, time.perf_counter() - t0))
+        for _ in range(args.batch_per_gpu):
+            q.put(None)
+
+    def worker():
+        stream = torch.cuda.Stream(device=dev)
+        while True:
+            item = q.get()
+            if item is None:
+                return
+            i, h, length, prep_s = item
+            t0 = time.perf_counter()
+            H = capi.Handle(h.row_ptr, h.col, h.k, length, device=local)
+            H.set_stream(stream.cuda_stream)
+            uh = H.init_mu()
+            it, ll, _ = H.em(1000, 0.1)
+            mu_em = H.get_mu()
+            H.gibbs(SEED + i, 0, args.batch_sweeps, stride=stride, trace_len=L)
+            S = H.summarize(0, [int(np.floor(p / 100.0 * (L - 1) + 0.5)) for p in (5, 25, 50, 75, 95)])
+            H.close()
+            with np.errstate(invalid="ignore"):
+                sd = np.sqrt(S["var"]); mcse = np.sqrt(S["tau"] * S["var"] / L)
+            tab = np.column_stack([S["log_mean"], sd, mcse, S["tau"], uh, np.log(np.maximum(mu_em, 1e-300))])
+            np.savetxt(os.path.join(args.batch_out, f"sample_{i:03d}.tsv"), tab, delimiter="\t", fmt="%.6g",
+                       header="log_mu\tsd\tmcse\tiact\tunique_hits\tlog_mu_em", comments="")
+            with lock:
+                done.append({"sample": i, "em_iters": int(it), "prep_s": round(prep_s, 2), "gpu_pipeline_s": round(time.perf_counter() - t0, 3),
+                             "finite_log_mu": int(np.isfinite(S["log_mean"]).sum()), "median_iact": float(np.nanmedian(S["tau"]))})
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = capi.launch_count()
+    t0 = time.perf_counter()
+    th = [threading.Thread(target=producer)] + [threading.Thread(target=worker) for _ in range(args.batch_per_gpu)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        allres = [None] * world
+        dist.all_gather_object(allres, done)
+        done = [d for r in allres for d in r]
+    wall = float(tw.item())
+    if rank == 0:
+        line = {"metric": "batch_samples_per_s", "value": args.batch / wall, "unit": "samples/s", "n_gpus": world, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "wall_s": wall,
+                "sweeps_per_s_all_samples": args.batch * args.batch_sweeps / wall,
+                "sweeps_per_s_per_gpu": args.batch * args.batch_sweeps / wall / world,
+                "gpu_pipeline_s_median": float(np.median([d["gpu_pipeline_s"] for d in done])),
+                "prep_s_median": float(np.median([d["prep_s"] for d in done])),
+                "gpu_launches": int(capi.launch_count() - launches0),
+                "config": {"workload": "C5-batch", "samples": args.batch, "transcripts": args.transcripts, "fragments_per_sample": args.fragments,
+                           "sweeps_per_sample": args.batch_sweeps, "trace_length": L, "in_flight_per_gpu": args.batch_per_gpu,
+                           "per_sample": "class construction (host) -> mmq_create -> init, EM -> Gibbs chain -> device summaries (Sokal) -> table"},
+                "tables": os.path.join(args.batch_out, "sample_*.tsv"), "samples": sorted(done, key=lambda d: d["sample"])[:8]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank, world, local = dist_env()
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.batch > 0:
+        run_batch(args, rank, world, local)
         return
 
     import torch

@@ -10,7 +10,8 @@
  * prior draws of hit-less isoforms, trace aggregation, Sokal, percentiles and
  * proportion summaries.  The host only parses, formats and writes.
  * Additive options: -gpus INT (shard hit classes over GPUs of this box),
- * -notraces (skip the four *.trace_gibbs.gz text dumps), -layout STR.
+ * -notraces (skip the four *.trace_gibbs.gz text dumps), -batch FILE / -per_gpu INT (many
+ * samples dealt to the GPUs, independent chains: BASELINE config 5).
  */
 #include <unistd.h>
 #include <zlib.h>
@@ -44,21 +45,6 @@
 
 using namespace std;
 
-static void tokenise(const string& str, vector<string>& tokens, const string& delimiters = " ") {
-  string::size_type lastPos = str.find_first_not_of(delimiters, 0);
-  string::size_type pos = str.find_first_of(delimiters, lastPos);
-  while (string::npos != pos || string::npos != lastPos) {
-    tokens.push_back(str.substr(lastPos, pos - lastPos));
-    lastPos = str.find_first_not_of(delimiters, pos);
-    pos = str.find_first_of(delimiters, lastPos);
-  }
-}
-
-static int powerof2(unsigned int x) {
-  while (((x & 1) == 0) && x > 1) x >>= 1;
-  return (x == 1);
-}
-
 /* The usage text of the reference (src/mmseq.cpp:156-177) plus the additive options. */
 static void printUsage(ostream& out) {
   out << "Usage: mmseq [OPTIONS...] hits_file output_base" << endl
@@ -81,6 +67,8 @@ static void printUsage(ostream& out) {
       << "  -version           print the version" << endl
       << "  -gpus INT          (B200 build) shard hit classes over this many GPUs (default: 1)" << endl
       << "  -notraces          (B200 build) do not write the *.trace_gibbs.gz text dumps" << endl
+      << "  -batch FILE        (B200 build) many samples: FILE lists one \"hits_file output_base\" pair per line (no positional arguments)" << endl
+      << "  -per_gpu INT       (B200 build) batch mode: samples in flight per GPU (default: 4)" << endl
       << endl;
 }
 
@@ -227,116 +215,101 @@ static void phase(const char* name) {
   t_last = now;
 }
 
-int main(int argc, char** argv) {
-  phase("start");
-  /* DEFAULT PARAMETER VALUES (src/mmseq.cpp:183-205) */
-  double alpha = 0.1, beta = 0.1;
-  int max_em_iter = 1000;
-  double epsilon = 0.1;
-  int gibbs_iter = 16384;
-  int trace_length = 1024;
-  int gibbs_ss = gibbs_iter / trace_length;
+/* ---- command line (src/mmseq.cpp:183-296): one table of options, the reference's messages and exit codes ---- */
+struct Options {
+  double alpha = 0.1, beta = 0.1, epsilon = 0.1;
+  int max_em_iter = 1000, gibbs_iter = 16384, trace_length = 1024, gibbs_ss = 16384 / 1024, seed = 1234;
   vector<double> percentiles{5.0, 25.0, 50.0, 75.0, 95.0};
-  vector<string> tokens;
-  int seed = 1234;
-  bool debug = false;
+  bool debug = false, notraces = false;
   int ngpus = 1;
-  bool notraces = false;
+  string batch;     /* -batch FILE: one "hits_file output_base" pair per line */
+  int per_gpu = 4;  /* -per_gpu INT: samples in flight per GPU in batch mode */
+  vector<string> positional;
+};
 
-  vector<string> arguments;
-  for (int i = 1; i < argc; i++) arguments.push_back(string(argv[i]));
-  auto need_value = [&](const char* opt) {
-    if (arguments.size() < 2) { cerr << "Error: option " << opt << " needs a value.\n"; printUsage(cerr); exit(1); }
-  };
-  while (true) {
-    if (arguments.size() > 0 && arguments[0] == "-alpha") {
-      need_value("-alpha"); arguments.erase(arguments.begin());
-      alpha = strtod(arguments[0].c_str(), NULL); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-beta") {
-      need_value("-beta"); arguments.erase(arguments.begin());
-      beta = strtod(arguments[0].c_str(), NULL); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-max_em_iter") {
-      need_value("-max_em_iter"); arguments.erase(arguments.begin());
-      max_em_iter = atoi(arguments[0].c_str()); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-epsilon") {
-      need_value("-epsilon"); arguments.erase(arguments.begin());
-      epsilon = strtod(arguments[0].c_str(), NULL); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-gibbs_iter") {
-      need_value("-gibbs_iter"); arguments.erase(arguments.begin());
-      gibbs_iter = atoi(arguments[0].c_str()); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-gibbs_ss") {
-      need_value("-gibbs_ss"); arguments.erase(arguments.begin());
-      gibbs_ss = atoi(arguments[0].c_str()); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-seed") {
-      need_value("-seed"); arguments.erase(arguments.begin());
-      seed = atoi(arguments[0].c_str()); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-percentiles") {
-      need_value("-percentiles"); arguments.erase(arguments.begin());
-      tokens.clear();
-      tokenise(arguments[0], tokens, ",");
-      percentiles.resize(tokens.size());
-      for (size_t i = 0; i < tokens.size(); i++) {
-        if (strtod(tokens[i].c_str(), NULL) >= 0 && strtod(tokens[i].c_str(), NULL) <= 100) {
-          percentiles[i] = strtod(tokens[i].c_str(), NULL);
-        } else {
-          cerr << "Percentiles must be in (0,100)\n";
-          exit(1);
-        }
-      }
-      arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-gpus") {
-      need_value("-gpus"); arguments.erase(arguments.begin());
-      ngpus = atoi(arguments[0].c_str()); arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-notraces") {
-      notraces = true; arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && arguments[0] == "-debug") {
-      debug = true; arguments.erase(arguments.begin());
-    } else if (arguments.size() > 0 && (arguments[0] == "-h" || arguments[0] == "--help" || arguments[0] == "-help")) {
-      cerr << "Calculate mmseq expression estimates.\n";
-      printUsage(cerr);
-      exit(1);
-    } else if (arguments.size() > 0 && (arguments[0] == "-v" || arguments[0] == "--version" || arguments[0] == "-version")) {
-      cerr << "mmseq-" << QUOTE(VERSION) << endl;
-      exit(1);
-    } else {
-      if (arguments.size() == 2) {
-        break;
-      } else {
-        if (arguments.size() > 0 && arguments[0][0] == '-') cerr << "Error: unrecognised option " << arguments[0] << ".\n";
-        else cerr << "Error: mandatory arguments missing.\n";
-        printUsage(cerr);
-        exit(1);
-      }
+[[noreturn]] static void usage_error(const string& msg) {
+  if (!msg.empty()) cerr << msg << "\n";
+  printUsage(cerr);
+  exit(1);
+}
+
+static bool is_power_of_two(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+static void parse_percentiles(const string& list, vector<double>& out) {
+  out.clear();
+  size_t pos = 0;
+  while (pos <= list.size()) {
+    const size_t comma = list.find(',', pos);
+    const string item = list.substr(pos, comma == string::npos ? string::npos : comma - pos);
+    if (!item.empty()) {
+      const double v = strtod(item.c_str(), NULL);
+      if (!(v >= 0 && v <= 100)) { cerr << "Percentiles must be in (0,100)\n"; exit(1); }
+      out.push_back(v);
     }
+    if (comma == string::npos) break;
+    pos = comma + 1;
+  }
+}
+
+static Options parse_command_line(int argc, char** argv) {
+  Options o;
+  enum Kind { REAL, INT, TEXT, FLAG };
+  struct Spec { const char* name; Kind kind; void* target; };
+  string pct;
+  const Spec specs[] = {
+      {"-alpha", REAL, &o.alpha},         {"-beta", REAL, &o.beta},           {"-max_em_iter", INT, &o.max_em_iter},
+      {"-epsilon", REAL, &o.epsilon},     {"-gibbs_iter", INT, &o.gibbs_iter}, {"-gibbs_ss", INT, &o.gibbs_ss},
+      {"-seed", INT, &o.seed},            {"-percentiles", TEXT, &pct},       {"-gpus", INT, &o.ngpus},
+      {"-batch", TEXT, &o.batch},         {"-per_gpu", INT, &o.per_gpu},      {"-notraces", FLAG, &o.notraces},
+      {"-debug", FLAG, &o.debug},
+  };
+  /* options come first; what is left must be the mandatory arguments (none in batch mode) */
+  int i = 1;
+  for (; i < argc; ++i) {
+    const string arg = argv[i];
+    if (arg == "-h" || arg == "--help" || arg == "-help") { cerr << "Calculate mmseq expression estimates.\n"; usage_error(""); }
+    if (arg == "-v" || arg == "--version" || arg == "-version") { cerr << "mmseq-" << QUOTE(VERSION) << endl; exit(1); }
+    const Spec* hit = nullptr;
+    for (const Spec& sp : specs) if (arg == sp.name) { hit = &sp; break; }
+    if (!hit) break;
+    if (hit->kind == FLAG) { *static_cast<bool*>(hit->target) = true; continue; }
+    if (i + 1 >= argc) usage_error("Error: option " + arg + " needs a value.");
+    const char* val = argv[++i];
+    if (hit->kind == REAL) *static_cast<double*>(hit->target) = strtod(val, NULL);
+    else if (hit->kind == INT) *static_cast<int*>(hit->target) = atoi(val);
+    else *static_cast<string*>(hit->target) = val;
+    if (hit->target == &pct) parse_percentiles(pct, o.percentiles);
+  }
+  for (; i < argc; ++i) o.positional.push_back(argv[i]);
+  const size_t want = o.batch.empty() ? 2 : 0;
+  if (o.positional.size() != want) {
+    if (!o.positional.empty() && o.positional[0][0] == '-') usage_error("Error: unrecognised option " + o.positional[0] + ".");
+    usage_error("Error: mandatory arguments missing.");
   }
   /* src/mmseq.cpp:278-296 (a zero -gibbs_ss would divide by zero there; rejected here) */
-  if (gibbs_ss == 0 || gibbs_iter % gibbs_ss != 0) {
-    cerr << "Error: gibbs_iter must be divisible by gibbs_ss.\n";
-    printUsage(cerr);
-    exit(1);
-  }
-  gibbs_ss = gibbs_iter / trace_length;
-  if (gibbs_iter <= 0 || trace_length <= 0) {
-    cerr << "Error: no. of iteratons or trace length <= 0. Possible integer overflow - is gibbs_iter too high?\n";
-    printUsage(cerr);
-    exit(1);
-  }
-  if (!powerof2(trace_length)) {
-    cerr << "Error: gibbs_iter/gibbs_ss must be a power of 2.\n";
-    printUsage(cerr);
-    exit(1);
-  }
-  if (gibbs_ss <= 0) {
-    cerr << "Error: gibbs_iter must be at least " << trace_length << " (the trace length).\n";
-    printUsage(cerr);
-    exit(1);
-  }
-  if (ngpus < 1) die("Error: -gpus must be >= 1.");
-  const string hits_file = arguments[0];
-  const string output_base(arguments[1]);
+  if (o.gibbs_ss == 0 || o.gibbs_iter % o.gibbs_ss != 0) usage_error("Error: gibbs_iter must be divisible by gibbs_ss.");
+  o.gibbs_ss = o.gibbs_iter / o.trace_length; /* forced, as the reference does (:284) */
+  if (o.gibbs_iter <= 0 || o.trace_length <= 0)
+    usage_error("Error: no. of iteratons or trace length <= 0. Possible integer overflow - is gibbs_iter too high?");
+  if (!is_power_of_two(o.trace_length)) usage_error("Error: gibbs_iter/gibbs_ss must be a power of 2.");
+  if (o.gibbs_ss <= 0) usage_error("Error: gibbs_iter must be at least " + to_string(o.trace_length) + " (the trace length).");
+  if (o.ngpus < 1) die("Error: -gpus must be >= 1.");
+  if (o.per_gpu < 1) die("Error: -per_gpu must be >= 1.");
+  return o;
+}
+
+/* One sample: hits file in, the nine output files out (src/mmseq.cpp:312-1694).  first_device: the GPU of a
+ * single-GPU run, or the first of o.ngpus consecutive devices.  Messages go to out / err (the terminal for a
+ * single sample, the sample's log in batch mode). */
+static void run_sample(const Options& o, const string& hits_file, const string& output_base, int first_device, ostream& out, ostream& err) {
+  const double alpha = o.alpha, beta = o.beta, epsilon = o.epsilon;
+  const int max_em_iter = o.max_em_iter, gibbs_iter = o.gibbs_iter, trace_length = o.trace_length, gibbs_ss = o.gibbs_ss, seed = o.seed;
+  const vector<double>& percentiles = o.percentiles;
+  const bool debug = o.debug, notraces = o.notraces;
+  const int ngpus = o.ngpus;
 
   /* the CUDA contexts come up (1-2 s) while the hits file is being parsed */
-  thread warmup([ngpus] { for (int g = 0; g < ngpus; ++g) mmq_warmup(g); });
+  thread warmup([ngpus, first_device] { for (int g = 0; g < ngpus; ++g) mmq_warmup(first_device + g); });
 
   /* ---- load: header + records -> hit classes (src/hitsio.cpp, src/mmseq.cpp:312-441) */
   mmq::HitsHeader hdr;
@@ -346,7 +319,7 @@ int main(int argc, char** argv) {
     if (mmq::load_hits_file(hits_file, mmq::LAYOUT_COLLAPSED, hdr, cls, err)) { warmup.join(); die(err); }
   }
   warmup.join();
-  cout << "Running mmseq with parameters:\n"
+  out << "Running mmseq with parameters:\n"
        << "  alpha:         " << alpha << endl
        << "  beta:          " << beta << endl
        << "  max_em_iter:   " << max_em_iter << endl
@@ -362,7 +335,7 @@ int main(int argc, char** argv) {
   const int64_t G = (int64_t)hdr.gene_names.size(), I = (int64_t)hdr.identical.size();
   const int L = trace_length;
   phase("hits file loaded");
-  cout << "Found " << n << " transcripts in " << m << " transcript combinations.\r" << endl;
+  out << "Found " << n << " transcripts in " << m << " transcript combinations.\r" << endl;
   if (n == 0 || m == 0) die("Error: no mapped fragments in the hits file.");
 
   vector<double> l;
@@ -381,7 +354,7 @@ int main(int argc, char** argv) {
   vector<vector<int32_t>> shard_col((size_t)ngpus), shard_k((size_t)ngpus);
   for (int g = 0; g < ngpus; ++g) {
     Shard& S = shards[(size_t)g];
-    S.device = g;
+    S.device = first_device + g;
     mmq_problem p;
     memset(&p, 0, sizeof p);
     p.n = n;
@@ -430,7 +403,7 @@ int main(int argc, char** argv) {
   if (ngpus > 1) { /* Gibbs: all-reduce + Gamma update fused over NVLink peer memory (no NCCL call per sweep) */
     vector<mmq_handle*> hs;
     for (auto& S : shards) hs.push_back(S.h);
-    if (mmq_p2p_attach_local(hs.data(), ngpus)) cerr << "Note: peer access unavailable (" << mmq_last_error(hs[0]) << "); using NCCL for the count exchange." << endl;
+    if (mmq_p2p_attach_local(hs.data(), ngpus)) err << "Note: peer access unavailable (" << mmq_last_error(hs[0]) << "); using NCCL for the count exchange." << endl;
   }
   mmq_handle* H0 = shards[0].h;
 
@@ -442,16 +415,16 @@ int main(int argc, char** argv) {
   vector<int32_t> identical_unique_hits((size_t)I, 0), gene_unique_hits((size_t)G, 0);
   {
     phase("shards on the GPUs");
-    cerr << "Counting unique hits to sets of identical transcripts...";
+    err << "Counting unique hits to sets of identical transcripts...";
     vector<int32_t> set_of((size_t)n, -1);
     for (int64_t s = 0; s < I; ++s)
       for (int32_t hidx : hdr.identical[(size_t)s]) { int32_t c = cls.hdr2col[(size_t)hidx]; if (c >= 0) set_of[(size_t)c] = (int32_t)s; }
     if (I > 0) on_all([&](int g) { check(mmq_unique_hits_sets(shards[(size_t)g].h, set_of.data(), I, g == 0 ? identical_unique_hits.data() : vector<int32_t>((size_t)I).data()), shards[(size_t)g].h, "mmq_unique_hits_sets"); });
-    cerr << "done." << endl;
-    cerr << "Counting unique hits to genes...";
+    err << "done." << endl;
+    err << "Counting unique hits to genes...";
     for (int64_t t = 0; t < n; ++t) set_of[(size_t)t] = hdr.gene_of[(size_t)cls.col2hdr[(size_t)t]];
     on_all([&](int g) { check(mmq_unique_hits_sets(shards[(size_t)g].h, set_of.data(), G, g == 0 ? gene_unique_hits.data() : vector<int32_t>((size_t)G).data()), shards[(size_t)g].h, "mmq_unique_hits_sets"); });
-    cerr << "done." << endl;
+    err << "done." << endl;
   }
 
   /* ---- .k and .M (src/mmseq.cpp:682-695): one integer per line / "row<TAB>col" per nonzero.  The
@@ -530,8 +503,8 @@ int main(int argc, char** argv) {
   /* ---- EM (src/mmseq.cpp:741-820) */
   vector<double> mu_em((size_t)n);
   {
-    cout.precision(5);
-    cout.setf(ios::fixed, ios::floatfield);
+    out.precision(5);
+    out.setf(ios::fixed, ios::floatfield);
     auto t0 = chrono::steady_clock::now();
     int iters = 0;
     double loglik = 0, llr = 0;
@@ -539,7 +512,7 @@ int main(int argc, char** argv) {
       vector<int> it_g((size_t)ngpus); vector<double> ll_g((size_t)ngpus), llr_g((size_t)ngpus);
       on_all([&](int g) { check(mmq_em(shards[(size_t)g].h, max_em_iter, epsilon, &it_g[(size_t)g], &ll_g[(size_t)g], &llr_g[(size_t)g]), shards[(size_t)g].h, "mmq_em"); });
       iters = it_g[0]; loglik = ll_g[0]; llr = llr_g[0];
-      if (iters > 0) cout << "EM iteration " << iters - 1 << ", log likelihood ratio: " << llr << "            \r";
+      if (iters > 0) out << "EM iteration " << iters - 1 << ", log likelihood ratio: " << llr << "            \r";
     } else { /* one iteration per call so that every mu can be dumped (.trace_em.gz, :764-768) */
       GzText g(output_base + ".trace_em.gz");
       for (int64_t t = 0; t < n; t++) { g.put(hdr.names[(size_t)cls.col2hdr[(size_t)t]]); g.put(" "); }
@@ -550,7 +523,7 @@ int main(int argc, char** argv) {
       loglik = ll_g[0];
       llr = epsilon + 1;
       while (iters < max_em_iter && llr > epsilon) {
-        cout << "EM iteration " << iters << flush;
+        out << "EM iteration " << iters << flush;
         check(mmq_get_mu(H0, mu.data()), H0, "mmq_get_mu");
         for (int64_t t = 0; t < n; t++) { g.put(mu[(size_t)t]); g.put(" "); }
         g.put("\n");
@@ -558,35 +531,35 @@ int main(int argc, char** argv) {
         on_all([&](int gi) { check(mmq_em(shards[(size_t)gi].h, 1, -numeric_limits<double>::infinity(), nullptr, &l2[(size_t)gi], nullptr), shards[(size_t)gi].h, "mmq_em"); });
         llr = l2[0] - loglik;
         loglik = l2[0];
-        cout << ", log likelihood ratio: " << llr << "            \r";
+        out << ", log likelihood ratio: " << llr << "            \r";
         iters++;
       }
     }
-    cout << endl;
-    cout.unsetf(ios::floatfield);
-    cout.precision(6);
+    out << endl;
+    out.unsetf(ios::floatfield);
+    out.precision(6);
     const double sec = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
-    cerr << "EM: " << iters << " iterations in " << sec << " s" << endl;
+    err << "EM: " << iters << " iterations in " << sec << " s" << endl;
     check(mmq_get_mu(H0, mu_em.data()), H0, "mmq_get_mu");
   }
 
   /* ---- Gibbs (src/mmseq.cpp:822-918) */
   {
     auto t0 = chrono::steady_clock::now();
-    cout << "Gibbs iteration " << gibbs_iter - 1 << "       \r";
+    out << "Gibbs iteration " << gibbs_iter - 1 << "       \r";
     on_all([&](int g) {
       mmq_handle* h = shards[(size_t)g].h;
       check(mmq_gibbs(h, (uint32_t)seed, 0, gibbs_iter, gibbs_ss, L, MMQ_GIBBS_DEFAULT), h, "mmq_gibbs");
       check(mmq_synchronize(h), h, "mmq_synchronize");
     });
-    cout << endl;
+    out << endl;
     const double sec = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
-    cerr << "Gibbs: " << gibbs_iter << " sweeps in " << sec << " s (" << gibbs_iter / sec << " sweeps/s, " << (double)m * gibbs_iter / sec
+    err << "Gibbs: " << gibbs_iter << " sweeps in " << sec << " s (" << gibbs_iter / sec << " sweeps/s, " << (double)m * gibbs_iter / sec
          << " hit-class allocations/s)" << endl;
   }
 
   phase("EM + Gibbs");
-  cout << "Amalgamating transcripts and calculating summary statistics..." << flush;
+  out << "Amalgamating transcripts and calculating summary statistics..." << flush;
 
   /* ---- prior-simulated traces for isoforms without hits (src/mmseq.cpp:971-978), on the device */
   vector<int64_t> unobs;           /* header indices */
@@ -859,28 +832,75 @@ int main(int argc, char** argv) {
   });
   ofs.close(); ofs.clear();
 
-  cout << "done." << endl;
+  out << "done." << endl;
   for (auto& S : shards) mmq_destroy(S.h);
 
   phase("tables");
-  cout << "Output files: " << endl
+  out << "Output files: " << endl
        << "  " << output_base << ".mmseq" << endl
        << "  " << output_base << ".identical.mmseq" << endl
        << "  " << output_base << ".gene.mmseq" << endl;
-  cout << "  " << output_base << ".M" << endl << "  " << output_base << ".k" << endl << endl;
+  out << "  " << output_base << ".M" << endl << "  " << output_base << ".k" << endl << endl;
   if (!notraces)
-    cout << "  " << output_base << ".trace_gibbs.gz" << endl
+    out << "  " << output_base << ".trace_gibbs.gz" << endl
          << "  " << output_base << ".identical.trace_gibbs.gz" << endl
          << "  " << output_base << ".gene.trace_gibbs.gz" << endl
          << "  " << output_base << ".prop.trace_gibbs.gz" << endl
          << endl;
   if (debug) {
-    cout << endl
+    out << endl
          << "  " << output_base << ".trace_em.gz" << endl
          << "  " << output_base << ".sharedcounts" << endl
          << "  " << output_base << ".Mt-nodups" << endl
          << "  " << output_base << ".doublehits" << endl
          << "  " << output_base << ".dupIDs" << endl;
+  }
+}
+
+/* -batch FILE (config 5: many samples, independent chains): every line of FILE names a hits file and an output base.
+ * Samples are dealt to the GPUs of the box, per_gpu of them in flight per GPU (their parsing, host-side formatting
+ * and device work overlap); each runs as a single-GPU sample and writes its messages to <output_base>.log. */
+static int run_batch(const Options& o) {
+  vector<pair<string, string>> samples;
+  {
+    ifstream f(o.batch.c_str());
+    if (!f) die("Error: cannot open batch file " + o.batch + ".");
+    string a, b;
+    while (f >> a >> b) samples.emplace_back(a, b);
+  }
+  if (samples.empty()) die("Error: no samples in " + o.batch + ".");
+  Options one = o;
+  one.ngpus = 1;
+  const int workers = (int)min<size_t>(samples.size(), (size_t)o.ngpus * (size_t)o.per_gpu);
+  cout << "Batch of " << samples.size() << " samples on " << o.ngpus << " GPU(s), " << o.per_gpu << " in flight per GPU." << endl;
+  const auto t0 = chrono::steady_clock::now();
+  atomic<size_t> next{0};
+  vector<thread> th;
+  for (int w = 0; w < workers; ++w)
+    th.emplace_back([&, w] {
+      for (size_t i = next.fetch_add(1); i < samples.size(); i = next.fetch_add(1)) {
+        ostringstream log;
+        const auto s0 = chrono::steady_clock::now();
+        run_sample(one, samples[i].first, samples[i].second, w % o.ngpus, log, log);
+        log << "wall " << chrono::duration<double>(chrono::steady_clock::now() - s0).count() << " s on GPU " << w % o.ngpus << endl;
+        ofstream lf((samples[i].second + ".log").c_str());
+        lf << log.str();
+      }
+    });
+  for (auto& t : th) t.join();
+  const double wall = chrono::duration<double>(chrono::steady_clock::now() - t0).count();
+  cout << "Batch done: " << samples.size() << " samples in " << wall << " s (" << samples.size() / wall << " samples/s, "
+       << (double)samples.size() * o.gibbs_iter / wall << " Gibbs sweeps/s over all samples)." << endl;
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  phase("start");
+  const Options o = parse_command_line(argc, argv);
+  if (!o.batch.empty()) {
+    run_batch(o);
+  } else {
+    run_sample(o, o.positional[0], o.positional[1], 0, cout, cerr);
   }
   /* every output file is closed: leave without unwinding gigabytes of host vectors and the CUDA
    * contexts (1-2 s at 30M fragments); exit status 0 as src/mmseq.cpp:1727 */

@@ -78,3 +78,45 @@ def test_config5_batch_of_samples_independent_chains():
         assert np.allclose(S["log_mean"], O["log_mu"], rtol=1e-12, atol=1e-12)
         assert np.allclose(S["tau"], O["iact"], rtol=1e-8, atol=1e-10, equal_nan=True)   # Sokal IACT per sample
         H.close()
+
+
+def test_config5_eight_handles_per_gpu_on_every_gpu_from_threads():
+    """The batch driver's shape (bench.py --batch, `mmseq -batch`): 8 samples in flight per GPU on every visible GPU,
+    each driven by its own host thread on its own stream; every chain equals its replay, Sokal summaries per sample."""
+    import threading
+    import torch
+    ngpu = torch.cuda.device_count()
+    per_gpu = 8
+    jobs = [(g, i) for g in range(ngpu) for i in range(per_gpu)]
+    results, errors = {}, []
+
+    def work(g, i):
+        try:
+            s = synth.Synth(20260101 + 5, 200, 6000, frag_seed=100 * g + i)
+            h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid)
+            with capi.Handle(h.row_ptr, h.col, h.k, h.len, device=g) as H:
+                H.init_mu()
+                it, _, _ = H.em(1000, 0.1)
+                mu_em = H.get_mu()
+                H.gibbs(7 + i, 0, 64, stride=4, trace_len=16)
+                S = H.summarize(0, [1, 8, 14])
+                results[(g, i)] = (h, it, mu_em, H.get_trace(), H.get_mu(), S)
+        except Exception as e:   # pragma: no cover
+            errors.append(repr(e))
+
+    th = [threading.Thread(target=work, args=j) for j in jobs]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errors, errors
+    assert len(results) == ngpu * per_gpu
+    for (g, i), (h, it, mu_em, tr, mu_end, S) in results.items():
+        P = orc.Problem(h.row_ptr, h.col, h.k, h.len)
+        mu_o, it_o, _, _ = P.em(P.init_mu()[0], 1000, 0.1)
+        assert it == it_o and np.max(np.abs(mu_em / mu_o - 1)) <= 1e-6
+        mu_r, tr_o = P.gibbs_replay(mu_em, 7 + i, 0, 64, 4, 16)
+        assert np.array_equal(tr, tr_o) and np.array_equal(mu_end, mu_r), (g, i)
+        O = orc.summaries_transcripts(tr_o, (5, 50, 95))
+        assert np.allclose(S["log_mean"], O["log_mu"], rtol=1e-12, atol=1e-12)
+        assert np.allclose(S["tau"], O["iact"], rtol=1e-8, atol=1e-10, equal_nan=True)
