@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <chrono>
 #include <condition_variable>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -132,7 +133,7 @@ class ByteSource {
         while (got < blk.size() && !last) {
           if (zs_.avail_in == 0) {
             size_t r = fread(in_.data(), 1, in_.size(), f_);
-            if (r == 0) { last = true; break; }
+            if (r == 0) { corrupt_ = true; last = true; break; } /* the file ends before the zlib stream does: truncated */
             zs_.next_in = (Bytef*)in_.data();
             zs_.avail_in = (uInt)r;
           }
@@ -659,9 +660,13 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
     tok >> t1;
     if (t1 == "@TranscriptMetaData") hdr.schema = 0;
     else if (line == "MMSEQ_HITSFILE") {
+      /* schema 1: the reference's binary format (src/hitsio.cpp:403-410 accepts nothing else); schema 2 (this
+       * package's extension): the same stream with one fp32 weight per hit after a record's
+       * transcript indices — likelihood x insert-size x bias weight of the alignment, what bam2hits computes and then
+       * throws away (src/bam2hits.cpp:778-801, :992-1003) */
       uint32_t s = 99;
-      if (!src.read_u32(s) || s != 1) { err = "Input file \"" + path + "\" does not seem to be a hits file."; return 1; }
-      hdr.schema = 1;
+      if (!src.read_u32(s) || (s != 1 && s != 2)) { err = "Input file \"" + path + "\" does not seem to be a hits file."; return 1; }
+      hdr.schema = (int)s;
     } else { err = "Input file \"" + path + "\" does not seem to be a hits file."; return 1; }
   }
   if (hdr.schema == 0) {
@@ -734,8 +739,13 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
   const bool timing = getenv("MMQ_LOADER_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_hdr = now();
-  ClassBuilder cb(T, layout, false);
+  if (hdr.schema == 2 && (layout & 15) == LAYOUT_COLLAPSED) {
+    err = "Error: \"" + path + "\" carries per-hit weights (schema 2): it needs a per-fragment layout.";
+    return 1;
+  }
+  ClassBuilder cb(T, layout, hdr.schema == 2);
   std::vector<int32_t> tids;
+  std::vector<float> wts;
   if (hdr.schema == 0) {
     /* records, src/hitsio.cpp:331-347 */
     idx.build_fast(hdr.names);
@@ -755,6 +765,10 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
         if (h < 0) { err = "Error: transcript '" + std::string(lp, ln) + "' has no length."; return 1; } /* src/mmseq.cpp:599-601 */
         tids.push_back(h);
       }
+      if (tids.empty()) { /* the reference would open a hit class with no transcripts (src/mmseq.cpp:401-440): refused here */
+        err = "Error: a read record without any mapping transcripts in the hits file.";
+        return 1;
+      }
       cb.add_record(tids.data(), nullptr, (int)tids.size());
     }
   } else {
@@ -763,24 +777,30 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
     for (;;) {
       const char* lp; size_t ln;
       if (!src.getline_view(lp, ln)) break;
+      /* the stream may end between records only: anything missing inside one is a malformed (truncated) file */
+      const std::string malformed = "Hits file looks malformed.";
       if (ln == 0) {
         uint32_t nb = 0, ne = 0;
-        if (!src.read_small(nb)) break;
-        if (!src.getline_view(lp, ln)) break;
-        if (!src.read_small(ne)) break;
+        if (!src.read_small(nb) || !src.getline_view(lp, ln) || !src.read_small(ne)) { err = src.corrupt() ? "Error: zlib stream of \"" + path + "\" is corrupt." : malformed; return 1; }
       }
       uint32_t cnt = 0;
-      if (!src.read_u32(cnt)) break;
+      if (!src.read_u32(cnt)) { err = src.corrupt() ? "Error: zlib stream of \"" + path + "\" is corrupt." : malformed; return 1; }
+      if (cnt == 0) { err = "Error: a read record without any mapping transcripts in the hits file."; return 1; }
+      if (cnt > (uint32_t)all_names.size()) { err = malformed; return 1; } /* more hits than transcripts: not a count */
       tids.resize(cnt);
-      bool ok = true;
       for (uint32_t j = 0; j < cnt; ++j) {
         uint32_t v = 0;
-        if (!src.read_u32(v)) { ok = false; break; }
-        if (v >= (uint32_t)all_names.size()) { err = "Hits file looks malformed."; return 1; }
+        if (!src.read_u32(v)) { err = src.corrupt() ? "Error: zlib stream of \"" + path + "\" is corrupt." : malformed; return 1; }
+        if (v >= (uint32_t)all_names.size()) { err = malformed; return 1; }
         tids[j] = (int32_t)v;
       }
-      if (!ok) break;
-      cb.add_record(tids.data(), nullptr, (int)cnt);
+      if (hdr.schema == 2) {
+        wts.resize(cnt);
+        if (!src.read_bytes(wts.data(), sizeof(float) * cnt)) { err = src.corrupt() ? "Error: zlib stream of \"" + path + "\" is corrupt." : malformed; return 1; }
+        for (uint32_t j = 0; j < cnt; ++j)
+          if (!(wts[j] >= 0.f) || !std::isfinite(wts[j])) { err = "Error: per-hit weights must be finite and non-negative."; return 1; }
+      }
+      cb.add_record(tids.data(), hdr.schema == 2 ? wts.data() : nullptr, (int)cnt);
     }
   }
   if (src.corrupt()) { err = "Error: zlib stream of \"" + path + "\" is corrupt."; return 1; }

@@ -19,7 +19,7 @@
 namespace mmq {
 
 struct HitsHeader {
-  int schema = 0;                              /* 0 text, 1 binary */
+  int schema = 0;                              /* 0 text, 1 binary, 2 binary with per-hit weights */
   std::vector<std::string> names;              /* header order = transcriptList */
   std::vector<double> efflen;                  /* sidLen */
   std::vector<int32_t> truelen;                /* sidSeqLen */

@@ -192,7 +192,8 @@ void* mmq_synth_create(uint64_t seed, uint64_t frag_seed, int64_t T_base, int64_
 }
 
 /* Fast writers for large hits files (the Python writers in synth.py are for small cases).
- * schema 0 = text (src/hitsio.cpp:162-187), schema 1 = zlib-binary (:189-240), names as synth.py. */
+ * schema 0 = text (src/hitsio.cpp:162-187), schema 1 = zlib-binary (:189-240), schema 2 = schema 1 plus one fp32 weight
+ * per hit after a record's transcript indices (needs a generator made with weights); names as synth.py. */
 static void tname(char* buf, int64_t t, int haplo) {
   if (haplo) snprintf(buf, 40, "T%07lld_%c", (long long)(t / 2), "AB"[t % 2]);
   else snprintf(buf, 40, "T%07lld", (long long)t);
@@ -206,7 +207,8 @@ int mmq_synth_write_hits(void* p, const char* path, int schema, int haplo) {
   FILE* f = fopen(path, "wb");
   if (!f) return 1;
   std::vector<unsigned char> zbuf((size_t)8 << 20);
-  if (schema == 1) { memset(&zs, 0, sizeof zs); if (deflateInit(&zs, 1) != Z_OK) { fclose(f); return 2; } }
+  if (schema == 2 && S->frag_w.empty()) { fclose(f); return 3; }
+  if (schema >= 1) { memset(&zs, 0, sizeof zs); if (deflateInit(&zs, 1) != Z_OK) { fclose(f); return 2; } }
   auto flush = [&](bool finish) {
     if (schema == 0) { fwrite(out.data(), 1, out.size(), f); out.clear(); return; }
     zs.next_in = (Bytef*)out.data(); zs.avail_in = (uInt)out.size();
@@ -231,7 +233,7 @@ int mmq_synth_write_hits(void* p, const char* path, int schema, int haplo) {
       if (out.size() > ((size_t)48 << 20)) flush(false);
     }
   } else {
-    out += "MMSEQ_HITSFILE\n"; u32(1); u32((uint32_t)S->T);
+    out += "MMSEQ_HITSFILE\n"; u32((uint32_t)schema); u32((uint32_t)S->T);
     for (int64_t t = 0; t < S->T; ++t) { tname(nm, t, haplo); out += nm; out += "\n"; snprintf(tmp, sizeof tmp, "%g\n", S->efflen[(size_t)t]); out += tmp; u32((uint32_t)S->truelen[(size_t)t]); }
     u32((uint32_t)S->G);
     for (int64_t g = 0; g < S->G; ++g) {
@@ -253,11 +255,12 @@ int mmq_synth_write_hits(void* p, const char* path, int schema, int haplo) {
       const int64_t b = S->frag_ptr[(size_t)r], e = S->frag_ptr[(size_t)r + 1];
       u32((uint32_t)(e - b));
       for (int64_t q = b; q < e; ++q) u32((uint32_t)S->frag_tid[(size_t)q]);
+      if (schema == 2) out.append((const char*)(S->frag_w.data() + b), sizeof(float) * (size_t)(e - b));
       if (out.size() > ((size_t)48 << 20)) flush(false);
     }
   }
   flush(true);
-  if (schema == 1) deflateEnd(&zs);
+  if (schema >= 1) deflateEnd(&zs);
   fclose(f);
   return 0;
 }

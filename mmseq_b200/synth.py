@@ -64,11 +64,12 @@ class Synth:
         self.haplo = haplo
         self._args = (seed, frag_seed, T // (2 if haplo else 1), N, int(haplo), int(weights), threads)
 
-    def write_hits_fast(self, path, binary=True):
-        """C++ writer for large files (no identical-transcript records); same bytes as the Python writers."""
+    def write_hits_fast(self, path, binary=True, weights=False):
+        """C++ writer for large files (no identical-transcript records); same bytes as the Python writers.
+        weights=True: schema 2 (binary + one fp32 weight per hit; the generator must have been made with weights)."""
         L = lib()
         h = L.mmq_synth_create(*self._args)
-        rc = L.mmq_synth_write_hits(h, os.fsencode(path), 1 if binary else 0, int(self.haplo))
+        rc = L.mmq_synth_write_hits(h, os.fsencode(path), 2 if weights else (1 if binary else 0), int(self.haplo))
         L.mmq_synth_destroy(h)
         if rc:
             raise RuntimeError(f"cannot write {path}")
@@ -113,10 +114,11 @@ def _small(v):
     return bytes([v]) if v < 255 else b"\xff" + _u32(v)
 
 
-def write_hits_binary(s, path, identical=None):
-    """Schema 1, whole stream zlib-compressed (src/hitsio.cpp:189-213, :232-240, :77-99)."""
+def write_hits_binary(s, path, identical=None, weights=None):
+    """Schema 1, whole stream zlib-compressed (src/hitsio.cpp:189-213, :232-240, :77-99).  With `weights` (fp32, one
+    per hit, aligned with s.frag_tid): schema 2, this package's extension — the weights follow a record's indices."""
     out = bytearray()
-    out += b"MMSEQ_HITSFILE\n" + _u32(1)
+    out += b"MMSEQ_HITSFILE\n" + _u32(1 if weights is None else 2)
     out += _u32(s.T)
     for t in range(s.T):
         out += s.transcript_name(t).encode() + b"\n" + _fmt_g6(s.efflen[t]).encode() + b"\n" + _u32(int(s.truelen[t]))
@@ -150,5 +152,7 @@ def write_hits_binary(s, path, identical=None):
         b, e = int(fp[r]), int(fp[r + 1])
         out += _u32(e - b)
         out += np.asarray(ft[b:e], dtype="<u4").tobytes()
+        if weights is not None:
+            out += np.asarray(weights[b:e], dtype="<f4").tobytes()
     with open(path, "wb") as f:
         f.write(zlib.compress(bytes(out), 1))

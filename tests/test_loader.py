@@ -148,3 +148,56 @@ def test_header_order_columns_is_a_pure_renumbering(small_synth):
                     wa = dict(zip(ha, a.w[a.row_ptr[i]:a.row_ptr[i + 1]])); wb = dict(zip(hb, b.w[b.row_ptr[i]:b.row_ptr[i + 1]]))
                     assert wa == wb
         assert np.allclose(np.sort(a.len), np.sort(b.len))
+
+
+def test_schema2_weighted_hits_round_trip(tmp_path):
+    """Schema 2 (this package's extension): binary records with one fp32 weight per hit.  The loader gives the
+    per-fragment CSR with the weights aligned to the columns — the same arrays as from the in-memory records."""
+    s = synth.Synth(11, 120, 3000, weights=True)
+    p = str(tmp_path / "w.hits")
+    synth.write_hits_binary(s, p, weights=s.frag_w)
+    pf = str(tmp_path / "wf.hits")
+    s.write_hits_fast(pf, weights=True)
+    assert open(p, "rb").read() == open(pf, "rb").read()          # the C++ writer emits the same bytes
+    for lay in (hostlib.LAYOUT_PER_FRAGMENT, hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH):
+        a = hostlib.load_hits(p, layout=lay)
+        b = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, frag_w=s.frag_w, layout=lay)
+        assert a.schema == 2 and a.w is not None and a.m == s.N
+        assert np.array_equal(a.row_ptr, b.row_ptr) and np.array_equal(a.col2hdr[a.col], b.col2hdr[b.col]) and np.array_equal(a.w, b.w)
+    with pytest.raises(RuntimeError, match="per-fragment layout"):
+        hostlib.load_hits(p)                                        # the collapsed layout cannot carry weights
+
+
+def test_truncated_and_degenerate_files_are_refused(tmp_path):
+    """ADVICE (round 1): a zlib stream cut short, a binary record cut mid-way, a record without transcripts and a hit
+    count above the number of transcripts are errors, not silently shorter samples."""
+    import struct
+    import zlib
+    s = synth.Synth(5, 80, 2000)
+    p = str(tmp_path / "ok.hits")
+    synth.write_hits_binary(s, p)
+    raw = open(p, "rb").read()
+    assert hostlib.load_hits(p).N == 2000
+    cut = str(tmp_path / "cut.hits")
+    open(cut, "wb").write(raw[:len(raw) // 2])                      # truncated zlib stream
+    with pytest.raises(RuntimeError, match="corrupt"):
+        hostlib.load_hits(cut)
+    plain = zlib.decompress(raw)
+    mid = str(tmp_path / "mid.hits")
+    open(mid, "wb").write(zlib.compress(plain[:-6], 1))             # complete stream, last record cut inside its index list
+    with pytest.raises(RuntimeError, match="malformed"):
+        hostlib.load_hits(mid)
+    empty = str(tmp_path / "empty.hits")
+    open(empty, "wb").write(zlib.compress(plain + b"rx\n" + struct.pack("<I", 0), 1))   # a record with no transcripts
+    with pytest.raises(RuntimeError, match="without any mapping transcripts"):
+        hostlib.load_hits(empty)
+    big = str(tmp_path / "big.hits")
+    open(big, "wb").write(zlib.compress(plain + b"ry\n" + struct.pack("<I", 4000000000), 1))   # an absurd hit count
+    with pytest.raises(RuntimeError, match="malformed"):
+        hostlib.load_hits(big)
+    txt = str(tmp_path / "t.hits")
+    synth.write_hits_text(synth.Synth(5, 20, 50), txt)
+    body = open(txt).read().replace(">r10\n", ">r10\n>r10b\n", 1)   # text: a read name directly followed by the next one
+    open(txt, "w").write(body)
+    with pytest.raises(RuntimeError, match="without any mapping transcripts"):
+        hostlib.load_hits(txt)
