@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--cpu-sweeps", type=int, default=768, help="most sweeps of the CPU baseline / posterior-gate chain (rank 0, N = 1)")
     ap.add_argument("--cpu-seconds", type=float, default=30.0, help="... and its time budget (at least 16 trace samples are taken)")
     ap.add_argument("--nccl-only", action="store_true", help="N > 1: exchange counts with ncclAllReduce instead of the fused peer-memory kernel")
+    ap.add_argument("--p2p-rs", action="store_true", help="N > 1: reduce-scatter / all-gather variant of the fused exchange (mmq_tune knob 6)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gates", action="store_true")
@@ -522,15 +523,27 @@ def run_batch(args, rank, world, local):
     done = []
     lock = threading.Lock()
 
+    nprod = max(1, min(args.batch_per_gpu, 3))   # class construction of the next samples on several host threads
+    it_lock = threading.Lock()
+    it_state = {"next": 0, "left": nprod}
+
     def producer():
-        for i in mine:
+        while True:
+            with it_lock:
+                if it_state["next"] >= len(mine):
+                    it_state["left"] -= 1
+                    last = it_state["left"] == 0
+                    break
+                i = mine[it_state["next"]]
+                it_state["next"] += 1
             t0 = time.perf_counter()
             s = synth.Synth(SYNTH_SEED, args.transcripts, args.fragments, frag_seed=1000 + i)
             h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_COLLAPSED | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
             length = s.efflen[h.col2hdr] * args.fragments / 1e9
             q.put((i, h, length, time.perf_counter() - t0))
-        for _ in range(args.batch_per_gpu):
-            q.put(None)
+        if last:
+            for _ in range(args.batch_per_gpu):
+                q.put(None)
 
     def worker():
         stream = torch.cuda.Stream(device=dev)
@@ -562,7 +575,7 @@ def run_batch(args, rank, world, local):
     torch.cuda.synchronize()
     launches0 = capi.launch_count()
     t0 = time.perf_counter()
-    th = [threading.Thread(target=producer)] + [threading.Thread(target=worker) for _ in range(args.batch_per_gpu)]
+    th = [threading.Thread(target=producer) for _ in range(nprod)] + [threading.Thread(target=worker) for _ in range(args.batch_per_gpu)]
     for t in th:
         t.start()
     for t in th:
@@ -649,6 +662,8 @@ def main():
             hs = [None] * world
             dist.all_gather_object(hs, Hx.p2p_export())
             Hx.p2p_attach(hs, rank, world)
+        if args.p2p_rs:
+            Hx.tune(6, 1)
 
     H = capi.Handle(h.row_ptr, h.col, h.k, w.length, weight=h.w, class_id_base=w.cid_base, device=local)
     H.set_stream(stream.cuda_stream)

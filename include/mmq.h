@@ -163,8 +163,9 @@ int mmq_rows_stats(mmq_handle* h, int64_t out[8]);
 /* Launch-geometry knobs of the class-plan sweep, for measurements (tools/gpu_tune_cls.py); value 0 restores the
  * default.  knob 0: bit mask of pieces NOT launched (1 k >= 2 small classes, 2 rest, 4 k >= 2 large classes, 8 chain,
  * 16 single-fragment classes: timing experiments only, the chain is then wrong); knobs 1..4: resident CTAs per SM the
- * grid of the chain / large / small / single-fragment kernel is capped at; knob 5: launch order variant.  Results do
- * not depend on knobs 1..5. */
+ * grid of the chain / large / small / single-fragment kernel is capped at; knob 5: launch order variant; knob 6: 1 =
+ * the multi-GPU count exchange as reduce-scatter + all-gather (k_gamma_rs) instead of the all-reduce inside the Gamma
+ * kernel (all ranks must set it alike).  Results do not depend on knobs 1..6. */
 int mmq_tune(mmq_handle* h, int knob, int value);
 
 /* Device time of the launches made under MMQ_GIBBS_TIME_KERNELS since the last

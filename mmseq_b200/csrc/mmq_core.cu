@@ -700,8 +700,10 @@ struct mmq_p2p_args {
 __global__ void __launch_bounds__(MMQ_GAMMA_THREADS)
 k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
             double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
-            double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy) {
+            double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy,
+            const uint32_t* __restrict__ sweep_base) {
   __shared__ gamma_smem S;
+  if (sweep_base) sweep += *sweep_base;
   const int32_t epoch = a.epoch + (a.epoch_base ? *a.epoch_base : 0);
   int32_t* own = reinterpret_cast<int32_t*>(a.base[a.rank]);
   if (blockIdx.x == 0 && threadIdx.x < a.nranks)
@@ -1465,13 +1467,16 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
     a.epoch = epoch_base ? (int32_t)(h->p2p_epoch - h->graph_epoch0) : (int32_t)h->p2p_epoch;
     a.epoch_base = epoch_base;
     mark(h->ev_gamma);
-    if (counts_copy) { /* debug / parity: full all-reduce, summed counts kept */
+    if (counts_copy || h->tune[6] != 1) {
+      /* default: every rank reads the count vectors of all ranks and draws every Gamma variate — ONE barrier per sweep.
+       * (The Gamma kernel is bound by the latency of one pass, not by throughput, so drawing n / N variates instead of
+       * n saves nothing, while the reduce-scatter variant below pays a second barrier and the peer stores: measured at
+       * N = 2, 36 us against 24 us per sweep.) */
       k_gamma_p2p<<<mmq_grid_for(h->n, MMQ_GAMMA_THREADS, h->num_sms * 4), MMQ_GAMMA_THREADS, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
-                                                                                h->trace_len, h->n, h->alpha, h->beta, seed, sweep, counts_copy);
+                                                                                h->trace_len, h->n, h->alpha, h->beta, seed, sweep, counts_copy, sweep_base);
       MMQ_LAUNCHED(h);
-    } else {
+    } else { /* mmq_tune(h, 6, 1): reduce-scatter + Gamma + all-gather */
       const int64_t slice = (h->n + h->p2p_n - 1) / h->p2p_n;
-      /* the grid must be co-resident (its last block waits for the peers while the others finish): <= 8 blocks of 128 per SM */
       k_gamma_rs<<<mmq_grid_for(std::max<int64_t>(slice, h->n / 8), MMQ_GAMMA_THREADS, h->num_sms * 4), MMQ_GAMMA_THREADS, 0, h->stream>>>(a, h->seg_base, h->len, h->n, h->alpha, h->beta, seed, sweep, sweep_base);
       MMQ_LAUNCHED(h);
       /* is this sweep recorded?  plain launch: the host knows; graph capture: sweep = j, the replays start at

@@ -256,7 +256,7 @@ template <bool HAS_W, int STAGE, int NW, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB)
 k_alloc_seg4(const mmq_seg* __restrict__ segs, int nsegs, int total_chunks, int nwarps, const int32_t* __restrict__ colp,
              const float* __restrict__ wp, const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
-             uint32_t sweep, int dbg_dmin, int dbg_dmax, int dbg_red, const uint32_t* __restrict__ sweep_base) {
+             uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
   if (sweep_base) sweep += *sweep_base; /* CUDA-graph replays: the sweep counter lives on the device */
   constexpr int WARP_BYTES = MMQ_SEG4_ROWS * STAGE * 4 * (HAS_W ? 2 : 1);
   extern __shared__ __align__(16) unsigned char seg4_smem[];
@@ -315,10 +315,10 @@ k_alloc_seg4(const mmq_seg* __restrict__ segs, int nsegs, int total_chunks, int 
       uint32_t sw_ = sweep;
       asm volatile("" : "+r"(sw_)); /* keeps the first Philox round in the loop instead of in spilled registers */
       wd[0] = (uint32_t)(cid >> 2); wd[1] = (uint32_t)(cid >> 34); wd[2] = sw_; wd[3] = 0u;
-      if (!(dbg_red & 4)) mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
+      mmq_philox4x32_10(wd, seed, MMQ_STREAM_CAT);
     }
     int32_t out[4] = {-1, -1, -1, -1};
-    const bool skip = D < dbg_dmin || D > dbg_dmax; /* timing experiments only (MMQ_DEBUG_DMIN / _DMAX) */
+    constexpr bool skip = false;
     if (D <= STAGE) {
       mbar_wait(bar, phase);
       phase ^= 1u;
@@ -361,12 +361,7 @@ k_alloc_seg4(const mmq_seg* __restrict__ segs, int nsegs, int total_chunks, int 
     }
     /* counts[c] += 1, one reduction per distinct column of the warp and row slot; the four matches are
      * issued back to back.  Masked rows share the key -1 (never reduced). */
-    if (dbg_red & 2) {
-    } else if (dbg_red & 1) { /* timing experiments only: no aggregation */
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-        if (((vmask >> r) & 1u) && !skip) atomicAdd(counts + out[r], 1);
-    } else {
+    {
       unsigned grp[4];
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
@@ -524,10 +519,6 @@ int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
   if (rc) return rc;
   if ((rc = mmq_seg_pack(h))) return rc;
   if (h->seg_count == 0) return MMQ_OK; /* only singletons: nothing random to do */
-  /* timing experiments only */
-  static const int dbg_dmin = [] { const char* e = getenv("MMQ_DEBUG_DMIN"); return e ? atoi(e) : 0; }();
-  static const int dbg_dmax = [] { const char* e = getenv("MMQ_DEBUG_DMAX"); return e ? atoi(e) : 0x7fffffff; }();
-  static const int dbg_red = [] { const char* e = getenv("MMQ_DEBUG_RED"); return e ? atoi(e) : 0; }();
   /* geometry (tuning knob): 0 = the measured best */
   static const int geo = [] { const char* e = getenv("MMQ_SEG_GEO"); return e ? atoi(e) : 0; }();
   const int chunks = (int)h->seg_chunks;
@@ -539,7 +530,7 @@ int mmq_seg_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
     MMQ_CUDA(h, cudaFuncSetAttribute(k_alloc_seg4<W, ST, NW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM));      \
     k_alloc_seg4<W, ST, NW, MINB><<<grid, NW * 32, SM, h->stream>>>((const mmq_seg*)h->seg_table, h->seg_count, chunks,     \
                                                                     grid * NW, h->seg_col, h->seg_w, h->mu, h->counts, seed, \
-                                                                    sweep, dbg_dmin, dbg_dmax, dbg_red, sweep_base);        \
+                                                                    sweep, sweep_base);                                 \
   } while (0)
   if (h->has_w) {
     if (geo == 1) MMQ_SEG4_GO(true, 8, 4, 6);
