@@ -212,11 +212,11 @@ k_alloc_cls(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, co
  * 56 registers — twice the resident warps of the general 9..16 instance, which is what hides the column load -> mu
  * gather -> sum chain of two memory latencies. */
 template <int D>
-__device__ __forceinline__ void cls1_chunk(const int32_t (&c)[MMQ_CLS_DREG], bool live, uint32_t cid, uint32_t cid_hi, const double* __restrict__ mu,
+__device__ __forceinline__ void cls1_chunk(const int32_t* __restrict__ pc, bool live, uint32_t cid, uint32_t cid_hi, const double* __restrict__ mu,
                                            int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, int lane) {
   double S[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) S[j] = mu[c[j]];
+  for (int j = 0; j < D; ++j) S[j] = mu[__ldg(pc + 32 * j)];
   const uint32_t word = cls_word1(cid, cid_hi, sweep, seed); /* independent of the loads in flight */
 #pragma unroll
   for (int j = 1; j < D; ++j) S[j] = S[j - 1] + S[j];
@@ -224,10 +224,7 @@ __device__ __forceinline__ void cls1_chunk(const int32_t (&c)[MMQ_CLS_DREG], boo
   int chosen = D - 1;
 #pragma unroll
   for (int j = 0; j < D - 1; ++j) chosen -= (target < S[j]) ? 1 : 0; /* S is non-decreasing: first j with target < S_j */
-  int32_t cc = c[0];
-#pragma unroll
-  for (int j = 1; j < D; ++j) cc = chosen == j ? c[j] : cc;
-  cat_red(counts, live ? cc : -1, lane);
+  cat_red(counts, live ? __ldg(pc + 32 * chosen) : -1, lane);
 }
 /* any class size: the members are read twice (the second time from L1) */
 __device__ __noinline__ void cls1_chunk_any(const int32_t* __restrict__ pc, int D, bool live, uint32_t cid, uint32_t cid_hi,
@@ -243,10 +240,7 @@ __device__ __noinline__ void cls1_chunk_any(const int32_t* __restrict__ pc, int 
   }
   cat_red(counts, live ? pc[32 * chosen] : -1, lane);
 }
-/* The kernel is bound by two dependent memory latencies per chunk (its columns, then the mu they point to), so the
- * columns are fetched ONE CHUNK AHEAD into registers (and the 8-byte descriptors two ahead): when a chunk's turn comes
- * its mu gathers go out at once. */
-__global__ void __launch_bounds__(MMQ_CLS_WARPS * 32, 6)
+__global__ void __launch_bounds__(MMQ_CLS_WARPS * 32, 9)
 k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, const uint16_t* __restrict__ pk, const uint32_t* __restrict__ pcid,
              const unsigned long long* __restrict__ cdesc, uint32_t cid_hi, const double* __restrict__ mu, int32_t* __restrict__ counts,
              uint32_t seed, uint32_t sweep, const uint32_t* __restrict__ sweep_base) {
@@ -257,40 +251,29 @@ k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, c
   /* the largest classes first (the plan orders the chunks by ascending size) */
   auto chunk_of = [&](int i) { return chunk_end - 1 - i; };
   int i = blockIdx.x * MMQ_CLS_WARPS + (threadIdx.x >> 5);
-  if (i >= count) return;
-  auto fetch_cols = [&](unsigned long long desc, int32_t (&c)[MMQ_CLS_DREG]) {
-    const int D = (int)(desc & 0xffull);
-    const int32_t* pc = pcol + (desc >> 8) + lane;
-#pragma unroll
-    for (int j = 0; j < MMQ_CLS_DREG; ++j)
-      if (j < D) c[j] = __ldg(pc + 32 * j); /* D > MMQ_CLS_DREG: the generic path reads the rest itself */
-  };
-  unsigned long long desc_c = cdesc[chunk_of(i)];
-  unsigned long long desc_n = i + nwarps < count ? cdesc[chunk_of(i + nwarps)] : 0ull;
-  uint32_t meta_n = pk[(int64_t)chunk_of(i) * 32 + lane], cid_n = pcid[(int64_t)chunk_of(i) * 32 + lane];
-  int32_t cn[MMQ_CLS_DREG];
-  fetch_cols(desc_c, cn);
+  uint32_t meta_n = 0, cid_n = 0;
+  unsigned long long desc_n = 0ull;
+  if (i < count) {
+    meta_n = pk[(int64_t)chunk_of(i) * 32 + lane];
+    cid_n = pcid[(int64_t)chunk_of(i) * 32 + lane];
+    desc_n = cdesc[chunk_of(i)];
+  }
   for (; i < count; i += nwarps) {
-    int32_t c[MMQ_CLS_DREG];
-#pragma unroll
-    for (int j = 0; j < MMQ_CLS_DREG; ++j) c[j] = cn[j];
-    const unsigned long long desc = desc_c;
-    const int D = (int)(desc & 0xffull);
+    const int D = (int)(desc_n & 0xffull);
+    const int32_t* pc = pcol + (desc_n >> 8) + lane;
     const bool live = (meta_n & 0xffu) != 0u; /* padding lanes make no draw */
     const uint32_t cid = cid_n;
-    desc_c = desc_n;
-    if (i + nwarps < count) { /* the next chunk's columns and metadata, the descriptor after it */
-      fetch_cols(desc_c, cn);
+    if (i + nwarps < count) { /* metadata one chunk ahead: its latency is off the critical path */
       meta_n = pk[(int64_t)chunk_of(i + nwarps) * 32 + lane];
       cid_n = pcid[(int64_t)chunk_of(i + nwarps) * 32 + lane];
-      desc_n = i + 2 * nwarps < count ? cdesc[chunk_of(i + 2 * nwarps)] : 0ull;
+      desc_n = cdesc[chunk_of(i + nwarps)];
     }
-#define MMQ_CLS1_CASE(DD) case DD: cls1_chunk<DD>(c, live, cid, cid_hi, mu, counts, seed, sweep, lane); break;
+#define MMQ_CLS1_CASE(DD) case DD: cls1_chunk<DD>(pc, live, cid, cid_hi, mu, counts, seed, sweep, lane); break;
     switch (D) {
       MMQ_CLS1_CASE(2) MMQ_CLS1_CASE(3) MMQ_CLS1_CASE(4) MMQ_CLS1_CASE(5) MMQ_CLS1_CASE(6) MMQ_CLS1_CASE(7) MMQ_CLS1_CASE(8)
       MMQ_CLS1_CASE(9) MMQ_CLS1_CASE(10) MMQ_CLS1_CASE(11) MMQ_CLS1_CASE(12) MMQ_CLS1_CASE(13) MMQ_CLS1_CASE(14) MMQ_CLS1_CASE(15)
       MMQ_CLS1_CASE(16)
-      default: cls1_chunk_any(pcol + (desc >> 8) + lane, D, live, cid, cid_hi, mu, counts, seed, sweep, lane); break;
+      default: cls1_chunk_any(pc, D, live, cid, cid_hi, mu, counts, seed, sweep, lane); break;
     }
 #undef MMQ_CLS1_CASE
   }
@@ -897,7 +880,7 @@ int mmq_cls_launch(mmq_handle* h, uint32_t seed, uint32_t sweep, const uint32_t*
 #define MMQ_CLS_ARGS(c0, c1) (int)(c0), (int)(c1), h->cls_pcol, h->cls_pk, h->cls_pcid, h->cls_cdesc, h->cls_cid_hi, h->mu, h->counts, seed, sweep, sweep_base
   auto launch_one = [&](cudaStream_t st) {
     const int64_t c0 = h->cls_chunks_gen, c1 = h->cls_chunks;
-    const int grid = (int)std::min<int64_t>((c1 - c0 + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, cap(4, 6));
+    const int grid = (int)std::min<int64_t>((c1 - c0 + MMQ_CLS_WARPS - 1) / MMQ_CLS_WARPS, cap(4, 9));
     k_alloc_cls1<<<grid, MMQ_CLS_WARPS * 32, 0, st>>>(MMQ_CLS_ARGS(c0, c1));
   };
   const bool one_first = h->tune[5] == 1; /* variant: the bulk kernel goes out first (on its own stream) */
