@@ -697,7 +697,7 @@ struct mmq_p2p_args {
 
 /* Debug / parity variant (mmq_sweep_debug): a full all-reduce — every rank reads the count vectors of
  * ALL ranks, draws every Gamma variate and keeps the summed counts.  One barrier. */
-__global__ void __launch_bounds__(MMQ_GAMMA_THREADS)
+__global__ void __launch_bounds__(MMQ_GAMMA_THREADS, 5)
 k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double* __restrict__ len,
             double* __restrict__ mu, double* __restrict__ trace, int stride, int trace_len, int64_t n,
             double alpha, double beta, uint32_t seed, uint32_t sweep, int32_t* __restrict__ counts_copy,
@@ -1472,7 +1472,7 @@ static int enqueue_sweep(mmq_handle* h, uint32_t seed, uint32_t sweep, int flags
        * (The Gamma kernel is bound by the latency of one pass, not by throughput, so drawing n / N variates instead of
        * n saves nothing, while the reduce-scatter variant below pays a second barrier and the peer stores: measured at
        * N = 2, 36 us against 24 us per sweep.) */
-      k_gamma_p2p<<<mmq_grid_for(h->n, MMQ_GAMMA_THREADS, h->num_sms * 4), MMQ_GAMMA_THREADS, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
+      k_gamma_p2p<<<mmq_grid_for(h->n, MMQ_GAMMA_THREADS, h->num_sms * 5), MMQ_GAMMA_THREADS, 0, h->stream>>>(a, h->seg_base, h->len, h->mu, stride > 0 ? h->trace : nullptr, stride,
                                                                                 h->trace_len, h->n, h->alpha, h->beta, seed, sweep, counts_copy, sweep_base);
       MMQ_LAUNCHED(h);
     } else { /* mmq_tune(h, 6, 1): reduce-scatter + Gamma + all-gather */
