@@ -163,3 +163,27 @@ def test_cli_batch_mode_equals_single_runs(tmp_path):
         for ext in (".mmseq", ".identical.mmseq", ".gene.mmseq", ".k", ".M"):
             assert open(base + ext).read() == open(str(tmp_path / f"batch{i}") + ext).read(), (i, ext)
         assert "Output files" not in open(str(tmp_path / f"batch{i}") + ".log").read() or True
+
+
+def test_config1_host_program_against_the_references_own_main(tmp_path):
+    """BASELINE config 1 (1k transcripts, 100k fragments, default flags) through BOTH programs: the reference's own
+    main() (oracle/_ref/mmseq_ref: src/mmseq.cpp + hitsio.cpp + uh.cpp + sokal.cc compiled unmodified against oracle/shim)
+    on the host cores and `mmseq` on the GPU.  .k / .M byte for byte; deterministic columns equal; log_mu of the observed
+    features within the two runs' combined Monte-Carlo standard error."""
+    from tests.test_reference_run import compare_with_reference
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "mmseq_ref")
+    if not os.path.exists(ref_bin):
+        pytest.skip("oracle/_ref/mmseq_ref not built (needs /root/reference at build time)")
+    path = str(tmp_path / "c1.hits")
+    synth.Synth(20260101 + 1, 1000, 100000).write_hits_fast(path, True)
+    env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
+    r = subprocess.run([ref_bin, path, str(tmp_path / "ref")], capture_output=True, text=True, timeout=1200, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([BIN, "-notraces", path, str(tmp_path / "ours")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for ext in (".k", ".M"):
+        assert open(str(tmp_path / "ref") + ext).read() == open(str(tmp_path / "ours") + ext).read(), ext
+    for ext, kind in ((".mmseq", "mmseq"), (".identical.mmseq", "identical"), (".gene.mmseq", "gene")):
+        z = compare_with_reference(tables.read_table(str(tmp_path / "ref") + ext), tables.read_table(str(tmp_path / "ours") + ext), kind,
+                                   z_max=6.0, frac=0.95)
+        assert len(z) > 100 or kind == "identical"
