@@ -334,13 +334,13 @@ def run_gates(args, H, w, mu0_gpu, mu_em_gpu, em_iters_gpu, rank, world, dev, al
         em_iters_gpu, _, _ = H.em(8, -1e300)
         mu_em_gpu = H.get_mu()
     mu = mu0_gpu.copy()
-    acc, ll = P.em_partial(mu)
+    acc, ll = P.em_partial(mu, threads)
     loglik = float(allreduce(np.array([ll]))[0]) - float((mu * w.length).sum())
     llr, it = 1.1, 0
     while it < (8 if bounded else 1000) and (bounded or llr > 0.1):
-        acc = allreduce(P.em_partial(mu)[0])
+        acc = allreduce(P.em_partial(mu, threads)[0])
         mu2 = mu * acc / w.length
-        ll2 = float(allreduce(np.array([P.em_partial(mu2)[1]]))[0]) - float((mu2 * w.length).sum())
+        ll2 = float(allreduce(np.array([P.em_partial(mu2, threads)[1]]))[0]) - float((mu2 * w.length).sum())
         llr, loglik, mu = ll2 - loglik, ll2, mu2
         it += 1
     pos = mu > 0   # transcripts whose classes all lost their mass stay at exactly 0 on both sides
@@ -406,15 +406,19 @@ def posterior_gate(args, H, w, mu_em, cpu_sweeps, threads):
     cpu_sps = Lc * S / t_cpu
     Lg = 256
     H.set_mu(mu_em)
-    H.gibbs(SEED, 0, burn + Lg * S, stride=S, trace_len=Lg + 1)
-    tr_g = H.get_trace()[:, 1:]   # slot 0 is sweep 0
+    H.gibbs(SEED + 7, 0, burn, stride=S, trace_len=0)         # burn-in (its own stream of sweeps)
+    H.gibbs(SEED, 0, Lg * S, stride=S, trace_len=Lg)          # slot j = the state after sweep 16 j
+    tr_g = H.get_trace()
     with np.errstate(divide="ignore"):
         lg, lc = np.log(tr_g), np.log(tr_c)
     sd = lg.std(axis=1, ddof=1)
-    # lag-1 autocorrelation of the GPU chain at this stride -> integrated autocorrelation time (AR(1) form), floor 1
+    # Monte-Carlo standard errors: the integrated autocorrelation time at this stride from the device's Sokal estimate on the
+    # GPU chain's log trace (mmq_summarize: src/mmseq.cpp:1308-1363, sokal.cc), floor 1; lag-1 AR(1) form where Sokal gives up
+    Sg = H.summarize(0)
     x = lg - lg.mean(axis=1, keepdims=True)
     rho = np.clip((x[:, 1:] * x[:, :-1]).sum(axis=1) / np.maximum((x * x).sum(axis=1), 1e-300), 0.0, 0.95)
-    tau = (1 + rho) / (1 - rho)
+    tau = np.where((Sg["status"] == 0) & np.isfinite(Sg["tau"]), np.maximum(Sg["tau"], 1.0), (1 + rho) / (1 - rho))
+    tau = np.maximum(tau, (1 + rho) / (1 - rho))
     se = sd * np.sqrt(tau) * np.sqrt(1.0 / Lg + 1.0 / Lc)
     diff = np.abs(lg.mean(axis=1) - lc.mean(axis=1))
     finite = np.isfinite(diff) & np.isfinite(se) & (se > 0)
@@ -696,14 +700,15 @@ def main():
     if not args.no_e2e:
         pin = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
         rp, col, kk, ww, ll, mu_h = pin(h.row_ptr), pin(h.col), pin(h.k), pin(h.w), pin(w.length), pin(mu_em)
+        mu_buf, tr_buf = pin(np.zeros(n)), pin(np.zeros((n, K)))   # pinned result buffers too
         barrier()
         t0 = time.perf_counter()
         H2 = capi.Handle(rp, col, kk, ll, weight=ww, class_id_base=w.cid_base, device=local)   # H2D of the CSR shard
         attach(H2, reuse_from=H)
         H2.set_mu(mu_h)                                                                        # H2D
         H2.gibbs(SEED, 0, K * S, stride=S, trace_len=K, flags=flags)
-        mu_out = H2.get_mu()                                                                   # D2H
-        tr = H2.get_trace()                                                                    # D2H, n x K doubles
+        mu_out = H2.get_mu(out=mu_buf)                                                         # D2H
+        tr = H2.get_trace(out=tr_buf)                                                          # D2H, n x K doubles
         barrier()
         wall = time.perf_counter() - t0
         tw = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -747,9 +752,10 @@ def main():
     roofline = {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": int(b_alloc), "avg_launch_ms": alloc_ms_avg, "launches_timed": int(alloc_n),
-                "share_of_sweep": alloc_ms_avg / per_sweep_ms if per_sweep_ms > 0 else None,
+                "share_of_sweep": alloc_ms_avg / (alloc_ms_avg + gamma_ms_avg) if alloc_n else None,
+                "alloc_ms_in_graph": per_sweep_ms - gamma_ms_avg,
                 "gamma_avg_launch_ms": gamma_ms_avg, "sweep_ms": per_sweep_ms,
-                "launch_gap_us_per_sweep": 1e3 * (per_sweep_ms - alloc_ms_avg - gamma_ms_avg),
+                "graph_vs_plain_us_per_sweep": 1e3 * (per_sweep_ms - alloc_ms_avg - gamma_ms_avg),
                 "sweep_bytes": int(b_sweep), "sweep_gbs": b_sweep / (per_sweep_ms * 1e-3) / 1e9,
                 "how": "value: K steps through mmq_gibbs (CUDA graph of 16 sweeps), CUDA events on the handle's stream; kernel "
                        "durations: the same K steps repeated with MMQ_GIBBS_TIME_KERNELS (events around every allocation / Gamma "

@@ -247,8 +247,8 @@ class Handle:
         assert mu.shape == (self.n,)
         self._check(lib().mmq_set_mu(self._h, _ptr(mu)), "mmq_set_mu")
 
-    def get_mu(self):
-        mu = np.zeros(self.n)
+    def get_mu(self, out=None):
+        mu = np.zeros(self.n) if out is None else out
         self._check(lib().mmq_get_mu(self._h, _ptr(mu)), "mmq_get_mu")
         return mu
 
@@ -297,8 +297,11 @@ class Handle:
     def trace_len(self):
         return int(lib().mmq_trace_len(self._h))
 
-    def get_trace(self):
-        out = np.zeros((self.n, self.trace_len()))
+    def get_trace(self, out=None):
+        """trace[t, slot]; `out`: a caller-provided (n, trace_len) float64 buffer (e.g. pinned memory)."""
+        if out is None:
+            out = np.zeros((self.n, self.trace_len()))
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.n * self.trace_len()
         self._check(lib().mmq_get_trace(self._h, _ptr(out)), "mmq_get_trace")
         return out
 

@@ -296,10 +296,13 @@ void orc_sweep_counts(int64_t m, int64_t n, const int64_t* rp, const int32_t* co
  * containing t of k_i w_it / D_i (classes in ascending row order, as orc_em), returns sum_i k_i log D_i.  The caller
  * (bench.py's EM gate) sums acc and the return value over shards and applies mu' = mu acc / l. */
 double orc_em_partial(int64_t m, int64_t n, const int64_t* rp, const int32_t* col, const int32_t* k, const float* w,
-                      const double* mu, double* acc) {
+                      const double* mu, double* acc, int threads) {
   std::vector<double> D((size_t)m);
   double ll = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : ll)
+#ifdef _OPENMP
+  if (threads <= 0) threads = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(static) reduction(+ : ll) num_threads(threads)
   for (int64_t i = 0; i < m; ++i) {
     D[(size_t)i] = row_dot(rp, col, w, mu, i);
     ll += (double)(k ? k[i] : 1) * std::log(D[(size_t)i]);

@@ -54,7 +54,7 @@ def lib():
         L.orc_gamma_replay.argtypes = [i64, vp, vp, dbl, dbl, u32, u32, vp]
         L.orc_sweep_counts.argtypes = [i64, i64, vp, vp, vp, vp, u32, u32, i64, vp, vp, vp, i32]
         L.orc_em_partial.restype = dbl
-        L.orc_em_partial.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp]
+        L.orc_em_partial.argtypes = [i64, i64, vp, vp, vp, vp, vp, vp, i32]
         L.orc_cls_plan_replay.restype = C.c_int
         L.orc_cls_plan_replay.argtypes = [i64, i64, vp, vp, vp, vp, i64, vp, u32, u32, vp, vp]
         L.orc_gibbs_replay.argtypes = [i64, i64, vp, vp, vp, vp, vp, dbl, dbl, u32, i64, i64, i32, i32, vp, vp]
@@ -207,10 +207,10 @@ class Problem:
                                _p(cid), _p(mu), _p(counts), threads)
         return counts
 
-    def em_partial(self, mu):
+    def em_partial(self, mu, threads=0):
         """This shard's part of one EM iteration: (acc[n], sum_i k_i log D_i)."""
         mu = _c(mu, np.float64); acc = np.zeros(self.n)
-        ll = lib().orc_em_partial(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(self.w), _p(mu), _p(acc))
+        ll = lib().orc_em_partial(self.m, self.n, _p(self.row_ptr), _p(self.col), _p(self.k), _p(self.w), _p(mu), _p(acc), threads)
         return acc, ll
 
     def gamma_replay(self, counts, seed, sweep):
