@@ -419,13 +419,17 @@ def posterior_gate(args, H, w, mu_em, cpu_sweeps, threads):
     rho = np.clip((x[:, 1:] * x[:, :-1]).sum(axis=1) / np.maximum((x * x).sum(axis=1), 1e-300), 0.0, 0.95)
     tau = np.where((Sg["status"] == 0) & np.isfinite(Sg["tau"]), np.maximum(Sg["tau"], 1.0), (1 + rho) / (1 - rho))
     tau = np.maximum(tau, (1 + rho) / (1 - rho))
-    se = sd * np.sqrt(tau) * np.sqrt(1.0 / Lg + 1.0 / Lc)
+    # the two chains are compared over the SAME window of sweeps (both start at the EM estimate: a chain that has not
+    # forgotten its start yet is biased the same way on both sides), the spread comes from the whole GPU chain
+    se = sd * np.sqrt(tau) * np.sqrt(2.0 / Lc)
+    lg = lg[:, 1:Lc + 1]   # GPU slot j: after sweep 16 j; CPU sample j: after 16 (j + 1) sweeps
     diff = np.abs(lg.mean(axis=1) - lc.mean(axis=1))
     finite = np.isfinite(diff) & np.isfinite(se) & (se > 0)
     frac = float((diff[finite] <= 4.0 * se[finite]).mean())
     sd_c = lc.std(axis=1, ddof=1) if Lc > 2 else None
     sd_ratio = float(np.median(sd_c[finite] / sd[finite])) if sd_c is not None else None
-    gate = {"chains": f"GPU {Lg} samples, CPU (GSL-like, {threads} threads) {Lc} samples, stride {S}, both from the EM estimate after {burn} sweeps",
+    gate = {"chains": f"GPU and CPU (GSL-like, {threads} threads) chains from the EM estimate, {burn} burn-in sweeps, the same {Lc} trace slots at stride {S} "
+                      f"compared; sd and autocorrelation time from {Lg} GPU slots",
             "frac_within_4se": frac, "need": 0.999, "median_sd_ratio_cpu_over_gpu": sd_ratio, "features": int(finite.sum()),
             "ok": bool(frac >= 0.999), "hard_fail_below": 0.99}
     base = {"value": cpu_sps * value_classes(args, w), "unit": "allocations/s", "sweeps_per_s": cpu_sps, "cores": threads, "kind": "port",
