@@ -233,6 +233,35 @@ int mmq_prior_draws(int device, int64_t count, const int64_t* ids, const double*
 int mmq_sokal_batch(int device, int64_t rows, int len, const double* x, double* var, double* tau,
                     int32_t* win, int32_t* status);
 
+/* ---- the consumer of the traces: mmcollapse's covariance step (src/mmcollapse.cpp:483-561) ----------
+ * The one dense contraction of the package: tensor cores (tcgen05, bf16 split products, fp32 accumulation in
+ * TMEM), everything around it fp64.  nsplit = bf16 terms per value: 1 (|dr| <~ 4e-3 in correlation units),
+ * 2 (<~ 2e-5, the default of the callers here), 3 (<~ 2e-6). */
+
+/* get_corrs()'s per-sample step, src/mmcollapse.cpp:553-558: R = cov(M) of the L x C trace matrix (column c =
+ * the L posterior draws of feature c, contiguous: Armadillo's layout of myM and the layout of mmq_get_trace),
+ * non-finite -> 0.  R: C x C fp64, both triangles, exactly symmetric, diagonal = the columns' variances.
+ * L a multiple of 64 (mmcollapse: TRACELEN 1024).  Host pointers; H2D, kernels and D2H inside. */
+int mmq_trace_cov(int device, const double* M, int L, int64_t C, int nsplit, double* R);
+/* Same on device-resident data, asynchronous on cuda_stream, no allocation inside: workspace_dev must hold
+ * mmq_trace_cov_workspace_bytes(L, C, nsplit) bytes (256-byte aligned). */
+int64_t mmq_trace_cov_workspace_bytes(int L, int64_t C, int nsplit);
+int mmq_trace_cov_dev(const double* M_dev, int L, int64_t C, int nsplit, double* R_dev, void* workspace_dev, void* cuda_stream);
+/* Straight from the trace a handle recorded (mmq_gibbs with trace_len = L): features[c] = index of an observed
+ * transcript; no trace file round trip (the reference re-reads *.trace_gibbs.gz, src/mmcollapse.cpp:530-551).
+ * R_out (host) and / or R_dev_out (device, C x C fp64) receive the matrix; either may be NULL. */
+int mmq_handle_trace_cov(mmq_handle* h, const int32_t* features, int64_t C, int nsplit, double* R_out, double* R_dev_out);
+
+/* mean_corrs(), src/mmcollapse.cpp:483-511.  R: C x C x ns cube (slice s at R + s C C, symmetric slices as
+ * mmq_trace_cov writes them), S: C x ns column-major, 1 where feature c was observed in sample s (:686-695);
+ * for every t in ts[0..nts) and v in 0..C-1: V(t,v) = V(v,t) = mean over the samples with S(t,s) S(v,s) = 1 of
+ * R(t,v,s)/sqrt(R(t,t,s))/sqrt(R(v,v,s)) + sdpenalty * W(t,v), W = their sd (0 for one sample or if not finite).
+ * V, W: C x C fp64, read and written (entries outside the rows / columns of ts stay). */
+int mmq_mean_corrs(int device, const double* R, const uint8_t* S, int64_t C, int ns, const int32_t* ts, int64_t nts, double sdpenalty,
+                   double* V, double* W);
+int mmq_mean_corrs_dev(const double* R_dev, const uint8_t* S_dev, int64_t C, int ns, const int32_t* ts_dev, int64_t nts, double sdpenalty,
+                       double* V_dev, double* W_dev, void* cuda_stream);
+
 /* Kernel launches issued by this process through the library so far. */
 int64_t mmq_launch_count(void);
 /* Bring up the CUDA context of `device` (the first CUDA call of a process costs 1-2 s): a host

@@ -76,6 +76,12 @@ def _load():
         "mmq_unique_hits_sets": (i32, [vp, vp, i64, vp]),
         "mmq_sokal_batch": (i32, [i32, i64, i32, vp, vp, vp, vp, vp]),
         "mmq_prior_draws": (i32, [i32, i64, vp, vp, dbl, u32, i32, vp]),
+        "mmq_trace_cov": (i32, [i32, vp, i32, i64, i32, vp]),
+        "mmq_trace_cov_workspace_bytes": (i64, [i32, i64, i32]),
+        "mmq_trace_cov_dev": (i32, [vp, i32, i64, i32, vp, vp, vp]),
+        "mmq_handle_trace_cov": (i32, [vp, vp, i64, i32, vp, vp]),
+        "mmq_mean_corrs": (i32, [i32, vp, vp, i64, i32, vp, i64, dbl, vp, vp]),
+        "mmq_mean_corrs_dev": (i32, [vp, vp, i64, i32, vp, i64, dbl, vp, vp, vp]),
         "mmq_launch_count": (i64, []),
         "mmq_warmup": (i32, [i32]),
         "mmq_version": (C.c_char_p, []),
@@ -102,7 +108,8 @@ EXPORTS = [
     "mmq_device_bytes", "mmq_comm_id", "mmq_comm_init", "mmq_comm_move", "mmq_p2p_export", "mmq_p2p_attach", "mmq_p2p_attach_local", "mmq_p2p_attached", "mmq_init_mu", "mmq_set_mu", "mmq_get_mu",
     "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_cls_stats", "mmq_rows_stats", "mmq_tune", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
-    "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_launch_count", "mmq_warmup", "mmq_version",
+    "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_trace_cov", "mmq_trace_cov_workspace_bytes", "mmq_trace_cov_dev",
+    "mmq_handle_trace_cov", "mmq_mean_corrs", "mmq_mean_corrs_dev", "mmq_launch_count", "mmq_warmup", "mmq_version",
 ]
 
 
@@ -142,6 +149,47 @@ def sokal_batch(x, device=0):
     if rc:
         raise MmqError("mmq_sokal_batch: " + lib().mmq_last_error(None).decode())
     return var, tau, win, status
+
+
+def _global_check(rc, what):
+    if rc:
+        raise MmqError(f"{what}: " + (lib().mmq_last_error(None) or b"").decode())
+
+
+def trace_cov(M, nsplit=2, device=0):
+    """mmq_trace_cov: cov() of the L x C trace matrix M[s, c] (src/mmcollapse.cpp:553-558).  Returns C x C."""
+    M = np.asarray(M, np.float64)
+    L, Cn = M.shape
+    Mf = np.asfortranarray(M)                      # column c contiguous (Armadillo's layout)
+    R = np.zeros((Cn, Cn), np.float64, order="F")
+    _global_check(lib().mmq_trace_cov(device, Mf.ctypes.data_as(C.c_void_p), L, Cn, nsplit, R.ctypes.data_as(C.c_void_p)), "mmq_trace_cov")
+    return R
+
+
+def trace_cov_workspace_bytes(L, Cn, nsplit=2):
+    return int(lib().mmq_trace_cov_workspace_bytes(L, Cn, nsplit))
+
+
+def trace_cov_dev(M_ptr, L, Cn, nsplit, R_ptr, ws_ptr, stream_ptr):
+    """Device pointers (ints); asynchronous on the stream."""
+    _global_check(lib().mmq_trace_cov_dev(M_ptr, L, Cn, nsplit, R_ptr, ws_ptr, stream_ptr), "mmq_trace_cov_dev")
+
+
+def mean_corrs(R, S, ts, sdpenalty=0.0, V=None, W=None, device=0):
+    """mmq_mean_corrs (src/mmcollapse.cpp:483-511).  R: (ns, C, C) symmetric slices, S: (C, ns) 0/1."""
+    R = np.ascontiguousarray(R, np.float64)
+    ns, Cn, _ = R.shape
+    Sf = np.asfortranarray(np.asarray(S, np.uint8))
+    ts = _c(ts, np.int32)
+    V = np.zeros((Cn, Cn), np.float64, order="F") if V is None else np.asfortranarray(V, np.float64)
+    W = np.zeros((Cn, Cn), np.float64, order="F") if W is None else np.asfortranarray(W, np.float64)
+    _global_check(lib().mmq_mean_corrs(device, _ptr(R), Sf.ctypes.data_as(C.c_void_p), Cn, ns, _ptr(ts), len(ts), float(sdpenalty),
+                                       V.ctypes.data_as(C.c_void_p), W.ctypes.data_as(C.c_void_p)), "mmq_mean_corrs")
+    return V, W
+
+
+def mean_corrs_dev(R_ptr, S_ptr, Cn, ns, ts_ptr, nts, sdpenalty, V_ptr, W_ptr, stream_ptr):
+    _global_check(lib().mmq_mean_corrs_dev(R_ptr, S_ptr, Cn, ns, ts_ptr, nts, float(sdpenalty), V_ptr, W_ptr, stream_ptr), "mmq_mean_corrs_dev")
 
 
 def prior_draws(ids, rate, alpha, seed, trace_len, device=0):
@@ -304,6 +352,14 @@ class Handle:
         assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == self.n * self.trace_len()
         self._check(lib().mmq_get_trace(self._h, _ptr(out)), "mmq_get_trace")
         return out
+
+    def trace_cov(self, features, nsplit=2):
+        """mmq_handle_trace_cov: covariance of the recorded traces of the given observed transcripts (C x C)."""
+        features = _c(features, np.int32)
+        Cn = len(features)
+        R = np.zeros((Cn, Cn), np.float64, order="F")
+        self._check(lib().mmq_handle_trace_cov(self._h, _ptr(features), Cn, nsplit, R.ctypes.data_as(C.c_void_p), None), "mmq_handle_trace_cov")
+        return R
 
     def set_groups(self, kind, group_ptr, members, extra=None):
         group_ptr = _c(group_ptr, np.int64); members = _c(members, np.int32); extra = _c(extra, np.float64)

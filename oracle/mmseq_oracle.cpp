@@ -533,3 +533,75 @@ int orc_cls_plan_replay(int64_t m, int64_t n, const int64_t* rp, const int32_t* 
 }
 
 } /* extern "C" */
+
+/* ---- mmcollapse's trace covariance and mean-correlation scan ----------------------
+ * PARITY STATUS of this part: src/mmcollapse.cpp needs Armadillo (absent from the image, no BLAS/LAPACK either), so
+ * the reference's own code for it cannot be compiled here and it ships no fixtures: the two functions below restate
+ *   orc_cov          get_corrs(), src/mmcollapse.cpp:514-561: R.slice(s) = cov(myM) of the 1024 x C trace matrix
+ *                    (Armadillo's cov(): columns centred on their means, X^T X / (rows - 1)), non-finite entries
+ *                    set to 0 (:556-558);
+ *   orc_mean_corrs   mean_corrs(), src/mmcollapse.cpp:483-511: mean and sd over the samples (slices) of the
+ *                    correlation of a pair, only over the samples in which both features were observed.
+ * tests/test_oracle_collapse.py pins orc_cov on numpy.cov (an independent implementation of the same definition)
+ * and orc_mean_corrs on a numpy transcription of :483-511. */
+extern "C" {
+
+/* M: L x C column-major (column c = the trace of feature c, as arma::mat stores it); R: C x C column-major. */
+void orc_cov(const double* M, int L, int64_t C, double* R) {
+  std::vector<double> X((size_t)L * (size_t)C);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < C; ++c) {
+    const double* x = M + (size_t)c * L;
+    double s = 0.0;
+    for (int i = 0; i < L; ++i) s += x[i];
+    const double mean = s / L;
+    for (int i = 0; i < L; ++i) X[(size_t)c * L + i] = x[i] - mean;
+  }
+  const double norm = L > 1 ? (double)(L - 1) : 1.0;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int64_t a = 0; a < C; ++a) {
+    const double* xa = X.data() + (size_t)a * L;
+    for (int64_t b = a; b < C; ++b) {
+      const double* xb = X.data() + (size_t)b * L;
+      double s = 0.0;
+      for (int i = 0; i < L; ++i) s += xa[i] * xb[i];
+      double v = s / norm;
+      if (!std::isfinite(v)) v = 0.0; /* :556-558 */
+      R[(size_t)a + (size_t)C * (size_t)b] = v;
+      R[(size_t)b + (size_t)C * (size_t)a] = v;
+    }
+  }
+}
+
+/* R: C x C x ns cube (slice s at R + s*C*C), S: C x ns column-major 0/1 (observed in sample s), ts: rows to refresh.
+ * V, W: C x C column-major, updated at (t, v) and (v, t) for t in ts, v in 0..C-1. */
+void orc_mean_corrs(const double* R, const uint8_t* S, int64_t C, int ns, const int32_t* ts, int64_t nts, double sdpenalty,
+                    double* V, double* W) {
+  const size_t CC = (size_t)C * (size_t)C;
+#pragma omp parallel for schedule(static)
+  for (int64_t q = 0; q < nts; ++q) {
+    const int64_t t = ts[q];
+    for (int64_t v = 0; v < C; ++v) {
+      double su = 0.0, sr = 0.0, sr2 = 0.0;
+      for (int s = 0; s < ns; ++s) {
+        const double* Rs = R + (size_t)s * CC;
+        double r = Rs[(size_t)t + (size_t)C * (size_t)v];
+        r = r / std::sqrt(Rs[(size_t)t + (size_t)C * (size_t)t]);
+        r = r / std::sqrt(Rs[(size_t)v + (size_t)C * (size_t)v]);
+        const double u = (double)(S[(size_t)t + (size_t)C * s] * S[(size_t)v + (size_t)C * s]);
+        if (u == 0.0) r = 0.0; /* :493-497 */
+        su += u; sr += u * r; sr2 += u * (r * r);
+      }
+      double mean = sr / su, sd = 0.0;
+      if (ns > 1) {
+        sd = std::sqrt((su / (su - 1.0)) * (sr2 / su - mean * mean));
+        if (!std::isfinite(sd)) sd = 0.0;
+      }
+      mean = mean + sdpenalty * sd;
+      V[(size_t)t + (size_t)C * (size_t)v] = V[(size_t)v + (size_t)C * (size_t)t] = mean;
+      W[(size_t)t + (size_t)C * (size_t)v] = W[(size_t)v + (size_t)C * (size_t)t] = sd;
+    }
+  }
+}
+
+} /* extern "C" */

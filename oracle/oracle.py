@@ -68,6 +68,8 @@ def lib():
         L.orc_sokal.restype = i32
         L.orc_sokal.argtypes = [i32, vp, vp, vp, vp]
         L.orc_uh_literal.argtypes = [i64, vp, vp, vp, i64, vp, vp, vp]
+        L.orc_cov.argtypes = [vp, i32, i64, vp]
+        L.orc_mean_corrs.argtypes = [vp, vp, i64, i32, vp, i64, dbl, vp, vp]
         _lib = L
     return _lib
 
@@ -265,6 +267,30 @@ def uh_literal(row_ptr, col, k, set_ptr, set_members):
     sp = _c(set_ptr, np.int64); sm = _c(set_members, np.int32); out = np.zeros(len(sp) - 1, np.int32)
     lib().orc_uh_literal(len(rp) - 1, _p(rp), _p(col), _p(k), len(sp) - 1, _p(sp), _p(sm), _p(out))
     return out
+
+
+def trace_cov(M):
+    """get_corrs()'s per-sample step, src/mmcollapse.cpp:553-558: cov() of the L x C trace matrix M[i, c] (non-finite -> 0).
+    Returns the C x C matrix (symmetric)."""
+    M = np.asarray(M, np.float64)
+    L, Cn = M.shape
+    Mf = np.asfortranarray(M)                       # column c contiguous, as arma::mat
+    R = np.zeros((Cn, Cn), np.float64, order="F")
+    lib().orc_cov(Mf.ctypes.data_as(vp), L, Cn, R.ctypes.data_as(vp))
+    return R
+
+
+def mean_corrs(R, S, ts, sdpenalty=0.0, V=None, W=None):
+    """mean_corrs(), src/mmcollapse.cpp:483-511.  R: (ns, C, C) covariance slices, S: (C, ns) 0/1, ts: rows to refresh.
+    Returns (V, W), C x C (entries outside the rows / columns of ts keep what was passed in, zeros by default)."""
+    R = np.ascontiguousarray(R, np.float64)          # symmetric slices: row- and column-major coincide
+    ns, Cn, _ = R.shape
+    Sf = np.asfortranarray(np.asarray(S, np.uint8))
+    ts = _c(ts, np.int32)
+    V = np.zeros((Cn, Cn), np.float64, order="F") if V is None else np.asfortranarray(V, np.float64)
+    W = np.zeros((Cn, Cn), np.float64, order="F") if W is None else np.asfortranarray(W, np.float64)
+    lib().orc_mean_corrs(_p(R), Sf.ctypes.data_as(vp), Cn, ns, _p(ts), len(ts), float(sdpenalty), V.ctypes.data_as(vp), W.ctypes.data_as(vp))
+    return V, W
 
 
 # ------------------------------------------------- hits reader (pure Python)
