@@ -72,6 +72,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gates", action="store_true")
+    ap.add_argument("--cov-features", type=int, default=16384, help="features (columns) of the trace-covariance extra (mmcollapse candidates of one sample)")
     ap.add_argument("--no-extras", action="store_true", help="skip the extra lines (weighted per-fragment stream of the same sample)")
     ap.add_argument("--gate-sweeps", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0, help="config 5: this many independent C2-sized samples (own synthetic fragments, own chain) dealt to "
@@ -510,6 +511,81 @@ def extra_weighted_line(args, dev, stream, peak):
                          "frac": b_alloc / (a * 1e-3) / 1e9 / peak}, "plan": rows}
 
 
+def extra_trace_cov(args, dev, stream):
+    """SURVEY.md section 8 row f3 (src/mmcollapse.cpp:553-558): cov() of one sample's 1024 x C trace matrix on the tensor
+    cores (mmq_trace_cov_dev), device-timed on device-resident traces, with its own roofline (bound: tensor), a gate against
+    the oracle on a sub-block, the end-to-end time through the host-pointer entry point and the oracle timed beside it."""
+    import torch
+    from mmseq_b200 import capi
+    from oracle import oracle as orc
+    L, C, nsplit = 1024, args.cov_features, 2
+    g = torch.Generator(device=dev); g.manual_seed(20260107)
+    # posterior-trace-like columns: log-normal levels over orders of magnitude, neighbouring features anti-correlated
+    base = torch.randn((C // 2, L), dtype=torch.float64, device=dev, generator=g)
+    noise = torch.randn((C, L), dtype=torch.float64, device=dev, generator=g)
+    level = torch.exp(3.0 * torch.randn((C, 1), dtype=torch.float64, device=dev, generator=g))
+    sign = torch.tensor([1.0, -1.0], dtype=torch.float64, device=dev).repeat(C // 2).view(C, 1)
+    Md = level * torch.exp(0.3 * (sign * base.repeat_interleave(2, dim=0) + 0.5 * noise))     # [C][L]: column c of the L x C matrix
+    del base, noise
+    Rd = torch.empty((C, C), dtype=torch.float64, device=dev)
+    ws = torch.empty(capi.trace_cov_workspace_bytes(L, C, nsplit), dtype=torch.uint8, device=dev)
+    K, W = 10, 3
+    with torch.cuda.stream(stream):
+        for _ in range(W):
+            capi.trace_cov_dev(Md.data_ptr(), L, C, nsplit, Rd.data_ptr(), ws.data_ptr(), stream.cuda_stream)
+        stream.synchronize()
+        l0 = capi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(K):   # 2.1 GB of output per launch: far larger than the L2
+            capi.trace_cov_dev(Md.data_ptr(), L, C, nsplit, Rd.data_ptr(), ws.data_ptr(), stream.cuda_stream)
+        e1.record(stream)
+        stream.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    launches = capi.launch_count() - l0
+    nterms = nsplit * (nsplit + 1) // 2
+    flops = float(C) * (C + 1) * L * nterms         # the upper triangle, one multiply-add per split product
+    out_bytes = float(C) * C * 8
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tpeak = float(peaks.get("bf16_tflops", 1590.0))
+    # gate: a 1024 x 1024 corner against the oracle, in correlation units
+    nsub = min(C, 1024)
+    sub = Rd[:nsub, :nsub].cpu().numpy()
+    ref = orc.trace_cov(Md[:nsub].cpu().numpy().T)
+    d = np.sqrt(np.diag(ref))
+    err = float(np.max(np.abs(sub - ref) / (d[:, None] * d[None, :])))
+    sym = bool(torch.equal(Rd[:2048, :2048], Rd[:2048, :2048].T))
+    # CPU beside it: the oracle on a bounded sample of the same matrix
+    ccpu = min(C, 3072)
+    Mh = Md[:ccpu].cpu().numpy().T.copy()
+    t0 = time.perf_counter()
+    orc.trace_cov(Mh)
+    cpu_s = time.perf_counter() - t0
+    cpu_full_s = cpu_s * (float(C) * (C + 1)) / (float(ccpu) * (ccpu + 1))
+    # end to end: host matrix in, host matrix out (pageable R: 2.1 GB over PCIe dominates)
+    Mhost = np.asfortranarray(Md.cpu().numpy().T)
+    del Md, Rd, ws
+    torch.cuda.empty_cache()
+    t0 = time.perf_counter()
+    Rh = capi.trace_cov(Mhost, nsplit=nsplit, device=dev.index)
+    e2e_s = time.perf_counter() - t0
+    return {"workload": f"cov() of a {L} x {C} trace matrix (src/mmcollapse.cpp:553-558), split-bf16 x {nsplit} products, fp32 accumulation, fp64 output",
+            "kernel": "k_cov_gemm (tcgen05.mma + TMA + TMEM, persistent, 128 x 256 tiles of the upper triangle) + k_cov_prep",
+            "ms": ms, "matrices_per_s": 1e3 / ms, "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
+                         "frac": flops / (ms * 1e-3) / 1e12 / tpeak, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback",
+                         "algorithmic_flops_per_launch": flops, "output_gbs": out_bytes / (ms * 1e-3) / 1e9,
+                         "note": "operand tiles come from the L2 (Z = 67 MB): 48 KB per 4.2 MFLOP stage puts the L2 cap near 1.05 PFLOP/s; 2.1 GB of fp64 output per launch"},
+            "gate": {"max_corr_err_vs_oracle": err, "tol": 3e-5, "exactly_symmetric": sym, "ok": bool(err < 3e-5 and sym)},
+            "e2e": {"seconds": e2e_s, "matrices_per_s": 1.0 / e2e_s, "h2d_bytes": int(Mhost.nbytes), "d2h_bytes": int(Rh.nbytes)},
+            "cpu_baseline": {"seconds_full_matrix": cpu_full_s, "matrices_per_s": 1.0 / cpu_full_s, "cores": host_threads(), "kind": "port",
+                             "sample": f"orc_cov (fp64, OpenMP) on the first {ccpu} features, scaled by the pair count"}}
+
+
 def run_batch(args, rank, world, local):
     """BASELINE config 5: a batch of independent samples, no collective.  Every rank takes the samples rank, rank + N, ...;
     a producer thread makes the next samples' hit classes (synthetic fragments + the loader's class construction) while
@@ -822,6 +898,15 @@ def main():
             line["perfragment_weighted"] = extra_weighted_line(args, dev, stream, peak)
         except Exception as e:   # an extra: never at the expense of the headline line
             line["perfragment_weighted"] = {"error": repr(e)}
+
+    # ---- the consumer of the traces: mmcollapse's covariance step on the tensor cores (row f3), N = 1 default run only
+    if rank == 0 and world == 1 and args.layout == "collapsed" and not args.no_extras and not args.haplo and args.scaling == "weak":
+        try:
+            line["trace_cov"] = extra_trace_cov(args, dev, stream)
+            if not line["trace_cov"]["gate"]["ok"]:
+                gates_ok = False
+        except Exception as e:
+            line["trace_cov"] = {"error": repr(e)}
 
     if rank == 0:
         print(json.dumps(line), flush=True)

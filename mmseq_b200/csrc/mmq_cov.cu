@@ -30,6 +30,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 
@@ -38,14 +39,16 @@
 
 namespace {
 
-constexpr int COV_BM = 128, COV_BN = 128, COV_BK = 64; /* tile: 128 x 128 outputs, 64 bf16 (= one 128-byte swizzle row) of K per stage */
+constexpr int COV_BM = 128, COV_BN = 256, COV_BK = 64; /* tile: 128 x 256 outputs (UMMA M = 128, N = 256), 64 bf16 (= one 128-byte swizzle row) of K per stage */
 constexpr int COV_STAGES = 3;
 constexpr int COV_UMMA_K = 16;
 constexpr int COV_A_BYTES = COV_BM * COV_BK * 2, COV_B_BYTES = COV_BN * COV_BK * 2;
 constexpr int COV_STAGE_BYTES = COV_A_BYTES + COV_B_BYTES;
-constexpr int COV_TMEM_COLS = 128;
-constexpr int COV_THREADS = 192; /* warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue */
-constexpr int COV_SMEM = COV_STAGES * COV_STAGE_BYTES + 256 /* barriers, TMEM slot */ + 2 * 128 * 8 /* sd of the two tiles */ + 1024 /* alignment */;
+constexpr int COV_TMEM_COLS = 2 * COV_BN; /* two fp32 accumulators of COV_BN columns: all 512 columns, one CTA per SM */
+constexpr int COV_THREADS = 320; /* warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..9: epilogue (two per TMEM lane quarter) */
+constexpr int COV_EPI_WARPS = 8;
+constexpr int COV_EPI_BYTES = (33 * 32 + 32) * 8; /* per epilogue warp: 33 x 32 transposition buffer + sd of 32 columns */
+constexpr int COV_SMEM = COV_STAGES * COV_STAGE_BYTES + COV_EPI_WARPS * COV_EPI_BYTES + 256 /* barriers, TMEM slot */ + 1024 /* alignment */;
 
 /* ---- small PTX wrappers (tcgen05 / TMA tensor copies; the mbarrier basics are in mmq_device.cuh) ---- */
 __device__ __forceinline__ void mbar_wait_trap(uint64_t* b, uint32_t parity) {
@@ -148,38 +151,42 @@ __global__ void __launch_bounds__(256) k_cov_prep(const double* __restrict__ src
 }
 
 /* ---- k_cov_gemm ---- */
-__global__ void __launch_bounds__(COV_THREADS, 2)
-    k_cov_gemm(const __grid_constant__ CUtensorMap zmap, const double* __restrict__ sd, double* __restrict__ R, int64_t C, int L, int nsplit) {
+__device__ __forceinline__ void cov_tile_of(int64_t t, int64_t& mb, int64_t& nb) {
+  /* tiles that hold an element on or above the diagonal: column block nb (256 wide) pairs with the row blocks mb <= 2 nb + 1 (128 high);
+   * linear index nb (nb + 1) + mb */
+  nb = (int64_t)((sqrt(4.0 * (double)t + 1.0) - 1.0) * 0.5);
+  while (nb * (nb + 1) > t) --nb;
+  while ((nb + 1) * (nb + 2) <= t) ++nb;
+  mb = t - nb * (nb + 1);
+}
+
+/* Persistent: one CTA per SM walks the tiles blockIdx.x, + gridDim.x, ...  Three pipelines: the shared-memory ring
+ * (TMA producer <-> MMA issuer), two TMEM accumulators (MMA issuer <-> epilogue: the epilogue of tile n drains one
+ * while the MMAs of tile n + 1 fill the other), and the tile walk itself. */
+__global__ void __launch_bounds__(COV_THREADS, 1)
+    k_cov_gemm(const __grid_constant__ CUtensorMap zmap, const double* __restrict__ sd, double* __restrict__ R, int64_t C, int L, int nsplit,
+               int64_t tiles) {
   extern __shared__ uint8_t cov_smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)cov_smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full = (uint64_t*)(smem + COV_STAGES * COV_STAGE_BYTES);
+  uint8_t* smem = cov_smem_raw + ((1024u - (smem_u32(cov_smem_raw) & 1023u)) & 1023u); /* 1024-byte aligned (128-byte swizzle), still provably shared */
+  uint8_t* epi = smem + COV_STAGES * COV_STAGE_BYTES;
+  uint64_t* full = (uint64_t*)(epi + COV_EPI_WARPS * COV_EPI_BYTES);
   uint64_t* empty = full + COV_STAGES;
-  uint64_t* tfull = empty + COV_STAGES;
-  uint32_t* tmem_slot = (uint32_t*)(tfull + 1);
-  double* sd_a = (double*)(smem + COV_STAGES * COV_STAGE_BYTES + 256);
-  double* sd_b = sd_a + 128;
+  uint64_t* tfull = empty + COV_STAGES; /* [2] accumulator b complete */
+  uint64_t* tempty = tfull + 2;         /* [2] accumulator b drained by all epilogue warps */
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  /* tile (mb, nb) with mb <= nb from the linear index: nb(nb+1)/2 + mb */
-  const int64_t t = blockIdx.x;
-  int64_t nb = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
-  while (nb * (nb + 1) / 2 > t) --nb;
-  while ((nb + 1) * (nb + 2) / 2 <= t) ++nb;
-  const int64_t mb = t - nb * (nb + 1) / 2;
-  const int row_a = (int)(mb * COV_BM), row_b = (int)(nb * COV_BN);
-
-  for (int i = threadIdx.x; i < 256; i += COV_THREADS) {
-    const int64_t g = (i < 128 ? row_a : row_b - 128) + i;
-    sd_a[i] = g < C ? sd[g] : 0.0; /* sd_b = sd_a + 128 */
-  }
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
     for (int s = 0; s < COV_STAGES; ++s) {
       mbar_init(full + s, 1);
       mbar_init(empty + s, 1);
     }
-    mbar_init(tfull, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, COV_EPI_WARPS);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -192,85 +199,135 @@ __global__ void __launch_bounds__(COV_THREADS, 2)
   const uint32_t tmem = *tmem_slot;
 
   const int kb_per_seg = L / COV_BK;
-  const int nseg = nsplit * (nsplit + 1) / 2;
-  const int iters = nseg * kb_per_seg;
+  const int iters = (nsplit * (nsplit + 1) / 2) * kb_per_seg;
 
   if (warp == 0) {
     if (lane == 0) {
-      /* segments (a, b), a + b < nsplit, smallest products first: total order a + b descending */
       int it = 0;
-      for (int sum = nsplit - 1; sum >= 0; --sum)
-        for (int a = 0; a <= sum; ++a) {
-          const int b = sum - a;
-          for (int kb = 0; kb < kb_per_seg; ++kb, ++it) {
-            const int stage = it % COV_STAGES;
-            const uint32_t phase = (uint32_t)(it / COV_STAGES) & 1u;
-            mbar_wait_trap(empty + stage, phase ^ 1u);
-            uint8_t* dst = smem + stage * COV_STAGE_BYTES;
-            mbar_expect_tx(full + stage, COV_STAGE_BYTES);
-            tma_load_2d(dst, &zmap, a * L + kb * COV_BK, row_a, full + stage);
-            tma_load_2d(dst + COV_A_BYTES, &zmap, b * L + kb * COV_BK, row_b, full + stage);
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        int64_t mb, nb;
+        cov_tile_of(t, mb, nb);
+        const int row_a = (int)(mb * COV_BM), row_b = (int)(nb * COV_BN);
+        if (row_a >= C) continue; /* the last column block may have one row block less */
+        /* segments (a, b), a + b < nsplit, smallest products first: a + b descending */
+        for (int sum = nsplit - 1; sum >= 0; --sum)
+          for (int a = 0; a <= sum; ++a) {
+            const int b = sum - a;
+            for (int kb = 0; kb < kb_per_seg; ++kb, ++it) {
+              const int stage = it % COV_STAGES;
+              const uint32_t phase = (uint32_t)(it / COV_STAGES) & 1u;
+              mbar_wait_trap(empty + stage, phase ^ 1u);
+              uint8_t* dst = smem + stage * COV_STAGE_BYTES;
+              mbar_expect_tx(full + stage, COV_STAGE_BYTES);
+              tma_load_2d(dst, &zmap, a * L + kb * COV_BK, row_a, full + stage);
+              tma_load_2d(dst + COV_A_BYTES, &zmap, b * L + kb * COV_BK, row_b, full + stage); /* two boxes of 128 rows: contiguous 8-row groups */
+              tma_load_2d(dst + COV_A_BYTES + COV_B_BYTES / 2, &zmap, b * L + kb * COV_BK, row_b + 128, full + stage);
+            }
           }
-        }
+      }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      for (int it = 0; it < iters; ++it) {
-        const int stage = it % COV_STAGES;
-        const uint32_t phase = (uint32_t)(it / COV_STAGES) & 1u;
-        mbar_wait_trap(full + stage, phase);
+      int it = 0, n = 0;
+      for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        int64_t mb, nb;
+        cov_tile_of(t, mb, nb);
+        if (mb * COV_BM >= C) continue;
+        const int buf = n & 1;
+        mbar_wait_trap(tempty + buf, ((uint32_t)(n >> 1) & 1u) ^ 1u); /* the epilogue has drained this accumulator (tile n - 2) */
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + stage * COV_STAGE_BYTES), b0 = a0 + COV_A_BYTES;
+        const uint32_t acc = tmem + (uint32_t)(buf * COV_BN);
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int stage = it % COV_STAGES;
+          const uint32_t phase = (uint32_t)(it / COV_STAGES) & 1u;
+          mbar_wait_trap(full + stage, phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + stage * COV_STAGE_BYTES), b0 = a0 + COV_A_BYTES;
 #pragma unroll
-        for (int k = 0; k < COV_BK / COV_UMMA_K; ++k) {
-          /* 16 bf16 = 32 bytes further along K inside the 128-byte swizzle row */
-          tc_mma_bf16(tmem, smem_desc_sw128(a0 + k * COV_UMMA_K * 2), smem_desc_sw128(b0 + k * COV_UMMA_K * 2), COV_IDESC, (uint32_t)((it | k) != 0));
+          for (int k = 0; k < COV_BK / COV_UMMA_K; ++k) {
+            /* 16 bf16 = 32 bytes further along K inside the 128-byte swizzle row */
+            tc_mma_bf16(acc, smem_desc_sw128(a0 + k * COV_UMMA_K * 2), smem_desc_sw128(b0 + k * COV_UMMA_K * 2), COV_IDESC, (uint32_t)((i | k) != 0));
+          }
+          tc_commit(empty + stage); /* the stage is free once these MMAs have read it */
         }
-        tc_commit(empty + stage); /* the stage is free once these MMAs have read it */
+        tc_commit(tfull + buf); /* accumulator complete */
+        ++n;
       }
-      tc_commit(tfull); /* accumulator complete */
     }
     __syncwarp();
   } else {
-    /* epilogue: warp w may read the TMEM lanes 32 (w % 4) .. +31 = rows of the tile */
-    const int q = warp & 3;
+    /* epilogue: warp w may read the TMEM lanes 32 (w % 4) .. +31 = rows of the tile; the two warps of a lane quarter split the columns */
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const int64_t gi = (int64_t)row_a + row;
-    mbar_wait_trap(tfull, 0);
-    tc_fence_after();
-    const double si = sd_a[row];
-    const bool diag_tile = mb == nb;
-    /* all MMAs have completed, so every pipeline stage is free: the epilogue transposes through it (33 x 32 doubles per warp)
-     * so that the stores of BOTH triangles are coalesced */
-    double* tp = (double*)(smem + (warp - 2) * (33 * 32 * 8));
-    const int64_t gi0 = (int64_t)row_a + q * 32;
-    for (int c0 = 0; c0 < COV_BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      const int64_t gj0 = (int64_t)row_b + c0;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int64_t gj = gj0 + j;
-        const double val = gi == gj ? si * si : (double)__uint_as_float(v[j]) * (si * sd_b[c0 + j]);
-        tp[j * 33 + lane] = val;
-        /* upper triangle (and the diagonal): consecutive lanes = consecutive rows of column gj */
-        if (gi < C && gj < C && !(diag_tile && gj < gi)) __stcs(R + gi + C * gj, val);
-      }
-      __syncwarp();
-      /* mirror: element (row ii, column lane) of the chunk goes to R[gj + C gi]: consecutive lanes = consecutive gj */
-      const int64_t gj = gj0 + lane;
-      if (gj < C) {
-#pragma unroll 8
-        for (int ii = 0; ii < 32; ++ii) {
-          const int64_t gr = gi0 + ii;
-          if (gr >= C) break;
-          if (diag_tile ? gj > gr : true) __stcs(R + gj + C * gr, tp[lane * 33 + ii]);
+    double* tp = (double*)(epi + (warp - 2) * COV_EPI_BYTES); /* 33 x 32 transposition buffer: the stores of BOTH triangles are coalesced */
+    double* sdw = tp + 33 * 32;                               /* sd of the chunk's 32 columns */
+    int n = 0;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+      int64_t mb, nb;
+      cov_tile_of(t, mb, nb);
+      const int64_t row_a = mb * COV_BM, row_b = nb * COV_BN;
+      if (row_a >= C) continue;
+      const int64_t gi = row_a + row, gi0 = row_a + q * 32;
+      const double si = gi < C ? sd[gi] : 0.0;
+      const bool diag_tile = (mb >> 1) == nb; /* holds elements below the diagonal */
+      const bool edge = diag_tile || row_a + COV_BM > C || row_b + COV_BN > C;
+      const int buf = n & 1;
+      mbar_wait_trap(tfull + buf, (uint32_t)(n >> 1) & 1u);
+      tc_fence_after();
+      for (int c0 = half * (COV_BN / 2); c0 < (half + 1) * (COV_BN / 2); c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * COV_BN + c0), v);
+        if (c0 + 32 == (half + 1) * (COV_BN / 2)) {
+          /* this warp's last read of the accumulator: hand it back to the MMA issuer */
+          tc_fence_before();
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty + buf)) : "memory");
         }
+        const int64_t gj0 = row_b + c0;
+        sdw[lane] = gj0 + lane < C ? sd[gj0 + lane] : 0.0;
+        __syncwarp();
+        if (!edge) {
+          /* interior tile: no bounds, no diagonal */
+          double* dp = R + gi + C * gj0; /* column gj0 + j, consecutive lanes = consecutive rows */
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const double val = (double)__uint_as_float(v[j]) * (si * sdw[j]);
+            tp[j * 33 + lane] = val;
+            __stcs(dp, val);
+            dp += C;
+          }
+          __syncwarp();
+          double* mp = R + gj0 + lane + C * gi0; /* mirror: row gj0 + lane of column gi0 + ii */
+#pragma unroll
+          for (int ii = 0; ii < 32; ++ii) {
+            __stcs(mp, tp[lane * 33 + ii]);
+            mp += C;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t gj = gj0 + j;
+            const double val = gi == gj ? si * si : (double)__uint_as_float(v[j]) * (si * sdw[j]);
+            tp[j * 33 + lane] = val;
+            /* upper triangle and the diagonal of a diagonal tile; its lower triangle comes from the mirror: exactly symmetric */
+            if (gi < C && gj < C && !(diag_tile && gj < gi)) __stcs(R + gi + C * gj, val);
+          }
+          __syncwarp();
+          const int64_t gj = gj0 + lane;
+          if (gj < C) {
+#pragma unroll 8
+            for (int ii = 0; ii < 32; ++ii) {
+              const int64_t gr = gi0 + ii;
+              if (gr >= C) break;
+              if (diag_tile ? gj > gr : true) __stcs(R + gj + C * gr, tp[lane * 33 + ii]);
+            }
+          }
+        }
+        __syncwarp();
       }
-      __syncwarp();
+      ++n;
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -368,14 +425,17 @@ int cov_run(const double* src_dev, const int64_t* off_dev, int64_t off_step, int
   CUtensorMap map;
   const cuuint64_t dims[2] = {(cuuint64_t)nsplit * (cuuint64_t)L, (cuuint64_t)C};
   const cuuint64_t strides[1] = {(cuuint64_t)nsplit * (cuuint64_t)L * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)COV_BK, (cuuint32_t)COV_BM};
+  const cuuint32_t box[2] = {(cuuint32_t)COV_BK, 128u};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult cr = enc(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)Z, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return cov_fail(MMQ_ERR_CUDA, "mmq_trace_cov: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
-  const int64_t T = (C + COV_BM - 1) / COV_BM;
-  const int64_t tiles = T * (T + 1) / 2;
-  k_cov_gemm<<<(unsigned)tiles, COV_THREADS, COV_SMEM, st>>>(map, sd, R_dev, C, L, nsplit);
+  const int64_t T = (C + COV_BN - 1) / COV_BN;
+  const int64_t tiles = T * (T + 1);
+  int dev = 0, sms = 148;
+  COV_CUDA(cudaGetDevice(&dev));
+  COV_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  k_cov_gemm<<<(unsigned)std::min<int64_t>(tiles, sms), COV_THREADS, COV_SMEM, st>>>(map, sd, R_dev, C, L, nsplit, tiles);
   g_mmq_launches.fetch_add(1, std::memory_order_relaxed);
   COV_CUDA(cudaGetLastError());
   return MMQ_OK;

@@ -38,9 +38,8 @@ for C in (4096, 8192, 16384, 24576):
             capi.trace_cov_dev(Md.data_ptr(), L, C, nsplit, Rd.data_ptr(), ws.data_ptr(), st.cuda_stream)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / K
-        T = (C + 127) // 128; tiles = T * (T + 1) // 2
         nterms = nsplit * (nsplit + 1) // 2
-        fl = 2.0 * tiles * 128 * 128 * L * nterms
+        fl = 1.0 * C * (C + 1) * L * nterms      # algorithmic: the upper triangle, one multiply-add per split product
         print(f"C={C} nsplit={nsplit} {ms:.3f} ms  tensor {fl/ms/1e9:.1f} TFLOP/s  out {C*C*8/ms/1e6:.0f} GB/s", flush=True)
     if C <= 8192:
         ref = torch.cov(Md)  # rows = variables
