@@ -23,7 +23,8 @@ benchmark shape and rank 0 prints them in the JSON line ("gates"); a failed gate
       summed over ranks), and the X matrix of one sweep entry by entry;
   (b) EM: |mu_gpu / mu_oracle - 1| <= 1e-6 and equal iteration count;
   (c) N = 1: posterior mean of log mu against the reference-like GSL chain (MT19937, GSL samplers)
-      within 4 Monte-Carlo standard errors for >= 99.9 % of the transcripts.
+      within 4 Monte-Carlo standard errors (batch means) for >= 99.9 % of the transcripts, or for no
+      fewer than the GPU chain against itself; posterior sd ratio within 5 %.
 
 `--impl reference` times the reference's own algorithm and data flow on ALL host cores (oracle/:
 MT19937 per OpenMP thread, GSL-style samplers, dense per-thread partials; the reference itself
@@ -385,56 +386,65 @@ def run_gates(args, H, w, mu0_gpu, mu_em_gpu, em_iters_gpu, rank, world, dev, al
 
 
 def posterior_gate(args, H, w, mu_em, cpu_sweeps, threads):
-    """(c) posterior mean of log mu: GPU chain vs the reference-like GSL chain on the host cores, both from the EM
-    estimate; also the CPU baseline (the same run is timed).  N = 1 only."""
+    """(c) posterior mean and sd of log mu: GPU chain vs the reference-like GSL chain on the host cores; also the CPU
+    baseline (the same run is timed).  N = 1 only.
+
+    Both chains start at the EM estimate, burn 16 sweeps, and then record EVERY sweep of a window of W sweeps; the statistic
+    compared per transcript is the mean of log mu over that window.  Its Monte-Carlo standard error is estimated by batch
+    means: the GPU chain runs on for NW more windows of the same length and the variance of their means is the sampling
+    variance of exactly that statistic (no autocorrelation-time estimate, no normality of single draws needed).
+    z = (mean_cpu - mean_gpu_window0) / sqrt(2 var_w).  The same estimator between two of the GPU chain's own windows gives
+    the null distribution of z: with posteriors this skewed / slowly mixing (30 % of the transcripts have no fragments of
+    their own) even the chain against itself leaves ~0.2 % of the transcripts beyond 4 standard errors, so the gate is
+    "99.9 % within 4 se, or no worse than the chain against itself" together with the clipped rms of z."""
     from oracle import oracle as orc
     h = w.h
     P = orc.Problem(h.row_ptr, h.col, h.k, w.length)
     S = SWEEPS_PER_STEP
-    burn = S  # one stride of burn-in on both chains (they start at the mode)
-    Lmax = max(1, cpu_sweeps // S)
+    burn = S
+    W = 64
+    while W * 2 <= min(max(cpu_sweeps, 64), 2048):
+        W *= 2                                                  # a power of two: the device summaries (Sokal) need it
+    NW = 32
     mu_c, _, _ = P.gibbs_gsl(mu_em, SEED, burn, threads=threads)
-    t_cpu = 0.0
-    cols = []
-    for j in range(Lmax):   # stride S: slot j = state after S more sweeps; bounded by the time budget
-        mu_c, _, sec = P.gibbs_gsl(mu_c, SEED + 1 + j, S, threads=threads)
-        t_cpu += sec
-        cols.append(mu_c.copy())
-        if t_cpu > args.cpu_seconds and len(cols) >= 16:
-            break
-    Lc = len(cols)
-    tr_c = np.stack(cols, axis=1)
-    cpu_sps = Lc * S / t_cpu
-    Lg = 256
-    H.set_mu(mu_em)
-    H.gibbs(SEED + 7, 0, burn, stride=S, trace_len=0)         # burn-in (its own stream of sweeps)
-    H.gibbs(SEED, 0, Lg * S, stride=S, trace_len=Lg)          # slot j = the state after sweep 16 j
-    tr_g = H.get_trace()
+    mu_c, tr_c, t_cpu = P.gibbs_gsl(mu_c, SEED + 1, W, stride=1, trace_len=W, threads=threads)
+    cpu_sps = W / t_cpu
     with np.errstate(divide="ignore"):
-        lg, lc = np.log(tr_g), np.log(tr_c)
-    sd = lg.std(axis=1, ddof=1)
-    # Monte-Carlo standard errors: the integrated autocorrelation time at this stride from the device's Sokal estimate on the
-    # GPU chain's log trace (mmq_summarize: src/mmseq.cpp:1308-1363, sokal.cc), floor 1; lag-1 AR(1) form where Sokal gives up
-    Sg = H.summarize(0)
-    x = lg - lg.mean(axis=1, keepdims=True)
-    rho = np.clip((x[:, 1:] * x[:, :-1]).sum(axis=1) / np.maximum((x * x).sum(axis=1), 1e-300), 0.0, 0.95)
-    tau = np.where((Sg["status"] == 0) & np.isfinite(Sg["tau"]), np.maximum(Sg["tau"], 1.0), (1 + rho) / (1 - rho))
-    tau = np.maximum(tau, (1 + rho) / (1 - rho))
-    # the two chains are compared over the SAME window of sweeps (both start at the EM estimate: a chain that has not
-    # forgotten its start yet is biased the same way on both sides), the spread comes from the whole GPU chain
-    se = sd * np.sqrt(tau) * np.sqrt(2.0 / Lc)
-    lg = lg[:, 1:Lc + 1]   # GPU slot j: after sweep 16 j; CPU sample j: after 16 (j + 1) sweeps
-    diff = np.abs(lg.mean(axis=1) - lc.mean(axis=1))
-    finite = np.isfinite(diff) & np.isfinite(se) & (se > 0)
-    frac = float((diff[finite] <= 4.0 * se[finite]).mean())
-    sd_c = lc.std(axis=1, ddof=1) if Lc > 2 else None
-    sd_ratio = float(np.median(sd_c[finite] / sd[finite])) if sd_c is not None else None
-    gate = {"chains": f"GPU and CPU (GSL-like, {threads} threads) chains from the EM estimate, {burn} burn-in sweeps, the same {Lc} trace slots at stride {S} "
-                      f"compared; sd and autocorrelation time from {Lg} GPU slots",
-            "frac_within_4se": frac, "need": 0.999, "median_sd_ratio_cpu_over_gpu": sd_ratio, "features": int(finite.sum()),
-            "ok": bool(frac >= 0.999), "hard_fail_below": 0.99}
+        lc = np.log(tr_c)
+    del tr_c
+    mean_c = lc.mean(axis=1)
+    sd_c = lc.std(axis=1, ddof=1)
+    del lc
+    H.set_mu(mu_em)
+    H.gibbs(SEED + 7, 0, burn, stride=S, trace_len=0)           # burn-in (its own stream of sweeps)
+    means, variances = [], []
+    for j in range(NW + 3):                                     # window 0 pairs with the CPU window, 1 and 2 make the null pair
+        H.gibbs(SEED + 100 + j, 0, W, stride=1, trace_len=W)
+        Sg = H.summarize(0)
+        means.append(Sg["log_mean"].copy())
+        variances.append(Sg["var"].copy())
+    G = np.stack(means[3:])
+    var_w = G.var(axis=0, ddof=1)
+    se = np.sqrt(2.0 * var_w)
+    with np.errstate(all="ignore"):
+        z = np.abs(mean_c - means[0]) / se
+        z0 = np.abs(means[1] - means[2]) / se
+    finite = np.isfinite(z) & np.isfinite(z0) & (se > 0)
+    z, z0 = z[finite], z0[finite]
+    frac, frac0 = float((z <= 4.0).mean()), float((z0 <= 4.0).mean())
+    rms, rms0 = float(np.sqrt(np.mean(np.minimum(z, 6.0) ** 2))), float(np.sqrt(np.mean(np.minimum(z0, 6.0) ** 2)))
+    sd_g = np.sqrt(np.mean(np.stack(variances[1:]), axis=0))
+    with np.errstate(all="ignore"):
+        sd_ratio = float(np.median((sd_c / sd_g)[finite]))
+    ok = bool((frac >= 0.999 or frac >= frac0 - 5e-4) and rms <= 1.05 * rms0 and abs(sd_ratio - 1.0) < 0.05)
+    gate = {"chains": f"GPU and CPU (GSL-like, {threads} threads) chains from the EM estimate, {burn} burn-in sweeps, mean of log mu over the same "
+                      f"window of {W} consecutive sweeps; standard error by batch means over {NW} further GPU windows",
+            "frac_within_4se": frac, "need": 0.999, "self_frac_within_4se": frac0,
+            "rms_z_clipped": rms, "self_rms_z_clipped": rms0, "median_sd_ratio_cpu_over_gpu": sd_ratio, "features": int(finite.sum()),
+            "rule": "frac >= 0.999 or frac >= self_frac - 5e-4 (the GPU chain against itself, same estimator); rms_z <= 1.05 self_rms_z; |sd ratio - 1| < 0.05",
+            "ok": ok, "hard_fail_below": 0.99}
     base = {"value": cpu_sps * value_classes(args, w), "unit": "allocations/s", "sweeps_per_s": cpu_sps, "cores": threads, "kind": "port",
-            "layout": w.layout, "sample": f"{Lc * S} full sweeps of the same shard (collapsed representation) after {burn} warm-up sweeps"}
+            "layout": w.layout, "sample": f"{W} full sweeps of the same shard (collapsed representation) after {burn} warm-up sweeps"}
     return gate, base
 
 
@@ -869,8 +879,9 @@ def main():
             wc = w if w.layout == "collapsed" else make_workload(args, 0, 1, weights=False, layout="collapsed")
             if wc is w:
                 pg, base = posterior_gate(args, H, wc, mu_oracle_em, args.cpu_sweeps, host_threads())
-                g["posterior"] = pg   # statistical: reported against 0.999, the run only FAILS on a gross miss
-                g["ok"] = bool(g["ok"] and pg["frac_within_4se"] >= pg["hard_fail_below"])
+                g["posterior"] = pg   # statistical: pg["rule"]; the run FAILS when the rule fails by a margin or on a gross miss
+                g["ok"] = bool(g["ok"] and pg["frac_within_4se"] >= pg["hard_fail_below"] and
+                               (pg["ok"] or pg["frac_within_4se"] >= pg["self_frac_within_4se"] - 2e-3))
             else:
                 from oracle import oracle as orc
                 Pc = orc.Problem(wc.h.row_ptr, wc.h.col, wc.h.k, wc.length)
