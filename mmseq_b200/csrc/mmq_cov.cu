@@ -11,18 +11,27 @@
  *   k_cov_prep   one block per feature: mean and centred sum of squares in fp64, z = (x - mean) / sqrt(ssq)
  *                (so that the Gram matrix of z IS the correlation matrix, |z| <= 1), split into 1..3 bf16 terms
  *                z = z0 + z1 + z2 with fp64 residuals, stored K-major: Z[c][split * L + s];
- *   k_cov_gemm   upper-triangular 128 x 128 tiles of Z Z^T on the 5th-generation tensor cores: operand tiles by TMA
- *                (cp.async.bulk.tensor, 128-byte swizzle, SASS UTMALDG) into a 3-stage shared-memory ring,
- *                tcgen05.mma (kind::f16, bf16 x bf16 -> fp32, SASS UTCHMMA) issued by one thread into a 128-column
- *                TMEM accumulator, completion through tcgen05.commit on mbarriers; the split terms z_a z_b with
- *                a + b < nsplit are extra K-segments of the same accumulation (smallest terms first).  Epilogue:
- *                tcgen05.ld (SASS LDTM), back to covariance in fp64 (r * sd_i * sd_j), both triangles stored, the
- *                diagonal exactly var_i.  Two CTAs per SM so that one tile's epilogue overlaps another's main loop.
+ *   k_cov_gemm   the 128 x 256 tiles of Z Z^T that touch the upper triangle, on the 5th-generation tensor cores.  Persistent,
+ *                one CTA per SM, warp-specialised: warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, SASS
+ *                UTMALDG) into a 3-stage shared-memory ring; warp 1 = one thread issuing tcgen05.mma (kind::f16, bf16 x
+ *                bf16 -> fp32, M 128 x N 256 x K 16, SASS UTCHMMA) into one of TWO 256-column TMEM accumulators, stage
+ *                release and accumulator hand-over through tcgen05.commit on mbarriers; warps 2..9 = epilogue of the
+ *                previous tile while the next one accumulates: tcgen05.ld (SASS LDTM), back to covariance in fp64
+ *                (r * sd_i * sd_j), a 32 x 32 transposition through shared memory so that BOTH triangles are stored with
+ *                full 256-byte warp stores (streaming), the diagonal exactly var_i, exactly symmetric.  The split terms
+ *                z_a z_b with a + b < nsplit are extra K-segments of the same accumulation (smallest terms first).
  *   k_mean_corrs the scan over samples, one thread per (row of ts, column) pair.
  *
- * Accuracy: nsplit = 2 (three bf16 products per fp64 product) leaves |r_gpu - r_fp64| <= ~2e-5 in correlation units,
- * nsplit = 3 (six products) ~2e-6 (fp32 accumulation over 6 L terms) — against a Monte-Carlo error of a correlation
- * estimated from 1024 draws of >= 1e-2.  The tests state the tolerance.
+ * Accuracy (measured, correlation units |cov_gpu - cov_fp64| / (sd_i sd_j), L = 1024): nsplit = 1: 3e-4, 2: 5e-6 (the
+ * default), 3: 2e-6 (the floor of fp32 accumulation) — against a Monte-Carlo error of a correlation estimated from 1024
+ * draws of >= 1e-2.  The tests state the tolerances.
+ *
+ * What bounds it (C = 16384, nsplit = 2: 0.99 ms, 0.83 PFLOP/s algorithmic = 0.50 of the measured cuBLAS bf16 peak, tensor
+ * pipe 52 % active; profiles/r02_k_cov_gemm_ncu_summary.txt): shared-memory bandwidth.  A single-CTA 128 x 256 x 16 MMA reads
+ * 12 KB of operands from shared memory per 1 MFLOP (66 B/clk at the measured peak rate), TMA writes 48 KB per four of them
+ * (64 B/clk) and the epilogue's transposition adds 40 B/clk: more than the 128 B/clk an SM has.  Loading every tile once
+ * for all split products (64-byte swizzle, 1.5x less L2 traffic) was measured: same time, so it is not the L2.  The next
+ * step is the CTA pair (tcgen05.mma.cta_group::2, 256 x 256 per pair: 8 KB of operand reads per MMA and SM).
  */
 #include <cuda.h>
 #include <cuda_bf16.h>
