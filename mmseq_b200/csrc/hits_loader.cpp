@@ -2,10 +2,12 @@
  * writer/reader pair: src/hitsio.cpp:162-240 (writer), :250-447 (reader),
  * README.md:388-403. */
 #include "hits_loader.h"
+#include "inflate_par.h"
 
 #include <zlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <cmath>
@@ -37,15 +39,47 @@ class ByteSource {
     int c = fgetc(f_);
     if (c == EOF) { compressed_ = false; }
     else { ungetc(c, f_); compressed_ = (c == 0x78); }
+    pos_ = len_ = 0;
+    base_ = nullptr;
+    if (compressed_ && !getenv("MMQ_LOADER_SERIAL_INFLATE")) {
+      /* the whole stream on all host threads (inflate_par.h); anything it cannot handle falls through to zlib below,
+       * which also produces the proper diagnosis for a corrupt or truncated file */
+      fseek(f_, 0, SEEK_END);
+      const long sz = ftell(f_);
+      fseek(f_, 0, SEEK_SET);
+      long par_min = 4 << 20; /* smaller files are not worth the threads */
+      if (const char* e = getenv("MMQ_LOADER_PAR_MIN_BYTES")) par_min = atol(e);
+      if (sz > par_min) {
+        const bool tm = getenv("MMQ_LOADER_TIMING") != nullptr;
+        auto clk = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t0 = clk();
+        std::unique_ptr<uint8_t[]> rawp(new uint8_t[(size_t)sz]);
+        struct { uint8_t* p; size_t n; uint8_t* data() { return p; } size_t size() { return n; } } raw{rawp.get(), (size_t)sz};
+        if (fread(raw.data(), 1, (size_t)sz, f_) == (size_t)sz) {
+          const double t1 = clk();
+          unsigned hc = std::thread::hardware_concurrency();
+          if (const char* e = getenv("MMQ_LOADER_INFLATE_THREADS")) hc = (unsigned)atoi(e);
+          const bool okp = ipar::inflate_parallel(raw.data(), raw.size(), (int)std::max(1u, hc), whole_);
+          if (tm) fprintf(stderr, "[loader] file read %.2f s, parallel inflate (%u threads) %.2f s%s\n", t1 - t0, hc, clk() - t1, okp ? "" : " FAILED: serial zlib instead");
+          if (okp) {
+            base_ = (const char*)whole_.data();
+            len_ = whole_.size();
+            whole_mode_ = true;
+            return true;
+          }
+        }
+        fseek(f_, 0, SEEK_SET);
+      }
+    }
     if (compressed_) {
       memset(&zs_, 0, sizeof zs_);
       if (inflateInit(&zs_) != Z_OK) return false;
       zinit_ = true;
       in_.resize(1 << 20);
     }
-    pos_ = len_ = 0;
     producer_done_ = false;
     stop_ = false;
+    whole_mode_ = false;
     prod_ = std::thread([this] { produce(); });
     return true;
   }
@@ -59,13 +93,18 @@ class ByteSource {
     if (f_) { fclose(f_); f_ = nullptr; }
   }
   bool corrupt() const { return corrupt_; }
+  /* the whole inflated file is in memory (parallel inflate): the record walk can then hand offsets to parallel builders */
+  bool whole() const { return whole_mode_; }
+  const char* whole_base() const { return base_; }
+  size_t whole_pos() const { return pos_; }
+  size_t whole_size() const { return len_; }
   int peek() {
     if (pos_ == len_ && !fill()) return EOF;
-    return (unsigned char)buf_[pos_];
+    return (unsigned char)base_[pos_];
   }
   int get() {
     if (pos_ == len_ && !fill()) return EOF;
-    return (unsigned char)buf_[pos_++];
+    return (unsigned char)base_[pos_++];
   }
   /* like std::getline: false only when nothing at all could be read */
   bool getline(std::string& out) {
@@ -74,7 +113,7 @@ class ByteSource {
     for (;;) {
       if (pos_ == len_ && !fill()) return any;
       any = true;
-      const char* b = buf_.data() + pos_;
+      const char* b = base_ + pos_;
       const char* nl = (const char*)memchr(b, '\n', len_ - pos_);
       if (nl) {
         out.append(b, (size_t)(nl - b));
@@ -88,7 +127,7 @@ class ByteSource {
   /* a line as a view into the current block (no copy) unless it straddles two blocks */
   bool getline_view(const char*& p, size_t& n) {
     if (pos_ == len_ && !fill()) return false;
-    const char* b = buf_.data() + pos_;
+    const char* b = base_ + pos_;
     const char* nl = (const char*)memchr(b, '\n', len_ - pos_);
     if (nl) { p = b; n = (size_t)(nl - b); pos_ += n + 1; return true; }
     if (!getline(carry_)) return false;
@@ -100,13 +139,13 @@ class ByteSource {
     while (n) {
       if (pos_ == len_ && !fill()) return false;
       size_t c = std::min(n, len_ - pos_);
-      memcpy(d, buf_.data() + pos_, c);
+      memcpy(d, base_ + pos_, c);
       pos_ += c; d += c; n -= c;
     }
     return true;
   }
   bool read_u32(uint32_t& v) { /* raw little-endian, src/hitsio.cpp:22-34 */
-    if (len_ - pos_ >= 4) { memcpy(&v, buf_.data() + pos_, 4); pos_ += 4; return true; }
+    if (len_ - pos_ >= 4) { memcpy(&v, base_ + pos_, 4); pos_ += 4; return true; }
     return read_bytes(&v, 4);
   }
   /* one byte, or 0xFF followed by a uint32 (src/hitsio.cpp:36-55) */
@@ -158,6 +197,7 @@ class ByteSource {
     }
   }
   bool fill() {
+    if (whole_mode_) return false; /* the whole file is already in memory */
     std::unique_lock<std::mutex> lk(mu_);
     cv_.wait(lk, [&] { return !q_.empty() || producer_done_; });
     if (q_.empty()) return false;
@@ -167,12 +207,16 @@ class ByteSource {
     cv_.notify_all();
     pos_ = 0;
     len_ = buf_.size();
+    base_ = buf_.data();
     return len_ > 0;
   }
   FILE* f_ = nullptr;
   bool compressed_ = false, zinit_ = false, corrupt_ = false;
   z_stream zs_;
   std::vector<char> buf_, in_;
+  const char* base_ = nullptr; /* the current block (or the whole inflated file) */
+  ipar::Bytes whole_;
+  bool whole_mode_ = false;
   std::string carry_;
   size_t pos_ = 0, len_ = 0;
   std::thread prod_;
@@ -193,8 +237,9 @@ inline uint64_t mix64(uint64_t x) {
 
 struct ClassBuilder::Impl {
   int layout;
-  bool header_order = false;
+  bool header_order = false, identity_cols = false;
   bool weighted;
+  int builders = 1; /* threads of ingest_parallel */
   int64_t N = 0;
   std::vector<int32_t> hdr2col, col2hdr, doublehits;
   /* distinct classes in first-appearance order */
@@ -285,6 +330,7 @@ struct ClassBuilder::Impl {
             S.table.swap(nt);
           }
         }
+        else if (b->rec[i] < S.first_rec[(size_t)cid]) S.first_rec[(size_t)cid] = b->rec[i]; /* batches of several builders arrive in any order */
         S.k[(size_t)cid]++;
         if (keep_rec) S.rec_cls.emplace_back(b->rec[i], cid);
       }
@@ -312,31 +358,197 @@ struct ClassBuilder::Impl {
     for (auto& sp : shards) { if (!sp->cur->rec.empty()) push(*sp); }
     for (auto& sp : shards) { { std::lock_guard<std::mutex> lk(sp->mu); sp->done = true; } sp->cv.notify_all(); }
     for (auto& sp : shards) sp->th.join();
-    struct Ref { int64_t first; int32_t shard, local; };
-    std::vector<Ref> refs;
-    for (size_t s = 0; s < shards.size(); ++s)
-      for (size_t c = 0; c < shards[s]->hash.size(); ++c) refs.push_back({shards[s]->first_rec[c], (int32_t)s, (int32_t)c});
-    std::sort(refs.begin(), refs.end(), [](const Ref& a, const Ref& b) { return a.first < b.first; });
-    std::vector<std::vector<int32_t>> l2g(shards.size());
-    for (size_t s = 0; s < shards.size(); ++s) l2g[s].resize(shards[s]->hash.size());
-    cls_ptr.assign(1, 0); cls_col.clear(); cls_k.clear(); cls_hash.clear();
-    cls_k.reserve(refs.size()); cls_hash.reserve(refs.size());
-    for (size_t g = 0; g < refs.size(); ++g) {
-      const Shard& S = *shards[(size_t)refs[g].shard];
-      const int32_t c = refs[g].local;
-      l2g[(size_t)refs[g].shard][(size_t)c] = (int32_t)g;
-      cls_col.insert(cls_col.end(), S.col.begin() + S.ptr[(size_t)c], S.col.begin() + S.ptr[(size_t)c + 1]);
-      cls_ptr.push_back((int64_t)cls_col.size());
-      cls_k.push_back(S.k[(size_t)c]);
-      cls_hash.push_back(S.hash[(size_t)c]);
+    /* global order = ascending first record.  Every shard sorts its own classes (in parallel), a K-way merge interleaves
+     * them, and the copies into the merged arrays run in parallel again: the sequential part is one pass over the classes. */
+    const size_t K = shards.size();
+    struct Ref { int64_t first; int32_t local; };
+    std::vector<std::vector<Ref>> sorted(K);
+    {
+      std::vector<std::thread> th;
+      for (size_t s = 0; s < K; ++s)
+        th.emplace_back([&, s] {
+          const Shard& S = *shards[s];
+          std::vector<Ref>& v = sorted[s];
+          v.resize(S.hash.size());
+          for (size_t c = 0; c < v.size(); ++c) v[c] = {S.first_rec[c], (int32_t)c};
+          std::sort(v.begin(), v.end(), [](const Ref& a, const Ref& b) { return a.first < b.first; });
+        });
+      for (auto& t : th) t.join();
+    }
+    size_t total = 0;
+    for (size_t s = 0; s < K; ++s) total += sorted[s].size();
+    std::vector<int32_t> g_shard(total), g_local(total);
+    std::vector<std::vector<int32_t>> l2g(K);
+    for (size_t s = 0; s < K; ++s) l2g[s].resize(sorted[s].size());
+    cls_ptr.assign(total + 1, 0);
+    {
+      std::vector<size_t> head(K, 0);
+      for (size_t g = 0; g < total; ++g) {
+        size_t best = K;
+        int64_t bf = 0;
+        for (size_t s = 0; s < K; ++s)
+          if (head[s] < sorted[s].size() && (best == K || sorted[s][head[s]].first < bf)) { best = s; bf = sorted[s][head[s]].first; }
+        const int32_t c = sorted[best][head[best]++].local;
+        g_shard[g] = (int32_t)best;
+        g_local[g] = c;
+        l2g[best][(size_t)c] = (int32_t)g;
+        const Shard& S = *shards[best];
+        cls_ptr[g + 1] = cls_ptr[g] + (S.ptr[(size_t)c + 1] - S.ptr[(size_t)c]);
+      }
+    }
+    cls_col.resize((size_t)cls_ptr[total]);
+    cls_k.resize(total);
+    cls_hash.resize(total);
+    {
+      const int W = (int)std::max<size_t>(1, std::min<size_t>(16, std::thread::hardware_concurrency()));
+      auto copy = [&](int w) {
+        for (size_t g = total * (size_t)w / (size_t)W; g < total * (size_t)(w + 1) / (size_t)W; ++g) {
+          const Shard& S = *shards[(size_t)g_shard[g]];
+          const size_t c = (size_t)g_local[g];
+          std::memcpy(cls_col.data() + cls_ptr[g], S.col.data() + S.ptr[c], sizeof(int32_t) * (size_t)(S.ptr[c + 1] - S.ptr[c]));
+          cls_k[g] = S.k[c];
+          cls_hash[g] = S.hash[c];
+        }
+      };
+      std::vector<std::thread> th;
+      for (int w = 1; w < W; ++w) th.emplace_back(copy, w);
+      copy(0);
+      for (auto& t : th) t.join();
     }
     if (layout != LAYOUT_COLLAPSED) {
-      /* records were numbered densely over the keyed ones, in stream order */
+      /* records were numbered densely over the keyed ones, in stream order; a record belongs to one shard only */
       rec_class.assign((size_t)n_records_keyed, -1);
-      for (size_t s = 0; s < shards.size(); ++s)
-        for (auto& rc : shards[s]->rec_cls) rec_class[(size_t)rc.first] = l2g[s][(size_t)rc.second];
+      std::vector<std::thread> th;
+      for (size_t s = 0; s < K; ++s)
+        th.emplace_back([&, s] { for (auto& rc : shards[s]->rec_cls) rec_class[(size_t)rc.first] = l2g[s][(size_t)rc.second]; });
+      for (auto& t : th) t.join();
     }
     shards.clear();
+  }
+
+  void push_batch(Shard& S, std::unique_ptr<Batch> b) {
+    {
+      std::unique_lock<std::mutex> lk(S.mu);
+      S.cv.wait(lk, [&] { return S.q.size() < 16; });
+      S.q.push_back(std::move(b));
+    }
+    S.cv.notify_all();
+  }
+
+  /* Records handed over all at once (the inflated file in memory, or the harness's arrays): W builder threads take
+   * contiguous ranges of records and do what add_record() does per record — de-duplication, sort, hash — but in HEADER index
+   * space, so that nothing depends on the order in which records are seen; the class keys go to the hash-sharded workers
+   * as before.  The numbering the reference derives from the stream order (column = first appearance of the transcript,
+   * src/mmseq.cpp:403; class = first appearance of the set, :417-418) is reconstructed afterwards from the smallest
+   * (record, position) each transcript was seen at and the smallest record of each class: same result as the sequential
+   * walk, checked against it in tests/test_loader.py.
+   * acc(r, p, cnt): record r's cnt little-endian uint32 transcript indices at p (unaligned).  Returns 0, or 1 when an index
+   * is out of range. */
+  template <class Acc>
+  int ingest_parallel(int64_t nrec, int64_t T, const Acc& acc, int W) {
+    const int K = (int)shards.size();
+    const uint64_t NONE = ~0ull;
+    std::vector<std::vector<uint64_t>> fa((size_t)W);
+    std::vector<std::vector<int32_t>> dh((size_t)W);
+    std::atomic<int> bad(0);
+    auto build = [&](int w) {
+      std::vector<uint64_t>& first = fa[(size_t)w];
+      std::vector<int32_t>& dbl = dh[(size_t)w];
+      first.assign((size_t)T, NONE);
+      dbl.assign((size_t)T, 0);
+      std::vector<std::unique_ptr<Batch>> cur((size_t)K);
+      for (auto& c : cur) c.reset(new Batch());
+      std::vector<int32_t> ids;
+      const int64_t r0 = nrec * w / W, r1 = nrec * (w + 1) / W;
+      for (int64_t r = r0; r < r1; ++r) {
+        const uint8_t* p;
+        int cnt;
+        acc(r, p, cnt);
+        ids.clear();
+        for (int j = 0; j < cnt; ++j) {
+          uint32_t v;
+          memcpy(&v, p + 4 * (size_t)j, 4);
+          if (v >= (uint32_t)T) { bad.store(1); return; }
+          if (first[v] == NONE) first[v] = ((uint64_t)r << 24) | (uint64_t)std::min(j, 0xffffff);
+          bool dup = false;
+          if (ids.size() <= 32) {
+            for (int32_t e : ids) if (e == (int32_t)v) { dup = true; break; }
+            if (dup) { dbl[v]++; continue; } /* src/mmseq.cpp:404-409 */
+          }
+          ids.push_back((int32_t)v);
+        }
+        std::sort(ids.begin(), ids.end());
+        if (ids.size() > 33) { /* long records: duplicates removed after the sort */
+          size_t o = 1;
+          for (size_t j = 1; j < ids.size(); ++j) {
+            if (ids[j] == ids[o - 1]) dbl[(size_t)ids[j]]++;
+            else ids[o++] = ids[j];
+          }
+          ids.resize(o);
+        }
+        uint64_t hsh = 0x9e3779b97f4a7c15ull ^ (uint64_t)ids.size();
+        for (int32_t e : ids) hsh = mix64(hsh ^ (uint64_t)(uint32_t)e) + 0x632be59bd9b4e019ull;
+        const int sh = (int)((hsh >> 40) % (uint64_t)K);
+        Batch& B = *cur[(size_t)sh];
+        B.rec.push_back(r);
+        B.hash.push_back(hsh);
+        B.cols.insert(B.cols.end(), ids.begin(), ids.end());
+        B.off.push_back((uint32_t)B.cols.size());
+        if (B.rec.size() >= BATCH_RECORDS) {
+          push_batch(*shards[(size_t)sh], std::move(cur[(size_t)sh]));
+          cur[(size_t)sh].reset(new Batch());
+        }
+      }
+      for (int sh = 0; sh < K; ++sh)
+        if (!cur[(size_t)sh]->rec.empty()) push_batch(*shards[(size_t)sh], std::move(cur[(size_t)sh]));
+    };
+    {
+      std::vector<std::thread> th;
+      for (int w = 1; w < W; ++w) th.emplace_back(build, w);
+      build(0);
+      for (auto& t : th) t.join();
+    }
+    N += nrec;
+    n_records_keyed += nrec;
+    const bool tm = getenv("MMQ_LOADER_TIMING") != nullptr;
+    auto clk = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tb = clk();
+    merge_shards(); /* classes in order of their first record, members still header indices */
+    if (tm) fprintf(stderr, "[loader]   %d builders + %d class-table workers; drain + merge %.2f s\n", W, K, clk() - tb);
+    if (bad.load()) return 1;
+    /* columns: transcripts in order of first appearance */
+    const bool identity = identity_cols;
+    std::vector<uint64_t>& first = fa[0];
+    for (int w = 1; w < W; ++w)
+      for (int64_t h = 0; h < T; ++h) first[(size_t)h] = std::min(first[(size_t)h], fa[(size_t)w][(size_t)h]);
+    if (!identity) {
+      std::vector<int32_t> seen;
+      for (int64_t h = 0; h < T; ++h) if (first[(size_t)h] != NONE) seen.push_back((int32_t)h);
+      std::sort(seen.begin(), seen.end(), [&](int32_t a, int32_t b) { return first[(size_t)a] < first[(size_t)b]; });
+      col2hdr = seen;
+      doublehits.assign(seen.size(), 0);
+      for (size_t c = 0; c < seen.size(); ++c) hdr2col[(size_t)seen[c]] = (int32_t)c;
+    }
+    for (int w = 0; w < W; ++w)
+      for (int64_t h = 0; h < T; ++h)
+        if (dh[(size_t)w][(size_t)h]) doublehits[(size_t)hdr2col[(size_t)h]] += dh[(size_t)w][(size_t)h];
+    if (!identity) {
+      /* members: header index -> column, ascending again (the reference sorts the column indices, :412) */
+      const int64_t C = (int64_t)cls_hash.size();
+      auto renum = [&](int w) {
+        for (int64_t c = C * w / W; c < C * (w + 1) / W; ++c) {
+          int32_t* b = cls_col.data() + cls_ptr[(size_t)c];
+          int32_t* e = cls_col.data() + cls_ptr[(size_t)c + 1];
+          for (int32_t* q = b; q < e; ++q) *q = hdr2col[(size_t)*q];
+          std::sort(b, e);
+        }
+      };
+      std::vector<std::thread> th;
+      for (int w = 1; w < W; ++w) th.emplace_back(renum, w);
+      renum(0);
+      for (auto& t : th) t.join();
+    }
+    return 0;
   }
 
   void grow_table() {
@@ -356,6 +568,7 @@ ClassBuilder::ClassBuilder(int64_t T, int layout, bool weighted) : p_(new Impl()
   p_->header_order = (layout & LAYOUT_HEADER_ORDER_COLUMNS) != 0 && !(layout & LAYOUT_IDENTITY_COLUMNS);
   p_->weighted = weighted;
   p_->hdr2col.assign((size_t)T, -1);
+  p_->identity_cols = (layout & LAYOUT_IDENTITY_COLUMNS) != 0;
   if (layout & LAYOUT_IDENTITY_COLUMNS) {
     p_->col2hdr.resize((size_t)T);
     p_->doublehits.assign((size_t)T, 0);
@@ -363,16 +576,39 @@ ClassBuilder::ClassBuilder(int64_t T, int layout, bool weighted) : p_(new Impl()
   }
   p_->grow_table();
   if (!weighted) {
-    int K = 3;
-    if (const char* e = getenv("MMQ_LOADER_THREADS")) K = atoi(e);
+    /* hash-shard workers (they own the class tables) and, for records handed over all at once, as many builder threads */
     const unsigned hc = std::thread::hardware_concurrency();
+    int K = hc >= 8 ? std::min(12, (int)hc / 2 - 1) : 3;
+    if (const char* e = getenv("MMQ_LOADER_THREADS")) K = atoi(e);
     if (hc && (int)hc - 2 < K) K = std::max(0, (int)hc - 2);
     if (K > 0) p_->start_workers(K);
+    p_->builders = std::max(1, std::min(16, (int)hc - K));
+    if (const char* e = getenv("MMQ_LOADER_BUILDERS")) p_->builders = std::max(1, atoi(e));
   }
 }
 ClassBuilder::~ClassBuilder() {
   if (!p_->shards.empty()) p_->merge_shards();
   delete p_;
+}
+
+bool ClassBuilder::parallel_ready() const { return !p_->weighted && !p_->shards.empty() && p_->N == 0; }
+int ClassBuilder::add_records_binary(const uint8_t* base, const uint64_t* off, int64_t nrec) {
+  Impl& P = *p_;
+  auto acc = [base, off](int64_t r, const uint8_t*& p, int& cnt) {
+    uint32_t c;
+    memcpy(&c, base + off[r], 4);
+    cnt = (int)c;
+    p = base + off[r] + 4;
+  };
+  return P.ingest_parallel(nrec, (int64_t)P.hdr2col.size(), acc, P.builders);
+}
+int ClassBuilder::add_records_csr(const int64_t* frag_ptr, const int32_t* frag_tid, int64_t nrec) {
+  Impl& P = *p_;
+  auto acc = [frag_ptr, frag_tid](int64_t r, const uint8_t*& p, int& cnt) {
+    cnt = (int)(frag_ptr[r + 1] - frag_ptr[r]);
+    p = (const uint8_t*)(frag_tid + frag_ptr[r]);
+  };
+  return P.ingest_parallel(nrec, (int64_t)P.hdr2col.size(), acc, P.builders);
 }
 
 void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
@@ -646,6 +882,7 @@ double parse_double_like_istream(const std::string& s) { /* string_to_double, sr
 
 int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClasses& cls, std::string& err) {
   ByteSource src;
+  const double t_open0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
   if (!src.open(path)) { err = "Error reading hits file \"" + path + "\"."; return 1; }
   hdr = HitsHeader();
   std::vector<std::pair<std::string, std::vector<std::string>>> genes_raw;
@@ -739,6 +976,7 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
   const bool timing = getenv("MMQ_LOADER_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t_hdr = now();
+  if (timing) fprintf(stderr, "[loader] open%s + header %.2f s\n", src.whole() ? " (file inflated on all threads)" : "", t_hdr - t_open0);
   if (hdr.schema == 2 && (layout & 15) == LAYOUT_COLLAPSED) {
     err = "Error: \"" + path + "\" carries per-hit weights (schema 2): it needs a per-fragment layout.";
     return 1;
@@ -774,6 +1012,49 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
   } else {
     /* records, src/hitsio.cpp:413-439; read names are delta-coded (:101-115) and unused here */
     std::string mid;
+    if (hdr.schema == 1 && src.whole() && cb.parallel_ready() && !getenv("MMQ_LOADER_SERIAL_RECORDS")) {
+      /* the inflated file is in memory: one cheap sequential walk finds where each record's hit list starts (the delta-coded
+       * names make record boundaries sequential), the rest — de-duplication, sort, hash, class tables — runs on all threads */
+      const uint8_t* b = (const uint8_t*)src.whole_base();
+      const size_t end = src.whole_size();
+      size_t p = src.whole_pos();
+      const std::string malformed = "Hits file looks malformed.";
+      std::vector<uint64_t> off;
+      off.reserve((end - p) / 24 + 16);
+      const uint32_t Tn = (uint32_t)all_names.size();
+      auto line_end = [&](size_t q) { while (q < end && b[q] != '\n') ++q; return q; }; /* names are a few bytes: no memchr call */
+      auto small = [&](size_t& q) { /* one byte, or 0xFF + uint32 (src/hitsio.cpp:36-55) */
+        if (q >= end) return false;
+        if (b[q] == 255) { if (q + 5 > end) return false; q += 5; } else q += 1;
+        return true;
+      };
+      while (p < end) {
+        size_t nl = line_end(p);
+        if (nl == p) { /* empty line: delta form */
+          ++p;
+          if (!small(p)) { err = malformed; return 1; }
+          nl = line_end(p);
+          if (nl >= end) { err = malformed; return 1; }
+          p = nl + 1;
+          if (!small(p)) { err = malformed; return 1; }
+        } else {
+          p = nl < end ? nl + 1 : end;
+        }
+        if (p + 4 > end) { err = malformed; return 1; }
+        uint32_t cnt;
+        memcpy(&cnt, b + p, 4);
+        if (cnt == 0) { err = "Error: a read record without any mapping transcripts in the hits file."; return 1; }
+        if (cnt > Tn || p + 4 + 4 * (size_t)cnt > end) { err = malformed; return 1; }
+        off.push_back((uint64_t)p);
+        p += 4 + 4 * (size_t)cnt;
+      }
+      const double t_scan = now();
+      if (cb.add_records_binary(b, off.data(), (int64_t)off.size())) { err = malformed; return 1; }
+      const double t_rec = now();
+      cb.finish(cls);
+      if (timing) fprintf(stderr, "[loader] record walk %.2f s, classes (parallel) %.2f s, finish (layout) %.2f s\n", t_scan - t_hdr, t_rec - t_scan, now() - t_rec);
+      return 0;
+    }
     for (;;) {
       const char* lp; size_t ln;
       if (!src.getline_view(lp, ln)) break;
@@ -860,11 +1141,18 @@ mmqh_hits* mmqh_from_records(int64_t T, const double* efflen, int64_t N, const i
   H->hdr.efflen.assign(efflen, efflen + T);
   H->hdr.names.resize((size_t)T);
   mmq::ClassBuilder cb(T, layout, frag_w != nullptr);
-  for (int64_t f = 0; f < N; ++f) {
-    const int64_t b = frag_ptr[f], e = frag_ptr[f + 1];
-    for (int64_t q = b; q < e; ++q)
-      if (frag_tid[q] < 0 || frag_tid[q] >= T) { set_err(err, errlen, "transcript index out of range"); delete H; return nullptr; }
-    cb.add_record(frag_tid + b, frag_w ? frag_w + b : nullptr, (int)(e - b));
+  bool any_empty = false;
+  for (int64_t f = 0; f < N && !any_empty; ++f) any_empty = frag_ptr[f + 1] == frag_ptr[f];
+  if (!any_empty && N > 0 && cb.parallel_ready() && !getenv("MMQ_LOADER_SERIAL_RECORDS")) {
+    /* all records at once on all host threads (a negative index reads as a huge unsigned one: out of range) */
+    if (cb.add_records_csr(frag_ptr, frag_tid, N)) { set_err(err, errlen, "transcript index out of range"); delete H; return nullptr; }
+  } else {
+    for (int64_t f = 0; f < N; ++f) {
+      const int64_t b = frag_ptr[f], e = frag_ptr[f + 1];
+      for (int64_t q = b; q < e; ++q)
+        if (frag_tid[q] < 0 || frag_tid[q] >= T) { set_err(err, errlen, "transcript index out of range"); delete H; return nullptr; }
+      cb.add_record(frag_tid + b, frag_w ? frag_w + b : nullptr, (int)(e - b));
+    }
   }
   cb.finish(H->cls);
   flatten(H);
@@ -872,6 +1160,16 @@ mmqh_hits* mmqh_from_records(int64_t T, const double* efflen, int64_t N, const i
 }
 
 void mmqh_free(mmqh_hits* H) { delete H; }
+
+/* test support: inflate_par.h on a zlib stream in memory; bytes written to out (capacity cap), -1 when the stream is
+ * refused (the loader then uses serial zlib), -2 when out is too small */
+int64_t mmqh_inflate_parallel(const void* in, int64_t n, int threads, void* out, int64_t cap) {
+  mmq::ipar::Bytes b;
+  if (!mmq::ipar::inflate_parallel((const uint8_t*)in, (size_t)n, threads, b)) return -1;
+  if ((int64_t)b.size() > cap) return -2;
+  memcpy(out, b.data(), b.size());
+  return (int64_t)b.size();
+}
 
 int64_t mmqh_dim(const mmqh_hits* H, int which) {
   switch (which) {

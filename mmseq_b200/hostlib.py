@@ -30,6 +30,8 @@ def lib():
         L.mmqh_load.argtypes = [C.c_char_p, i32, C.c_char_p, i32]
         L.mmqh_from_records.restype = vp
         L.mmqh_from_records.argtypes = [i64, vp, i64, vp, vp, vp, i32, C.c_char_p, i32]
+        L.mmqh_inflate_parallel.restype = i64
+        L.mmqh_inflate_parallel.argtypes = [vp, i64, i32, vp, i64]
         L.mmqh_free.restype = None
         L.mmqh_free.argtypes = [vp]
         L.mmqh_dim.restype = i64
@@ -84,6 +86,17 @@ class Hits:
             self.ident_ptr = _arr(L.mmqh_ident_ptr(handle), self.I + 1, np.int64)
             self.ident_members = _arr(L.mmqh_ident_members(handle), int(self.ident_ptr[-1]), np.int32)
         L.mmqh_free(handle)
+
+
+def inflate_parallel(data, threads, cap):
+    """inflate_par.h (the loader's multi-threaded inflate) on a zlib stream; None when it refuses the stream."""
+    buf = np.frombuffer(data, np.uint8)
+    out = np.empty(cap, np.uint8)
+    n = lib().mmqh_inflate_parallel(buf.ctypes.data_as(C.c_void_p), len(buf), threads, out.ctypes.data_as(C.c_void_p), cap)
+    if n == -1:
+        return None
+    assert n >= 0, "output buffer too small"
+    return out[:n].tobytes()
 
 
 def load_hits(path, layout=LAYOUT_COLLAPSED):

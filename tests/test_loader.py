@@ -201,3 +201,129 @@ def test_truncated_and_degenerate_files_are_refused(tmp_path):
     open(txt, "w").write(body)
     with pytest.raises(RuntimeError, match="without any mapping transcripts"):
         hostlib.load_hits(txt)
+
+
+# ---- the loader on all host threads: parallel inflate (inflate_par.h) and parallel class building ------------------
+
+def _streams():
+    import zlib
+    rng = np.random.default_rng(11)
+    for it in range(60):
+        n = int(2 ** rng.uniform(8, 23))
+        kind = it % 5
+        if kind == 0:
+            raw = rng.integers(0, 256, n, dtype=np.uint8).tobytes()                      # incompressible: stored blocks
+        elif kind == 1:
+            raw = bytes(rng.choice(np.frombuffer(b"ACGT\n>r", np.uint8), n))
+        elif kind == 2:
+            raw = (np.arange(n) // 3 % 251).astype(np.uint8).tobytes()                   # long matches
+        elif kind == 3:
+            raw = np.where(rng.random(n) < 0.9, 0, rng.integers(0, 256, n)).astype(np.uint8).tobytes()
+        else:
+            raw = b"".join(b"\n\x02%d\n\x00" % i + int(i % 977).to_bytes(4, "little") * (1 + i % 5) for i in range(n // 16))
+        level = [1, 1, 6, 9, 0][int(rng.integers(5))]
+        strategy = [zlib.Z_DEFAULT_STRATEGY, zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE][int(rng.integers(5))]
+        c = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+        yield raw, c.compress(raw) + c.flush(), int(rng.integers(1, 9))
+
+
+def test_parallel_inflate_equals_zlib_on_every_block_type():
+    refused = 0
+    for raw, z, threads in _streams():
+        out = hostlib.inflate_parallel(z, threads, len(raw) + 16)
+        if out is None:
+            refused += 1          # allowed (the loader then falls back to zlib), but must be rare
+            continue
+        assert out == raw
+    assert refused <= 3
+
+
+def test_parallel_inflate_refuses_damaged_streams():
+    import zlib
+    rng = np.random.default_rng(5)
+    raw = bytes(rng.choice(np.frombuffer(b"ACGT\n>r0123", np.uint8), 3 << 20))
+    z = bytearray(zlib.compress(raw, 1))
+    for it in range(24):
+        zz = bytearray(z)
+        if it % 2:
+            del zz[len(zz) * (1 + it % 7) // 9:]                  # truncated
+        else:
+            zz[len(zz) // 3 + it * 1013] ^= 1 << (it % 8)         # one flipped bit
+        out = hostlib.inflate_parallel(bytes(zz), 4, len(raw) + 16)
+        assert out is None or out == raw                           # never wrong data
+
+
+class _Recs:
+    """A synthetic sample whose records repeat transcripts (doublehits, src/mmseq.cpp:404-409) and include very long ones."""
+    def __init__(self, s, seed=3):
+        rng = np.random.default_rng(seed)
+        self.__dict__.update({k: getattr(s, k) for k in ("T", "G", "efflen", "truelen", "gene_ptr")})
+        self._s = s
+        ptr, tid = [0], []
+        for r in range(s.N):
+            ids = list(s.frag_tid[s.frag_ptr[r]:s.frag_ptr[r + 1]])
+            u = rng.random()
+            if u < 0.05:
+                ids = ids + ids[:1]                                # a repeated transcript
+            elif u < 0.06:
+                ids = list(rng.integers(0, s.T, 50)) + ids * 3     # a long record with repeats
+            elif u < 0.10:
+                ids = ids[::-1]                                    # same set, other order
+            tid += ids
+            ptr.append(len(tid))
+        self.frag_ptr = np.array(ptr, np.int64)
+        self.frag_tid = np.array(tid, np.int32)
+        self.N = s.N
+    def transcript_name(self, t): return self._s.transcript_name(t)
+    def gene_name(self, g): return self._s.gene_name(g)
+
+
+def _load_env(path, layout, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return hostlib.load_hits(path, layout)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+LAYOUTS = [hostlib.LAYOUT_COLLAPSED, hostlib.LAYOUT_PER_FRAGMENT, hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH,
+           hostlib.LAYOUT_COLLAPSED | hostlib.LAYOUT_HEADER_ORDER_COLUMNS]
+
+
+def _equal(a, b):
+    assert (a.n, a.m, a.N, a.nnz) == (b.n, b.m, b.N, b.nnz)
+    for f in ("row_ptr", "col", "col2hdr", "hdr2col", "doublehits"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert (a.k is None and b.k is None) or np.array_equal(a.k, b.k)
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_parallel_loader_equals_the_sequential_walk(tmp_path, small_synth, layout):
+    """Whole file inflated in memory + parallel builders (first-appearance numbering reconstructed afterwards) against the
+    record-by-record path: identical classes, numbering, counts, doublehits."""
+    recs = _Recs(small_synth)
+    path = str(tmp_path / "dups.hits")
+    synth.write_hits_binary(recs, path)
+    serial = _load_env(path, layout, MMQ_LOADER_SERIAL_INFLATE=1)
+    for builders, workers in ((1, 1), (3, 2), (5, 3)):
+        par = _load_env(path, layout, MMQ_LOADER_PAR_MIN_BYTES=0, MMQ_LOADER_BUILDERS=builders, MMQ_LOADER_THREADS=workers)
+        _equal(par, serial)
+    if layout == hostlib.LAYOUT_COLLAPSED:
+        _same(serial, orc.build_classes(orc.HitsFile(path)))      # and both equal the restated reference reader
+
+
+def test_in_memory_records_parallel_equals_sequential(small_synth):
+    recs = _Recs(small_synth, seed=8)
+    for layout in LAYOUTS + [hostlib.LAYOUT_COLLAPSED | hostlib.LAYOUT_IDENTITY_COLUMNS]:
+        os.environ["MMQ_LOADER_SERIAL_RECORDS"] = "1"
+        try:
+            a = hostlib.from_records(recs.T, recs.efflen, recs.frag_ptr, recs.frag_tid, layout=layout)
+        finally:
+            os.environ.pop("MMQ_LOADER_SERIAL_RECORDS")
+        b = hostlib.from_records(recs.T, recs.efflen, recs.frag_ptr, recs.frag_tid, layout=layout)
+        _equal(a, b)
