@@ -79,7 +79,9 @@ struct BitReader {
  * offset << 8 | 0x80 | extra index bits.  0 = no code. */
 struct Huff {
   static constexpr int PB = 10;
-  std::vector<uint32_t> t;
+  /* primary table + second-level tables: at most 286 symbols with codes longer than PB, each opening at most 2^5 slots */
+  uint32_t t[(1 << PB) + 288 * 32];
+  int used = 0;
   int maxlen = 0;
   /* returns false unless the lengths form a complete prefix code (what zlib emits) */
   bool build(const uint8_t* len, int nsym) {
@@ -93,10 +95,12 @@ struct Huff {
     uint32_t code = 0, first[16];
     for (int l = 1; l <= 15; ++l) { code = (code + (uint32_t)count[l - 1]) << 1; first[l] = code; }
     /* second-level tables: one per distinct PB-bit prefix of the codes longer than PB */
-    t.assign((size_t)1 << PB, 0);
+    memset(t, 0, sizeof(uint32_t) << PB);
+    used = 1 << PB;
     if (maxlen > PB) {
       /* how many index bits each prefix needs: the longest code under it */
-      std::vector<uint8_t> sub((size_t)1 << PB, 0);
+      uint8_t sub[1 << PB];
+      memset(sub, 0, sizeof sub);
       uint32_t nxt[16];
       memcpy(nxt, first, sizeof nxt);
       for (int i = 0; i < nsym; ++i) {
@@ -108,8 +112,10 @@ struct Huff {
       }
       for (uint32_t pre = 0; pre < (1u << PB); ++pre)
         if (sub[pre]) {
-          t[pre] = ((uint32_t)t.size() << 8) | 0x80u | sub[pre];
-          t.resize(t.size() + ((size_t)1 << sub[pre]), 0);
+          if (used + (1 << sub[pre]) > (int)(sizeof t / sizeof t[0])) return false;
+          t[pre] = ((uint32_t)used << 8) | 0x80u | sub[pre];
+          memset(t + used, 0, sizeof(uint32_t) << sub[pre]);
+          used += 1 << sub[pre];
         }
     }
     for (int i = 0; i < nsym; ++i) {
@@ -147,6 +153,27 @@ struct Huff {
     br.drop((int)(e & 0xff));
     return (int)(e >> 8);
   }
+};
+
+/* growable array of 16-bit symbols without value initialisation (a std::vector would zero every page it grows into) */
+struct SymBuf {
+  uint16_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  SymBuf() {}
+  SymBuf(const SymBuf&) = delete;
+  SymBuf& operator=(const SymBuf&) = delete;
+  ~SymBuf() { free(p); }
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    uint16_t* q = (uint16_t*)realloc(p, want * sizeof(uint16_t));
+    if (!q) return false;
+    p = q; cap = want;
+    return true;
+  }
+  void release() { free(p); p = nullptr; n = cap = 0; }
+  void swap(SymBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
+  size_t size() const { return n; }
+  void clear() { n = 0; }
 };
 
 static const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
@@ -205,7 +232,7 @@ struct FixedTables {
  * precedes the chunk; has_window = false: references before the start are an error).  Stops at a block boundary equal to
  * stop_bit (returns 1), after the final block (returns 2; *end_bit = the bit after it), or returns 0 on any error / when the
  * decoding runs past stop_bit.  max_blocks > 0 limits the number of blocks (used by the block finder; returns 3 when hit). */
-inline int decode_chunk_impl(const uint8_t* in, size_t n_in, uint64_t start, uint64_t stop_bit, bool has_window, std::vector<uint16_t>& out,
+inline int decode_chunk_impl(const uint8_t* in, size_t n_in, uint64_t start, uint64_t stop_bit, bool has_window, SymBuf& out,
                              uint64_t* end_bit, int max_blocks) {
   static const FixedTables fixed;
   BitReader br(in, n_in, start);
@@ -227,9 +254,9 @@ inline int decode_chunk_impl(const uint8_t* in, size_t n_in, uint64_t start, uin
       if (br.over || (len ^ 0xffffu) != nlen) return 0;
       size_t at = (size_t)(br.pos >> 3);
       if (at + len > n_in) return 0;
-      const size_t o = out.size();
-      out.resize(o + len);
-      for (uint32_t i = 0; i < len; ++i) out[o + i] = in[at + i];
+      if (!out.reserve(out.n + len)) return 0;
+      for (uint32_t i = 0; i < len; ++i) out.p[out.n + i] = in[at + i];
+      out.n += len;
       br = BitReader(in, n_in, br.pos + (uint64_t)len * 8);
     } else {
       const Huff *L, *D;
@@ -238,13 +265,28 @@ inline int decode_chunk_impl(const uint8_t* in, size_t n_in, uint64_t start, uin
         if (!read_dynamic_header(br, lit, dist)) return 0;
         L = &lit; D = &dist;
       }
+      size_t o = out.n;
+      if (!out.reserve(o + 600)) return 0;
+      uint16_t* q = out.p;
+      size_t cap = out.cap;
       for (;;) {
+        if (o + 600 > cap) { /* room for two literals and one match of 258 */
+          if (!out.reserve(std::max<size_t>(cap * 2, o + (1 << 20)))) return 0;
+          cap = out.cap;
+          q = out.p;
+        }
         br.need(48);
         int s = L->decode(br);
         if (s < 256) {
           if (s < 0) return 0;
-          out.push_back((uint16_t)s);
-          continue;
+          q[o++] = (uint16_t)s;
+          s = L->decode(br); /* 48 bits hold three codes: a second symbol without another refill */
+          if (s < 256) {
+            if (s < 0) return 0;
+            q[o++] = (uint16_t)s;
+            continue;
+          }
+          br.need(48);
         }
         if (s == 256) break;
         s -= 257;
@@ -255,15 +297,20 @@ inline int decode_chunk_impl(const uint8_t* in, size_t n_in, uint64_t start, uin
         if (ds < 0 || ds >= 30) return 0;
         const int64_t d = DIST_BASE[ds] + (int64_t)br.get(DIST_EXTRA[ds]);
         if (br.over) return 0;
-        const int64_t o = (int64_t)out.size();
-        if (d > o && (!has_window || d - o > 32768)) return 0;
-        out.resize((size_t)(o + len));
-        uint16_t* q = out.data();
-        for (int j = 0; j < len; ++j) {
-          const int64_t src = o + j - d;
-          q[o + j] = src >= 0 ? q[src] : (uint16_t)(256 + 32768 + src);
+        const int64_t src0 = (int64_t)o - d;
+        if (src0 >= 0) {
+          if (d >= len) memcpy(q + o, q + src0, (size_t)len * 2);
+          else for (int j = 0; j < len; ++j) q[o + j] = q[src0 + j];
+        } else {
+          if (!has_window || -src0 > 32768) return 0;
+          for (int j = 0; j < len; ++j) {
+            const int64_t src = src0 + j;
+            q[o + j] = src >= 0 ? q[src] : (uint16_t)(256 + 32768 + src);
+          }
         }
+        o += (size_t)len;
       }
+      out.n = o;
       if (br.over) return 0;
     }
     ++blocks;
@@ -271,11 +318,11 @@ inline int decode_chunk_impl(const uint8_t* in, size_t n_in, uint64_t start, uin
   }
 }
 
-inline int decode_chunk(const uint8_t* in, size_t n_in, uint64_t start, uint64_t stop_bit, bool has_window, std::vector<uint16_t>& out,
+inline int decode_chunk(const uint8_t* in, size_t n_in, uint64_t start, uint64_t stop_bit, bool has_window, SymBuf& out,
                         uint64_t* end_bit, int max_blocks = 0) {
   /* the vector's header is updated for every symbol: keep it on this thread's stack, not next to the other chunks' headers
    * (measured: eight threads appending to neighbouring std::vector objects ran no faster than one) */
-  std::vector<uint16_t> local;
+  SymBuf local;
   local.swap(out);
   uint64_t eb = 0;
   const int rc = decode_chunk_impl(in, n_in, start, stop_bit, has_window, local, &eb, max_blocks);
@@ -287,7 +334,7 @@ inline int decode_chunk(const uint8_t* in, size_t n_in, uint64_t start, uint64_t
 /* first bit offset >= from (and < limit) that starts a verified dynamic block, or UINT64_MAX */
 inline uint64_t find_block(const uint8_t* in, size_t n_in, uint64_t from, uint64_t limit) {
   Huff lit, dist;
-  std::vector<uint16_t> scratch;
+  SymBuf scratch;
   for (uint64_t b = from; b < limit; ++b) {
     const size_t byte = (size_t)(b >> 3);
     if (byte + 4 > n_in) break;
@@ -355,7 +402,7 @@ inline bool inflate_parallel(const uint8_t* in, size_t n_in, int threads, Bytes&
     if (start[(size_t)c] != UINT64_MAX) st.push_back(start[(size_t)c]);
   nch = (int)st.size();
   st.push_back(UINT64_MAX);
-  std::vector<std::vector<uint16_t>> sym((size_t)nch);
+  std::vector<SymBuf> sym((size_t)nch);
   std::vector<int> rc((size_t)nch, 0);
   std::vector<uint64_t> endb((size_t)nch, 0);
   {
@@ -363,7 +410,7 @@ inline bool inflate_parallel(const uint8_t* in, size_t n_in, int threads, Bytes&
     auto work = [&] {
       for (int c; (c = nx.fetch_add(1)) < nch;) {
         const size_t span = (size_t)(((c + 1 < nch ? st[(size_t)c + 1] : (uint64_t)nd * 8) - st[(size_t)c]) >> 3);
-        sym[(size_t)c].reserve(span * 3 + 65536);
+        if (!sym[(size_t)c].reserve(span * 3 + 65536)) { rc[(size_t)c] = 0; continue; }
         rc[(size_t)c] = decode_chunk(d, nd, st[(size_t)c], st[(size_t)c + 1], c > 0, sym[(size_t)c], &endb[(size_t)c]);
       }
     };
@@ -383,7 +430,7 @@ inline bool inflate_parallel(const uint8_t* in, size_t n_in, int threads, Bytes&
   for (int c = 0; c < nch; ++c) off[(size_t)c + 1] = off[(size_t)c] + sym[(size_t)c].size();
   std::vector<std::vector<uint8_t>> win((size_t)nch);
   for (int c = 1; c < nch; ++c) {
-    const std::vector<uint16_t>& s = sym[(size_t)c - 1];
+    const SymBuf& s = sym[(size_t)c - 1];
     const std::vector<uint8_t>& pw = win[(size_t)c - 1];
     std::vector<uint8_t>& w = win[(size_t)c];
     w.assign(32768, 0);
@@ -391,7 +438,7 @@ inline bool inflate_parallel(const uint8_t* in, size_t n_in, int threads, Bytes&
     for (size_t i = 0; i < 32768; ++i) {
       /* byte 32768 - 1 - i positions back from the end of chunk c - 1 */
       const int64_t p = (int64_t)ns - 32768 + (int64_t)i;
-      if (p >= 0) { const uint16_t v = s[(size_t)p]; w[i] = v < 256 ? (uint8_t)v : (pw.empty() ? 0 : pw[v - 256]); }
+      if (p >= 0) { const uint16_t v = s.p[(size_t)p]; w[i] = v < 256 ? (uint8_t)v : (pw.empty() ? 0 : pw[v - 256]); }
       else if (!pw.empty()) w[i] = pw[(size_t)(32768 + p)];
     }
   }
@@ -401,12 +448,12 @@ inline bool inflate_parallel(const uint8_t* in, size_t n_in, int threads, Bytes&
     std::atomic<int> nx(0);
     auto work = [&] {
       for (int c; (c = nx.fetch_add(1)) < nch;) {
-        std::vector<uint16_t>& s = sym[(size_t)c];
+        SymBuf& s = sym[(size_t)c];
         uint8_t* o = out.data() + off[(size_t)c];
         const uint8_t* w = win[(size_t)c].empty() ? nullptr : win[(size_t)c].data();
         const size_t ns = s.size();
-        for (size_t i = 0; i < ns; ++i) { const uint16_t v = s[i]; o[i] = v < 256 ? (uint8_t)v : w[v - 256]; }
-        std::vector<uint16_t>().swap(s);
+        for (size_t i = 0; i < ns; ++i) { const uint16_t v = s.p[i]; o[i] = v < 256 ? (uint8_t)v : w[v - 256]; }
+        s.release();
         uint32_t a = 1;
         for (size_t i = 0; i < ns; i += (size_t)1 << 30) a = (uint32_t)adler32(a, o + i, (uInt)std::min<size_t>((size_t)1 << 30, ns - i));
         adl[(size_t)c] = a;
