@@ -3,6 +3,7 @@
  * README.md:388-403. */
 #include "hits_loader.h"
 #include "inflate_par.h"
+#include "fmt_g6.h"
 
 #include <zlib.h>
 
@@ -1162,6 +1163,13 @@ mmqh_hits* mmqh_from_records(int64_t T, const double* efflen, int64_t N, const i
 }
 
 void mmqh_free(mmqh_hits* H) { delete H; }
+
+/* test support: fmt_g6.h on an array of doubles, the texts separated by single spaces; returns the bytes written */
+int64_t mmqh_fmt_g6(const double* v, int64_t n, char* out) {
+  char* p = out;
+  for (int64_t i = 0; i < n; ++i) { p = fmt_g6(p, v[i]); *p++ = ' '; }
+  return (int64_t)(p - out);
+}
 
 /* test support: inflate_par.h on a zlib stream in memory; bytes written to out (capacity cap), -1 when the stream is
  * refused (the loader then uses serial zlib), -2 when out is too small */

@@ -30,6 +30,8 @@ def lib():
         L.mmqh_load.argtypes = [C.c_char_p, i32, C.c_char_p, i32]
         L.mmqh_from_records.restype = vp
         L.mmqh_from_records.argtypes = [i64, vp, i64, vp, vp, vp, i32, C.c_char_p, i32]
+        L.mmqh_fmt_g6.restype = i64
+        L.mmqh_fmt_g6.argtypes = [vp, i64, vp]
         L.mmqh_inflate_parallel.restype = i64
         L.mmqh_inflate_parallel.argtypes = [vp, i64, i32, vp, i64]
         L.mmqh_free.restype = None
@@ -86,6 +88,14 @@ class Hits:
             self.ident_ptr = _arr(L.mmqh_ident_ptr(handle), self.I + 1, np.int64)
             self.ident_members = _arr(L.mmqh_ident_members(handle), int(self.ident_ptr[-1]), np.int32)
         L.mmqh_free(handle)
+
+
+def fmt_g6(values):
+    """fmt_g6.h (the host program's "%g" for trace files) on an array; list of strings."""
+    v = np.ascontiguousarray(values, np.float64)
+    out = np.empty(40 * len(v) + 8, np.uint8)
+    n = lib().mmqh_fmt_g6(v.ctypes.data_as(C.c_void_p), len(v), out.ctypes.data_as(C.c_void_p))
+    return out[:n].tobytes().decode().split()
 
 
 def inflate_parallel(data, threads, cap):

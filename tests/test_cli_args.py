@@ -53,3 +53,20 @@ def test_bad_header_message(tmp_path):
     p.write_text("@TranscriptMetaData\tA\t10\t20\n@TranscriptMetaData\tB\t10\t20\n@GeneIsoforms\tg\tA\n>r\nA\n")
     r = run(str(p), str(tmp_path / "out"))
     assert r.returncode == 1 and "does not belong to a gene in the @GeneIsoforms header entries." in r.stderr
+
+
+def test_fast_g_format_equals_printf():
+    """fmt_g6.h (the trace files' number format) gives the characters of printf's %g == operator<< at precision 6."""
+    import numpy as np
+    from mmseq_b200 import hostlib
+    rng = np.random.default_rng(3)
+    edge = [0.0, -0.0, 1.0, -1.5, 1e5, 999999.0, 999999.5, 1e6, 123456.5, 1e-4, 1e-5, 0.000099999949, 9.999995e-5, 1e22, 1e23, 1e27,
+            float("inf"), float("-inf"), 5e-324, 2.5, 0.5, 1234565.0, 1234575.0, 1e-17, 9.99999e-18, 1.0000005, 0.1, 1 / 3, 2 / 3, 1e-300, 1e300]
+    pw = np.array([m * 10.0 ** k for k in range(-40, 40) for m in (1.0, 9.999995, 9.9999949, 1.0000005, 1.234565, 0.9999995)])
+    pw = np.concatenate([pw, np.nextafter(pw, 0), np.nextafter(pw, np.inf)])
+    vals = np.concatenate([np.array(edge), pw, np.exp(rng.uniform(-45, 45, 400000)), rng.integers(0, 10 ** 8, 200000) / rng.integers(1, 10 ** 6, 200000),
+                           rng.gamma(0.1, 1.0, 200000), rng.standard_normal(50000)])
+    got = hostlib.fmt_g6(vals)
+    want = ["%g" % v for v in vals]
+    assert got == want
+    assert hostlib.fmt_g6([float("nan")])[0].lstrip("-") == "nan"
