@@ -262,6 +262,12 @@ int mmq_mean_corrs(int device, const double* R, const uint8_t* S, int64_t C, int
 int mmq_mean_corrs_dev(const double* R_dev, const uint8_t* S_dev, int64_t C, int ns, const int32_t* ts_dev, int64_t nts, double sdpenalty,
                        double* V_dev, double* W_dev, void* cuda_stream);
 
+/* Device memory given back by mmq_destroy and by the set-up steps' temporaries is kept in a per-device cache and handed
+ * out again (cudaMalloc / cudaFree of these sizes cost 1-100 ms each and made mmq_create vary between 8 ms and 2 s; a
+ * process that runs one sample after another — config 5 — now pays them once).  At most MMQ_DEVICE_CACHE_MB (environment,
+ * default 16384; 0 disables) are held per device; this call returns them to the driver (device < 0: every device). */
+int mmq_release_cache(int device);
+
 /* Kernel launches issued by this process through the library so far. */
 int64_t mmq_launch_count(void);
 /* Bring up the CUDA context of `device` (the first CUDA call of a process costs 1-2 s): a host

@@ -82,6 +82,7 @@ def _load():
         "mmq_handle_trace_cov": (i32, [vp, vp, i64, i32, vp, vp]),
         "mmq_mean_corrs": (i32, [i32, vp, vp, i64, i32, vp, i64, dbl, vp, vp]),
         "mmq_mean_corrs_dev": (i32, [vp, vp, i64, i32, vp, i64, dbl, vp, vp, vp]),
+        "mmq_release_cache": (i32, [i32]),
         "mmq_launch_count": (i64, []),
         "mmq_warmup": (i32, [i32]),
         "mmq_version": (C.c_char_p, []),
@@ -109,7 +110,7 @@ EXPORTS = [
     "mmq_loglik", "mmq_em", "mmq_gibbs", "mmq_sweep_debug", "mmq_kernel_times", "mmq_cls_stats", "mmq_rows_stats", "mmq_tune", "mmq_get_trace", "mmq_trace_len",
     "mmq_set_groups", "mmq_summarize", "mmq_get_group_trace", "mmq_prop_summaries",
     "mmq_unique_hits_sets", "mmq_sokal_batch", "mmq_prior_draws", "mmq_trace_cov", "mmq_trace_cov_workspace_bytes", "mmq_trace_cov_dev",
-    "mmq_handle_trace_cov", "mmq_mean_corrs", "mmq_mean_corrs_dev", "mmq_launch_count", "mmq_warmup", "mmq_version",
+    "mmq_handle_trace_cov", "mmq_mean_corrs", "mmq_mean_corrs_dev", "mmq_release_cache", "mmq_launch_count", "mmq_warmup", "mmq_version",
 ]
 
 
@@ -121,6 +122,10 @@ def _c(a, dtype):
     if a is None:
         return None
     return np.ascontiguousarray(a, dtype=dtype)
+
+
+def release_cache(device=-1):
+    return int(lib().mmq_release_cache(device))
 
 
 def launch_count():

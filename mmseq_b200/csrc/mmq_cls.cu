@@ -609,17 +609,18 @@ static int cls_plan_device(mmq_handle* h, const mmq_problem* p) {
   clsb_run* runs_dev = nullptr;
   void* temp = nullptr;
   auto cleanup = [&] {
+    cudaStreamSynchronize(h->stream); /* the temporaries go back to the block cache: nothing queued may still touch them */
     for (void* q : {(void*)nslots, (void*)off, (void*)keys, (void*)keys2, (void*)vals, (void*)vals2, (void*)slot_class, (void*)slot_no,
                     (void*)info, (void*)first, (void*)nch_dev, (void*)runs_dev, temp})
-      if (q) cudaFree(q);
+      if (q) mmq_cache_free(q);
   };
 #define CLSB(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { cleanup(); return mmq_cuda_fail(h, e__, #call, __FILE__, __LINE__); } } while (0)
-  CLSB(cudaMalloc(&nslots, sizeof(int32_t) * (size_t)(m + 1)));
-  CLSB(cudaMalloc(&off, sizeof(int32_t) * (size_t)(m + 1)));
-  CLSB(cudaMalloc(&info, sizeof(int) * 4));
-  CLSB(cudaMalloc(&first, sizeof(int) * MMQ_CLSB_NDP));
-  CLSB(cudaMalloc(&nch_dev, sizeof(int) * MMQ_CLSB_NDP));
-  CLSB(cudaMalloc(&runs_dev, sizeof(clsb_run) * MMQ_CLSB_NDP));
+  CLSB(mmq_cache_malloc(&nslots, sizeof(int32_t) * (size_t)(m + 1)));
+  CLSB(mmq_cache_malloc(&off, sizeof(int32_t) * (size_t)(m + 1)));
+  CLSB(mmq_cache_malloc(&info, sizeof(int) * 4));
+  CLSB(mmq_cache_malloc(&first, sizeof(int) * MMQ_CLSB_NDP));
+  CLSB(mmq_cache_malloc(&nch_dev, sizeof(int) * MMQ_CLSB_NDP));
+  CLSB(mmq_cache_malloc(&runs_dev, sizeof(clsb_run) * MMQ_CLSB_NDP));
   CLSB(cudaMemsetAsync(info, 0, sizeof(int) * 4, h->stream));
   CLSB(cudaMemsetAsync(nslots + m, 0, sizeof(int32_t), h->stream));
   if ((rc = mmq_dev_alloc(h, (void**)&h->seg_base, sizeof(int32_t) * (size_t)n))) { cleanup(); return rc; }
@@ -632,13 +633,13 @@ static int cls_plan_device(mmq_handle* h, const mmq_problem* p) {
   int host_info[4] = {0, 0, 0, 0};
   {
     void* t1 = nullptr;
-    CLSB(cudaMalloc(&t1, tb1));
+    CLSB(mmq_cache_malloc(&t1, tb1));
     cudaError_t e = cub::DeviceScan::ExclusiveSum(t1, tb1, nslots, off, (int)(m + 1), h->stream);
     int total = 0;
     if (e == cudaSuccess) e = cudaMemcpyAsync(&total, off + m, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(host_info, info, sizeof(host_info), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(t1);
+    mmq_cache_free(t1); /* the stream was synchronised just above */
     if (e != cudaSuccess) { cleanup(); return mmq_cuda_fail(h, e, "class plan scan", __FILE__, __LINE__); }
     host_info[3] = total;
   }
@@ -648,18 +649,18 @@ static int cls_plan_device(mmq_handle* h, const mmq_problem* p) {
   std::vector<clsb_run> runs(MMQ_CLSB_NDP);
   int64_t chunks = 0, packed = 0, chunks_lo = 0, chunks_gen = 0, c_chunks = 0, c_packed = 0, small_slots = 0, n_chain = 0;
   if (S > 0) {
-    CLSB(cudaMalloc(&keys, sizeof(unsigned long long) * (size_t)S));
-    CLSB(cudaMalloc(&keys2, sizeof(unsigned long long) * (size_t)S));
-    CLSB(cudaMalloc(&vals, sizeof(uint32_t) * (size_t)S));
-    CLSB(cudaMalloc(&vals2, sizeof(uint32_t) * (size_t)S));
-    CLSB(cudaMalloc(&slot_class, sizeof(uint32_t) * (size_t)S));
-    CLSB(cudaMalloc(&slot_no, (size_t)S));
+    CLSB(mmq_cache_malloc(&keys, sizeof(unsigned long long) * (size_t)S));
+    CLSB(mmq_cache_malloc(&keys2, sizeof(unsigned long long) * (size_t)S));
+    CLSB(mmq_cache_malloc(&vals, sizeof(uint32_t) * (size_t)S));
+    CLSB(mmq_cache_malloc(&vals2, sizeof(uint32_t) * (size_t)S));
+    CLSB(mmq_cache_malloc(&slot_class, sizeof(uint32_t) * (size_t)S));
+    CLSB(mmq_cache_malloc(&slot_no, (size_t)S));
     k_clsb_slots<<<grid, 256, 0, h->stream>>>(h->row_ptr, h->col, h->k, nslots, off, m, keys, slot_class, slot_no);
     g_mmq_launches.fetch_add(1);
     k_iota_u32<<<mmq_grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(vals, S);
     g_mmq_launches.fetch_add(1);
     CLSB(cub::DeviceRadixSort::SortPairs(nullptr, tb2, keys, keys2, vals, vals2, (int)S, 0, 44, h->stream));
-    CLSB(cudaMalloc(&temp, tb2));
+    CLSB(mmq_cache_malloc(&temp, tb2));
     CLSB(cub::DeviceRadixSort::SortPairs(temp, tb2, keys, keys2, vals, vals2, (int)S, 0, 44, h->stream));
     CLSB(cudaMemsetAsync(first, 0xff, sizeof(int) * MMQ_CLSB_NDP, h->stream));
     k_clsb_bounds<<<mmq_grid_for(S, 256, h->num_sms * 8), 256, 0, h->stream>>>(keys2, S, first);

@@ -17,6 +17,9 @@
 
 #include <algorithm>
 #include <chrono>
+#include <map>
+#include <mutex>
+#include <unordered_map>
 #include <cstdio>
 #include <cstring>
 
@@ -40,6 +43,66 @@ int mmq_cuda_fail(mmq_handle* h, cudaError_t e, const char* what, const char* fi
   return mmq_fail(h, MMQ_ERR_CUDA, buf);
 }
 
+/* ---- the device block cache (mmq_internal.h) ---- */
+namespace {
+struct dev_cache {
+  std::mutex mu;
+  std::multimap<size_t, void*> free_blocks;       /* by size */
+  std::unordered_map<void*, size_t> size_of;      /* every block handed out or cached */
+  size_t cached = 0;
+};
+dev_cache g_cache[16];
+size_t cache_limit() {
+  static const size_t lim = [] { const char* e = getenv("MMQ_DEVICE_CACHE_MB"); return (size_t)(e ? atoll(e) : 16384) << 20; }();
+  return lim;
+}
+void cache_drop_all(dev_cache& c) { /* c.mu held */
+  for (auto& kv : c.free_blocks) { cudaFree(kv.second); c.size_of.erase(kv.second); }
+  c.free_blocks.clear();
+  c.cached = 0;
+}
+}  // namespace
+
+cudaError_t mmq_cache_malloc_raw(void** p, size_t bytes) {
+  *p = nullptr;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (bytes == 0) bytes = 16;
+  /* small blocks in 512-byte steps, large ones in 2 MB steps (the driver's own granularity): more hits */
+  const size_t want = bytes < ((size_t)1 << 20) ? (bytes + 511) & ~(size_t)511 : (bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+  dev_cache& c = g_cache[dev & 15];
+  std::lock_guard<std::mutex> lk(c.mu);
+  auto it = c.free_blocks.lower_bound(want);
+  if (it != c.free_blocks.end() && it->first <= want + want / 4 + ((size_t)4 << 20)) { /* close enough in size: no big waste */
+    *p = it->second;
+    c.cached -= it->first;
+    c.free_blocks.erase(it);
+    return cudaSuccess;
+  }
+  e = cudaMalloc(p, want);
+  if (e != cudaSuccess && !c.free_blocks.empty()) { /* out of memory with blocks parked here: give them back and retry */
+    cudaGetLastError();
+    cache_drop_all(c);
+    e = cudaMalloc(p, want);
+  }
+  if (e == cudaSuccess) c.size_of[*p] = want;
+  return e;
+}
+
+void mmq_cache_free(void* p) {
+  if (!p) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  dev_cache& c = g_cache[dev & 15];
+  std::lock_guard<std::mutex> lk(c.mu);
+  auto it = c.size_of.find(p);
+  if (it == c.size_of.end()) { cudaFree(p); return; } /* not ours (or another device's): plain free */
+  if (c.cached + it->second > cache_limit()) { cudaFree(p); c.size_of.erase(it); return; }
+  c.free_blocks.emplace(it->second, p);
+  c.cached += it->second;
+}
+
 int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes) {
   *p = nullptr;
   if (bytes == 0) bytes = 16;
@@ -50,7 +113,7 @@ int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes) {
     h->bytes += (int64_t)bytes;
     return MMQ_OK;
   }
-  cudaError_t e = cudaMalloc(p, bytes);
+  cudaError_t e = mmq_cache_malloc_raw(p, bytes);
   if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaMalloc", __FILE__, __LINE__);
   h->bytes += (int64_t)bytes;
   h->allocs.push_back(*p);
@@ -62,7 +125,8 @@ void mmq_dev_free(mmq_handle* h, void* p) {
   if (h->arena && (char*)p >= h->arena && (char*)p < h->arena + h->arena_cap) return; /* released with the arena */
   auto it = std::find(h->allocs.begin(), h->allocs.end(), p);
   if (it != h->allocs.end()) h->allocs.erase(it);
-  cudaFree(p);
+  if (h->stream) cudaStreamSynchronize(h->stream); /* nothing queued may still touch the block when it is handed out again */
+  mmq_cache_free(p);
 }
 
 /* ------------------------------------------------------- device utilities */
@@ -846,6 +910,22 @@ int mmq_allreduce(mmq_handle* h, void* buf, size_t count, int is_double) {
 extern "C" {
 
 const char* mmq_version(void) { return "mmseq-b200 0.1 (hot path of eturro/mmseq 1.0.11)"; }
+int mmq_release_cache(int device) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess) return MMQ_ERR_CUDA;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < ndev && d < 16; ++d) {
+    if (device >= 0 && d != device) continue;
+    cudaSetDevice(d);
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(g_cache[d].mu);
+    cache_drop_all(g_cache[d]);
+  }
+  cudaSetDevice(cur);
+  return MMQ_OK;
+}
+
 int64_t mmq_launch_count(void) { return (int64_t)g_mmq_launches.load(); }
 
 const char* mmq_last_error(const mmq_handle* h) { return h ? h->err.c_str() : g_mmq_create_err.c_str(); }
@@ -905,8 +985,8 @@ static int build_transpose(mmq_handle* h) {
   uint32_t* iota = nullptr;
   void* temp = nullptr;
   size_t temp_bytes = 0;
-  MMQ_CUDA(h, cudaMalloc(&keys_out, sizeof(int32_t) * (size_t)nnz));
-  MMQ_CUDA(h, cudaMalloc(&iota, sizeof(uint32_t) * (size_t)nnz));
+  MMQ_CUDA(h, mmq_cache_malloc(&keys_out, sizeof(int32_t) * (size_t)nnz));
+  MMQ_CUDA(h, mmq_cache_malloc(&iota, sizeof(uint32_t) * (size_t)nnz));
   const int grid = mmq_grid_for(nnz, 256, h->num_sms * 8);
   k_iota<<<grid, 256, 0, h->stream>>>(iota, nnz);
   MMQ_LAUNCHED(h);
@@ -914,16 +994,16 @@ static int build_transpose(mmq_handle* h) {
   while (end_bit < 31 && ((int64_t)1 << end_bit) < n) ++end_bit;
   /* stable LSD radix sort of (column, position): positions stay ascending within a column */
   MMQ_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, h->col, keys_out, iota, h->perm, nnz, 0, end_bit, h->stream));
-  MMQ_CUDA(h, cudaMalloc(&temp, temp_bytes));
+  MMQ_CUDA(h, mmq_cache_malloc(&temp, temp_bytes));
   MMQ_CUDA(h, cub::DeviceRadixSort::SortPairs(temp, temp_bytes, h->col, keys_out, iota, h->perm, nnz, 0, end_bit, h->stream));
   k_tptr<<<grid, 256, 0, h->stream>>>(keys_out, nnz, n, h->tptr);
   MMQ_LAUNCHED(h);
   k_trow<<<grid, 256, 0, h->stream>>>(h->perm, h->row_ptr, m, nnz, h->trow);
   MMQ_LAUNCHED(h);
   MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
-  cudaFree(keys_out);
-  cudaFree(iota);
-  cudaFree(temp);
+  mmq_cache_free(keys_out);
+  mmq_cache_free(iota);
+  mmq_cache_free(temp);
   return MMQ_OK;
 }
 
@@ -986,7 +1066,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
     else if (!h->has_w) want += 4 * (nnz + nnz / 8) + 6 * (m + m / 4) + 4 * n + (1 << 16);     /* the class plan's (an estimate: what does not fit is allocated separately) */
     want += 64 * 256;                                                                      /* alignment of the pieces */
     void* a = nullptr;
-    if (cudaMalloc(&a, want) == cudaSuccess) { h->arena = (char*)a; h->arena_cap = want; }
+    if (mmq_cache_malloc_raw(&a, want) == cudaSuccess) { h->arena = (char*)a; h->arena_cap = want; }
     else cudaGetLastError(); /* fall back to separate allocations */
   }
   CREATE_TRY(upload(h, (void**)&h->row_ptr, p->row_ptr, sizeof(int64_t) * (size_t)(p->m + 1)));
@@ -1056,8 +1136,9 @@ void mmq_destroy(mmq_handle* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_join3) cudaEventDestroy(h->ev_join3);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
-  for (void* p : h->allocs) cudaFree(p);
-  if (h->arena) cudaFree(h->arena);
+  cudaDeviceSynchronize(); /* the blocks go back to the cache: nothing may still be running on them */
+  for (void* p : h->allocs) mmq_cache_free(p);
+  if (h->arena) mmq_cache_free(h->arena);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -1150,8 +1231,11 @@ static int p2p_alloc(mmq_handle* h) {
   MMQ_CUDA(h, cudaSetDevice(h->device));
   MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
   const size_t bytes = p2p_off_mu(h) + sizeof(double) * (size_t)(h->n + 1);
-  int rc = mmq_dev_alloc(h, &h->p2p_buf, bytes);
-  if (rc) return rc;
+  /* a plain allocation, not one from the block cache: the block is exported to other processes (cudaIpcGetMemHandle), it
+   * must not be handed out again under a mapping a peer still holds; mmq_cache_free() frees what it does not know */
+  MMQ_CUDA(h, cudaMalloc(&h->p2p_buf, bytes));
+  h->allocs.push_back(h->p2p_buf);
+  h->bytes += (int64_t)bytes;
   MMQ_CUDA(h, cudaMemsetAsync(h->p2p_buf, 0, bytes, h->stream));
   MMQ_CUDA(h, cudaStreamSynchronize(h->stream));
   return MMQ_OK;

@@ -476,10 +476,11 @@ int mmq_trace_cov(int device, const double* M, int L, int64_t C, int nsplit, dou
   cudaStream_t st = nullptr;
   const size_t mb = (size_t)L * (size_t)C * 8, rb = (size_t)C * (size_t)C * 8;
   int rc = MMQ_OK;
-  auto cleanup = [&] {
-    if (dM) cudaFree(dM);
-    if (dR) cudaFree(dR);
-    if (ws) cudaFree(ws);
+  auto cleanup = [&] { /* the blocks go back to the device block cache (mmq_internal.h): per-sample calls pay cudaMalloc once */
+    if (st) cudaStreamSynchronize(st);
+    mmq_cache_free(dM);
+    mmq_cache_free(dR);
+    mmq_cache_free(ws);
     if (st) cudaStreamDestroy(st);
   };
 #define COV_TRY(call)                                                                                    \
@@ -491,9 +492,9 @@ int mmq_trace_cov(int device, const double* M, int L, int64_t C, int nsplit, dou
     }                                                                                                    \
   } while (0)
   COV_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  COV_TRY(cudaMalloc(&dM, mb));
-  COV_TRY(cudaMalloc(&dR, rb));
-  COV_TRY(cudaMalloc(&ws, cov_ws_bytes(L, C, nsplit)));
+  COV_TRY(mmq_cache_malloc(&dM, mb));
+  COV_TRY(mmq_cache_malloc(&dR, rb));
+  COV_TRY(mmq_cache_malloc(&ws, cov_ws_bytes(L, C, nsplit)));
   COV_TRY(cudaMemcpyAsync(dM, M, mb, cudaMemcpyHostToDevice, st));
   rc = cov_run(dM, nullptr, L, 1, L, C, nsplit, dR, ws, st);
   if (rc == MMQ_OK) {
@@ -528,9 +529,10 @@ int mmq_handle_trace_cov(mmq_handle* h, const int32_t* features, int64_t C, int 
   double* dR = R_dev_out;
   const size_t rb = (size_t)C * (size_t)C * 8;
   auto cleanup = [&] {
-    if (off_dev) cudaFree(off_dev);
-    if (ws) cudaFree(ws);
-    if (dR && dR != R_dev_out) cudaFree(dR);
+    cudaStreamSynchronize(h->stream);
+    mmq_cache_free(off_dev);
+    mmq_cache_free(ws);
+    if (dR != R_dev_out) mmq_cache_free(dR);
   };
 #define COVH_TRY(call)                                                          \
   do {                                                                          \
@@ -540,9 +542,9 @@ int mmq_handle_trace_cov(mmq_handle* h, const int32_t* features, int64_t C, int 
       return mmq_cuda_fail(h, e__, #call, __FILE__, __LINE__);                  \
     }                                                                           \
   } while (0)
-  COVH_TRY(cudaMalloc((void**)&off_dev, (size_t)C * 8));
-  COVH_TRY(cudaMalloc(&ws, cov_ws_bytes(L, C, nsplit)));
-  if (!dR) COVH_TRY(cudaMalloc((void**)&dR, rb));
+  COVH_TRY(mmq_cache_malloc(&off_dev, (size_t)C * 8));
+  COVH_TRY(mmq_cache_malloc(&ws, cov_ws_bytes(L, C, nsplit)));
+  if (!dR) COVH_TRY(mmq_cache_malloc(&dR, rb));
   COVH_TRY(cudaMemcpyAsync(off_dev, off.data(), (size_t)C * 8, cudaMemcpyHostToDevice, h->stream));
   const int rc = cov_run(h->trace, off_dev, 0, 1, L, C, nsplit, dR, ws, h->stream);
   if (rc != MMQ_OK) {
@@ -582,17 +584,18 @@ int mmq_mean_corrs(int device, const double* R, const uint8_t* S, int64_t C, int
   uint8_t* dS = nullptr;
   int32_t* dts = nullptr;
   auto cleanup = [&] {
-    cudaFree(dR);
-    cudaFree(dV);
-    cudaFree(dW);
-    cudaFree(dS);
-    cudaFree(dts);
+    cudaDeviceSynchronize();
+    mmq_cache_free(dR);
+    mmq_cache_free(dV);
+    mmq_cache_free(dW);
+    mmq_cache_free(dS);
+    mmq_cache_free(dts);
   };
-  COV_TRY(cudaMalloc((void**)&dR, cc * (size_t)ns));
-  COV_TRY(cudaMalloc((void**)&dV, cc));
-  COV_TRY(cudaMalloc((void**)&dW, cc));
-  COV_TRY(cudaMalloc((void**)&dS, (size_t)C * (size_t)ns));
-  COV_TRY(cudaMalloc((void**)&dts, (size_t)(nts > 0 ? nts : 1) * 4));
+  COV_TRY(mmq_cache_malloc(&dR, cc * (size_t)ns));
+  COV_TRY(mmq_cache_malloc(&dV, cc));
+  COV_TRY(mmq_cache_malloc(&dW, cc));
+  COV_TRY(mmq_cache_malloc(&dS, (size_t)C * (size_t)ns));
+  COV_TRY(mmq_cache_malloc(&dts, (size_t)(nts > 0 ? nts : 1) * 4));
   COV_TRY(cudaMemcpy(dR, R, cc * (size_t)ns, cudaMemcpyHostToDevice));
   COV_TRY(cudaMemcpy(dV, V, cc, cudaMemcpyHostToDevice));
   COV_TRY(cudaMemcpy(dW, W, cc, cudaMemcpyHostToDevice));

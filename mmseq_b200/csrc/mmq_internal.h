@@ -184,6 +184,14 @@ extern thread_local std::string g_mmq_create_err;
 
 int mmq_fail(mmq_handle* h, int code, const std::string& msg);
 int mmq_cuda_fail(mmq_handle* h, cudaError_t e, const char* what, const char* file, int line);
+/* Device blocks through a process-wide cache (per device, mmq_core.cu): cudaMalloc / cudaFree cost 1-100 ms each at these
+ * sizes and vary wildly from call to call (measured: the class plan's dozen temporaries made mmq_create take anywhere from 8
+ * to 1900 ms), so blocks that are given back are kept and handed out again.  mmq_cache_free: the caller guarantees that no
+ * queued GPU work still touches the block (synchronise the stream first).  mmq_release_cache (mmq.h) returns them to the driver. */
+cudaError_t mmq_cache_malloc_raw(void** p, size_t bytes);
+void mmq_cache_free(void* p);
+template <class T>
+static inline cudaError_t mmq_cache_malloc(T** p, size_t bytes) { return mmq_cache_malloc_raw((void**)p, bytes); }
 int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes);
 void mmq_dev_free(mmq_handle* h, void* p);
 int mmq_allreduce(mmq_handle* h, void* buf, size_t count, int is_double);
