@@ -115,6 +115,10 @@ int mmq_dev_alloc(mmq_handle* h, void** p, size_t bytes) {
   }
   cudaError_t e = mmq_cache_malloc_raw(p, bytes);
   if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaMalloc", __FILE__, __LINE__);
+  /* a recycled block holds what its last user left: every handle starts from zeroed memory, whatever ran before it in
+   * the process (padding slots of the plans are read, if never used) */
+  e = cudaMemsetAsync(*p, 0, bytes, h->stream);
+  if (e != cudaSuccess) return mmq_cuda_fail(h, e, "cudaMemsetAsync", __FILE__, __LINE__);
   h->bytes += (int64_t)bytes;
   h->allocs.push_back(*p);
   return MMQ_OK;
@@ -918,8 +922,7 @@ int mmq_release_cache(int device) {
   for (int d = 0; d < ndev && d < 16; ++d) {
     if (device >= 0 && d != device) continue;
     cudaSetDevice(d);
-    cudaDeviceSynchronize();
-    std::lock_guard<std::mutex> lk(g_cache[d].mu);
+    std::lock_guard<std::mutex> lk(g_cache[d].mu); /* cached blocks are idle by contract (mmq_cache_free) */
     cache_drop_all(g_cache[d]);
   }
   cudaSetDevice(cur);
@@ -1066,7 +1069,7 @@ int mmq_create(const mmq_problem* p, int device, mmq_handle** out) {
     else if (!h->has_w) want += 4 * (nnz + nnz / 8) + 6 * (m + m / 4) + 4 * n + (1 << 16);     /* the class plan's (an estimate: what does not fit is allocated separately) */
     want += 64 * 256;                                                                      /* alignment of the pieces */
     void* a = nullptr;
-    if (mmq_cache_malloc_raw(&a, want) == cudaSuccess) { h->arena = (char*)a; h->arena_cap = want; }
+    if (mmq_cache_malloc_raw(&a, want) == cudaSuccess && cudaMemsetAsync(a, 0, want, h->stream) == cudaSuccess) { h->arena = (char*)a; h->arena_cap = want; }
     else cudaGetLastError(); /* fall back to separate allocations */
   }
   CREATE_TRY(upload(h, (void**)&h->row_ptr, p->row_ptr, sizeof(int64_t) * (size_t)(p->m + 1)));
@@ -1136,7 +1139,8 @@ void mmq_destroy(mmq_handle* h) {
   if (h->ev_join) cudaEventDestroy(h->ev_join);
   if (h->ev_join3) cudaEventDestroy(h->ev_join3);
   if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy((ncclComm_t)h->comm);
-  cudaDeviceSynchronize(); /* the blocks go back to the cache: nothing may still be running on them */
+  /* the blocks go back to the cache: nothing may still be running on them — every stream this handle ever launched on was
+   * synchronised above (no cudaDeviceSynchronize: another thread may be capturing a graph on its own stream) */
   for (void* p : h->allocs) mmq_cache_free(p);
   if (h->arena) mmq_cache_free(h->arena);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);

@@ -583,29 +583,32 @@ int mmq_mean_corrs(int device, const double* R, const uint8_t* S, int64_t C, int
   double *dR = nullptr, *dV = nullptr, *dW = nullptr;
   uint8_t* dS = nullptr;
   int32_t* dts = nullptr;
+  cudaStream_t st = nullptr;
   auto cleanup = [&] {
-    cudaDeviceSynchronize();
+    if (st) cudaStreamSynchronize(st);
     mmq_cache_free(dR);
     mmq_cache_free(dV);
     mmq_cache_free(dW);
     mmq_cache_free(dS);
     mmq_cache_free(dts);
+    if (st) cudaStreamDestroy(st);
   };
+  COV_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
   COV_TRY(mmq_cache_malloc(&dR, cc * (size_t)ns));
   COV_TRY(mmq_cache_malloc(&dV, cc));
   COV_TRY(mmq_cache_malloc(&dW, cc));
   COV_TRY(mmq_cache_malloc(&dS, (size_t)C * (size_t)ns));
   COV_TRY(mmq_cache_malloc(&dts, (size_t)(nts > 0 ? nts : 1) * 4));
-  COV_TRY(cudaMemcpy(dR, R, cc * (size_t)ns, cudaMemcpyHostToDevice));
-  COV_TRY(cudaMemcpy(dV, V, cc, cudaMemcpyHostToDevice));
-  COV_TRY(cudaMemcpy(dW, W, cc, cudaMemcpyHostToDevice));
-  COV_TRY(cudaMemcpy(dS, S, (size_t)C * (size_t)ns, cudaMemcpyHostToDevice));
-  COV_TRY(cudaMemcpy(dts, ts, (size_t)nts * 4, cudaMemcpyHostToDevice));
-  const int rc = mmq_mean_corrs_dev(dR, dS, C, ns, dts, nts, sdpenalty, dV, dW, nullptr);
+  COV_TRY(cudaMemcpyAsync(dR, R, cc * (size_t)ns, cudaMemcpyHostToDevice, st));
+  COV_TRY(cudaMemcpyAsync(dV, V, cc, cudaMemcpyHostToDevice, st));
+  COV_TRY(cudaMemcpyAsync(dW, W, cc, cudaMemcpyHostToDevice, st));
+  COV_TRY(cudaMemcpyAsync(dS, S, (size_t)C * (size_t)ns, cudaMemcpyHostToDevice, st));
+  COV_TRY(cudaMemcpyAsync(dts, ts, (size_t)nts * 4, cudaMemcpyHostToDevice, st));
+  const int rc = mmq_mean_corrs_dev(dR, dS, C, ns, dts, nts, sdpenalty, dV, dW, st);
   if (rc == MMQ_OK) {
-    COV_TRY(cudaDeviceSynchronize());
-    COV_TRY(cudaMemcpy(V, dV, cc, cudaMemcpyDeviceToHost));
-    COV_TRY(cudaMemcpy(W, dW, cc, cudaMemcpyDeviceToHost));
+    COV_TRY(cudaMemcpyAsync(V, dV, cc, cudaMemcpyDeviceToHost, st));
+    COV_TRY(cudaMemcpyAsync(W, dW, cc, cudaMemcpyDeviceToHost, st));
+    COV_TRY(cudaStreamSynchronize(st));
   }
   cleanup();
   return rc;
