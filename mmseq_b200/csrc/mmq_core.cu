@@ -776,9 +776,9 @@ k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const doubl
   int32_t* own = reinterpret_cast<int32_t*>(a.base[a.rank]);
   if (blockIdx.x == 0 && threadIdx.x < a.nranks)
     p2p_publish(reinterpret_cast<int32_t*>(a.base[threadIdx.x]) + MMQ_P2P_FLAG_ALLOC + 8 * a.rank, epoch);
-  if (threadIdx.x == 0)
-    for (int r = 0; r < a.nranks; ++r) /* own allocation is complete by stream order: no wait on self */
-      if (r != a.rank) p2p_wait(own + MMQ_P2P_FLAG_ALLOC + 8 * r, epoch);
+  /* one thread per peer polls that peer's flag (own allocation is complete by stream order: no wait on self): the waits
+   * overlap instead of one system-scope round trip after the other; the block barrier orders everybody else's loads behind them */
+  if (threadIdx.x < a.nranks && (int)threadIdx.x != a.rank) p2p_wait(own + MMQ_P2P_FLAG_ALLOC + 8 * threadIdx.x, epoch);
   __syncthreads();
   double* trace_col = nullptr;
   if (trace && stride > 0 && sweep % (uint32_t)stride == 0 && sweep / (uint32_t)stride < (uint32_t)trace_len) trace_col = trace + sweep / (uint32_t)stride;
@@ -788,7 +788,13 @@ k_gamma_p2p(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const doubl
     int32_t c = 0;
     double rate = 1.0;
     if (t >= 0) {
-      for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
+      /* all ranks' counts in flight at once: with a run-time trip count the adds serialise the peer loads, one NVLink round
+       * trip after the other */
+      int32_t v[MMQ_P2P_MAX];
+#pragma unroll
+      for (int r = 0; r < MMQ_P2P_MAX; ++r) v[r] = r < a.nranks ? __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t) : 0;
+#pragma unroll
+      for (int r = 0; r < MMQ_P2P_MAX; ++r) c += v[r];
       reset[t] = counts_base ? counts_base[t] : 0;
       if (counts_copy) counts_copy[t] = c;
       rate = beta + len[t];
@@ -821,9 +827,9 @@ k_gamma_rs(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double
   int32_t* own = reinterpret_cast<int32_t*>(a.base[a.rank]);
   if (blockIdx.x == 0 && threadIdx.x < a.nranks)
     p2p_publish(reinterpret_cast<int32_t*>(a.base[threadIdx.x]) + MMQ_P2P_FLAG_ALLOC + 8 * a.rank, epoch);
-  if (threadIdx.x == 0)
-    for (int r = 0; r < a.nranks; ++r)
-      if (r != a.rank) p2p_wait(own + MMQ_P2P_FLAG_ALLOC + 8 * r, epoch);
+  /* one thread per peer polls that peer's flag (own allocation is complete by stream order: no wait on self): the waits
+   * overlap instead of one system-scope round trip after the other; the block barrier orders everybody else's loads behind them */
+  if (threadIdx.x < a.nranks && (int)threadIdx.x != a.rank) p2p_wait(own + MMQ_P2P_FLAG_ALLOC + 8 * threadIdx.x, epoch);
   __syncthreads();
   const int64_t s0 = n * a.rank / a.nranks, s1 = n * (a.rank + 1) / a.nranks;
   for (int64_t t0 = s0 + (int64_t)blockIdx.x * MMQ_GAMMA_THREADS; t0 < s1; t0 += (int64_t)gridDim.x * MMQ_GAMMA_THREADS) {
@@ -831,7 +837,11 @@ k_gamma_rs(mmq_p2p_args a, const int32_t* __restrict__ counts_base, const double
     int32_t c = 0;
     double rate = 1.0;
     if (t >= 0) {
-      for (int r = 0; r < a.nranks; ++r) c += __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t);
+      int32_t v[MMQ_P2P_MAX];
+#pragma unroll
+      for (int r = 0; r < MMQ_P2P_MAX; ++r) v[r] = r < a.nranks ? __ldcv(reinterpret_cast<const int32_t*>(a.base[r] + a.off_counts) + t) : 0;
+#pragma unroll
+      for (int r = 0; r < MMQ_P2P_MAX; ++r) c += v[r];
       rate = beta + len[t];
     }
     const double v = gamma_block(S, t, c, rate, alpha, seed, sweep);
