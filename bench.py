@@ -618,6 +618,10 @@ def run_batch(args, rank, world, local):
     lock = threading.Lock()
 
     nprod = max(1, min(args.batch_per_gpu, 3))   # class construction of the next samples on several host threads
+    # the loader builds classes on all host threads it is given: share the cores between the ranks and their producers
+    share = max(2, host_threads() // (max(1, world) * nprod))
+    os.environ.setdefault("MMQ_LOADER_BUILDERS", str(max(1, share // 2)))
+    os.environ.setdefault("MMQ_LOADER_THREADS", str(max(1, share // 2)))
     it_lock = threading.Lock()
     it_state = {"next": 0, "left": nprod}
 

@@ -13,6 +13,8 @@ B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-gates --
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_alloc|k_gamma|k_trace|k_add2|k_set2" -c 600 --csv --log-file $O/r02_launches.csv $B > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k_alloc_chain|k_alloc_cls|k_gamma" -s 10 -c 5 -o $O/prof_r02_sweep -f $B > $O/ncu.log 2>&1; tail -1 $O/ncu.log
 ncu --set full --clock-control none --import-source on -k regex:"k_alloc_seg4" -s 4 -c 1 -o $O/prof_r02_seg4w -f python bench.py --weights --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-gates --no-extras > $O/ncu_seg4w.log 2>&1; tail -1 $O/ncu_seg4w.log
+ncu --set full --clock-control none --import-source on -k regex:k_cov_gemm -s 1 -c 1 -o $O/prof_r02_cov -f python tools/gpu_cov_prof.py > $O/ncu_cov.log 2>&1; tail -1 $O/ncu_cov.log
+timeout 300 python tools/gpu_cov_first.py > $O/r02_cov_sizes.txt 2>&1; tail -4 $O/r02_cov_sizes.txt
 # config 5 on one GPU: 4 samples, the reference's default chain length
 timeout 900 python bench.py --batch 4 --batch-per-gpu 4 > $O/r02_bench_batch_1gpu.json 2> $O/bench_batch.err; echo "batch rc=$?"
 # config 1 end to end: the reference's own main() (unmodified sources + oracle/shim) on the host cores vs the host program on the GPU
@@ -38,7 +40,8 @@ for ext, kind in ((".mmseq", "mmseq"), (".gene.mmseq", "gene")):
     print(ext, "deterministic columns equal;", len(z), "observed features, |z| of log_mu: median %.2f, 99th percentile %.2f, max %.2f" % (np.median(z), np.percentile(z, 99), z.max()))
 PY
 cat $O/r02_c1_compare.txt
-( MMQ_TIMING=1 mmseq_b200/bin/mmseq -notraces /tmp/c2.bin.hits /tmp/c2_ours > /dev/null ) 2> $O/r02_cli_c2_notraces_timing.txt; tail -12 $O/r02_cli_c2_notraces_timing.txt
+( MMQ_TIMING=1 MMQ_LOADER_TIMING=1 mmseq_b200/bin/mmseq -notraces /tmp/c2.bin.hits /tmp/c2_ours > /dev/null ) 2> $O/r02_cli_c2_notraces_timing.txt; tail -12 $O/r02_cli_c2_notraces_timing.txt
+( MMQ_TIMING=1 mmseq_b200/bin/mmseq /tmp/c2.bin.hits /tmp/c2_tr > /dev/null ) 2> $O/r02_cli_c2_timing.txt; grep "timing" $O/r02_cli_c2_timing.txt
 python - <<'PY'
 import json
 for f in ("reference","ours"):
@@ -48,6 +51,7 @@ for f in ("reference","ours"):
         print(f, "value %.4g"%d["value"], "sweeps/s", round(d["sweeps_per_s"],1), "alloc_ms", r.get("avg_launch_ms"), "gamma_ms", r.get("gamma_avg_launch_ms"), "frac", r.get("frac"), "e2e", d["e2e"] and round(d["e2e"].get("sweeps_per_s",0),1), "cpu", d.get("cpu_baseline",{}).get("sweeps_per_s"), "clocks", d.get("clocks"))
         print("  gates", json.dumps(d.get("gates")))
         print("  weighted", json.dumps(d.get("perfragment_weighted")))
+        print("  trace_cov", json.dumps(d.get("trace_cov"))[:900])
     except Exception as e: print(f,"failed",e)
 try:
     b=json.loads(open("gpurun_out/r02_bench_batch_1gpu.json").read().strip().split("\n")[-1]); print("batch", {k:b[k] for k in ("value","wall_s","sweeps_per_s_per_gpu","gpu_pipeline_s_median","prep_s_median")})
