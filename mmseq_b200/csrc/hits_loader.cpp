@@ -4,6 +4,7 @@
 #include "hits_loader.h"
 #include "inflate_par.h"
 #include "fmt_g6.h"
+#include "huff_gz.h"
 
 #include <zlib.h>
 
@@ -1169,6 +1170,14 @@ int64_t mmqh_fmt_g6(const double* v, int64_t n, char* out) {
   char* p = out;
   for (int64_t i = 0; i < n; ++i) { p = fmt_g6(p, v[i]); *p++ = ' '; }
   return (int64_t)(p - out);
+}
+
+/* test support: huff_gz.h, one gzip member for the n bytes; returns its size (out must hold n + 1024 bytes) */
+int64_t mmqh_gz_huffman(const void* in, int64_t n, void* out) {
+  std::vector<uint8_t> z;
+  mmq::hgz::gz_member((const char*)in, (size_t)n, z);
+  memcpy(out, z.data(), z.size());
+  return (int64_t)z.size();
 }
 
 /* test support: inflate_par.h on a zlib stream in memory; bytes written to out (capacity cap), -1 when the stream is

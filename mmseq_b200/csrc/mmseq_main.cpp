@@ -36,6 +36,7 @@
 
 #include "../../include/mmq.h"
 #include "fmt_g6.h"
+#include "huff_gz.h"
 #include "hits_loader.h"
 
 #define QUOTE_(x) #x
@@ -111,14 +112,17 @@ struct GzText {
  * members (RFC 1952 2.2); zlib's gzread, gzip(1), R's gzfile and Boost's gzip_decompressor all
  * read the concatenation as one stream, so the members can be produced in parallel. */
 static void gz_member(const string& text, vector<unsigned char>& out) {
+  /* The text is digits of continuous random values: string matching finds next to nothing in it, the gain is all in the
+   * entropy coding (zlib on trace-like text: Z_HUFFMAN_ONLY 1.5x faster than level 1 with matching AND 9 % smaller, ratio
+   * 2.22 against 2.04; level 6: 2.24 at an eighth of the speed).  Default: huff_gz.h, the same Huffman-only coding without
+   * zlib's per-symbol overhead.  The decompressed bytes are the reference's either way; MMQ_GZIP_LEVEL=6 gives zlib at the
+   * reference's settings back. */
+  static const int level = [] { const char* e = getenv("MMQ_GZIP_LEVEL"); return e ? atoi(e) : 0; }();
+  out.clear();
+  if (level <= 0) { mmq::hgz::gz_member(text.data(), text.size(), out); return; }
   z_stream zs;
   memset(&zs, 0, sizeof zs);
-  /* The text is digits of continuous random values: string matching finds next to nothing in it, the gain is all in the
-   * entropy coding.  Z_HUFFMAN_ONLY is 1.5x faster than level 1 with matching AND 9 % smaller (ratio 2.22 against 2.04;
-   * level 6: 2.24 at an eighth of the speed) — measured on trace-like text.  The decompressed bytes are the reference's
-   * either way; MMQ_GZIP_LEVEL=6 gives its exact settings back. */
-  static const int level = [] { const char* e = getenv("MMQ_GZIP_LEVEL"); return e ? atoi(e) : 0; }();
-  if (deflateInit2(&zs, level ? level : Z_BEST_SPEED, Z_DEFLATED, 15 + 16, 8, level ? Z_DEFAULT_STRATEGY : Z_HUFFMAN_ONLY) != Z_OK) die("Error: deflateInit2 failed.");
+  if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("Error: deflateInit2 failed.");
   out.resize(deflateBound(&zs, (uLong)text.size()) + 64);
   zs.next_in = (Bytef*)text.data();
   zs.avail_in = (uInt)text.size();

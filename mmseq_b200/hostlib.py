@@ -30,6 +30,8 @@ def lib():
         L.mmqh_load.argtypes = [C.c_char_p, i32, C.c_char_p, i32]
         L.mmqh_from_records.restype = vp
         L.mmqh_from_records.argtypes = [i64, vp, i64, vp, vp, vp, i32, C.c_char_p, i32]
+        L.mmqh_gz_huffman.restype = i64
+        L.mmqh_gz_huffman.argtypes = [vp, i64, vp]
         L.mmqh_fmt_g6.restype = i64
         L.mmqh_fmt_g6.argtypes = [vp, i64, vp]
         L.mmqh_inflate_parallel.restype = i64
@@ -88,6 +90,14 @@ class Hits:
             self.ident_ptr = _arr(L.mmqh_ident_ptr(handle), self.I + 1, np.int64)
             self.ident_members = _arr(L.mmqh_ident_members(handle), int(self.ident_ptr[-1]), np.int32)
         L.mmqh_free(handle)
+
+
+def gz_huffman(data):
+    """huff_gz.h (the trace files' compressor): one gzip member holding `data`."""
+    buf = np.frombuffer(bytes(data), np.uint8) if len(data) else np.zeros(0, np.uint8)
+    out = np.empty(len(buf) + 1024, np.uint8)
+    n = lib().mmqh_gz_huffman(buf.ctypes.data_as(C.c_void_p) if len(buf) else None, len(buf), out.ctypes.data_as(C.c_void_p))
+    return out[:n].tobytes()
 
 
 def fmt_g6(values):

@@ -70,3 +70,27 @@ def test_fast_g_format_equals_printf():
     want = ["%g" % v for v in vals]
     assert got == want
     assert hostlib.fmt_g6([float("nan")])[0].lstrip("-") == "nan"
+
+
+def test_huffman_only_gzip_members_decode_with_zlib():
+    """huff_gz.h (the trace files' compressor): any inflate must read its members; concatenated members read as one stream."""
+    import gzip
+    import io
+    import zlib
+    import numpy as np
+    from mmseq_b200 import hostlib
+    rng = np.random.default_rng(9)
+    texts = [b"", b"a", b"aaaaaaaaaaaaaaaa", bytes(range(256)) * 3,
+             " ".join("%g" % v for v in np.exp(rng.normal(0, 3, 200000))).encode() + b"\n",
+             rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),
+             # a very skewed histogram: code lengths beyond 15 bits before the limit is enforced
+             b"".join(bytes([i]) * (1 << min(i, 22)) for i in range(26))]
+    whole = b""
+    for t in texts:
+        z = hostlib.gz_huffman(t)
+        assert gzip.decompress(z) == t
+        assert zlib.decompress(z, 15 + 16) == t
+        whole += z
+    assert gzip.GzipFile(fileobj=io.BytesIO(whole)).read() == b"".join(texts)
+    digits = texts[4]
+    assert len(hostlib.gz_huffman(digits)) < 1.02 * len(zlib.compress(digits, 1)) / 1.05   # at least zlib level 1's ratio on digit text

@@ -6,7 +6,7 @@ O=gpurun_out
 mkdir -p $O
 T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 1200 $T --master-port 29600 bench.py --gpus $N > $O/r02_bench_${N}gpu_weak.json 2> $O/bench_${N}gpu_weak.err; echo "weak rc=$?"; tail -2 $O/bench_${N}gpu_weak.err
-timeout 1200 $T --master-port 29601 bench.py --gpus $N --scaling strong --fragments-total 200000000 --weights --steps 10 > $O/r02_bench_${N}gpu_c4.json 2> $O/bench_${N}gpu_c4.err; echo "c4 rc=$?"; tail -2 $O/bench_${N}gpu_c4.err
+if [ "$2" = "c4" ]; then timeout 1200 $T --master-port 29601 bench.py --gpus $N --scaling strong --fragments-total 200000000 --weights --steps 10 > $O/r02_bench_${N}gpu_c4.json 2> $O/bench_${N}gpu_c4.err; echo "c4 rc=$?"; tail -2 $O/bench_${N}gpu_c4.err; fi
 timeout 1200 $T --master-port 29602 bench.py --gpus $N --batch $((8 * N)) --batch-per-gpu 4 > $O/r02_bench_${N}gpu_batch.json 2> $O/bench_${N}gpu_batch.err; echo "batch rc=$?"; tail -2 $O/bench_${N}gpu_batch.err
 python - <<PY
 import json
