@@ -121,7 +121,7 @@ def make_workload(args, rank, world, weights=None, layout=None):
     nfrag, ntot = fragments_of(args, rank, world)
     t0 = time.time()
     s = synth.Synth(SYNTH_SEED + (1 if args.haplo else 0), args.transcripts * (2 if args.haplo else 1), nfrag, haplo=args.haplo,
-                    weights=weights, frag_seed=rank)
+                    weights=weights, frag_seed=rank, threads=max(1, host_threads() // max(1, world)))   # not OMP_NUM_THREADS (1 under torchrun)
     t1 = time.time()
     lay = hostlib.LAYOUT_COLLAPSED if layout == "collapsed" else hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH
     lay |= hostlib.LAYOUT_IDENTITY_COLUMNS if world > 1 else hostlib.LAYOUT_HEADER_ORDER_COLUMNS
@@ -635,7 +635,7 @@ def run_batch(args, rank, world, local):
                 i = mine[it_state["next"]]
                 it_state["next"] += 1
             t0 = time.perf_counter()
-            s = synth.Synth(SYNTH_SEED, args.transcripts, args.fragments, frag_seed=1000 + i)
+            s = synth.Synth(SYNTH_SEED, args.transcripts, args.fragments, frag_seed=1000 + i, threads=share)   # not OMP_NUM_THREADS (1 under torchrun)
             h = hostlib.from_records(s.T, s.efflen, s.frag_ptr, s.frag_tid, layout=hostlib.LAYOUT_COLLAPSED | hostlib.LAYOUT_HEADER_ORDER_COLUMNS)
             length = s.efflen[h.col2hdr] * args.fragments / 1e9
             q.put((i, h, length, time.perf_counter() - t0))
