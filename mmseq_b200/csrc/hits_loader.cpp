@@ -17,6 +17,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -428,6 +429,11 @@ struct ClassBuilder::Impl {
     shards.clear();
   }
 
+  void stop_workers() { /* records come one by one with weights: the sequential tables below take over */
+    for (auto& sp : shards) { { std::lock_guard<std::mutex> lk(sp->mu); sp->done = true; } sp->cv.notify_all(); }
+    for (auto& sp : shards) sp->th.join();
+    shards.clear();
+  }
   void push_batch(Shard& S, std::unique_ptr<Batch> b) {
     {
       std::unique_lock<std::mutex> lk(S.mu);
@@ -452,6 +458,9 @@ struct ClassBuilder::Impl {
     const uint64_t NONE = ~0ull;
     std::vector<std::vector<uint64_t>> fa((size_t)W);
     std::vector<std::vector<int32_t>> dh((size_t)W);
+    /* weighted: every builder keeps the weights of its (contiguous) record range, in header-sorted member order */
+    std::vector<std::vector<float>> bw((size_t)W);
+    std::vector<std::vector<int32_t>> bcnt((size_t)W);
     std::atomic<int> bad(0);
     auto build = [&](int w) {
       std::vector<uint64_t>& first = fa[(size_t)w];
@@ -461,32 +470,56 @@ struct ClassBuilder::Impl {
       std::vector<std::unique_ptr<Batch>> cur((size_t)K);
       for (auto& c : cur) c.reset(new Batch());
       std::vector<int32_t> ids;
+      std::vector<std::pair<int32_t, float>> pw;
       const int64_t r0 = nrec * w / W, r1 = nrec * (w + 1) / W;
+      if (weighted) { bw[(size_t)w].reserve((size_t)(r1 - r0) * 4); bcnt[(size_t)w].reserve((size_t)(r1 - r0)); }
       for (int64_t r = r0; r < r1; ++r) {
         const uint8_t* p;
+        const float* wp = nullptr;
         int cnt;
-        acc(r, p, cnt);
+        acc(r, p, cnt, wp);
         ids.clear();
-        for (int j = 0; j < cnt; ++j) {
-          uint32_t v;
-          memcpy(&v, p + 4 * (size_t)j, 4);
-          if (v >= (uint32_t)T) { bad.store(1); return; }
-          if (first[v] == NONE) first[v] = ((uint64_t)r << 24) | (uint64_t)std::min(j, 0xffffff);
-          bool dup = false;
-          if (ids.size() <= 32) {
-            for (int32_t e : ids) if (e == (int32_t)v) { dup = true; break; }
-            if (dup) { dbl[v]++; continue; } /* src/mmseq.cpp:404-409 */
+        if (!weighted) {
+          for (int j = 0; j < cnt; ++j) {
+            uint32_t v;
+            memcpy(&v, p + 4 * (size_t)j, 4);
+            if (v >= (uint32_t)T) { bad.store(1); return; }
+            if (first[v] == NONE) first[v] = ((uint64_t)r << 24) | (uint64_t)std::min(j, 0xffffff);
+            bool dup = false;
+            if (ids.size() <= 32) {
+              for (int32_t e : ids) if (e == (int32_t)v) { dup = true; break; }
+              if (dup) { dbl[v]++; continue; } /* src/mmseq.cpp:404-409 */
+            }
+            ids.push_back((int32_t)v);
           }
-          ids.push_back((int32_t)v);
-        }
-        std::sort(ids.begin(), ids.end());
-        if (ids.size() > 33) { /* long records: duplicates removed after the sort */
-          size_t o = 1;
-          for (size_t j = 1; j < ids.size(); ++j) {
-            if (ids[j] == ids[o - 1]) dbl[(size_t)ids[j]]++;
-            else ids[o++] = ids[j];
+          std::sort(ids.begin(), ids.end());
+          if (ids.size() > 33) { /* long records: duplicates removed after the sort */
+            size_t o = 1;
+            for (size_t j = 1; j < ids.size(); ++j) {
+              if (ids[j] == ids[o - 1]) dbl[(size_t)ids[j]]++;
+              else ids[o++] = ids[j];
+            }
+            ids.resize(o);
           }
-          ids.resize(o);
+        } else {
+          /* (transcript, weight) pairs; a repeated transcript adds its weight to the first occurrence, in record order */
+          pw.clear();
+          for (int j = 0; j < cnt; ++j) {
+            uint32_t v;
+            float wj;
+            memcpy(&v, p + 4 * (size_t)j, 4);
+            memcpy(&wj, (const uint8_t*)wp + 4 * (size_t)j, 4);
+            if (v >= (uint32_t)T) { bad.store(1); return; }
+            if (!(wj >= 0.f) || !std::isfinite(wj)) { bad.store(2); return; }
+            if (first[v] == NONE) first[v] = ((uint64_t)r << 24) | (uint64_t)std::min(j, 0xffffff);
+            bool dup = false;
+            for (auto& e : pw) if (e.first == (int32_t)v) { dup = true; e.second += wj; break; }
+            if (dup) dbl[v]++;
+            else pw.emplace_back((int32_t)v, wj);
+          }
+          std::sort(pw.begin(), pw.end(), [](const std::pair<int32_t, float>& a, const std::pair<int32_t, float>& b) { return a.first < b.first; });
+          for (auto& e : pw) { ids.push_back(e.first); bw[(size_t)w].push_back(e.second); }
+          bcnt[(size_t)w].push_back((int32_t)pw.size());
         }
         uint64_t hsh = 0x9e3779b97f4a7c15ull ^ (uint64_t)ids.size();
         for (int32_t e : ids) hsh = mix64(hsh ^ (uint64_t)(uint32_t)e) + 0x632be59bd9b4e019ull;
@@ -519,7 +552,7 @@ struct ClassBuilder::Impl {
     const double tb = clk();
     merge_shards(); /* classes in order of their first record, members still header indices */
     if (tm) fprintf(stderr, "[loader]   %d builders + %d class-table workers; drain + merge %.2f s\n", W, K, clk() - tb);
-    if (bad.load()) return 1;
+    if (bad.load()) return bad.load();
     /* columns: transcripts in order of first appearance */
     const bool identity = identity_cols;
     std::vector<uint64_t>& first = fa[0];
@@ -536,20 +569,57 @@ struct ClassBuilder::Impl {
     for (int w = 0; w < W; ++w)
       for (int64_t h = 0; h < T; ++h)
         if (dh[(size_t)w][(size_t)h]) doublehits[(size_t)hdr2col[(size_t)h]] += dh[(size_t)w][(size_t)h];
+    /* members: header index -> column, ascending again (the reference sorts the column indices, :412); weighted: where
+     * each member came from, so that every record's weights can follow */
+    const int64_t C = (int64_t)cls_hash.size();
+    std::vector<int32_t> perm; /* [entry of cls_col] position of that member in the header-sorted class */
+    if (weighted) perm.resize(cls_col.size());
     if (!identity) {
-      /* members: header index -> column, ascending again (the reference sorts the column indices, :412) */
-      const int64_t C = (int64_t)cls_hash.size();
       auto renum = [&](int w) {
+        std::vector<std::pair<int32_t, int32_t>> tmp;
         for (int64_t c = C * w / W; c < C * (w + 1) / W; ++c) {
           int32_t* b = cls_col.data() + cls_ptr[(size_t)c];
           int32_t* e = cls_col.data() + cls_ptr[(size_t)c + 1];
           for (int32_t* q = b; q < e; ++q) *q = hdr2col[(size_t)*q];
-          std::sort(b, e);
+          if (!weighted) { std::sort(b, e); continue; }
+          tmp.clear();
+          for (int32_t* q = b; q < e; ++q) tmp.emplace_back(*q, (int32_t)(q - b));
+          std::sort(tmp.begin(), tmp.end());
+          int32_t* pm = perm.data() + cls_ptr[(size_t)c];
+          for (size_t j = 0; j < tmp.size(); ++j) { b[j] = tmp[j].first; pm[j] = tmp[j].second; }
         }
       };
       std::vector<std::thread> th;
       for (int w = 1; w < W; ++w) th.emplace_back(renum, w);
       renum(0);
+      for (auto& t : th) t.join();
+    } else if (weighted) {
+      for (int64_t c = 0; c < C; ++c)
+        for (int64_t q = cls_ptr[(size_t)c]; q < cls_ptr[(size_t)c + 1]; ++q) perm[(size_t)q] = (int32_t)(q - cls_ptr[(size_t)c]);
+    }
+    if (weighted) {
+      /* the records' weights, in the column order of their class */
+      rec_wptr.assign((size_t)nrec + 1, 0);
+      {
+        int64_t r = 0;
+        for (int w = 0; w < W; ++w)
+          for (int32_t c : bcnt[(size_t)w]) { rec_wptr[(size_t)r + 1] = rec_wptr[(size_t)r] + c; ++r; }
+      }
+      rec_w.resize((size_t)rec_wptr[(size_t)nrec]);
+      auto place = [&](int w) {
+        const int64_t r0 = nrec * w / W, r1 = nrec * (w + 1) / W;
+        const float* src = bw[(size_t)w].data();
+        for (int64_t r = r0; r < r1; ++r) {
+          const int64_t d = rec_wptr[(size_t)r + 1] - rec_wptr[(size_t)r];
+          const int32_t* pm = perm.data() + cls_ptr[(size_t)rec_class[(size_t)r]];
+          float* dst = rec_w.data() + rec_wptr[(size_t)r];
+          for (int64_t j = 0; j < d; ++j) dst[j] = src[pm[j]];
+          src += d;
+        }
+      };
+      std::vector<std::thread> th;
+      for (int w = 1; w < W; ++w) th.emplace_back(place, w);
+      place(0);
       for (auto& t : th) t.join();
     }
     return 0;
@@ -579,7 +649,7 @@ ClassBuilder::ClassBuilder(int64_t T, int layout, bool weighted) : p_(new Impl()
     for (int64_t t = 0; t < T; ++t) { p_->hdr2col[(size_t)t] = (int32_t)t; p_->col2hdr[(size_t)t] = (int32_t)t; }
   }
   p_->grow_table();
-  if (!weighted) {
+  {
     /* hash-shard workers (they own the class tables) and, for records handed over all at once, as many builder threads */
     const unsigned hc = std::thread::hardware_concurrency();
     int K = hc >= 8 ? std::min(12, (int)hc / 2) : 3; /* measured on 8 threads: 4 builders + 4 workers 0.91 s, 5 + 3 1.09 s, 6 + 2 1.92 s */
@@ -595,28 +665,32 @@ ClassBuilder::~ClassBuilder() {
   delete p_;
 }
 
-bool ClassBuilder::parallel_ready() const { return !p_->weighted && !p_->shards.empty() && p_->N == 0; }
+bool ClassBuilder::parallel_ready() const { return !p_->shards.empty() && p_->N == 0; }
 int ClassBuilder::add_records_binary(const uint8_t* base, const uint64_t* off, int64_t nrec) {
   Impl& P = *p_;
-  auto acc = [base, off](int64_t r, const uint8_t*& p, int& cnt) {
+  const bool wt = P.weighted;
+  auto acc = [base, off, wt](int64_t r, const uint8_t*& p, int& cnt, const float*& w) {
     uint32_t c;
     memcpy(&c, base + off[r], 4);
     cnt = (int)c;
     p = base + off[r] + 4;
+    w = wt ? (const float*)(p + 4 * (size_t)c) : nullptr; /* schema 2: the weights follow the indices (unaligned: read with memcpy) */
   };
   return P.ingest_parallel(nrec, (int64_t)P.hdr2col.size(), acc, P.builders);
 }
-int ClassBuilder::add_records_csr(const int64_t* frag_ptr, const int32_t* frag_tid, int64_t nrec) {
+int ClassBuilder::add_records_csr(const int64_t* frag_ptr, const int32_t* frag_tid, const float* frag_w, int64_t nrec) {
   Impl& P = *p_;
-  auto acc = [frag_ptr, frag_tid](int64_t r, const uint8_t*& p, int& cnt) {
+  auto acc = [frag_ptr, frag_tid, frag_w](int64_t r, const uint8_t*& p, int& cnt, const float*& w) {
     cnt = (int)(frag_ptr[r + 1] - frag_ptr[r]);
     p = (const uint8_t*)(frag_tid + frag_ptr[r]);
+    w = frag_w ? frag_w + frag_ptr[r] : nullptr;
   };
   return P.ingest_parallel(nrec, (int64_t)P.hdr2col.size(), acc, P.builders);
 }
 
 void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
   Impl& P = *p_;
+  if (P.weighted && !P.shards.empty()) P.stop_workers();
   P.N++;
   auto& comb = P.comb;
   comb.clear();
@@ -687,6 +761,10 @@ void ClassBuilder::add_record(const int32_t* tids, const float* w, int cnt) {
 
 void ClassBuilder::finish(HitClasses& out) {
   Impl& P = *p_;
+  const bool tm = getenv("MMQ_LOADER_TIMING") != nullptr;
+  auto clk = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_last = clk();
+  auto tick = [&](const char* what) { if (tm) { const double t = clk(); fprintf(stderr, "[loader]   finish: %-28s %.2f s\n", what, t - t_last); t_last = t; } };
   if (!P.shards.empty()) P.merge_shards();
   if (P.header_order) {
     /* renumber the observed transcripts by header index; members of a class stay ascending */
@@ -701,27 +779,39 @@ void ClassBuilder::finish(HitClasses& out) {
     P.doublehits.swap(dh);
     for (size_t hI = 0; hI < P.hdr2col.size(); ++hI) if (P.hdr2col[hI] >= 0) P.hdr2col[hI] = newcol[(size_t)P.hdr2col[hI]];
     const int64_t C = (int64_t)P.cls_hash.size();
-    std::vector<std::pair<int32_t, int32_t>> tmp; /* (new column, old position) */
-    std::vector<std::vector<int32_t>> perm_of_class;
-    if (P.weighted) perm_of_class.resize((size_t)C);
-    for (int64_t c = 0; c < C; ++c) {
-      const int64_t b = P.cls_ptr[(size_t)c], e = P.cls_ptr[(size_t)c + 1];
-      tmp.clear();
-      for (int64_t q = b; q < e; ++q) tmp.emplace_back(newcol[(size_t)P.cls_col[(size_t)q]], (int32_t)(q - b));
-      std::sort(tmp.begin(), tmp.end());
-      for (int64_t q = b; q < e; ++q) P.cls_col[(size_t)q] = tmp[(size_t)(q - b)].first;
-      if (P.weighted) { auto& pm = perm_of_class[(size_t)c]; pm.resize(tmp.size()); for (size_t j = 0; j < tmp.size(); ++j) pm[j] = tmp[j].second; }
-    }
-    if (P.weighted) {
-      std::vector<float> t2;
-      for (size_t r = 0; r < P.rec_class.size(); ++r) {
-        const auto& pm = perm_of_class[(size_t)P.rec_class[r]];
-        float* wr = P.rec_w.data() + P.rec_wptr[r];
-        t2.assign(wr, wr + pm.size());
-        for (size_t j = 0; j < pm.size(); ++j) wr[j] = t2[(size_t)pm[j]];
+    const int W = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto par = [&](int64_t count, const std::function<void(int64_t, int64_t)>& body) { /* body(begin, end) on W threads */
+      std::vector<std::thread> th;
+      for (int w = 1; w < W; ++w) th.emplace_back([&, w] { body(count * w / W, count * (w + 1) / W); });
+      body(0, count / W);
+      for (auto& t : th) t.join();
+    };
+    std::vector<int32_t> perm; /* weighted: [entry of cls_col] old position of the member now at that place */
+    if (P.weighted) perm.resize(P.cls_col.size());
+    par(C, [&](int64_t c0, int64_t c1) {
+      std::vector<std::pair<int32_t, int32_t>> tmp; /* (new column, old position) */
+      for (int64_t c = c0; c < c1; ++c) {
+        const int64_t b = P.cls_ptr[(size_t)c], e = P.cls_ptr[(size_t)c + 1];
+        tmp.clear();
+        for (int64_t q = b; q < e; ++q) tmp.emplace_back(newcol[(size_t)P.cls_col[(size_t)q]], (int32_t)(q - b));
+        std::sort(tmp.begin(), tmp.end());
+        for (int64_t q = b; q < e; ++q) P.cls_col[(size_t)q] = tmp[(size_t)(q - b)].first;
+        if (P.weighted) for (int64_t q = b; q < e; ++q) perm[(size_t)q] = tmp[(size_t)(q - b)].second;
       }
-    }
+    });
+    if (P.weighted)
+      par((int64_t)P.rec_class.size(), [&](int64_t r0, int64_t r1) {
+        std::vector<float> t2;
+        for (int64_t r = r0; r < r1; ++r) {
+          const int64_t cb = P.cls_ptr[(size_t)P.rec_class[(size_t)r]];
+          const size_t d = (size_t)(P.cls_ptr[(size_t)P.rec_class[(size_t)r] + 1] - cb);
+          float* wr = P.rec_w.data() + P.rec_wptr[(size_t)r];
+          t2.assign(wr, wr + d);
+          for (size_t j = 0; j < d; ++j) wr[j] = t2[(size_t)perm[(size_t)cb + j]];
+        }
+      });
   }
+  tick("header-order renumbering");
   out.layout = P.layout;
   out.N = P.N;
   out.n = (int64_t)P.col2hdr.size();
@@ -748,14 +838,38 @@ void ClassBuilder::finish(HitClasses& out) {
       for (int64_t c = 0; c < out.n_classes; ++c) by[(size_t)c] = c;
       /* by class size, then by the member columns lexicographically: neighbouring rows gather
        * the same or neighbouring mu entries */
-      std::stable_sort(by.begin(), by.end(), [&](int64_t a, int64_t b) {
+      auto less = [&](int64_t a, int64_t b) {
         const int64_t da = P.cls_ptr[(size_t)a + 1] - P.cls_ptr[(size_t)a], db = P.cls_ptr[(size_t)b + 1] - P.cls_ptr[(size_t)b];
         if (da != db) return da < db;
         const int32_t* pa = P.cls_col.data() + P.cls_ptr[(size_t)a];
         const int32_t* pb = P.cls_col.data() + P.cls_ptr[(size_t)b];
-        return std::lexicographical_compare(pa, pa + da, pb, pb + db);
-      });
+        for (int64_t j = 0; j < da; ++j)
+          if (pa[j] != pb[j]) return pa[j] < pb[j];
+        return a < b; /* distinct classes never tie; a total order anyway */
+      };
+      {
+        /* sorted chunks on all threads, then pairwise merges */
+        const int64_t nC = out.n_classes;
+        int W = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        while (W > 1 && nC / W < 64) W /= 2;
+        std::vector<int64_t> cut((size_t)W + 1);
+        for (int w = 0; w <= W; ++w) cut[(size_t)w] = nC * w / W;
+        {
+          std::vector<std::thread> th;
+          for (int w = 0; w < W; ++w) th.emplace_back([&, w] { std::sort(by.begin() + cut[(size_t)w], by.begin() + cut[(size_t)w + 1], less); });
+          for (auto& t : th) t.join();
+        }
+        for (int step = 1; step < W; step *= 2) {
+          std::vector<std::thread> th;
+          for (int w = 0; w + step < W; w += 2 * step)
+            th.emplace_back([&, w, step] {
+              std::inplace_merge(by.begin() + cut[(size_t)w], by.begin() + cut[(size_t)(w + step)], by.begin() + cut[(size_t)std::min(W, w + 2 * step)], less);
+            });
+          for (auto& t : th) t.join();
+        }
+      }
       for (int64_t i = 0; i < out.n_classes; ++i) rank[(size_t)by[(size_t)i]] = i;
+      tick("classes by size and members");
     }
     std::vector<int64_t> start((size_t)out.n_classes + 1, 0);
     for (int64_t r = 0; r < R; ++r) start[(size_t)rank[(size_t)P.rec_class[(size_t)r]] + 1]++;
@@ -764,6 +878,7 @@ void ClassBuilder::finish(HitClasses& out) {
   } else {
     for (int64_t r = 0; r < R; ++r) order[(size_t)r] = r;
   }
+  tick("records by class");
   out.m = R;
   out.k.clear();
   out.row_ptr.assign((size_t)R + 1, 0);
@@ -773,15 +888,26 @@ void ClassBuilder::finish(HitClasses& out) {
     total += P.cls_ptr[(size_t)c + 1] - P.cls_ptr[(size_t)c];
     out.row_ptr[(size_t)i + 1] = total;
   }
+  tick("row pointers");
   out.col.resize((size_t)total);
   if (P.weighted) out.w.resize((size_t)total);
-  for (int64_t i = 0; i < R; ++i) {
-    const int64_t r = order[(size_t)i];
-    const int32_t c = P.rec_class[(size_t)r];
-    const int64_t b = P.cls_ptr[(size_t)c], d = P.cls_ptr[(size_t)c + 1] - b;
-    std::memcpy(out.col.data() + out.row_ptr[(size_t)i], P.cls_col.data() + b, sizeof(int32_t) * (size_t)d);
-    if (P.weighted) std::memcpy(out.w.data() + out.row_ptr[(size_t)i], P.rec_w.data() + P.rec_wptr[(size_t)r], sizeof(float) * (size_t)d);
+  {
+    const int W = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto copy = [&](int w) {
+      for (int64_t i = R * w / W; i < R * (w + 1) / W; ++i) {
+        const int64_t r = order[(size_t)i];
+        const int32_t c = P.rec_class[(size_t)r];
+        const int64_t b = P.cls_ptr[(size_t)c], d = P.cls_ptr[(size_t)c + 1] - b;
+        std::memcpy(out.col.data() + out.row_ptr[(size_t)i], P.cls_col.data() + b, sizeof(int32_t) * (size_t)d);
+        if (P.weighted) std::memcpy(out.w.data() + out.row_ptr[(size_t)i], P.rec_w.data() + P.rec_wptr[(size_t)r], sizeof(float) * (size_t)d);
+      }
+    };
+    std::vector<std::thread> th;
+    for (int w = 1; w < W; ++w) th.emplace_back(copy, w);
+    copy(0);
+    for (auto& t : th) t.join();
   }
+  tick("rows copied");
 }
 
 /* ------------------------------------------------------------------ header */
@@ -1016,7 +1142,7 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
   } else {
     /* records, src/hitsio.cpp:413-439; read names are delta-coded (:101-115) and unused here */
     std::string mid;
-    if (hdr.schema == 1 && src.whole() && cb.parallel_ready() && !getenv("MMQ_LOADER_SERIAL_RECORDS")) {
+    if (src.whole() && cb.parallel_ready() && !getenv("MMQ_LOADER_SERIAL_RECORDS")) {
       /* the inflated file is in memory: one cheap sequential walk finds where each record's hit list starts (the delta-coded
        * names make record boundaries sequential), the rest — de-duplication, sort, hash, class tables — runs on all threads */
       const uint8_t* b = (const uint8_t*)src.whole_base();
@@ -1048,12 +1174,16 @@ int load_hits_file(const std::string& path, int layout, HitsHeader& hdr, HitClas
         uint32_t cnt;
         memcpy(&cnt, b + p, 4);
         if (cnt == 0) { err = "Error: a read record without any mapping transcripts in the hits file."; return 1; }
-        if (cnt > Tn || p + 4 + 4 * (size_t)cnt > end) { err = malformed; return 1; }
+        const size_t per_hit = hdr.schema == 2 ? 8 : 4; /* schema 2: one fp32 weight per hit after the indices */
+        if (cnt > Tn || p + 4 + per_hit * (size_t)cnt > end) { err = malformed; return 1; }
         off.push_back((uint64_t)p);
-        p += 4 + 4 * (size_t)cnt;
+        p += 4 + per_hit * (size_t)cnt;
       }
       const double t_scan = now();
-      if (cb.add_records_binary(b, off.data(), (int64_t)off.size())) { err = malformed; return 1; }
+      if (int brc = cb.add_records_binary(b, off.data(), (int64_t)off.size())) {
+        err = brc == 2 ? "Error: per-hit weights must be finite and non-negative." : malformed;
+        return 1;
+      }
       const double t_rec = now();
       cb.finish(cls);
       if (timing) fprintf(stderr, "[loader] record walk %.2f s, classes (parallel) %.2f s, finish (layout) %.2f s\n", t_scan - t_hdr, t_rec - t_scan, now() - t_rec);
@@ -1149,7 +1279,11 @@ mmqh_hits* mmqh_from_records(int64_t T, const double* efflen, int64_t N, const i
   for (int64_t f = 0; f < N && !any_empty; ++f) any_empty = frag_ptr[f + 1] == frag_ptr[f];
   if (!any_empty && N > 0 && cb.parallel_ready() && !getenv("MMQ_LOADER_SERIAL_RECORDS")) {
     /* all records at once on all host threads (a negative index reads as a huge unsigned one: out of range) */
-    if (cb.add_records_csr(frag_ptr, frag_tid, N)) { set_err(err, errlen, "transcript index out of range"); delete H; return nullptr; }
+    if (int brc = cb.add_records_csr(frag_ptr, frag_tid, frag_w, N)) {
+      set_err(err, errlen, brc == 2 ? "per-hit weights must be finite and non-negative" : "transcript index out of range");
+      delete H;
+      return nullptr;
+    }
   } else {
     for (int64_t f = 0; f < N; ++f) {
       const int64_t b = frag_ptr[f], e = frag_ptr[f + 1];

@@ -72,12 +72,13 @@ class ClassBuilder {
   ClassBuilder(int64_t n_header_transcripts, int layout, bool weighted);
   /* one record: header transcript indices (and weights) of one fragment */
   void add_record(const int32_t* tids, const float* w, int cnt);
-  /* All records at once, on all host threads (unweighted; nothing added before): either the inflated binary file —
+  /* All records at once, on all host threads (nothing added before): either the inflated binary file —
    * off[r] = offset of record r's uint32 hit count, the uint32 transcript indices follow — or the harness's arrays.
-   * Same classes, numbering and counts as add_record() record by record.  Return 1 on an index out of range. */
+   * Same classes, numbering and counts as add_record() record by record.  Return 1 on an index out of range, 2 on a weight that is negative or not finite
+   * (weights: schema 2 — one fp32 per hit after a record's indices — or frag_w). */
   bool parallel_ready() const;
   int add_records_binary(const uint8_t* base, const uint64_t* off, int64_t nrec);
-  int add_records_csr(const int64_t* frag_ptr, const int32_t* frag_tid, int64_t nrec);
+  int add_records_csr(const int64_t* frag_ptr, const int32_t* frag_tid, const float* frag_w, int64_t nrec);
   void finish(HitClasses& out);
  private:
   struct Impl;

@@ -327,3 +327,48 @@ def test_in_memory_records_parallel_equals_sequential(small_synth):
             os.environ.pop("MMQ_LOADER_SERIAL_RECORDS")
         b = hostlib.from_records(recs.T, recs.efflen, recs.frag_ptr, recs.frag_tid, layout=layout)
         _equal(a, b)
+
+
+WLAYOUTS = [hostlib.LAYOUT_PER_FRAGMENT, hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH, hostlib.LAYOUT_PER_FRAGMENT_SORTED,
+            hostlib.LAYOUT_PER_FRAGMENT_BY_LENGTH | hostlib.LAYOUT_HEADER_ORDER_COLUMNS]
+
+
+def _equal_w(a, b):
+    _equal(a, b)
+    assert a.w is not None and b.w is not None and np.array_equal(a.w, b.w)     # bit for bit: same sums in the same order
+
+
+@pytest.mark.parametrize("layout", WLAYOUTS)
+def test_weighted_parallel_loader_equals_the_sequential_walk(tmp_path, small_synth, layout):
+    """Schema 2 (one fp32 weight per hit): weights of repeated transcripts are summed in record order, every record's
+    weights follow its class's column order — the parallel path against the record-by-record one."""
+    recs = _Recs(small_synth, seed=5)
+    rng = np.random.default_rng(12)
+    wts = rng.lognormal(0.0, 0.5, len(recs.frag_tid)).astype(np.float32)
+    path = str(tmp_path / "w.hits")
+    synth.write_hits_binary(recs, path, weights=wts)
+    serial = _load_env(path, layout, MMQ_LOADER_SERIAL_INFLATE=1)
+    assert serial.schema == 2
+    for builders, workers in ((1, 1), (4, 3)):
+        par = _load_env(path, layout, MMQ_LOADER_PAR_MIN_BYTES=0, MMQ_LOADER_BUILDERS=builders, MMQ_LOADER_THREADS=workers)
+        _equal_w(par, serial)
+    os.environ["MMQ_LOADER_SERIAL_RECORDS"] = "1"
+    try:
+        a = hostlib.from_records(recs.T, recs.efflen, recs.frag_ptr, recs.frag_tid, frag_w=wts, layout=layout)
+    finally:
+        os.environ.pop("MMQ_LOADER_SERIAL_RECORDS")
+    b = hostlib.from_records(recs.T, recs.efflen, recs.frag_ptr, recs.frag_tid, frag_w=wts, layout=layout)
+    _equal_w(a, b)
+    _equal_w(a, serial)
+
+
+def test_weighted_parallel_loader_refuses_bad_weights(tmp_path, small_synth):
+    s = small_synth
+    wts = np.ones(len(s.frag_tid), np.float32)
+    wts[len(wts) // 2] = -1.0
+    path = str(tmp_path / "bad.hits")
+    synth.write_hits_binary(s, path, weights=wts)
+    for env in ({"MMQ_LOADER_SERIAL_INFLATE": 1}, {"MMQ_LOADER_PAR_MIN_BYTES": 0}):
+        with pytest.raises(RuntimeError) as e:
+            _load_env(path, hostlib.LAYOUT_PER_FRAGMENT, **env)
+        assert "weights" in str(e.value)
