@@ -589,7 +589,7 @@ def extra_trace_cov(args, dev, stream):
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / tpeak, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback",
                          "algorithmic_flops_per_launch": flops, "output_gbs": out_bytes / (ms * 1e-3) / 1e9,
-                         "note": "operand tiles come from the L2 (Z = 67 MB): 48 KB per 4.2 MFLOP stage puts the L2 cap near 1.05 PFLOP/s; 2.1 GB of fp64 output per launch"},
+                         "note": "bound by the SM's shared-memory bandwidth as a single-CTA kernel (operand reads of the 128 x 256 x 16 MMA + TMA writes + the epilogue's transposition, DESIGN.md section 4); 2.1 GB of fp64 output per launch"},
             "gate": {"max_corr_err_vs_oracle": err, "tol": 3e-5, "exactly_symmetric": sym, "ok": bool(err < 3e-5 and sym)},
             "e2e": {"seconds": e2e_s, "matrices_per_s": 1.0 / e2e_s, "h2d_bytes": int(Mhost.nbytes), "d2h_bytes": int(Rh.nbytes)},
             "cpu_baseline": {"seconds_full_matrix": cpu_full_s, "matrices_per_s": 1.0 / cpu_full_s, "cores": host_threads(), "kind": "port",

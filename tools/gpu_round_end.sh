@@ -15,6 +15,7 @@ ncu --set full --clock-control none --import-source on -k regex:"k_alloc_chain|k
 ncu --set full --clock-control none --import-source on -k regex:"k_alloc_seg4" -s 4 -c 1 -o $O/prof_r02_seg4w -f python bench.py --weights --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --no-gates --no-extras > $O/ncu_seg4w.log 2>&1; tail -1 $O/ncu_seg4w.log
 ncu --set full --clock-control none --import-source on -k regex:k_cov_gemm -s 1 -c 1 -o $O/prof_r02_cov -f python tools/gpu_cov_prof.py > $O/ncu_cov.log 2>&1; tail -1 $O/ncu_cov.log
 timeout 300 python tools/gpu_cov_first.py > $O/r02_cov_sizes.txt 2>&1; tail -4 $O/r02_cov_sizes.txt
+timeout 400 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_collapse.py -q -x -k "not full_size" > $O/r02_memcheck_cov.log 2>&1; echo "memcheck cov rc=$?"; tail -3 $O/r02_memcheck_cov.log
 # config 5 on one GPU: 4 samples, the reference's default chain length
 timeout 900 python bench.py --batch 4 --batch-per-gpu 4 > $O/r02_bench_batch_1gpu.json 2> $O/bench_batch.err; echo "batch rc=$?"
 # config 1 end to end: the reference's own main() (unmodified sources + oracle/shim) on the host cores vs the host program on the GPU
