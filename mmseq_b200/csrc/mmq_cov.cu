@@ -30,13 +30,23 @@
  * pipe 52 % active; profiles/r02_k_cov_gemm_ncu_summary.txt): shared-memory bandwidth.  A single-CTA 128 x 256 x 16 MMA reads
  * 12 KB of operands from shared memory per 1 MFLOP (66 B/clk at the measured peak rate), TMA writes 48 KB per four of them
  * (64 B/clk) and the epilogue's transposition adds 40 B/clk: more than the 128 B/clk an SM has.  Loading every tile once
- * for all split products (64-byte swizzle, 1.5x less L2 traffic) was measured: same time, so it is not the L2.  The next
- * step is the CTA pair (tcgen05.mma.cta_group::2, 256 x 256 per pair: 8 KB of operand reads per MMA and SM).
+ * for all split products (64-byte swizzle, 1.5x less L2 traffic) was measured: same time, so it is not the L2.
+ *   k_cov_gemm2 (the default; MMQ_COV_PAIR=0 selects k_cov_gemm) is the same pipeline on CTA PAIRS: clusters of two CTAs,
+ *                tcgen05.mma.cta_group::2 (M 256 x N 256 x K 16 per pair; SASS UTCHMMA.2CTA), each CTA loading its 128 rows
+ *                of both operands (UTMALDG.2D.2CTA, both signalling the leader's mbarrier), tcgen05.commit multicast to both
+ *                CTAs (UTCBAR.2CTA.MULTICAST), accumulators handed back by the epilogue warps of both CTAs (remote mbarrier
+ *                arrive): 8 KB of operand reads per MMA and SM instead of 12, 32 KB of TMA writes per stage instead of 48.
+ *                0.91-0.93 ms at C = 16384, nsplit = 2 (0.55 of the measured peak; 0.66 with nsplit = 3): each further split
+ *                product now costs 0.18 ms = 1.5 PFLOP/s, what is left is the epilogue (0.57 ms for the 2.1 GB of fp64 output
+ *                with one product), which does not hide behind the MMAs of the next tile as it should — ncu's top stall there
+ *                is the FP64 pipe (math-pipe throttle on the r * sd_i * sd_j products), but an integer-only conversion
+ *                (split scale, exponent arithmetic) measured the same, so the store path itself is the suspect.
  */
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include <algorithm>
@@ -344,6 +354,224 @@ __global__ void __launch_bounds__(COV_THREADS, 1)
   }
 }
 
+/* ---- k_cov_gemm2: the same product on CTA PAIRS (tcgen05.mma.cta_group::2) ----
+ * A cluster of two CTAs (two SMs of one TPC) computes one 256 x 256 tile: CTA r of the pair holds rows 128 r .. of the A
+ * operand and rows 128 r .. of the B operand (each loaded by its own TMA producer, both signalling the LEADER's mbarrier),
+ * the leader's elected thread issues M 256 x N 256 x K 16 MMAs for both SMs, every SM accumulates its own 128 x 256 half in
+ * its own TMEM and drains it with its own epilogue warps.  Per MMA an SM reads 8 KB of operands from shared memory instead
+ * of 12 KB and receives 32 KB per stage instead of 48 KB: the single-CTA kernel above is bound by exactly that.
+ * Stage release and accumulator hand-over: tcgen05.commit with .multicast::cluster to both CTAs; the accumulator is handed
+ * back to the leader by the epilogue warps of BOTH CTAs (remote mbarrier arrive through mapa). */
+constexpr int COV2_STAGES = 4;
+constexpr int COV2_STAGE_BYTES = 2 * COV_A_BYTES; /* this CTA's 128 rows of A and its 128 rows of B */
+constexpr int COV2_SMEM = COV2_STAGES * COV2_STAGE_BYTES + COV_EPI_WARPS * COV_EPI_BYTES + 256 + 1024;
+/* instruction descriptor of the pair: M = 256 */
+constexpr uint32_t COV2_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+/* the address of the same shared-memory location in CTA `rank` of the cluster */
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, int c0, int c1, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) { /* arrives on this barrier in BOTH CTAs of the pair */
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(COV_THREADS, 1)
+    k_cov_gemm2(const __grid_constant__ CUtensorMap zmap, const double* __restrict__ sd, double* __restrict__ R, int64_t C, int L, int nsplit,
+                int64_t tiles) {
+  extern __shared__ uint8_t cov_smem_raw[];
+  uint8_t* smem = cov_smem_raw + ((1024u - (smem_u32(cov_smem_raw) & 1023u)) & 1023u);
+  uint8_t* epi = smem + COV2_STAGES * COV2_STAGE_BYTES;
+  uint64_t* full = (uint64_t*)(epi + COV_EPI_WARPS * COV_EPI_BYTES); /* used in the leader only: both producers' bytes land there */
+  uint64_t* empty = full + COV2_STAGES;
+  uint64_t* tfull = empty + COV2_STAGES;
+  uint64_t* tempty = tfull + 2; /* used in the leader only: 8 epilogue warps of each CTA arrive */
+  uint32_t* tmem_slot = (uint32_t*)(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_rank();
+  const bool leader = rank == 0;
+  const int64_t pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&zmap) : "memory");
+    for (int s = 0; s < COV2_STAGES; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull + b, 1);
+      mbar_init(tempty + b, 2 * COV_EPI_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  cluster_sync_all(); /* nobody signals a barrier of the peer before it is initialised */
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(COV_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  const int kb_per_seg = L / COV_BK;
+  const int iters = (nsplit * (nsplit + 1) / 2) * kb_per_seg;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int64_t t = pair; t < tiles; t += npairs) {
+        int64_t nb = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+        while (nb * (nb + 1) / 2 > t) --nb;
+        while ((nb + 1) * (nb + 2) / 2 <= t) ++nb;
+        const int64_t mb = t - nb * (nb + 1) / 2;
+        const int row_a = (int)(mb * 256 + rank * 128), row_b = (int)(nb * 256 + rank * 128);
+        for (int sum = nsplit - 1; sum >= 0; --sum)
+          for (int a = 0; a <= sum; ++a) {
+            const int b = sum - a;
+            for (int kb = 0; kb < kb_per_seg; ++kb, ++it) {
+              const int stage = it % COV2_STAGES;
+              const uint32_t phase = (uint32_t)(it / COV2_STAGES) & 1u;
+              mbar_wait_trap(empty + stage, phase ^ 1u);
+              uint8_t* dst = smem + stage * COV2_STAGE_BYTES;
+              if (leader) mbar_expect_tx(full + stage, 2 * COV2_STAGE_BYTES); /* the bytes of both CTAs */
+              const uint32_t lbar = mapa_u32(smem_u32(full + stage), 0);
+              tma_load_2d_pair(dst, &zmap, a * L + kb * COV_BK, row_a, lbar);
+              tma_load_2d_pair(dst + COV_A_BYTES, &zmap, b * L + kb * COV_BK, row_b, lbar);
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int it = 0, n = 0;
+      for (int64_t t = pair; t < tiles; t += npairs, ++n) {
+        const int buf = n & 1;
+        mbar_wait_trap(tempty + buf, ((uint32_t)(n >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t acc = tmem + (uint32_t)(buf * COV_BN);
+        for (int i = 0; i < iters; ++i, ++it) {
+          const int stage = it % COV2_STAGES;
+          const uint32_t phase = (uint32_t)(it / COV2_STAGES) & 1u;
+          mbar_wait_trap(full + stage, phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + stage * COV2_STAGE_BYTES), b0 = a0 + COV_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < COV_BK / COV_UMMA_K; ++k)
+            tc_mma_bf16_pair(acc, smem_desc_sw128(a0 + k * COV_UMMA_K * 2), smem_desc_sw128(b0 + k * COV_UMMA_K * 2), COV2_IDESC, (uint32_t)((i | k) != 0));
+          tc_commit_pair(empty + stage);
+        }
+        tc_commit_pair(tfull + buf);
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    double* tp = (double*)(epi + (warp - 2) * COV_EPI_BYTES);
+    double* sdw = tp + 33 * 32;
+    int n = 0;
+    for (int64_t t = pair; t < tiles; t += npairs, ++n) {
+      int64_t nb = (int64_t)((sqrt(8.0 * (double)t + 1.0) - 1.0) * 0.5);
+      while (nb * (nb + 1) / 2 > t) --nb;
+      while ((nb + 1) * (nb + 2) / 2 <= t) ++nb;
+      const int64_t mb = t - nb * (nb + 1) / 2;
+      const int64_t row_a = mb * 256 + (int64_t)rank * 128, row_b = nb * 256;
+      const int64_t gi = row_a + row, gi0 = row_a + q * 32;
+      const double si = gi < C ? sd[gi] : 0.0;
+      const bool diag_tile = mb == nb;
+      const bool edge = diag_tile || row_a + COV_BM > C || row_b + COV_BN > C;
+      const int buf = n & 1;
+      mbar_wait_trap(tfull + buf, (uint32_t)(n >> 1) & 1u);
+      tc_fence_after();
+      for (int c0 = half * (COV_BN / 2); c0 < (half + 1) * (COV_BN / 2); c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * COV_BN + c0), v);
+        if (c0 + 32 == (half + 1) * (COV_BN / 2)) {
+          tc_fence_before();
+          if (lane == 0) {
+            const uint32_t lb = mapa_u32(smem_u32(tempty + buf), 0);
+            asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(lb) : "memory");
+          }
+        }
+        const int64_t gj0 = row_b + c0;
+        sdw[lane] = gj0 + lane < C ? sd[gj0 + lane] : 0.0;
+        __syncwarp();
+        if (!edge) {
+          double* dp = R + gi + C * gj0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const double val = (double)__uint_as_float(v[j]) * (si * sdw[j]);
+            tp[j * 33 + lane] = val;
+            __stcs(dp, val);
+            dp += C;
+          }
+          __syncwarp();
+          double* mp = R + gj0 + lane + C * gi0;
+#pragma unroll
+          for (int ii = 0; ii < 32; ++ii) {
+            __stcs(mp, tp[lane * 33 + ii]);
+            mp += C;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t gj = gj0 + j;
+            const double val = gi == gj ? si * si : (double)__uint_as_float(v[j]) * (si * sdw[j]);
+            tp[j * 33 + lane] = val;
+            if (gi < C && gj < C && !(diag_tile && gj < gi)) __stcs(R + gi + C * gj, val);
+          }
+          __syncwarp();
+          const int64_t gj = gj0 + lane;
+          if (gj < C) {
+#pragma unroll 8
+            for (int ii = 0; ii < 32; ++ii) {
+              const int64_t gr = gi0 + ii;
+              if (gr >= C) break;
+              if (diag_tile ? gj > gr : true) __stcs(R + gj + C * gr, tp[lane * 33 + ii]);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all(); /* the leader's MMAs write the peer's TMEM and barriers: nobody leaves before everybody is done */
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(COV_TMEM_COLS) : "memory");
+  }
+}
+
 /* ---- k_mean_corrs: src/mmcollapse.cpp:483-511 ---- */
 __global__ void __launch_bounds__(256) k_mean_corrs(const double* __restrict__ R, const uint8_t* __restrict__ S, int64_t C, int ns,
                                                     const int32_t* __restrict__ ts, int64_t nts, double sdpenalty, double* __restrict__ V,
@@ -440,6 +668,23 @@ int cov_run(const double* src_dev, const int64_t* off_dev, int64_t off_step, int
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (cr != CUDA_SUCCESS) return cov_fail(MMQ_ERR_CUDA, "mmq_trace_cov: cuTensorMapEncodeTiled failed (" + std::to_string((int)cr) + ")");
   const int64_t T = (C + COV_BN - 1) / COV_BN;
+  const char* pair_env = getenv("MMQ_COV_PAIR"); /* 0: the single-CTA kernel (k_cov_gemm); default: CTA pairs (k_cov_gemm2) */
+  const int use_pair = pair_env ? atoi(pair_env) : 1;
+  if (use_pair) {
+    static std::once_flag attr2_once;
+    static cudaError_t attr2_err = cudaSuccess;
+    std::call_once(attr2_once, [] { attr2_err = cudaFuncSetAttribute(k_cov_gemm2, cudaFuncAttributeMaxDynamicSharedMemorySize, COV2_SMEM); });
+    if (attr2_err != cudaSuccess) return cov_fail(MMQ_ERR_CUDA, std::string("mmq_trace_cov: shared-memory attribute: ") + cudaGetErrorString(attr2_err));
+    const int64_t tiles2 = T * (T + 1) / 2; /* 256 x 256 tiles of the upper triangle, one per CTA pair */
+    int dev2 = 0, sms2 = 148;
+    COV_CUDA(cudaGetDevice(&dev2));
+    COV_CUDA(cudaDeviceGetAttribute(&sms2, cudaDevAttrMultiProcessorCount, dev2));
+    const int64_t pairs = std::max<int64_t>(1, std::min<int64_t>(tiles2, sms2 / 2));
+    k_cov_gemm2<<<(unsigned)(2 * pairs), COV_THREADS, COV2_SMEM, st>>>(map, sd, R_dev, C, L, nsplit, tiles2);
+    g_mmq_launches.fetch_add(1, std::memory_order_relaxed);
+    COV_CUDA(cudaGetLastError());
+    return MMQ_OK;
+  }
   const int64_t tiles = T * (T + 1);
   int dev = 0, sms = 148;
   COV_CUDA(cudaGetDevice(&dev));
