@@ -584,7 +584,7 @@ def extra_trace_cov(args, dev, stream):
     Rh = capi.trace_cov(Mhost, nsplit=nsplit, device=dev.index)
     e2e_s = time.perf_counter() - t0
     return {"workload": f"cov() of a {L} x {C} trace matrix (src/mmcollapse.cpp:553-558), split-bf16 x {nsplit} products, fp32 accumulation, fp64 output",
-            "kernel": "k_cov_gemm (tcgen05.mma + TMA + TMEM, persistent, 128 x 256 tiles of the upper triangle) + k_cov_prep",
+            "kernel": "k_cov_gemm2 (tcgen05.mma.cta_group::2 on CTA pairs + 2-CTA TMA + TMEM, persistent, 256 x 256 tiles of the upper triangle per pair) + k_cov_prep",
             "ms": ms, "matrices_per_s": 1e3 / ms, "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tpeak, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / tpeak, "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops, burst)" if peaks else "fallback",
