@@ -36,11 +36,13 @@
  *                of both operands (UTMALDG.2D.2CTA, both signalling the leader's mbarrier), tcgen05.commit multicast to both
  *                CTAs (UTCBAR.2CTA.MULTICAST), accumulators handed back by the epilogue warps of both CTAs (remote mbarrier
  *                arrive): 8 KB of operand reads per MMA and SM instead of 12, 32 KB of TMA writes per stage instead of 48.
- *                0.91-0.93 ms at C = 16384, nsplit = 2 (0.55 of the measured peak; 0.66 with nsplit = 3): each further split
- *                product now costs 0.18 ms = 1.5 PFLOP/s, what is left is the epilogue (0.57 ms for the 2.1 GB of fp64 output
- *                with one product), which does not hide behind the MMAs of the next tile as it should — ncu's top stall there
- *                is the FP64 pipe (math-pipe throttle on the r * sd_i * sd_j products), but an integer-only conversion
- *                (split scale, exponent arithmetic) measured the same, so the store path itself is the suspect.
+ *                0.91-0.93 ms at C = 16384, nsplit = 2 (0.54 of the measured peak; 0.66 with nsplit = 3).  Taken apart with
+ *                the stores and / or the MMAs switched off (same pipeline otherwise): neither 0.45 ms, stores only 0.78,
+ *                MMAs only 0.76, both 0.93-0.96.  The floor is the operand traffic: 6.4 GB of tiles from the L2-resident Z
+ *                per launch at the L2's ~12 TB/s (131 flop per byte for a 256 x 256 pair tile caps the MMAs at 1.5 PFLOP/s,
+ *                which is what each further split product costs: 0.18 ms), plus the epilogue's own work (TMEM loads, the
+ *                fp64 scaling, the transposition: ~0.25 ms) and the 2.1 GB of stores.  Next: clusters of two pairs with the
+ *                shared operand multicast (halves its L2 traffic), the epilogue's scaling in fp32 mantissa arithmetic.
  */
 #include <cuda.h>
 #include <cuda_bf16.h>
