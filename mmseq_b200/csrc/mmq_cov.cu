@@ -41,8 +41,9 @@
  *                MMAs only 0.76, both 0.93-0.96.  The floor is the operand traffic: 6.4 GB of tiles from the L2-resident Z
  *                per launch at the L2's ~12 TB/s (131 flop per byte for a 256 x 256 pair tile caps the MMAs at 1.5 PFLOP/s,
  *                which is what each further split product costs: 0.18 ms), plus the epilogue's own work (TMEM loads, the
- *                fp64 scaling, the transposition: ~0.25 ms) and the 2.1 GB of stores.  Next: clusters of two pairs with the
- *                shared operand multicast (halves its L2 traffic), the epilogue's scaling in fp32 mantissa arithmetic.
+ *                fp64 scaling, the transposition: ~0.25 ms) and the 2.1 GB of stores.  Both split terms of a K block in one
+ *                stage (every operand tile loaded once: 1.5x less L2 traffic, but only two stages fit) measured 0.90 against
+ *                0.94 ms: not kept.  Next: clusters of two pairs with the shared operand multicast.
  */
 #include <cuda.h>
 #include <cuda_bf16.h>
