@@ -120,3 +120,31 @@ def test_config5_eight_handles_per_gpu_on_every_gpu_from_threads():
         O = orc.summaries_transcripts(tr_o, (5, 50, 95))
         assert np.allclose(S["log_mean"], O["log_mu"], rtol=1e-12, atol=1e-12)
         assert np.allclose(S["tau"], O["iact"], rtol=1e-8, atol=1e-10, equal_nan=True)
+
+
+def test_block_cache_recycles_memory_without_changing_results(small_problem):
+    """mmq_destroy gives its device blocks to the per-device cache and the next mmq_create takes them back zeroed: the chain of a
+    handle does not depend on what ran before it in the process; mmq_release_cache returns the memory to the driver."""
+    import torch
+    p = small_problem
+
+    def run(seed):
+        with capi.Handle(p.row_ptr, p.col, p.k, p.len) as H:
+            H.init_mu()
+            H.em(100, 0.1)
+            H.gibbs(seed, 0, 48, stride=4, trace_len=12)
+            return H.get_trace().copy(), H.get_mu().copy()
+
+    first = run(11)
+    # something else in between leaves other data in the recycled blocks
+    rng = np.random.default_rng(0)
+    capi.trace_cov(np.exp(rng.normal(0, 1, (256, 300))), nsplit=2)
+    run(12)
+    again = run(11)
+    assert np.array_equal(first[0], again[0]) and np.array_equal(first[1], again[1])
+    free0, _ = torch.cuda.mem_get_info()
+    assert capi.release_cache() == 0
+    free1, _ = torch.cuda.mem_get_info()
+    assert free1 >= free0
+    third = run(11)
+    assert np.array_equal(first[0], third[0])
