@@ -66,6 +66,44 @@ __device__ __forceinline__ uint32_t cls_word1(uint32_t cid, uint32_t cid_hi, uin
 /* One chunk: 32 slots of compile-time class size D, everything in registers.  A slot is a class
  * with its first block b0 and the number of draws kq <= 64 it makes (classes with more than 64
  * fragments occupy several slots). */
+/* plan streams are read once per sweep and are as large as the L2: ask the L2 to evict them first, so that mu and counts stay
+ * (measured on the config-2 shard: 8900 -> 9100 sweeps/s) */
+__device__ __forceinline__ uint32_t ld_plan_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "ld.global.nc.L2::cache_hint.u32 %0, [%1], pol;\n\t"
+      "}\n"
+      : "=r"(v)
+      : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_plan_u16(const uint16_t* p) {
+  uint16_t v;
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "ld.global.nc.L2::cache_hint.u16 %0, [%1], pol;\n\t"
+      "}\n"
+      : "=h"(v)
+      : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int32_t ld_plan(const int32_t* p) {
+  int32_t v;
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "ld.global.nc.L2::cache_hint.s32 %0, [%1], pol;\n\t"
+      "}\n"
+      : "=r"(v)
+      : "l"(p));
+  return v;
+}
 template <int D>
 __device__ __forceinline__ void cls_chunk(const int32_t* __restrict__ pc, int kq, uint32_t b0, uint32_t cid, uint32_t cid_hi,
                                           const double* __restrict__ mu, int32_t* __restrict__ counts, uint32_t seed,
@@ -74,7 +112,7 @@ __device__ __forceinline__ void cls_chunk(const int32_t* __restrict__ pc, int kq
    * which leaves the registers to the running sums and buys resident warps */
   double S[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) S[j] = mu[__ldg(pc + 32 * j)];
+  for (int j = 0; j < D; ++j) S[j] = mu[ld_plan(pc + 32 * j)];
 #pragma unroll
   for (int j = 1; j < D; ++j) S[j] = S[j - 1] + S[j];
   const double norm = S[D - 1];
@@ -173,8 +211,8 @@ k_alloc_cls(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, co
   uint32_t meta_n = 0, cid_n = 0;
   unsigned long long desc_n = 0ull;
   if (i < count) {
-    meta_n = pk[(int64_t)chunk_of(i) * 32 + lane];
-    cid_n = pcid[(int64_t)chunk_of(i) * 32 + lane];
+    meta_n = ld_plan_u16(pk + (int64_t)chunk_of(i) * 32 + lane);
+    cid_n = ld_plan_u32(pcid + (int64_t)chunk_of(i) * 32 + lane);
     desc_n = cdesc[chunk_of(i)];
   }
   for (; i < count; i += nwarps) {
@@ -183,8 +221,8 @@ k_alloc_cls(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, co
     const uint32_t meta = meta_n; /* draws of the slot | slot number within its class << 8 */
     const uint32_t cid = cid_n;
     if (i + nwarps < count) {
-      meta_n = pk[(int64_t)chunk_of(i + nwarps) * 32 + lane];
-      cid_n = pcid[(int64_t)chunk_of(i + nwarps) * 32 + lane];
+      meta_n = ld_plan_u16(pk + (int64_t)chunk_of(i + nwarps) * 32 + lane);
+      cid_n = ld_plan_u32(pcid + (int64_t)chunk_of(i + nwarps) * 32 + lane);
       desc_n = cdesc[chunk_of(i + nwarps)];
     }
     const int kq = (int)(meta & 0xffu);
@@ -216,7 +254,7 @@ __device__ __forceinline__ void cls1_chunk(const int32_t* __restrict__ pc, bool 
                                            int32_t* __restrict__ counts, uint32_t seed, uint32_t sweep, int lane) {
   double S[D];
 #pragma unroll
-  for (int j = 0; j < D; ++j) S[j] = mu[__ldg(pc + 32 * j)];
+  for (int j = 0; j < D; ++j) S[j] = mu[ld_plan(pc + 32 * j)];
   const uint32_t word = cls_word1(cid, cid_hi, sweep, seed); /* independent of the loads in flight */
 #pragma unroll
   for (int j = 1; j < D; ++j) S[j] = S[j - 1] + S[j];
@@ -254,8 +292,8 @@ k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, c
   uint32_t meta_n = 0, cid_n = 0;
   unsigned long long desc_n = 0ull;
   if (i < count) {
-    meta_n = pk[(int64_t)chunk_of(i) * 32 + lane];
-    cid_n = pcid[(int64_t)chunk_of(i) * 32 + lane];
+    meta_n = ld_plan_u16(pk + (int64_t)chunk_of(i) * 32 + lane);
+    cid_n = ld_plan_u32(pcid + (int64_t)chunk_of(i) * 32 + lane);
     desc_n = cdesc[chunk_of(i)];
   }
   for (; i < count; i += nwarps) {
@@ -264,8 +302,8 @@ k_alloc_cls1(int chunk_begin, int chunk_end, const int32_t* __restrict__ pcol, c
     const bool live = (meta_n & 0xffu) != 0u; /* padding lanes make no draw */
     const uint32_t cid = cid_n;
     if (i + nwarps < count) { /* metadata one chunk ahead: its latency is off the critical path */
-      meta_n = pk[(int64_t)chunk_of(i + nwarps) * 32 + lane];
-      cid_n = pcid[(int64_t)chunk_of(i + nwarps) * 32 + lane];
+      meta_n = ld_plan_u16(pk + (int64_t)chunk_of(i + nwarps) * 32 + lane);
+      cid_n = ld_plan_u32(pcid + (int64_t)chunk_of(i + nwarps) * 32 + lane);
       desc_n = cdesc[chunk_of(i + nwarps)];
     }
 #define MMQ_CLS1_CASE(DD) case DD: cls1_chunk<DD>(pc, live, cid, cid_hi, mu, counts, seed, sweep, lane); break;
@@ -340,7 +378,7 @@ k_alloc_chain(int chunks, const int32_t* __restrict__ pcol, const int32_t* __res
     if (owner_warp) {
       S.cid[tid] = cid;
       S.cnt[0][tid] = kv;
-      for (int j = 0; j < D; ++j) S.p[j][tid] = mu[__ldg(pc + 32 * j)];
+      for (int j = 0; j < D; ++j) S.p[j][tid] = mu[ld_plan(pc + 32 * j)];
     }
     __syncthreads();
     {
