@@ -137,7 +137,9 @@ def make_workload(args, rank, world, weights=None, layout=None):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons of one GPU, sampled while the timed region runs."""
+    """SM clock and throttle reasons of one GPU, sampled while the timed region runs.  NVML is brought up in the constructor
+    (before the region: its initialisation takes longer than the 36 ms a default run is timed for) and a last sample is
+    taken when the region ends, so that there is always at least one."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -147,33 +149,47 @@ class ClockSampler(threading.Thread):
         self.reasons = set()
         self.max_mhz = None
         self.ok = False
-
-    def run(self):
         try:
             import pynvml as nv
             nv.nvmlInit()
-            dev = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(dev, nv.NVML_CLOCK_SM)
-            names = {
+            self.nv = nv
+            self.dev = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.dev, nv.NVML_CLOCK_SM)
+            self.names = {
                 getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
                 getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
                 getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
                 getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
             }
-            get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
             self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+
+    def sample(self):
+        self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.dev, self.nv.NVML_CLOCK_SM))
+        r = self.get(self.dev)
+        for bit, nm in self.names.items():
+            if r & bit:
+                self.reasons.add(nm)
+
+    def run(self):
+        if not self.ok:
+            return
+        try:
             while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(dev, nv.NVML_CLOCK_SM))
-                r = get(dev)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.005)
+                self.sample()
+                time.sleep(0.004)
         except Exception as e:  # pragma: no cover
             self.err = repr(e)
 
     def result(self):
+        if self.ok:
+            try:
+                self.sample()   # the region has just ended: the clocks are still those it ran at
+            except Exception:  # pragma: no cover
+                pass
         if not self.ok or not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
