@@ -41,6 +41,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(b))
                : "memory");
 }
+/* the same with an L2 evict-first policy: for streams that are read once per sweep and are larger than the L2 */
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b64 pol;\n\t"
+      "createpolicy.fractional.L2::evict_first.b64 pol, 1.0;\n\t"
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], pol;\n\t"
+      "}\n" ::"r"(smem_u32(dst)),
+      "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(smem_u32(b))
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
   uint32_t ok;
   do {

@@ -281,8 +281,8 @@ k_alloc_seg4(const mmq_seg* __restrict__ segs, int nsegs, int total_chunks, int 
     const int64_t e = s_seg[s].e_virtual + (int64_t)(ch - s_seg[s].chunk0) * (MMQ_SEG4_ROWS * d);
     const uint32_t bytes = (uint32_t)(MMQ_SEG4_ROWS * 4 * d); /* 512*d: a multiple of 16; the packed array has slack */
     mbar_expect_tx(bar, HAS_W ? 2 * bytes : bytes);
-    bulk_g2s(sc, colp + e, bytes, bar);
-    if (HAS_W) bulk_g2s(sw, wp + e, bytes, bar);
+    bulk_g2s_stream(sc, colp + e, bytes, bar);
+    if (HAS_W) bulk_g2s_stream(sw, wp + e, bytes, bar);
   };
   int si = 0;
   while (si + 1 < nsegs && chunk >= s_seg[si + 1].chunk0) ++si;
