@@ -168,11 +168,14 @@ def test_schema2_weighted_hits_round_trip(tmp_path):
         hostlib.load_hits(p)                                        # the collapsed layout cannot carry weights
 
 
-def test_truncated_and_degenerate_files_are_refused(tmp_path):
-    """ADVICE (round 1): a zlib stream cut short, a binary record cut mid-way, a record without transcripts and a hit
+@pytest.mark.parametrize("parallel", [False, True])
+def test_truncated_and_degenerate_files_are_refused(tmp_path, monkeypatch, parallel):
+    """(parallel: the all-threads loader path, which small files do not take by default.)  ADVICE (round 1): a zlib stream cut short, a binary record cut mid-way, a record without transcripts and a hit
     count above the number of transcripts are errors, not silently shorter samples."""
     import struct
     import zlib
+    if parallel:
+        monkeypatch.setenv("MMQ_LOADER_PAR_MIN_BYTES", "0")
     s = synth.Synth(5, 80, 2000)
     p = str(tmp_path / "ok.hits")
     synth.write_hits_binary(s, p)
