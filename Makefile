@@ -29,10 +29,10 @@ $(LIB): build/mmq_core.o build/mmq_post.o build/mmq_seg.o build/mmq_cls.o build/
 $(SYNTH): $(CSRC)/mmq_synth.cpp
 	$(HOST_CXX) -O3 -std=c++17 -fPIC -fopenmp -shared -o $@ $< -lz
 
-$(HOSTLIB): $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h $(CSRC)/inflate_par.h $(CSRC)/fmt_g6.h $(CSRC)/huff_gz.h $(CSRC)/mmq_cls_plan.h include/mmq_sampler.h
+$(HOSTLIB): $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h $(CSRC)/inflate_par.h $(CSRC)/fmt_g6.h $(CSRC)/huff_gz.h $(CSRC)/trace_writer.h $(CSRC)/mmq_cls_plan.h include/mmq_sampler.h
 	$(HOST_CXX) -O3 -std=c++17 -fPIC -ffp-contract=off -pthread -shared -o $@ $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp -lz
 
-$(CLI): $(CSRC)/mmseq_main.cpp $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h $(CSRC)/inflate_par.h $(CSRC)/fmt_g6.h $(CSRC)/huff_gz.h include/mmq.h $(LIB)
+$(CLI): $(CSRC)/mmseq_main.cpp $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp $(CSRC)/hits_loader.h $(CSRC)/inflate_par.h $(CSRC)/fmt_g6.h $(CSRC)/huff_gz.h $(CSRC)/trace_writer.h include/mmq.h $(LIB)
 	@mkdir -p mmseq_b200/bin
 	$(HOST_CXX) -O2 -std=c++17 -ffp-contract=off -pthread -Iinclude -DVERSION=1.0.11-b200 -o $@ $(CSRC)/mmseq_main.cpp $(CSRC)/hits_loader.cpp $(CSRC)/host_special.cpp -Lmmseq_b200 -lmmseq_b200 -lz -Wl,-rpath,'$$ORIGIN/..'
 

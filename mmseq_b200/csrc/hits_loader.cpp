@@ -5,6 +5,7 @@
 #include "inflate_par.h"
 #include "fmt_g6.h"
 #include "huff_gz.h"
+#include "trace_writer.h"
 
 #include <zlib.h>
 
@@ -1304,6 +1305,20 @@ int64_t mmqh_fmt_g6(const double* v, int64_t n, char* out) {
   char* p = out;
   for (int64_t i = 0; i < n; ++i) { p = fmt_g6(p, v[i]); *p++ = ' '; }
   return (int64_t)(p - out);
+}
+
+/* test support: trace_writer.h — ids separated by '\n' in one string, keep (may be NULL) one flag per feature; 0 on success */
+int mmqh_write_trace_gz(const char* path, const char* ids_nl, int64_t nfeat, const uint8_t* keep, const double* tr, int L) {
+  std::vector<std::string> ids;
+  const char* p = ids_nl;
+  for (int64_t i = 0; i < nfeat; ++i) {
+    const char* e = strchr(p, '\n');
+    ids.emplace_back(p, e ? (size_t)(e - p) : strlen(p));
+    p = e ? e + 1 : p + strlen(p);
+  }
+  std::vector<char> kp;
+  if (keep) kp.assign(keep, keep + nfeat);
+  return mmq::write_trace_gz(path, ids, kp, tr, L).empty() ? 0 : 1;
 }
 
 /* test support: huff_gz.h, one gzip member for the n bytes; returns its size (out must hold n + 1024 bytes) */

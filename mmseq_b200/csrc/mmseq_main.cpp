@@ -37,6 +37,7 @@
 #include "../../include/mmq.h"
 #include "fmt_g6.h"
 #include "huff_gz.h"
+#include "trace_writer.h"
 #include "hits_loader.h"
 
 #define QUOTE_(x) #x
@@ -108,86 +109,10 @@ struct GzText {
   ~GzText() { flush(); if (f) gzclose(f); }
 };
 
-/* "%g" text of one trace line range -> one complete gzip member.  A gzip file is a sequence of
- * members (RFC 1952 2.2); zlib's gzread, gzip(1), R's gzfile and Boost's gzip_decompressor all
- * read the concatenation as one stream, so the members can be produced in parallel. */
-static void gz_member(const string& text, vector<unsigned char>& out) {
-  /* The text is digits of continuous random values: string matching finds next to nothing in it, the gain is all in the
-   * entropy coding (zlib on trace-like text: Z_HUFFMAN_ONLY 1.5x faster than level 1 with matching AND 9 % smaller, ratio
-   * 2.22 against 2.04; level 6: 2.24 at an eighth of the speed).  Default: huff_gz.h, the same Huffman-only coding without
-   * zlib's per-symbol overhead.  The decompressed bytes are the reference's either way; MMQ_GZIP_LEVEL=6 gives zlib at the
-   * reference's settings back. */
-  static const int level = [] { const char* e = getenv("MMQ_GZIP_LEVEL"); return e ? atoi(e) : 0; }();
-  out.clear();
-  if (level <= 0) { mmq::hgz::gz_member(text.data(), text.size(), out); return; }
-  z_stream zs;
-  memset(&zs, 0, sizeof zs);
-  if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16, 8, Z_DEFAULT_STRATEGY) != Z_OK) die("Error: deflateInit2 failed.");
-  out.resize(deflateBound(&zs, (uLong)text.size()) + 64);
-  zs.next_in = (Bytef*)text.data();
-  zs.avail_in = (uInt)text.size();
-  zs.next_out = out.data();
-  zs.avail_out = (uInt)out.size();
-  if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die("Error: deflate failed.");
-  out.resize(zs.total_out);
-  deflateEnd(&zs);
-}
-
-/* one (rows x L) trace as the reference writes it (src/mmseq.cpp:1033-1108): ids each followed by a
- * space, then L lines of values.  Formatting and compression run on all host threads, a block of
- * lines per thread and round; the members are written in order. */
+/* the *.trace_gibbs.gz writer lives in trace_writer.h (shared with the test-support library) */
 static void write_trace_gz(const string& path, const vector<string>& ids, const vector<char>& keep, const double* tr, int L) {
-  FILE* f = fopen(path.c_str(), "wb");
-  if (!f) die("Error: cannot open " + path + " for writing.");
-  vector<size_t> rows;
-  for (size_t r = 0; r < ids.size(); ++r)
-    if (keep.empty() || keep[r]) rows.push_back(r);
-  {
-    string head;
-    for (size_t r : rows) { head += ids[r]; head += ' '; }
-    head += '\n';
-    vector<unsigned char> z;
-    gz_member(head, z);
-    fwrite(z.data(), 1, z.size(), f);
-  }
-  const int T = (int)std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-  /* lines per block: every thread gets one, at most about 32 MB of text each, at least one line */
-  const int B = (int)std::max<size_t>(1, std::min<size_t>((size_t)(L + T - 1) / (size_t)T, (32u << 20) / (rows.size() * 12 + 1)));
-  vector<vector<unsigned char>> z((size_t)T);
-  for (int base = 0; base < L; base += T * B) {
-    vector<std::thread> th;
-    for (int t = 0; t < T; ++t) {
-      const int i0 = base + t * B, i1 = std::min(L, i0 + B);
-      z[(size_t)t].clear();
-      if (i0 >= i1) continue;
-      th.emplace_back([&, t, i0, i1] {
-        /* the trace is feature-major (tr[r * L + i]): walk it row by row, appending to the block's lines side by side, so
-         * that every cache line of the trace is read once */
-        const int nl = i1 - i0;
-        vector<string> line((size_t)nl);
-        for (auto& s : line) s.reserve(rows.size() * 12 + 2);
-        char tmp[40];
-        for (size_t r : rows) {
-          const double* v = tr + r * (size_t)L + (size_t)i0;
-          for (int j = 0; j < nl; ++j) {
-            char* e = fmt_g(tmp, v[j]);
-            *e++ = ' ';
-            line[(size_t)j].append(tmp, (size_t)(e - tmp));
-          }
-        }
-        string text;
-        size_t total = 0;
-        for (auto& s : line) total += s.size() + 1;
-        text.reserve(total);
-        for (auto& s : line) { text += s; text += '\n'; string().swap(s); }
-        gz_member(text, z[(size_t)t]);
-      });
-    }
-    for (auto& x : th) x.join();
-    for (int t = 0; t < T; ++t)
-      if (!z[(size_t)t].empty()) fwrite(z[(size_t)t].data(), 1, z[(size_t)t].size(), f);
-  }
-  if (fclose(f) != 0) die("Error: cannot write " + path + ".");
+  const string err = mmq::write_trace_gz(path, ids, keep, tr, L);
+  if (!err.empty()) die(err);
 }
 
 static void write_pcts(ostream& ofs, const double* v, size_t np, char last) {

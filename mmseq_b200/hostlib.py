@@ -30,6 +30,8 @@ def lib():
         L.mmqh_load.argtypes = [C.c_char_p, i32, C.c_char_p, i32]
         L.mmqh_from_records.restype = vp
         L.mmqh_from_records.argtypes = [i64, vp, i64, vp, vp, vp, i32, C.c_char_p, i32]
+        L.mmqh_write_trace_gz.restype = i32
+        L.mmqh_write_trace_gz.argtypes = [C.c_char_p, C.c_char_p, i64, vp, vp, i32]
         L.mmqh_gz_huffman.restype = i64
         L.mmqh_gz_huffman.argtypes = [vp, i64, vp]
         L.mmqh_fmt_g6.restype = i64
@@ -90,6 +92,16 @@ class Hits:
             self.ident_ptr = _arr(L.mmqh_ident_ptr(handle), self.I + 1, np.int64)
             self.ident_members = _arr(L.mmqh_ident_members(handle), int(self.ident_ptr[-1]), np.int32)
         L.mmqh_free(handle)
+
+
+def write_trace_gz(path, ids, trace, keep=None):
+    """trace_writer.h (the host program's *.trace_gibbs.gz writer): trace[feature, slot]."""
+    tr = np.ascontiguousarray(trace, np.float64)
+    kp = None if keep is None else np.ascontiguousarray(keep, np.uint8)
+    rc = lib().mmqh_write_trace_gz(os.fsencode(path), "\n".join(ids).encode(), len(ids), None if kp is None else kp.ctypes.data_as(C.c_void_p),
+                                   tr.ctypes.data_as(C.c_void_p), tr.shape[1])
+    if rc:
+        raise RuntimeError(f"cannot write {path}")
 
 
 def gz_huffman(data):

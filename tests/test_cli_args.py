@@ -94,3 +94,34 @@ def test_huffman_only_gzip_members_decode_with_zlib():
     assert gzip.GzipFile(fileobj=io.BytesIO(whole)).read() == b"".join(texts)
     digits = texts[4]
     assert len(hostlib.gz_huffman(digits)) < 1.02 * len(zlib.compress(digits, 1)) / 1.05   # at least zlib level 1's ratio on digit text
+
+
+def test_trace_file_writer_round_trip(tmp_path, monkeypatch):
+    """trace_writer.h: ids line, one line per slot, "%g" of every kept feature (src/mmseq.cpp:1033-1108), through the built-in
+    Huffman-only members and through zlib (MMQ_GZIP_LEVEL): the decompressed text is the same."""
+    import gzip
+    import numpy as np
+    from mmseq_b200 import hostlib
+    rng = np.random.default_rng(4)
+    n, L = 3000, 64
+    tr = np.exp(rng.normal(0, 3, (n, L)))
+    tr[5, :] = 0.0
+    tr[6, 3] = np.inf
+    ids = [f"T{i}" for i in range(n)]
+    keep = (rng.random(n) < 0.9).astype(np.uint8)
+    texts = []
+    monkeypatch.setenv("MMQ_TRACE_BLOCK_BYTES", str(2 * 12 * n))       # two lines per thread and round: several rounds, the writer thread overlaps
+    for level in (None, "6"):
+        if level:
+            monkeypatch.setenv("MMQ_GZIP_LEVEL", level)
+        for kp in (None, keep):
+            path = str(tmp_path / f"t{level}{kp is None}.gz")
+            hostlib.write_trace_gz(path, ids, tr, kp)
+            lines = gzip.open(path, "rt").read().split("\n")
+            sel = np.arange(n) if kp is None else np.flatnonzero(kp)
+            assert lines[0].split() == [ids[i] for i in sel] and lines[0].endswith(" ")
+            assert len(lines) == L + 2 and lines[-1] == ""
+            for i in (0, 1, L // 2, L - 1):
+                assert lines[1 + i].split() == ["%g" % v for v in tr[sel, i]]
+            texts.append((kp is None, "\n".join(lines)))
+    assert texts[0][1] == texts[2][1] and texts[1][1] == texts[3][1]
